@@ -1,0 +1,51 @@
+"""Builds libdigilogic_b200.so in-tree with nvcc for sm_100a (no JIT cache: the built
+library travels with the repo snapshot to the GPU box)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libdigilogic_b200.so")
+SOURCES = ["engine.cu", "netlist.cpp", "capi.cpp"]
+HEADERS = ["engine.hpp", "netlist.hpp", os.path.join("..", "..", "include", "digilogic_b200.h")]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the engine is CUDA-only and cannot be built without it")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [
+        _nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+        "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-o", LIB_PATH,
+    ] + [os.path.join(CSRC, f) for f in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force=True, verbose="-v" in sys.argv))

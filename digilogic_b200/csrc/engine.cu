@@ -1,0 +1,1144 @@
+// engine.cu — sm_100a kernels and the settle loops.
+//
+// Wire-state store: one row per 1-bit net, `stride` 64-lane words per row, value and valid in
+// separate planes, resident in HBM.  A thread owns one 128-bit pair of lane-words of a row; a
+// warp therefore reads each fan-in row as one contiguous 512-byte segment (coalesced,
+// LDG.128) and the gate function is a handful of LOP3s: this path is HBM/gather bound, there
+// is no contraction for the tensor cores to do.
+//
+// Semantics: with W the wire states and D the external drives, one gsim
+// step is W' = G(W), W'[w] = resolve(D[w], F_driver(w)(W)).  run_sim(max_steps) allows
+// applications k = 1..N+2 (N = max_steps+1; a cold start spends k = 1 on W_1 = D).  A lane is
+// Ok iff W_k == W_{k-1} for some k <= N+2, MaxStepsReached otherwise (state W_{N+1}); a driver
+// conflict while computing W_k, k <= N+1, is Err.  For an acyclic single-driver netlist with
+// max_steps >= depth the fixed point is unique and is computed level by level in one pass.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/digilogic_b200.h"
+#include "engine.hpp"
+
+namespace b2 {
+
+// ---------------------------------------------------------------------------- errors / counters
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+const char *get_last_error() { return g_last_error.c_str(); }
+uint64_t kernel_launches() { return g_launches.load(); }
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            set_last_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                       \
+            return e_ == cudaErrorMemoryAllocation ? B2_ERR_OUT_OF_MEMORY : B2_ERR_CUDA;             \
+        }                                                                                             \
+    } while (0)
+
+#define LAUNCHED()                                          \
+    do {                                                    \
+        g_launches.fetch_add(1, std::memory_order_relaxed); \
+        CU_TRY(cudaGetLastError());                         \
+    } while (0)
+
+#define ST ((cudaStream_t)stream_)
+
+// ---------------------------------------------------------------------------- device helpers
+
+__device__ __forceinline__ ulonglong2 ld_stream(const uint64_t *p) {
+    ulonglong2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_pair(uint64_t *p, ulonglong2 v) {
+    asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+
+// 4-state gate on one 64-lane word: k1 = known one, k0 = known zero.
+typedef unsigned long long u64;  // the element type of ulonglong2
+__device__ __forceinline__ void gate_word(uint32_t kind, u64 av, u64 am, u64 bv, u64 bm, u64 &rv, u64 &rm) {
+    u64 v, m;
+    switch (kind) {
+        case K_AND:
+        case K_NAND: {
+            const u64 k1 = (av & am) & (bv & bm), k0 = (~av & am) | (~bv & bm);
+            m = k0 | k1;
+            v = k1;
+        } break;
+        case K_OR:
+        case K_NOR: {
+            const u64 k1 = (av & am) | (bv & bm), k0 = (~av & am) & (~bv & bm);
+            m = k0 | k1;
+            v = k1;
+        } break;
+        case K_XOR:
+        case K_XNOR:
+            m = am & bm;
+            v = av ^ bv;
+            break;
+        default:  // K_NOT (single input)
+            m = am;
+            v = av;
+            break;
+    }
+    if (kind >= K_NAND) v = ~v;
+    rv = v | ~m;  // not-valid lanes carry the canonical X = (1,0)
+    rm = m;
+}
+
+__device__ __forceinline__ uint64_t lane_mask_of(uint32_t w, uint64_t n_lanes) {
+    const uint64_t lo = (uint64_t)w * 64;
+    if (lo + 64 <= n_lanes) return ~0ull;
+    if (lo >= n_lanes) return 0ull;
+    return (1ull << (n_lanes - lo)) - 1;
+}
+
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// ---------------------------------------------------------------------------- kernels
+//
+// Common thread mapping: blockDim = (BX, BY), BX * BY = 256.  threadIdx.x walks 128-bit pairs of
+// lane-words inside a row, threadIdx.y walks gates; the flat 1-D grid is decomposed as
+// (pair block fastest, gate block slowest) so that neighbouring CTAs stream neighbouring
+// pieces of the same fan-in rows.
+
+struct Eval2Args {
+    const uint32_t *fan0, *fan1;
+    const uint8_t *kind;
+    const uint64_t *in_val, *in_vld;  // rows read (A)
+    uint64_t *out_val, *out_vld;      // rows written (A in place for the levelised pass, B for unit delay)
+    uint64_t *changed;                // [stride] OR of (new ^ old) per lane-word; unit delay only
+    uint32_t g_begin, g_end;          // gate range; output row = row_base + gate
+    uint32_t row_base;
+    uint32_t stride;                  // words per row
+    uint32_t pairs;                   // stride / 2
+    uint32_t pair_blocks;
+};
+
+// One- and two-input gates.  U gates per thread keep 4*U independent 128-bit loads in flight.
+template <int U, bool JACOBI>
+__global__ void __launch_bounds__(256) k_eval2(const Eval2Args a) {
+    const uint32_t pb = blockIdx.x % a.pair_blocks, gb = blockIdx.x / a.pair_blocks;
+    const uint32_t pair = pb * blockDim.x + threadIdx.x;
+    if (pair >= a.pairs) return;
+    const size_t col = (size_t)pair * 2;
+    const uint32_t g0 = a.g_begin + gb * (blockDim.y * U) + threadIdx.y;
+
+    uint32_t kind[U];
+    ulonglong2 av[U], am[U], bv[U], bm[U], ov[U], om[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const uint32_t g = g0 + u * blockDim.y;
+        if (g < a.g_end) {
+            const uint32_t f0 = a.fan0[g], f1 = a.fan1[g];
+            kind[u] = a.kind[g];
+            av[u] = ld_stream(a.in_val + (size_t)f0 * a.stride + col);
+            am[u] = ld_stream(a.in_vld + (size_t)f0 * a.stride + col);
+            if (kind[u] != K_NOT) {
+                bv[u] = ld_stream(a.in_val + (size_t)f1 * a.stride + col);
+                bm[u] = ld_stream(a.in_vld + (size_t)f1 * a.stride + col);
+            } else {
+                bv[u] = av[u];
+                bm[u] = am[u];
+            }
+            if (JACOBI) {
+                const size_t o = (size_t)(a.row_base + g) * a.stride + col;
+                ov[u] = ld_stream(a.in_val + o);
+                om[u] = ld_stream(a.in_vld + o);
+            }
+        }
+    }
+    uint64_t dx = 0, dy = 0;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const uint32_t g = g0 + u * blockDim.y;
+        if (g < a.g_end) {
+            ulonglong2 rv, rm;
+            gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
+            gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
+            const size_t o = (size_t)(a.row_base + g) * a.stride + col;
+            st_pair(a.out_val + o, rv);
+            st_pair(a.out_vld + o, rm);
+            if (JACOBI) {
+                dx |= (rv.x ^ ov[u].x) | (rm.x ^ om[u].x);
+                dy |= (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
+            }
+        }
+    }
+    if (JACOBI) {
+        if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
+        if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
+    }
+}
+
+struct WideArgs {
+    const uint32_t *off, *in;
+    const uint8_t *kind, *nsel;
+    const uint64_t *in_val, *in_vld;
+    uint64_t *out_val, *out_vld;
+    uint64_t *changed;
+    uint32_t g_begin, g_end, row_base, stride, pairs, pair_blocks;
+};
+
+// n-ary gates (left fold, inverted kinds invert once at the end) and multiplexer slices.
+template <bool JACOBI>
+__global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
+    const uint32_t pb = blockIdx.x % a.pair_blocks, gb = blockIdx.x / a.pair_blocks;
+    const uint32_t pair = pb * blockDim.x + threadIdx.x;
+    const uint32_t g = a.g_begin + gb * blockDim.y + threadIdx.y;
+    if (pair >= a.pairs || g >= a.g_end) return;
+    const size_t col = (size_t)pair * 2;
+    const uint32_t b = a.off[g], e = a.off[g + 1];
+    const uint32_t kind = a.kind[g];
+    ulonglong2 rv, rm;
+    if (kind == K_MUX) {
+        const uint32_t ns = a.nsel[g];
+        ulonglong2 allv = make_ulonglong2(~0ull, ~0ull);
+        for (uint32_t s = 0; s < ns; s++) {
+            const ulonglong2 m = ld_stream(a.in_vld + (size_t)a.in[b + s] * a.stride + col);
+            allv.x &= m.x;
+            allv.y &= m.y;
+        }
+        ulonglong2 pv = make_ulonglong2(0, 0), pm = make_ulonglong2(0, 0);
+        for (uint32_t j = 0; b + ns + j < e; j++) {
+            ulonglong2 match = make_ulonglong2(~0ull, ~0ull);
+            for (uint32_t s = 0; s < ns; s++) {
+                const ulonglong2 sv = ld_stream(a.in_val + (size_t)a.in[b + s] * a.stride + col);
+                const uint64_t want = ((j >> s) & 1) ? ~0ull : 0ull;
+                match.x &= ~(sv.x ^ want);
+                match.y &= ~(sv.y ^ want);
+            }
+            const size_t r = (size_t)a.in[b + ns + j] * a.stride + col;
+            const ulonglong2 dv = ld_stream(a.in_val + r), dm = ld_stream(a.in_vld + r);
+            pv.x |= match.x & dv.x;
+            pv.y |= match.y & dv.y;
+            pm.x |= match.x & dm.x;
+            pm.y |= match.y & dm.y;
+        }
+        rm.x = allv.x & pm.x;
+        rm.y = allv.y & pm.y;
+        rv.x = (allv.x & pv.x) | ~rm.x;  // Z on the selected input reads X; invalid select -> X
+        rv.y = (allv.y & pv.y) | ~rm.y;
+    } else {
+        const uint32_t base = kind >= K_NAND ? kind - 3 : kind;  // fold with the positive op
+        size_t r = (size_t)a.in[b] * a.stride + col;
+        rv = ld_stream(a.in_val + r);
+        rm = ld_stream(a.in_vld + r);
+        for (uint32_t i = b + 1; i < e; i++) {
+            r = (size_t)a.in[i] * a.stride + col;
+            const ulonglong2 xv = ld_stream(a.in_val + r), xm = ld_stream(a.in_vld + r);
+            gate_word(base, rv.x, rm.x, xv.x, xm.x, rv.x, rm.x);
+            gate_word(base, rv.y, rm.y, xv.y, xm.y, rv.y, rm.y);
+        }
+        if (kind >= K_NAND) {
+            rv.x = ~rv.x | ~rm.x;
+            rv.y = ~rv.y | ~rm.y;
+        }
+    }
+    const size_t o = (size_t)(a.row_base + g) * a.stride + col;
+    if (JACOBI) {
+        const ulonglong2 ov = ld_stream(a.in_val + o), om = ld_stream(a.in_vld + o);
+        const uint64_t dx = (rv.x ^ ov.x) | (rm.x ^ om.x), dy = (rv.y ^ ov.y) | (rm.y ^ om.y);
+        if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
+        if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
+    }
+    st_pair(a.out_val + o, rv);
+    st_pair(a.out_vld + o, rm);
+}
+
+// Source rows take their external drive: out[row] = D[row] (rows [0, n_rows) of both stores).
+template <bool JACOBI>
+__global__ void __launch_bounds__(256) k_apply_drive(const uint64_t *dval, const uint64_t *dvld, const uint64_t *old_val,
+                                                     const uint64_t *old_vld, uint64_t *out_val, uint64_t *out_vld,
+                                                     uint64_t *changed, uint32_t n_rows, uint32_t stride, uint32_t pairs,
+                                                     uint32_t pair_blocks) {
+    const uint32_t pb = blockIdx.x % pair_blocks, rb = blockIdx.x / pair_blocks;
+    const uint32_t pair = pb * blockDim.x + threadIdx.x;
+    const uint32_t row = rb * blockDim.y + threadIdx.y;
+    if (pair >= pairs || row >= n_rows) return;
+    const size_t col = (size_t)pair * 2, o = (size_t)row * stride + col;
+    const ulonglong2 v = ld_stream(dval + o), m = ld_stream(dvld + o);
+    if (JACOBI) {
+        const ulonglong2 ov = ld_stream(old_val + o), om = ld_stream(old_vld + o);
+        const uint64_t dx = (v.x ^ ov.x) | (m.x ^ om.x), dy = (v.y ^ ov.y) | (m.y ^ om.y);
+        if (dx) atomicOr((unsigned long long *)&changed[col], (unsigned long long)dx);
+        if (dy) atomicOr((unsigned long long *)&changed[col + 1], (unsigned long long)dy);
+    }
+    st_pair(out_val + o, v);
+    st_pair(out_vld + o, m);
+}
+
+// External drives on gate-driven rows: resolve(D, gate output) and conflict detection
+// (both operands not High-Z).  mode 0: merge + conflict; mode 1 (cold start,
+// component outputs still High-Z): the row simply takes the drive.
+__global__ void __launch_bounds__(256) k_extra_drive(const uint32_t *rows, uint32_t n, const uint64_t *xval,
+                                                     const uint64_t *xvld, uint64_t *val, uint64_t *vld, uint64_t *conf,
+                                                     uint32_t stride, int mode) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= stride) return;
+    uint64_t c = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const size_t o = (size_t)rows[i] * stride + w, x = (size_t)i * stride + w;
+        const uint64_t dv = xval[x], dm = xvld[x];
+        if (mode == 1) {
+            val[o] = dv;
+            vld[o] = dm;
+        } else {
+            const uint64_t gv = val[o], gm = vld[o];
+            c |= (dv | dm) & (gv | gm);
+            val[o] = gv | dv;
+            vld[o] = gm | dm;
+        }
+    }
+    if (mode == 0 && c) atomicOr((unsigned long long *)&conf[w], (unsigned long long)c);
+}
+
+// Per-lane bookkeeping after one application (mirrors oracle/bitsliced.c bs_run):
+//   conflict |= conf_step & live (only while k < last); live &= changed & ~conflict;
+//   on the last (check-only) application: unsettled = live.
+__global__ void __launch_bounds__(256) k_status_step(uint64_t *changed, uint64_t *conf_step, uint64_t *live,
+                                                     uint64_t *conflict, uint64_t *unsettled, RunFlags *flags,
+                                                     uint32_t words, uint64_t n_lanes, int count_conflicts, int is_last) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lv = 0, cf = 0, un = 0;
+    if (w < words) {
+        const uint64_t mask = lane_mask_of(w, n_lanes);
+        lv = live[w] & mask;
+        cf = conflict[w];
+        if (count_conflicts) cf |= conf_step[w] & lv;
+        lv &= changed[w] & ~cf;
+        live[w] = lv;
+        conflict[w] = cf;
+        if (is_last) {
+            un = lv;
+            unsettled[w] = un;
+        }
+        changed[w] = 0;
+        conf_step[w] = 0;
+    }
+    const unsigned any_l = __ballot_sync(0xFFFFFFFFu, lv != 0), any_c = __ballot_sync(0xFFFFFFFFu, cf != 0),
+                   any_u = __ballot_sync(0xFFFFFFFFu, un != 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (any_l) atomicOr(&flags->any_live, 1u);
+        if (any_c) atomicOr(&flags->any_conflict, 1u);
+        if (any_u) atomicOr(&flags->any_unsettled, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_init_status(uint64_t *changed, uint64_t *conf_step, uint64_t *live, uint64_t *conflict,
+                                                     uint64_t *unsettled, RunFlags *flags, uint32_t words, uint64_t n_lanes,
+                                                     int all_conflict) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w == 0) {
+        flags->any_live = 0;
+        flags->any_conflict = all_conflict ? 1u : 0u;
+        flags->any_unsettled = 0;
+    }
+    if (w >= words) return;
+    const uint64_t mask = lane_mask_of(w, n_lanes);
+    changed[w] = 0;
+    conf_step[w] = 0;
+    live[w] = mask;
+    conflict[w] = all_conflict ? mask : 0;
+    unsettled[w] = 0;
+}
+
+__global__ void k_clear_flags(RunFlags *flags) {
+    flags->any_live = 0;
+    flags->any_conflict = 0;
+    flags->any_unsettled = 0;
+}
+
+// Levelised runs: conflicts can only come from drives on gate-driven rows.
+__global__ void __launch_bounds__(256) k_levelised_status(uint64_t *conflict, uint64_t *unsettled, RunFlags *flags,
+                                                          uint32_t words, uint64_t n_lanes) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t cf = 0;
+    if (w < words) {
+        cf = conflict[w] & lane_mask_of(w, n_lanes);
+        conflict[w] = cf;
+        unsettled[w] = 0;
+    }
+    const unsigned any_c = __ballot_sync(0xFFFFFFFFu, cf != 0);
+    if ((threadIdx.x & 31) == 0 && any_c) atomicOr(&flags->any_conflict, 1u);
+}
+
+struct Planes8 {
+    uint32_t p0[8], p1[8];
+};
+
+// set_wire_drive broadcast: bit j of the wire -> all lanes of drive row rows.row[j].
+__global__ void __launch_bounds__(256) k_broadcast_drive(uint64_t *const *row_val, uint64_t *const *row_vld, Planes8 p,
+                                                         uint32_t n_bits, uint32_t stride) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = blockIdx.y;
+    if (w >= stride || j >= n_bits) return;
+    const uint64_t v = ((p.p0[j >> 5] >> (j & 31)) & 1) ? ~0ull : 0ull;
+    const uint64_t m = ((p.p1[j >> 5] >> (j & 31)) & 1) ? ~0ull : 0ull;
+    row_val[j][w] = v;
+    row_vld[j][w] = m;
+}
+
+__global__ void __launch_bounds__(256) k_fill_stimulus(uint64_t *const *row_val, uint64_t *const *row_vld, uint32_t n,
+                                                       uint32_t words, uint64_t seed, uint64_t word_base, int mode) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (w >= words || i >= n) return;
+    const uint64_t v = splitmix64(seed ^ ((uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull) ^ ((word_base + w) * 0xD1B54A32D192ED03ull));
+    const uint64_t m = mode == 0 ? ~0ull : (splitmix64(v ^ 1) | splitmix64(v ^ 2));
+    row_val[i][w] = v;
+    row_vld[i][w] = m;
+}
+
+// rows[] of (val, vld) -> dense planes [n][dst_stride]
+__global__ void __launch_bounds__(256) k_gather_rows(const uint32_t *rows, uint32_t n, const uint64_t *val, const uint64_t *vld,
+                                                     uint64_t *dst_val, uint64_t *dst_vld, uint32_t stride, uint32_t word0,
+                                                     uint32_t n_words, size_t dst_stride) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (w >= n_words || i >= n) return;
+    const size_t s = (size_t)rows[i] * stride + word0 + w;
+    dst_val[(size_t)i * dst_stride + w] = val[s];
+    dst_vld[(size_t)i * dst_stride + w] = vld[s];
+}
+
+// dense planes [n][src_stride] -> drive rows given by pointer tables
+__global__ void __launch_bounds__(256) k_scatter_rows(uint64_t *const *row_val, uint64_t *const *row_vld, uint32_t n,
+                                                      const uint64_t *src_val, const uint64_t *src_vld, uint32_t words,
+                                                      size_t src_stride) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (w >= words || i >= n) return;
+    row_val[i][w] = src_val[(size_t)i * src_stride + w];
+    row_vld[i][w] = src_vld[(size_t)i * src_stride + w];
+}
+
+// SimState bit-packing of lane 0 (reference crates/digilogic_netcode/src/lib.rs:241-270): bit k
+// of the packed planes = bit 0 / lane 0 of rows[k].  One thread builds one output byte.
+__global__ void __launch_bounds__(256) k_pack_lane0(const uint32_t *rows, uint32_t n_bits, const uint64_t *val,
+                                                    const uint64_t *vld, uint32_t stride, uint8_t *out0, uint8_t *out1,
+                                                    uint32_t n_bytes) {
+    const uint32_t byte = blockIdx.x * blockDim.x + threadIdx.x;
+    if (byte >= n_bytes) return;
+    uint32_t b0 = 0, b1 = 0;
+    for (uint32_t j = 0; j < 8; j++) {
+        const uint32_t k = byte * 8 + j;
+        if (k < n_bits) {
+            const size_t s = (size_t)rows[k] * stride;
+            b0 |= (uint32_t)(val[s] & 1) << j;
+            b1 |= (uint32_t)(vld[s] & 1) << j;
+        }
+    }
+    out0[byte] = (uint8_t)b0;
+    out1[byte] = (uint8_t)b1;
+}
+
+// ---------------------------------------------------------------------------- Engine: setup
+
+Engine::Engine(Compiled &&net) : net_(std::move(net)) {}
+
+Engine::~Engine() {
+    if (device_ready_) {
+        cudaSetDevice(device_);
+        if (stream_) cudaStreamSynchronize(ST);
+        free_store();
+        cudaFree(d_fan0_);
+        cudaFree(d_fan1_);
+        cudaFree(d_kind2_);
+        cudaFree(d_wide_off_);
+        cudaFree(d_wide_in_);
+        cudaFree(d_wide_kind_);
+        cudaFree(d_wide_nsel_);
+        cudaFree(d_flags_);
+        if (h_flags_) cudaFreeHost(h_flags_);
+        if (own_stream_ && stream_) cudaStreamDestroy(ST);
+    }
+}
+
+void Engine::free_store() {
+    for (int i = 0; i < 2; i++) {
+        cudaFree(val_[i]);
+        cudaFree(vld_[i]);
+        val_[i] = vld_[i] = nullptr;
+    }
+    cudaFree(drv_val_);
+    cudaFree(drv_vld_);
+    cudaFree(xdrv_val_);
+    cudaFree(xdrv_vld_);
+    cudaFree(d_extra_rows_);
+    cudaFree(d_changed_);
+    cudaFree(d_conf_step_);
+    cudaFree(d_live_);
+    cudaFree(d_conflict_);
+    cudaFree(d_unsettled_);
+    cudaFree(stage_val_);
+    cudaFree(stage_vld_);
+    cudaFree(d_rows_);
+    cudaFree(d_pack_);
+    drv_val_ = drv_vld_ = xdrv_val_ = xdrv_vld_ = nullptr;
+    d_extra_rows_ = nullptr;
+    d_changed_ = d_conf_step_ = d_live_ = d_conflict_ = d_unsettled_ = nullptr;
+    stage_val_ = stage_vld_ = nullptr;
+    stage_words_ = 0;
+    d_rows_ = nullptr;
+    rows_cap_ = 0;
+    d_pack_ = nullptr;
+    pack_cap_ = 0;
+    extra_slot_.clear();
+    extra_rows_.clear();
+    extra_cap_ = 0;
+    store_bytes_ = 0;
+}
+
+int Engine::set_device(int device) {
+    if (device_ready_) return device == device_ ? B2_OK : B2_ERR_INVALID_ARG;
+    device_ = device;
+    return B2_OK;
+}
+
+int Engine::set_stream(void *stream) {
+    if (device_ready_ && stream_ && stream != stream_) CU_TRY(cudaStreamSynchronize(ST));
+    if (own_stream_ && stream_) {
+        cudaStreamDestroy(ST);
+        own_stream_ = false;
+    }
+    stream_ = stream;
+    if (!stream_ && device_ready_) {
+        cudaStream_t s;
+        CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        stream_ = s;
+        own_stream_ = true;
+    }
+    return B2_OK;
+}
+
+template <typename Tv>
+static int upload(Tv **dst, const std::vector<Tv> &src) {
+    const size_t n = src.size() ? src.size() : 1;
+    CU_TRY(cudaMalloc((void **)dst, n * sizeof(Tv)));
+    if (src.size()) CU_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(Tv), cudaMemcpyHostToDevice));
+    return B2_OK;
+}
+
+int Engine::ensure_device() {
+    if (device_ready_) {
+        CU_TRY(cudaSetDevice(device_));
+        return B2_OK;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_last_error(std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                       " (this engine has no CPU path)");
+        cudaGetLastError();
+        return B2_ERR_NO_DEVICE;
+    }
+    if (device_ < 0) {
+        if (cudaGetDevice(&device_) != cudaSuccess) device_ = 0;
+    }
+    if (device_ >= count) {
+        set_last_error("device ordinal out of range");
+        return B2_ERR_INVALID_ARG;
+    }
+    CU_TRY(cudaSetDevice(device_));
+    // the kernels are built for sm_100a only: fail loudly on anything else
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, k_clear_flags);
+    if (e != cudaSuccess) {
+        set_last_error(std::string("sm_100a kernels not loadable on this device: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+        return B2_ERR_NO_DEVICE;
+    }
+    if (!stream_) {
+        cudaStream_t s;
+        CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        stream_ = s;
+        own_stream_ = true;
+    }
+    int rc;
+    if ((rc = upload(&d_fan0_, net_.fan0))) return rc;
+    if ((rc = upload(&d_fan1_, net_.fan1))) return rc;
+    if ((rc = upload(&d_kind2_, net_.kind2))) return rc;
+    if ((rc = upload(&d_wide_off_, net_.wide_off))) return rc;
+    if ((rc = upload(&d_wide_in_, net_.wide_in))) return rc;
+    if ((rc = upload(&d_wide_kind_, net_.wide_kind))) return rc;
+    if ((rc = upload(&d_wide_nsel_, net_.wide_nsel))) return rc;
+    CU_TRY(cudaMalloc((void **)&d_flags_, sizeof(RunFlags)));
+    CU_TRY(cudaMemset(d_flags_, 0, sizeof(RunFlags)));
+    CU_TRY(cudaMallocHost((void **)&h_flags_, sizeof(RunFlags)));
+    device_ready_ = true;
+    return B2_OK;
+}
+
+int Engine::synchronize() {
+    if (!device_ready_) return B2_OK;
+    CU_TRY(cudaSetDevice(device_));
+    CU_TRY(cudaStreamSynchronize(ST));
+    return B2_OK;
+}
+
+static uint32_t stride_for(uint32_t T) {
+    if (T <= 2) return 2;
+    if (T < 32) return (T + 1) & ~1u;
+    return (T + 15) & ~15u;  // 128-byte aligned rows
+}
+
+static uint64_t bytes_per_lane_word(const Compiled &n, bool second) {
+    // A (+B) planes, drive rows, status words
+    return ((uint64_t)n.n_rows * (second ? 2 : 1) + n.n_src) * 16 + 5 * 8;
+}
+
+uint64_t Engine::max_lanes(uint64_t bytes) const {
+    if (bytes == 0) {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        bytes = fr;
+    }
+    const uint64_t per = bytes_per_lane_word(net_, net_.cyclic);
+    uint64_t words = bytes / (per ? per : 1);
+    if (words > 32) words &= ~15ull;
+    if (words > 0x7FFFFFF0ull) words = 0x7FFFFFF0ull;
+    return words * 64;
+}
+
+int Engine::set_lanes(uint64_t n_lanes) {
+    if (n_lanes == 0 || n_lanes > 64ull * 0x7FFFFFF0ull) return B2_ERR_INVALID_ARG;
+    int rc = ensure_device();
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(ST));
+    free_store();
+    n_lanes_ = n_lanes;
+    T_ = (uint32_t)((n_lanes + 63) / 64);
+    stride_ = stride_for(T_);
+    const size_t row_words = (size_t)(net_.n_rows ? net_.n_rows : 1) * stride_;
+    const size_t src_words = (size_t)(net_.n_src ? net_.n_src : 1) * stride_;
+    auto alloc0 = [&](uint64_t **p, size_t words) -> int {
+        CU_TRY(cudaMalloc((void **)p, words * 8));
+        CU_TRY(cudaMemsetAsync(*p, 0, words * 8, ST));
+        store_bytes_ += words * 8;
+        return B2_OK;
+    };
+    if ((rc = alloc0(&val_[0], row_words)) || (rc = alloc0(&vld_[0], row_words)) || (rc = alloc0(&drv_val_, src_words)) ||
+        (rc = alloc0(&drv_vld_, src_words)) || (rc = alloc0(&d_changed_, stride_)) || (rc = alloc0(&d_conf_step_, stride_)) ||
+        (rc = alloc0(&d_live_, stride_)) || (rc = alloc0(&d_conflict_, stride_)) || (rc = alloc0(&d_unsettled_, stride_))) {
+        free_store();
+        n_lanes_ = 0;
+        T_ = stride_ = 0;
+        return rc;
+    }
+    cur_ = 0;
+    cold_ = true;
+    last_mode_ = 0;
+    last_apps_ = 0;
+    return B2_OK;
+}
+
+int Engine::ensure_lanes() {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (n_lanes_ == 0) return set_lanes(1);
+    return B2_OK;
+}
+
+int Engine::ensure_second_buffer() {
+    if (val_[1]) return B2_OK;
+    const size_t row_words = (size_t)(net_.n_rows ? net_.n_rows : 1) * stride_;
+    CU_TRY(cudaMalloc((void **)&val_[1], row_words * 8));
+    CU_TRY(cudaMalloc((void **)&vld_[1], row_words * 8));
+    CU_TRY(cudaMemsetAsync(val_[1], 0, row_words * 8, ST));
+    CU_TRY(cudaMemsetAsync(vld_[1], 0, row_words * 8, ST));
+    store_bytes_ += row_words * 16;
+    return B2_OK;
+}
+
+int Engine::ensure_stage(size_t words) {
+    if (stage_words_ >= words) return B2_OK;
+    CU_TRY(cudaStreamSynchronize(ST));
+    cudaFree(stage_val_);
+    cudaFree(stage_vld_);
+    stage_val_ = stage_vld_ = nullptr;
+    store_bytes_ -= stage_words_ * 16;
+    stage_words_ = 0;
+    CU_TRY(cudaMalloc((void **)&stage_val_, words * 8));
+    CU_TRY(cudaMalloc((void **)&stage_vld_, words * 8));
+    stage_words_ = words;
+    store_bytes_ += words * 16;
+    return B2_OK;
+}
+
+int Engine::ensure_rows_buffer(uint32_t n) {
+    // holds n row indices and, behind them (8-byte aligned), two tables of n row pointers
+    if (rows_cap_ >= n) return B2_OK;
+    CU_TRY(cudaStreamSynchronize(ST));
+    cudaFree(d_rows_);
+    d_rows_ = nullptr;
+    rows_cap_ = 0;
+    const uint32_t cap = std::max<uint32_t>(n, 1024);
+    const size_t idx_bytes = (((size_t)cap * 4) + 15) & ~(size_t)15;
+    CU_TRY(cudaMalloc((void **)&d_rows_, idx_bytes + (size_t)cap * 16));
+    rows_cap_ = cap;
+    return B2_OK;
+}
+
+// Row pointers of the drive of a bit-net; gate-driven bits get a slot in the extra store.
+int Engine::drive_target(uint32_t bitnet, uint64_t **val, uint64_t **vld) {
+    if (!net_.bit_driven[bitnet]) {
+        const size_t o = (size_t)net_.row_of_bit[bitnet] * stride_;
+        *val = drv_val_ + o;
+        *vld = drv_vld_ + o;
+        return B2_OK;
+    }
+    auto it = extra_slot_.find(bitnet);
+    uint32_t slot;
+    if (it != extra_slot_.end()) {
+        slot = it->second;
+    } else {
+        slot = (uint32_t)extra_rows_.size();
+        if (slot >= extra_cap_) {
+            const uint32_t cap = extra_cap_ ? extra_cap_ * 2 : 64;
+            uint64_t *nv = nullptr, *nm = nullptr;
+            CU_TRY(cudaMalloc((void **)&nv, (size_t)cap * stride_ * 8));
+            CU_TRY(cudaMalloc((void **)&nm, (size_t)cap * stride_ * 8));
+            CU_TRY(cudaMemsetAsync(nv, 0, (size_t)cap * stride_ * 8, ST));
+            CU_TRY(cudaMemsetAsync(nm, 0, (size_t)cap * stride_ * 8, ST));
+            if (extra_cap_) {
+                CU_TRY(cudaMemcpyAsync(nv, xdrv_val_, (size_t)extra_cap_ * stride_ * 8, cudaMemcpyDeviceToDevice, ST));
+                CU_TRY(cudaMemcpyAsync(nm, xdrv_vld_, (size_t)extra_cap_ * stride_ * 8, cudaMemcpyDeviceToDevice, ST));
+            }
+            CU_TRY(cudaStreamSynchronize(ST));
+            cudaFree(xdrv_val_);
+            cudaFree(xdrv_vld_);
+            cudaFree(d_extra_rows_);
+            d_extra_rows_ = nullptr;
+            CU_TRY(cudaMalloc((void **)&d_extra_rows_, (size_t)cap * 4));
+            xdrv_val_ = nv;
+            xdrv_vld_ = nm;
+            store_bytes_ += (size_t)(cap - extra_cap_) * stride_ * 16;
+            extra_cap_ = cap;
+        }
+        extra_slot_[bitnet] = slot;
+        extra_rows_.push_back(net_.row_of_bit[bitnet]);
+        extra_rows_dirty_ = true;
+    }
+    *val = xdrv_val_ + (size_t)slot * stride_;
+    *vld = xdrv_vld_ + (size_t)slot * stride_;
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------- Engine: drives
+
+int Engine::set_wire_drive(uint32_t wire, const uint32_t *p0, const uint32_t *p1, size_t words) {
+    if (wire >= net_.n_wires()) return B2_ERR_INVALID_WIRE_ID;
+    if (words && (!p0 || !p1)) return B2_ERR_NULL;
+    int rc = ensure_lanes();
+    if (rc) return rc;
+    const uint32_t width = net_.width[wire];
+    Planes8 p;
+    for (uint32_t i = 0; i < 8; i++) {
+        p.p0[i] = i < words ? p0[i] : 0;
+        p.p1[i] = i < words ? p1[i] : 0;
+    }
+    // row pointer tables for the bits of this wire (two passes: the first may grow the extra store)
+    if ((rc = ensure_rows_buffer(width))) return rc;
+    std::vector<uint64_t *> tv(width), tm(width);
+    for (int pass = 0; pass < 2; pass++)
+        for (uint32_t j = 0; j < width; j++)
+            if ((rc = drive_target(net_.bit_off[wire] + j, &tv[j], &tm[j]))) return rc;
+    const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
+    uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
+    CU_TRY(cudaMemcpyAsync(d_tv, tv.data(), (size_t)width * 8, cudaMemcpyHostToDevice, ST));
+    CU_TRY(cudaMemcpyAsync(d_tm, tm.data(), (size_t)width * 8, cudaMemcpyHostToDevice, ST));
+    dim3 grid((stride_ + 255) / 256, width);
+    k_broadcast_drive<<<grid, 256, 0, ST>>>(d_tv, d_tm, p, width, stride_);
+    LAUNCHED();
+    CU_TRY(cudaStreamSynchronize(ST));  // tv/tm are stack-lifetime host buffers
+    return B2_OK;
+}
+
+int Engine::set_wire_drive_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint32_t nw, const uint64_t *value,
+                                 const uint64_t *valid) {
+    if (wire >= net_.n_wires() || bit >= net_.width[wire]) return B2_ERR_INVALID_WIRE_ID;
+    if (!value || !valid) return B2_ERR_NULL;
+    int rc = ensure_lanes();
+    if (rc) return rc;
+    if ((uint64_t)w0 + nw > T_) return B2_ERR_RANGE;
+    uint64_t *dv, *dm;
+    if ((rc = drive_target(net_.bit_off[wire] + bit, &dv, &dm))) return rc;
+    CU_TRY(cudaMemcpyAsync(dv + w0, value, (size_t)nw * 8, cudaMemcpyHostToDevice, ST));
+    CU_TRY(cudaMemcpyAsync(dm + w0, valid, (size_t)nw * 8, cudaMemcpyHostToDevice, ST));
+    CU_TRY(cudaStreamSynchronize(ST));  // caller may reuse its buffers
+    return B2_OK;
+}
+
+// Uploads row indices (store rows) or drive row pointer tables for bit 0 of `wires`.
+int Engine::upload_rows(const uint32_t *wires, uint32_t n, bool drive_rows) {
+    int rc = ensure_rows_buffer(n);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; i++)
+        if (wires[i] >= net_.n_wires()) return B2_ERR_INVALID_WIRE_ID;
+    if (!drive_rows) {
+        std::vector<uint32_t> rows(n);
+        for (uint32_t i = 0; i < n; i++) rows[i] = net_.row_of_bit[net_.bit_off[wires[i]]];
+        CU_TRY(cudaMemcpyAsync(d_rows_, rows.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ST));
+        CU_TRY(cudaStreamSynchronize(ST));
+    } else {
+        std::vector<uint64_t *> tv(n), tm(n);
+        for (uint32_t i = 0; i < n; i++)
+            if ((rc = drive_target(net_.bit_off[wires[i]], &tv[i], &tm[i]))) return rc;
+        // drive_target may have re-allocated the extra store: resolve again so every pointer is current
+        for (uint32_t i = 0; i < n; i++)
+            if ((rc = drive_target(net_.bit_off[wires[i]], &tv[i], &tm[i]))) return rc;
+        const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
+        uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
+        CU_TRY(cudaMemcpyAsync(d_tv, tv.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ST));
+        CU_TRY(cudaMemcpyAsync(d_tm, tm.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ST));
+        CU_TRY(cudaStreamSynchronize(ST));
+    }
+    return B2_OK;
+}
+
+int Engine::set_drives_lanes(const uint32_t *wires, uint32_t n, const uint64_t *value, const uint64_t *valid, size_t src_stride) {
+    if (n && (!wires || !value || !valid)) return B2_ERR_NULL;
+    int rc = ensure_lanes();
+    if (rc) return rc;
+    if (n == 0) return B2_OK;
+    if (src_stride < T_) return B2_ERR_RANGE;
+    if ((rc = upload_rows(wires, n, true))) return rc;
+    if ((rc = ensure_stage((size_t)n * T_))) return rc;
+    CU_TRY(cudaMemcpy2DAsync(stage_val_, (size_t)T_ * 8, value, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyHostToDevice, ST));
+    CU_TRY(cudaMemcpy2DAsync(stage_vld_, (size_t)T_ * 8, valid, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyHostToDevice, ST));
+    const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
+    uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
+    dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
+    k_scatter_rows<<<grid, block, 0, ST>>>(d_tv, d_tm, n, stage_val_, stage_vld_, T_, T_);
+    LAUNCHED();
+    return B2_OK;
+}
+
+int Engine::fill_stimulus(const uint32_t *wires, uint32_t n, uint64_t seed, uint64_t word_base, int mode) {
+    if (n && !wires) return B2_ERR_NULL;
+    if (mode != 0 && mode != 1) return B2_ERR_INVALID_ARG;
+    int rc = ensure_lanes();
+    if (rc) return rc;
+    if (n == 0) return B2_OK;
+    if ((rc = upload_rows(wires, n, true))) return rc;
+    const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
+    uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
+    dim3 block(64, 4), grid((stride_ + 63) / 64, (n + 3) / 4);
+    k_fill_stimulus<<<grid, block, 0, ST>>>(d_tv, d_tm, n, stride_, seed, word_base, mode);
+    LAUNCHED();
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------- Engine: settle loops
+
+namespace {
+struct Shape {
+    dim3 block;
+    uint32_t pair_blocks;
+};
+// BX = power of two covering the row (<= 256), BY = 256 / BX gates per CTA slice.
+Shape shape_for(uint32_t pairs) {
+    uint32_t bx = 1;
+    while (bx < pairs && bx < 256) bx <<= 1;
+    Shape s;
+    s.block = dim3(bx, 256 / bx);
+    s.pair_blocks = (pairs + bx - 1) / bx;
+    return s;
+}
+}  // namespace
+
+#define EVAL2_U 4
+
+int Engine::run_levelised(bool async) {
+    const uint32_t pairs = stride_ / 2;
+    const Shape sh = shape_for(pairs);
+    uint64_t *V = val_[cur_], *M = vld_[cur_];
+    if (net_.n_src) {
+        const uint32_t rb = (net_.n_src + sh.block.y - 1) / sh.block.y;
+        k_apply_drive<false><<<sh.pair_blocks * rb, sh.block, 0, ST>>>(drv_val_, drv_vld_, nullptr, nullptr, V, M, nullptr,
+                                                                        net_.n_src, stride_, pairs, sh.pair_blocks);
+        LAUNCHED();
+    }
+    for (const Level &lv : net_.levels) {
+        if (lv.g2_end > lv.g2_begin) {
+            Eval2Args a{d_fan0_, d_fan1_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
+                        sh.pair_blocks};
+            const uint32_t per = sh.block.y * EVAL2_U;
+            const uint32_t gb = (lv.g2_end - lv.g2_begin + per - 1) / per;
+            k_eval2<EVAL2_U, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+            LAUNCHED();
+        }
+        if (lv.wide_end > lv.wide_begin) {
+            WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, V, M, V, M, nullptr, lv.wide_begin, lv.wide_end,
+                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks};
+            const uint32_t gb = (lv.wide_end - lv.wide_begin + sh.block.y - 1) / sh.block.y;
+            k_eval_wide<false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+            LAUNCHED();
+        }
+    }
+    cold_ = false;
+    last_mode_ = 1;
+    last_apps_ = 1;
+    if (extra_rows_.empty()) {
+        if (async) return B2_RUN_OK;  // no wire can conflict; status words are refreshed lazily
+        CU_TRY(cudaMemsetAsync(d_conflict_, 0, (size_t)stride_ * 8, ST));
+        CU_TRY(cudaMemsetAsync(d_unsettled_, 0, (size_t)stride_ * 8, ST));
+        h_flags_->any_live = h_flags_->any_conflict = h_flags_->any_unsettled = 0;
+        return B2_RUN_OK;
+    }
+    if (extra_rows_dirty_) {
+        CU_TRY(cudaMemcpyAsync(d_extra_rows_, extra_rows_.data(), extra_rows_.size() * 4, cudaMemcpyHostToDevice, ST));
+        extra_rows_dirty_ = false;
+    }
+    CU_TRY(cudaMemsetAsync(d_conflict_, 0, (size_t)stride_ * 8, ST));
+    k_clear_flags<<<1, 1, 0, ST>>>(d_flags_);
+    LAUNCHED();
+    k_extra_drive<<<(stride_ + 255) / 256, 256, 0, ST>>>(d_extra_rows_, (uint32_t)extra_rows_.size(), xdrv_val_, xdrv_vld_, V, M,
+                                                         d_conflict_, stride_, 0);
+    LAUNCHED();
+    k_levelised_status<<<(stride_ + 255) / 256, 256, 0, ST>>>(d_conflict_, d_unsettled_, d_flags_, stride_, n_lanes_);
+    LAUNCHED();
+    CU_TRY(cudaMemcpyAsync(h_flags_, d_flags_, sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaStreamSynchronize(ST));
+    return h_flags_->any_conflict ? B2_RUN_CONFLICT : B2_RUN_OK;
+}
+
+int Engine::run_jacobi(uint64_t max_steps) {
+    int rc = ensure_second_buffer();
+    if (rc) return rc;
+    const uint32_t pairs = stride_ / 2;
+    const Shape sh = shape_for(pairs);
+    const uint64_t N = max_steps == UINT64_MAX ? UINT64_MAX : max_steps + 1;
+    const uint64_t last = N >= UINT64_MAX - 2 ? UINT64_MAX : N + 2;  // the final, check-only application
+    const uint32_t n_extra = (uint32_t)extra_rows_.size();
+    if (n_extra && extra_rows_dirty_) {
+        CU_TRY(cudaMemcpyAsync(d_extra_rows_, extra_rows_.data(), (size_t)n_extra * 4, cudaMemcpyHostToDevice, ST));
+        extra_rows_dirty_ = false;
+    }
+    const uint32_t sgrid = (stride_ + 255) / 256;
+    k_init_status<<<sgrid, 256, 0, ST>>>(d_changed_, d_conf_step_, d_live_, d_conflict_, d_unsettled_, d_flags_, stride_, n_lanes_, 0);
+    LAUNCHED();
+    last_mode_ = 2;
+    last_apps_ = 0;
+    h_flags_->any_live = h_flags_->any_conflict = h_flags_->any_unsettled = 0;
+    uint64_t k = 0;
+    if (cold_) {
+        // W_1 = resolve(D, all outputs High-Z) = D
+        uint64_t *V = val_[cur_], *M = vld_[cur_];
+        const size_t row_words = (size_t)net_.n_rows * stride_;
+        CU_TRY(cudaMemsetAsync(V, 0, row_words * 8, ST));
+        CU_TRY(cudaMemsetAsync(M, 0, row_words * 8, ST));
+        if (net_.n_src) {
+            const uint32_t rb = (net_.n_src + sh.block.y - 1) / sh.block.y;
+            k_apply_drive<false><<<sh.pair_blocks * rb, sh.block, 0, ST>>>(drv_val_, drv_vld_, nullptr, nullptr, V, M, nullptr,
+                                                                            net_.n_src, stride_, pairs, sh.pair_blocks);
+            LAUNCHED();
+        }
+        if (n_extra) {
+            k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_extra, xdrv_val_, xdrv_vld_, V, M, d_conf_step_, stride_, 1);
+            LAUNCHED();
+        }
+        cold_ = false;
+        k = 1;
+        if (net_.n_g2() + net_.n_wide() == 0) return B2_RUN_OK;
+    }
+    for (;;) {
+        k++;
+        last_apps_++;
+        const bool is_last = k == last;
+        const uint64_t *AV = val_[cur_], *AM = vld_[cur_];
+        uint64_t *BV = val_[cur_ ^ 1], *BM = vld_[cur_ ^ 1];
+        if (net_.n_src) {
+            const uint32_t rb = (net_.n_src + sh.block.y - 1) / sh.block.y;
+            k_apply_drive<true><<<sh.pair_blocks * rb, sh.block, 0, ST>>>(drv_val_, drv_vld_, AV, AM, BV, BM, d_changed_, net_.n_src,
+                                                                           stride_, pairs, sh.pair_blocks);
+            LAUNCHED();
+        }
+        if (net_.n_g2()) {
+            Eval2Args a{d_fan0_, d_fan1_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
+                        sh.pair_blocks};
+            const uint32_t per = sh.block.y * EVAL2_U;
+            const uint32_t gb = (net_.n_g2() + per - 1) / per;
+            k_eval2<EVAL2_U, true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+            LAUNCHED();
+        }
+        if (net_.n_wide()) {
+            WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, AV, AM, BV, BM, d_changed_, 0, net_.n_wide(),
+                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks};
+            const uint32_t gb = (net_.n_wide() + sh.block.y - 1) / sh.block.y;
+            k_eval_wide<true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+            LAUNCHED();
+        }
+        if (n_extra) {
+            k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_extra, xdrv_val_, xdrv_vld_, BV, BM, d_conf_step_, stride_, 0);
+            LAUNCHED();
+        }
+        k_clear_flags<<<1, 1, 0, ST>>>(d_flags_);
+        LAUNCHED();
+        k_status_step<<<sgrid, 256, 0, ST>>>(d_changed_, d_conf_step_, d_live_, d_conflict_, d_unsettled_, d_flags_, stride_, n_lanes_,
+                                             is_last ? 0 : 1, is_last ? 1 : 0);
+        LAUNCHED();
+        CU_TRY(cudaMemcpyAsync(h_flags_, d_flags_, sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
+        CU_TRY(cudaStreamSynchronize(ST));
+        if (is_last) break;  // check-only: MaxStepsReached lanes keep W_{N+1} (the current buffer)
+        cur_ ^= 1;
+        if (!h_flags_->any_live) break;
+    }
+    if (h_flags_->any_conflict) return B2_RUN_CONFLICT;
+    if (h_flags_->any_unsettled) return B2_RUN_MAX_STEPS_REACHED;
+    return B2_RUN_OK;
+}
+
+int Engine::run(uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled, bool async) {
+    int rc = ensure_lanes();
+    if (rc) return -rc;
+    int result;
+    if (net_.multi_driver) {
+        // two gate outputs on one wire are never High-Z: every lane conflicts on its first step
+        k_init_status<<<(stride_ + 255) / 256, 256, 0, ST>>>(d_changed_, d_conf_step_, d_live_, d_conflict_, d_unsettled_, d_flags_,
+                                                             stride_, n_lanes_, 1);
+        g_launches.fetch_add(1);
+        if (cudaGetLastError() != cudaSuccess) return -B2_ERR_CUDA;
+        cold_ = false;
+        last_mode_ = 0;
+        last_apps_ = 0;
+        result = B2_RUN_CONFLICT;
+    } else if (!net_.cyclic && max_steps >= net_.depth) {
+        result = run_levelised(async && !conflict && !unsettled);
+    } else {
+        result = run_jacobi(max_steps);
+    }
+    if (result < 0) return result;
+    if (result > 2) return -result;  // a b2_status from CU_TRY
+    if (conflict || unsettled) {
+        if (conflict) {
+            cudaError_t e = cudaMemcpyAsync(conflict, d_conflict_, (size_t)T_ * 8, cudaMemcpyDeviceToHost, ST);
+            if (e != cudaSuccess) return -B2_ERR_CUDA;
+        }
+        if (unsettled) {
+            cudaError_t e = cudaMemcpyAsync(unsettled, d_unsettled_, (size_t)T_ * 8, cudaMemcpyDeviceToHost, ST);
+            if (e != cudaSuccess) return -B2_ERR_CUDA;
+        }
+        if (cudaStreamSynchronize(ST) != cudaSuccess) return -B2_ERR_CUDA;
+    }
+    return result;
+}
+
+// ---------------------------------------------------------------------------- Engine: read-back
+
+int Engine::get_wire_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint32_t nw, uint64_t *value, uint64_t *valid) {
+    if (wire >= net_.n_wires() || bit >= net_.width[wire]) return B2_ERR_INVALID_WIRE_ID;
+    if (!value || !valid) return B2_ERR_NULL;
+    int rc = ensure_lanes();
+    if (rc) return rc;
+    if ((uint64_t)w0 + nw > T_) return B2_ERR_RANGE;
+    const size_t o = (size_t)net_.row_of_bit[net_.bit_off[wire] + bit] * stride_ + w0;
+    CU_TRY(cudaMemcpyAsync(value, val_[cur_] + o, (size_t)nw * 8, cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaMemcpyAsync(valid, vld_[cur_] + o, (size_t)nw * 8, cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaStreamSynchronize(ST));
+    return B2_OK;
+}
+
+int Engine::get_wire_state(uint32_t wire, uint32_t *p0, uint32_t *p1, size_t words) {
+    if (wire >= net_.n_wires()) return B2_ERR_INVALID_WIRE_ID;
+    if (!p0 || !p1) return B2_ERR_NULL;
+    const uint32_t width = net_.width[wire], need = (width + 31) / 32;
+    if (words < need) return B2_ERR_RANGE;
+    int rc = ensure_lanes();
+    if (rc) return rc;
+    for (uint32_t i = 0; i < need; i++) p0[i] = p1[i] = 0;
+    if (width == 1) {
+        uint64_t v = 0, m = 0;
+        const size_t o = (size_t)net_.row_of_bit[net_.bit_off[wire]] * stride_;
+        CU_TRY(cudaMemcpyAsync(&v, val_[cur_] + o, 8, cudaMemcpyDeviceToHost, ST));
+        CU_TRY(cudaMemcpyAsync(&m, vld_[cur_] + o, 8, cudaMemcpyDeviceToHost, ST));
+        CU_TRY(cudaStreamSynchronize(ST));
+        p0[0] = (uint32_t)(v & 1);
+        p1[0] = (uint32_t)(m & 1);
+        return B2_OK;
+    }
+    // wide wire: pack lane 0 of its bit rows on the device
+    uint8_t b0[32] = {0}, b1[32] = {0};
+    uint64_t bits = 0;
+    if ((rc = pack_sim_state(&wire, 1, b0, b1, sizeof(b0) + 1, &bits))) return rc;
+    for (uint32_t j = 0; j < width; j++) {
+        p0[j >> 5] |= (uint32_t)((b0[j >> 3] >> (j & 7)) & 1) << (j & 31);
+        p1[j >> 5] |= (uint32_t)((b1[j >> 3] >> (j & 7)) & 1) << (j & 31);
+    }
+    return B2_OK;
+}
+
+int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid, size_t dst_stride, bool dst_is_device) {
+    if (n && (!wires || !value || !valid)) return B2_ERR_NULL;
+    int rc = ensure_lanes();
+    if (rc) return rc;
+    if (n == 0) return B2_OK;
+    if (dst_stride < T_) return B2_ERR_RANGE;
+    if ((rc = upload_rows(wires, n, false))) return rc;
+    dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
+    if (dst_is_device) {
+        k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], value, valid, stride_, 0, T_, dst_stride);
+        LAUNCHED();
+        return B2_OK;
+    }
+    if ((rc = ensure_stage((size_t)n * T_))) return rc;
+    k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], stage_val_, stage_vld_, stride_, 0, T_, T_);
+    LAUNCHED();
+    CU_TRY(cudaMemcpy2DAsync(value, dst_stride * 8, stage_val_, (size_t)T_ * 8, (size_t)T_ * 8, n, cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaMemcpy2DAsync(valid, dst_stride * 8, stage_vld_, (size_t)T_ * 8, (size_t)T_ * 8, n, cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaStreamSynchronize(ST));
+    return B2_OK;
+}
+
+int Engine::pack_sim_state(const uint32_t *wires, uint32_t n, uint8_t *p0, uint8_t *p1, size_t cap, uint64_t *bit_len) {
+    if ((n && !wires) || !p0 || !p1) return B2_ERR_NULL;
+    int rc = ensure_lanes();
+    if (rc) return rc;
+    uint64_t bits = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (wires[i] >= net_.n_wires()) return B2_ERR_INVALID_WIRE_ID;
+        bits += net_.width[wires[i]];
+    }
+    if (bits > 0xFFFFFFF0ull) return B2_ERR_RANGE;
+    const size_t n_bytes = (size_t)(bits / 8 + 1);  // always at least one unused bit (netcode lib.rs:168)
+    if (cap < n_bytes) return B2_ERR_RANGE;
+    if (bit_len) *bit_len = bits;
+    std::vector<uint32_t> rows;
+    rows.reserve((size_t)bits);
+    for (uint32_t i = 0; i < n; i++)
+        for (uint32_t j = 0; j < net_.width[wires[i]]; j++) rows.push_back(net_.row_of_bit[net_.bit_off[wires[i]] + j]);
+    if ((rc = ensure_rows_buffer((uint32_t)std::max<size_t>(rows.size(), 1)))) return rc;
+    if (pack_cap_ < 2 * n_bytes) {
+        CU_TRY(cudaStreamSynchronize(ST));
+        cudaFree(d_pack_);
+        d_pack_ = nullptr;
+        pack_cap_ = 0;
+        CU_TRY(cudaMalloc((void **)&d_pack_, 2 * n_bytes + 64));
+        pack_cap_ = 2 * n_bytes + 64;
+    }
+    if (!rows.empty()) CU_TRY(cudaMemcpyAsync(d_rows_, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, ST));
+    k_pack_lane0<<<(uint32_t)((n_bytes + 255) / 256), 256, 0, ST>>>(d_rows_, (uint32_t)bits, val_[cur_], vld_[cur_], stride_, d_pack_,
+                                                                    d_pack_ + n_bytes, (uint32_t)n_bytes);
+    LAUNCHED();
+    CU_TRY(cudaMemcpyAsync(p0, d_pack_, n_bytes, cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaMemcpyAsync(p1, d_pack_ + n_bytes, n_bytes, cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaStreamSynchronize(ST));
+    return B2_OK;
+}
+
+}  // namespace b2

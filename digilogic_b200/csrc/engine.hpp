@@ -1,0 +1,116 @@
+// engine.hpp — device-resident simulator: wire-state store, drive store, settle loops.
+//
+// Replaces gsim::Simulator behind the calls the reference makes at
+// crates/digilogic_gsim/src/lib.rs:209-230 (set_wire_drive, run_sim, get_wire_state).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "netlist.hpp"
+
+namespace b2 {
+
+void set_last_error(const std::string &msg);
+const char *get_last_error();
+uint64_t kernel_launches();
+
+struct RunFlags {  // written by the status kernel, read by the host after each application
+    uint32_t any_live, any_conflict, any_unsettled, pad;
+};
+
+class Engine {
+   public:
+    explicit Engine(Compiled &&net);
+    ~Engine();
+    Engine(const Engine &) = delete;
+    Engine &operator=(const Engine &) = delete;
+
+    const Compiled &net() const { return net_; }
+
+    int set_device(int device);
+    int set_stream(void *stream);
+    int synchronize();
+    int set_lanes(uint64_t n_lanes);
+    uint64_t max_lanes(uint64_t bytes) const;
+
+    int set_wire_drive(uint32_t wire, const uint32_t *p0, const uint32_t *p1, size_t words);
+    int set_wire_drive_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint32_t nw, const uint64_t *value, const uint64_t *valid);
+    int set_drives_lanes(const uint32_t *wires, uint32_t n, const uint64_t *value, const uint64_t *valid, size_t src_stride);
+    int fill_stimulus(const uint32_t *wires, uint32_t n, uint64_t seed, uint64_t word_base, int mode);
+
+    // returns b2_run_result or -(b2_status)
+    int run(uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled, bool async);
+
+    int get_wire_state(uint32_t wire, uint32_t *p0, uint32_t *p1, size_t words);
+    int get_wire_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint32_t nw, uint64_t *value, uint64_t *valid);
+    int gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid, size_t dst_stride, bool dst_is_device);
+    int pack_sim_state(const uint32_t *wires, uint32_t n, uint8_t *p0, uint8_t *p1, size_t cap, uint64_t *bit_len);
+
+    // info
+    uint64_t n_lanes() const { return n_lanes_; }
+    uint32_t lane_words() const { return T_; }
+    uint32_t row_stride() const { return stride_; }
+    uint64_t store_bytes() const { return store_bytes_; }
+    uint32_t last_mode() const { return last_mode_; }
+    uint64_t last_applications() const { return last_apps_; }
+
+   private:
+    int ensure_device();
+    int ensure_lanes();
+    int ensure_second_buffer();
+    int ensure_stage(size_t words_per_plane);
+    int ensure_rows_buffer(uint32_t n);
+    void free_store();
+    int drive_target(uint32_t bitnet, uint64_t **val, uint64_t **vld);  // row pointers for a bit-net's drive
+    int upload_rows(const uint32_t *wires, uint32_t n, bool drive_rows);
+    int run_levelised(bool async);
+    int run_jacobi(uint64_t max_steps);
+    int finish_status(uint64_t *conflict, uint64_t *unsettled);
+
+    Compiled net_;
+    int device_ = -1;
+    bool device_ready_ = false;
+    void *stream_ = nullptr;  // cudaStream_t
+    bool own_stream_ = false;
+
+    uint64_t n_lanes_ = 0;
+    uint32_t T_ = 0, stride_ = 0;
+    uint64_t store_bytes_ = 0;
+
+    // netlist on the device
+    uint32_t *d_fan0_ = nullptr, *d_fan1_ = nullptr, *d_wide_off_ = nullptr, *d_wide_in_ = nullptr;
+    uint8_t *d_kind2_ = nullptr, *d_wide_kind_ = nullptr, *d_wide_nsel_ = nullptr;
+
+    // wire-state store: two buffers (second one only for unit-delay runs), separate planes
+    uint64_t *val_[2] = {nullptr, nullptr}, *vld_[2] = {nullptr, nullptr};
+    int cur_ = 0;
+    // drive store for source rows [n_src][stride]
+    uint64_t *drv_val_ = nullptr, *drv_vld_ = nullptr;
+    // drives on gate-driven bits (conflict-prone, rare): slot per bit-net
+    std::unordered_map<uint32_t, uint32_t> extra_slot_;
+    std::vector<uint32_t> extra_rows_;
+    uint32_t extra_cap_ = 0;
+    uint64_t *xdrv_val_ = nullptr, *xdrv_vld_ = nullptr;
+    uint32_t *d_extra_rows_ = nullptr;
+    bool extra_rows_dirty_ = false;
+
+    // per-lane status words [T]
+    uint64_t *d_changed_ = nullptr, *d_conf_step_ = nullptr, *d_live_ = nullptr, *d_conflict_ = nullptr, *d_unsettled_ = nullptr;
+    RunFlags *d_flags_ = nullptr, *h_flags_ = nullptr;
+
+    // staging
+    uint64_t *stage_val_ = nullptr, *stage_vld_ = nullptr;
+    size_t stage_words_ = 0;
+    uint32_t *d_rows_ = nullptr;
+    uint32_t rows_cap_ = 0;
+    uint8_t *d_pack_ = nullptr;
+    size_t pack_cap_ = 0;
+
+    bool cold_ = true;
+    uint32_t last_mode_ = 0;
+    uint64_t last_apps_ = 0;
+};
+
+}  // namespace b2

@@ -1,0 +1,247 @@
+// netlist.cpp — builder validation and the netlist compiler (host only, no CUDA).
+#include "netlist.hpp"
+
+#include <algorithm>
+#include <numeric>
+
+#include "../../include/digilogic_b200.h"
+
+namespace b2 {
+
+// ---------------------------------------------------------------------------- builder
+// Validation order and error variants follow SURVEY.md A.2 / the reference's mapping table
+// crates/digilogic_gsim/src/lib.rs:55-66.
+
+int Builder::add_wire(uint8_t w, uint32_t *out) {
+    if (w == 0) return B2_ERR_INVALID_ARG;
+    if (width.size() >= 0xFFFFFFFFull) return B2_ERR_OUT_OF_WIRES;
+    if (out) *out = (uint32_t)width.size();
+    width.push_back(w);
+    return B2_OK;
+}
+
+int Builder::wire_width(uint32_t wire, uint8_t *out) const {
+    if (wire >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    *out = width[wire];
+    return B2_OK;
+}
+
+static int push(Builder &b, uint8_t kind, const uint32_t *in, size_t n, uint32_t select, uint32_t output, uint32_t *cell) {
+    if (b.comps.size() >= 0xFFFFFFFFull || b.inputs.size() + n >= 0xFFFFFFFFull) return B2_ERR_TOO_MANY_COMPONENTS;
+    Component c;
+    c.kind = kind;
+    c.n_inputs = (uint32_t)n;
+    c.in_off = (uint32_t)b.inputs.size();
+    c.select = select;
+    c.output = output;
+    b.inputs.insert(b.inputs.end(), in, in + n);
+    if (cell) *cell = (uint32_t)b.comps.size();
+    b.comps.push_back(c);
+    return B2_OK;
+}
+
+int Builder::add_gate(int kind, const uint32_t *in, size_t n, uint32_t output, uint32_t *cell) {
+    if (kind < K_AND || kind > K_XNOR) return B2_ERR_INVALID_ARG;
+    if (output >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    for (size_t i = 0; i < n; i++)
+        if (in[i] >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    if (n < 2) return B2_ERR_TOO_FEW_INPUTS;
+    for (size_t i = 0; i < n; i++)
+        if (width[in[i]] != width[output]) return B2_ERR_WIRE_WIDTH_MISMATCH;
+    return push(*this, (uint8_t)kind, in, n, 0, output, cell);
+}
+
+int Builder::add_not(uint32_t in, uint32_t output, uint32_t *cell) {
+    if (output >= width.size() || in >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    if (width[in] != width[output]) return B2_ERR_WIRE_WIDTH_MISMATCH;
+    return push(*this, K_NOT, &in, 1, 0, output, cell);
+}
+
+int Builder::add_mux(const uint32_t *in, size_t n, uint32_t select, uint32_t output, uint32_t *cell) {
+    if (output >= width.size() || select >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    for (size_t i = 0; i < n; i++)
+        if (in[i] >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    if (n < 2 || (n & (n - 1)) != 0) return B2_ERR_INVALID_INPUT_COUNT;
+    uint32_t k = 0;
+    while (((size_t)1 << k) < n) k++;
+    if (width[select] != k) return B2_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    for (size_t i = 0; i < n; i++)
+        if (width[in[i]] != width[output]) return B2_ERR_WIRE_WIDTH_MISMATCH;
+    return push(*this, K_MUX, in, n, select, output, cell);
+}
+
+// ---------------------------------------------------------------------------- compiler
+
+namespace {
+// A 1-bit gate before ordering. Inputs are bit-nets.
+struct BitGate {
+    uint8_t kind;
+    uint8_t nsel;
+    uint32_t in_off, n_in;  // into bit_inputs (mux: select bits first)
+    uint32_t out;           // bit-net
+    uint32_t level;
+};
+}  // namespace
+
+void compile(const Builder &b, Compiled &c) {
+    const uint32_t W = (uint32_t)b.width.size();
+    c.width = b.width;
+    c.bit_off.resize((size_t)W + 1);
+    uint32_t nb = 0;
+    for (uint32_t w = 0; w < W; w++) {
+        c.bit_off[w] = nb;
+        nb += b.width[w];
+    }
+    c.bit_off[W] = nb;
+
+    // ---- bit-blast
+    std::vector<BitGate> gates;
+    std::vector<uint32_t> bin;
+    size_t est = 0;
+    for (const Component &cp : b.comps) est += b.width[cp.output];
+    gates.reserve(est);
+    for (const Component &cp : b.comps) {
+        const uint32_t *in = b.inputs.data() + cp.in_off;
+        const uint32_t wout = b.width[cp.output];
+        for (uint32_t j = 0; j < wout; j++) {
+            BitGate g;
+            g.kind = cp.kind;
+            g.nsel = 0;
+            g.in_off = (uint32_t)bin.size();
+            g.out = c.bit_off[cp.output] + j;
+            g.level = 0;
+            if (cp.kind == K_MUX) {
+                const uint32_t k = b.width[cp.select];
+                g.nsel = (uint8_t)k;
+                for (uint32_t s = 0; s < k; s++) bin.push_back(c.bit_off[cp.select] + s);
+            }
+            for (uint32_t i = 0; i < cp.n_inputs; i++) bin.push_back(c.bit_off[in[i]] + j);
+            g.n_in = (uint32_t)bin.size() - g.in_off;
+            gates.push_back(g);
+        }
+    }
+    const uint32_t G = (uint32_t)gates.size();
+
+    // ---- drivers
+    const uint32_t NONE = 0xFFFFFFFFu;
+    std::vector<uint32_t> driver(nb, NONE);
+    c.multi_driver = false;
+    for (uint32_t g = 0; g < G; g++) {
+        if (driver[gates[g].out] != NONE) c.multi_driver = true;
+        else driver[gates[g].out] = g;
+    }
+    c.bit_driven.assign(nb, 0);
+    for (uint32_t i = 0; i < nb; i++) c.bit_driven[i] = driver[i] != NONE;
+
+    // ---- levelise (Kahn). consumers CSR over bit-nets that are gate driven.
+    std::vector<uint32_t> indeg(G, 0), cons_off((size_t)nb + 2, 0);
+    for (uint32_t g = 0; g < G; g++)
+        for (uint32_t i = 0; i < gates[g].n_in; i++) {
+            uint32_t bn = bin[gates[g].in_off + i];
+            if (driver[bn] != NONE) {
+                indeg[g]++;
+                cons_off[bn + 2]++;
+            }
+        }
+    for (uint32_t i = 0; i < nb; i++) cons_off[i + 2] += cons_off[i + 1];
+    std::vector<uint32_t> cons(cons_off[nb + 1]);
+    for (uint32_t g = 0; g < G; g++)
+        for (uint32_t i = 0; i < gates[g].n_in; i++) {
+            uint32_t bn = bin[gates[g].in_off + i];
+            if (driver[bn] != NONE) cons[cons_off[bn + 1]++] = g;
+        }
+    std::vector<uint32_t> queue;
+    queue.reserve(G);
+    for (uint32_t g = 0; g < G; g++)
+        if (indeg[g] == 0) {
+            gates[g].level = 1;
+            queue.push_back(g);
+        }
+    uint32_t depth = 0;
+    for (size_t h = 0; h < queue.size(); h++) {
+        const uint32_t g = queue[h];
+        depth = std::max(depth, gates[g].level);
+        // only the registered driver of a net propagates (multi-driver netlists never simulate)
+        if (driver[gates[g].out] != g) continue;
+        const uint32_t bn = gates[g].out;
+        for (uint32_t k = cons_off[bn]; k < cons_off[bn + 1]; k++) {
+            const uint32_t h2 = cons[k];
+            gates[h2].level = std::max(gates[h2].level, gates[g].level + 1);
+            if (--indeg[h2] == 0) queue.push_back(h2);
+        }
+    }
+    c.cyclic = queue.size() != G;
+    c.depth = c.cyclic ? 0 : depth;
+    if (c.cyclic)
+        for (auto &g : gates) g.level = 1;  // one pseudo-level: unit-delay evaluation only
+
+    // ---- order: class (2-input first), then level, then kind, then creation order (stable)
+    std::vector<uint32_t> order(G);
+    std::iota(order.begin(), order.end(), 0u);
+    auto is_wide = [&](uint32_t g) { return gates[g].kind == K_MUX || gates[g].n_in > 2; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        const bool wx = is_wide(x), wy = is_wide(y);
+        if (wx != wy) return !wx;
+        if (gates[x].level != gates[y].level) return gates[x].level < gates[y].level;
+        return gates[x].kind < gates[y].kind;
+    });
+
+    // ---- rows: sources first (in bit-net order), then gates in `order`
+    c.row_of_bit.assign(nb, 0);
+    uint32_t row = 0;
+    for (uint32_t i = 0; i < nb; i++)
+        if (driver[i] == NONE) c.row_of_bit[i] = row++;
+    c.n_src = row;
+    std::vector<uint32_t> gate_row(G);
+    for (uint32_t k = 0; k < G; k++) gate_row[order[k]] = c.n_src + k;
+    for (uint32_t i = 0; i < nb; i++)
+        if (driver[i] != NONE) c.row_of_bit[i] = gate_row[driver[i]];
+    c.n_rows = c.n_src + G;
+
+    // ---- SoA emission
+    uint32_t n2 = 0;
+    while (n2 < G && !is_wide(order[n2])) n2++;
+    c.fan0.resize(n2);
+    c.fan1.resize(n2);
+    c.kind2.resize(n2);
+    for (uint32_t k = 0; k < n2; k++) {
+        const BitGate &g = gates[order[k]];
+        c.kind2[k] = g.kind;
+        c.fan0[k] = c.row_of_bit[bin[g.in_off]];
+        c.fan1[k] = g.n_in > 1 ? c.row_of_bit[bin[g.in_off + 1]] : c.fan0[k];
+    }
+    const uint32_t nw = G - n2;
+    c.wide_kind.resize(nw);
+    c.wide_nsel.resize(nw);
+    c.wide_off.assign((size_t)nw + 1, 0);
+    c.wide_in.clear();
+    for (uint32_t k = 0; k < nw; k++) {
+        const BitGate &g = gates[order[n2 + k]];
+        c.wide_kind[k] = g.kind;
+        c.wide_nsel[k] = g.nsel;
+        c.wide_off[k] = (uint32_t)c.wide_in.size();
+        for (uint32_t i = 0; i < g.n_in; i++) c.wide_in.push_back(c.row_of_bit[bin[g.in_off + i]]);
+    }
+    c.wide_off[nw] = (uint32_t)c.wide_in.size();
+
+    // ---- level table
+    c.levels.clear();
+    const uint32_t n_levels = c.cyclic ? (G ? 1u : 0u) : depth;
+    c.levels.assign(n_levels, Level{0, 0, 0, 0});
+    {
+        uint32_t k = 0;
+        for (uint32_t l = 1; l <= n_levels; l++) {
+            c.levels[l - 1].g2_begin = k;
+            while (k < n2 && gates[order[k]].level == l) k++;
+            c.levels[l - 1].g2_end = k;
+        }
+        k = 0;
+        for (uint32_t l = 1; l <= n_levels; l++) {
+            c.levels[l - 1].wide_begin = k;
+            while (k < nw && gates[order[n2 + k]].level == l) k++;
+            c.levels[l - 1].wide_end = k;
+        }
+    }
+}
+
+}  // namespace b2

@@ -1,0 +1,68 @@
+// netlist.hpp — host-side builder and netlist compiler.
+//
+// Builder mirrors the validation surface of gsim::SimulatorBuilder as the reference uses it
+// (crates/digilogic_gsim/src/lib.rs:76-192; error variants lib.rs:55-66).  compile() is what
+// stands where SimulatorBuilder::build() (lib.rs:127) stood: it bit-blasts wires into 1-bit
+// rows, analyses drivers, levelises, sorts gates by (level, kind) and emits the SoA arrays the
+// kernels stream.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace b2 {
+
+enum Kind : uint8_t { K_AND = 0, K_OR = 1, K_XOR = 2, K_NAND = 3, K_NOR = 4, K_XNOR = 5, K_NOT = 6, K_MUX = 7 };
+
+struct Component {
+    uint8_t kind;
+    uint32_t n_inputs;  // data inputs
+    uint32_t in_off;    // into Builder::inputs
+    uint32_t select;    // mux only
+    uint32_t output;
+};
+
+struct Builder {
+    std::vector<uint8_t> width;
+    std::vector<Component> comps;
+    std::vector<uint32_t> inputs;
+
+    int add_wire(uint8_t w, uint32_t *out);
+    int wire_width(uint32_t wire, uint8_t *out) const;
+    int add_gate(int kind, const uint32_t *in, size_t n, uint32_t output, uint32_t *cell);
+    int add_not(uint32_t in, uint32_t output, uint32_t *cell);
+    int add_mux(const uint32_t *in, size_t n, uint32_t select, uint32_t output, uint32_t *cell);
+};
+
+// One level of the levelised order: 2-input gates [g2_begin, g2_end) and wide gates
+// [wide_begin, wide_end).  Output rows are implicit:
+//   row(2-input gate i) = n_src + i,   row(wide gate j) = n_src + n_g2 + j.
+struct Level {
+    uint32_t g2_begin, g2_end, wide_begin, wide_end;
+};
+
+struct Compiled {
+    // wires as the caller numbered them
+    std::vector<uint8_t> width;
+    std::vector<uint32_t> bit_off;     // wire -> first bit-net (size n_wires+1)
+    std::vector<uint32_t> row_of_bit;  // bit-net -> store row
+    std::vector<uint8_t> bit_driven;   // bit-net has a gate driver
+    uint32_t n_rows = 0, n_src = 0;
+    // one/two-input gates, in row order
+    std::vector<uint32_t> fan0, fan1;  // store rows
+    std::vector<uint8_t> kind2;
+    // wide gates (n-ary, mux slices), CSR over store rows; mux: first n_sel entries are select bits
+    std::vector<uint32_t> wide_off, wide_in;
+    std::vector<uint8_t> wide_kind, wide_nsel;
+    std::vector<Level> levels;         // acyclic: one per level (1..depth); cyclic: a single entry
+    uint32_t depth = 0;
+    bool cyclic = false, multi_driver = false;
+
+    uint32_t n_wires() const { return (uint32_t)width.size(); }
+    uint32_t n_g2() const { return (uint32_t)kind2.size(); }
+    uint32_t n_wide() const { return (uint32_t)wide_kind.size(); }
+};
+
+// Never fails on a validated Builder.
+void compile(const Builder &b, Compiled &out);
+
+}  // namespace b2

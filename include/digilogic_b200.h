@@ -1,0 +1,241 @@
+/*
+ * digilogic_b200.h — C ABI of the B200-native gate-level simulation engine.
+ *
+ * This is the drop-in boundary for the hot path of rj45/digilogic: everything the
+ * reference's engine adapter `GsimServer` (crates/digilogic_gsim/src/lib.rs:101-239)
+ * calls on the third-party crate gsim 1.1.4 has one entry point here, so that a
+ * `B200Server: SimServer` written like that file can stand behind
+ * `SimulationEngine::GsimCompute` (crates/digilogic/src/main.rs:312-318,373).
+ *
+ * Conventions: plain pointers and sizes only; caller-owned buffers; no exceptions or
+ * aborts cross this boundary — every failure is a return code.  There is NO CPU
+ * fallback: simulation entry points return B2_ERR_NO_DEVICE without a CUDA device.
+ *
+ * Value encoding (reference crates/digilogic/src/ui/palette.rs:326-341,
+ * crates/digilogic_core/src/components.rs:104-110): two planes per bit,
+ *   plane0 = value/state, plane1 = valid:  Z=(0,0)  X=(1,0)  0=(0,1)  1=(1,1).
+ * A "lane" is one independent stimulus vector (= one gsim `Simulator`); lane l lives in
+ * bit l%64 of 64-bit lane-word l/64 of every wire row.
+ */
+#ifndef DIGILOGIC_B200_H
+#define DIGILOGIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_builder b2_builder; /* replaces gsim::SimulatorBuilder (lib.rs:6,12) */
+typedef struct b2_sim b2_sim;         /* replaces gsim::Simulator        (lib.rs:7)    */
+typedef struct b2_server b2_server;   /* mirrors GsimServer              (lib.rs:16-22) */
+
+/* Gate kinds accepted by b2_add_gate (0..5), plus the ids used in bulk adds / reports. */
+enum b2_gate_kind { B2_AND = 0, B2_OR = 1, B2_XOR = 2, B2_NAND = 3, B2_NOR = 4, B2_XNOR = 5, B2_NOT = 6, B2_MUX = 7 };
+
+/* 1..7 are gsim's AddComponentError variants in the order the reference maps them
+   (crates/digilogic_gsim/src/lib.rs:55-66); >= 16 are this library's own. */
+enum b2_status {
+    B2_OK = 0,
+    B2_ERR_TOO_MANY_COMPONENTS = 1,
+    B2_ERR_INVALID_WIRE_ID = 2,
+    B2_ERR_WIRE_WIDTH_MISMATCH = 3,
+    B2_ERR_WIRE_WIDTH_INCOMPATIBLE = 4,
+    B2_ERR_OFFSET_OUT_OF_RANGE = 5,
+    B2_ERR_TOO_FEW_INPUTS = 6,
+    B2_ERR_INVALID_INPUT_COUNT = 7,
+    B2_ERR_NULL = 16,          /* a required pointer was NULL */
+    B2_ERR_INVALID_ARG = 17,
+    B2_ERR_NO_DEVICE = 18,     /* no CUDA device / kernels not loadable: there is no CPU path */
+    B2_ERR_CUDA = 19,          /* a CUDA call failed; see b2_last_error() */
+    B2_ERR_OUT_OF_MEMORY = 20,
+    B2_ERR_RANGE = 21,         /* lane-word / bit range outside the store */
+    B2_ERR_OUT_OF_WIRES = 22   /* add_wire returned None (-> ServerError::OutOfResources, lib.rs:138) */
+};
+
+/* gsim::SimulationRunResult (lib.rs:68-74). Run entry points return one of these, or
+   -(b2_status) on failure. */
+enum b2_run_result { B2_RUN_OK = 0, B2_RUN_MAX_STEPS_REACHED = 1, B2_RUN_CONFLICT = 2 };
+
+/* Thread-local text of the last B2_ERR_CUDA / B2_ERR_NO_DEVICE on this thread ("" if none). */
+const char *b2_last_error(void);
+/* Library version string. */
+const char *b2_version(void);
+/* Number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
+uint64_t b2_kernel_launches(void);
+
+/* ------------------------------------------------------------------------------------
+ * Builder — replaces gsim::SimulatorBuilder
+ * ---------------------------------------------------------------------------------- */
+
+/* SimulatorBuilder::default()  (lib.rs:12) */
+b2_builder *b2_builder_new(void);
+void b2_builder_free(b2_builder *b);
+
+/* SimulatorBuilder::add_wire(width) -> Option<WireId>  (lib.rs:135-139). width 1..255. */
+int b2_add_wire(b2_builder *b, uint8_t width, uint32_t *out_wire);
+/* Batch extension: n wires of one width with consecutive ids starting at *out_first. */
+int b2_add_wires(b2_builder *b, uint8_t width, uint32_t n, uint32_t *out_first);
+/* SimulatorBuilder::get_wire_width(wire)  (lib.rs:87-92,157-162,178-183) */
+int b2_builder_wire_width(const b2_builder *b, uint32_t wire, uint8_t *out_width);
+
+/* SimulatorBuilder::add_{and,or,xor,nand,nor,xnor}_gate(inputs, output) -> Result<ComponentId, AddComponentError>
+   (lib.rs:76-99,141-146).  kind = B2_AND..B2_XNOR; n >= 2 inputs, all of the output's width. */
+int b2_add_gate(b2_builder *b, int kind, const uint32_t *inputs, size_t n, uint32_t output, uint32_t *out_cell);
+/* SimulatorBuilder::add_not_gate(input, output)  (lib.rs:148-167) */
+int b2_add_not(b2_builder *b, uint32_t input, uint32_t output, uint32_t *out_cell);
+/* SimulatorBuilder::add_multiplexer(inputs, select, output)  (lib.rs:169-192): n = 2^k data
+   inputs of the output's width, select of width k. */
+int b2_add_mux(b2_builder *b, const uint32_t *inputs, size_t n, uint32_t select, uint32_t output, uint32_t *out_cell);
+/* Batch extension: n one- or two-input gates at once (kinds[i] in B2_AND..B2_NOT; in1 ignored
+   for B2_NOT), validated exactly like the single calls; stops at the first error. */
+int b2_add_gates2(b2_builder *b, const uint8_t *kinds, const uint32_t *in0, const uint32_t *in1, const uint32_t *out, size_t n);
+
+/* SimulatorBuilder::build()  (lib.rs:123-133): compiles the netlist (bit-blast, driver
+   analysis, levelisation, kind/level-sorted SoA arrays).  Like `std::mem::take(builder).build()`
+   it leaves *b an empty default builder.  Host-only: no CUDA call is made until lanes are
+   allocated.  Returns NULL only on allocation failure or b == NULL. */
+b2_sim *b2_build(b2_builder *b);
+void b2_sim_free(b2_sim *s);
+
+/* ------------------------------------------------------------------------------------
+ * Simulator — replaces gsim::Simulator
+ * ---------------------------------------------------------------------------------- */
+
+typedef struct b2_sim_info {
+    uint32_t n_wires;       /* wires as added by the caller */
+    uint32_t n_rows;        /* 1-bit rows of the wire-state store (sources first, then gate outputs) */
+    uint32_t n_sources;     /* rows without a gate driver (primary inputs and floating nets) */
+    uint32_t n_gates2;      /* 1-bit gates with one or two inputs (fast kernels) */
+    uint32_t n_gates_wide;  /* 1-bit n-ary gates and multiplexer slices (CSR kernel) */
+    uint32_t depth;         /* number of levels; 0 when cyclic */
+    uint32_t cyclic;        /* 1 if the netlist has a combinational feedback loop */
+    uint32_t multi_driver;  /* 1 if some wire has two or more gate drivers (every run conflicts) */
+    uint64_t n_lanes;       /* lanes allocated (0 before b2_sim_set_lanes / first use) */
+    uint32_t lane_words;    /* 64-lane words per row in use */
+    uint32_t row_stride;    /* allocated words per row */
+    uint64_t store_bytes;   /* device bytes held by this simulator */
+    uint32_t last_mode;     /* 0 none, 1 levelised, 2 unit-delay (Jacobi) */
+    uint32_t reserved;
+    uint64_t last_applications; /* whole-netlist evaluations made by the last run */
+} b2_sim_info;
+
+int b2_sim_get_info(const b2_sim *s, b2_sim_info *out);
+
+/* Simulator::get_wire_width(wire)  (lib.rs:228) */
+int b2_wire_width(const b2_sim *s, uint32_t wire, uint8_t *out_width);
+
+/* Device / stream selection (before the first call that touches the device). `stream` is a
+   cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = a private stream. */
+int b2_sim_set_device(b2_sim *s, int device);
+int b2_sim_set_stream(b2_sim *s, void *stream);
+/* Block until everything queued by this simulator has finished. */
+int b2_sim_synchronize(b2_sim *s);
+
+/* Batch extension: allocate the HBM-resident wire-state store for n_lanes independent
+   stimulus lanes (default 1 = gsim behaviour).  Resets all lanes to the cold initial state
+   (every wire and drive High-Z). */
+int b2_sim_set_lanes(b2_sim *s, uint64_t n_lanes);
+/* Largest n_lanes whose store would fit in `bytes` of device memory (0 = use currently free memory). */
+uint64_t b2_sim_max_lanes(const b2_sim *s, uint64_t bytes);
+
+/* LogicState::from_bit_planes(&p0[..words], &p1[..words]) + Simulator::set_wire_drive(wire, &state)
+   (lib.rs:194-214).  plane words are little-endian u32, missing words are High-Z.  With more
+   than one lane the drive is applied to every lane. */
+int b2_set_wire_drive(b2_sim *s, uint32_t wire, const uint32_t *plane0, const uint32_t *plane1, size_t words);
+
+/* Simulator::run_sim(max_steps)  (lib.rs:216-219).  Returns b2_run_result of lane 0 when one
+   lane is allocated; with more lanes the worst result over all lanes (conflict > max-steps > ok). */
+int b2_run_sim(b2_sim *s, uint64_t max_steps);
+
+/* Simulator::get_wire_state(wire) + LogicState::to_bit_planes(width)  (lib.rs:228-230): lane 0.
+   Writes ceil(width/32) words per plane; `words` is the capacity of each buffer. */
+int b2_get_wire_state(b2_sim *s, uint32_t wire, uint32_t *plane0, uint32_t *plane1, size_t words);
+
+/* ---- batch-lane extension (no reference counterpart: gsim has one lane per Simulator) ---- */
+
+/* Drive bit `bit` of `wire` in lanes [64*lane_word0, 64*(lane_word0+n_words)) from host words. */
+int b2_set_wire_drive_lanes(b2_sim *s, uint32_t wire, uint32_t bit, uint32_t lane_word0, uint32_t n_words,
+                            const uint64_t *value, const uint64_t *valid);
+/* Drive bit 0 of n wires for all lane-words from host planes laid out [n][src_stride] (one
+   staged copy + one scatter kernel).  value/valid should be pinned for an asynchronous copy. */
+int b2_set_drives_lanes(b2_sim *s, const uint32_t *wires, uint32_t n, const uint64_t *value, const uint64_t *valid,
+                        size_t src_stride_words);
+/* Counter-based stimulus generated on the device: input i (position in `wires`), global
+   lane-word w = lane_word_base + local word:
+     value = splitmix64(seed ^ (i+1)*0x9E3779B97F4A7C15 ^ w*0xD1B54A32D192ED03)
+     mode 0: valid = ~0 (two-valued);  mode 1: valid = splitmix64(value ^ 1) | splitmix64(value ^ 2)
+   (about 25 % of the lanes not valid: X where value=1, Z where value=0). */
+int b2_fill_stimulus(b2_sim *s, const uint32_t *wires, uint32_t n, uint64_t seed, uint64_t lane_word_base, int mode);
+
+/* run_sim(max_steps) on every lane.  conflict / unsettled (each lane_words long, may be NULL)
+   receive the lanes that ended in Err(conflict) / MaxStepsReached.  Returns the worst result. */
+int b2_run_sim_lanes(b2_sim *s, uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled);
+/* Same, but nothing is copied to the host and the call does not wait for the device when the
+   levelised path is taken (the returned result is then B2_RUN_OK if no wire can conflict). */
+int b2_run_sim_lanes_async(b2_sim *s, uint64_t max_steps);
+
+/* Read bit `bit` of `wire` for lane-words [lane_word0, lane_word0+n_words) into host buffers. */
+int b2_get_wire_lanes(b2_sim *s, uint32_t wire, uint32_t bit, uint32_t lane_word0, uint32_t n_words,
+                      uint64_t *value, uint64_t *valid);
+/* Gather bit 0 of n wires, all lane-words, into DEVICE planes laid out [n][dst_stride_words]
+   (e.g. a torch tensor that is then all-gathered with NCCL). */
+int b2_gather_wires_device(b2_sim *s, const uint32_t *wires, uint32_t n, uint64_t *dev_value, uint64_t *dev_valid,
+                           size_t dst_stride_words);
+/* Same into HOST planes [n][dst_stride_words] (staged through a device buffer, one copy per plane). */
+int b2_gather_wires_host(b2_sim *s, const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid,
+                         size_t dst_stride_words);
+
+/* Bulk read-back in the netcode `SimState` layout (replaces the per-net get_net_state +
+   SimState::push_net loop of crates/digilogic_netcode/src/server.rs:375-383 and
+   src/lib.rs:241-270): lane 0 of `n` wires appended LSB-first with no padding between
+   nets.  plane buffers must hold bit_len/8 + 1 bytes (the "at least one unused bit"
+   invariant, lib.rs:168).  *out_bit_len receives the total bit count. */
+int b2_pack_sim_state(b2_sim *s, const uint32_t *wires, uint32_t n, uint8_t *plane0, uint8_t *plane1, size_t cap_bytes,
+                      uint64_t *out_bit_len);
+
+/* ------------------------------------------------------------------------------------
+ * Server — mirrors `impl SimServer for GsimServer` (crates/digilogic_gsim/src/lib.rs:101-239;
+ * trait at crates/digilogic_netcode/src/server.rs:43-102).  Return value: 0 = Ok(..), else
+ * 1 + the ordinal of the ServerError variant (crates/digilogic_netcode/src/lib.rs:67-85).
+ * ---------------------------------------------------------------------------------- */
+enum b2_server_error {
+    B2S_OK = 0,
+    B2S_UNSUPPORTED = 1, B2S_OTHER = 2, B2S_INVALID_STATE = 3, B2S_OUT_OF_RESOURCES = 4, B2S_INVALID_NET_ID = 5,
+    B2S_WIDTH_MISMATCH = 6, B2S_WIDTH_INCOMPATIBLE = 7, B2S_OUT_OF_RANGE = 8, B2S_INVALID_INPUT_COUNT = 9,
+    B2S_MAX_STEPS_REACHED = 10, B2S_DRIVER_CONFLICT = 11
+};
+
+b2_server *b2_server_new(void);                                   /* GsimServer::default() */
+void b2_server_free(b2_server *sv);
+uint64_t b2_server_max_clients(b2_server *sv);                    /* lib.rs:105-107 */
+void b2_server_client_connected(b2_server *sv, uint64_t client);  /* lib.rs:109-111 */
+void b2_server_client_disconnected(b2_server *sv, uint64_t client); /* lib.rs:113-115 */
+int b2_server_begin_build(b2_server *sv, uint64_t client);        /* lib.rs:117-121 */
+int b2_server_end_build(b2_server *sv, uint64_t client);          /* lib.rs:123-133 */
+int b2_server_add_net(b2_server *sv, uint64_t client, uint8_t width, uint32_t *out_net); /* lib.rs:135-139 */
+/* gate_impl!(add_*_gate) lib.rs:76-99: kind = B2_AND..B2_XNOR */
+int b2_server_add_gate(b2_server *sv, uint64_t client, int kind, uint8_t width, const uint32_t *inputs, size_t n,
+                       uint32_t output, uint32_t *out_cell);
+int b2_server_add_not_gate(b2_server *sv, uint64_t client, uint8_t width, uint32_t input, uint32_t output,
+                           uint32_t *out_cell);           /* lib.rs:148-167 */
+/* inputs[0] is the select net, inputs[1..] the data nets (lib.rs:185-187) */
+int b2_server_add_mux(b2_server *sv, uint64_t client, uint8_t width, const uint32_t *inputs, size_t n, uint32_t output,
+                      uint32_t *out_cell);                /* lib.rs:169-192 */
+int b2_server_set_net_drive(b2_server *sv, uint64_t client, uint32_t net, const uint8_t *bit_plane_0, size_t len0,
+                            const uint8_t *bit_plane_1, size_t len1); /* lib.rs:194-214 */
+int b2_server_eval(b2_server *sv, uint64_t client, uint64_t max_steps); /* lib.rs:216-219 */
+/* lib.rs:221-238: the two returned plane pointers point at the server's 32-byte scratch planes, valid until the
+   next call on this server; bytes past ceil(width/8) are stale. */
+int b2_server_get_net_state(b2_server *sv, uint64_t client, uint32_t net, uint8_t *out_width, const uint8_t **plane0,
+                            const uint8_t **plane1);
+/* Bulk replacement for Adapter::sim_state (server.rs:375-383): all `n` nets of the client in
+   SimState layout, see b2_pack_sim_state. */
+int b2_server_sim_state(b2_server *sv, uint64_t client, const uint32_t *nets, uint32_t n, uint8_t *plane0, uint8_t *plane1,
+                        size_t cap_bytes, uint64_t *out_bit_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIGILOGIC_B200_H */
