@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — gate-lane evaluations per second of the B200 engine on BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE config 3 — synthetic random combinational DAG, 1M gates,
+depth 200, fan-in 2, 4096 inputs, 2^24 stimulus lanes per GPU, 4-state engine with two-valued
+stimulus generated on the device from (seed, input, global lane-word).  One step = one settle
+(run_sim to the fixed point) of every lane of the batch, tile by tile, plus extraction of the
+1024 designated output rows.  At N GPUs every rank runs the same per-GPU batch on its own lane
+range (weak scaling) and the packed output planes are all-gathered once per step with NCCL.
+
+value      = G * L_total / max-over-ranks device time                (gate-lane evals/s)
+e2e        = the same through the C ABI with HOST buffers: pinned-host stimulus planes in,
+             output planes out, copies inside the timed region
+roofline   = k_eval2 (the per-level gate kernel): 48 algorithmic bytes per gate per 64-lane
+             word / its average launch duration, against MEASURED_PEAKS.json
+cpu_baseline = the scalar event-driven gsim restatement (oracle/gsim_oracle.c, "port") on the
+             host cores over a bounded lane sample of the same netlist
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gate_lane_evals_per_s"
+UNIT = "gate-lane evals/s"
+SEED = 0xD1610003
+ALGO_BYTES_PER_GATE_WORD = 48.0   # 2 fan-ins x 2 planes x 8 B read + 2 planes x 8 B written
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gates", type=int, default=1_000_000)
+    ap.add_argument("--depth", type=int, default=200)
+    ap.add_argument("--inputs", type=int, default=4096)
+    ap.add_argument("--outputs", type=int, default=1024)
+    ap.add_argument("--lanes", type=int, default=1 << 24, help="stimulus lanes per GPU")
+    ap.add_argument("--tile-words", type=int, default=4096, help="64-lane words resident per tile")
+    ap.add_argument("--max-steps", type=int, default=10_000)
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-lanes-per-core", type=int, default=8)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_netlist(args):
+    from digilogic_b200 import netgen
+    return netgen.random_dag(n_gates=args.gates, depth=args.depth, n_inputs=args.inputs, n_outputs=args.outputs, seed=SEED)
+
+
+def config_dict(args, n_gpus, extra=None):
+    cfg = {
+        "workload": f"BASELINE config 3: random combinational DAG, {args.gates} gates, depth {args.depth}, fan-in 2, "
+                    f"{args.inputs} inputs, {args.lanes} lanes per GPU (4-state engine, two-valued device-generated stimulus)",
+        "gates": args.gates, "depth": args.depth, "inputs": args.inputs, "outputs": args.outputs,
+        "lanes_per_gpu": args.lanes, "lanes_total": args.lanes * n_gpus, "tile_words": args.tile_words,
+        "max_steps": args.max_steps, "seed": hex(SEED),
+        "cache": "working set per tile (wire store, GBs) exceeds the 126 MB L2; no flush needed",
+        "parallelism": f"lane-sharded x{n_gpus}, full netlist replica per GPU, one NCCL all-gather of output planes per step",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ----------------------------------------------------------------------------- CPU arms
+
+def cpu_port_run(gen, n_lanes, threads, max_steps):
+    """Scalar event-driven gsim restatement (oracle/, the checker) on `n_lanes` lanes of the
+    workload.  Returns (seconds, gate-lane evals/s)."""
+    import oracle
+    from digilogic_b200 import netgen
+    ob = gen.emit(oracle.Builder())
+    lanes = oracle.Lanes(ob, n_lanes)
+    words = (n_lanes + 63) // 64
+    v, m = netgen.stimulus_words(SEED, len(gen.inputs), words, 0, 0)
+    for i, w in enumerate(gen.inputs):
+        lanes.set_drive(int(w), v[i], m[i])
+    t0 = time.perf_counter()
+    status, _, _ = lanes.run(max_steps, threads=threads)
+    dt = time.perf_counter() - t0
+    assert (status == 0).all()
+    return dt, gen.n_gates * n_lanes / dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  gsim 1.1.4 itself cannot
+    be built here (Rust crate, not vendored, no cargo), so this is the oracle port on all host
+    cores, on a bounded lane sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    gen = build_netlist(args)
+    n_lanes = max(cores * max(args.cpu_lanes_per_core // 2, 1), 1)
+    times = []
+    for i in range(args.warmup + args.steps):
+        if i < args.warmup and i > 0:
+            continue  # one warm-up pass is enough to fault the netlist in; CPU passes take seconds
+        dt, _ = cpu_port_run(gen, n_lanes, cores, args.max_steps)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = gen.n_gates * n_lanes * len(times) / total
+    sample = f"{n_lanes} lanes of the {args.lanes}-lane batch per step, {cores} threads (one simulator per lane)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 bit-planes (CPU: u32 atoms)", "data": "synthetic",
+        "config": config_dict(args, args.gpus, {"note": "CPU restatement of gsim 1.1.4 (oracle port), not the Rust crate"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from digilogic_b200 import SimulatorBuilder, SimulationRunResult
+    from digilogic_b200.batch import BatchRunner, gather_output_planes, reduce_worst, shard_words
+    from digilogic_b200.gsim import kernel_launches
+
+    gen = build_netlist(args)
+    t0 = time.perf_counter()
+    sim = gen.emit(SimulatorBuilder()).build()
+    compile_s = time.perf_counter() - t0
+    sim.set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    sim.set_stream(stream.cuda_stream)
+
+    words_local = args.lanes // 64
+    total_words = words_local * world
+    w_begin, w_end = shard_words(total_words, world, rank)
+    tile = min(args.tile_words, words_local)
+    assert words_local % tile == 0
+    runner = BatchRunner(sim, gen.inputs, gen.outputs, tile, args.max_steps)
+    info = sim.info
+    n_out = len(gen.outputs)
+    out_v = torch.zeros((n_out, words_local), dtype=torch.int64, device=dev)
+    out_m = torch.zeros_like(out_v)
+
+    settle_events = []
+
+    def rec(which):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        settle_events.append(ev)
+
+    def step(record=False):
+        worst = runner.run_generated(w_begin, words_local, SEED, 0, out_v, out_m, 0, rec if record else None)
+        if world > 1:
+            gv, gm = gather_output_planes(out_v, out_m, world)
+            worst = reduce_worst(worst, dev)
+            return worst, gv, gm
+        return worst, out_v, out_m
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        worst, gv, gm = step()
+    barrier()
+    assert worst == SimulationRunResult.Ok
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = kernel_launches()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        worst, gv, gm = step(record=True)
+    e1.record(stream)
+    barrier()
+    launches = kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    settle_ms = sum(settle_events[i].elapsed_time(settle_events[i + 1]) for i in range(0, len(settle_events), 2))
+
+    # a checksum of the outputs, so that the timed work is observable (and comparable across N)
+    checksum = int((gv.to(torch.int64).sum() ^ gm.to(torch.int64).sum()).item()) & 0xFFFFFFFFFFFFFFFF
+
+    gate_lane_evals = float(args.gates) * args.lanes * world * args.steps
+    value = gate_lane_evals / (ms * 1e-3)
+
+    # roofline of the dominant kernel (k_eval2, one launch per level per tile)
+    n_tiles = words_local // tile
+    eval_launches = n_tiles * info.depth * args.steps
+    avg_launch_s = settle_ms * 1e-3 / eval_launches
+    gate_words_per_launch = (args.gates / info.depth) * info.row_stride
+    algo_bytes_per_launch = ALGO_BYTES_PER_GATE_WORD * gate_words_per_launch
+    peak, peak_kind = load_peaks()
+    achieved = algo_bytes_per_launch / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "kernel": "k_eval2<4,false>",
+                "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
+                "launches_timed": eval_launches}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path):
+        try:
+            with open(traffic_path) as f:
+                tj = json.load(f)
+            if tj.get("tile_words") == tile and tj.get("gates") == args.gates:
+                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words_local, w_begin, barrier)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_cpu_lanes = cores * args.cpu_lanes_per_core
+        dt, v = cpu_port_run(gen, n_cpu_lanes, cores, args.max_steps)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_cpu_lanes} of the {args.lanes} lanes, {dt:.1f} s, scalar event-driven gsim restatement "
+                         f"(oracle/gsim_oracle.c), one simulator per lane, {cores} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 bit-planes (value+valid)", "data": "synthetic",
+            "config": config_dict(args, world, {"tiles_per_step": n_tiles, "row_stride_words": info.row_stride,
+                                                "store_bytes": info.store_bytes, "compile_s": round(compile_s, 3)}),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "settle_ms_per_step": settle_ms / args.steps, "output_checksum": f"{checksum:#018x}",
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words_local, w_begin, barrier):
+    """Same metric through the C ABI with host buffers (b2_set_drives_lanes / b2_gather_wires_host)."""
+    n_in, n_out = len(gen.inputs), len(gen.outputs)
+    # host stimulus = the same counter-based words, produced once on the device and copied out
+    # before the timed region (host-side numpy generation of 2 x 8.6 GB would take minutes)
+    try:
+        hin_v = torch.empty((n_in, words_local), dtype=torch.int64, pin_memory=True)
+        hin_m = torch.empty((n_in, words_local), dtype=torch.int64, pin_memory=True)
+        hout_v = torch.empty((n_out, words_local), dtype=torch.int64, pin_memory=True)
+        hout_m = torch.empty((n_out, words_local), dtype=torch.int64, pin_memory=True)
+    except Exception as ex:  # not enough pinnable host memory on this box
+        return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
+    tile = runner.tile_words
+    for w0 in range(0, words_local, tile):
+        sim.fill_stimulus(gen.inputs, SEED, lane_word_base=w_begin + w0, mode=0)
+        # b2_fill_stimulus writes the drive rows; read them back through a settle-free path:
+        # run once so the source rows carry the drives, then gather the input rows
+        sim.run_sim_lanes_async(args.max_steps)
+        sim.gather_wires_ptr(gen.inputs, hin_v.data_ptr() + 8 * w0, hin_m.data_ptr() + 8 * w0, words_local, device=False)
+    inv, inm, outv, outm = hin_v.numpy(), hin_m.numpy(), hout_v.numpy(), hout_m.numpy()
+    worst = runner.run_host(inv, inm, outv, outm)  # warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.e2e_steps):
+        worst = runner.run_host(inv, inm, outv, outm)
+        if world > 1:
+            dv, dm = hout_v.to(dev, non_blocking=True), hout_m.to(dev, non_blocking=True)
+            from digilogic_b200.batch import gather_output_planes
+            gather_output_planes(dv, dm, world)
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = max(e0.elapsed_time(e1), wall * 1e3)  # host-side copies are part of the path: take the longer clock
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = float(args.gates) * args.lanes * world * args.e2e_steps / (ms * 1e-3)
+    return {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(n_in * words_local * 16),
+            "d2h_bytes_per_step": int(n_out * words_local * 16), "ms_per_step": ms / args.e2e_steps, "steps": args.e2e_steps,
+            "result": int(worst), "host_checksum": f"{int(outv.sum() ^ outm.sum()) & 0xFFFFFFFFFFFFFFFF:#018x}"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,124 @@
+"""Lane-tiled batch runs and stimulus-sharded multi-GPU runs.
+
+A batch of L stimulus lanes is L independent gsim simulators of one netlist.  One GPU holds a
+full netlist replica and a wire-state store of `tile_words` 64-lane words; the batch is
+processed tile by tile (stimulus in -> settle -> designated output rows out).  Across GPUs the
+lane-words are split into contiguous ranges, one per rank, with no traffic between GPUs until
+the packed output planes are all-gathered once at the end (NCCL over NVLink; `gloo` in the CPU
+tests).  torch is used for device buffers, streams and the collective only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .gsim import Simulator, SimulationRunResult
+
+
+def shard_words(total_words: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous lane-word range [begin, end) owned by `rank` (equal ranges; total must divide)."""
+    if total_words % world_size:
+        raise ValueError(f"{total_words} lane-words do not split evenly over {world_size} ranks")
+    per = total_words // world_size
+    return rank * per, (rank + 1) * per
+
+
+def plan_tiles(n_words: int, tile_words: int) -> list[tuple[int, int]]:
+    """[(first_word, n_words)] tiles covering n_words; the last tile may be short."""
+    return [(w, min(tile_words, n_words - w)) for w in range(0, n_words, tile_words)]
+
+
+def choose_tile_words(sim: Simulator, n_words: int, budget_bytes: int, unit_delay: bool = False) -> int:
+    """Largest tile (multiple of 512 words where possible) whose store fits the byte budget."""
+    info = sim.info
+    per_word = (info.n_rows * (2 if unit_delay else 1) + info.n_sources) * 16 + 64
+    t = max(int(budget_bytes // per_word), 1)
+    if t >= 512:
+        t -= t % 512
+    return min(t, n_words)
+
+
+@dataclass
+class BatchResult:
+    value: "object"        # [n_outputs, words_local] device tensor (uint64 bit pattern in int64) or numpy array
+    valid: "object"
+    worst: SimulationRunResult
+    words: int
+
+
+class BatchRunner:
+    """Runs a lane batch through one simulator replica, tile by tile."""
+
+    def __init__(self, sim: Simulator, inputs, outputs, tile_words: int, max_steps: int = 10_000):
+        self.sim = sim
+        self.inputs = np.ascontiguousarray(inputs, np.uint32)
+        self.outputs = np.ascontiguousarray(outputs, np.uint32)
+        self.tile_words = int(tile_words)
+        self.max_steps = int(max_steps)
+        sim.set_lanes(self.tile_words * 64)
+        self.run_seconds_events = []   # (start, end) torch events around the settle calls, if requested
+
+    # -- device-resident stimulus (generated on the GPU from the global lane-word index)
+    def run_generated(self, word_begin: int, n_words: int, seed: int, mode: int, out_value, out_valid,
+                      out_word0: int = 0, record_events=None) -> SimulationRunResult:
+        """out_value/out_valid: device tensors [n_outputs, >= out_word0 + n_words] (int64 storage)."""
+        assert n_words % self.tile_words == 0, "batch must be a whole number of tiles"
+        worst = SimulationRunResult.Ok
+        stride = out_value.stride(0)
+        base_v, base_m = out_value.data_ptr(), out_valid.data_ptr()
+        for w0, _ in plan_tiles(n_words, self.tile_words):
+            self.sim.fill_stimulus(self.inputs, seed, lane_word_base=word_begin + w0, mode=mode)
+            if record_events is not None:
+                record_events("start")
+            r = self.sim.run_sim_lanes_async(self.max_steps)
+            if record_events is not None:
+                record_events("end")
+            worst = max(worst, r)
+            off = (out_word0 + w0) * 8
+            self.sim.gather_wires_ptr(self.outputs, base_v + off, base_m + off, stride, device=True)
+        return worst
+
+    # -- host stimulus through the C ABI (end-to-end path: H2D copies and D2H read-back included)
+    def run_host(self, in_value, in_valid, out_value, out_valid) -> SimulationRunResult:
+        """in_*: host arrays [n_inputs, n_words]; out_*: host arrays [n_outputs, n_words] (numpy
+        views of pinned memory for asynchronous copies)."""
+        n_words = in_value.shape[1]
+        assert n_words % self.tile_words == 0
+        worst = SimulationRunResult.Ok
+        in_stride, out_stride = in_value.strides[0] // 8, out_value.strides[0] // 8
+        for w0, _ in plan_tiles(n_words, self.tile_words):
+            self.sim.set_drives_lanes_ptr(self.inputs, in_value.ctypes.data + 8 * w0, in_valid.ctypes.data + 8 * w0, in_stride)
+            r = self.sim.run_sim_lanes_async(self.max_steps)
+            worst = max(worst, r)
+            self.sim.gather_wires_ptr(self.outputs, out_value.ctypes.data + 8 * w0, out_valid.ctypes.data + 8 * w0,
+                                      out_stride, device=False)
+        return worst
+
+
+def gather_output_planes(local_value, local_valid, world_size: int):
+    """All-gather of the packed output planes: [n_out, words_local] per rank ->
+    [world_size, n_out, words_local] (rank-major = lane-word order, since ranks own contiguous
+    lane-word ranges).  NCCL on GPU tensors, gloo on CPU tensors."""
+    import torch
+    import torch.distributed as dist
+
+    if world_size == 1:
+        return local_value.unsqueeze(0), local_valid.unsqueeze(0)
+    gv = torch.empty((world_size,) + tuple(local_value.shape), dtype=local_value.dtype, device=local_value.device)
+    gm = torch.empty_like(gv)
+    dist.all_gather_into_tensor(gv, local_value.contiguous())
+    dist.all_gather_into_tensor(gm, local_valid.contiguous())
+    return gv, gm
+
+
+def reduce_worst(worst: SimulationRunResult, device) -> SimulationRunResult:
+    """MAX all-reduce of the run result (conflict > max-steps > ok) over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return worst
+    t = torch.tensor([int(worst)], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return SimulationRunResult(int(t.item()))
