@@ -214,7 +214,8 @@ def run_b200(args):
     sim = gen.emit(SimulatorBuilder()).build()
     compile_s = time.perf_counter() - t0
     sim.set_device(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # every engine launch and every timing event is on this stream
+    torch.cuda.set_stream(stream)
     sim.set_stream(stream.cuda_stream)
 
     words_local = args.lanes // 64

@@ -451,7 +451,7 @@ Engine::Engine(Compiled &&net) : net_(std::move(net)) {}
 Engine::~Engine() {
     if (device_ready_) {
         cudaSetDevice(device_);
-        if (stream_) cudaStreamSynchronize(ST);
+        cudaStreamSynchronize(ST);
         free_store();
         cudaFree(d_fan0_);
         cudaFree(d_fan1_);
@@ -493,6 +493,7 @@ void Engine::free_store() {
     stage_words_ = 0;
     d_rows_ = nullptr;
     rows_cap_ = 0;
+    rows_key_ = ptrs_key_ = 0;
     d_pack_ = nullptr;
     pack_cap_ = 0;
     extra_slot_.clear();
@@ -508,18 +509,16 @@ int Engine::set_device(int device) {
 }
 
 int Engine::set_stream(void *stream) {
-    if (device_ready_ && stream_ && stream != stream_) CU_TRY(cudaStreamSynchronize(ST));
+    // The handle is used as given; 0 is CUDA's legacy default stream.  A private stream is
+    // created only when no stream was ever set.
+    if (device_ready_ && stream_set_ && stream != stream_) CU_TRY(cudaStreamSynchronize(ST));
     if (own_stream_ && stream_) {
+        cudaStreamSynchronize(ST);
         cudaStreamDestroy(ST);
         own_stream_ = false;
     }
     stream_ = stream;
-    if (!stream_ && device_ready_) {
-        cudaStream_t s;
-        CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-        stream_ = s;
-        own_stream_ = true;
-    }
+    stream_set_ = true;
     return B2_OK;
 }
 
@@ -560,11 +559,12 @@ int Engine::ensure_device() {
         cudaGetLastError();
         return B2_ERR_NO_DEVICE;
     }
-    if (!stream_) {
+    if (!stream_set_) {
         cudaStream_t s;
         CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         stream_ = s;
         own_stream_ = true;
+        stream_set_ = true;
     }
     int rc;
     if ((rc = upload(&d_fan0_, net_.fan0))) return rc;
@@ -727,6 +727,7 @@ int Engine::drive_target(uint32_t bitnet, uint64_t **val, uint64_t **vld) {
             CU_TRY(cudaMalloc((void **)&d_extra_rows_, (size_t)cap * 4));
             xdrv_val_ = nv;
             xdrv_vld_ = nm;
+            ptrs_key_ = 0;
             store_bytes_ += (size_t)(cap - extra_cap_) * stride_ * 16;
             extra_cap_ = cap;
         }
@@ -754,6 +755,7 @@ int Engine::set_wire_drive(uint32_t wire, const uint32_t *p0, const uint32_t *p1
     }
     // row pointer tables for the bits of this wire (two passes: the first may grow the extra store)
     if ((rc = ensure_rows_buffer(width))) return rc;
+    rows_key_ = ptrs_key_ = 0;
     std::vector<uint64_t *> tv(width), tm(width);
     for (int pass = 0; pass < 2; pass++)
         for (uint32_t j = 0; j < width; j++)
@@ -784,29 +786,43 @@ int Engine::set_wire_drive_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint3
     return B2_OK;
 }
 
-// Uploads row indices (store rows) or drive row pointer tables for bit 0 of `wires`.
+static uint64_t hash_wires(const uint32_t *wires, uint32_t n) {
+    uint64_t h = 0xCBF29CE484222325ull ^ n;
+    for (uint32_t i = 0; i < n; i++) h = (h ^ wires[i]) * 0x100000001B3ull;
+    return h | 1;  // never 0 (0 = nothing cached)
+}
+
+// Uploads row indices (store rows) or drive row pointer tables for bit 0 of `wires`.  The last
+// list of each kind stays cached on the device, so a tile loop re-using the same input and
+// output lists neither re-uploads nor synchronises.
 int Engine::upload_rows(const uint32_t *wires, uint32_t n, bool drive_rows) {
+    const uint32_t cap_before = rows_cap_;
     int rc = ensure_rows_buffer(n);
     if (rc) return rc;
+    if (rows_cap_ != cap_before) rows_key_ = ptrs_key_ = 0;
     for (uint32_t i = 0; i < n; i++)
         if (wires[i] >= net_.n_wires()) return B2_ERR_INVALID_WIRE_ID;
+    const uint64_t key = hash_wires(wires, n);
     if (!drive_rows) {
+        if (rows_key_ == key) return B2_OK;
         std::vector<uint32_t> rows(n);
         for (uint32_t i = 0; i < n; i++) rows[i] = net_.row_of_bit[net_.bit_off[wires[i]]];
         CU_TRY(cudaMemcpyAsync(d_rows_, rows.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ST));
         CU_TRY(cudaStreamSynchronize(ST));
+        rows_key_ = key;
     } else {
+        if (ptrs_key_ == key) return B2_OK;
         std::vector<uint64_t *> tv(n), tm(n);
-        for (uint32_t i = 0; i < n; i++)
-            if ((rc = drive_target(net_.bit_off[wires[i]], &tv[i], &tm[i]))) return rc;
-        // drive_target may have re-allocated the extra store: resolve again so every pointer is current
-        for (uint32_t i = 0; i < n; i++)
-            if ((rc = drive_target(net_.bit_off[wires[i]], &tv[i], &tm[i]))) return rc;
+        // two passes: the first may grow the extra store and move earlier rows
+        for (int pass = 0; pass < 2; pass++)
+            for (uint32_t i = 0; i < n; i++)
+                if ((rc = drive_target(net_.bit_off[wires[i]], &tv[i], &tm[i]))) return rc;
         const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
         uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
         CU_TRY(cudaMemcpyAsync(d_tv, tv.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ST));
         CU_TRY(cudaMemcpyAsync(d_tm, tm.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ST));
         CU_TRY(cudaStreamSynchronize(ST));
+        ptrs_key_ = key;
     }
     return B2_OK;
 }
@@ -1123,6 +1139,7 @@ int Engine::pack_sim_state(const uint32_t *wires, uint32_t n, uint8_t *p0, uint8
     for (uint32_t i = 0; i < n; i++)
         for (uint32_t j = 0; j < net_.width[wires[i]]; j++) rows.push_back(net_.row_of_bit[net_.bit_off[wires[i]] + j]);
     if ((rc = ensure_rows_buffer((uint32_t)std::max<size_t>(rows.size(), 1)))) return rc;
+    rows_key_ = ptrs_key_ = 0;
     if (pack_cap_ < 2 * n_bytes) {
         CU_TRY(cudaStreamSynchronize(ST));
         cudaFree(d_pack_);

@@ -67,13 +67,12 @@ class Engine {
     int upload_rows(const uint32_t *wires, uint32_t n, bool drive_rows);
     int run_levelised(bool async);
     int run_jacobi(uint64_t max_steps);
-    int finish_status(uint64_t *conflict, uint64_t *unsettled);
 
     Compiled net_;
     int device_ = -1;
     bool device_ready_ = false;
     void *stream_ = nullptr;  // cudaStream_t
-    bool own_stream_ = false;
+    bool own_stream_ = false, stream_set_ = false;
 
     uint64_t n_lanes_ = 0;
     uint32_t T_ = 0, stride_ = 0;
@@ -105,6 +104,7 @@ class Engine {
     size_t stage_words_ = 0;
     uint32_t *d_rows_ = nullptr;
     uint32_t rows_cap_ = 0;
+    uint64_t rows_key_ = 0, ptrs_key_ = 0;  // hashes of the cached wire lists (0 = none)
     uint8_t *d_pack_ = nullptr;
     size_t pack_cap_ = 0;
 

@@ -127,7 +127,8 @@ int b2_sim_get_info(const b2_sim *s, b2_sim_info *out);
 int b2_wire_width(const b2_sim *s, uint32_t wire, uint8_t *out_width);
 
 /* Device / stream selection (before the first call that touches the device). `stream` is a
-   cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = a private stream. */
+   cudaStream_t used as given (e.g. torch.cuda.current_stream().cuda_stream; 0 = CUDA's legacy
+   default stream).  Without this call the simulator creates a private non-blocking stream. */
 int b2_sim_set_device(b2_sim *s, int device);
 int b2_sim_set_stream(b2_sim *s, void *stream);
 /* Block until everything queued by this simulator has finished. */
