@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) k_extra_drive(const uint32_t *rows, uint3
     if (mode == 0 && c) atomicOr((unsigned long long *)&conf[w], (unsigned long long)c);
 }
 
-// Per-lane bookkeeping after one application (mirrors oracle/bitsliced.c bs_run):
+// Per-lane bookkeeping after one application:
 //   conflict |= conf_step & live (only while k < last); live &= changed & ~conflict;
 //   on the last (check-only) application: unsettled = live.
 __global__ void __launch_bounds__(256) k_status_step(uint64_t *changed, uint64_t *conf_step, uint64_t *live,

@@ -1,0 +1,180 @@
+"""CPU-side checks of the C ABI: every symbol the header declares is exported, the builder
+validates like gsim (variants at reference crates/digilogic_gsim/src/lib.rs:55-66), the netlist
+compiler's levelisation, the B200Server state machine (lib.rs:5-52,101-239) — and that the
+product fails loudly, not quietly, without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import digilogic_b200 as d
+from digilogic_b200 import _ffi, netgen
+from digilogic_b200.gsim import AddComponentError, ComponentError
+from digilogic_b200.server import B200Server, ServerError, ServerErrorException
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "digilogic_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 45
+    lib = C.CDLL(_ffi._build.LIB_PATH) if os.path.exists(_ffi._build.LIB_PATH) else _ffi.lib()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    # and the ctypes table covers the header exactly
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+    assert b"sm_100a" in _ffi.lib().b2_version()
+
+
+def test_builder_validation_matches_gsim_variants():
+    b = d.SimulatorBuilder()
+    w1, w1b, w4 = b.add_wire(1), b.add_wire(1), b.add_wire(4)
+    for fn, err in [
+        (lambda: b.add_and_gate([w1, 99], w1b), AddComponentError.InvalidWireId),
+        (lambda: b.add_and_gate([w1, w1b], 99), AddComponentError.InvalidWireId),
+        (lambda: b.add_or_gate([w1], w1b), AddComponentError.TooFewInputs),
+        (lambda: b.add_xor_gate([w1, w4], w1b), AddComponentError.WireWidthMismatch),
+        (lambda: b.add_not_gate(w4, w1), AddComponentError.WireWidthMismatch),
+        (lambda: b.add_multiplexer([w1, w1b, w1], w1, w1b), AddComponentError.InvalidInputCount),
+        (lambda: b.add_multiplexer([w1, w1b], w4, w1b), AddComponentError.WireWidthIncompatible),
+        (lambda: b.add_multiplexer([w1, w4], w1, w1b), AddComponentError.WireWidthMismatch),
+    ]:
+        with pytest.raises(ComponentError) as e:
+            fn()
+        assert e.value.error == err
+    assert b.get_wire_width(w4) == 4
+    assert b.add_and_gate([w1, w1b], w1b) == 0 and b.add_not_gate(w1, w1b) == 1  # ComponentIds count up
+
+
+def test_same_validation_as_oracle():
+    """The engine's builder and the oracle's builder accept and reject the same calls."""
+    import oracle
+    rng = np.random.default_rng(5)
+    gb, ob = d.SimulatorBuilder(), oracle.Builder()
+    widths = [1, 1, 1, 2, 2, 4, 8, 1]
+    for w in widths:
+        assert gb.add_wire(w) == ob.add_wire(w)
+    for _ in range(300):
+        kind = int(rng.integers(0, 8))
+        n = int(rng.integers(0, 5))
+        ins = [int(x) for x in rng.integers(0, len(widths) + 1, n)]
+        out = int(rng.integers(0, len(widths) + 1))
+        sel = int(rng.integers(0, len(widths) + 1))
+        def call(b):
+            try:
+                if kind == 7:
+                    return ("ok", b.add_multiplexer(ins, sel, out))
+                if kind == 6:
+                    return ("ok", b.add_not_gate(ins[0] if ins else 0, out))
+                return ("ok", b.add_gate(kind, ins, out))
+            except ComponentError as e:
+                return ("err", e.error.name)
+            except oracle.OracleError as e:
+                return ("err", str(e))
+        assert call(gb) == call(ob)
+
+
+def test_compile_info_levels():
+    gen = netgen.random_dag(n_gates=4000, depth=40, n_inputs=64, n_outputs=16)
+    sim = gen.emit(d.SimulatorBuilder()).build()
+    i = sim.info
+    assert (i.n_wires, i.n_rows, i.n_sources, i.n_gates2, i.n_gates_wide) == (4064, 4064, 64, 4000, 0)
+    assert i.depth == 40 and i.cyclic == 0 and i.multi_driver == 0
+    add = netgen.ripple_adder(4).emit(d.SimulatorBuilder()).build().info
+    assert add.n_gates2 == 20 and add.depth == 9 and add.n_sources == 9
+    mul = netgen.array_multiplier(32).emit(d.SimulatorBuilder()).build().info
+    assert mul.n_gates2 == 5888 and mul.cyclic == 0
+    b = d.SimulatorBuilder()
+    s_, r_, q, qn, w8, o8 = b.add_wire(), b.add_wire(), b.add_wire(), b.add_wire(), b.add_wire(8), b.add_wire(8)
+    b.add_nand_gate([s_, qn], q)
+    b.add_nand_gate([r_, q], qn)
+    b.add_not_gate(w8, o8)
+    b.add_and_gate([s_, r_, q], qn)
+    i = b.build().info
+    assert i.cyclic == 1 and i.depth == 0 and i.multi_driver == 1
+    assert i.n_sources == 10 and i.n_rows == 10 + 11 and i.n_gates2 == 2 + 8 and i.n_gates_wide == 1  # one row per gate
+
+
+def test_build_takes_the_builder():
+    b = d.SimulatorBuilder()
+    a = b.add_wire()
+    sim = b.build()
+    assert sim.info.n_wires == 1
+    assert b.add_wire() == 0, "after build() the builder is an empty default builder (mem::take)"
+    assert a == 0
+
+
+def test_server_state_machine_and_errors():
+    sv = B200Server()
+    assert sv.max_clients() == 2**64 - 1
+    with pytest.raises(ServerErrorException) as e:   # the reference panics on an unknown client (gsim/lib.rs:26)
+        sv.begin_build(1)
+    assert e.value.error == ServerError.Other
+    sv.client_connected(1)
+    sv.begin_build(1)
+    a, b_, o = sv.add_net(1, 1), sv.add_net(1, 1), sv.add_net(1, 1)
+    w4 = sv.add_net(1, 4)
+    assert (a, b_, o, w4) == (0, 1, 2, 3)
+    assert sv.add_and_gate(1, 1, [a, b_], o) == 0
+    for fn, err in [
+        (lambda: sv.add_or_gate(1, 4, [a, b_], o), ServerError.WidthMismatch),        # width != output width
+        (lambda: sv.add_or_gate(1, 1, [a, b_], 77), ServerError.InvalidNetId),        # unknown output
+        (lambda: sv.add_xor_gate(1, 1, [a, 77], o), ServerError.InvalidNetId),
+        (lambda: sv.add_nand_gate(1, 1, [a], o), ServerError.InvalidInputCount),      # TooFewInputs
+        (lambda: sv.add_nor_gate(1, 1, [a, w4], o), ServerError.WidthMismatch),
+        (lambda: sv.add_not_gate(1, 1, w4, o), ServerError.WidthMismatch),
+        (lambda: sv.add_mux(1, 1, [a, a, b_, o], o), ServerError.InvalidInputCount),  # 3 data inputs
+        (lambda: sv.add_mux(1, 1, [w4, a, b_], o), ServerError.WidthIncompatible),    # select width
+        (lambda: sv.set_net_drive(1, a, b"\1", b"\1"), ServerError.InvalidState),     # still Building
+        (lambda: sv.eval(1, 10), ServerError.InvalidState),
+        (lambda: sv.get_net_state(1, a), ServerError.InvalidState),
+    ]:
+        with pytest.raises(ServerErrorException) as e:
+            fn()
+        assert e.value.error == err, (err, e.value.error)
+    assert sv.add_mux(1, 1, [a, b_, o], o) == 1          # inputs[0] is the select
+    sv.end_build(1)
+    for fn in (lambda: sv.end_build(1), lambda: sv.add_net(1, 1), lambda: sv.add_and_gate(1, 1, [a, b_], o)):
+        with pytest.raises(ServerErrorException) as e:
+            fn()
+        assert e.value.error == ServerError.InvalidState
+    with pytest.raises(ServerErrorException) as e:       # > 32 plane bytes panics in the reference (gsim/lib.rs:205)
+        sv.set_net_drive(1, a, bytes(33), bytes(33))
+    assert e.value.error == ServerError.OutOfRange
+    sv.begin_build(1)                                    # always resets to a fresh builder (gsim/lib.rs:117-121)
+    assert sv.add_net(1, 1) == 0
+    sv.client_connected(1)                               # Adapter::client_disconnected calls this (server.rs:296-299)
+    assert sv.add_net(1, 1) == 0
+    sv.client_disconnected(1)
+    with pytest.raises(ServerErrorException):
+        sv.add_net(1, 1)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the engine must refuse, and nothing in the product imports the oracle."""
+    for root, _, files in os.walk(os.path.join(ROOT, "digilogic_b200")):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".hpp", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
+                assert "gsim_oracle" not in src and "bitsliced.c" not in src, f
+    if _has_gpu():
+        pytest.skip("GPU present")
+    b = d.SimulatorBuilder()
+    a, o = b.add_wire(), b.add_wire()
+    b.add_not_gate(a, o)
+    sim = b.build()
+    for fn in (lambda: sim.run_sim(10), lambda: sim.set_lanes(64), lambda: sim.set_wire_drive(a, d.LogicState(1, 1)),
+               lambda: sim.get_wire_state(o)):
+        with pytest.raises(d.B200Error) as e:
+            fn()
+        assert e.value.code == 18 and "no CPU path" in str(e.value)
