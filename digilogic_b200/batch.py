@@ -107,8 +107,9 @@ def gather_output_planes(local_value, local_valid, world_size: int):
         return local_value.unsqueeze(0), local_valid.unsqueeze(0)
     gv = torch.empty((world_size,) + tuple(local_value.shape), dtype=local_value.dtype, device=local_value.device)
     gm = torch.empty_like(gv)
-    dist.all_gather_into_tensor(gv, local_value.contiguous())
-    dist.all_gather_into_tensor(gm, local_valid.contiguous())
+    # the output is the concatenation of the ranks' planes along dim 0 (the form gloo also accepts)
+    dist.all_gather_into_tensor(gv.view(-1, local_value.shape[-1]), local_value.contiguous())
+    dist.all_gather_into_tensor(gm.view(-1, local_valid.shape[-1]), local_valid.contiguous())
     return gv, gm
 
 

@@ -1,0 +1,266 @@
+"""Harness-side readers (and writers) for the two circuit file formats behind BASELINE configs 1
+and 2 — SURVEY.md §8 row f1.
+
+* Digital `.dig` (H. Neemann's Digital, XML): restates what the reference's importer does —
+  symbols are placed with the port geometry of crates/digilogic_core/src/symbol.rs:32-253, wire
+  segments join nets only at identical end points, and nets are found by a flood fill over
+  positions (crates/digilogic_serde/src/digital.rs:111-215).  Element names:
+  crates/digilogic_serde/src/digital/circuitfile.rs:55-79.
+* Yosys JSON: 1-bit `$and/$or/$xor/$not` cells joined by bit ids
+  (crates/digilogic_serde/src/yosys.rs:115-243, schema yosys/netlist.rs:159-196).
+
+Both produce an `ImportedCircuit`, whose `emit()` issues the same calls the GUI client sends
+(crates/digilogic_netcode/src/client.rs:288-427): one 1-bit net per net, then one gate per
+symbol with inputs in port order (mux: S, A, B so that inputs[0] is the select).
+"""
+from __future__ import annotations
+
+import json
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+
+AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX = range(8)
+
+# port name -> (dx, dy, is_input), in the reference's port order
+_GATE2 = [("A", 0, 0, True), ("B", 0, 40, True), ("Y", 80, 20, False)]
+_GATE1 = [("A", 0, 0, True), ("Y", 40, 0, False)]
+DIG_SYMBOLS = {
+    "And": (AND, _GATE2), "Or": (OR, _GATE2), "XOr": (XOR, _GATE2), "Not": (NOT, _GATE1),
+    "In": (None, [("Y", 0, 0, False)]), "Out": (None, [("A", 0, 0, True)]),
+    "Multiplexer": (MUX, [("S", 20, 40, True), ("A", 0, 0, True), ("B", 0, 40, True), ("Y", 40, 20, False)]),
+}
+YOSYS_CELLS = {"$and": AND, "$or": OR, "$xor": XOR, "$not": NOT}
+
+
+@dataclass
+class ImportedCircuit:
+    name: str
+    n_nets: int
+    gates: list = field(default_factory=list)      # (kind, [input nets], output net); mux inputs = [S, A, B]
+    inputs: dict = field(default_factory=dict)     # label -> [nets] (LSB first)
+    outputs: dict = field(default_factory=dict)
+
+    def emit(self, builder):
+        """Same sequence as the client's build: AddNet{width:1} per net, then the gates."""
+        for _ in range(self.n_nets):
+            builder.add_wire(1)
+        for kind, ins, out in self.gates:
+            if kind == MUX:
+                builder.add_multiplexer(ins[1:], ins[0], out)
+            elif kind == NOT:
+                builder.add_not_gate(ins[0], out)
+            else:
+                builder.add_gate(kind, ins, out)
+        return builder
+
+    def to_json(self) -> dict:
+        return {"name": self.name, "n_nets": self.n_nets, "gates": [[k, list(i), o] for k, i, o in self.gates],
+                "inputs": self.inputs, "outputs": self.outputs}
+
+    @classmethod
+    def from_json(cls, d: dict) -> "ImportedCircuit":
+        return cls(d["name"], d["n_nets"], [(k, list(i), o) for k, i, o in d["gates"]], dict(d["inputs"]), dict(d["outputs"]))
+
+
+# ------------------------------------------------------------------------------ Digital .dig
+
+def load_dig(text: str, name: str = "circuit") -> ImportedCircuit:
+    root = ET.fromstring(text)
+    symbols = []   # (element name, label, [(port name, (x, y), is_input)])
+    for ve in root.find("visualElements").findall("visualElement"):
+        elem = ve.findtext("elementName")
+        if elem not in DIG_SYMBOLS:
+            raise ValueError(f"unsupported Digital element {elem!r}")
+        pos = ve.find("pos")
+        x, y = int(pos.get("x")), int(pos.get("y"))
+        label = None
+        attrs = ve.find("elementAttributes")
+        if attrs is not None:
+            for entry in attrs.findall("entry"):
+                kids = list(entry)
+                if len(kids) == 2 and kids[0].text == "Label":
+                    label = kids[1].text
+        ports = [(pn, (x + dx, y + dy), is_in) for pn, dx, dy, is_in in DIG_SYMBOLS[elem][1]]
+        symbols.append((elem, label, ports))
+
+    # union-find over positions: a port position and the two ends of every wire segment
+    parent = {}
+
+    def find(p):
+        parent.setdefault(p, p)
+        while parent[p] != p:
+            parent[p] = parent[parent[p]]
+            p = parent[p]
+        return p
+
+    for _, _, ports in symbols:
+        for _, p, _ in ports:
+            find(p)
+    wires = root.find("wires")
+    for w in (wires.findall("wire") if wires is not None else []):
+        p1 = (int(w.find("p1").get("x")), int(w.find("p1").get("y")))
+        p2 = (int(w.find("p2").get("x")), int(w.find("p2").get("y")))
+        parent[find(p1)] = find(p2)
+
+    # nets in first-seen order of the symbols' ports (any order is a valid client numbering)
+    net_of = {}
+
+    def net(p):
+        r = find(p)
+        if r not in net_of:
+            net_of[r] = len(net_of)
+        return net_of[r]
+
+    circ = ImportedCircuit(name, 0)
+    for elem, label, ports in symbols:
+        kind = DIG_SYMBOLS[elem][0]
+        if elem == "In":
+            circ.inputs.setdefault(label or f"in{len(circ.inputs)}", []).append(net(ports[0][1]))
+        elif elem == "Out":
+            circ.outputs.setdefault(label or f"out{len(circ.outputs)}", []).append(net(ports[0][1]))
+        else:
+            ins = [net(p) for _, p, is_in in ports if is_in]
+            outs = [net(p) for _, p, is_in in ports if not is_in]
+            circ.gates.append((kind, ins, outs[0]))
+    circ.n_nets = len(net_of)
+    return circ
+
+
+def write_dig(symbols, wires) -> str:
+    """symbols: [(element name, label or None, x, y)], wires: [((x1,y1),(x2,y2))] -> Digital XML v2."""
+    out = ['<?xml version="1.0" encoding="utf-8"?>', "<circuit>", "  <version>2</version>", "  <attributes/>", "  <visualElements>"]
+    for elem, label, x, y in symbols:
+        out.append("    <visualElement>")
+        out.append(f"      <elementName>{elem}</elementName>")
+        if label is not None:
+            out += ["      <elementAttributes>", "        <entry>", "          <string>Label</string>",
+                    f"          <string>{label}</string>", "        </entry>", "      </elementAttributes>"]
+        elif elem in ("And", "Or", "XOr"):
+            out += ["      <elementAttributes>", "        <entry>", "          <string>wideShape</string>",
+                    "          <boolean>true</boolean>", "        </entry>", "      </elementAttributes>"]
+        else:
+            out.append("      <elementAttributes/>")
+        out.append(f'      <pos x="{x}" y="{y}"/>')
+        out.append("    </visualElement>")
+    out += ["  </visualElements>", "  <wires>"]
+    for (x1, y1), (x2, y2) in wires:
+        out += ["    <wire>", f'      <p1 x="{x1}" y="{y1}"/>', f'      <p2 x="{x2}" y="{y2}"/>', "    </wire>"]
+    out += ["  </wires>", "  <measurementOrdering/>", "</circuit>", ""]
+    return "\n".join(out)
+
+
+def adder_dig(nbits: int = 4) -> str:
+    """BASELINE config 1: an nbits ripple-carry adder authored as a Digital file from In/Out/And/Or/XOr
+    symbols at the reference's port geometry; every connection is one point-to-point wire segment
+    (a net with fan-out is a star of segments from the driver's port)."""
+    symbols, wires = [], []
+    port = {"gate2": {"A": (0, 0), "B": (0, 40), "Y": (80, 20)}}
+
+    def place(elem, label, x, y):
+        symbols.append((elem, label, x, y))
+        return (x, y)
+
+    def pin(pos, name):
+        dx, dy = port["gate2"][name]
+        return (pos[0] + dx, pos[1] + dy)
+
+    def connect(src, dst):
+        wires.append((src, dst))
+
+    carry = place("In", "Cin", 0, -200)          # In: port Y at (0,0)
+    for i in range(nbits):
+        y0 = i * 400
+        a = place("In", f"A{i}", 0, y0)
+        b = place("In", f"B{i}", 0, y0 + 100)
+        x1 = place("XOr", None, 200, y0)
+        s = place("XOr", None, 500, y0)
+        a1 = place("And", None, 200, y0 + 160)
+        a2 = place("And", None, 500, y0 + 160)
+        co = place("Or", None, 800, y0 + 160)
+        so = place("Out", f"S{i}", 1000, y0 + 20)
+        for g in (x1, a1):
+            connect(a, pin(g, "A"))
+            connect(b, pin(g, "B"))
+        for g in (s, a2):
+            connect(pin(x1, "Y"), pin(g, "A"))
+            connect(carry, pin(g, "B"))
+        connect(pin(a1, "Y"), pin(co, "A"))
+        connect(pin(a2, "Y"), pin(co, "B"))
+        connect(pin(s, "Y"), so)
+        carry = pin(co, "Y")
+    cout = place("Out", "Cout", 1000, nbits * 400)
+    connect(carry, cout)
+    return write_dig(symbols, wires)
+
+
+# ------------------------------------------------------------------------------ Yosys JSON
+
+def load_yosys(text: str, module: str | None = None) -> ImportedCircuit:
+    doc = json.loads(text)
+    mods = doc["modules"]
+    if module is None:
+        tops = [m for m, v in mods.items() if int(v.get("attributes", {}).get("top", "0"), 2) == 1]
+        module = tops[0] if tops else next(iter(mods))
+    mod = mods[module]
+    net_of = {}
+
+    def net(bit):
+        if not isinstance(bit, int):
+            raise ValueError("constant bits are not supported (the reference importer todo!()s on them)")
+        if bit not in net_of:
+            net_of[bit] = len(net_of)
+        return net_of[bit]
+
+    circ = ImportedCircuit(module, 0)
+    for pname, port in mod.get("ports", {}).items():
+        nets = [net(b) for b in port["bits"]]
+        if port["direction"] == "input":
+            circ.inputs[pname] = nets
+        elif port["direction"] == "output":
+            circ.outputs[pname] = nets
+        else:
+            raise ValueError("inout ports are not supported")
+    for cname, cell in mod.get("cells", {}).items():
+        ctype = cell["type"]
+        if ctype not in YOSYS_CELLS:
+            raise ValueError(f"unsupported cell type {ctype!r} ({cname})")
+        kind = YOSYS_CELLS[ctype]
+        conn = cell["connections"]
+        width = len(conn["Y"])
+        for j in range(width):
+            ins = [net(conn["A"][j])] if kind == NOT else [net(conn["A"][j]), net(conn["B"][j])]
+            circ.gates.append((kind, ins, net(conn["Y"][j])))
+    circ.n_nets = len(net_of)
+    return circ
+
+
+def netlist_to_yosys(gen, name: str, in_ports: dict, out_ports: dict) -> str:
+    """Writes a two-input gate list (netgen.GeneratedNetlist with And/Or/Xor/Not only) as Yosys JSON
+    with 1-bit cells; wire id w becomes bit id w + 2 (0 and 1 are constants in Yosys)."""
+    names = {AND: "$and", OR: "$or", XOR: "$xor", NOT: "$not"}
+    cells = {}
+    for i in range(gen.n_gates):
+        k = int(gen.kinds[i])
+        if k not in names:
+            raise ValueError("only $and/$or/$xor/$not cells can be written")
+        conn = {"A": [int(gen.in0[i]) + 2]}
+        dirs = {"A": "input", "Y": "output"}
+        if k != NOT:
+            conn["B"] = [int(gen.in1[i]) + 2]
+            dirs["B"] = "input"
+        conn["Y"] = [int(gen.out[i]) + 2]
+        cells[f"{names[k]}${i}"] = {"hide_name": 1, "type": names[k], "parameters": {}, "attributes": {},
+                                     "port_directions": dirs, "connections": conn}
+    ports = {p: {"direction": "input", "bits": [int(w) + 2 for w in ws]} for p, ws in in_ports.items()}
+    ports.update({p: {"direction": "output", "bits": [int(w) + 2 for w in ws]} for p, ws in out_ports.items()})
+    netnames = {p: {"hide_name": 0, "bits": v["bits"], "attributes": {}} for p, v in ports.items()}
+    doc = {"creator": "digilogic_b200.importers", "modules": {name: {"attributes": {"top": "1".zfill(32)}, "ports": ports,
+                                                                       "cells": cells, "netnames": netnames}}}
+    return json.dumps(doc)
+
+
+def multiplier_yosys(n: int = 32) -> str:
+    """BASELINE config 2: n x n array multiplier as Yosys JSON (ports A, B: n bits, P: 2n bits)."""
+    from . import netgen
+    gen = netgen.array_multiplier(n)
+    return netlist_to_yosys(gen, f"mul{n}x{n}", {"A": gen.inputs[:n], "B": gen.inputs[n:]}, {"P": gen.outputs})

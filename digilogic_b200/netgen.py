@@ -161,3 +161,85 @@ def array_multiplier(n=32) -> GeneratedNetlist:
         name=f"array_multiplier_{n}x{n}", n_wires=wires, n_gates=len(kinds), inputs=np.array(A + B, np.uint32),
         outputs=np.array(P, np.uint32), kinds=np.array(kinds, np.uint8), in0=np.array(in0, np.uint32),
         in1=np.array(in1, np.uint32), out=np.array(out, np.uint32))
+
+
+@dataclass
+class SequentialNetlist:
+    """BASELINE config 4: NAND-only edge-triggered D flip-flops (async preset/clear) forming
+    Fibonacci LFSR chains, plus cross-coupled NAND SR latches fed by the flip-flop outputs."""
+    n_wires: int
+    clk: int
+    preset_n: list            # per bit position: active-low preset input wire
+    clear_n: list             # per bit position: active-low clear input wire
+    q: list                   # q[chain][bit] wire ids
+    latch_q: list             # [(Q, Qn)] wire ids
+    hazard_latches: list      # indices into latch_q of latches whose S'/R' can rise together (oscillate)
+    ops: list                 # (kind, [inputs], output)
+    n_gates: int = 0
+
+    def emit(self, builder):
+        first = builder.add_wires(self.n_wires)
+        assert first == 0
+        for kind, ins, out in self.ops:
+            if kind == NOT:
+                builder.add_not_gate(ins[0], out)
+            else:
+                builder.add_gate(kind, ins, out)
+        return builder
+
+
+def sequential(n_latches=4096, n_chains=64, bits=64, n_hazard=0, taps=None) -> SequentialNetlist:
+    """Flip-flop (7474 structure, 3-input NANDs):
+        g1 = NAND(pre', g4, g2)   g2 = NAND(g1, clr', clk)   g3 = NAND(g2, clk, g4)   g4 = NAND(g3, clr', d)
+        q  = NAND(pre', g2, qn)   qn = NAND(q, g3, clr')
+    Chain c, bit b uses preset/clear inputs of bit position (b + c) % bits, so one per-lane init
+    pattern gives every chain a different start state.  d_0 = XOR of the tap bits, d_b = q_{b-1}.
+    Latch j: S' = q, R' = qn of one flip-flop (never 0,0 -> never oscillates); the first
+    `n_hazard` latches instead take S' and R' from the q of two different chains at the same bit,
+    so S' = R' = 0 -> 1 on one clock edge makes the lane oscillate until max_steps."""
+    if taps is None:
+        taps = [bits - 1, bits - 2, bits - 4, bits - 5] if bits >= 8 else [bits - 1, bits - 2]
+    n_w = 0
+
+    def wire():
+        nonlocal n_w
+        n_w += 1
+        return n_w - 1
+
+    ops = []
+    clk = wire()
+    preset_n = [wire() for _ in range(bits)]
+    clear_n = [wire() for _ in range(bits)]
+    q = [[wire() for _ in range(bits)] for _ in range(n_chains)]
+    qn = [[wire() for _ in range(bits)] for _ in range(n_chains)]
+    for c in range(n_chains):
+        # feedback
+        fb = q[c][taps[0]]
+        for t in taps[1:]:
+            x = wire()
+            ops.append((XOR, [fb, q[c][t]], x))
+            fb = x
+        for b in range(bits):
+            d = fb if b == 0 else q[c][b - 1]
+            pre, clr = preset_n[(b + c) % bits], clear_n[(b + c) % bits]
+            g1, g2, g3, g4 = wire(), wire(), wire(), wire()
+            ops.append((NAND, [pre, g4, g2], g1))
+            ops.append((NAND, [g1, clr, clk], g2))
+            ops.append((NAND, [g2, clk, g4], g3))
+            ops.append((NAND, [g3, clr, d], g4))
+            ops.append((NAND, [pre, g2, qn[c][b]], q[c][b]))
+            ops.append((NAND, [q[c][b], g3, clr], qn[c][b]))
+    latch_q, hazard = [], []
+    for j in range(n_latches):
+        c, b = j % n_chains, (j // n_chains) % bits
+        if j < n_hazard and n_chains > 1:
+            s_n, r_n = q[c][b], q[(c + 1) % n_chains][b]
+            hazard.append(j)
+        else:
+            s_n, r_n = q[c][b], qn[c][b]
+        lq, lqn = wire(), wire()
+        ops.append((NAND, [s_n, lqn], lq))
+        ops.append((NAND, [r_n, lq], lqn))
+        latch_q.append((lq, lqn))
+    return SequentialNetlist(n_wires=n_w, clk=clk, preset_n=preset_n, clear_n=clear_n, q=q, latch_q=latch_q,
+                             hazard_latches=hazard, ops=ops, n_gates=len(ops))
