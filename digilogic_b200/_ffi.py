@@ -54,6 +54,7 @@ SIGNATURES = {
     "b2_get_wire_lanes": (i32, [vp, u32, u32, u32, u32, vp, vp]),
     "b2_gather_wires_device": (i32, [vp, vp, u32, vp, vp, sz]),
     "b2_gather_wires_host": (i32, [vp, vp, u32, vp, vp, sz]),
+    "b2_gather_wires_host_async": (i32, [vp, vp, u32, vp, vp, sz]),
     "b2_pack_sim_state": (i32, [vp, vp, u32, vp, vp, sz, pu64]),
     "b2_server_new": (vp, []),
     "b2_server_free": (None, [vp]),

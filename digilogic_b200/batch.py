@@ -80,19 +80,34 @@ class BatchRunner:
         return worst
 
     # -- host stimulus through the C ABI (end-to-end path: H2D copies and D2H read-back included)
-    def run_host(self, in_value, in_valid, out_value, out_valid) -> SimulationRunResult:
-        """in_*: host arrays [n_inputs, n_words]; out_*: host arrays [n_outputs, n_words] (numpy
-        views of pinned memory for asynchronous copies)."""
-        n_words = in_value.shape[1]
-        assert n_words % self.tile_words == 0
+    def run_host(self, in_value, in_valid, out_value, out_valid, n_words: int | None = None) -> SimulationRunResult:
+        """in_*: host arrays [n_inputs, ring_words]; out_*: host arrays [n_outputs, ring_words] (numpy
+        views of pinned memory).  n_words lane-words are processed; if that is more than the host
+        arrays hold, the arrays are used as a ring (tile i reads/writes slot i mod ring).  The drives
+        of tile i+1 are uploaded while tile i settles, and the outputs of tile i are copied out
+        while tile i+1 settles (the engine's copy streams); the call returns after the last copy."""
+        ring_words = in_value.shape[1]
+        n_words = ring_words if n_words is None else n_words
+        assert n_words % self.tile_words == 0 and ring_words % self.tile_words == 0
+        assert out_value.shape[1] == ring_words
         worst = SimulationRunResult.Ok
         in_stride, out_stride = in_value.strides[0] // 8, out_value.strides[0] // 8
-        for w0, _ in plan_tiles(n_words, self.tile_words):
-            self.sim.set_drives_lanes_ptr(self.inputs, in_value.ctypes.data + 8 * w0, in_valid.ctypes.data + 8 * w0, in_stride)
+        tiles = plan_tiles(n_words, self.tile_words)
+
+        def upload(w0):
+            o = 8 * (w0 % ring_words)
+            self.sim.set_drives_lanes_ptr(self.inputs, in_value.ctypes.data + o, in_valid.ctypes.data + o, in_stride)
+
+        upload(tiles[0][0])
+        for i, (w0, _) in enumerate(tiles):
             r = self.sim.run_sim_lanes_async(self.max_steps)
             worst = max(worst, r)
-            self.sim.gather_wires_ptr(self.outputs, out_value.ctypes.data + 8 * w0, out_valid.ctypes.data + 8 * w0,
-                                      out_stride, device=False)
+            if i + 1 < len(tiles):
+                upload(tiles[i + 1][0])
+            o = 8 * (w0 % ring_words)
+            self.sim.gather_wires_ptr(self.outputs, out_value.ctypes.data + o, out_valid.ctypes.data + o, out_stride,
+                                      device=False, async_=True)
+        self.sim.synchronize()
         return worst
 
 

@@ -240,6 +240,14 @@ int b2_gather_wires_host(b2_sim *s, const uint32_t *wires, uint32_t n, uint64_t 
     GUARD_END(B2_ERR_OUT_OF_MEMORY)
 }
 
+int b2_gather_wires_host_async(b2_sim *s, const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid,
+                               size_t dst_stride_words) {
+    if (!s) return B2_ERR_NULL;
+    GUARD_BEGIN
+    return s->e->gather_wires(wires, n, value, valid, dst_stride_words, false, true);
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
 int b2_pack_sim_state(b2_sim *s, const uint32_t *wires, uint32_t n, uint8_t *plane0, uint8_t *plane1, size_t cap_bytes,
                       uint64_t *out_bit_len) {
     if (!s) return B2_ERR_NULL;

@@ -48,6 +48,9 @@ uint64_t kernel_launches() { return g_launches.load(); }
     } while (0)
 
 #define ST ((cudaStream_t)stream_)
+#define CIN ((cudaStream_t)cin_stream_)
+#define COUT ((cudaStream_t)cout_stream_)
+#define EV(x) ((cudaEvent_t)(x))
 
 // ---------------------------------------------------------------------------- device helpers
 
@@ -452,6 +455,8 @@ Engine::~Engine() {
     if (device_ready_) {
         cudaSetDevice(device_);
         cudaStreamSynchronize(ST);
+        if (cin_stream_) cudaStreamSynchronize(CIN);
+        if (cout_stream_) cudaStreamSynchronize(COUT);
         free_store();
         cudaFree(d_fan0_);
         cudaFree(d_fan1_);
@@ -463,6 +468,10 @@ Engine::~Engine() {
         cudaFree(d_flags_);
         if (h_flags_) cudaFreeHost(h_flags_);
         if (own_stream_ && stream_) cudaStreamDestroy(ST);
+        if (cin_stream_) cudaStreamDestroy(CIN);
+        if (cout_stream_) cudaStreamDestroy(COUT);
+        for (void *e : {ev_drive_consumed_, ev_drives_ready_, ev_gathered_, ev_out_free_})
+            if (e) cudaEventDestroy(EV(e));
     }
 }
 
@@ -482,15 +491,18 @@ void Engine::free_store() {
     cudaFree(d_live_);
     cudaFree(d_conflict_);
     cudaFree(d_unsettled_);
-    cudaFree(stage_val_);
-    cudaFree(stage_vld_);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(stage_val_[i]);
+        cudaFree(stage_vld_[i]);
+        stage_val_[i] = stage_vld_[i] = nullptr;
+        stage_words_[i] = 0;
+    }
+    cin_pending_ = false;
     cudaFree(d_rows_);
     cudaFree(d_pack_);
     drv_val_ = drv_vld_ = xdrv_val_ = xdrv_vld_ = nullptr;
     d_extra_rows_ = nullptr;
     d_changed_ = d_conf_step_ = d_live_ = d_conflict_ = d_unsettled_ = nullptr;
-    stage_val_ = stage_vld_ = nullptr;
-    stage_words_ = 0;
     d_rows_ = nullptr;
     rows_cap_ = 0;
     rows_key_ = ptrs_key_ = 0;
@@ -577,6 +589,18 @@ int Engine::ensure_device() {
     CU_TRY(cudaMalloc((void **)&d_flags_, sizeof(RunFlags)));
     CU_TRY(cudaMemset(d_flags_, 0, sizeof(RunFlags)));
     CU_TRY(cudaMallocHost((void **)&h_flags_, sizeof(RunFlags)));
+    {
+        cudaStream_t a, b;
+        CU_TRY(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking));
+        cin_stream_ = a;
+        cout_stream_ = b;
+        for (void **e : {&ev_drive_consumed_, &ev_drives_ready_, &ev_gathered_, &ev_out_free_}) {
+            cudaEvent_t ev;
+            CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            *e = ev;
+        }
+    }
     device_ready_ = true;
     return B2_OK;
 }
@@ -584,7 +608,23 @@ int Engine::ensure_device() {
 int Engine::synchronize() {
     if (!device_ready_) return B2_OK;
     CU_TRY(cudaSetDevice(device_));
+    CU_TRY(cudaStreamSynchronize(CIN));
     CU_TRY(cudaStreamSynchronize(ST));
+    CU_TRY(cudaStreamSynchronize(COUT));
+    return B2_OK;
+}
+
+// The drive store is written by the copy-in stream (b2_set_drives_lanes) and read/written by the
+// main stream; two events order the two streams without serialising whole tiles.
+int Engine::drives_begin() {
+    if (cin_pending_) {
+        CU_TRY(cudaStreamWaitEvent(ST, EV(ev_drives_ready_), 0));
+        cin_pending_ = false;
+    }
+    return B2_OK;
+}
+int Engine::drives_end() {
+    CU_TRY(cudaEventRecord(EV(ev_drive_consumed_), ST));
     return B2_OK;
 }
 
@@ -619,7 +659,9 @@ int Engine::set_lanes(uint64_t n_lanes) {
     if (n_lanes == 0 || n_lanes > 64ull * 0x7FFFFFF0ull) return B2_ERR_INVALID_ARG;
     int rc = ensure_device();
     if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(CIN));
     CU_TRY(cudaStreamSynchronize(ST));
+    CU_TRY(cudaStreamSynchronize(COUT));
     free_store();
     n_lanes_ = n_lanes;
     T_ = (uint32_t)((n_lanes + 63) / 64);
@@ -644,6 +686,7 @@ int Engine::set_lanes(uint64_t n_lanes) {
     cold_ = true;
     last_mode_ = 0;
     last_apps_ = 0;
+    CU_TRY(cudaStreamSynchronize(ST));  // the zero-fills are done before any other stream touches the store
     return B2_OK;
 }
 
@@ -665,17 +708,19 @@ int Engine::ensure_second_buffer() {
     return B2_OK;
 }
 
-int Engine::ensure_stage(size_t words) {
-    if (stage_words_ >= words) return B2_OK;
+int Engine::ensure_stage(bool out, size_t words) {
+    const int i = out ? 1 : 0;
+    if (stage_words_[i] >= words) return B2_OK;
     CU_TRY(cudaStreamSynchronize(ST));
-    cudaFree(stage_val_);
-    cudaFree(stage_vld_);
-    stage_val_ = stage_vld_ = nullptr;
-    store_bytes_ -= stage_words_ * 16;
-    stage_words_ = 0;
-    CU_TRY(cudaMalloc((void **)&stage_val_, words * 8));
-    CU_TRY(cudaMalloc((void **)&stage_vld_, words * 8));
-    stage_words_ = words;
+    CU_TRY(cudaStreamSynchronize(out ? COUT : CIN));
+    cudaFree(stage_val_[i]);
+    cudaFree(stage_vld_[i]);
+    stage_val_[i] = stage_vld_[i] = nullptr;
+    store_bytes_ -= stage_words_[i] * 16;
+    stage_words_[i] = 0;
+    CU_TRY(cudaMalloc((void **)&stage_val_[i], words * 8));
+    CU_TRY(cudaMalloc((void **)&stage_vld_[i], words * 8));
+    stage_words_[i] = words;
     store_bytes_ += words * 16;
     return B2_OK;
 }
@@ -756,6 +801,7 @@ int Engine::set_wire_drive(uint32_t wire, const uint32_t *p0, const uint32_t *p1
     // row pointer tables for the bits of this wire (two passes: the first may grow the extra store)
     if ((rc = ensure_rows_buffer(width))) return rc;
     rows_key_ = ptrs_key_ = 0;
+    CU_TRY(cudaStreamSynchronize(CIN));  // a scatter kernel may still be reading the pointer tables
     std::vector<uint64_t *> tv(width), tm(width);
     for (int pass = 0; pass < 2; pass++)
         for (uint32_t j = 0; j < width; j++)
@@ -764,9 +810,11 @@ int Engine::set_wire_drive(uint32_t wire, const uint32_t *p0, const uint32_t *p1
     uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
     CU_TRY(cudaMemcpyAsync(d_tv, tv.data(), (size_t)width * 8, cudaMemcpyHostToDevice, ST));
     CU_TRY(cudaMemcpyAsync(d_tm, tm.data(), (size_t)width * 8, cudaMemcpyHostToDevice, ST));
+    if ((rc = drives_begin())) return rc;
     dim3 grid((stride_ + 255) / 256, width);
     k_broadcast_drive<<<grid, 256, 0, ST>>>(d_tv, d_tm, p, width, stride_);
     LAUNCHED();
+    if ((rc = drives_end())) return rc;
     CU_TRY(cudaStreamSynchronize(ST));  // tv/tm are stack-lifetime host buffers
     return B2_OK;
 }
@@ -780,8 +828,10 @@ int Engine::set_wire_drive_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint3
     if ((uint64_t)w0 + nw > T_) return B2_ERR_RANGE;
     uint64_t *dv, *dm;
     if ((rc = drive_target(net_.bit_off[wire] + bit, &dv, &dm))) return rc;
+    if ((rc = drives_begin())) return rc;
     CU_TRY(cudaMemcpyAsync(dv + w0, value, (size_t)nw * 8, cudaMemcpyHostToDevice, ST));
     CU_TRY(cudaMemcpyAsync(dm + w0, valid, (size_t)nw * 8, cudaMemcpyHostToDevice, ST));
+    if ((rc = drives_end())) return rc;
     CU_TRY(cudaStreamSynchronize(ST));  // caller may reuse its buffers
     return B2_OK;
 }
@@ -812,6 +862,7 @@ int Engine::upload_rows(const uint32_t *wires, uint32_t n, bool drive_rows) {
         rows_key_ = key;
     } else {
         if (ptrs_key_ == key) return B2_OK;
+        CU_TRY(cudaStreamSynchronize(CIN));  // a scatter kernel may still be reading the old tables
         std::vector<uint64_t *> tv(n), tm(n);
         // two passes: the first may grow the extra store and move earlier rows
         for (int pass = 0; pass < 2; pass++)
@@ -834,14 +885,20 @@ int Engine::set_drives_lanes(const uint32_t *wires, uint32_t n, const uint64_t *
     if (n == 0) return B2_OK;
     if (src_stride < T_) return B2_ERR_RANGE;
     if ((rc = upload_rows(wires, n, true))) return rc;
-    if ((rc = ensure_stage((size_t)n * T_))) return rc;
-    CU_TRY(cudaMemcpy2DAsync(stage_val_, (size_t)T_ * 8, value, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyHostToDevice, ST));
-    CU_TRY(cudaMemcpy2DAsync(stage_vld_, (size_t)T_ * 8, valid, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyHostToDevice, ST));
+    if ((rc = ensure_stage(false, (size_t)n * T_))) return rc;
+    // copy-in stream: wait until the main stream has consumed the previous drives (early in the
+    // previous settle), then H2D + scatter while that settle is still running
+    CU_TRY(cudaStreamWaitEvent(CIN, EV(ev_drive_consumed_), 0));
+    CU_TRY(cudaMemcpy2DAsync(stage_val_[0], (size_t)T_ * 8, value, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyHostToDevice, CIN));
+    CU_TRY(cudaMemcpy2DAsync(stage_vld_[0], (size_t)T_ * 8, valid, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyHostToDevice, CIN));
     const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
     uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
     dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
-    k_scatter_rows<<<grid, block, 0, ST>>>(d_tv, d_tm, n, stage_val_, stage_vld_, T_, T_);
+    k_scatter_rows<<<grid, block, 0, CIN>>>(d_tv, d_tm, n, stage_val_[0], stage_vld_[0], T_, T_);
     LAUNCHED();
+    CU_TRY(cudaEventRecord(EV(ev_drives_ready_), CIN));
+    cin_pending_ = true;
+    CU_TRY(cudaStreamSynchronize(CIN));  // the caller may reuse its buffers; the main stream is not waited for
     return B2_OK;
 }
 
@@ -854,9 +911,11 @@ int Engine::fill_stimulus(const uint32_t *wires, uint32_t n, uint64_t seed, uint
     if ((rc = upload_rows(wires, n, true))) return rc;
     const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
     uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
+    if ((rc = drives_begin())) return rc;
     dim3 block(64, 4), grid((stride_ + 63) / 64, (n + 3) / 4);
     k_fill_stimulus<<<grid, block, 0, ST>>>(d_tv, d_tm, n, stride_, seed, word_base, mode);
     LAUNCHED();
+    if ((rc = drives_end())) return rc;
     return B2_OK;
 }
 
@@ -884,12 +943,15 @@ int Engine::run_levelised(bool async) {
     const uint32_t pairs = stride_ / 2;
     const Shape sh = shape_for(pairs);
     uint64_t *V = val_[cur_], *M = vld_[cur_];
+    int rc0 = drives_begin();
+    if (rc0) return rc0;
     if (net_.n_src) {
         const uint32_t rb = (net_.n_src + sh.block.y - 1) / sh.block.y;
         k_apply_drive<false><<<sh.pair_blocks * rb, sh.block, 0, ST>>>(drv_val_, drv_vld_, nullptr, nullptr, V, M, nullptr,
                                                                         net_.n_src, stride_, pairs, sh.pair_blocks);
         LAUNCHED();
     }
+    if (extra_rows_.empty() && (rc0 = drives_end())) return rc0;  // the drive rows may be refilled from here on
     for (const Level &lv : net_.levels) {
         if (lv.g2_end > lv.g2_begin) {
             Eval2Args a{d_fan0_, d_fan1_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
@@ -929,6 +991,7 @@ int Engine::run_levelised(bool async) {
     LAUNCHED();
     k_levelised_status<<<(stride_ + 255) / 256, 256, 0, ST>>>(d_conflict_, d_unsettled_, d_flags_, stride_, n_lanes_);
     LAUNCHED();
+    if ((rc0 = drives_end())) return rc0;
     CU_TRY(cudaMemcpyAsync(h_flags_, d_flags_, sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
     CU_TRY(cudaStreamSynchronize(ST));
     return h_flags_->any_conflict ? B2_RUN_CONFLICT : B2_RUN_OK;
@@ -937,6 +1000,7 @@ int Engine::run_levelised(bool async) {
 int Engine::run_jacobi(uint64_t max_steps) {
     int rc = ensure_second_buffer();
     if (rc) return rc;
+    if ((rc = drives_begin())) return rc;
     const uint32_t pairs = stride_ / 2;
     const Shape sh = shape_for(pairs);
     const uint64_t N = max_steps == UINT64_MAX ? UINT64_MAX : max_steps + 1;
@@ -971,7 +1035,10 @@ int Engine::run_jacobi(uint64_t max_steps) {
         }
         cold_ = false;
         k = 1;
-        if (net_.n_g2() + net_.n_wide() == 0) return B2_RUN_OK;
+        if (net_.n_g2() + net_.n_wide() == 0) {
+            if ((rc = drives_end())) return rc;
+            return B2_RUN_OK;
+        }
     }
     for (;;) {
         k++;
@@ -1015,6 +1082,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
         cur_ ^= 1;
         if (!h_flags_->any_live) break;
     }
+    if ((rc = drives_end())) return rc;
     if (h_flags_->any_conflict) return B2_RUN_CONFLICT;
     if (h_flags_->any_unsettled) return B2_RUN_MAX_STEPS_REACHED;
     return B2_RUN_OK;
@@ -1099,7 +1167,8 @@ int Engine::get_wire_state(uint32_t wire, uint32_t *p0, uint32_t *p1, size_t wor
     return B2_OK;
 }
 
-int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid, size_t dst_stride, bool dst_is_device) {
+int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid, size_t dst_stride, bool dst_is_device,
+                         bool async) {
     if (n && (!wires || !value || !valid)) return B2_ERR_NULL;
     int rc = ensure_lanes();
     if (rc) return rc;
@@ -1112,12 +1181,18 @@ int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uin
         LAUNCHED();
         return B2_OK;
     }
-    if ((rc = ensure_stage((size_t)n * T_))) return rc;
-    k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], stage_val_, stage_vld_, stride_, 0, T_, T_);
+    if ((rc = ensure_stage(true, (size_t)n * T_))) return rc;
+    // main stream: gather into the out-stage once the previous D2H has drained it;
+    // copy-out stream: D2H while the main stream goes on with the next tile
+    CU_TRY(cudaStreamWaitEvent(ST, EV(ev_out_free_), 0));
+    k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], stage_val_[1], stage_vld_[1], stride_, 0, T_, T_);
     LAUNCHED();
-    CU_TRY(cudaMemcpy2DAsync(value, dst_stride * 8, stage_val_, (size_t)T_ * 8, (size_t)T_ * 8, n, cudaMemcpyDeviceToHost, ST));
-    CU_TRY(cudaMemcpy2DAsync(valid, dst_stride * 8, stage_vld_, (size_t)T_ * 8, (size_t)T_ * 8, n, cudaMemcpyDeviceToHost, ST));
-    CU_TRY(cudaStreamSynchronize(ST));
+    CU_TRY(cudaEventRecord(EV(ev_gathered_), ST));
+    CU_TRY(cudaStreamWaitEvent(COUT, EV(ev_gathered_), 0));
+    CU_TRY(cudaMemcpy2DAsync(value, dst_stride * 8, stage_val_[1], (size_t)T_ * 8, (size_t)T_ * 8, n, cudaMemcpyDeviceToHost, COUT));
+    CU_TRY(cudaMemcpy2DAsync(valid, dst_stride * 8, stage_vld_[1], (size_t)T_ * 8, (size_t)T_ * 8, n, cudaMemcpyDeviceToHost, COUT));
+    CU_TRY(cudaEventRecord(EV(ev_out_free_), COUT));
+    if (!async) CU_TRY(cudaStreamSynchronize(COUT));
     return B2_OK;
 }
 

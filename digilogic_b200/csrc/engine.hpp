@@ -45,7 +45,8 @@ class Engine {
 
     int get_wire_state(uint32_t wire, uint32_t *p0, uint32_t *p1, size_t words);
     int get_wire_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint32_t nw, uint64_t *value, uint64_t *valid);
-    int gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid, size_t dst_stride, bool dst_is_device);
+    int gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid, size_t dst_stride, bool dst_is_device,
+                     bool async = false);
     int pack_sim_state(const uint32_t *wires, uint32_t n, uint8_t *p0, uint8_t *p1, size_t cap, uint64_t *bit_len);
 
     // info
@@ -60,7 +61,9 @@ class Engine {
     int ensure_device();
     int ensure_lanes();
     int ensure_second_buffer();
-    int ensure_stage(size_t words_per_plane);
+    int ensure_stage(bool out, size_t words_per_plane);
+    int drives_begin();   // main stream is about to touch the drive store
+    int drives_end();     // ... and is done with it
     int ensure_rows_buffer(uint32_t n);
     void free_store();
     int drive_target(uint32_t bitnet, uint64_t **val, uint64_t **vld);  // row pointers for a bit-net's drive
@@ -99,9 +102,14 @@ class Engine {
     uint64_t *d_changed_ = nullptr, *d_conf_step_ = nullptr, *d_live_ = nullptr, *d_conflict_ = nullptr, *d_unsettled_ = nullptr;
     RunFlags *d_flags_ = nullptr, *h_flags_ = nullptr;
 
-    // staging
-    uint64_t *stage_val_ = nullptr, *stage_vld_ = nullptr;
-    size_t stage_words_ = 0;
+    // staging for host <-> device plane transfers, on their own copy streams so that the H2D of
+    // the next tile and the D2H of the previous one overlap the settle of the current tile
+    uint64_t *stage_val_[2] = {nullptr, nullptr}, *stage_vld_[2] = {nullptr, nullptr};  // [0] in, [1] out
+    size_t stage_words_[2] = {0, 0};
+    void *cin_stream_ = nullptr, *cout_stream_ = nullptr;                  // cudaStream_t
+    void *ev_drive_consumed_ = nullptr, *ev_drives_ready_ = nullptr;       // cudaEvent_t
+    void *ev_gathered_ = nullptr, *ev_out_free_ = nullptr;
+    bool cin_pending_ = false;
     uint32_t *d_rows_ = nullptr;
     uint32_t rows_cap_ = 0;
     uint64_t rows_key_ = 0, ptrs_key_ = 0;  // hashes of the cached wire lists (0 = none)

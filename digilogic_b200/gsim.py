@@ -312,9 +312,10 @@ class Simulator:
                                               out_value.strides[0] // 8), "gather_wires_host")
         return out_value, out_valid
 
-    def gather_wires_ptr(self, wires, value_ptr, valid_ptr, stride_words, device: bool):
+    def gather_wires_ptr(self, wires, value_ptr, valid_ptr, stride_words, device: bool, async_: bool = False):
         wires = np.ascontiguousarray(wires, np.uint32)
-        fn = self._lib.b2_gather_wires_device if device else self._lib.b2_gather_wires_host
+        fn = self._lib.b2_gather_wires_device if device else (
+            self._lib.b2_gather_wires_host_async if async_ else self._lib.b2_gather_wires_host)
         _check(fn(self._h, _p(wires), wires.size, C.c_void_p(value_ptr), C.c_void_p(valid_ptr), stride_words), "gather_wires")
 
     def pack_sim_state(self, wires):

@@ -159,8 +159,10 @@ int b2_get_wire_state(b2_sim *s, uint32_t wire, uint32_t *plane0, uint32_t *plan
 /* Drive bit `bit` of `wire` in lanes [64*lane_word0, 64*(lane_word0+n_words)) from host words. */
 int b2_set_wire_drive_lanes(b2_sim *s, uint32_t wire, uint32_t bit, uint32_t lane_word0, uint32_t n_words,
                             const uint64_t *value, const uint64_t *valid);
-/* Drive bit 0 of n wires for all lane-words from host planes laid out [n][src_stride] (one
-   staged copy + one scatter kernel).  value/valid should be pinned for an asynchronous copy. */
+/* Drive bit 0 of n wires for all lane-words from host planes laid out [n][src_stride]: one
+   staged copy + one scatter kernel on a private copy stream.  Returns when the host planes
+   have been consumed — it does not wait for settles still running on the main stream, so the
+   drives of the next tile can be uploaded while the current tile settles. */
 int b2_set_drives_lanes(b2_sim *s, const uint32_t *wires, uint32_t n, const uint64_t *value, const uint64_t *valid,
                         size_t src_stride_words);
 /* Counter-based stimulus generated on the device: input i (position in `wires`), global
@@ -187,6 +189,13 @@ int b2_gather_wires_device(b2_sim *s, const uint32_t *wires, uint32_t n, uint64_
 /* Same into HOST planes [n][dst_stride_words] (staged through a device buffer, one copy per plane). */
 int b2_gather_wires_host(b2_sim *s, const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid,
                          size_t dst_stride_words);
+
+/* Same, but returns once the gather and the copy are queued (the copy runs on a private copy
+   stream and overlaps later settles); the host planes (pinned memory) are valid after the next
+   b2_sim_synchronize().  At most one such read-back is in flight: a second call waits on the
+   device, not on the host, for the first copy to drain the staging buffer. */
+int b2_gather_wires_host_async(b2_sim *s, const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid,
+                               size_t dst_stride_words);
 
 /* Bulk read-back in the netcode `SimState` layout (replaces the per-net get_net_state +
    SimState::push_net loop of crates/digilogic_netcode/src/server.rs:375-383 and
