@@ -305,7 +305,8 @@ def run_b200(args):
 
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words_local, w_begin, barrier)
+        e2e = run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words_local, w_begin, barrier,
+                      (out_v, out_m))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -331,7 +332,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words_local, w_begin, barrier):
+def run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words_local, w_begin, barrier, dev_out):
     """Same metric through the C ABI with host buffers (b2_set_drives_lanes / b2_gather_wires_host_async):
     every tile's stimulus planes are copied from pinned host memory and its output planes back to
     pinned host memory inside the timed region."""
@@ -361,11 +362,13 @@ def run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        worst = runner.run_host(inv, inm, outv, outm, words_local)   # returns after the last D2H copy
         if world > 1:
+            # host planes go to this rank's host memory; the cross-rank gather moves the device copies
             from digilogic_b200.batch import gather_output_planes
-            dv, dm = hout_v.to(dev, non_blocking=True), hout_m.to(dev, non_blocking=True)
-            gather_output_planes(dv, dm, world)
+            worst = runner.run_host(inv, inm, outv, outm, words_local, dev_out[0], dev_out[1])
+            gather_output_planes(dev_out[0], dev_out[1], world)
+        else:
+            worst = runner.run_host(inv, inm, outv, outm, words_local)   # returns after the last D2H copy
     barrier()
     ms = (time.perf_counter() - t0) * 1e3   # host clock: the path ends in host memory
     t = torch.tensor([ms], dtype=torch.float64, device=dev)

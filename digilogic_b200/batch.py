@@ -80,12 +80,15 @@ class BatchRunner:
         return worst
 
     # -- host stimulus through the C ABI (end-to-end path: H2D copies and D2H read-back included)
-    def run_host(self, in_value, in_valid, out_value, out_valid, n_words: int | None = None) -> SimulationRunResult:
+    def run_host(self, in_value, in_valid, out_value, out_valid, n_words: int | None = None,
+                 dev_out_value=None, dev_out_valid=None) -> SimulationRunResult:
         """in_*: host arrays [n_inputs, ring_words]; out_*: host arrays [n_outputs, ring_words] (numpy
         views of pinned memory).  n_words lane-words are processed; if that is more than the host
         arrays hold, the arrays are used as a ring (tile i reads/writes slot i mod ring).  The drives
         of tile i+1 are uploaded while tile i settles, and the outputs of tile i are copied out
-        while tile i+1 settles (the engine's copy streams); the call returns after the last copy."""
+        while tile i+1 settles (the engine's copy streams); the call returns after the last copy.
+        dev_out_*: optional device tensors [n_outputs, n_words] that also receive the output planes
+        (multi-GPU runs all-gather those with NCCL)."""
         ring_words = in_value.shape[1]
         n_words = ring_words if n_words is None else n_words
         assert n_words % self.tile_words == 0 and ring_words % self.tile_words == 0
@@ -107,6 +110,9 @@ class BatchRunner:
             o = 8 * (w0 % ring_words)
             self.sim.gather_wires_ptr(self.outputs, out_value.ctypes.data + o, out_valid.ctypes.data + o, out_stride,
                                       device=False, async_=True)
+            if dev_out_value is not None:
+                self.sim.gather_wires_ptr(self.outputs, dev_out_value.data_ptr() + 8 * w0, dev_out_valid.data_ptr() + 8 * w0,
+                                          dev_out_value.stride(0), device=True)
         self.sim.synchronize()
         return worst
 
