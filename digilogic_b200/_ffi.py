@@ -41,6 +41,7 @@ SIGNATURES = {
     "b2_sim_set_device": (i32, [vp, i32]),
     "b2_sim_set_stream": (i32, [vp, vp]),
     "b2_sim_synchronize": (i32, [vp]),
+    "b2_sim_set_option": (i32, [vp, i32, C.c_int64]),
     "b2_sim_set_lanes": (i32, [vp, u64]),
     "b2_sim_max_lanes": (u64, [vp, u64]),
     "b2_set_wire_drive": (i32, [vp, u32, pu32, pu32, sz]),

@@ -150,6 +150,14 @@ int b2_sim_set_device(b2_sim *s, int device) { return s ? s->e->set_device(devic
 int b2_sim_set_stream(b2_sim *s, void *stream) { return s ? s->e->set_stream(stream) : B2_ERR_NULL; }
 int b2_sim_synchronize(b2_sim *s) { return s ? s->e->synchronize() : B2_ERR_NULL; }
 
+int b2_sim_set_option(b2_sim *s, int option, int64_t value) {
+    if (!s) return B2_ERR_NULL;
+    switch (option) {
+        case B2_OPT_RESIDENT_KERNEL: s->e->set_use_resident(value != 0); return B2_OK;
+        default: return B2_ERR_INVALID_ARG;
+    }
+}
+
 int b2_sim_set_lanes(b2_sim *s, uint64_t n_lanes) {
     if (!s) return B2_ERR_NULL;
     GUARD_BEGIN

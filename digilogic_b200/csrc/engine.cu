@@ -447,6 +447,193 @@ __global__ void __launch_bounds__(256) k_pack_lane0(const uint32_t *rows, uint32
     out1[byte] = (uint8_t)b1;
 }
 
+// ---------------------------------------------------------------------------- resident kernel
+//
+// Small netlists: the whole wire-state store of a few lane-words fits in shared memory, so one
+// CTA runs the complete run_sim loop for its lane-words on chip — every application of G reads
+// its fan-in from shared memory, __syncthreads() separates applications, and nothing but the
+// drives (in) and the final state + lane status (out) touches HBM.  Lanes are independent, so
+// CTAs never talk to each other and each stops at its own fixed point.  This is the path of the
+// reference's real use (GUI: one lane, max_steps = 10 000, latches that may oscillate).
+struct ResidentArgs {
+    const uint32_t *fan0, *fan1;
+    const uint8_t *kind2;
+    const uint32_t *woff, *win;
+    const uint8_t *wkind, *wnsel;
+    const uint32_t *xrows;            // rows with an external drive on a gate output
+    const uint64_t *xval, *xvld;      // their drives [n_extra][stride]
+    const uint64_t *dval, *dvld;      // source drives [n_src][stride]
+    uint64_t *val, *vld;              // store (current buffer), read at start, written at the end
+    uint64_t *conflict, *unsettled;   // lane status words [stride]
+    RunFlags *flags;
+    unsigned long long *max_apps;     // max applications over CTAs
+    uint32_t n_src, n_g2, n_wide, n_extra, n_rows;
+    uint32_t stride, wpc;             // words per row; lane-words per CTA
+    uint64_t n_lanes;
+    uint64_t last;                    // index of the final, check-only application
+    int cold;
+};
+
+__device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g, const uint64_t *av, const uint64_t *am, uint32_t wpc,
+                                               uint32_t j, u64 &rv, u64 &rm) {
+    const uint32_t b = a.woff[g], e = a.woff[g + 1], kind = a.wkind[g];
+    if (kind == K_MUX) {
+        const uint32_t ns = a.wnsel[g];
+        u64 allv = ~0ull, pv = 0, pm = 0;
+        for (uint32_t s = 0; s < ns; s++) allv &= am[(size_t)a.win[b + s] * wpc + j];
+        for (uint32_t d = 0; b + ns + d < e; d++) {
+            u64 match = ~0ull;
+            for (uint32_t s = 0; s < ns; s++) match &= ~(av[(size_t)a.win[b + s] * wpc + j] ^ (((d >> s) & 1) ? ~0ull : 0ull));
+            const size_t r = (size_t)a.win[b + ns + d] * wpc + j;
+            pv |= match & av[r];
+            pm |= match & am[r];
+        }
+        rm = allv & pm;
+        rv = (allv & pv) | ~rm;
+    } else {
+        const uint32_t base = kind >= K_NAND ? kind - 3 : kind;
+        size_t r = (size_t)a.win[b] * wpc + j;
+        rv = av[r];
+        rm = am[r];
+        for (uint32_t i = b + 1; i < e; i++) {
+            r = (size_t)a.win[i] * wpc + j;
+            gate_word(base, rv, rm, av[r], am[r], rv, rm);
+        }
+        if (kind >= K_NAND) rv = ~rv | ~rm;
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) {
+    extern __shared__ uint64_t smem[];
+    const uint32_t wpc = a.wpc, tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t w0 = blockIdx.x * wpc;
+    const size_t plane = (size_t)a.n_rows * wpc;
+    uint64_t *AV = smem, *AM = smem + plane, *BV = smem + 2 * plane, *BM = smem + 3 * plane;
+    uint64_t *s_changed = smem + 4 * plane, *s_conf = s_changed + wpc, *s_live = s_conf + wpc, *s_conflict = s_live + wpc,
+             *s_unsettled = s_conflict + wpc;
+    __shared__ unsigned s_any;
+
+    // ---- load: the current state, or the cold start W_1 = resolve(D, all outputs High-Z) = D
+    for (size_t i = tid; i < plane; i += nt) {
+        const uint32_t row = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
+        u64 v = 0, m = 0;
+        if (w < a.stride) {
+            const size_t o = (size_t)row * a.stride + w;
+            if (!a.cold) {
+                v = a.val[o];
+                m = a.vld[o];
+            } else if (row < a.n_src) {
+                v = a.dval[o];
+                m = a.dvld[o];
+            }
+        }
+        AV[i] = v;
+        AM[i] = m;
+    }
+    if (tid < wpc) {
+        s_changed[tid] = 0;
+        s_conf[tid] = 0;
+        s_live[tid] = (w0 + tid < a.stride) ? lane_mask_of(w0 + tid, a.n_lanes) : 0;
+        s_conflict[tid] = 0;
+        s_unsettled[tid] = 0;
+    }
+    __syncthreads();
+    if (a.cold) {
+        for (size_t i = tid; i < (size_t)a.n_extra * wpc; i += nt) {
+            const uint32_t x = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
+            if (w < a.stride) {
+                AV[(size_t)a.xrows[x] * wpc + j] = a.xval[(size_t)x * a.stride + w];
+                AM[(size_t)a.xrows[x] * wpc + j] = a.xvld[(size_t)x * a.stride + w];
+            }
+        }
+        __syncthreads();
+    }
+
+    uint64_t k = a.cold ? 1 : 0;
+    unsigned long long apps = 0;
+    const size_t n_items = (size_t)(a.n_src + a.n_g2 + a.n_wide) * wpc;
+    if (a.n_g2 + a.n_wide > 0) {
+        for (;;) {
+            k++;
+            apps++;
+            const bool is_last = k == a.last;
+            // ---- B = G(A)
+            for (size_t i = tid; i < n_items; i += nt) {
+                const uint32_t row = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
+                u64 rv, rm;
+                if (row < a.n_src) {
+                    rv = rm = 0;
+                    if (w < a.stride) {
+                        rv = a.dval[(size_t)row * a.stride + w];
+                        rm = a.dvld[(size_t)row * a.stride + w];
+                    }
+                } else if (row < a.n_src + a.n_g2) {
+                    const uint32_t g = row - a.n_src;
+                    const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j;
+                    gate_word(a.kind2[g], AV[r0], AM[r0], AV[r1], AM[r1], rv, rm);
+                } else {
+                    wide_gate_word(a, row - a.n_src - a.n_g2, AV, AM, wpc, j, rv, rm);
+                }
+                const u64 d = (rv ^ AV[i]) | (rm ^ AM[i]);
+                BV[i] = rv;
+                BM[i] = rm;
+                if (d) atomicOr((unsigned long long *)&s_changed[j], d);
+            }
+            __syncthreads();
+            // ---- drives on gate outputs: merge + conflict
+            if (a.n_extra) {
+                for (size_t i = tid; i < (size_t)a.n_extra * wpc; i += nt) {
+                    const uint32_t x = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
+                    if (w < a.stride) {
+                        const size_t r = (size_t)a.xrows[x] * wpc + j;
+                        const u64 dv = a.xval[(size_t)x * a.stride + w], dm = a.xvld[(size_t)x * a.stride + w];
+                        const u64 c = (dv | dm) & (BV[r] | BM[r]);
+                        BV[r] |= dv;
+                        BM[r] |= dm;
+                        if (c) atomicOr((unsigned long long *)&s_conf[j], c);
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- per-lane bookkeeping (same rules as k_status_step)
+            if (tid == 0) s_any = 0;
+            __syncthreads();
+            if (tid < wpc) {
+                u64 cf = s_conflict[tid], lv = s_live[tid];
+                if (!is_last) cf |= s_conf[tid] & lv;
+                lv &= s_changed[tid] & ~cf;
+                s_live[tid] = lv;
+                s_conflict[tid] = cf;
+                if (is_last) s_unsettled[tid] = lv;
+                s_changed[tid] = 0;
+                s_conf[tid] = 0;
+                if (lv) atomicOr(&s_any, 1u);
+            }
+            __syncthreads();
+            if (is_last) break;  // check-only application: the state stays W_{N+1}
+            uint64_t *t;
+            t = AV; AV = BV; BV = t;
+            t = AM; AM = BM; BM = t;
+            if (!s_any) break;
+        }
+    }
+    // ---- write back
+    for (size_t i = tid; i < plane; i += nt) {
+        const uint32_t row = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
+        if (w < a.stride) {
+            a.val[(size_t)row * a.stride + w] = AV[i];
+            a.vld[(size_t)row * a.stride + w] = AM[i];
+        }
+    }
+    if (tid < wpc && w0 + tid < a.stride) {
+        a.conflict[w0 + tid] = s_conflict[tid];
+        a.unsettled[w0 + tid] = s_unsettled[tid];
+        if (s_conflict[tid]) atomicOr(&a.flags->any_conflict, 1u);
+        if (s_unsettled[tid]) atomicOr(&a.flags->any_unsettled, 1u);
+    }
+    if (tid == 0) atomicMax(a.max_apps, apps);
+}
+
 // ---------------------------------------------------------------------------- Engine: setup
 
 Engine::Engine(Compiled &&net) : net_(std::move(net)) {}
@@ -466,6 +653,7 @@ Engine::~Engine() {
         cudaFree(d_wide_kind_);
         cudaFree(d_wide_nsel_);
         cudaFree(d_flags_);
+        cudaFree(d_max_apps_);
         if (h_flags_) cudaFreeHost(h_flags_);
         if (own_stream_ && stream_) cudaStreamDestroy(ST);
         if (cin_stream_) cudaStreamDestroy(CIN);
@@ -1088,6 +1276,73 @@ int Engine::run_jacobi(uint64_t max_steps) {
     return B2_RUN_OK;
 }
 
+// Shared-memory budget of the resident kernel (bytes of dynamic shared memory per CTA).
+static const size_t kResidentSmem = 200 * 1024;
+
+// 0 = not applicable, else lane-words per CTA
+uint32_t Engine::resident_wpc() const {
+    if (net_.n_rows == 0) return 0;
+    const size_t per_word = (size_t)net_.n_rows * 32 + 5 * 8;
+    if (per_word > kResidentSmem) return 0;
+    size_t wpc = kResidentSmem / per_word;
+    const size_t spread = ((size_t)stride_ + 147) / 148;  // enough CTAs to cover the SMs first
+    if (wpc > spread) wpc = spread;
+    if (wpc > 64) wpc = 64;
+    return (uint32_t)(wpc ? wpc : 1);
+}
+
+int Engine::run_resident(uint64_t max_steps) {
+    const uint32_t wpc = resident_wpc();
+    const uint64_t N = max_steps == UINT64_MAX ? UINT64_MAX : max_steps + 1;
+    const uint64_t last = N >= UINT64_MAX - 2 ? UINT64_MAX : N + 2;
+    const uint32_t n_extra = (uint32_t)extra_rows_.size();
+    int rc;
+    if ((rc = drives_begin())) return rc;
+    if (n_extra && extra_rows_dirty_) {
+        CU_TRY(cudaMemcpyAsync(d_extra_rows_, extra_rows_.data(), (size_t)n_extra * 4, cudaMemcpyHostToDevice, ST));
+        extra_rows_dirty_ = false;
+    }
+    if (!d_max_apps_) CU_TRY(cudaMalloc((void **)&d_max_apps_, 8));
+    CU_TRY(cudaMemsetAsync(d_max_apps_, 0, 8, ST));
+    k_clear_flags<<<1, 1, 0, ST>>>(d_flags_);
+    LAUNCHED();
+    ResidentArgs a;
+    a.fan0 = d_fan0_; a.fan1 = d_fan1_; a.kind2 = d_kind2_;
+    a.woff = d_wide_off_; a.win = d_wide_in_; a.wkind = d_wide_kind_; a.wnsel = d_wide_nsel_;
+    a.xrows = d_extra_rows_; a.xval = xdrv_val_; a.xvld = xdrv_vld_;
+    a.dval = drv_val_; a.dvld = drv_vld_;
+    a.val = val_[cur_]; a.vld = vld_[cur_];
+    a.conflict = d_conflict_; a.unsettled = d_unsettled_;
+    a.flags = d_flags_;
+    a.max_apps = d_max_apps_;
+    a.n_src = net_.n_src; a.n_g2 = net_.n_g2(); a.n_wide = net_.n_wide(); a.n_extra = n_extra; a.n_rows = net_.n_rows;
+    a.stride = stride_; a.wpc = wpc;
+    a.n_lanes = n_lanes_;
+    a.last = last;
+    a.cold = cold_ ? 1 : 0;
+    const size_t smem = ((size_t)net_.n_rows * wpc * 4 + (size_t)wpc * 5) * 8;
+    if (!resident_attr_set_) {
+        CU_TRY(cudaFuncSetAttribute(k_resident_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kResidentSmem + 4096)));
+        resident_attr_set_ = true;
+    }
+    const size_t items = (size_t)net_.n_rows * wpc;
+    const uint32_t threads = items >= 1024 ? 1024 : (items >= 256 ? 512 : 128);
+    const uint32_t ctas = (stride_ + wpc - 1) / wpc;
+    k_resident_run<<<ctas, threads, smem, ST>>>(a);
+    LAUNCHED();
+    unsigned long long apps = 0;
+    CU_TRY(cudaMemcpyAsync(h_flags_, d_flags_, sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaMemcpyAsync(&apps, d_max_apps_, 8, cudaMemcpyDeviceToHost, ST));
+    if ((rc = drives_end())) return rc;
+    CU_TRY(cudaStreamSynchronize(ST));
+    cold_ = false;
+    last_mode_ = 3;
+    last_apps_ = apps;
+    if (h_flags_->any_conflict) return B2_RUN_CONFLICT;
+    if (h_flags_->any_unsettled) return B2_RUN_MAX_STEPS_REACHED;
+    return B2_RUN_OK;
+}
+
 int Engine::run(uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled, bool async) {
     int rc = ensure_lanes();
     if (rc) return -rc;
@@ -1102,8 +1357,10 @@ int Engine::run(uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled, boo
         last_mode_ = 0;
         last_apps_ = 0;
         result = B2_RUN_CONFLICT;
-    } else if (!net_.cyclic && max_steps >= net_.depth) {
+    } else if (!net_.cyclic && max_steps >= net_.depth && !(stride_ <= 4 && resident_wpc() && use_resident_)) {
         result = run_levelised(async && !conflict && !unsettled);
+    } else if (use_resident_ && resident_wpc()) {
+        result = run_resident(max_steps);  // small netlist: the whole run_sim loop on chip
     } else {
         result = run_jacobi(max_steps);
     }

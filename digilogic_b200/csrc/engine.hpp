@@ -56,6 +56,7 @@ class Engine {
     uint64_t store_bytes() const { return store_bytes_; }
     uint32_t last_mode() const { return last_mode_; }
     uint64_t last_applications() const { return last_apps_; }
+    void set_use_resident(bool on) { use_resident_ = on; }
 
    private:
     int ensure_device();
@@ -70,6 +71,8 @@ class Engine {
     int upload_rows(const uint32_t *wires, uint32_t n, bool drive_rows);
     int run_levelised(bool async);
     int run_jacobi(uint64_t max_steps);
+    int run_resident(uint64_t max_steps);
+    uint32_t resident_wpc() const;
 
     Compiled net_;
     int device_ = -1;
@@ -117,6 +120,8 @@ class Engine {
     size_t pack_cap_ = 0;
 
     bool cold_ = true;
+    bool use_resident_ = true, resident_attr_set_ = false;
+    unsigned long long *d_max_apps_ = nullptr;
     uint32_t last_mode_ = 0;
     uint64_t last_apps_ = 0;
 };

@@ -239,6 +239,11 @@ class Simulator:
     def set_stream(self, stream_handle: int | None):
         _check(self._lib.b2_sim_set_stream(self._h, C.c_void_p(stream_handle or 0)), "set_stream")
 
+    OPT_RESIDENT_KERNEL = 1
+
+    def set_option(self, option: int, value: int):
+        _check(self._lib.b2_sim_set_option(self._h, option, value), "set_option")
+
     def synchronize(self):
         _check(self._lib.b2_sim_synchronize(self._h), "synchronize")
 

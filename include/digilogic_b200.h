@@ -116,7 +116,7 @@ typedef struct b2_sim_info {
     uint32_t lane_words;    /* 64-lane words per row in use */
     uint32_t row_stride;    /* allocated words per row */
     uint64_t store_bytes;   /* device bytes held by this simulator */
-    uint32_t last_mode;     /* 0 none, 1 levelised, 2 unit-delay (Jacobi) */
+    uint32_t last_mode;     /* 0 none, 1 levelised, 2 unit-delay (Jacobi) in HBM, 3 unit-delay resident in shared memory */
     uint32_t reserved;
     uint64_t last_applications; /* whole-netlist evaluations made by the last run */
 } b2_sim_info;
@@ -131,6 +131,12 @@ int b2_wire_width(const b2_sim *s, uint32_t wire, uint8_t *out_width);
    default stream).  Without this call the simulator creates a private non-blocking stream. */
 int b2_sim_set_device(b2_sim *s, int device);
 int b2_sim_set_stream(b2_sim *s, void *stream);
+/* Engine options (all default to the values shown). */
+enum b2_option {
+    B2_OPT_RESIDENT_KERNEL = 1 /* 1: netlists whose store fits in shared memory run the whole run_sim loop in
+                                  one on-chip kernel when the path is unit-delay or the lane count is tiny; 0: never */
+};
+int b2_sim_set_option(b2_sim *s, int option, int64_t value);
 /* Block until everything queued by this simulator has finished. */
 int b2_sim_synchronize(b2_sim *s);
 

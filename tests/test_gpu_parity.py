@@ -15,9 +15,10 @@ pytestmark = pytest.mark.gpu
 Z, X, L0, L1 = (0, 0), (1, 0), (0, 1), (1, 1)
 
 
-def both(nl: Netlist, n_lanes: int):
+def both(nl: Netlist, n_lanes: int, resident: bool = True):
     ob = nl.replay(oracle.Builder())
     sim = nl.replay(SimulatorBuilder()).build()
+    sim.set_option(sim.OPT_RESIDENT_KERNEL, int(resident))
     sim.set_lanes(n_lanes)
     return ob, sim
 
@@ -84,15 +85,17 @@ def test_single_lane_gsim_surface():
 @pytest.mark.parametrize("seed", range(4))
 @pytest.mark.parametrize("cyclic", [False, True])
 @pytest.mark.parametrize("n_lanes", [1, 100, 64 * 37])
-def test_random_netlists_vs_scalar_oracle(seed, cyclic, n_lanes):
+@pytest.mark.parametrize("resident", [True, False])
+def test_random_netlists_vs_scalar_oracle(seed, cyclic, n_lanes, resident):
     """Random netlists (n-ary gates and muxes included), 4-state stimulus, warm restarts and a
     max_steps sweep that crosses the levelised/unit-delay switch."""
     rng = np.random.default_rng(77 * seed + cyclic)
     n_in, n_gates = 6, 48
     nl, first_in = random_netlist(rng, n_in, n_gates, cyclic=cyclic, wide=True, mux=True)
-    ob, sim = both(nl, n_lanes)
+    ob, sim = both(nl, n_lanes, resident)
     lanes = oracle.Lanes(ob, n_lanes)
     words = lanes.words
+    modes = set()
     for rnd, max_steps in enumerate([0, 1, 2, 3, 5, 8, 60, 7, 0, 1000]):
         for i in range(n_in):
             if rng.random() < 0.7:
@@ -105,6 +108,8 @@ def test_random_netlists_vs_scalar_oracle(seed, cyclic, n_lanes):
         assert int(res) == int(status.max()), (rnd, max_steps)
         rv, rm = lanes.get_all(nl.n_wires)
         compare_all_wires(sim, rv, rm, nl.n_wires, n_lanes)
+        modes.add(sim.info.last_mode)
+    assert (3 in modes) == resident and (2 in modes) == (not resident), modes
 
 
 @pytest.mark.parametrize("n_lanes,n_gates", [(64 * 64, 3000), (64 * 600, 500)])
@@ -138,7 +143,7 @@ def test_random_dag_vs_bitsliced_oracle(n_lanes, n_gates):
     for ms in (depth // 2, depth - 1):
         c_ref, u_ref = bs2.run(ms)
         res, conflict, unsettled = sim2.run_sim_lanes(ms)
-        assert sim2.info.last_mode == 2
+        assert sim2.info.last_mode in (2, 3)
         assert (conflict == c_ref).all() and ((unsettled ^ u_ref) & lane_mask(n_lanes)).max() == 0
         rv, rm = bs2.get_all()
         compare_all_wires(sim2, rv, rm, nl.n_wires, n_lanes)
@@ -146,14 +151,14 @@ def test_random_dag_vs_bitsliced_oracle(n_lanes, n_gates):
 
 def test_conflict_lanes():
     """A driven gate output conflicts exactly in the lanes whose drive is not High-Z; both paths."""
-    for cyclic in (False, True):
+    for cyclic, resident in ((False, True), (True, True), (True, False), (False, False)):
         nl = Netlist()
         a, c, o, q, qn = (nl.add_wire() for _ in range(5))
         nl.add_gate(AND, [a, c], o)
         if cyclic:
             nl.add_gate(NAND, [a, qn], q)
             nl.add_gate(NAND, [c, q], qn)
-        ob, sim = both(nl, 64)
+        ob, sim = both(nl, 64, resident)
         lanes = oracle.Lanes(ob, 64)
         ones = np.array([0xFFFFFFFFFFFFFFFF], np.uint64)
         dv, dm = np.array([0x00FF], np.uint64), np.array([0x0F0F], np.uint64)
