@@ -660,6 +660,8 @@ Engine::~Engine() {
         if (cout_stream_) cudaStreamDestroy(COUT);
         for (void *e : {ev_drive_consumed_, ev_drives_ready_, ev_gathered_, ev_out_free_})
             if (e) cudaEventDestroy(EV(e));
+        for (void *e : ev_flags_)
+            if (e) cudaEventDestroy(EV(e));
     }
 }
 
@@ -774,9 +776,14 @@ int Engine::ensure_device() {
     if ((rc = upload(&d_wide_in_, net_.wide_in))) return rc;
     if ((rc = upload(&d_wide_kind_, net_.wide_kind))) return rc;
     if ((rc = upload(&d_wide_nsel_, net_.wide_nsel))) return rc;
-    CU_TRY(cudaMalloc((void **)&d_flags_, sizeof(RunFlags)));
-    CU_TRY(cudaMemset(d_flags_, 0, sizeof(RunFlags)));
-    CU_TRY(cudaMallocHost((void **)&h_flags_, sizeof(RunFlags)));
+    CU_TRY(cudaMalloc((void **)&d_flags_, 8 * sizeof(RunFlags)));
+    CU_TRY(cudaMemset(d_flags_, 0, 8 * sizeof(RunFlags)));
+    CU_TRY(cudaMallocHost((void **)&h_flags_, 8 * sizeof(RunFlags)));
+    for (int i = 0; i < 8; i++) {
+        cudaEvent_t ev;
+        CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ev_flags_[i] = ev;
+    }
     {
         cudaStream_t a, b;
         CU_TRY(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
@@ -1126,6 +1133,7 @@ Shape shape_for(uint32_t pairs) {
 }  // namespace
 
 #define EVAL2_U 4
+static const uint32_t kFlagSlots = 8, kFlagLag = 2;
 
 int Engine::run_levelised(bool async) {
     const uint32_t pairs = stride_ / 2;
@@ -1205,6 +1213,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
     last_apps_ = 0;
     h_flags_->any_live = h_flags_->any_conflict = h_flags_->any_unsettled = 0;
     uint64_t k = 0;
+    uint32_t newest = 0;
     if (cold_) {
         // W_1 = resolve(D, all outputs High-Z) = D
         uint64_t *V = val_[cur_], *M = vld_[cur_];
@@ -1228,6 +1237,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
             return B2_RUN_OK;
         }
     }
+    const uint64_t first_k = k + 1;
     for (;;) {
         k++;
         last_apps_++;
@@ -1259,20 +1269,32 @@ int Engine::run_jacobi(uint64_t max_steps) {
             k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_extra, xdrv_val_, xdrv_vld_, BV, BM, d_conf_step_, stride_, 0);
             LAUNCHED();
         }
-        k_clear_flags<<<1, 1, 0, ST>>>(d_flags_);
+        // The lane bookkeeping of application k goes to flag slot k % kFlagSlots; the host reads it
+        // kFlagLag applications later, so the device never waits for the host.  Applications queued
+        // past the point where every lane has settled are no-ops on a fixed point.
+        const uint32_t slot = (uint32_t)(k % kFlagSlots);
+        k_clear_flags<<<1, 1, 0, ST>>>(d_flags_ + slot);
         LAUNCHED();
-        k_status_step<<<sgrid, 256, 0, ST>>>(d_changed_, d_conf_step_, d_live_, d_conflict_, d_unsettled_, d_flags_, stride_, n_lanes_,
-                                             is_last ? 0 : 1, is_last ? 1 : 0);
+        k_status_step<<<sgrid, 256, 0, ST>>>(d_changed_, d_conf_step_, d_live_, d_conflict_, d_unsettled_, d_flags_ + slot, stride_,
+                                             n_lanes_, is_last ? 0 : 1, is_last ? 1 : 0);
         LAUNCHED();
-        CU_TRY(cudaMemcpyAsync(h_flags_, d_flags_, sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
-        CU_TRY(cudaStreamSynchronize(ST));
-        if (is_last) break;  // check-only: MaxStepsReached lanes keep W_{N+1} (the current buffer)
-        cur_ ^= 1;
-        if (!h_flags_->any_live) break;
+        CU_TRY(cudaMemcpyAsync(h_flags_ + slot, d_flags_ + slot, sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
+        CU_TRY(cudaEventRecord(EV(ev_flags_[slot]), ST));
+        if (!is_last) cur_ ^= 1;  // check-only last application: MaxStepsReached lanes keep W_{N+1}
+        newest = slot;
+        bool stop = is_last;
+        if (!stop && k >= first_k + kFlagLag) {
+            const uint32_t old = (uint32_t)((k - kFlagLag) % kFlagSlots);
+            CU_TRY(cudaEventSynchronize(EV(ev_flags_[old])));
+            if (!h_flags_[old].any_live) stop = true;
+        }
+        if (stop) break;
     }
+    CU_TRY(cudaStreamSynchronize(ST));
+    const RunFlags fin = h_flags_[newest];  // conflict flags are cumulative; unsettled exists only on the last application
     if ((rc = drives_end())) return rc;
-    if (h_flags_->any_conflict) return B2_RUN_CONFLICT;
-    if (h_flags_->any_unsettled) return B2_RUN_MAX_STEPS_REACHED;
+    if (fin.any_conflict) return B2_RUN_CONFLICT;
+    if (fin.any_unsettled) return B2_RUN_MAX_STEPS_REACHED;
     return B2_RUN_OK;
 }
 

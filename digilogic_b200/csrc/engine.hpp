@@ -113,6 +113,7 @@ class Engine {
     void *ev_drive_consumed_ = nullptr, *ev_drives_ready_ = nullptr;       // cudaEvent_t
     void *ev_gathered_ = nullptr, *ev_out_free_ = nullptr;
     bool cin_pending_ = false;
+    void *ev_flags_[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t *d_rows_ = nullptr;
     uint32_t rows_cap_ = 0;
     uint64_t rows_key_ = 0, ptrs_key_ = 0;  // hashes of the cached wire lists (0 = none)
