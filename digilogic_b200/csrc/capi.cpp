@@ -154,6 +154,7 @@ int b2_sim_set_option(b2_sim *s, int option, int64_t value) {
     if (!s) return B2_ERR_NULL;
     switch (option) {
         case B2_OPT_RESIDENT_KERNEL: s->e->set_use_resident(value != 0); return B2_OK;
+        case B2_OPT_VALID_ELISION: s->e->set_valid_elision(value != 0); return B2_OK;
         default: return B2_ERR_INVALID_ARG;
     }
 }

@@ -127,10 +127,15 @@ struct Eval2Args {
     uint32_t stride;                  // words per row
     uint32_t pairs;                   // stride / 2
     uint32_t pair_blocks;
+    uint8_t *kv;                      // valid-plane elision (KV): row -> 1 if its valid plane is all-ones and not stored
 };
 
 // One- and two-input gates.  U gates per thread keep 4*U independent 128-bit loads in flight.
-template <int U, bool JACOBI>
+// KV (levelised only): a row whose fan-ins are all "known valid" for this tile has an all-ones
+// valid plane by construction (every gate maps valid inputs to a valid output), so that plane is
+// neither read nor written: 24 B instead of 48 B per gate-word.  Rows that may carry X/Z take the
+// full two-plane path; the result is bit-identical either way.
+template <int U, bool JACOBI, bool KV>
 __global__ void __launch_bounds__(256) k_eval2(const Eval2Args a) {
     const uint32_t pb = blockIdx.x % a.pair_blocks, gb = blockIdx.x / a.pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
@@ -140,17 +145,26 @@ __global__ void __launch_bounds__(256) k_eval2(const Eval2Args a) {
 
     uint32_t kind[U];
     ulonglong2 av[U], am[U], bv[U], bm[U], ov[U], om[U];
+    bool okv[U];
+    const ulonglong2 ones = make_ulonglong2(~0ull, ~0ull);
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const uint32_t g = g0 + u * blockDim.y;
+        okv[u] = false;
         if (g < a.g_end) {
             const uint32_t f0 = a.fan0[g], f1 = a.fan1[g];
             kind[u] = a.kind[g];
+            bool k0 = false, k1 = false;
+            if (KV) {
+                k0 = a.kv[f0] != 0;
+                k1 = a.kv[f1] != 0;
+                okv[u] = k0 && k1;  // NOT gates have f1 == f0
+            }
             av[u] = ld_stream(a.in_val + (size_t)f0 * a.stride + col);
-            am[u] = ld_stream(a.in_vld + (size_t)f0 * a.stride + col);
+            am[u] = (KV && k0) ? ones : ld_stream(a.in_vld + (size_t)f0 * a.stride + col);
             if (kind[u] != K_NOT) {
                 bv[u] = ld_stream(a.in_val + (size_t)f1 * a.stride + col);
-                bm[u] = ld_stream(a.in_vld + (size_t)f1 * a.stride + col);
+                bm[u] = (KV && k1) ? ones : ld_stream(a.in_vld + (size_t)f1 * a.stride + col);
             } else {
                 bv[u] = av[u];
                 bm[u] = am[u];
@@ -172,7 +186,8 @@ __global__ void __launch_bounds__(256) k_eval2(const Eval2Args a) {
             gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
             const size_t o = (size_t)(a.row_base + g) * a.stride + col;
             st_pair(a.out_val + o, rv);
-            st_pair(a.out_vld + o, rm);
+            if (!(KV && okv[u])) st_pair(a.out_vld + o, rm);
+            if (KV && pb == 0 && threadIdx.x == 0) a.kv[a.row_base + g] = okv[u] ? 1 : 0;
             if (JACOBI) {
                 dx |= (rv.x ^ ov[u].x) | (rm.x ^ om[u].x);
                 dy |= (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
@@ -192,7 +207,13 @@ struct WideArgs {
     uint64_t *out_val, *out_vld;
     uint64_t *changed;
     uint32_t g_begin, g_end, row_base, stride, pairs, pair_blocks;
+    uint8_t *kv;  // nullable: rows whose valid plane is elided (read as all-ones); outputs are always stored
 };
+
+__device__ __forceinline__ ulonglong2 ld_valid(const WideArgs &a, uint32_t row, size_t col) {
+    if (a.kv && a.kv[row]) return make_ulonglong2(~0ull, ~0ull);
+    return ld_stream(a.in_vld + (size_t)row * a.stride + col);
+}
 
 // n-ary gates (left fold, inverted kinds invert once at the end) and multiplexer slices.
 template <bool JACOBI>
@@ -209,7 +230,7 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
         const uint32_t ns = a.nsel[g];
         ulonglong2 allv = make_ulonglong2(~0ull, ~0ull);
         for (uint32_t s = 0; s < ns; s++) {
-            const ulonglong2 m = ld_stream(a.in_vld + (size_t)a.in[b + s] * a.stride + col);
+            const ulonglong2 m = ld_valid(a, a.in[b + s], col);
             allv.x &= m.x;
             allv.y &= m.y;
         }
@@ -223,7 +244,7 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
                 match.y &= ~(sv.y ^ want);
             }
             const size_t r = (size_t)a.in[b + ns + j] * a.stride + col;
-            const ulonglong2 dv = ld_stream(a.in_val + r), dm = ld_stream(a.in_vld + r);
+            const ulonglong2 dv = ld_stream(a.in_val + r), dm = ld_valid(a, a.in[b + ns + j], col);
             pv.x |= match.x & dv.x;
             pv.y |= match.y & dv.y;
             pm.x |= match.x & dm.x;
@@ -237,10 +258,10 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
         const uint32_t base = kind >= K_NAND ? kind - 3 : kind;  // fold with the positive op
         size_t r = (size_t)a.in[b] * a.stride + col;
         rv = ld_stream(a.in_val + r);
-        rm = ld_stream(a.in_vld + r);
+        rm = ld_valid(a, a.in[b], col);
         for (uint32_t i = b + 1; i < e; i++) {
             r = (size_t)a.in[i] * a.stride + col;
-            const ulonglong2 xv = ld_stream(a.in_val + r), xm = ld_stream(a.in_vld + r);
+            const ulonglong2 xv = ld_stream(a.in_val + r), xm = ld_valid(a, a.in[i], col);
             gate_word(base, rv.x, rm.x, xv.x, xm.x, rv.x, rm.x);
             gate_word(base, rv.y, rm.y, xv.y, xm.y, rv.y, rm.y);
         }
@@ -258,14 +279,17 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
     }
     st_pair(a.out_val + o, rv);
     st_pair(a.out_vld + o, rm);
+    if (a.kv && pb == 0 && threadIdx.x == 0) a.kv[a.row_base + g] = 0;
 }
 
 // Source rows take their external drive: out[row] = D[row] (rows [0, n_rows) of both stores).
+// kv (nullable, pre-set to 1 per source row): cleared when any in-use lane-word of the row's
+// valid plane is not all-ones.
 template <bool JACOBI>
 __global__ void __launch_bounds__(256) k_apply_drive(const uint64_t *dval, const uint64_t *dvld, const uint64_t *old_val,
                                                      const uint64_t *old_vld, uint64_t *out_val, uint64_t *out_vld,
                                                      uint64_t *changed, uint32_t n_rows, uint32_t stride, uint32_t pairs,
-                                                     uint32_t pair_blocks) {
+                                                     uint32_t pair_blocks, uint8_t *kv = nullptr, uint32_t words_in_use = 0) {
     const uint32_t pb = blockIdx.x % pair_blocks, rb = blockIdx.x / pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
     const uint32_t row = rb * blockDim.y + threadIdx.y;
@@ -280,6 +304,20 @@ __global__ void __launch_bounds__(256) k_apply_drive(const uint64_t *dval, const
     }
     st_pair(out_val + o, v);
     st_pair(out_vld + o, m);
+    if (kv) {
+        const bool bad = (col < words_in_use && m.x != ~0ull) || (col + 1 < words_in_use && m.y != ~0ull);
+        if (bad) kv[row] = 0;
+    }
+}
+
+// expands elided valid planes back to all-ones words (leaving the store plain two-plane)
+__global__ void __launch_bounds__(256) k_materialise_valid(uint64_t *vld, uint8_t *kv, uint32_t n_rows, uint32_t stride, uint32_t pairs,
+                                                           uint32_t pair_blocks) {
+    const uint32_t pb = blockIdx.x % pair_blocks, rb = blockIdx.x / pair_blocks;
+    const uint32_t pair = pb * blockDim.x + threadIdx.x;
+    const uint32_t row = rb * blockDim.y + threadIdx.y;
+    if (pair >= pairs || row >= n_rows) return;
+    if (kv[row]) st_pair(vld + (size_t)row * stride + (size_t)pair * 2, make_ulonglong2(~0ull, ~0ull));
 }
 
 // External drives on gate-driven rows: resolve(D, gate output) and conflict detection
@@ -407,13 +445,13 @@ __global__ void __launch_bounds__(256) k_fill_stimulus(uint64_t *const *row_val,
 // rows[] of (val, vld) -> dense planes [n][dst_stride]
 __global__ void __launch_bounds__(256) k_gather_rows(const uint32_t *rows, uint32_t n, const uint64_t *val, const uint64_t *vld,
                                                      uint64_t *dst_val, uint64_t *dst_vld, uint32_t stride, uint32_t word0,
-                                                     uint32_t n_words, size_t dst_stride) {
+                                                     uint32_t n_words, size_t dst_stride, const uint8_t *kv) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y;
     if (w >= n_words || i >= n) return;
     const size_t s = (size_t)rows[i] * stride + word0 + w;
     dst_val[(size_t)i * dst_stride + w] = val[s];
-    dst_vld[(size_t)i * dst_stride + w] = vld[s];
+    dst_vld[(size_t)i * dst_stride + w] = (kv && kv[rows[i]]) ? ~0ull : vld[s];
 }
 
 // dense planes [n][src_stride] -> drive rows given by pointer tables
@@ -676,6 +714,9 @@ void Engine::free_store() {
     cudaFree(xdrv_val_);
     cudaFree(xdrv_vld_);
     cudaFree(d_extra_rows_);
+    cudaFree(d_kv_);
+    d_kv_ = nullptr;
+    elided_ = false;
     cudaFree(d_changed_);
     cudaFree(d_conf_step_);
     cudaFree(d_live_);
@@ -877,6 +918,9 @@ int Engine::set_lanes(uint64_t n_lanes) {
         T_ = stride_ = 0;
         return rc;
     }
+    CU_TRY(cudaMalloc((void **)&d_kv_, net_.n_rows ? net_.n_rows : 1));
+    CU_TRY(cudaMemsetAsync(d_kv_, 0, net_.n_rows ? net_.n_rows : 1, ST));
+    store_bytes_ += net_.n_rows;
     cur_ = 0;
     cold_ = true;
     last_mode_ = 0;
@@ -1132,6 +1176,20 @@ Shape shape_for(uint32_t pairs) {
 }
 }  // namespace
 
+// Elided valid planes are expanded before any path that reads the store as plain two-plane rows.
+int Engine::materialise_valid() {
+    if (!elided_) return B2_OK;
+    const uint32_t pairs = stride_ / 2;
+    uint32_t bx = 1;
+    while (bx < pairs && bx < 256) bx <<= 1;
+    const dim3 block(bx, 256 / bx);
+    const uint32_t pair_blocks = (pairs + bx - 1) / bx, rb = (net_.n_rows + block.y - 1) / block.y;
+    k_materialise_valid<<<pair_blocks * rb, block, 0, ST>>>(vld_[cur_], d_kv_, net_.n_rows, stride_, pairs, pair_blocks);
+    LAUNCHED();
+    elided_ = false;
+    return B2_OK;
+}
+
 #define EVAL2_U 4
 static const uint32_t kFlagSlots = 8, kFlagLag = 2;
 
@@ -1141,25 +1199,32 @@ int Engine::run_levelised(bool async) {
     uint64_t *V = val_[cur_], *M = vld_[cur_];
     int rc0 = drives_begin();
     if (rc0) return rc0;
+    // valid-plane elision: only when no gate output carries an external drive (those merge into valid planes)
+    const bool kv = opt_elision_ && extra_rows_.empty();
+    if (kv && net_.n_src) CU_TRY(cudaMemsetAsync(d_kv_, 1, net_.n_src, ST));
     if (net_.n_src) {
         const uint32_t rb = (net_.n_src + sh.block.y - 1) / sh.block.y;
         k_apply_drive<false><<<sh.pair_blocks * rb, sh.block, 0, ST>>>(drv_val_, drv_vld_, nullptr, nullptr, V, M, nullptr,
-                                                                        net_.n_src, stride_, pairs, sh.pair_blocks);
+                                                                        net_.n_src, stride_, pairs, sh.pair_blocks,
+                                                                        kv ? d_kv_ : nullptr, T_);
         LAUNCHED();
     }
     if (extra_rows_.empty() && (rc0 = drives_end())) return rc0;  // the drive rows may be refilled from here on
     for (const Level &lv : net_.levels) {
         if (lv.g2_end > lv.g2_begin) {
             Eval2Args a{d_fan0_, d_fan1_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
-                        sh.pair_blocks};
+                        sh.pair_blocks, d_kv_};
             const uint32_t per = sh.block.y * EVAL2_U;
             const uint32_t gb = (lv.g2_end - lv.g2_begin + per - 1) / per;
-            k_eval2<EVAL2_U, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+            if (kv)
+                k_eval2<EVAL2_U, false, true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+            else
+                k_eval2<EVAL2_U, false, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
             LAUNCHED();
         }
         if (lv.wide_end > lv.wide_begin) {
             WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, V, M, V, M, nullptr, lv.wide_begin, lv.wide_end,
-                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks};
+                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr};
             const uint32_t gb = (lv.wide_end - lv.wide_begin + sh.block.y - 1) / sh.block.y;
             k_eval_wide<false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
             LAUNCHED();
@@ -1168,6 +1233,7 @@ int Engine::run_levelised(bool async) {
     cold_ = false;
     last_mode_ = 1;
     last_apps_ = 1;
+    elided_ = kv;  // a plain pass rewrites every valid plane, so nothing stays elided
     if (extra_rows_.empty()) {
         if (async) return B2_RUN_OK;  // no wire can conflict; status words are refreshed lazily
         CU_TRY(cudaMemsetAsync(d_conflict_, 0, (size_t)stride_ * 8, ST));
@@ -1196,6 +1262,7 @@ int Engine::run_levelised(bool async) {
 int Engine::run_jacobi(uint64_t max_steps) {
     int rc = ensure_second_buffer();
     if (rc) return rc;
+    if ((rc = materialise_valid())) return rc;
     if ((rc = drives_begin())) return rc;
     const uint32_t pairs = stride_ / 2;
     const Shape sh = shape_for(pairs);
@@ -1252,15 +1319,15 @@ int Engine::run_jacobi(uint64_t max_steps) {
         }
         if (net_.n_g2()) {
             Eval2Args a{d_fan0_, d_fan1_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
-                        sh.pair_blocks};
+                        sh.pair_blocks, nullptr};
             const uint32_t per = sh.block.y * EVAL2_U;
             const uint32_t gb = (net_.n_g2() + per - 1) / per;
-            k_eval2<EVAL2_U, true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+            k_eval2<EVAL2_U, true, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
             LAUNCHED();
         }
         if (net_.n_wide()) {
             WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, AV, AM, BV, BM, d_changed_, 0, net_.n_wide(),
-                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks};
+                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, nullptr};
             const uint32_t gb = (net_.n_wide() + sh.block.y - 1) / sh.block.y;
             k_eval_wide<true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
             LAUNCHED();
@@ -1319,6 +1386,7 @@ int Engine::run_resident(uint64_t max_steps) {
     const uint64_t last = N >= UINT64_MAX - 2 ? UINT64_MAX : N + 2;
     const uint32_t n_extra = (uint32_t)extra_rows_.size();
     int rc;
+    if ((rc = materialise_valid())) return rc;
     if ((rc = drives_begin())) return rc;
     if (n_extra && extra_rows_dirty_) {
         CU_TRY(cudaMemcpyAsync(d_extra_rows_, extra_rows_.data(), (size_t)n_extra * 4, cudaMemcpyHostToDevice, ST));
@@ -1410,6 +1478,7 @@ int Engine::get_wire_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint32_t nw
     int rc = ensure_lanes();
     if (rc) return rc;
     if ((uint64_t)w0 + nw > T_) return B2_ERR_RANGE;
+    if ((rc = materialise_valid())) return rc;
     const size_t o = (size_t)net_.row_of_bit[net_.bit_off[wire] + bit] * stride_ + w0;
     CU_TRY(cudaMemcpyAsync(value, val_[cur_] + o, (size_t)nw * 8, cudaMemcpyDeviceToHost, ST));
     CU_TRY(cudaMemcpyAsync(valid, vld_[cur_] + o, (size_t)nw * 8, cudaMemcpyDeviceToHost, ST));
@@ -1425,6 +1494,7 @@ int Engine::get_wire_state(uint32_t wire, uint32_t *p0, uint32_t *p1, size_t wor
     int rc = ensure_lanes();
     if (rc) return rc;
     for (uint32_t i = 0; i < need; i++) p0[i] = p1[i] = 0;
+    if ((rc = materialise_valid())) return rc;
     if (width == 1) {
         uint64_t v = 0, m = 0;
         const size_t o = (size_t)net_.row_of_bit[net_.bit_off[wire]] * stride_;
@@ -1456,7 +1526,7 @@ int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uin
     if ((rc = upload_rows(wires, n, false))) return rc;
     dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
     if (dst_is_device) {
-        k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], value, valid, stride_, 0, T_, dst_stride);
+        k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], value, valid, stride_, 0, T_, dst_stride, elided_ ? d_kv_ : nullptr);
         LAUNCHED();
         return B2_OK;
     }
@@ -1464,7 +1534,8 @@ int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uin
     // main stream: gather into the out-stage once the previous D2H has drained it;
     // copy-out stream: D2H while the main stream goes on with the next tile
     CU_TRY(cudaStreamWaitEvent(ST, EV(ev_out_free_), 0));
-    k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], stage_val_[1], stage_vld_[1], stride_, 0, T_, T_);
+    k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], stage_val_[1], stage_vld_[1], stride_, 0, T_, T_,
+                                          elided_ ? d_kv_ : nullptr);
     LAUNCHED();
     CU_TRY(cudaEventRecord(EV(ev_gathered_), ST));
     CU_TRY(cudaStreamWaitEvent(COUT, EV(ev_gathered_), 0));
@@ -1485,6 +1556,7 @@ int Engine::pack_sim_state(const uint32_t *wires, uint32_t n, uint8_t *p0, uint8
         bits += net_.width[wires[i]];
     }
     if (bits > 0xFFFFFFF0ull) return B2_ERR_RANGE;
+    if ((rc = materialise_valid())) return rc;
     const size_t n_bytes = (size_t)(bits / 8 + 1);  // always at least one unused bit (netcode lib.rs:168)
     if (cap < n_bytes) return B2_ERR_RANGE;
     if (bit_len) *bit_len = bits;

@@ -57,6 +57,7 @@ class Engine {
     uint32_t last_mode() const { return last_mode_; }
     uint64_t last_applications() const { return last_apps_; }
     void set_use_resident(bool on) { use_resident_ = on; }
+    void set_valid_elision(bool on) { opt_elision_ = on; }
 
    private:
     int ensure_device();
@@ -72,6 +73,7 @@ class Engine {
     int run_levelised(bool async);
     int run_jacobi(uint64_t max_steps);
     int run_resident(uint64_t max_steps);
+    int materialise_valid();
     uint32_t resident_wpc() const;
 
     Compiled net_;
@@ -121,6 +123,9 @@ class Engine {
     size_t pack_cap_ = 0;
 
     bool cold_ = true;
+    // valid-plane elision: d_kv_[row] = 1 while the row's valid plane is all-ones and not stored
+    uint8_t *d_kv_ = nullptr;
+    bool elided_ = false, opt_elision_ = false;
     bool use_resident_ = true, resident_attr_set_ = false;
     unsigned long long *d_max_apps_ = nullptr;
     uint32_t last_mode_ = 0;

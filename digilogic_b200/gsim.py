@@ -240,6 +240,7 @@ class Simulator:
         _check(self._lib.b2_sim_set_stream(self._h, C.c_void_p(stream_handle or 0)), "set_stream")
 
     OPT_RESIDENT_KERNEL = 1
+    OPT_VALID_ELISION = 2
 
     def set_option(self, option: int, value: int):
         _check(self._lib.b2_sim_set_option(self._h, option, value), "set_option")

@@ -135,6 +135,11 @@ int b2_sim_set_stream(b2_sim *s, void *stream);
 enum b2_option {
     B2_OPT_RESIDENT_KERNEL = 1 /* 1: netlists whose store fits in shared memory run the whole run_sim loop in
                                   one on-chip kernel when the path is unit-delay or the lane count is tiny; 0: never */
+    ,
+    B2_OPT_VALID_ELISION = 2   /* default 0.  1: in levelised runs, rows that are provably valid on every lane of the
+                                  store (all fan-ins valid, starting from drives whose valid plane is all-ones) keep no
+                                  valid plane in HBM — it is neither read nor written and is re-created on read-back.
+                                  Results are bit-identical; rows that may carry X/Z take the full two-plane path. */
 };
 int b2_sim_set_option(b2_sim *s, int option, int64_t value);
 /* Block until everything queued by this simulator has finished. */
