@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--e2e-ring-tiles", type=int, default=0, help="host stimulus ring size in tiles (0 = whole batch on 1 GPU, 8 otherwise)")
     ap.add_argument("--cpu-lanes-per-core", type=int, default=8)
+    ap.add_argument("--valid-elision", action="store_true", help="experiment: run the main timed loop with B2_OPT_VALID_ELISION (not the headline configuration)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-elision-probe", action="store_true", help="skip the secondary run with B2_OPT_VALID_ELISION")
     ap.add_argument("--no-cpu", action="store_true")
@@ -227,6 +228,9 @@ def run_b200(args):
     tile = min(args.tile_words, words_local)
     assert words_local % tile == 0
     runner = BatchRunner(sim, gen.inputs, gen.outputs, tile, args.max_steps)
+    if args.valid_elision:
+        sim.set_option(sim.OPT_VALID_ELISION, 1)
+        args.no_elision_probe = True
     info = sim.info
     n_out = len(gen.outputs)
     out_v = torch.zeros((n_out, words_local), dtype=torch.int64, device=dev)

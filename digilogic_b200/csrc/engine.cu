@@ -59,6 +59,15 @@ __device__ __forceinline__ ulonglong2 ld_stream(const uint64_t *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
     return r;
 }
+// the same load, predicated off (result all-ones) when `skip`: no branch, no memory transaction
+__device__ __forceinline__ ulonglong2 ld_stream_unless(const uint64_t *p, bool skip) {
+    ulonglong2 r = make_ulonglong2(~0ull, ~0ull);
+    asm volatile(
+        "{ .reg .pred q; setp.eq.u32 q, %3, 0; @q ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2]; }"
+        : "+l"(r.x), "+l"(r.y)
+        : "l"(p), "r"((uint32_t)skip));
+    return r;
+}
 __device__ __forceinline__ void st_pair(uint64_t *p, ulonglong2 v) {
     asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }
@@ -136,58 +145,65 @@ struct Eval2Args {
 // neither read nor written: 24 B instead of 48 B per gate-word.  Rows that may carry X/Z take the
 // full two-plane path; the result is bit-identical either way.
 template <int U, bool JACOBI, bool KV>
-__global__ void __launch_bounds__(256) k_eval2(const Eval2Args a) {
+__global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a) {
     const uint32_t pb = blockIdx.x % a.pair_blocks, gb = blockIdx.x / a.pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
     if (pair >= a.pairs) return;
     const size_t col = (size_t)pair * 2;
     const uint32_t g0 = a.g_begin + gb * (blockDim.y * U) + threadIdx.y;
 
-    uint32_t kind[U];
-    ulonglong2 av[U], am[U], bv[U], bm[U], ov[U], om[U];
-    bool okv[U];
-    const ulonglong2 ones = make_ulonglong2(~0ull, ~0ull);
+    // Explicit phases, each a fully unrolled loop over the U gates of this thread, so that every
+    // dependent step (indices -> elision flags -> plane words) costs one memory round trip for all
+    // U gates together; loads are branch-free (tail gates are clamped, elided planes predicated off).
+    uint32_t f0[U], f1[U], kind[U], orow[U];
+    bool live[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const uint32_t g = g0 + u * blockDim.y;
-        okv[u] = false;
-        if (g < a.g_end) {
-            const uint32_t f0 = a.fan0[g], f1 = a.fan1[g];
-            kind[u] = a.kind[g];
-            bool k0 = false, k1 = false;
-            if (KV) {
-                k0 = a.kv[f0] != 0;
-                k1 = a.kv[f1] != 0;
-                okv[u] = k0 && k1;  // NOT gates have f1 == f0
-            }
-            av[u] = ld_stream(a.in_val + (size_t)f0 * a.stride + col);
-            am[u] = (KV && k0) ? ones : ld_stream(a.in_vld + (size_t)f0 * a.stride + col);
-            if (kind[u] != K_NOT) {
-                bv[u] = ld_stream(a.in_val + (size_t)f1 * a.stride + col);
-                bm[u] = (KV && k1) ? ones : ld_stream(a.in_vld + (size_t)f1 * a.stride + col);
-            } else {
-                bv[u] = av[u];
-                bm[u] = am[u];
-            }
-            if (JACOBI) {
-                const size_t o = (size_t)(a.row_base + g) * a.stride + col;
-                ov[u] = ld_stream(a.in_val + o);
-                om[u] = ld_stream(a.in_vld + o);
-            }
+        live[u] = g < a.g_end;
+        const uint32_t gg = live[u] ? g : a.g_end - 1;
+        f0[u] = a.fan0[gg];
+        f1[u] = a.fan1[gg];
+        kind[u] = a.kind[gg];
+        orow[u] = a.row_base + gg;
+    }
+    bool k0[U], k1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        k0[u] = KV && a.kv[f0[u]] != 0;
+        k1[u] = KV && a.kv[f1[u]] != 0;  // NOT gates have f1 == f0
+    }
+    ulonglong2 av[U], am[U], bv[U], bm[U], ov[U], om[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const size_t r0 = (size_t)f0[u] * a.stride + col, r1 = (size_t)f1[u] * a.stride + col;
+        av[u] = ld_stream(a.in_val + r0);
+        bv[u] = ld_stream(a.in_val + r1);
+        if (KV) {
+            am[u] = ld_stream_unless(a.in_vld + r0, k0[u]);
+            bm[u] = ld_stream_unless(a.in_vld + r1, k1[u]);
+        } else {
+            am[u] = ld_stream(a.in_vld + r0);
+            bm[u] = ld_stream(a.in_vld + r1);
+        }
+        if (JACOBI) {
+            const size_t o = (size_t)orow[u] * a.stride + col;
+            ov[u] = ld_stream(a.in_val + o);
+            om[u] = ld_stream(a.in_vld + o);
         }
     }
     uint64_t dx = 0, dy = 0;
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        const uint32_t g = g0 + u * blockDim.y;
-        if (g < a.g_end) {
-            ulonglong2 rv, rm;
-            gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
-            gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
-            const size_t o = (size_t)(a.row_base + g) * a.stride + col;
+        ulonglong2 rv, rm;
+        gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
+        gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
+        if (live[u]) {
+            const size_t o = (size_t)orow[u] * a.stride + col;
+            const bool okv = KV && k0[u] && k1[u];
             st_pair(a.out_val + o, rv);
-            if (!(KV && okv[u])) st_pair(a.out_vld + o, rm);
-            if (KV && pb == 0 && threadIdx.x == 0) a.kv[a.row_base + g] = okv[u] ? 1 : 0;
+            if (!okv) st_pair(a.out_vld + o, rm);
+            if (KV && pb == 0 && threadIdx.x == 0) a.kv[orow[u]] = okv ? 1 : 0;
             if (JACOBI) {
                 dx |= (rv.x ^ ov[u].x) | (rm.x ^ om[u].x);
                 dy |= (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
