@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--max-steps", type=int, default=10_000)
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--e2e-ring-tiles", type=int, default=0, help="host stimulus ring size in tiles (0 = whole batch on 1 GPU, 8 otherwise)")
-    ap.add_argument("--cpu-lanes-per-core", type=int, default=8)
+    ap.add_argument("--cpu-lanes-per-core", type=int, default=24)
     ap.add_argument("--valid-elision", action="store_true", help="experiment: run the main timed loop with B2_OPT_VALID_ELISION (not the headline configuration)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-elision-probe", action="store_true", help="skip the secondary run with B2_OPT_VALID_ELISION")
@@ -296,7 +296,7 @@ def run_b200(args):
     peak, peak_kind = load_peaks()
     achieved = algo_bytes_per_launch / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "kernel": "k_eval2<4,false>",
+                "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "kernel": "k_eval2<4,false,false>",
                 "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
                 "launches_timed": eval_launches}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
