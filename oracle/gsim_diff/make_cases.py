@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Writes cases.json for the Rust harness: the probes of SURVEY.md A.6/A.7 (latch trace with step
+budgets, driver conflicts, mux with Z/X select and data, cold-start read-back), truth tables, wide
+wires, n-ary gates, random cyclic netlists with max_steps sweeps."""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+KINDS = ["and", "or", "xor", "nand", "nor", "xnor", "not", "mux"]
+Z, X, L0, L1 = (0, 0), (1, 0), (0, 1), (1, 1)
+
+
+def drive(wire, state):
+    return [wire, [state[0]], [state[1]]]
+
+
+def cases():
+    out = []
+    # A.7 latch trace (also probes A.6-1 and A.6-5)
+    a7 = [(L1, L1, 10000), (L0, L1, 10000), (L1, L1, 10000), (L1, L0, 10000), (L0, L0, 10000), (L1, L1, 10), (L1, L1, 11),
+          (L0, L1, 10000), (X, L1, 10000), (Z, L0, 10000)]
+    out.append({"name": "latch_trace_A7", "wires": [1, 1, 1, 1],
+                "comps": [{"kind": "nand", "inputs": [0, 3], "output": 2}, {"kind": "nand", "inputs": [1, 2], "output": 3}],
+                "runs": [{"drives": [drive(0, s), drive(1, r)], "max_steps": ms} for s, r, ms in a7]})
+    # truth tables: one case per kind, 16 runs
+    for k in KINDS[:6]:
+        out.append({"name": f"truth_{k}", "wires": [1, 1, 1], "comps": [{"kind": k, "inputs": [0, 1], "output": 2}],
+                    "runs": [{"drives": [drive(0, a), drive(1, b)], "max_steps": 10} for a in (Z, X, L0, L1) for b in (Z, X, L0, L1)]})
+    # A.6-2/3: conflicts (agreeing and disagreeing drive on a gate output; two gate drivers)
+    out.append({"name": "conflict_drive_on_gate_output", "wires": [1, 1, 1], "comps": [{"kind": "and", "inputs": [0, 1], "output": 2}],
+                "runs": [{"drives": [drive(0, L1), drive(1, L1)], "max_steps": 10}, {"drives": [drive(2, L1)], "max_steps": 10},
+                         {"drives": [drive(2, L0)], "max_steps": 10}, {"drives": [drive(2, X)], "max_steps": 10},
+                         {"drives": [drive(2, Z)], "max_steps": 10}]})
+    out.append({"name": "conflict_two_drivers", "wires": [1, 1, 1],
+                "comps": [{"kind": "and", "inputs": [0, 1], "output": 2}, {"kind": "or", "inputs": [0, 1], "output": 2}],
+                "runs": [{"drives": [drive(0, L1), drive(1, L0)], "max_steps": 10}]})
+    # A.6-4: mux
+    out.append({"name": "mux_z_x", "wires": [1, 1, 1, 1], "comps": [{"kind": "mux", "inputs": [1, 2], "select": 0, "output": 3}],
+                "runs": [{"drives": [drive(0, s), drive(1, a), drive(2, b)], "max_steps": 10}
+                         for s in (Z, X, L0, L1) for a in (Z, L1) for b in (X, L0)]})
+    # random cyclic netlists, max_steps sweep
+    rng = np.random.default_rng(1)
+    for n in range(4):
+        n_in, n_g = 5, 30
+        comps = []
+        for g in range(n_g):
+            kind = KINDS[int(rng.integers(0, 7))]
+            ins = [int(x) for x in rng.integers(0, n_in + n_g, 1 if kind == "not" else int(rng.integers(2, 4)))]
+            comps.append({"kind": kind, "inputs": ins, "output": n_in + g})
+        runs = []
+        for ms in [0, 1, 2, 3, 5, 8, 50, 7, 0, 1000]:
+            runs.append({"drives": [drive(int(w), [Z, X, L0, L1][int(rng.integers(0, 4))]) for w in range(n_in) if rng.random() < 0.7],
+                         "max_steps": ms})
+        out.append({"name": f"random_cyclic_{n}", "wires": [1] * (n_in + n_g), "comps": comps, "runs": runs})
+    return out
+
+
+if __name__ == "__main__":
+    path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "cases.json")
+    with open(path, "w") as f:
+        json.dump(cases(), f)
+    print("wrote", path)
