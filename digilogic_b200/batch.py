@@ -117,6 +117,47 @@ class BatchRunner:
         return worst
 
 
+class InterleavedRunner:
+    """K simulator replicas of one netlist on K CUDA streams, taking alternate lane tiles of a batch.
+
+    Small tiles keep a level's output rows in the 126 MB L2 until the next level reads them (a
+    third of the fan-in traffic never reaches HBM), but a single stream of small kernels is
+    launch-gap bound; with K tiles in flight the gaps and kernel tails of one tile are filled by
+    the others.  The replicas share nothing but the GPU: lanes are independent simulators."""
+
+    def __init__(self, make_sim, inputs, outputs, tile_words: int, n_streams: int, max_steps: int = 10_000, device=None):
+        import torch
+        self.torch = torch
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
+        self.runners = []
+        for st in self.streams:
+            sim = make_sim()
+            sim.set_stream(st.cuda_stream)
+            self.runners.append(BatchRunner(sim, inputs, outputs, tile_words, max_steps))
+        self.tile_words = int(tile_words)
+
+    @property
+    def sims(self):
+        return [r.sim for r in self.runners]
+
+    def run_generated(self, word_begin: int, n_words: int, seed: int, mode: int, out_value, out_valid,
+                      out_word0: int = 0) -> SimulationRunResult:
+        """Same contract as BatchRunner.run_generated; work is forked from and joined to the
+        caller's current stream, so events recorded there bracket it."""
+        assert n_words % self.tile_words == 0
+        main = self.torch.cuda.current_stream()
+        for st in self.streams:
+            st.wait_stream(main)
+        worst = SimulationRunResult.Ok
+        k = len(self.runners)
+        for i, (w0, nw) in enumerate(plan_tiles(n_words, self.tile_words)):
+            worst = max(worst, self.runners[i % k].run_generated(word_begin + w0, nw, seed, mode, out_value, out_valid,
+                                                                 out_word0 + w0))
+        for st in self.streams:
+            main.wait_stream(st)
+        return worst
+
+
 def gather_output_planes(local_value, local_valid, world_size: int):
     """All-gather of the packed output planes: [n_out, words_local] per rank ->
     [world_size, n_out, words_local] (rank-major = lane-word order, since ranks own contiguous

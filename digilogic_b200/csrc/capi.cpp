@@ -155,6 +155,7 @@ int b2_sim_set_option(b2_sim *s, int option, int64_t value) {
     switch (option) {
         case B2_OPT_RESIDENT_KERNEL: s->e->set_use_resident(value != 0); return B2_OK;
         case B2_OPT_VALID_ELISION: s->e->set_valid_elision(value != 0); return B2_OK;
+        case B2_OPT_LEVEL_GRAPH: s->e->set_use_graph(value != 0); return B2_OK;
         default: return B2_ERR_INVALID_ARG;
     }
 }

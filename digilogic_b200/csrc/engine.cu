@@ -730,6 +730,10 @@ void Engine::free_store() {
     cudaFree(xdrv_val_);
     cudaFree(xdrv_vld_);
     cudaFree(d_extra_rows_);
+    if (level_graph_exec_) {
+        cudaGraphExecDestroy((cudaGraphExec_t)level_graph_exec_);
+        level_graph_exec_ = nullptr;
+    }
     cudaFree(d_kv_);
     d_kv_ = nullptr;
     elided_ = false;
@@ -1226,25 +1230,63 @@ int Engine::run_levelised(bool async) {
         LAUNCHED();
     }
     if (extra_rows_.empty() && (rc0 = drives_end())) return rc0;  // the drive rows may be refilled from here on
-    for (const Level &lv : net_.levels) {
-        if (lv.g2_end > lv.g2_begin) {
-            Eval2Args a{d_fan0_, d_fan1_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
-                        sh.pair_blocks, d_kv_};
-            const uint32_t per = sh.block.y * EVAL2_U;
-            const uint32_t gb = (lv.g2_end - lv.g2_begin + per - 1) / per;
-            if (kv)
-                k_eval2<EVAL2_U, false, true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
-            else
-                k_eval2<EVAL2_U, false, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
-            LAUNCHED();
+    // The level sweep is a fixed sequence of launches for a given store: it is captured once into a
+    // CUDA graph and replayed per run, which takes the per-launch CPU cost and most of the
+    // launch-to-launch gap out of small tiles (hundreds of levels of a few microseconds each).
+    const bool want_graph = opt_graph_ && net_.levels.size() >= 8;
+    const uint64_t gkey = ((uint64_t)(uintptr_t)V) ^ ((uint64_t)stride_ << 1) ^ (kv ? 1u : 0u);
+    if (want_graph && level_graph_exec_ && level_graph_key_ == gkey) {
+        CU_TRY(cudaGraphLaunch((cudaGraphExec_t)level_graph_exec_, ST));
+        g_launches.fetch_add(level_graph_nodes_, std::memory_order_relaxed);
+    } else {
+        bool capturing = false;
+        if (want_graph) {
+            if (level_graph_exec_) {
+                cudaGraphExecDestroy((cudaGraphExec_t)level_graph_exec_);
+                level_graph_exec_ = nullptr;
+            }
+            capturing = cudaStreamBeginCapture(ST, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (!capturing) cudaGetLastError();
         }
-        if (lv.wide_end > lv.wide_begin) {
-            WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, V, M, V, M, nullptr, lv.wide_begin, lv.wide_end,
-                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr};
-            const uint32_t gb = (lv.wide_end - lv.wide_begin + sh.block.y - 1) / sh.block.y;
-            k_eval_wide<false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
-            LAUNCHED();
+        uint32_t nodes = 0;
+        for (const Level &lv : net_.levels) {
+            if (lv.g2_end > lv.g2_begin) {
+                Eval2Args a{d_fan0_, d_fan1_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
+                            sh.pair_blocks, d_kv_};
+                const uint32_t per = sh.block.y * EVAL2_U;
+                const uint32_t gb = (lv.g2_end - lv.g2_begin + per - 1) / per;
+                if (kv)
+                    k_eval2<EVAL2_U, false, true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                else
+                    k_eval2<EVAL2_U, false, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                nodes++;
+            }
+            if (lv.wide_end > lv.wide_begin) {
+                WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, V, M, V, M, nullptr, lv.wide_begin, lv.wide_end,
+                           net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr};
+                const uint32_t gb = (lv.wide_end - lv.wide_begin + sh.block.y - 1) / sh.block.y;
+                k_eval_wide<false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                nodes++;
+            }
         }
+        if (capturing) {
+            cudaGraph_t graph = nullptr;
+            CU_TRY(cudaStreamEndCapture(ST, &graph));
+            cudaGraphExec_t exec = nullptr;
+            cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) {
+                set_last_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+                return B2_ERR_CUDA;
+            }
+            level_graph_exec_ = exec;
+            level_graph_key_ = gkey;
+            level_graph_nodes_ = nodes;
+            CU_TRY(cudaGraphLaunch(exec, ST));
+        } else {
+            CU_TRY(cudaGetLastError());
+        }
+        g_launches.fetch_add(nodes, std::memory_order_relaxed);
     }
     cold_ = false;
     last_mode_ = 1;

@@ -58,6 +58,7 @@ class Engine {
     uint64_t last_applications() const { return last_apps_; }
     void set_use_resident(bool on) { use_resident_ = on; }
     void set_valid_elision(bool on) { opt_elision_ = on; }
+    void set_use_graph(bool on) { opt_graph_ = on; }
 
    private:
     int ensure_device();
@@ -126,6 +127,11 @@ class Engine {
     // valid-plane elision: d_kv_[row] = 1 while the row's valid plane is all-ones and not stored
     uint8_t *d_kv_ = nullptr;
     bool elided_ = false, opt_elision_ = false;
+    // CUDA graph of the level sweep (levelised path)
+    void *level_graph_exec_ = nullptr;  // cudaGraphExec_t
+    uint64_t level_graph_key_ = 0;
+    uint32_t level_graph_nodes_ = 0;
+    bool opt_graph_ = true;
     bool use_resident_ = true, resident_attr_set_ = false;
     unsigned long long *d_max_apps_ = nullptr;
     uint32_t last_mode_ = 0;

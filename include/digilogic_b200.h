@@ -140,6 +140,9 @@ enum b2_option {
                                   store (all fan-ins valid, starting from drives whose valid plane is all-ones) keep no
                                   valid plane in HBM — it is neither read nor written and is re-created on read-back.
                                   Results are bit-identical; rows that may carry X/Z take the full two-plane path. */
+    ,
+    B2_OPT_LEVEL_GRAPH = 3     /* default 1.  The per-level launches of the levelised path are captured once into a
+                                  CUDA graph and replayed per run. */
 };
 int b2_sim_set_option(b2_sim *s, int option, int64_t value);
 /* Block until everything queued by this simulator has finished. */
