@@ -51,7 +51,8 @@ def parse_args():
     ap.add_argument("--inputs", type=int, default=4096)
     ap.add_argument("--outputs", type=int, default=1024)
     ap.add_argument("--lanes", type=int, default=1 << 24, help="stimulus lanes per GPU")
-    ap.add_argument("--tile-words", type=int, default=4096, help="64-lane words resident per tile")
+    ap.add_argument("--tile-words", type=int, default=256, help="64-lane words resident per tile and replica")
+    ap.add_argument("--streams", type=int, default=2, help="simulator replicas on separate CUDA streams, alternating tiles")
     ap.add_argument("--max-steps", type=int, default=10_000)
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--e2e-ring-tiles", type=int, default=0, help="host stimulus ring size in tiles (0 = whole batch on 1 GPU, 8 otherwise)")
@@ -131,7 +132,9 @@ def config_dict(args, n_gpus, extra=None):
         "gates": args.gates, "depth": args.depth, "inputs": args.inputs, "outputs": args.outputs,
         "lanes_per_gpu": args.lanes, "lanes_total": args.lanes * n_gpus, "tile_words": args.tile_words,
         "max_steps": args.max_steps, "seed": hex(SEED),
-        "cache": "working set per tile (wire store, GBs) exceeds the 126 MB L2; no flush needed",
+        "streams": args.streams,
+        "cache": "no flush: every step streams the whole wire store of each replica (GBs, far beyond the 126 MB L2) "
+                 "200 levels deep; what L2 keeps between consecutive level kernels is part of the design (DESIGN.md §6)",
         "parallelism": f"lane-sharded x{n_gpus}, full netlist replica per GPU, one NCCL all-gather of output planes per step",
     }
     if extra:
@@ -210,41 +213,43 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from digilogic_b200 import SimulatorBuilder, SimulationRunResult
-    from digilogic_b200.batch import BatchRunner, gather_output_planes, reduce_worst, shard_words
+    from digilogic_b200.batch import InterleavedRunner, gather_output_planes, reduce_worst, shard_words
     from digilogic_b200.gsim import kernel_launches
 
     gen = build_netlist(args)
     t0 = time.perf_counter()
-    sim = gen.emit(SimulatorBuilder()).build()
+    first = gen.emit(SimulatorBuilder()).build()
     compile_s = time.perf_counter() - t0
-    sim.set_device(local_rank)
-    stream = torch.cuda.Stream(device=dev)   # every engine launch and every timing event is on this stream
+    stream = torch.cuda.Stream(device=dev)   # timing events, output planes and the collective live on this stream
     torch.cuda.set_stream(stream)
-    sim.set_stream(stream.cuda_stream)
 
     words_local = args.lanes // 64
     total_words = words_local * world
     w_begin, w_end = shard_words(total_words, world, rank)
     tile = min(args.tile_words, words_local)
     assert words_local % tile == 0
-    runner = BatchRunner(sim, gen.inputs, gen.outputs, tile, args.max_steps)
+    made = []
+
+    def make_sim():
+        sim = first if not made else gen.emit(SimulatorBuilder()).build()
+        made.append(sim)
+        sim.set_device(local_rank)
+        return sim
+
+    runner = InterleavedRunner(make_sim, gen.inputs, gen.outputs, tile, args.streams, args.max_steps, device=dev)
+    sims = runner.sims
+    sim = sims[0]
     if args.valid_elision:
-        sim.set_option(sim.OPT_VALID_ELISION, 1)
+        for x in sims:
+            x.set_option(x.OPT_VALID_ELISION, 1)
         args.no_elision_probe = True
     info = sim.info
     n_out = len(gen.outputs)
     out_v = torch.zeros((n_out, words_local), dtype=torch.int64, device=dev)
     out_m = torch.zeros_like(out_v)
 
-    settle_events = []
-
-    def rec(which):
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record(stream)
-        settle_events.append(ev)
-
     def step(record=False):
-        worst = runner.run_generated(w_begin, words_local, SEED, 0, out_v, out_m, 0, rec if record else None)
+        worst = runner.run_generated(w_begin, words_local, SEED, 0, out_v, out_m, 0)
         if world > 1:
             gv, gm = gather_output_planes(out_v, out_m, world)
             worst = reduce_worst(worst, dev)
@@ -279,7 +284,6 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    settle_ms = sum(settle_events[i].elapsed_time(settle_events[i + 1]) for i in range(0, len(settle_events), 2))
 
     # a checksum of the outputs, so that the timed work is observable (and comparable across N)
     checksum = int((gv.to(torch.int64).sum() ^ gm.to(torch.int64).sum()).item()) & 0xFFFFFFFFFFFFFFFF
@@ -287,10 +291,12 @@ def run_b200(args):
     gate_lane_evals = float(args.gates) * args.lanes * world * args.steps
     value = gate_lane_evals / (ms * 1e-3)
 
-    # roofline of the dominant kernel (k_eval2, one launch per level per tile)
+    # roofline of the dominant kernel (k_eval2, one launch per level per tile).  With several replicas in
+    # flight the launches overlap, so the per-launch duration is the effective one: timed region / launches
+    # (the few other kernels of a step, 0.6 % of it, are charged to k_eval2).
     n_tiles = words_local // tile
     eval_launches = n_tiles * info.depth * args.steps
-    avg_launch_s = settle_ms * 1e-3 / eval_launches
+    avg_launch_s = ms * 1e-3 / eval_launches
     gate_words_per_launch = (args.gates / info.depth) * info.row_stride
     algo_bytes_per_launch = ALGO_BYTES_PER_GATE_WORD * gate_words_per_launch
     peak, peak_kind = load_peaks()
@@ -298,13 +304,16 @@ def run_b200(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "kernel": "k_eval2<4,false,false>",
                 "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
-                "launches_timed": eval_launches}
+                "launches_timed": eval_launches,
+                "note": "effective launch duration (timed region / launches; replicas overlap). frac > 1: a level's output rows are "
+                        "still in L2 when the next level reads them, so about a third of the algorithmic fan-in bytes never reach HBM "
+                        "(see traffic)"}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
             with open(traffic_path) as f:
                 tj = json.load(f)
-            if tj.get("tile_words") == tile and tj.get("gates") == args.gates:
+            if tj.get("tile_words") == tile and tj.get("gates") == args.gates and tj.get("streams", 1) == args.streams:
                 roofline["traffic"] = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -313,7 +322,8 @@ def run_b200(args):
     # valid on every lane keep no valid plane in HBM: 24 B instead of 48 B per gate-word; bit-identical results)
     elision = None
     if not args.no_elision_probe:
-        sim.set_option(sim.OPT_VALID_ELISION, 1)
+        for x in sims:
+            x.set_option(x.OPT_VALID_ELISION, 1)
         worst, gv2, gm2 = step()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -331,7 +341,8 @@ def run_b200(args):
         elision = {"value": float(args.gates) * args.lanes * world * n_el / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / n_el,
                    "steps": n_el, "bytes_per_gate_word": 24, "output_checksum_equal": cs2 == checksum,
                    "note": "B2_OPT_VALID_ELISION=1; all stimulus lanes valid, so no valid plane is read or written"}
-        sim.set_option(sim.OPT_VALID_ELISION, 0)
+        for x in sims:
+            x.set_option(x.OPT_VALID_ELISION, 0)
         step()   # back to plain two-plane rows before the end-to-end leg
         barrier()
 
@@ -355,9 +366,9 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 bit-planes (value+valid)", "data": "synthetic",
             "config": config_dict(args, world, {"tiles_per_step": n_tiles, "row_stride_words": info.row_stride,
-                                                "store_bytes": info.store_bytes, "compile_s": round(compile_s, 3)}),
+                                                "store_bytes": info.store_bytes * len(sims), "compile_s": round(compile_s, 3)}),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "valid_elision": elision, "gpu_launches": int(launches), "clocks": clocks,
-            "settle_ms_per_step": settle_ms / args.steps, "output_checksum": f"{checksum:#018x}",
+            "output_checksum": f"{checksum:#018x}",
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -385,10 +396,12 @@ def run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words
     # host stimulus = the same counter-based words, produced once on the device and copied out before
     # the timed region (numpy generation of 17 GB would take minutes): after a settle the source rows
     # of the store hold the drives, so gathering the input rows returns the stimulus planes
+    torch.cuda.synchronize()
     for w0 in range(0, ring_words, tile):
         sim.fill_stimulus(gen.inputs, SEED, lane_word_base=w_begin + w0, mode=0)
         sim.run_sim_lanes_async(args.max_steps)
         sim.gather_wires_ptr(gen.inputs, hin_v.data_ptr() + 8 * w0, hin_m.data_ptr() + 8 * w0, ring_words, device=False)
+    sim.synchronize()
     inv, inm, outv, outm = hin_v.numpy(), hin_m.numpy(), hout_v.numpy(), hout_m.numpy()
     worst = runner.run_host(inv, inm, outv, outm, words_local)  # warm-up
     barrier()
@@ -411,7 +424,7 @@ def run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words
     return {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(n_in * words_local * 16),
             "d2h_bytes_per_step": int(n_out * words_local * 16), "ms_per_step": ms / args.e2e_steps, "steps": args.e2e_steps,
             "result": int(worst), "host_ring_tiles": ring_tiles, "tiles_per_step": words_local // tile,
-            "overlap": "H2D of tile i+1 and D2H of tile i-1 overlap the settle of tile i (engine copy streams)",
+            "overlap": "H2D of a replica's next tile and D2H of its previous one overlap the settles (engine copy streams)",
             "host_checksum": f"{int(outv.sum() ^ outm.sum()) & 0xFFFFFFFFFFFFFFFF:#018x}"}
 
 

@@ -158,6 +158,47 @@ class InterleavedRunner:
         return worst
 
 
+    def run_host(self, in_value, in_valid, out_value, out_valid, n_words: int | None = None,
+                 dev_out_value=None, dev_out_valid=None) -> SimulationRunResult:
+        """Same contract as BatchRunner.run_host (host planes in, host planes out, optional ring),
+        with the K replicas' upload -> settle -> read-back pipelines interleaved tile by tile."""
+        ring_words = in_value.shape[1]
+        n_words = ring_words if n_words is None else n_words
+        tw = self.tile_words
+        assert n_words % tw == 0 and ring_words % tw == 0 and out_value.shape[1] == ring_words
+        main = self.torch.cuda.current_stream()
+        for st in self.streams:
+            st.wait_stream(main)
+        in_stride, out_stride = in_value.strides[0] // 8, out_value.strides[0] // 8
+        tiles = plan_tiles(n_words, tw)
+        k = len(self.runners)
+        worst = SimulationRunResult.Ok
+
+        def upload(i):
+            r = self.runners[i % k]
+            o = 8 * (tiles[i][0] % ring_words)
+            r.sim.set_drives_lanes_ptr(r.inputs, in_value.ctypes.data + o, in_valid.ctypes.data + o, in_stride)
+
+        for i in range(min(k, len(tiles))):
+            upload(i)
+        for i, (w0, _) in enumerate(tiles):
+            r = self.runners[i % k]
+            worst = max(worst, r.sim.run_sim_lanes_async(r.max_steps))
+            if i + k < len(tiles):
+                upload(i + k)           # waits for this replica's drives to be consumed, not for its settle
+            o = 8 * (w0 % ring_words)
+            r.sim.gather_wires_ptr(r.outputs, out_value.ctypes.data + o, out_valid.ctypes.data + o, out_stride,
+                                   device=False, async_=True)
+            if dev_out_value is not None:
+                r.sim.gather_wires_ptr(r.outputs, dev_out_value.data_ptr() + 8 * w0, dev_out_valid.data_ptr() + 8 * w0,
+                                       dev_out_value.stride(0), device=True)
+        for r in self.runners:
+            r.sim.synchronize()
+        for st in self.streams:
+            main.wait_stream(st)
+        return worst
+
+
 def gather_output_planes(local_value, local_valid, world_size: int):
     """All-gather of the packed output planes: [n_out, words_local] per rank ->
     [world_size, n_out, words_local] (rank-major = lane-word order, since ranks own contiguous
