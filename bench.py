@@ -7,17 +7,21 @@
 Workload (config.workload): BASELINE config 3 — synthetic random combinational DAG, 1M gates,
 depth 200, fan-in 2, 4096 inputs, 2^24 stimulus lanes per GPU, 4-state engine with two-valued
 stimulus generated on the device from (seed, input, global lane-word).  One step = one settle
-(run_sim to the fixed point) of every lane of the batch, tile by tile, plus extraction of the
-1024 designated output rows.  At N GPUs every rank runs the same per-GPU batch on its own lane
-range (weak scaling) and the packed output planes are all-gathered once per step with NCCL.
+(run_sim to the fixed point) of every lane of the batch, tile by tile (256 lane-words per tile,
+two simulator replicas on two CUDA streams taking alternate tiles), plus extraction of the 1024
+designated output rows.  At N GPUs every rank runs the same per-GPU batch on its own lane range
+(weak scaling) and the packed output planes are all-gathered once per step with NCCL.
 
 value      = G * L_total / max-over-ranks device time                (gate-lane evals/s)
 e2e        = the same through the C ABI with HOST buffers: pinned-host stimulus planes in,
-             output planes out, copies inside the timed region
+             output planes out, copies inside the timed region (overlapped with the settles)
 roofline   = k_eval2 (the per-level gate kernel): 48 algorithmic bytes per gate per 64-lane
-             word / its average launch duration, against MEASURED_PEAKS.json
+             word / its effective launch duration (timed region / launches: the
+             replicas' launches overlap), against MEASURED_PEAKS.json; traffic = DRAM bytes per
+             launch from the committed ncu capture (profiles/traffic.json)
 cpu_baseline = the scalar event-driven gsim restatement (oracle/gsim_oracle.c, "port") on the
              host cores over a bounded lane sample of the same netlist
+valid_elision = secondary figure (never the headline): the same job with B2_OPT_VALID_ELISION
 """
 from __future__ import annotations
 
@@ -55,7 +59,7 @@ def parse_args():
     ap.add_argument("--streams", type=int, default=2, help="simulator replicas on separate CUDA streams, alternating tiles")
     ap.add_argument("--max-steps", type=int, default=10_000)
     ap.add_argument("--e2e-steps", type=int, default=1)
-    ap.add_argument("--e2e-ring-tiles", type=int, default=0, help="host stimulus ring size in tiles (0 = whole batch on 1 GPU, 8 otherwise)")
+    ap.add_argument("--e2e-ring-tiles", type=int, default=0, help="host stimulus ring size in tiles (0 = whole batch on 1 GPU, 2^20 lanes otherwise)")
     ap.add_argument("--cpu-lanes-per-core", type=int, default=24)
     ap.add_argument("--valid-elision", action="store_true", help="experiment: run the main timed loop with B2_OPT_VALID_ELISION (not the headline configuration)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -382,8 +386,8 @@ def run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words
     n_in, n_out = len(gen.inputs), len(gen.outputs)
     tile = runner.tile_words
     # One GPU: host planes for the whole batch (17.2 + 4.3 GB).  Several GPUs share one host: a ring of
-    # 8 tiles per rank bounds the pinned memory; every tile is still copied in and out.
-    ring_tiles = args.e2e_ring_tiles or (words_local // tile if world == 1 else 8)
+    # 2^20 lanes (1.3 GB) per rank bounds the pinned memory; every tile is still copied in and out.
+    ring_tiles = args.e2e_ring_tiles or (words_local // tile if world == 1 else max(8, 16384 // tile))
     ring_tiles = min(ring_tiles, words_local // tile)
     ring_words = ring_tiles * tile
     try:

@@ -20,6 +20,7 @@ ap.add_argument("--ks", default="1,2,3")
 ap.add_argument("--lanes", type=int, default=1 << 24)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--graph", type=int, default=1)
+ap.add_argument("--unroll", default="0")
 args = ap.parse_args()
 
 gen = netgen.random_dag()
@@ -31,6 +32,7 @@ out_v = torch.zeros((len(gen.outputs), words), dtype=torch.int64, device=dev)
 out_m = torch.zeros_like(out_v)
 ref = None
 for tile in [int(x) for x in args.tiles.split(",")]:
+  for unroll in [int(x) for x in args.unroll.split(",")]:
     for k in [int(x) for x in args.ks.split(",")]:
         streams = [torch.cuda.Stream(device=dev) for _ in range(k)]
         runners = []
@@ -38,6 +40,7 @@ for tile in [int(x) for x in args.tiles.split(",")]:
             sim = gen.emit(SimulatorBuilder()).build()
             sim.set_stream(s.cuda_stream)
             sim.set_option(sim.OPT_LEVEL_GRAPH, args.graph)
+            sim.set_option(sim.OPT_EVAL_UNROLL, unroll)
             runners.append(BatchRunner(sim, gen.inputs, gen.outputs, tile))
 
         def step():
@@ -64,6 +67,6 @@ for tile in [int(x) for x in args.tiles.split(",")]:
         ref = ref or cs
         evals = 1e6 * args.lanes / (ms * 1e-3)
         print(json.dumps({"tile_words": tile, "streams": k, "ms_per_step": ms, "gate_lane_evals_per_s": evals,
-                          "graph": args.graph, "frac_of_measured_hbm": 0.75 * evals / 6554.9e9, "checksum_ok": cs == ref}), flush=True)
+                          "graph": args.graph, "unroll": unroll, "frac_of_measured_hbm": 0.75 * evals / 6554.9e9, "checksum_ok": cs == ref}), flush=True)
         del runners
         torch.cuda.empty_cache()

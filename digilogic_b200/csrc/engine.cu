@@ -1253,12 +1253,24 @@ int Engine::run_levelised(bool async) {
             if (lv.g2_end > lv.g2_begin) {
                 Eval2Args a{d_fan0_, d_fan1_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
                             sh.pair_blocks, d_kv_};
-                const uint32_t per = sh.block.y * EVAL2_U;
-                const uint32_t gb = (lv.g2_end - lv.g2_begin + per - 1) / per;
-                if (kv)
-                    k_eval2<EVAL2_U, false, true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
-                else
-                    k_eval2<EVAL2_U, false, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                // U gates per thread: 4 when the level still fills the machine several times over, else 2
+                // (more, smaller CTAs: a level of a small tile is only a wave or two of work)
+                const uint32_t n_g = lv.g2_end - lv.g2_begin;
+                const uint32_t ctas4 = sh.pair_blocks * ((n_g + sh.block.y * 4 - 1) / (sh.block.y * 4));
+                const uint32_t U = (opt_u_ ? opt_u_ : (ctas4 >= 148 * 3 * 4 ? 4u : 2u));
+                const uint32_t per = sh.block.y * U;
+                const uint32_t gb = (n_g + per - 1) / per;
+                if (U == 4) {
+                    if (kv)
+                        k_eval2<4, false, true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                    else
+                        k_eval2<4, false, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                } else {
+                    if (kv)
+                        k_eval2<2, false, true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                    else
+                        k_eval2<2, false, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                }
                 nodes++;
             }
             if (lv.wide_end > lv.wide_begin) {
