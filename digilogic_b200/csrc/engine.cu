@@ -137,7 +137,19 @@ struct Eval2Args {
     uint32_t pairs;                   // stride / 2
     uint32_t pair_blocks;
     uint8_t *kv;                      // valid-plane elision (KV): row -> 1 if its valid plane is all-ones and not stored
+    const uint8_t *chg_prev;          // unit delay: row -> changed in the previous application (nullptr: evaluate every gate)
+    uint8_t *chg_cur;                 // unit delay: row -> changed in this application (the frontier of the next one)
 };
+
+// Changed-row frontier write: with a whole warp on one gate, one ballot and one byte store.
+__device__ __forceinline__ void mark_changed(uint8_t *chg, uint32_t row, bool changed) {
+    if (blockDim.x >= 32) {
+        const unsigned any = __ballot_sync(0xFFFFFFFFu, changed);
+        if (any && (threadIdx.x & 31) == 0) chg[row] = 1;
+    } else if (changed) {
+        chg[row] = 1;
+    }
+}
 
 // One- and two-input gates.  U gates per thread keep 4*U independent 128-bit loads in flight.
 // KV (levelised only): a row whose fan-ins are all "known valid" for this tile has an all-ones
@@ -167,29 +179,41 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
         kind[u] = a.kind[gg];
         orow[u] = a.row_base + gg;
     }
-    bool k0[U], k1[U];
+    bool k0[U], k1[U], act[U];
+    bool any_act = false;
 #pragma unroll
     for (int u = 0; u < U; u++) {
         k0[u] = KV && a.kv[f0[u]] != 0;
         k1[u] = KV && a.kv[f1[u]] != 0;  // NOT gates have f1 == f0
+        // unit delay: a gate whose fan-ins did not change in the previous application keeps its
+        // output; it is evaluated only if that output row itself changed (the other buffer is stale)
+        act[u] = !JACOBI || !a.chg_prev || (a.chg_prev[f0[u]] | a.chg_prev[f1[u]] | a.chg_prev[orow[u]]) != 0;
+        any_act |= act[u] && live[u];
     }
+    if (JACOBI && !any_act) return;
     ulonglong2 av[U], am[U], bv[U], bm[U], ov[U], om[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const size_t r0 = (size_t)f0[u] * a.stride + col, r1 = (size_t)f1[u] * a.stride + col;
-        av[u] = ld_stream(a.in_val + r0);
-        bv[u] = ld_stream(a.in_val + r1);
-        if (KV) {
-            am[u] = ld_stream_unless(a.in_vld + r0, k0[u]);
-            bm[u] = ld_stream_unless(a.in_vld + r1, k1[u]);
-        } else {
-            am[u] = ld_stream(a.in_vld + r0);
-            bm[u] = ld_stream(a.in_vld + r1);
-        }
         if (JACOBI) {
+            const bool skip = !act[u];
             const size_t o = (size_t)orow[u] * a.stride + col;
-            ov[u] = ld_stream(a.in_val + o);
-            om[u] = ld_stream(a.in_vld + o);
+            av[u] = ld_stream_unless(a.in_val + r0, skip);
+            bv[u] = ld_stream_unless(a.in_val + r1, skip);
+            am[u] = ld_stream_unless(a.in_vld + r0, skip);
+            bm[u] = ld_stream_unless(a.in_vld + r1, skip);
+            ov[u] = ld_stream_unless(a.in_val + o, skip);
+            om[u] = ld_stream_unless(a.in_vld + o, skip);
+        } else {
+            av[u] = ld_stream(a.in_val + r0);
+            bv[u] = ld_stream(a.in_val + r1);
+            if (KV) {
+                am[u] = ld_stream_unless(a.in_vld + r0, k0[u]);
+                bm[u] = ld_stream_unless(a.in_vld + r1, k1[u]);
+            } else {
+                am[u] = ld_stream(a.in_vld + r0);
+                bm[u] = ld_stream(a.in_vld + r1);
+            }
         }
     }
     uint64_t dx = 0, dy = 0;
@@ -198,17 +222,21 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
         ulonglong2 rv, rm;
         gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
         gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
-        if (live[u]) {
+        bool ch = false;
+        if (live[u] && act[u]) {
             const size_t o = (size_t)orow[u] * a.stride + col;
             const bool okv = KV && k0[u] && k1[u];
             st_pair(a.out_val + o, rv);
             if (!okv) st_pair(a.out_vld + o, rm);
             if (KV && pb == 0 && threadIdx.x == 0) a.kv[orow[u]] = okv ? 1 : 0;
             if (JACOBI) {
-                dx |= (rv.x ^ ov[u].x) | (rm.x ^ om[u].x);
-                dy |= (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
+                const uint64_t ex = (rv.x ^ ov[u].x) | (rm.x ^ om[u].x), ey = (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
+                dx |= ex;
+                dy |= ey;
+                ch = (ex | ey) != 0;
             }
         }
+        if (JACOBI && a.chg_cur) mark_changed(a.chg_cur, orow[u], ch);
     }
     if (JACOBI) {
         if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
@@ -224,6 +252,8 @@ struct WideArgs {
     uint64_t *changed;
     uint32_t g_begin, g_end, row_base, stride, pairs, pair_blocks;
     uint8_t *kv;  // nullable: rows whose valid plane is elided (read as all-ones); outputs are always stored
+    const uint8_t *chg_prev;  // unit-delay frontier, as in Eval2Args
+    uint8_t *chg_cur;
 };
 
 __device__ __forceinline__ ulonglong2 ld_valid(const WideArgs &a, uint32_t row, size_t col) {
@@ -241,6 +271,11 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
     const size_t col = (size_t)pair * 2;
     const uint32_t b = a.off[g], e = a.off[g + 1];
     const uint32_t kind = a.kind[g];
+    if (JACOBI && a.chg_prev) {
+        uint32_t act = a.chg_prev[a.row_base + g];
+        for (uint32_t i = b; i < e; i++) act |= a.chg_prev[a.in[i]];
+        if (!act) return;  // warp-uniform when a warp sits on one gate
+    }
     ulonglong2 rv, rm;
     if (kind == K_MUX) {
         const uint32_t ns = a.nsel[g];
@@ -292,6 +327,7 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
         const uint64_t dx = (rv.x ^ ov.x) | (rm.x ^ om.x), dy = (rv.y ^ ov.y) | (rm.y ^ om.y);
         if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
         if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
+        if (a.chg_cur && (dx | dy)) a.chg_cur[a.row_base + g] = 1;
     }
     st_pair(a.out_val + o, rv);
     st_pair(a.out_vld + o, rm);
@@ -305,7 +341,8 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(256) k_apply_drive(const uint64_t *dval, const uint64_t *dvld, const uint64_t *old_val,
                                                      const uint64_t *old_vld, uint64_t *out_val, uint64_t *out_vld,
                                                      uint64_t *changed, uint32_t n_rows, uint32_t stride, uint32_t pairs,
-                                                     uint32_t pair_blocks, uint8_t *kv = nullptr, uint32_t words_in_use = 0) {
+                                                     uint32_t pair_blocks, uint8_t *kv = nullptr, uint32_t words_in_use = 0,
+                                                     uint8_t *chg_cur = nullptr) {
     const uint32_t pb = blockIdx.x % pair_blocks, rb = blockIdx.x / pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
     const uint32_t row = rb * blockDim.y + threadIdx.y;
@@ -317,6 +354,7 @@ __global__ void __launch_bounds__(256) k_apply_drive(const uint64_t *dval, const
         const uint64_t dx = (v.x ^ ov.x) | (m.x ^ om.x), dy = (v.y ^ ov.y) | (m.y ^ om.y);
         if (dx) atomicOr((unsigned long long *)&changed[col], (unsigned long long)dx);
         if (dy) atomicOr((unsigned long long *)&changed[col + 1], (unsigned long long)dy);
+        if (chg_cur && (dx | dy)) chg_cur[row] = 1;
     }
     st_pair(out_val + o, v);
     st_pair(out_vld + o, m);
@@ -734,6 +772,10 @@ void Engine::free_store() {
         cudaGraphExecDestroy((cudaGraphExec_t)level_graph_exec_);
         level_graph_exec_ = nullptr;
     }
+    cudaFree(d_rowchg_[0]);
+    cudaFree(d_rowchg_[1]);
+    d_rowchg_[0] = d_rowchg_[1] = nullptr;
+    frontier_valid_ = false;
     cudaFree(d_kv_);
     d_kv_ = nullptr;
     elided_ = false;
@@ -1207,6 +1249,7 @@ int Engine::materialise_valid() {
     k_materialise_valid<<<pair_blocks * rb, block, 0, ST>>>(vld_[cur_], d_kv_, net_.n_rows, stride_, pairs, pair_blocks);
     LAUNCHED();
     elided_ = false;
+    frontier_valid_ = false;
     return B2_OK;
 }
 
@@ -1252,7 +1295,7 @@ int Engine::run_levelised(bool async) {
         for (const Level &lv : net_.levels) {
             if (lv.g2_end > lv.g2_begin) {
                 Eval2Args a{d_fan0_, d_fan1_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
-                            sh.pair_blocks, d_kv_};
+                            sh.pair_blocks, d_kv_, nullptr, nullptr};
                 // U gates per thread: 4 when the level still fills the machine several times over, else 2
                 // (more, smaller CTAs: a level of a small tile is only a wave or two of work)
                 const uint32_t n_g = lv.g2_end - lv.g2_begin;
@@ -1275,7 +1318,7 @@ int Engine::run_levelised(bool async) {
             }
             if (lv.wide_end > lv.wide_begin) {
                 WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, V, M, V, M, nullptr, lv.wide_begin, lv.wide_end,
-                           net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr};
+                           net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr, nullptr, nullptr};
                 const uint32_t gb = (lv.wide_end - lv.wide_begin + sh.block.y - 1) / sh.block.y;
                 k_eval_wide<false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
                 nodes++;
@@ -1301,6 +1344,7 @@ int Engine::run_levelised(bool async) {
         g_launches.fetch_add(nodes, std::memory_order_relaxed);
     }
     cold_ = false;
+    frontier_valid_ = false;
     last_mode_ = 1;
     last_apps_ = 1;
     elided_ = kv;  // a plain pass rewrites every valid plane, so nothing stays elided
@@ -1368,12 +1412,25 @@ int Engine::run_jacobi(uint64_t max_steps) {
             LAUNCHED();
         }
         cold_ = false;
+        frontier_valid_ = false;
         k = 1;
         if (net_.n_g2() + net_.n_wide() == 0) {
             if ((rc = drives_end())) return rc;
             return B2_RUN_OK;
         }
     }
+    // Frontier (event-driven at row granularity): a gate is re-evaluated only if one of its fan-in rows, or
+    // its own output row, changed in the previous application.  The flags persist across runs — a settled
+    // run leaves them all zero, so the next run starts from just the source rows whose drive changed.
+    // Off when gate outputs carry external drives (their merge bypasses the flags).
+    const bool use_frontier = opt_frontier_ && n_extra == 0;
+    if (use_frontier && !d_rowchg_[0]) {
+        CU_TRY(cudaMalloc((void **)&d_rowchg_[0], net_.n_rows));
+        CU_TRY(cudaMalloc((void **)&d_rowchg_[1], net_.n_rows));
+        store_bytes_ += 2 * (size_t)net_.n_rows;
+        frontier_valid_ = false;
+    }
+    if (!use_frontier) frontier_valid_ = false;
     const uint64_t first_k = k + 1;
     for (;;) {
         k++;
@@ -1381,15 +1438,19 @@ int Engine::run_jacobi(uint64_t max_steps) {
         const bool is_last = k == last;
         const uint64_t *AV = val_[cur_], *AM = vld_[cur_];
         uint64_t *BV = val_[cur_ ^ 1], *BM = vld_[cur_ ^ 1];
+        // changed-row frontier: this application reads the flags of the previous one and writes its own
+        uint8_t *chg_cur = use_frontier ? d_rowchg_[chg_w_] : nullptr;
+        const uint8_t *chg_prev = (use_frontier && frontier_valid_) ? d_rowchg_[chg_w_ ^ 1] : nullptr;
+        if (use_frontier) CU_TRY(cudaMemsetAsync(chg_cur, 0, net_.n_rows, ST));
         if (net_.n_src) {
             const uint32_t rb = (net_.n_src + sh.block.y - 1) / sh.block.y;
             k_apply_drive<true><<<sh.pair_blocks * rb, sh.block, 0, ST>>>(drv_val_, drv_vld_, AV, AM, BV, BM, d_changed_, net_.n_src,
-                                                                           stride_, pairs, sh.pair_blocks);
+                                                                           stride_, pairs, sh.pair_blocks, nullptr, 0, chg_cur);
             LAUNCHED();
         }
         if (net_.n_g2()) {
             Eval2Args a{d_fan0_, d_fan1_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
-                        sh.pair_blocks, nullptr};
+                        sh.pair_blocks, nullptr, chg_prev, chg_cur};
             const uint32_t per = sh.block.y * EVAL2_U;
             const uint32_t gb = (net_.n_g2() + per - 1) / per;
             k_eval2<EVAL2_U, true, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
@@ -1397,10 +1458,14 @@ int Engine::run_jacobi(uint64_t max_steps) {
         }
         if (net_.n_wide()) {
             WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, AV, AM, BV, BM, d_changed_, 0, net_.n_wide(),
-                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, nullptr};
+                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur};
             const uint32_t gb = (net_.n_wide() + sh.block.y - 1) / sh.block.y;
             k_eval_wide<true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
             LAUNCHED();
+        }
+        if (use_frontier) {
+            frontier_valid_ = true;
+            chg_w_ ^= 1;
         }
         if (n_extra) {
             k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_extra, xdrv_val_, xdrv_vld_, BV, BM, d_conf_step_, stride_, 0);
@@ -1428,6 +1493,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
         if (stop) break;
     }
     CU_TRY(cudaStreamSynchronize(ST));
+    if (k == last) frontier_valid_ = false;  // ended on the check-only application: the other buffer is one step ahead
     const RunFlags fin = h_flags_[newest];  // conflict flags are cumulative; unsettled exists only on the last application
     if ((rc = drives_end())) return rc;
     if (fin.any_conflict) return B2_RUN_CONFLICT;
@@ -1496,6 +1562,7 @@ int Engine::run_resident(uint64_t max_steps) {
     if ((rc = drives_end())) return rc;
     CU_TRY(cudaStreamSynchronize(ST));
     cold_ = false;
+    frontier_valid_ = false;
     last_mode_ = 3;
     last_apps_ = apps;
     if (h_flags_->any_conflict) return B2_RUN_CONFLICT;

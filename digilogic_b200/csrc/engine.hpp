@@ -59,6 +59,7 @@ class Engine {
     void set_use_resident(bool on) { use_resident_ = on; }
     void set_valid_elision(bool on) { opt_elision_ = on; }
     void set_use_graph(bool on) { opt_graph_ = on; }
+    void set_use_frontier(bool on) { opt_frontier_ = on; frontier_valid_ = false; }
     void set_eval_unroll(uint32_t u) { opt_u_ = (u == 2 || u == 4) ? u : 0; level_graph_key_ = 0; }
 
    private:
@@ -133,6 +134,10 @@ class Engine {
     uint64_t level_graph_key_ = 0;
     uint32_t level_graph_nodes_ = 0;
     bool opt_graph_ = true;
+    // unit-delay changed-row frontier
+    uint8_t *d_rowchg_[2] = {nullptr, nullptr};
+    int chg_w_ = 0;
+    bool frontier_valid_ = false, opt_frontier_ = true;
     uint32_t opt_u_ = 0;  // 0 = automatic gates-per-thread choice in k_eval2
     bool use_resident_ = true, resident_attr_set_ = false;
     unsigned long long *d_max_apps_ = nullptr;

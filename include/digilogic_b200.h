@@ -144,7 +144,9 @@ enum b2_option {
     B2_OPT_LEVEL_GRAPH = 3     /* default 1.  The per-level launches of the levelised path are captured once into a
                                   CUDA graph and replayed per run. */
     ,
-    B2_OPT_EVAL_UNROLL = 4     /* default 0 = automatic.  2 or 4: gates per thread in the per-level kernel (tuning knob). */
+    B2_OPT_EVAL_UNROLL = 4,    /* default 0 = automatic.  2 or 4: gates per thread in the per-level kernel (tuning knob). */
+    B2_OPT_FRONTIER = 5        /* default 1.  Unit-delay runs in HBM re-evaluate a gate only if one of its fan-in rows or
+                                  its own output row changed (on any lane) in the previous application. */
 };
 int b2_sim_set_option(b2_sim *s, int option, int64_t value);
 /* Block until everything queued by this simulator has finished. */
