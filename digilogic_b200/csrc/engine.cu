@@ -644,7 +644,8 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
     uint64_t k = a.cold ? 1 : 0;
     unsigned long long apps = 0;
     const size_t n_items = (size_t)(a.n_src + a.n_g2 + a.n_wide) * wpc;
-    if (a.n_g2 + a.n_wide > 0) {
+    // (a cold start without components is already final: W_1 = D; a warm one still takes the new drives)
+    if (a.n_g2 + a.n_wide > 0 || !a.cold) {
         for (;;) {
             k++;
             apps++;
