@@ -139,6 +139,7 @@ struct Eval2Args {
     uint8_t *kv;                      // valid-plane elision (KV): row -> 1 if its valid plane is all-ones and not stored
     const uint8_t *chg_prev;          // unit delay: row -> changed in the previous application (nullptr: evaluate every gate)
     uint8_t *chg_cur;                 // unit delay: row -> changed in this application (the frontier of the next one)
+    const uint32_t *all_valid;        // KV: 1 if every source row of this run is known valid (then every row is)
 };
 
 // Changed-row frontier write: with a whole warp on one gate, one ballot and one byte store.
@@ -181,10 +182,11 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
     }
     bool k0[U], k1[U], act[U];
     bool any_act = false;
+    const bool allv = KV && *a.all_valid != 0;  // uniform: with all drives valid no per-row flag is read or written
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        k0[u] = KV && a.kv[f0[u]] != 0;
-        k1[u] = KV && a.kv[f1[u]] != 0;  // NOT gates have f1 == f0
+        k0[u] = KV && (allv || a.kv[f0[u]] != 0);
+        k1[u] = KV && (allv || a.kv[f1[u]] != 0);  // NOT gates have f1 == f0
         // unit delay: a gate whose fan-ins did not change in the previous application keeps its
         // output; it is evaluated only if that output row itself changed (the other buffer is stale)
         act[u] = !JACOBI || !a.chg_prev || (a.chg_prev[f0[u]] | a.chg_prev[f1[u]] | a.chg_prev[orow[u]]) != 0;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
             const bool okv = KV && k0[u] && k1[u];
             st_pair(a.out_val + o, rv);
             if (!okv) st_pair(a.out_vld + o, rm);
-            if (KV && pb == 0 && threadIdx.x == 0) a.kv[orow[u]] = okv ? 1 : 0;
+            if (KV && !allv && pb == 0 && threadIdx.x == 0) a.kv[orow[u]] = okv ? 1 : 0;
             if (JACOBI) {
                 const uint64_t ex = (rv.x ^ ov[u].x) | (rm.x ^ om[u].x), ey = (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
                 dx |= ex;
@@ -254,10 +256,11 @@ struct WideArgs {
     uint8_t *kv;  // nullable: rows whose valid plane is elided (read as all-ones); outputs are always stored
     const uint8_t *chg_prev;  // unit-delay frontier, as in Eval2Args
     uint8_t *chg_cur;
+    const uint32_t *all_valid;  // as in Eval2Args (nullable)
 };
 
 __device__ __forceinline__ ulonglong2 ld_valid(const WideArgs &a, uint32_t row, size_t col) {
-    if (a.kv && a.kv[row]) return make_ulonglong2(~0ull, ~0ull);
+    if (a.kv && (*a.all_valid || a.kv[row])) return make_ulonglong2(~0ull, ~0ull);
     return ld_stream(a.in_vld + (size_t)row * a.stride + col);
 }
 
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
         if (a.chg_cur && (dx | dy)) a.chg_cur[a.row_base + g] = 1;
     }
     st_pair(a.out_val + o, rv);
+    if (a.kv && *a.all_valid) return;  // valid fan-ins give a valid output: its plane stays elided
     st_pair(a.out_vld + o, rm);
     if (a.kv && pb == 0 && threadIdx.x == 0) a.kv[a.row_base + g] = 0;
 }
@@ -364,14 +368,25 @@ __global__ void __launch_bounds__(256) k_apply_drive(const uint64_t *dval, const
     }
 }
 
+// all_valid = AND of the source rows' flags (one CTA)
+__global__ void __launch_bounds__(256) k_all_valid(const uint8_t *kv, uint32_t n_src, uint32_t *all_valid) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_src; i += blockDim.x)
+        if (!kv[i]) bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) *all_valid = bad ? 0u : 1u;
+}
+
 // expands elided valid planes back to all-ones words (leaving the store plain two-plane)
-__global__ void __launch_bounds__(256) k_materialise_valid(uint64_t *vld, uint8_t *kv, uint32_t n_rows, uint32_t stride, uint32_t pairs,
-                                                           uint32_t pair_blocks) {
+__global__ void __launch_bounds__(256) k_materialise_valid(uint64_t *vld, uint8_t *kv, const uint32_t *all_valid, uint32_t n_rows,
+                                                           uint32_t stride, uint32_t pairs, uint32_t pair_blocks) {
     const uint32_t pb = blockIdx.x % pair_blocks, rb = blockIdx.x / pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
     const uint32_t row = rb * blockDim.y + threadIdx.y;
     if (pair >= pairs || row >= n_rows) return;
-    if (kv[row]) st_pair(vld + (size_t)row * stride + (size_t)pair * 2, make_ulonglong2(~0ull, ~0ull));
+    if (*all_valid || kv[row]) st_pair(vld + (size_t)row * stride + (size_t)pair * 2, make_ulonglong2(~0ull, ~0ull));
 }
 
 // External drives on gate-driven rows: resolve(D, gate output) and conflict detection
@@ -499,13 +514,14 @@ __global__ void __launch_bounds__(256) k_fill_stimulus(uint64_t *const *row_val,
 // rows[] of (val, vld) -> dense planes [n][dst_stride]
 __global__ void __launch_bounds__(256) k_gather_rows(const uint32_t *rows, uint32_t n, const uint64_t *val, const uint64_t *vld,
                                                      uint64_t *dst_val, uint64_t *dst_vld, uint32_t stride, uint32_t word0,
-                                                     uint32_t n_words, size_t dst_stride, const uint8_t *kv) {
+                                                     uint32_t n_words, size_t dst_stride, const uint8_t *kv,
+                                                     const uint32_t *all_valid) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y;
     if (w >= n_words || i >= n) return;
     const size_t s = (size_t)rows[i] * stride + word0 + w;
     dst_val[(size_t)i * dst_stride + w] = val[s];
-    dst_vld[(size_t)i * dst_stride + w] = (kv && kv[rows[i]]) ? ~0ull : vld[s];
+    dst_vld[(size_t)i * dst_stride + w] = (kv && (*all_valid || kv[rows[i]])) ? ~0ull : vld[s];
 }
 
 // dense planes [n][src_stride] -> drive rows given by pointer tables
@@ -778,7 +794,9 @@ void Engine::free_store() {
     d_rowchg_[0] = d_rowchg_[1] = nullptr;
     frontier_valid_ = false;
     cudaFree(d_kv_);
+    cudaFree(d_all_valid_);
     d_kv_ = nullptr;
+    d_all_valid_ = nullptr;
     elided_ = false;
     cudaFree(d_changed_);
     cudaFree(d_conf_step_);
@@ -983,6 +1001,8 @@ int Engine::set_lanes(uint64_t n_lanes) {
     }
     CU_TRY(cudaMalloc((void **)&d_kv_, net_.n_rows ? net_.n_rows : 1));
     CU_TRY(cudaMemsetAsync(d_kv_, 0, net_.n_rows ? net_.n_rows : 1, ST));
+    CU_TRY(cudaMalloc((void **)&d_all_valid_, 4));
+    CU_TRY(cudaMemsetAsync(d_all_valid_, 0, 4, ST));
     store_bytes_ += net_.n_rows;
     cur_ = 0;
     cold_ = true;
@@ -1247,7 +1267,7 @@ int Engine::materialise_valid() {
     while (bx < pairs && bx < 256) bx <<= 1;
     const dim3 block(bx, 256 / bx);
     const uint32_t pair_blocks = (pairs + bx - 1) / bx, rb = (net_.n_rows + block.y - 1) / block.y;
-    k_materialise_valid<<<pair_blocks * rb, block, 0, ST>>>(vld_[cur_], d_kv_, net_.n_rows, stride_, pairs, pair_blocks);
+    k_materialise_valid<<<pair_blocks * rb, block, 0, ST>>>(vld_[cur_], d_kv_, d_all_valid_, net_.n_rows, stride_, pairs, pair_blocks);
     LAUNCHED();
     elided_ = false;
     frontier_valid_ = false;
@@ -1273,6 +1293,10 @@ int Engine::run_levelised(bool async) {
                                                                         kv ? d_kv_ : nullptr, T_);
         LAUNCHED();
     }
+    if (kv) {
+        k_all_valid<<<1, 256, 0, ST>>>(d_kv_, net_.n_src, d_all_valid_);
+        LAUNCHED();
+    }
     if (extra_rows_.empty() && (rc0 = drives_end())) return rc0;  // the drive rows may be refilled from here on
     // The level sweep is a fixed sequence of launches for a given store: it is captured once into a
     // CUDA graph and replayed per run, which takes the per-launch CPU cost and most of the
@@ -1296,7 +1320,7 @@ int Engine::run_levelised(bool async) {
         for (const Level &lv : net_.levels) {
             if (lv.g2_end > lv.g2_begin) {
                 Eval2Args a{d_fan0_, d_fan1_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
-                            sh.pair_blocks, d_kv_, nullptr, nullptr};
+                            sh.pair_blocks, d_kv_, nullptr, nullptr, d_all_valid_};
                 // U gates per thread: 4 when the level still fills the machine several times over, else 2
                 // (more, smaller CTAs: a level of a small tile is only a wave or two of work)
                 const uint32_t n_g = lv.g2_end - lv.g2_begin;
@@ -1319,7 +1343,7 @@ int Engine::run_levelised(bool async) {
             }
             if (lv.wide_end > lv.wide_begin) {
                 WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, V, M, V, M, nullptr, lv.wide_begin, lv.wide_end,
-                           net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr, nullptr, nullptr};
+                           net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr, nullptr, nullptr, d_all_valid_};
                 const uint32_t gb = (lv.wide_end - lv.wide_begin + sh.block.y - 1) / sh.block.y;
                 k_eval_wide<false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
                 nodes++;
@@ -1451,7 +1475,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
         }
         if (net_.n_g2()) {
             Eval2Args a{d_fan0_, d_fan1_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
-                        sh.pair_blocks, nullptr, chg_prev, chg_cur};
+                        sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
             const uint32_t per = sh.block.y * EVAL2_U;
             const uint32_t gb = (net_.n_g2() + per - 1) / per;
             k_eval2<EVAL2_U, true, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
@@ -1459,7 +1483,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
         }
         if (net_.n_wide()) {
             WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, AV, AM, BV, BM, d_changed_, 0, net_.n_wide(),
-                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur};
+                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
             const uint32_t gb = (net_.n_wide() + sh.block.y - 1) / sh.block.y;
             k_eval_wide<true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
             LAUNCHED();
@@ -1664,7 +1688,8 @@ int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uin
     if ((rc = upload_rows(wires, n, false))) return rc;
     dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
     if (dst_is_device) {
-        k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], value, valid, stride_, 0, T_, dst_stride, elided_ ? d_kv_ : nullptr);
+        k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], value, valid, stride_, 0, T_, dst_stride, elided_ ? d_kv_ : nullptr,
+                                              d_all_valid_);
         LAUNCHED();
         return B2_OK;
     }
@@ -1673,7 +1698,7 @@ int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uin
     // copy-out stream: D2H while the main stream goes on with the next tile
     CU_TRY(cudaStreamWaitEvent(ST, EV(ev_out_free_), 0));
     k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], stage_val_[1], stage_vld_[1], stride_, 0, T_, T_,
-                                          elided_ ? d_kv_ : nullptr);
+                                          elided_ ? d_kv_ : nullptr, d_all_valid_);
     LAUNCHED();
     CU_TRY(cudaEventRecord(EV(ev_gathered_), ST));
     CU_TRY(cudaStreamWaitEvent(COUT, EV(ev_gathered_), 0));

@@ -128,6 +128,7 @@ class Engine {
     bool cold_ = true;
     // valid-plane elision: d_kv_[row] = 1 while the row's valid plane is all-ones and not stored
     uint8_t *d_kv_ = nullptr;
+    uint32_t *d_all_valid_ = nullptr;  // 1 when every source row of the last elided run was valid
     bool elided_ = false, opt_elision_ = false;
     // CUDA graph of the level sweep (levelised path)
     void *level_graph_exec_ = nullptr;  // cudaGraphExec_t
