@@ -21,6 +21,7 @@ ap.add_argument("--lanes", type=int, default=1 << 24)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--graph", type=int, default=1)
 ap.add_argument("--unroll", default="0")
+ap.add_argument("--elision", type=int, default=0)
 args = ap.parse_args()
 
 gen = netgen.random_dag()
@@ -41,6 +42,7 @@ for tile in [int(x) for x in args.tiles.split(",")]:
             sim.set_stream(s.cuda_stream)
             sim.set_option(sim.OPT_LEVEL_GRAPH, args.graph)
             sim.set_option(sim.OPT_EVAL_UNROLL, unroll)
+            sim.set_option(sim.OPT_VALID_ELISION, args.elision)
             runners.append(BatchRunner(sim, gen.inputs, gen.outputs, tile))
 
         def step():
@@ -67,6 +69,6 @@ for tile in [int(x) for x in args.tiles.split(",")]:
         ref = ref or cs
         evals = 1e6 * args.lanes / (ms * 1e-3)
         print(json.dumps({"tile_words": tile, "streams": k, "ms_per_step": ms, "gate_lane_evals_per_s": evals,
-                          "graph": args.graph, "unroll": unroll, "frac_of_measured_hbm": 0.75 * evals / 6554.9e9, "checksum_ok": cs == ref}), flush=True)
+                          "graph": args.graph, "elision": args.elision, "unroll": unroll, "frac_of_measured_hbm": 0.75 * evals / 6554.9e9, "checksum_ok": cs == ref}), flush=True)
         del runners
         torch.cuda.empty_cache()
