@@ -22,6 +22,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--graph", type=int, default=1)
 ap.add_argument("--unroll", default="0")
 ap.add_argument("--elision", type=int, default=0)
+ap.add_argument("--threads", type=int, default=1)
 args = ap.parse_args()
 
 gen = netgen.random_dag()
@@ -35,25 +36,19 @@ ref = None
 for tile in [int(x) for x in args.tiles.split(",")]:
   for unroll in [int(x) for x in args.unroll.split(",")]:
     for k in [int(x) for x in args.ks.split(",")]:
-        streams = [torch.cuda.Stream(device=dev) for _ in range(k)]
-        runners = []
-        for s in streams:
+        from digilogic_b200.batch import InterleavedRunner
+
+        def make_sim():
             sim = gen.emit(SimulatorBuilder()).build()
-            sim.set_stream(s.cuda_stream)
             sim.set_option(sim.OPT_LEVEL_GRAPH, args.graph)
             sim.set_option(sim.OPT_EVAL_UNROLL, unroll)
             sim.set_option(sim.OPT_VALID_ELISION, args.elision)
-            runners.append(BatchRunner(sim, gen.inputs, gen.outputs, tile))
+            return sim
+
+        runners = InterleavedRunner(make_sim, gen.inputs, gen.outputs, tile, k, device=dev, host_threads=bool(args.threads))
 
         def step():
-            for s in streams:
-                s.wait_stream(main)
-            n_tiles = words // tile
-            for t in range(n_tiles):
-                r = runners[t % k]
-                r.run_generated(t * tile, tile, 0xD1610003, 0, out_v, out_m, t * tile)
-            for s in streams:
-                main.wait_stream(s)
+            runners.run_generated(0, words, 0xD1610003, 0, out_v, out_m, 0)
 
         for _ in range(2):
             step()
@@ -69,6 +64,6 @@ for tile in [int(x) for x in args.tiles.split(",")]:
         ref = ref or cs
         evals = 1e6 * args.lanes / (ms * 1e-3)
         print(json.dumps({"tile_words": tile, "streams": k, "ms_per_step": ms, "gate_lane_evals_per_s": evals,
-                          "graph": args.graph, "elision": args.elision, "unroll": unroll, "frac_of_measured_hbm": 0.75 * evals / 6554.9e9, "checksum_ok": cs == ref}), flush=True)
+                          "graph": args.graph, "threads": args.threads, "elision": args.elision, "unroll": unroll, "frac_of_measured_hbm": 0.75 * evals / 6554.9e9, "checksum_ok": cs == ref}), flush=True)
         del runners
         torch.cuda.empty_cache()

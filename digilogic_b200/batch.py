@@ -125,9 +125,12 @@ class InterleavedRunner:
     launch-gap bound; with K tiles in flight the gaps and kernel tails of one tile are filled by
     the others.  The replicas share nothing but the GPU: lanes are independent simulators."""
 
-    def __init__(self, make_sim, inputs, outputs, tile_words: int, n_streams: int, max_steps: int = 10_000, device=None):
+    def __init__(self, make_sim, inputs, outputs, tile_words: int, n_streams: int, max_steps: int = 10_000, device=None,
+                 host_threads: bool = True):
         import torch
+        from concurrent.futures import ThreadPoolExecutor
         self.torch = torch
+        self.pool = ThreadPoolExecutor(max_workers=n_streams) if (host_threads and n_streams > 1) else None
         self.streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
         self.runners = []
         for st in self.streams:
@@ -148,11 +151,21 @@ class InterleavedRunner:
         main = self.torch.cuda.current_stream()
         for st in self.streams:
             st.wait_stream(main)
-        worst = SimulationRunResult.Ok
         k = len(self.runners)
-        for i, (w0, nw) in enumerate(plan_tiles(n_words, self.tile_words)):
-            worst = max(worst, self.runners[i % k].run_generated(word_begin + w0, nw, seed, mode, out_value, out_valid,
-                                                                 out_word0 + w0))
+        tiles = plan_tiles(n_words, self.tile_words)
+
+        def drive(j):
+            # one host thread per replica: kernel / graph launches of the replicas proceed in parallel
+            # (ctypes releases the GIL for the duration of every C-ABI call)
+            w = SimulationRunResult.Ok
+            for w0, nw in tiles[j::k]:
+                w = max(w, self.runners[j].run_generated(word_begin + w0, nw, seed, mode, out_value, out_valid, out_word0 + w0))
+            return w
+
+        if self.pool is not None and k > 1:
+            worst = max(self.pool.map(drive, range(k)))
+        else:
+            worst = max(drive(j) for j in range(k))
         for st in self.streams:
             main.wait_stream(st)
         return worst
