@@ -1051,6 +1051,7 @@ int Engine::ensure_rows_buffer(uint32_t n) {
     // holds n row indices and, behind them (8-byte aligned), two tables of n row pointers
     if (rows_cap_ >= n) return B2_OK;
     CU_TRY(cudaStreamSynchronize(ST));
+    CU_TRY(cudaStreamSynchronize(CIN));  // a scatter kernel may still be reading the pointer tables
     cudaFree(d_rows_);
     d_rows_ = nullptr;
     rows_cap_ = 0;
