@@ -188,7 +188,7 @@ def config5(args):
     import torch
     import torch.distributed as dist
     from digilogic_b200 import SimulationRunResult, SimulatorBuilder, netgen
-    from digilogic_b200.batch import BatchRunner, gather_output_planes, shard_words
+    from digilogic_b200.batch import InterleavedRunner, gather_output_planes, shard_words
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -201,19 +201,26 @@ def config5(args):
         dist.init_process_group("nccl", device_id=dev)
     t0 = time.perf_counter()
     gen = netgen.random_dag(n_gates=10_000_000, depth=200, n_inputs=16384, n_outputs=1024, seed=0xD1610005)
-    sim = gen.emit(SimulatorBuilder()).build()
+    first = gen.emit(SimulatorBuilder()).build()
     build_s = time.perf_counter() - t0
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    sim.set_device(local)
-    sim.set_stream(stream.cuda_stream)
+    made = []
+
+    def make_sim():
+        sim = first if not made else gen.emit(SimulatorBuilder()).build()
+        made.append(sim)
+        sim.set_device(local)
+        return sim
+
     words_local = args.lanes // 64
     w0, _ = shard_words(words_local * world, world, rank)
-    runner = BatchRunner(sim, gen.inputs, gen.outputs, args.tile_words)
+    runner = InterleavedRunner(make_sim, gen.inputs, gen.outputs, args.tile_words, args.streams, device=dev)
+    sim = runner.sims[0]
     ov = torch.zeros((len(gen.outputs), words_local), dtype=torch.int64, device=dev)
     om = torch.zeros_like(ov)
     # warm-up on two tiles
-    runner.run_generated(w0, 2 * args.tile_words, 0xD1610005, 0, ov, om)
+    runner.run_generated(w0, 2 * args.streams * args.tile_words, 0xD1610005, 0, ov, om)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -232,8 +239,8 @@ def config5(args):
     if rank == 0:
         evals = 10_000_000 * args.lanes * world
         print(json.dumps({"config": 5, "workload": "random DAG, 10M gates, depth 200, 16384 inputs; lanes sharded over ranks, NCCL all-gather of 1024 output rows",
-                          "n_gpus": world, "lanes_per_gpu": args.lanes, "lanes_total": args.lanes * world, "tile_words": args.tile_words,
-                          "store_bytes": sim.info.store_bytes, "netlist_build_s": build_s, "ms": ms,
+                          "n_gpus": world, "lanes_per_gpu": args.lanes, "lanes_total": args.lanes * world, "tile_words": args.tile_words, "streams": args.streams,
+                          "store_bytes": sim.info.store_bytes * args.streams, "netlist_build_s": build_s, "ms": ms,
                           "gate_lane_evals_per_s": evals / (ms * 1e-3), "hbm_roofline_frac_of_measured": 0.75 * evals / (ms * 1e-3) / 6554.9e9 / world,
                           "outputs_all_valid": all_valid,
                           "checksum": f"{int((gv.sum() ^ gm.sum()).item()) & 0xFFFFFFFFFFFFFFFF:#018x}"}))
@@ -246,7 +253,8 @@ def main():
     ap.add_argument("--config", type=int, required=True, choices=[2, 4, 5])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--lanes", type=int, default=None)
-    ap.add_argument("--tile-words", type=int, default=512)
+    ap.add_argument("--tile-words", type=int, default=None)
+    ap.add_argument("--streams", type=int, default=2)
     ap.add_argument("--clocks", type=int, default=200)
     ap.add_argument("--bits", type=int, default=64)
     ap.add_argument("--chains", type=int, default=64)
@@ -256,6 +264,8 @@ def main():
     args = ap.parse_args()
     if args.lanes is None:
         args.lanes = {2: 1 << 20, 4: 65536, 5: 1 << 23}[args.config]
+    if args.tile_words is None:
+        args.tile_words = 32   # config 5: 50 000 gates per level x 32 lane-words = the launch size of config 3 at 256
     {2: config2, 4: config4, 5: config5}[args.config](args)
 
 
