@@ -178,3 +178,33 @@ def test_no_cpu_fallback():
         with pytest.raises(d.B200Error) as e:
             fn()
         assert e.value.code == 18 and "no CPU path" in str(e.value)
+
+
+def _compile_c_client(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "c_abi_smoke")
+    lib_dir = os.path.dirname(_ffi._build.LIB_PATH)
+    _ffi.lib()
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L", lib_dir, "-ldigilogic_b200",
+                    f"-Wl,-rpath,{lib_dir}"], check=True)
+    return exe
+
+
+def test_header_is_c99_and_a_c_client_links(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and a plain-C program links against the library.
+    Without a GPU the client must stop at B2_ERR_NO_DEVICE (exit 77), never compute on the CPU."""
+    import subprocess
+    exe = _compile_c_client(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    if _has_gpu():
+        assert res.returncode == 0, res.stderr
+    else:
+        assert res.returncode == 77 and "no CUDA device" in res.stderr, (res.returncode, res.stderr)
+
+
+@pytest.mark.gpu
+def test_c_client_on_gpu(tmp_path):
+    import subprocess
+    res = subprocess.run([_compile_c_client(tmp_path)], capture_output=True, text=True)
+    assert res.returncode == 0 and "c_abi_smoke ok" in res.stdout, res.stderr
