@@ -133,3 +133,29 @@ def test_config4_sequential_vs_oracle(n_hazard, max_steps, resident):
         run_and_compare(("down", step))
     assert seen_unsettled == (n_hazard > 0)
     assert sim.info.last_mode == (3 if resident else 2)
+
+
+def test_config5_netlist_sampled_against_oracle():
+    """10M gates, depth 200, 16 384 inputs (BASELINE config 5): one 32-word tile from the end of the
+    2^26-lane batch, two of its lane-words re-computed by the CPU bit-sliced model — every 997th wire
+    of the netlist and the whole block of designated outputs."""
+    gen = netgen.random_dag(n_gates=10_000_000, depth=200, n_inputs=16384, n_outputs=1024, seed=0xD1610005)
+    sim = gen.emit(SimulatorBuilder()).build()
+    info = sim.info
+    assert (info.n_gates2, info.depth, info.n_sources) == (10_000_000, 200, 16384)
+    tile, word_base = 32, (1 << 20) - 32
+    sim.set_lanes(tile * 64)
+    sim.fill_stimulus(gen.inputs, seed=0xD1610005, lane_word_base=word_base, mode=1)
+    res, conflict, unsettled = sim.run_sim_lanes(10_000)
+    assert res == SimulationRunResult.Ok and not conflict.any() and not unsettled.any()
+    sample = [3, 31]
+    bs = oracle.BitSliced(gen.emit(oracle.Builder()), 64 * len(sample), gen.n_wires)
+    v, m = netgen.stimulus_words(0xD1610005, len(gen.inputs), tile, word_base, 1)
+    for i, w in enumerate(gen.inputs):
+        bs.set_drive(int(w), v[i, sample], m[i, sample])
+    assert not bs.eval_dag().any()
+    some = np.concatenate([np.arange(0, gen.n_wires, 997, dtype=np.uint32), gen.outputs])
+    gv, gm = sim.gather_wires_host(some)
+    ref_v = np.stack([bs.get(int(w))[0] for w in some])
+    ref_m = np.stack([bs.get(int(w))[1] for w in some])
+    assert (gv[:, sample] == ref_v).all() and (gm[:, sample] == ref_m).all()
