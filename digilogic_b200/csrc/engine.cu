@@ -1406,7 +1406,8 @@ int Engine::run_jacobi(uint64_t max_steps) {
     if ((rc = drives_begin())) return rc;
     const uint32_t pairs = stride_ / 2;
     const Shape sh = shape_for(pairs);
-    const uint64_t N = max_steps == UINT64_MAX ? UINT64_MAX : max_steps + 1;
+    // step_sim calls gsim allows after begin_sim: max_steps + 1 with its `steps > max_steps` check
+    const uint64_t N = opt_budget_inclusive_ ? max_steps : (max_steps == UINT64_MAX ? UINT64_MAX : max_steps + 1);
     const uint64_t last = N >= UINT64_MAX - 2 ? UINT64_MAX : N + 2;  // the final, check-only application
     const uint32_t n_extra = (uint32_t)extra_rows_.size();
     if (n_extra && extra_rows_dirty_) {
@@ -1544,7 +1545,8 @@ uint32_t Engine::resident_wpc() const {
 
 int Engine::run_resident(uint64_t max_steps) {
     const uint32_t wpc = resident_wpc();
-    const uint64_t N = max_steps == UINT64_MAX ? UINT64_MAX : max_steps + 1;
+    // step_sim calls gsim allows after begin_sim: max_steps + 1 with its `steps > max_steps` check
+    const uint64_t N = opt_budget_inclusive_ ? max_steps : (max_steps == UINT64_MAX ? UINT64_MAX : max_steps + 1);
     const uint64_t last = N >= UINT64_MAX - 2 ? UINT64_MAX : N + 2;
     const uint32_t n_extra = (uint32_t)extra_rows_.size();
     int rc;
@@ -1610,7 +1612,7 @@ int Engine::run(uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled, boo
         last_mode_ = 0;
         last_apps_ = 0;
         result = B2_RUN_CONFLICT;
-    } else if (!net_.cyclic && max_steps >= net_.depth && !(stride_ <= 4 && resident_wpc() && use_resident_)) {
+    } else if (!net_.cyclic && max_steps >= (uint64_t)net_.depth + 1 && !(stride_ <= 4 && resident_wpc() && use_resident_)) {
         result = run_levelised(async && !conflict && !unsettled);
     } else if (use_resident_ && resident_wpc()) {
         result = run_resident(max_steps);  // small netlist: the whole run_sim loop on chip

@@ -59,6 +59,7 @@ class Engine {
     void set_use_resident(bool on) { use_resident_ = on; }
     void set_valid_elision(bool on) { opt_elision_ = on; }
     void set_use_graph(bool on) { opt_graph_ = on; }
+    void set_budget_inclusive(bool on) { opt_budget_inclusive_ = on; }
     void set_use_frontier(bool on) { opt_frontier_ = on; frontier_valid_ = false; }
     void set_eval_unroll(uint32_t u) { opt_u_ = (u == 2 || u == 4) ? u : 0; level_graph_key_ = 0; }
 
@@ -139,6 +140,7 @@ class Engine {
     uint8_t *d_rowchg_[2] = {nullptr, nullptr};
     int chg_w_ = 0;
     bool frontier_valid_ = false, opt_frontier_ = true;
+    bool opt_budget_inclusive_ = false;  // SURVEY.md A.6-1 switch: `steps >= max_steps` instead of `>`
     uint32_t opt_u_ = 0;  // 0 = automatic gates-per-thread choice in k_eval2
     bool use_resident_ = true, resident_attr_set_ = false;
     unsigned long long *d_max_apps_ = nullptr;

@@ -145,6 +145,9 @@ enum b2_option {
                                   CUDA graph and replayed per run. */
     ,
     B2_OPT_EVAL_UNROLL = 4,    /* default 0 = automatic.  2 or 4: gates per thread in the per-level kernel (tuning knob). */
+    B2_OPT_STEP_BUDGET_INCLUSIVE = 6, /* default 0.  gsim's run_sim is restated as `if steps > max_steps { MaxStepsReached }`
+                                  (at most max_steps + 1 steps after begin_sim).  1 switches to `>=`, should the differential
+                                  run against the real crate (oracle/gsim_diff) say so — SURVEY.md A.6-1. */
     B2_OPT_FRONTIER = 5        /* default 1.  Unit-delay runs in HBM re-evaluate a gate only if one of its fan-in rows or
                                   its own output row changed (on any lane) in the previous application. */
 };

@@ -161,3 +161,31 @@ def test_many_clients_independent():
     for cid in range(1, 9):
         w, p0, p1 = sv.get_net_state(cid, 2)
         assert (w, p0[0] & 1, p1[0] & 1) == (1, 0 if cid % 2 else 1, 1)
+
+
+@pytest.mark.parametrize("resident", [True, False])
+def test_step_budget_switch_moves_with_the_oracle(resident):
+    """SURVEY.md A.6-1 is one switch on both sides: with `steps >= max_steps` the oscillating latch of
+    A.7 row 6 stops one step earlier (Q = Q' = 1 instead of 0) — engine and oracle must agree either way."""
+    for inclusive in (0, 1):
+        oracle.lib().go_set_config(inclusive, 0, 0, 0)
+        try:
+            def mk(builder):
+                s_, r_, q, qn = (builder.add_wire() for _ in range(4))
+                builder.add_nand_gate([s_, qn], q)
+                builder.add_nand_gate([r_, q], qn)
+                return builder.build(), s_, r_, q, qn
+            osim, s_, r_, q, qn = mk(oracle.Builder())
+            gsim, *_ = mk(SimulatorBuilder())
+            gsim.set_option(gsim.OPT_RESIDENT_KERNEL, int(resident))
+            gsim.set_option(gsim.OPT_STEP_BUDGET_INCLUSIVE, inclusive)
+            for sd, rd, ms in [(L0, L0, 100), (L1, L1, 10), (L1, L1, 11), (L0, L1, 0), (L1, L1, 0), (L1, L0, 1), (L1, L1, 3)]:
+                osim.set_wire_drive(s_, *sd); osim.set_wire_drive(r_, *rd)
+                gsim.set_wire_drive(s_, LogicState(*sd)); gsim.set_wire_drive(r_, LogicState(*rd))
+                assert int(gsim.run_sim(ms)) == osim.run_sim(ms), (inclusive, sd, rd, ms)
+                for w in (q, qn):
+                    assert gsim.get_wire_state(w) == LogicState(*osim.get_wire_state(w)), (inclusive, sd, rd, ms, w)
+            if inclusive == 0:
+                pass
+        finally:
+            oracle.lib().go_set_config(0, 0, 0, 0)
