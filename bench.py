@@ -55,7 +55,8 @@ def parse_args():
     ap.add_argument("--inputs", type=int, default=4096)
     ap.add_argument("--outputs", type=int, default=1024)
     ap.add_argument("--lanes", type=int, default=1 << 24, help="stimulus lanes per GPU")
-    ap.add_argument("--tile-words", type=int, default=256, help="64-lane words resident per tile and replica")
+    ap.add_argument("--tile-words", type=int, default=0,
+                    help="64-lane words resident per tile and replica (0 = batch.auto_tile_words: 256 for this netlist)")
     ap.add_argument("--streams", type=int, default=2, help="simulator replicas on separate CUDA streams, alternating tiles")
     ap.add_argument("--max-steps", type=int, default=10_000)
     ap.add_argument("--e2e-steps", type=int, default=1)
@@ -233,7 +234,9 @@ def run_b200(args):
     words_local = args.lanes // 64
     total_words = words_local * world
     w_begin, w_end = shard_words(total_words, world, rank)
-    tile = min(args.tile_words, words_local)
+    from digilogic_b200.batch import auto_tile_words
+    tile = min(args.tile_words, words_local) if args.tile_words else auto_tile_words(first, words_local)
+    args.tile_words = tile
     assert words_local % tile == 0
     made = []
 

@@ -215,6 +215,9 @@ def config5(args):
 
     words_local = args.lanes // 64
     w0, _ = shard_words(words_local * world, world, rank)
+    if args.tile_words is None:
+        from digilogic_b200.batch import auto_tile_words
+        args.tile_words = auto_tile_words(first, words_local)   # 32 for this netlist (50 000 gates per level)
     runner = InterleavedRunner(make_sim, gen.inputs, gen.outputs, args.tile_words, args.streams, device=dev)
     sim = runner.sims[0]
     ov = torch.zeros((len(gen.outputs), words_local), dtype=torch.int64, device=dev)
@@ -264,8 +267,7 @@ def main():
     args = ap.parse_args()
     if args.lanes is None:
         args.lanes = {2: 1 << 20, 4: 65536, 5: 1 << 23}[args.config]
-    if args.tile_words is None:
-        args.tile_words = 32   # config 5: 50 000 gates per level x 32 lane-words = the launch size of config 3 at 256
+
     {2: config2, 4: config4, 5: config5}[args.config](args)
 
 

@@ -9,8 +9,6 @@ tests).  torch is used for device buffers, streams and the collective only.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
-
 import numpy as np
 
 from .gsim import Simulator, SimulationRunResult
@@ -39,12 +37,22 @@ def choose_tile_words(sim: Simulator, n_words: int, budget_bytes: int, unit_dela
     return min(t, n_words)
 
 
-@dataclass
-class BatchResult:
-    value: "object"        # [n_outputs, words_local] device tensor (uint64 bit pattern in int64) or numpy array
-    valid: "object"
-    worst: SimulationRunResult
-    words: int
+def auto_tile_words(sim: Simulator, n_words: int, l2_level_bytes: int = 20 << 20) -> int:
+    """Tile size (64-lane words) for the levelised path: small enough that one level's output rows
+    (gates per level x tile x 16 B) stay in L2 until the next level has read them — about 20 MB per
+    replica with two replicas in flight on a 126 MB L2 — but never below 32 words (one warp per row
+    pair keeps loads coalesced) nor above what the batch holds.  Config 3 (5000 gates per level)
+    -> 256, config 5 (50 000 per level) -> 32; measured optimum in profiles/README.md."""
+    info = sim.info
+    if info.cyclic or info.depth == 0:
+        return min(n_words, 1024)
+    per_level = max((info.n_gates2 + info.n_gates_wide) / info.depth, 1.0)
+    t = int(l2_level_bytes / (16.0 * per_level))
+    t = max(32, min(t, 4096))
+    t = 1 << (t.bit_length() - 1)          # power of two: divides the usual batch sizes
+    while t > 1 and n_words % t:
+        t >>= 1
+    return max(1, min(t, n_words))
 
 
 class BatchRunner:
@@ -57,7 +65,6 @@ class BatchRunner:
         self.tile_words = int(tile_words)
         self.max_steps = int(max_steps)
         sim.set_lanes(self.tile_words * 64)
-        self.run_seconds_events = []   # (start, end) torch events around the settle calls, if requested
 
     # -- device-resident stimulus (generated on the GPU from the global lane-word index)
     def run_generated(self, word_begin: int, n_words: int, seed: int, mode: int, out_value, out_valid,

@@ -208,3 +208,14 @@ def test_c_client_on_gpu(tmp_path):
     import subprocess
     res = subprocess.run([_compile_c_client(tmp_path)], capture_output=True, text=True)
     assert res.returncode == 0 and "c_abi_smoke ok" in res.stdout, res.stderr
+
+
+def test_auto_tile_words():
+    from digilogic_b200.batch import auto_tile_words
+    cfg3 = netgen.random_dag(n_gates=200_000, depth=40, n_inputs=64, n_outputs=16).emit(d.SimulatorBuilder()).build()   # 5000 per level
+    assert auto_tile_words(cfg3, 262144) == 256
+    cfg5 = netgen.random_dag(n_gates=500_000, depth=10, n_inputs=64, n_outputs=16).emit(d.SimulatorBuilder()).build()   # 50 000 per level
+    assert auto_tile_words(cfg5, 131072) == 16 or auto_tile_words(cfg5, 131072) == 32
+    mul = netgen.array_multiplier(32).emit(d.SimulatorBuilder()).build()
+    assert auto_tile_words(mul, 16384) == 4096
+    assert auto_tile_words(mul, 96) == 32 and auto_tile_words(mul, 7) == 1
