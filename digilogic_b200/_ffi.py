@@ -16,7 +16,7 @@ class SimInfo(C.Structure):
     _fields_ = [
         ("n_wires", u32), ("n_rows", u32), ("n_sources", u32), ("n_gates2", u32), ("n_gates_wide", u32),
         ("depth", u32), ("cyclic", u32), ("multi_driver", u32), ("n_lanes", u64), ("lane_words", u32),
-        ("row_stride", u32), ("store_bytes", u64), ("last_mode", u32), ("reserved", u32),
+        ("row_stride", u32), ("store_bytes", u64), ("last_mode", u32), ("n_gates3", u32),
         ("last_applications", u64),
     ]
 

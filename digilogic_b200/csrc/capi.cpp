@@ -126,6 +126,7 @@ int b2_sim_get_info(const b2_sim *s, b2_sim_info *out) {
     out->n_rows = n.n_rows;
     out->n_sources = n.n_src;
     out->n_gates2 = n.n_g2();
+    out->n_gates3 = n.n_g3();
     out->n_gates_wide = n.n_wide();
     out->depth = n.depth;
     out->cyclic = n.cyclic;

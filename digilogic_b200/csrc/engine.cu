@@ -126,7 +126,7 @@ __host__ __device__ inline uint64_t splitmix64(uint64_t x) {
 // pieces of the same fan-in rows.
 
 struct Eval2Args {
-    const uint32_t *fan0, *fan1;
+    const uint32_t *fan0, *fan1, *fan2;  // fan2: three-input gates only (NIN = 3)
     const uint8_t *kind;
     const uint64_t *in_val, *in_vld;  // rows read (A)
     uint64_t *out_val, *out_vld;      // rows written (A in place for the levelised pass, B for unit delay)
@@ -157,7 +157,8 @@ __device__ __forceinline__ void mark_changed(uint8_t *chg, uint32_t row, bool ch
 // valid plane by construction (every gate maps valid inputs to a valid output), so that plane is
 // neither read nor written: 24 B instead of 48 B per gate-word.  Rows that may carry X/Z take the
 // full two-plane path; the result is bit-identical either way.
-template <int U, bool JACOBI, bool KV>
+// NIN = 3: three-input gates, ((a op b) op c) with one inversion at the end for NAND/NOR/XNOR.
+template <int U, bool JACOBI, bool KV, int NIN = 2>
 __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a) {
     const uint32_t pb = blockIdx.x % a.pair_blocks, gb = blockIdx.x / a.pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
     // Explicit phases, each a fully unrolled loop over the U gates of this thread, so that every
     // dependent step (indices -> elision flags -> plane words) costs one memory round trip for all
     // U gates together; loads are branch-free (tail gates are clamped, elided planes predicated off).
-    uint32_t f0[U], f1[U], kind[U], orow[U];
+    uint32_t f0[U], f1[U], f2[U], kind[U], orow[U];
     bool live[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -177,26 +178,35 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
         const uint32_t gg = live[u] ? g : a.g_end - 1;
         f0[u] = a.fan0[gg];
         f1[u] = a.fan1[gg];
+        f2[u] = NIN == 3 ? a.fan2[gg] : 0;
         kind[u] = a.kind[gg];
         orow[u] = a.row_base + gg;
     }
-    bool k0[U], k1[U], act[U];
+    bool k0[U], k1[U], k2[U], act[U];
     bool any_act = false;
     const bool allv = KV && *a.all_valid != 0;  // uniform: with all drives valid no per-row flag is read or written
 #pragma unroll
     for (int u = 0; u < U; u++) {
         k0[u] = KV && (allv || a.kv[f0[u]] != 0);
         k1[u] = KV && (allv || a.kv[f1[u]] != 0);  // NOT gates have f1 == f0
+        k2[u] = NIN == 3 ? (KV && (allv || a.kv[f2[u]] != 0)) : true;
         // unit delay: a gate whose fan-ins did not change in the previous application keeps its
         // output; it is evaluated only if that output row itself changed (the other buffer is stale)
-        act[u] = !JACOBI || !a.chg_prev || (a.chg_prev[f0[u]] | a.chg_prev[f1[u]] | a.chg_prev[orow[u]]) != 0;
+        act[u] = !JACOBI || !a.chg_prev ||
+                 (a.chg_prev[f0[u]] | a.chg_prev[f1[u]] | (NIN == 3 ? a.chg_prev[f2[u]] : 0) | a.chg_prev[orow[u]]) != 0;
         any_act |= act[u] && live[u];
     }
     if (JACOBI && !any_act) return;
-    ulonglong2 av[U], am[U], bv[U], bm[U], ov[U], om[U];
+    ulonglong2 av[U], am[U], bv[U], bm[U], cv[U], cm[U], ov[U], om[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const size_t r0 = (size_t)f0[u] * a.stride + col, r1 = (size_t)f1[u] * a.stride + col;
+        if (NIN == 3) {
+            const size_t r2 = (size_t)f2[u] * a.stride + col;
+            const bool skip = JACOBI && !act[u];
+            cv[u] = ld_stream_unless(a.in_val + r2, skip);
+            cm[u] = ld_stream_unless(a.in_vld + r2, skip || (KV && k2[u]));
+        }
         if (JACOBI) {
             const bool skip = !act[u];
             const size_t o = (size_t)orow[u] * a.stride + col;
@@ -222,12 +232,24 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
 #pragma unroll
     for (int u = 0; u < U; u++) {
         ulonglong2 rv, rm;
-        gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
-        gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
+        if (NIN == 3) {
+            const uint32_t base = kind[u] >= K_NAND ? kind[u] - 3 : kind[u];  // fold with the positive op
+            gate_word(base, av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
+            gate_word(base, av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
+            gate_word(base, rv.x, rm.x, cv[u].x, cm[u].x, rv.x, rm.x);
+            gate_word(base, rv.y, rm.y, cv[u].y, cm[u].y, rv.y, rm.y);
+            if (kind[u] >= K_NAND) {
+                rv.x = ~rv.x | ~rm.x;
+                rv.y = ~rv.y | ~rm.y;
+            }
+        } else {
+            gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
+            gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
+        }
         bool ch = false;
         if (live[u] && act[u]) {
             const size_t o = (size_t)orow[u] * a.stride + col;
-            const bool okv = KV && k0[u] && k1[u];
+            const bool okv = KV && k0[u] && k1[u] && k2[u];
             st_pair(a.out_val + o, rv);
             if (!okv) st_pair(a.out_vld + o, rm);
             if (KV && !allv && pb == 0 && threadIdx.x == 0) a.kv[orow[u]] = okv ? 1 : 0;
@@ -564,7 +586,7 @@ __global__ void __launch_bounds__(256) k_pack_lane0(const uint32_t *rows, uint32
 // CTAs never talk to each other and each stops at its own fixed point.  This is the path of the
 // reference's real use (GUI: one lane, max_steps = 10 000, latches that may oscillate).
 struct ResidentArgs {
-    const uint32_t *fan0, *fan1;
+    const uint32_t *fan0, *fan1, *fan2;
     const uint8_t *kind2;
     const uint32_t *woff, *win;
     const uint8_t *wkind, *wnsel;
@@ -575,7 +597,7 @@ struct ResidentArgs {
     uint64_t *conflict, *unsettled;   // lane status words [stride]
     RunFlags *flags;
     unsigned long long *max_apps;     // max applications over CTAs
-    uint32_t n_src, n_g2, n_wide, n_extra, n_rows;
+    uint32_t n_src, n_g2, n_g3, n_wide, n_extra, n_rows;   // n_g2: one/two-input gates, n_g3: three-input gates
     uint32_t stride, wpc;             // words per row; lane-words per CTA
     uint64_t n_lanes;
     uint64_t last;                    // index of the final, check-only application
@@ -659,9 +681,9 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
 
     uint64_t k = a.cold ? 1 : 0;
     unsigned long long apps = 0;
-    const size_t n_items = (size_t)(a.n_src + a.n_g2 + a.n_wide) * wpc;
+    const size_t n_items = (size_t)(a.n_src + a.n_g2 + a.n_g3 + a.n_wide) * wpc;
     // (a cold start without components is already final: W_1 = D; a warm one still takes the new drives)
-    if (a.n_g2 + a.n_wide > 0 || !a.cold) {
+    if (a.n_g2 + a.n_g3 + a.n_wide > 0 || !a.cold) {
         for (;;) {
             k++;
             apps++;
@@ -680,8 +702,14 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
                     const uint32_t g = row - a.n_src;
                     const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j;
                     gate_word(a.kind2[g], AV[r0], AM[r0], AV[r1], AM[r1], rv, rm);
+                } else if (row < a.n_src + a.n_g2 + a.n_g3) {
+                    const uint32_t g = row - a.n_src, kind = a.kind2[g], base = kind >= K_NAND ? kind - 3 : kind;
+                    const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j, r2 = (size_t)a.fan2[g] * wpc + j;
+                    gate_word(base, AV[r0], AM[r0], AV[r1], AM[r1], rv, rm);
+                    gate_word(base, rv, rm, AV[r2], AM[r2], rv, rm);
+                    if (kind >= K_NAND) rv = ~rv | ~rm;
                 } else {
-                    wide_gate_word(a, row - a.n_src - a.n_g2, AV, AM, wpc, j, rv, rm);
+                    wide_gate_word(a, row - a.n_src - a.n_g2 - a.n_g3, AV, AM, wpc, j, rv, rm);
                 }
                 const u64 d = (rv ^ AV[i]) | (rm ^ AM[i]);
                 BV[i] = rv;
@@ -756,6 +784,7 @@ Engine::~Engine() {
         free_store();
         cudaFree(d_fan0_);
         cudaFree(d_fan1_);
+        cudaFree(d_fan2_);
         cudaFree(d_kind2_);
         cudaFree(d_wide_off_);
         cudaFree(d_wide_in_);
@@ -893,6 +922,7 @@ int Engine::ensure_device() {
     int rc;
     if ((rc = upload(&d_fan0_, net_.fan0))) return rc;
     if ((rc = upload(&d_fan1_, net_.fan1))) return rc;
+    if ((rc = upload(&d_fan2_, net_.fan2))) return rc;
     if ((rc = upload(&d_kind2_, net_.kind2))) return rc;
     if ((rc = upload(&d_wide_off_, net_.wide_off))) return rc;
     if ((rc = upload(&d_wide_in_, net_.wide_in))) return rc;
@@ -1320,7 +1350,7 @@ int Engine::run_levelised(bool async) {
         uint32_t nodes = 0;
         for (const Level &lv : net_.levels) {
             if (lv.g2_end > lv.g2_begin) {
-                Eval2Args a{d_fan0_, d_fan1_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
+                Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
                             sh.pair_blocks, d_kv_, nullptr, nullptr, d_all_valid_};
                 // U gates per thread: 4 when the level still fills the machine several times over, else 2
                 // (more, smaller CTAs: a level of a small tile is only a wave or two of work)
@@ -1342,9 +1372,20 @@ int Engine::run_levelised(bool async) {
                 }
                 nodes++;
             }
+            if (lv.g3_end > lv.g3_begin) {
+                Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, V, M, V, M, nullptr, lv.g3_begin, lv.g3_end, net_.n_src, stride_, pairs,
+                            sh.pair_blocks, d_kv_, nullptr, nullptr, d_all_valid_};
+                const uint32_t per = sh.block.y * 2;
+                const uint32_t gb = (lv.g3_end - lv.g3_begin + per - 1) / per;
+                if (kv)
+                    k_eval2<2, false, true, 3><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                else
+                    k_eval2<2, false, false, 3><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                nodes++;
+            }
             if (lv.wide_end > lv.wide_begin) {
                 WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, V, M, V, M, nullptr, lv.wide_begin, lv.wide_end,
-                           net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr, nullptr, nullptr, d_all_valid_};
+                           net_.n_src + net_.n_fast(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr, nullptr, nullptr, d_all_valid_};
                 const uint32_t gb = (lv.wide_end - lv.wide_begin + sh.block.y - 1) / sh.block.y;
                 k_eval_wide<false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
                 nodes++;
@@ -1441,7 +1482,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
         cold_ = false;
         frontier_valid_ = false;
         k = 1;
-        if (net_.n_g2() + net_.n_wide() == 0) {
+        if (net_.n_fast() + net_.n_wide() == 0) {
             if ((rc = drives_end())) return rc;
             return B2_RUN_OK;
         }
@@ -1476,16 +1517,24 @@ int Engine::run_jacobi(uint64_t max_steps) {
             LAUNCHED();
         }
         if (net_.n_g2()) {
-            Eval2Args a{d_fan0_, d_fan1_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
+            Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
                         sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
             const uint32_t per = sh.block.y * EVAL2_U;
             const uint32_t gb = (net_.n_g2() + per - 1) / per;
             k_eval2<EVAL2_U, true, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
             LAUNCHED();
         }
+        if (net_.n_g3()) {
+            Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, net_.n_g2(), net_.n_fast(), net_.n_src, stride_,
+                        pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
+            const uint32_t per = sh.block.y * 2;
+            const uint32_t gb = (net_.n_g3() + per - 1) / per;
+            k_eval2<2, true, false, 3><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+            LAUNCHED();
+        }
         if (net_.n_wide()) {
             WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, AV, AM, BV, BM, d_changed_, 0, net_.n_wide(),
-                       net_.n_src + net_.n_g2(), stride_, pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
+                       net_.n_src + net_.n_fast(), stride_, pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
             const uint32_t gb = (net_.n_wide() + sh.block.y - 1) / sh.block.y;
             k_eval_wide<true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
             LAUNCHED();
@@ -1561,7 +1610,7 @@ int Engine::run_resident(uint64_t max_steps) {
     k_clear_flags<<<1, 1, 0, ST>>>(d_flags_);
     LAUNCHED();
     ResidentArgs a;
-    a.fan0 = d_fan0_; a.fan1 = d_fan1_; a.kind2 = d_kind2_;
+    a.fan0 = d_fan0_; a.fan1 = d_fan1_; a.fan2 = d_fan2_; a.kind2 = d_kind2_;
     a.woff = d_wide_off_; a.win = d_wide_in_; a.wkind = d_wide_kind_; a.wnsel = d_wide_nsel_;
     a.xrows = d_extra_rows_; a.xval = xdrv_val_; a.xvld = xdrv_vld_;
     a.dval = drv_val_; a.dvld = drv_vld_;
@@ -1569,7 +1618,7 @@ int Engine::run_resident(uint64_t max_steps) {
     a.conflict = d_conflict_; a.unsettled = d_unsettled_;
     a.flags = d_flags_;
     a.max_apps = d_max_apps_;
-    a.n_src = net_.n_src; a.n_g2 = net_.n_g2(); a.n_wide = net_.n_wide(); a.n_extra = n_extra; a.n_rows = net_.n_rows;
+    a.n_src = net_.n_src; a.n_g2 = net_.n_g2(); a.n_g3 = net_.n_g3(); a.n_wide = net_.n_wide(); a.n_extra = n_extra; a.n_rows = net_.n_rows;
     a.stride = stride_; a.wpc = wpc;
     a.n_lanes = n_lanes_;
     a.last = last;

@@ -91,7 +91,7 @@ class Engine {
     uint64_t store_bytes_ = 0;
 
     // netlist on the device
-    uint32_t *d_fan0_ = nullptr, *d_fan1_ = nullptr, *d_wide_off_ = nullptr, *d_wide_in_ = nullptr;
+    uint32_t *d_fan0_ = nullptr, *d_fan1_ = nullptr, *d_fan2_ = nullptr, *d_wide_off_ = nullptr, *d_wide_in_ = nullptr;
     uint8_t *d_kind2_ = nullptr, *d_wide_kind_ = nullptr, *d_wide_nsel_ = nullptr;
 
     // wire-state store: two buffers (second one only for unit-delay runs), separate planes

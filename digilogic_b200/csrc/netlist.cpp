@@ -178,10 +178,12 @@ void compile(const Builder &b, Compiled &c) {
     // ---- order: class (2-input first), then level, then kind, then creation order (stable)
     std::vector<uint32_t> order(G);
     std::iota(order.begin(), order.end(), 0u);
-    auto is_wide = [&](uint32_t g) { return gates[g].kind == K_MUX || gates[g].n_in > 2; };
+    // class 0: one/two inputs, class 1: three inputs (both on the fast kernels), class 2: CSR kernel
+    auto cls = [&](uint32_t g) -> int { return gates[g].kind == K_MUX || gates[g].n_in > 3 ? 2 : (gates[g].n_in == 3 ? 1 : 0); };
+    auto is_wide = [&](uint32_t g) { return cls(g) == 2; };
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-        const bool wx = is_wide(x), wy = is_wide(y);
-        if (wx != wy) return !wx;
+        const int wx = cls(x), wy = cls(y);
+        if (wx != wy) return wx < wy;
         if (gates[x].level != gates[y].level) return gates[x].level < gates[y].level;
         return gates[x].kind < gates[y].kind;
     });
@@ -203,12 +205,16 @@ void compile(const Builder &b, Compiled &c) {
     while (n2 < G && !is_wide(order[n2])) n2++;
     c.fan0.resize(n2);
     c.fan1.resize(n2);
+    c.fan2.resize(n2);
     c.kind2.resize(n2);
+    c.n_two = 0;
     for (uint32_t k = 0; k < n2; k++) {
         const BitGate &g = gates[order[k]];
         c.kind2[k] = g.kind;
         c.fan0[k] = c.row_of_bit[bin[g.in_off]];
         c.fan1[k] = g.n_in > 1 ? c.row_of_bit[bin[g.in_off + 1]] : c.fan0[k];
+        c.fan2[k] = g.n_in > 2 ? c.row_of_bit[bin[g.in_off + 2]] : c.fan0[k];
+        if (g.n_in <= 2) c.n_two = k + 1;
     }
     const uint32_t nw = G - n2;
     c.wide_kind.resize(nw);
@@ -227,13 +233,19 @@ void compile(const Builder &b, Compiled &c) {
     // ---- level table
     c.levels.clear();
     const uint32_t n_levels = c.cyclic ? (G ? 1u : 0u) : depth;
-    c.levels.assign(n_levels, Level{0, 0, 0, 0});
+    c.levels.assign(n_levels, Level{0, 0, 0, 0, 0, 0});
     {
         uint32_t k = 0;
         for (uint32_t l = 1; l <= n_levels; l++) {
             c.levels[l - 1].g2_begin = k;
-            while (k < n2 && gates[order[k]].level == l) k++;
+            while (k < c.n_two && gates[order[k]].level == l) k++;
             c.levels[l - 1].g2_end = k;
+        }
+        k = c.n_two;
+        for (uint32_t l = 1; l <= n_levels; l++) {
+            c.levels[l - 1].g3_begin = k;
+            while (k < n2 && gates[order[k]].level == l) k++;
+            c.levels[l - 1].g3_end = k;
         }
         k = 0;
         for (uint32_t l = 1; l <= n_levels; l++) {

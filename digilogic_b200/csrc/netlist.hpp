@@ -33,11 +33,12 @@ struct Builder {
     int add_mux(const uint32_t *in, size_t n, uint32_t select, uint32_t output, uint32_t *cell);
 };
 
-// One level of the levelised order: 2-input gates [g2_begin, g2_end) and wide gates
-// [wide_begin, wide_end).  Output rows are implicit:
-//   row(2-input gate i) = n_src + i,   row(wide gate j) = n_src + n_g2 + j.
+// One level of the levelised order: one/two-input gates [g2_begin, g2_end), three-input gates
+// [g3_begin, g3_end) (both index the fast arrays fan0/fan1/fan2/kind2; all three-input gates come
+// after all one/two-input gates) and wide gates [wide_begin, wide_end).  Output rows are implicit:
+//   row(fast gate i) = n_src + i,   row(wide gate j) = n_src + n_g2 + n_g3 + j.
 struct Level {
-    uint32_t g2_begin, g2_end, wide_begin, wide_end;
+    uint32_t g2_begin, g2_end, g3_begin, g3_end, wide_begin, wide_end;
 };
 
 struct Compiled {
@@ -47,9 +48,10 @@ struct Compiled {
     std::vector<uint32_t> row_of_bit;  // bit-net -> store row
     std::vector<uint8_t> bit_driven;   // bit-net has a gate driver
     uint32_t n_rows = 0, n_src = 0;
-    // one/two-input gates, in row order
-    std::vector<uint32_t> fan0, fan1;  // store rows
+    // fast gates (one to three inputs), in row order: n_g2 one/two-input gates, then n_g3 three-input gates
+    std::vector<uint32_t> fan0, fan1, fan2;  // store rows (fan2 = fan0 for gates with fewer inputs)
     std::vector<uint8_t> kind2;
+    uint32_t n_two = 0;
     // wide gates (n-ary, mux slices), CSR over store rows; mux: first n_sel entries are select bits
     std::vector<uint32_t> wide_off, wide_in;
     std::vector<uint8_t> wide_kind, wide_nsel;
@@ -58,7 +60,9 @@ struct Compiled {
     bool cyclic = false, multi_driver = false;
 
     uint32_t n_wires() const { return (uint32_t)width.size(); }
-    uint32_t n_g2() const { return (uint32_t)kind2.size(); }
+    uint32_t n_g2() const { return n_two; }
+    uint32_t n_g3() const { return (uint32_t)kind2.size() - n_two; }
+    uint32_t n_fast() const { return (uint32_t)kind2.size(); }
     uint32_t n_wide() const { return (uint32_t)wide_kind.size(); }
 };
 

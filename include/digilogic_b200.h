@@ -108,7 +108,7 @@ typedef struct b2_sim_info {
     uint32_t n_rows;        /* 1-bit rows of the wire-state store (sources first, then gate outputs) */
     uint32_t n_sources;     /* rows without a gate driver (primary inputs and floating nets) */
     uint32_t n_gates2;      /* 1-bit gates with one or two inputs (fast kernels) */
-    uint32_t n_gates_wide;  /* 1-bit n-ary gates and multiplexer slices (CSR kernel) */
+    uint32_t n_gates_wide;  /* 1-bit gates with four or more inputs and multiplexer slices (CSR kernel) */
     uint32_t depth;         /* number of levels; 0 when cyclic */
     uint32_t cyclic;        /* 1 if the netlist has a combinational feedback loop */
     uint32_t multi_driver;  /* 1 if some wire has two or more gate drivers (every run conflicts) */
@@ -117,7 +117,7 @@ typedef struct b2_sim_info {
     uint32_t row_stride;    /* allocated words per row */
     uint64_t store_bytes;   /* device bytes held by this simulator */
     uint32_t last_mode;     /* 0 none, 1 levelised, 2 unit-delay (Jacobi) in HBM, 3 unit-delay resident in shared memory */
-    uint32_t reserved;
+    uint32_t n_gates3;      /* 1-bit gates with three inputs (fast kernels, third operand) */
     uint64_t last_applications; /* whole-netlist evaluations made by the last run */
 } b2_sim_info;
 

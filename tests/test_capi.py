@@ -101,7 +101,7 @@ def test_compile_info_levels():
     b.add_and_gate([s_, r_, q], qn)
     i = b.build().info
     assert i.cyclic == 1 and i.depth == 0 and i.multi_driver == 1
-    assert i.n_sources == 10 and i.n_rows == 10 + 11 and i.n_gates2 == 2 + 8 and i.n_gates_wide == 1  # one row per gate
+    assert i.n_sources == 10 and i.n_rows == 10 + 11 and i.n_gates2 == 2 + 8 and i.n_gates3 == 1 and i.n_gates_wide == 0
 
 
 def test_build_takes_the_builder():

@@ -92,7 +92,7 @@ def test_config4_sequential_vs_oracle(n_hazard, max_steps, resident):
     seq = netgen.sequential(n_latches=24, n_chains=4, bits=8, n_hazard=n_hazard)
     ob = seq.emit(oracle.Builder())
     sim = seq.emit(SimulatorBuilder()).build()
-    assert sim.info.cyclic == 1 and sim.info.n_gates_wide > 0
+    assert sim.info.cyclic == 1 and sim.info.n_gates3 > 0
     sim.set_option(sim.OPT_RESIDENT_KERNEL, int(resident))
     sim.set_lanes(n_lanes)
     lanes = oracle.Lanes(ob, n_lanes)
