@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=1 << 24, help="stimulus lanes per GPU")
     ap.add_argument("--tile-words", type=int, default=0,
                     help="64-lane words resident per tile and replica (0 = batch.auto_tile_words: 256 for this netlist)")
+    ap.add_argument("--host-threads", type=int, default=1,
+                    help="1: one host thread per replica issues its launches (0 for runs under ncu)")
     ap.add_argument("--streams", type=int, default=2, help="simulator replicas on separate CUDA streams, alternating tiles")
     ap.add_argument("--max-steps", type=int, default=10_000)
     ap.add_argument("--e2e-steps", type=int, default=1)
@@ -246,7 +248,8 @@ def run_b200(args):
         sim.set_device(local_rank)
         return sim
 
-    runner = InterleavedRunner(make_sim, gen.inputs, gen.outputs, tile, args.streams, args.max_steps, device=dev)
+    runner = InterleavedRunner(make_sim, gen.inputs, gen.outputs, tile, args.streams, args.max_steps, device=dev,
+                               host_threads=bool(args.host_threads))
     sims = runner.sims
     sim = sims[0]
     if args.valid_elision:

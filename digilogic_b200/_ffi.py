@@ -81,8 +81,10 @@ def lib():
     """Loads libdigilogic_b200.so, building it first if needed. Fails loudly: no fallback."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
-        if not os.path.exists(path) or (os.environ.get("B2_AUTOBUILD", "1") == "1" and _build.needs_build()):
+        path = os.environ.get("B2_LIB_PATH") or _build.LIB_PATH   # B2_LIB_PATH: A/B runs of two builds on one box
+        if os.environ.get("B2_LIB_PATH"):
+            pass
+        elif not os.path.exists(path) or (os.environ.get("B2_AUTOBUILD", "1") == "1" and _build.needs_build()):
             path = _build.build()
         L = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
