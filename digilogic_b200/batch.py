@@ -193,28 +193,36 @@ class InterleavedRunner:
         in_stride, out_stride = in_value.strides[0] // 8, out_value.strides[0] // 8
         tiles = plan_tiles(n_words, tw)
         k = len(self.runners)
-        worst = SimulationRunResult.Ok
 
-        def upload(i):
-            r = self.runners[i % k]
-            o = 8 * (tiles[i][0] % ring_words)
-            r.sim.set_drives_lanes_ptr(r.inputs, in_value.ctypes.data + o, in_valid.ctypes.data + o, in_stride)
+        def drive(j):
+            # replica j's pipeline over its tiles: upload(next) while the current tile settles, read-back async
+            r = self.runners[j]
+            mine = tiles[j::k]
+            w = SimulationRunResult.Ok
 
-        for i in range(min(k, len(tiles))):
-            upload(i)
-        for i, (w0, _) in enumerate(tiles):
-            r = self.runners[i % k]
-            worst = max(worst, r.sim.run_sim_lanes_async(r.max_steps))
-            if i + k < len(tiles):
-                upload(i + k)           # waits for this replica's drives to be consumed, not for its settle
-            o = 8 * (w0 % ring_words)
-            r.sim.gather_wires_ptr(r.outputs, out_value.ctypes.data + o, out_valid.ctypes.data + o, out_stride,
-                                   device=False, async_=True)
-            if dev_out_value is not None:
-                r.sim.gather_wires_ptr(r.outputs, dev_out_value.data_ptr() + 8 * w0, dev_out_valid.data_ptr() + 8 * w0,
-                                       dev_out_value.stride(0), device=True)
-        for r in self.runners:
+            def upload(w0):
+                o = 8 * (w0 % ring_words)
+                r.sim.set_drives_lanes_ptr(r.inputs, in_value.ctypes.data + o, in_valid.ctypes.data + o, in_stride)
+
+            if mine:
+                upload(mine[0][0])
+            for i, (w0, _) in enumerate(mine):
+                w = max(w, r.sim.run_sim_lanes_async(r.max_steps))
+                if i + 1 < len(mine):
+                    upload(mine[i + 1][0])    # waits for this replica's drives to be consumed, not for its settle
+                o = 8 * (w0 % ring_words)
+                r.sim.gather_wires_ptr(r.outputs, out_value.ctypes.data + o, out_valid.ctypes.data + o, out_stride,
+                                       device=False, async_=True)
+                if dev_out_value is not None:
+                    r.sim.gather_wires_ptr(r.outputs, dev_out_value.data_ptr() + 8 * w0, dev_out_valid.data_ptr() + 8 * w0,
+                                           dev_out_value.stride(0), device=True)
             r.sim.synchronize()
+            return w
+
+        if self.pool is not None and k > 1:
+            worst = max(self.pool.map(drive, range(k)))
+        else:
+            worst = max(drive(j) for j in range(k))
         for st in self.streams:
             main.wait_stream(st)
         return worst
