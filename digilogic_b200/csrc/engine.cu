@@ -94,6 +94,12 @@ __device__ __forceinline__ void gate_word(uint32_t kind, u64 av, u64 am, u64 bv,
             m = am & bm;
             v = av ^ bv;
             break;
+        case K_BUF: {  // a = data, b = enable.  enable 1: the data (High-Z reads X); 0: High-Z; Z/X: X
+            const u64 en1 = bv & bm;
+            rm = en1 & am;
+            rv = (en1 & (av | ~am)) | ~bm;
+            return;
+        }
         default:  // K_NOT (single input)
             m = am;
             v = av;
@@ -421,6 +427,7 @@ __global__ void __launch_bounds__(256) k_extra_drive(const uint32_t *rows, uint3
     if (w >= stride) return;
     uint64_t c = 0;
     for (uint32_t i = 0; i < n; i++) {
+        if (rows[i] == 0xFFFFFFFFu) continue;  // slot of a tri-state net: k_resolve merges it
         const size_t o = (size_t)rows[i] * stride + w, x = (size_t)i * stride + w;
         const uint64_t dv = xval[x], dm = xvld[x];
         if (mode == 1) {
@@ -434,6 +441,62 @@ __global__ void __launch_bounds__(256) k_extra_drive(const uint32_t *rows, uint3
         }
     }
     if (mode == 0 && c) atomicOr((unsigned long long *)&conf[w], (unsigned long long)c);
+}
+
+// Tri-state nets (SURVEY.md A.4 wire update, restated for nets whose drivers can be High-Z):
+//   W'[net] = resolve(D[net], outputs of its drivers),  resolve = plane-wise OR,
+//   conflict where two operands are not High-Z.
+// The drivers' outputs were written to their own rows of B by the gate kernels of this application;
+// this kernel runs right after them, so the wire sees its drivers with no extra delay.  Every entry is
+// evaluated in every application (such nets are few); `cold` = first step of a fresh simulator, when
+// all component outputs are still High-Z and the wire is just its drive.
+struct ResolveArgs {
+    const uint32_t *off, *in;
+    const int32_t *xslot;             // entry -> slot of its external drive in the extra store, or -1
+    const uint64_t *xval, *xvld;      // extra drive store [slot][stride]
+    const uint64_t *a_val, *a_vld;    // previous state (change detection)
+    uint64_t *b_val, *b_vld;          // driver rows are read from, the wire row is written to, this buffer
+    uint64_t *changed, *conf;
+    uint8_t *chg_cur;
+    uint32_t n_res, row_base, stride, pairs, pair_blocks;
+    int cold;
+};
+
+__global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
+    const uint32_t pb = blockIdx.x % a.pair_blocks, rb = blockIdx.x / a.pair_blocks;
+    const uint32_t pair = pb * blockDim.x + threadIdx.x;
+    const uint32_t r = rb * blockDim.y + threadIdx.y;
+    if (pair >= a.pairs || r >= a.n_res) return;
+    const size_t col = (size_t)pair * 2;
+    ulonglong2 v = make_ulonglong2(0, 0), m = make_ulonglong2(0, 0);
+    const int32_t slot = a.xslot[r];
+    if (slot >= 0) {
+        const size_t x = (size_t)slot * a.stride + col;
+        v = *(const ulonglong2 *)(a.xval + x);
+        m = *(const ulonglong2 *)(a.xvld + x);
+    }
+    uint64_t cx = 0, cy = 0;
+    if (!a.cold)
+        for (uint32_t i = a.off[r]; i < a.off[r + 1]; i++) {
+            const size_t o = (size_t)a.in[i] * a.stride + col;
+            const ulonglong2 ov = *(const ulonglong2 *)(a.b_val + o), om = *(const ulonglong2 *)(a.b_vld + o);
+            cx |= (v.x | m.x) & (ov.x | om.x);
+            cy |= (v.y | m.y) & (ov.y | om.y);
+            v.x |= ov.x; v.y |= ov.y;
+            m.x |= om.x; m.y |= om.y;
+        }
+    const size_t o = (size_t)(a.row_base + r) * a.stride + col;
+    if (a.changed) {
+        const ulonglong2 pv = *(const ulonglong2 *)(a.a_val + o), pm = *(const ulonglong2 *)(a.a_vld + o);
+        const uint64_t dx = (v.x ^ pv.x) | (m.x ^ pm.x), dy = (v.y ^ pv.y) | (m.y ^ pm.y);
+        if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
+        if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
+        if (a.chg_cur && (dx | dy)) a.chg_cur[a.row_base + r] = 1;
+    }
+    if (cx) atomicOr((unsigned long long *)&a.conf[col], (unsigned long long)cx);
+    if (cy) atomicOr((unsigned long long *)&a.conf[col + 1], (unsigned long long)cy);
+    st_pair(a.b_val + o, v);
+    st_pair(a.b_vld + o, m);
 }
 
 // Per-lane bookkeeping after one application:
@@ -590,6 +653,9 @@ struct ResidentArgs {
     const uint8_t *kind2;
     const uint32_t *woff, *win;
     const uint8_t *wkind, *wnsel;
+    const uint32_t *res_off, *res_in; // tri-state nets: driver rows per resolved row (see k_resolve)
+    const int32_t *res_xslot;
+    uint32_t n_res;
     const uint32_t *xrows;            // rows with an external drive on a gate output
     const uint64_t *xval, *xvld;      // their drives [n_extra][stride]
     const uint64_t *dval, *dvld;      // source drives [n_src][stride]
@@ -668,12 +734,21 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
         s_unsettled[tid] = 0;
     }
     __syncthreads();
+    const uint32_t res_base = a.n_src + a.n_g2 + a.n_g3 + a.n_wide;
     if (a.cold) {
         for (size_t i = tid; i < (size_t)a.n_extra * wpc; i += nt) {
             const uint32_t x = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
-            if (w < a.stride) {
+            if (w < a.stride && a.xrows[x] != 0xFFFFFFFFu) {
                 AV[(size_t)a.xrows[x] * wpc + j] = a.xval[(size_t)x * a.stride + w];
                 AM[(size_t)a.xrows[x] * wpc + j] = a.xvld[(size_t)x * a.stride + w];
+            }
+        }
+        for (size_t i = tid; i < (size_t)a.n_res * wpc; i += nt) {
+            const uint32_t r = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
+            const int32_t slot = a.res_xslot[r];
+            if (w < a.stride && slot >= 0) {
+                AV[(size_t)(res_base + r) * wpc + j] = a.xval[(size_t)slot * a.stride + w];
+                AM[(size_t)(res_base + r) * wpc + j] = a.xvld[(size_t)slot * a.stride + w];
             }
         }
         __syncthreads();
@@ -717,11 +792,36 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
                 if (d) atomicOr((unsigned long long *)&s_changed[j], d);
             }
             __syncthreads();
+            // ---- tri-state nets: wire = resolve(drive, driver rows of B), conflict where two are not High-Z
+            if (a.n_res) {
+                for (size_t i = tid; i < (size_t)a.n_res * wpc; i += nt) {
+                    const uint32_t r = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
+                    u64 v = 0, m = 0, c = 0;
+                    const int32_t slot = a.res_xslot[r];
+                    if (slot >= 0 && w < a.stride) {
+                        v = a.xval[(size_t)slot * a.stride + w];
+                        m = a.xvld[(size_t)slot * a.stride + w];
+                    }
+                    for (uint32_t q = a.res_off[r]; q < a.res_off[r + 1]; q++) {
+                        const size_t o = (size_t)a.res_in[q] * wpc + j;
+                        c |= (v | m) & (BV[o] | BM[o]);
+                        v |= BV[o];
+                        m |= BM[o];
+                    }
+                    const size_t idx = (size_t)(res_base + r) * wpc + j;
+                    const u64 d = (v ^ AV[idx]) | (m ^ AM[idx]);
+                    BV[idx] = v;
+                    BM[idx] = m;
+                    if (d) atomicOr((unsigned long long *)&s_changed[j], d);
+                    if (c) atomicOr((unsigned long long *)&s_conf[j], c);
+                }
+                __syncthreads();
+            }
             // ---- drives on gate outputs: merge + conflict
             if (a.n_extra) {
                 for (size_t i = tid; i < (size_t)a.n_extra * wpc; i += nt) {
                     const uint32_t x = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
-                    if (w < a.stride) {
+                    if (w < a.stride && a.xrows[x] != 0xFFFFFFFFu) {
                         const size_t r = (size_t)a.xrows[x] * wpc + j;
                         const u64 dv = a.xval[(size_t)x * a.stride + w], dm = a.xvld[(size_t)x * a.stride + w];
                         const u64 c = (dv | dm) & (BV[r] | BM[r]);
@@ -790,6 +890,9 @@ Engine::~Engine() {
         cudaFree(d_wide_in_);
         cudaFree(d_wide_kind_);
         cudaFree(d_wide_nsel_);
+        cudaFree(d_res_off_);
+        cudaFree(d_res_in_);
+        cudaFree(d_res_xslot_);
         cudaFree(d_flags_);
         cudaFree(d_max_apps_);
         if (h_flags_) cudaFreeHost(h_flags_);
@@ -852,6 +955,9 @@ void Engine::free_store() {
     extra_slot_.clear();
     extra_rows_.clear();
     extra_cap_ = 0;
+    n_plain_extra_ = 0;
+    std::fill(res_xslot_.begin(), res_xslot_.end(), -1);
+    res_xslot_dirty_ = true;
     store_bytes_ = 0;
 }
 
@@ -928,6 +1034,11 @@ int Engine::ensure_device() {
     if ((rc = upload(&d_wide_in_, net_.wide_in))) return rc;
     if ((rc = upload(&d_wide_kind_, net_.wide_kind))) return rc;
     if ((rc = upload(&d_wide_nsel_, net_.wide_nsel))) return rc;
+    if ((rc = upload(&d_res_off_, net_.res_off))) return rc;
+    if ((rc = upload(&d_res_in_, net_.res_in))) return rc;
+    res_xslot_.assign(net_.n_res(), -1);
+    if ((rc = upload(&d_res_xslot_, res_xslot_))) return rc;
+    res_xslot_dirty_ = false;
     CU_TRY(cudaMalloc((void **)&d_flags_, 8 * sizeof(RunFlags)));
     CU_TRY(cudaMemset(d_flags_, 0, 8 * sizeof(RunFlags)));
     CU_TRY(cudaMallocHost((void **)&h_flags_, 8 * sizeof(RunFlags)));
@@ -1130,11 +1241,31 @@ int Engine::drive_target(uint32_t bitnet, uint64_t **val, uint64_t **vld) {
             extra_cap_ = cap;
         }
         extra_slot_[bitnet] = slot;
-        extra_rows_.push_back(net_.row_of_bit[bitnet]);
+        const int32_t res = net_.res_of_bit[bitnet];
+        if (res >= 0) {  // tri-state net: the drive is an operand of its resolve, not a merge into a gate row
+            extra_rows_.push_back(0xFFFFFFFFu);
+            res_xslot_[res] = (int32_t)slot;
+            res_xslot_dirty_ = true;
+        } else {
+            extra_rows_.push_back(net_.row_of_bit[bitnet]);
+            n_plain_extra_++;
+        }
         extra_rows_dirty_ = true;
     }
     *val = xdrv_val_ + (size_t)slot * stride_;
     *vld = xdrv_vld_ + (size_t)slot * stride_;
+    return B2_OK;
+}
+
+int Engine::sync_extra_tables() {
+    if (extra_rows_dirty_ && !extra_rows_.empty()) {
+        CU_TRY(cudaMemcpyAsync(d_extra_rows_, extra_rows_.data(), extra_rows_.size() * 4, cudaMemcpyHostToDevice, ST));
+        extra_rows_dirty_ = false;
+    }
+    if (res_xslot_dirty_ && !res_xslot_.empty()) {
+        CU_TRY(cudaMemcpyAsync(d_res_xslot_, res_xslot_.data(), res_xslot_.size() * 4, cudaMemcpyHostToDevice, ST));
+        res_xslot_dirty_ = false;
+    }
     return B2_OK;
 }
 
@@ -1422,10 +1553,7 @@ int Engine::run_levelised(bool async) {
         h_flags_->any_live = h_flags_->any_conflict = h_flags_->any_unsettled = 0;
         return B2_RUN_OK;
     }
-    if (extra_rows_dirty_) {
-        CU_TRY(cudaMemcpyAsync(d_extra_rows_, extra_rows_.data(), extra_rows_.size() * 4, cudaMemcpyHostToDevice, ST));
-        extra_rows_dirty_ = false;
-    }
+    if ((rc0 = sync_extra_tables())) return rc0;
     CU_TRY(cudaMemsetAsync(d_conflict_, 0, (size_t)stride_ * 8, ST));
     k_clear_flags<<<1, 1, 0, ST>>>(d_flags_);
     LAUNCHED();
@@ -1450,11 +1578,10 @@ int Engine::run_jacobi(uint64_t max_steps) {
     // step_sim calls gsim allows after begin_sim: max_steps + 1 with its `steps > max_steps` check
     const uint64_t N = opt_budget_inclusive_ ? max_steps : (max_steps == UINT64_MAX ? UINT64_MAX : max_steps + 1);
     const uint64_t last = N >= UINT64_MAX - 2 ? UINT64_MAX : N + 2;  // the final, check-only application
-    const uint32_t n_extra = (uint32_t)extra_rows_.size();
-    if (n_extra && extra_rows_dirty_) {
-        CU_TRY(cudaMemcpyAsync(d_extra_rows_, extra_rows_.data(), (size_t)n_extra * 4, cudaMemcpyHostToDevice, ST));
-        extra_rows_dirty_ = false;
-    }
+    const uint32_t n_slots = (uint32_t)extra_rows_.size(), n_extra = n_plain_extra_, n_res = net_.n_res();
+    if ((rc = sync_extra_tables())) return rc;
+    const uint32_t res_base = net_.n_src + net_.n_fast() + net_.n_wide();
+    const uint32_t res_gb = n_res ? (n_res + sh.block.y - 1) / sh.block.y : 0;
     const uint32_t sgrid = (stride_ + 255) / 256;
     k_init_status<<<sgrid, 256, 0, ST>>>(d_changed_, d_conf_step_, d_live_, d_conflict_, d_unsettled_, d_flags_, stride_, n_lanes_, 0);
     LAUNCHED();
@@ -1476,7 +1603,13 @@ int Engine::run_jacobi(uint64_t max_steps) {
             LAUNCHED();
         }
         if (n_extra) {
-            k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_extra, xdrv_val_, xdrv_vld_, V, M, d_conf_step_, stride_, 1);
+            k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_slots, xdrv_val_, xdrv_vld_, V, M, d_conf_step_, stride_, 1);
+            LAUNCHED();
+        }
+        if (n_res) {
+            ResolveArgs ra{d_res_off_, d_res_in_, d_res_xslot_, xdrv_val_, xdrv_vld_, V, M, V, M, nullptr, d_conf_step_, nullptr,
+                           n_res, res_base, stride_, pairs, sh.pair_blocks, 1};
+            k_resolve<<<sh.pair_blocks * res_gb, sh.block, 0, ST>>>(ra);
             LAUNCHED();
         }
         cold_ = false;
@@ -1543,8 +1676,14 @@ int Engine::run_jacobi(uint64_t max_steps) {
             frontier_valid_ = true;
             chg_w_ ^= 1;
         }
+        if (n_res) {
+            ResolveArgs ra{d_res_off_, d_res_in_, d_res_xslot_, xdrv_val_, xdrv_vld_, AV, AM, BV, BM, d_changed_, d_conf_step_, chg_cur,
+                           n_res, res_base, stride_, pairs, sh.pair_blocks, 0};
+            k_resolve<<<sh.pair_blocks * res_gb, sh.block, 0, ST>>>(ra);
+            LAUNCHED();
+        }
         if (n_extra) {
-            k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_extra, xdrv_val_, xdrv_vld_, BV, BM, d_conf_step_, stride_, 0);
+            k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_slots, xdrv_val_, xdrv_vld_, BV, BM, d_conf_step_, stride_, 0);
             LAUNCHED();
         }
         // The lane bookkeeping of application k goes to flag slot k % kFlagSlots; the host reads it
@@ -1601,10 +1740,7 @@ int Engine::run_resident(uint64_t max_steps) {
     int rc;
     if ((rc = materialise_valid())) return rc;
     if ((rc = drives_begin())) return rc;
-    if (n_extra && extra_rows_dirty_) {
-        CU_TRY(cudaMemcpyAsync(d_extra_rows_, extra_rows_.data(), (size_t)n_extra * 4, cudaMemcpyHostToDevice, ST));
-        extra_rows_dirty_ = false;
-    }
+    if ((rc = sync_extra_tables())) return rc;
     if (!d_max_apps_) CU_TRY(cudaMalloc((void **)&d_max_apps_, 8));
     CU_TRY(cudaMemsetAsync(d_max_apps_, 0, 8, ST));
     k_clear_flags<<<1, 1, 0, ST>>>(d_flags_);
@@ -1613,6 +1749,7 @@ int Engine::run_resident(uint64_t max_steps) {
     a.fan0 = d_fan0_; a.fan1 = d_fan1_; a.fan2 = d_fan2_; a.kind2 = d_kind2_;
     a.woff = d_wide_off_; a.win = d_wide_in_; a.wkind = d_wide_kind_; a.wnsel = d_wide_nsel_;
     a.xrows = d_extra_rows_; a.xval = xdrv_val_; a.xvld = xdrv_vld_;
+    a.res_off = d_res_off_; a.res_in = d_res_in_; a.res_xslot = d_res_xslot_; a.n_res = net_.n_res();
     a.dval = drv_val_; a.dvld = drv_vld_;
     a.val = val_[cur_]; a.vld = vld_[cur_];
     a.conflict = d_conflict_; a.unsettled = d_unsettled_;

@@ -106,6 +106,13 @@ class Engine {
     uint64_t *xdrv_val_ = nullptr, *xdrv_vld_ = nullptr;
     uint32_t *d_extra_rows_ = nullptr;
     bool extra_rows_dirty_ = false;
+    uint32_t n_plain_extra_ = 0;  // slots on plain gate rows (merged by k_extra_drive); the others belong to tri-state nets
+    // tri-state nets: resolve tables on the device; entry -> slot of its external drive (or -1)
+    uint32_t *d_res_off_ = nullptr, *d_res_in_ = nullptr;
+    int32_t *d_res_xslot_ = nullptr;
+    std::vector<int32_t> res_xslot_;
+    bool res_xslot_dirty_ = false;
+    int sync_extra_tables();  // uploads d_extra_rows_ / d_res_xslot_ when they changed
 
     // per-lane status words [T]
     uint64_t *d_changed_ = nullptr, *d_conf_step_ = nullptr, *d_live_ = nullptr, *d_conflict_ = nullptr, *d_unsettled_ = nullptr;

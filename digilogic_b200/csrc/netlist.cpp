@@ -70,6 +70,15 @@ int Builder::add_mux(const uint32_t *in, size_t n, uint32_t select, uint32_t out
     return push(*this, K_MUX, in, n, select, output, cell);
 }
 
+// gsim SimulatorBuilder::add_buffer (tri-state; no call site in the reference — SURVEY.md 8f row f4)
+int Builder::add_buffer(uint32_t in, uint32_t enable, uint32_t output, uint32_t *cell) {
+    if (output >= width.size() || in >= width.size() || enable >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    if (width[in] != width[output]) return B2_ERR_WIRE_WIDTH_MISMATCH;
+    if (width[enable] != 1) return B2_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    const uint32_t both[2] = {in, enable};
+    return push(*this, K_BUF, both, 2, 0, output, cell);
+}
+
 // ---------------------------------------------------------------------------- compiler
 
 namespace {
@@ -115,7 +124,12 @@ void compile(const Builder &b, Compiled &c) {
                 g.nsel = (uint8_t)k;
                 for (uint32_t s = 0; s < k; s++) bin.push_back(c.bit_off[cp.select] + s);
             }
-            for (uint32_t i = 0; i < cp.n_inputs; i++) bin.push_back(c.bit_off[in[i]] + j);
+            if (cp.kind == K_BUF) {
+                bin.push_back(c.bit_off[in[0]] + j);  // data bit j
+                bin.push_back(c.bit_off[in[1]]);      // the one enable bit
+            } else {
+                for (uint32_t i = 0; i < cp.n_inputs; i++) bin.push_back(c.bit_off[in[i]] + j);
+            }
             g.n_in = (uint32_t)bin.size() - g.in_off;
             gates.push_back(g);
         }
@@ -124,11 +138,21 @@ void compile(const Builder &b, Compiled &c) {
 
     // ---- drivers
     const uint32_t NONE = 0xFFFFFFFFu;
-    std::vector<uint32_t> driver(nb, NONE);
+    // A net with a buffer among its drivers is a tri-state net: it may have any number of drivers and is
+    // resolved per step (k_resolve).  Two drivers that are never High-Z on one net conflict in every run.
+    std::vector<uint32_t> driver(nb, NONE), n_firm(nb, 0);
+    std::vector<uint8_t> tri(nb, 0);
     c.multi_driver = false;
+    c.has_tristate = false;
     for (uint32_t g = 0; g < G; g++) {
-        if (driver[gates[g].out] != NONE) c.multi_driver = true;
-        else driver[gates[g].out] = g;
+        const uint32_t bn = gates[g].out;
+        if (gates[g].kind == K_BUF) {
+            tri[bn] = 1;
+            c.has_tristate = true;
+        } else if (++n_firm[bn] > 1) {
+            c.multi_driver = true;
+        }
+        if (driver[bn] == NONE) driver[bn] = g;
     }
     c.bit_driven.assign(nb, 0);
     for (uint32_t i = 0; i < nb; i++) c.bit_driven[i] = driver[i] != NONE;
@@ -170,7 +194,7 @@ void compile(const Builder &b, Compiled &c) {
             if (--indeg[h2] == 0) queue.push_back(h2);
         }
     }
-    c.cyclic = queue.size() != G;
+    c.cyclic = queue.size() != G || c.has_tristate;
     c.depth = c.cyclic ? 0 : depth;
     if (c.cyclic)
         for (auto &g : gates) g.level = 1;  // one pseudo-level: unit-delay evaluation only
@@ -199,6 +223,26 @@ void compile(const Builder &b, Compiled &c) {
     for (uint32_t i = 0; i < nb; i++)
         if (driver[i] != NONE) c.row_of_bit[i] = gate_row[driver[i]];
     c.n_rows = c.n_src + G;
+    // tri-state nets: the wire lives in a resolved row behind the gate rows; its drivers keep their own rows
+    c.res_off.clear();
+    c.res_in.clear();
+    c.res_of_bit.assign(nb, -1);
+    if (c.has_tristate) {
+        std::vector<uint32_t> cnt((size_t)nb + 1, 0);
+        for (uint32_t g = 0; g < G; g++)
+            if (tri[gates[g].out]) cnt[gates[g].out]++;
+        c.res_off.push_back(0);
+        for (uint32_t i = 0; i < nb; i++)
+            if (tri[i]) {
+                c.res_of_bit[i] = (int32_t)c.res_off.size() - 1;
+                c.row_of_bit[i] = c.n_rows++;
+                c.res_off.push_back(c.res_off.back() + cnt[i]);
+            }
+        c.res_in.resize(c.res_off.back());
+        std::vector<uint32_t> fill(c.res_off.begin(), c.res_off.end() - 1);
+        for (uint32_t g = 0; g < G; g++)  // creation order, like gsim's driver lists
+            if (tri[gates[g].out]) c.res_in[fill[c.res_of_bit[gates[g].out]]++] = gate_row[g];
+    }
 
     // ---- SoA emission
     uint32_t n2 = 0;

@@ -11,7 +11,10 @@
 
 namespace b2 {
 
-enum Kind : uint8_t { K_AND = 0, K_OR = 1, K_XOR = 2, K_NAND = 3, K_NOR = 4, K_XNOR = 5, K_NOT = 6, K_MUX = 7 };
+enum Kind : uint8_t {
+    K_AND = 0, K_OR = 1, K_XOR = 2, K_NAND = 3, K_NOR = 4, K_XNOR = 5, K_NOT = 6, K_MUX = 7,
+    K_BUF = 8  // tri-state buffer: inputs = {data, enable}; the only component whose output can be High-Z
+};
 
 struct Component {
     uint8_t kind;
@@ -31,6 +34,7 @@ struct Builder {
     int add_gate(int kind, const uint32_t *in, size_t n, uint32_t output, uint32_t *cell);
     int add_not(uint32_t in, uint32_t output, uint32_t *cell);
     int add_mux(const uint32_t *in, size_t n, uint32_t select, uint32_t output, uint32_t *cell);
+    int add_buffer(uint32_t in, uint32_t enable, uint32_t output, uint32_t *cell);
 };
 
 // One level of the levelised order: one/two-input gates [g2_begin, g2_end), three-input gates
@@ -57,7 +61,16 @@ struct Compiled {
     std::vector<uint8_t> wide_kind, wide_nsel;
     std::vector<Level> levels;         // acyclic: one per level (1..depth); cyclic: a single entry
     uint32_t depth = 0;
-    bool cyclic = false, multi_driver = false;
+    // cyclic: unit-delay evaluation only — feedback, or tri-state nets (their conflicts can be transient,
+    // so the steps have to be walked exactly).  multi_driver: some net has two drivers that are never
+    // High-Z, so every run conflicts.
+    bool cyclic = false, multi_driver = false, has_tristate = false;
+    // Tri-state nets (every net with a buffer among its drivers): each driver keeps its own output row
+    // (the gate's implicit row) and the wire gets a resolved row  n_src + n_gates + r  computed by
+    // k_resolve from the driver rows res_in[res_off[r] .. res_off[r+1]) and the net's external drive.
+    std::vector<uint32_t> res_off, res_in;
+    std::vector<int32_t> res_of_bit;   // bit-net -> index of its resolved row entry, or -1
+    uint32_t n_res() const { return res_off.empty() ? 0 : (uint32_t)res_off.size() - 1; }
 
     uint32_t n_wires() const { return (uint32_t)width.size(); }
     uint32_t n_g2() const { return n_two; }

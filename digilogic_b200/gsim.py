@@ -171,6 +171,12 @@ class SimulatorBuilder:
         _check(self._lib.b2_add_mux(self._h, arr, len(inputs), select, output, C.byref(cell)), "add_multiplexer")
         return cell.value
 
+    def add_buffer(self, input, enable, output):
+        """gsim ``SimulatorBuilder::add_buffer``: tri-state buffer (no call site in the reference yet)."""
+        cell = C.c_uint32()
+        _check(self._lib.b2_add_buffer(self._h, input, enable, output, C.byref(cell)), "add_buffer")
+        return cell.value
+
     def add_gates2(self, kinds, in0, in1, out):
         """Bulk add of one/two-input gates (batch extension)."""
         kinds = np.ascontiguousarray(kinds, np.uint8)

@@ -88,6 +88,15 @@ int b2_add_not(b2_builder *b, uint32_t input, uint32_t output, uint32_t *out_cel
 /* SimulatorBuilder::add_multiplexer(inputs, select, output)  (lib.rs:169-192): n = 2^k data
    inputs of the output's width, select of width k. */
 int b2_add_mux(b2_builder *b, const uint32_t *inputs, size_t n, uint32_t select, uint32_t output, uint32_t *out_cell);
+/* SimulatorBuilder::add_buffer(input, enable, output) — tri-state buffer.  gsim has it; the reference never
+   calls it (SimServer has no such method, crates/digilogic_netcode/src/server.rs:43-102; the Yosys
+   importer's `TriBuf` arm is todo!(), crates/digilogic_serde/src/yosys.rs:197) — SURVEY.md 8f row f4.
+   enable = 1: output = input with High-Z bits read as X; enable = 0: High-Z; enable Z/X: Undefined.
+   A net with a buffer among its drivers may have any number of drivers; it is resolved every step
+   (plane-wise OR, conflict where two drivers or the external drive are not High-Z) and such netlists
+   always run the unit-delay path.  Errors: InvalidWireId, WireWidthMismatch (input vs output),
+   WireWidthIncompatible (enable wider than one bit). */
+int b2_add_buffer(b2_builder *b, uint32_t input, uint32_t enable, uint32_t output, uint32_t *out_cell);
 /* Batch extension: n one- or two-input gates at once (kinds[i] in B2_AND..B2_NOT; in1 ignored
    for B2_NOT), validated exactly like the single calls; stops at the first error. */
 int b2_add_gates2(b2_builder *b, const uint8_t *kinds, const uint32_t *in0, const uint32_t *in1, const uint32_t *out, size_t n);

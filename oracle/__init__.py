@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libgsim_oracle.so")
 
-AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX = range(8)
+AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX, BUF = range(9)
 RUN_OK, RUN_MAX_STEPS, RUN_CONFLICT = 0, 1, 2
 ERR_NAMES = {
     0: "Ok", 1: "TooManyComponents", 2: "InvalidWireId", 3: "WireWidthMismatch",
@@ -56,6 +56,8 @@ def lib():
             "go_add_gate": (C.c_int, [vp, C.c_int, pu32, u32, u32, pu32]),
             "go_add_not": (C.c_int, [vp, u32, u32, pu32]),
             "go_add_mux": (C.c_int, [vp, pu32, u32, u32, u32, pu32]),
+            "go_add_buffer": (C.c_int, [vp, u32, u32, u32, pu32]),
+            "go_set_buffer_z_passthrough": (None, [C.c_int]),
             "go_add_gates2": (C.c_int, [vp, vp, vp, vp, vp, u32]),
             "go_build": (vp, [vp]),
             "go_sim_free": (None, [vp]),
@@ -163,6 +165,13 @@ class Builder:
         arr = (C.c_uint32 * len(inputs))(*inputs)
         cell = C.c_uint32()
         rc = lib().go_add_mux(self._h, arr, len(inputs), select, output, C.byref(cell))
+        if rc:
+            raise OracleError(rc)
+        return cell.value
+
+    def add_buffer(self, input, enable, output):
+        cell = C.c_uint32()
+        rc = lib().go_add_buffer(self._h, input, enable, output, C.byref(cell))
         if rc:
             raise OracleError(rc)
         return cell.value

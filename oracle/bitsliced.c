@@ -18,6 +18,11 @@
  *   k = 1..N+2 (N = max_steps+1; a cold start spends k = 1 on W_1 = D); the
  *   lane is Ok iff some k <= N+2 has W_k == W_{k-1}, else MaxStepsReached with
  *   state W_{N+1}; a driver conflict while computing W_k, k <= N+1, is Err.
+ *   Nets with several drivers (tri-state buffers): gsim's two stop checks — "no wire changed" and "no
+ *   component output changed" — no longer coincide (two drivers can swap roles and leave the wire as it
+ *   was), so the component outputs O_k = F(W_{k-1}) are kept too and "changed" is W_k != W_{k-1} or
+ *   O_k != O_{k-1}.  The chain  no output change at k  =>  no wire change at k  =>  no output change at
+ *   k+1  makes "nothing changed at some k <= N+2" equal to gsim's last check (outputs, after step N).
  */
 #include "gsim_oracle.h"
 #include <stdlib.h>
@@ -31,6 +36,8 @@ typedef struct {
     uint64_t *dv, *dm;      /* drive planes  [wire][words] */
     uint64_t *av, *am;      /* state A       */
     uint64_t *bv, *bm;      /* state B (scratch) */
+    uint64_t *ov, *om;      /* component outputs O = F(W) of the previous application [comp][words] */
+    int multi;              /* some wire has two or more drivers */
     int cold;
     int topo;               /* component order is topological and single-driver: DAG fast check allowed */
     uint64_t applications;  /* G applications performed by the last run */
@@ -81,6 +88,8 @@ bs_sim *bs_new(const go_builder *b, uint32_t n_lanes) {
     s->dv = (uint64_t *)calloc(n, 8); s->dm = (uint64_t *)calloc(n, 8);
     s->av = (uint64_t *)calloc(n, 8); s->am = (uint64_t *)calloc(n, 8);
     s->bv = (uint64_t *)calloc(n, 8); s->bm = (uint64_t *)calloc(n, 8);
+    size_t nc = (size_t)(C ? C : 1) * (s->words ? s->words : 1);
+    s->ov = (uint64_t *)calloc(nc, 8); s->om = (uint64_t *)calloc(nc, 8);
     s->cold = 1;
     /* topological + single-driver check */
     s->topo = 1;
@@ -88,12 +97,13 @@ bs_sim *bs_new(const go_builder *b, uint32_t n_lanes) {
     for (uint32_t w = 0; w < W; w++) {
         uint32_t nd = s->drivers_off[w + 1] - s->drivers_off[w];
         if (nd == 0) ready[w] = 1;
-        if (nd > 1) s->topo = 0;
+        if (nd > 1) { s->topo = 0; s->multi = 1; }
     }
     for (uint32_t c = 0; c < C && s->topo; c++) {
         const comp_t *cp = &s->comps[c];
         for (uint32_t i = 0; i < cp->n_inputs; i++) if (!ready[s->inputs[cp->in_off + i]]) s->topo = 0;
         if (cp->kind == GO_MUX && !ready[cp->select]) s->topo = 0;
+        if (cp->kind == GO_BUF) s->topo = 0;  /* transient conflicts / Z outputs: unit-delay model only */
         ready[cp->output] = 1;
     }
     free(ready);
@@ -103,7 +113,7 @@ bs_sim *bs_new(const go_builder *b, uint32_t n_lanes) {
 void bs_free(bs_sim *s) {
     if (!s) return;
     free(s->comps); free(s->inputs); free(s->drivers_off); free(s->drivers);
-    free(s->dv); free(s->dm); free(s->av); free(s->am); free(s->bv); free(s->bm); free(s);
+    free(s->dv); free(s->dm); free(s->av); free(s->am); free(s->bv); free(s->bm); free(s->ov); free(s->om); free(s);
 }
 
 int bs_is_topological(const bs_sim *s) { return s->topo; }
@@ -142,6 +152,13 @@ static inline void eval_comp(const bs_sim *s, const comp_t *cp, const uint64_t *
     } else if (cp->kind == GO_NOT) {
         uint64_t a = wv[(size_t)in[0] * T + k]; m = wm[(size_t)in[0] * T + k];
         v = ~a | ~m;
+    } else if (cp->kind == GO_BUF) {
+        /* enable 1: the input, High-Z read as X; enable 0: High-Z (0,0); enable Z/X: X (1,0) */
+        uint64_t a = wv[(size_t)in[0] * T + k], am = wm[(size_t)in[0] * T + k];
+        uint64_t ev = wv[(size_t)in[1] * T + k], em = wm[(size_t)in[1] * T + k];
+        uint64_t en1 = ev & em;
+        m = en1 & am;
+        v = (en1 & (a | ~am)) | ~em;
     } else {
         v = wv[(size_t)in[0] * T + k]; m = wm[(size_t)in[0] * T + k];
         for (uint32_t i = 1; i < cp->n_inputs; i++) {
@@ -166,9 +183,15 @@ static uint64_t apply_word(bs_sim *s, uint32_t k, uint64_t *conflict) {
         uint64_t rv = s->dv[idx], rm = s->dm[idx];
         for (uint32_t d = s->drivers_off[w]; d < s->drivers_off[w + 1]; d++) {
             uint64_t ov, om;
-            eval_comp(s, &s->comps[s->drivers[d]], s->av, s->am, k, &ov, &om);
+            const uint32_t c = s->drivers[d];
+            eval_comp(s, &s->comps[c], s->av, s->am, k, &ov, &om);
             conf |= (rv | rm) & (ov | om);
             rv |= ov; rm |= om;
+            if (s->multi) { /* output-change check (differs from the wire check only with several drivers) */
+                size_t oi = (size_t)c * T + k;
+                changed |= (ov ^ s->ov[oi]) | (om ^ s->om[oi]);
+                s->ov[oi] = ov; s->om[oi] = om;
+            }
         }
         changed |= (rv ^ s->av[idx]) | (rm ^ s->am[idx]);
         s->bv[idx] = rv; s->bm[idx] = rm;

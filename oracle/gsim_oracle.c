@@ -39,7 +39,7 @@
 
 #include "gsim_oracle.h"
 
-static go_config_t g_cfg = {0, 0, 0, 0};
+static go_config_t g_cfg = {0, 0, 0, 0, 0};
 
 void go_set_config(int steps_check_ge, int conflict_needs_disagree, int mux_z_passthrough, int initial_undefined) {
     g_cfg.steps_check_ge = steps_check_ge;
@@ -47,6 +47,7 @@ void go_set_config(int steps_check_ge, int conflict_needs_disagree, int mux_z_pa
     g_cfg.mux_z_passthrough = mux_z_passthrough;
     g_cfg.initial_undefined = initial_undefined;
 }
+void go_set_buffer_z_passthrough(int on) { g_cfg.buffer_z_passthrough = on; }
 
 /* ------------------------------------------------------------------ builder */
 
@@ -125,6 +126,17 @@ int go_add_mux(go_builder *b, const uint32_t *inputs, uint32_t n, uint32_t selec
     if (b->width[select] != k) return GO_ERR_WIRE_WIDTH_INCOMPATIBLE;
     for (uint32_t i = 0; i < n; i++) if (b->width[inputs[i]] != b->width[output]) return GO_ERR_WIRE_WIDTH_MISMATCH;
     return push_comp(b, GO_MUX, inputs, n, select, output, cell);
+}
+
+/* add_buffer(input, enable, output): tri-state buffer (gsim SimulatorBuilder::add_buffer; no call site
+   in the reference — SURVEY.md 8f row f4).  Validation as for the other components of A.2: data width
+   must equal the output width (WireWidthMismatch), the enable is one bit (WireWidthIncompatible). */
+int go_add_buffer(go_builder *b, uint32_t input, uint32_t enable, uint32_t output, uint32_t *cell) {
+    if (output >= b->n_wires || input >= b->n_wires || enable >= b->n_wires) return GO_ERR_INVALID_WIRE_ID;
+    if (b->width[input] != b->width[output]) return GO_ERR_WIRE_WIDTH_MISMATCH;
+    if (b->width[enable] != 1) return GO_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    uint32_t in[2] = {input, enable};
+    return push_comp(b, GO_BUF, in, 2, 0, output, cell);
 }
 
 /* Bulk 2-input gate add used by the large generators (same validation per gate). */
@@ -317,6 +329,15 @@ static int eval_component(go_sim *s, uint32_t c) {
     } else if (cp->kind == GO_NOT) {
         const atom_t *a = s->state + s->atom_off[in[0]];
         for (uint32_t i = 0; i < na; i++) res[i] = op_not(a[i]);
+    } else if (cp->kind == GO_BUF) {
+        /* enable = 1: the input (High-Z bits read X); enable = 0: High-Z; enable Z/X: Undefined */
+        const atom_t *a = s->state + s->atom_off[in[0]];
+        const atom_t en = s->state[s->atom_off[in[1]]];
+        for (uint32_t i = 0; i < na; i++) {
+            if (!(en.valid & 1)) { res[i].state = 0xFFFFFFFFu; res[i].valid = 0; }
+            else if (!(en.state & 1)) { res[i].state = 0; res[i].valid = 0; }
+            else { res[i] = a[i]; if (!g_cfg.buffer_z_passthrough) res[i].state |= ~a[i].valid; }
+        }
     } else {
         const atom_t *a = s->state + s->atom_off[in[0]];
         for (uint32_t i = 0; i < na; i++) res[i] = a[i];

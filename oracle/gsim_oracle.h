@@ -7,7 +7,8 @@
 
 typedef struct { uint32_t state, valid; } atom_t;
 
-enum { GO_AND = 0, GO_OR = 1, GO_XOR = 2, GO_NAND = 3, GO_NOR = 4, GO_XNOR = 5, GO_NOT = 6, GO_MUX = 7 };
+enum { GO_AND = 0, GO_OR = 1, GO_XOR = 2, GO_NAND = 3, GO_NOR = 4, GO_XNOR = 5, GO_NOT = 6, GO_MUX = 7,
+       GO_BUF = 8 /* tri-state buffer: inputs[0] = data, inputs[1] = 1-bit enable */ };
 
 /* AddComponentError ordinals, names pinned by crates/digilogic_gsim/src/lib.rs:55-66 */
 enum {
@@ -30,6 +31,7 @@ typedef struct {
     int conflict_needs_disagree; /* A.6-2: 0 => both non-Z conflicts (default) */
     int mux_z_passthrough;     /* A.6-4: 0 => Z on selected input reads X (default) */
     int initial_undefined;     /* A.6-5: 0 => High-Z initial state (default) */
+    int buffer_z_passthrough;  /* A.6-6: 0 => an enabled buffer passes a High-Z input bit on as X (default), 1 => as Z */
 } go_config_t;
 
 typedef struct {

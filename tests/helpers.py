@@ -2,7 +2,7 @@
 engine's builder (both expose the gsim SimulatorBuilder method names)."""
 import numpy as np
 
-AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX = range(8)
+AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX, BUF = range(9)
 ALL1 = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
@@ -31,6 +31,9 @@ class Netlist:
     def add_multiplexer(self, inputs, select, output):
         self.ops.append((MUX, list(inputs), select, output))
 
+    def add_buffer(self, input, enable, output):
+        self.ops.append((BUF, [input, enable], None, output))
+
     @property
     def n_wires(self):
         return len(self.widths)
@@ -38,7 +41,7 @@ class Netlist:
     def replay(self, builder):
         for w in self.widths:
             builder.add_wire(w)
-        simple = all(k != MUX and len(i) <= 2 for k, i, _, _ in self.ops)
+        simple = all(k not in (MUX, BUF) and len(i) <= 2 for k, i, _, _ in self.ops)
         if simple and len(self.ops) > 64:
             kinds = np.array([k for k, _, _, _ in self.ops], np.uint8)
             in0 = np.array([i[0] for _, i, _, _ in self.ops], np.uint32)
@@ -51,6 +54,8 @@ class Netlist:
                 builder.add_multiplexer(inputs, select, output)
             elif kind == NOT:
                 builder.add_not_gate(inputs[0], output)
+            elif kind == BUF:
+                builder.add_buffer(inputs[0], inputs[1], output)
             else:
                 builder.add_gate(kind, inputs, output)
         return builder
@@ -74,6 +79,63 @@ def random_netlist(rng, n_in, n_gates, cyclic=False, wide=False, mux=False):
             n = int(rng.integers(3, 6)) if (wide and r < 0.3) else 2
             nl.add_gate(kind, [int(x) for x in rng.integers(0, hi, n)], first_g + g)
     return nl, first_in
+
+
+def random_bus_netlist(rng, n_in, n_gates, n_bus, cyclic=True):
+    """Random netlist with tri-state buffers: `n_bus` wires are each driven by two or three buffers
+    (real multi-driver nets) whose enables are dedicated input wires (see `bus_enable_drives`), a few
+    more buffers drive ordinary wires, the rest are plain gates; gates may read the buses when `cyclic`.
+    Returns (netlist, first_in, enable_groups)."""
+    nl = Netlist()
+    first_in = nl.add_wires(n_in)
+    first_g = nl.add_wires(n_gates)
+    first_bus = nl.add_wires(n_bus)
+    n_w = n_in + n_gates + n_bus
+
+    def pick(g):
+        return int(rng.integers(0, n_w)) if cyclic else int(rng.integers(0, n_in + g))
+
+    for g in range(n_gates):
+        r = rng.random()
+        if r < 0.15:
+            nl.add_buffer(pick(g), pick(g), first_g + g)
+            continue
+        kind = int(rng.integers(0, 7))
+        if kind == NOT:
+            nl.add_not_gate(pick(g), first_g + g)
+        else:
+            nl.add_gate(kind, [pick(g), pick(g)], first_g + g)
+    groups = []
+    for b in range(n_bus):
+        k = int(rng.integers(2, 4))
+        en = [nl.add_wire() for _ in range(k)]
+        for e in en:
+            nl.add_buffer(pick(n_gates), e, first_bus + b)
+        groups.append(en)
+    return nl, first_in, groups
+
+
+def bus_enable_drives(rng, group, words, p_bad=0.03):
+    """(value, valid) planes for the enables of one bus: per lane one driver on or none, except a
+    fraction `p_bad` of lanes where two are on (conflict) or an enable is X."""
+    k = len(group)
+    lanes = words * 64
+    choice = rng.integers(0, k + 1, lanes)  # k = nobody drives
+    val = np.zeros((k, lanes), np.uint8)
+    vld = np.ones((k, lanes), np.uint8)
+    for j in range(k):
+        val[j] = choice == j
+    bad = rng.random(lanes) < p_bad
+    both = bad & (rng.random(lanes) < 0.5)
+    val[0][both] = 1
+    val[1][both] = 1
+    unk = bad & ~both
+    vld[int(rng.integers(0, k))][unk] = 0
+
+    def pack(bits):
+        return np.packbits(bits.reshape(words, 64), axis=1, bitorder="little").view(np.uint64).reshape(words)
+
+    return [(pack(val[j]), pack(vld[j])) for j in range(k)]
 
 
 def random_drive(rng, words, four_state=True):

@@ -47,6 +47,9 @@ def test_builder_validation_matches_gsim_variants():
         (lambda: b.add_multiplexer([w1, w1b, w1], w1, w1b), AddComponentError.InvalidInputCount),
         (lambda: b.add_multiplexer([w1, w1b], w4, w1b), AddComponentError.WireWidthIncompatible),
         (lambda: b.add_multiplexer([w1, w4], w1, w1b), AddComponentError.WireWidthMismatch),
+        (lambda: b.add_buffer(w1, w1b, 99), AddComponentError.InvalidWireId),
+        (lambda: b.add_buffer(w4, w1, w1b), AddComponentError.WireWidthMismatch),
+        (lambda: b.add_buffer(w4, w4, w4), AddComponentError.WireWidthIncompatible),
     ]:
         with pytest.raises(ComponentError) as e:
             fn()
