@@ -47,6 +47,7 @@ def multiplier(resident):
         state[0] ^= 1
         sim.set_wire_drive(int(gen.inputs[0]), LogicState(state[0], 1))
         assert sim.run_sim(10_000) == SimulationRunResult.Ok
+        sim.get_wire_state(int(gen.outputs[-1]))  # the read-back waits for the run (the levelised path returns early)
 
     for w in gen.inputs:
         sim.set_wire_drive(int(w), LogicState(1, 1))

@@ -569,20 +569,21 @@ __global__ void __launch_bounds__(256) k_levelised_status(uint64_t *conflict, ui
     if ((threadIdx.x & 31) == 0 && any_c) atomicOr(&flags->any_conflict, 1u);
 }
 
-struct Planes8 {
-    uint32_t p0[8], p1[8];
+// set_wire_drive, batched: every pending (bit-net, value bit, valid bit) is broadcast to all lanes of
+// its drive row.  One launch per flush, however many wires were driven since the last run.
+struct PendingBit {
+    uint64_t *val, *vld;  // drive row of the bit-net
+    uint32_t flags;       // bit 0 = plane 0 (value), bit 1 = plane 1 (valid)
+    uint32_t pad;
 };
 
-// set_wire_drive broadcast: bit j of the wire -> all lanes of drive row rows.row[j].
-__global__ void __launch_bounds__(256) k_broadcast_drive(uint64_t *const *row_val, uint64_t *const *row_vld, Planes8 p,
-                                                         uint32_t n_bits, uint32_t stride) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t j = blockIdx.y;
+__global__ void __launch_bounds__(256) k_broadcast_bits(const PendingBit *bits, uint32_t n_bits, uint32_t stride,
+                                                        uint32_t word_blocks) {
+    const uint32_t j = blockIdx.x / word_blocks, w = (blockIdx.x % word_blocks) * blockDim.x + threadIdx.x;
     if (w >= stride || j >= n_bits) return;
-    const uint64_t v = ((p.p0[j >> 5] >> (j & 31)) & 1) ? ~0ull : 0ull;
-    const uint64_t m = ((p.p1[j >> 5] >> (j & 31)) & 1) ? ~0ull : 0ull;
-    row_val[j][w] = v;
-    row_vld[j][w] = m;
+    const PendingBit b = bits[j];
+    b.val[w] = (b.flags & 1) ? ~0ull : 0ull;
+    b.vld[w] = (b.flags & 2) ? ~0ull : 0ull;
 }
 
 __global__ void __launch_bounds__(256) k_fill_stimulus(uint64_t *const *row_val, uint64_t *const *row_vld, uint32_t n,
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(256) k_pack_lane0(const uint32_t *rows, uint32
     for (uint32_t j = 0; j < 8; j++) {
         const uint32_t k = byte * 8 + j;
         if (k < n_bits) {
-            const size_t s = (size_t)rows[k] * stride;
+            const size_t s = (size_t)(rows ? rows[k] : k) * stride;
             b0 |= (uint32_t)(val[s] & 1) << j;
             b1 |= (uint32_t)(vld[s] & 1) << j;
         }
@@ -668,6 +669,12 @@ struct ResidentArgs {
     uint64_t n_lanes;
     uint64_t last;                    // index of the final, check-only application
     int cold;
+    // Acyclic single-driver netlist and a step budget that covers its depth: the fixed point is computed
+    // once, level by level, in place (the same rule as Engine::run_levelised), with a CTA barrier per
+    // level instead of a launch per level.
+    const Level *levels;
+    uint32_t n_levels;
+    int levelised;
 };
 
 __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g, const uint64_t *av, const uint64_t *am, uint32_t wpc,
@@ -710,12 +717,13 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
     __shared__ unsigned s_any;
 
     // ---- load: the current state, or the cold start W_1 = resolve(D, all outputs High-Z) = D
-    for (size_t i = tid; i < plane; i += nt) {
+    //      (a levelised pass recomputes every row: only the source rows are loaded, from their drives)
+    for (size_t i = tid; i < (a.levelised ? (size_t)a.n_src * wpc : plane); i += nt) {
         const uint32_t row = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
         u64 v = 0, m = 0;
         if (w < a.stride) {
             const size_t o = (size_t)row * a.stride + w;
-            if (!a.cold) {
+            if (!a.cold && !a.levelised) {
                 v = a.val[o];
                 m = a.vld[o];
             } else if (row < a.n_src) {
@@ -735,7 +743,52 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
     }
     __syncthreads();
     const uint32_t res_base = a.n_src + a.n_g2 + a.n_g3 + a.n_wide;
-    if (a.cold) {
+    if (a.levelised) {
+        for (uint32_t l = 0; l < a.n_levels; l++) {
+            const Level lv = a.levels[l];
+            const uint32_t n2 = lv.g2_end - lv.g2_begin, n3 = lv.g3_end - lv.g3_begin, nw = lv.wide_end - lv.wide_begin;
+            const size_t total = (size_t)(n2 + n3 + nw) * wpc;
+            for (size_t i = tid; i < total; i += nt) {
+                const uint32_t gi = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc);
+                u64 rv, rm;
+                uint32_t row;
+                if (gi < n2) {
+                    const uint32_t g = lv.g2_begin + gi;
+                    const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j;
+                    gate_word(a.kind2[g], AV[r0], AM[r0], AV[r1], AM[r1], rv, rm);
+                    row = a.n_src + g;
+                } else if (gi < n2 + n3) {
+                    const uint32_t g = lv.g3_begin + (gi - n2), kind = a.kind2[g], base = kind >= K_NAND ? kind - 3 : kind;
+                    const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j, r2 = (size_t)a.fan2[g] * wpc + j;
+                    gate_word(base, AV[r0], AM[r0], AV[r1], AM[r1], rv, rm);
+                    gate_word(base, rv, rm, AV[r2], AM[r2], rv, rm);
+                    if (kind >= K_NAND) rv = ~rv | ~rm;
+                    row = a.n_src + g;
+                } else {
+                    const uint32_t g = lv.wide_begin + (gi - n2 - n3);
+                    wide_gate_word(a, g, AV, AM, wpc, j, rv, rm);
+                    row = a.n_src + a.n_g2 + a.n_g3 + g;
+                }
+                AV[(size_t)row * wpc + j] = rv;  // in place: gates of one level never read each other
+                AM[(size_t)row * wpc + j] = rm;
+            }
+            __syncthreads();
+        }
+        // drives on gate outputs: a gate output is never High-Z, so the lane conflicts where the drive is not High-Z
+        for (size_t i = tid; i < (size_t)a.n_extra * wpc; i += nt) {
+            const uint32_t x = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
+            if (w < a.stride && a.xrows[x] != 0xFFFFFFFFu) {
+                const size_t r = (size_t)a.xrows[x] * wpc + j;
+                const u64 dv = a.xval[(size_t)x * a.stride + w], dm = a.xvld[(size_t)x * a.stride + w];
+                const u64 c = (dv | dm) & (AV[r] | AM[r]);
+                AV[r] |= dv;
+                AM[r] |= dm;
+                if (c) atomicOr((unsigned long long *)&s_conflict[j], c);
+            }
+        }
+        __syncthreads();
+        if (tid < wpc) s_conflict[tid] &= s_live[tid];  // lanes in use
+    } else if (a.cold) {
         for (size_t i = tid; i < (size_t)a.n_extra * wpc; i += nt) {
             const uint32_t x = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
             if (w < a.stride && a.xrows[x] != 0xFFFFFFFFu) {
@@ -758,7 +811,9 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
     unsigned long long apps = 0;
     const size_t n_items = (size_t)(a.n_src + a.n_g2 + a.n_g3 + a.n_wide) * wpc;
     // (a cold start without components is already final: W_1 = D; a warm one still takes the new drives)
-    if (a.n_g2 + a.n_g3 + a.n_wide > 0 || !a.cold) {
+    if (a.levelised) {
+        apps = 1;
+    } else if (a.n_g2 + a.n_g3 + a.n_wide > 0 || !a.cold) {
         for (;;) {
             k++;
             apps++;
@@ -893,7 +948,9 @@ Engine::~Engine() {
         cudaFree(d_res_off_);
         cudaFree(d_res_in_);
         cudaFree(d_res_xslot_);
+        cudaFree(d_levels_);
         cudaFree(d_flags_);
+        cudaFree(d_pend_);
         cudaFree(d_max_apps_);
         if (h_flags_) cudaFreeHost(h_flags_);
         if (own_stream_ && stream_) cudaStreamDestroy(ST);
@@ -956,6 +1013,8 @@ void Engine::free_store() {
     extra_rows_.clear();
     extra_cap_ = 0;
     n_plain_extra_ = 0;
+    snap_valid_ = false;
+    pending_.clear();
     std::fill(res_xslot_.begin(), res_xslot_.end(), -1);
     res_xslot_dirty_ = true;
     store_bytes_ = 0;
@@ -1038,6 +1097,7 @@ int Engine::ensure_device() {
     if ((rc = upload(&d_res_in_, net_.res_in))) return rc;
     res_xslot_.assign(net_.n_res(), -1);
     if ((rc = upload(&d_res_xslot_, res_xslot_))) return rc;
+    if ((rc = upload(&d_levels_, net_.levels))) return rc;
     res_xslot_dirty_ = false;
     CU_TRY(cudaMalloc((void **)&d_flags_, 8 * sizeof(RunFlags)));
     CU_TRY(cudaMemset(d_flags_, 0, 8 * sizeof(RunFlags)));
@@ -1271,35 +1331,101 @@ int Engine::sync_extra_tables() {
 
 // ---------------------------------------------------------------------------- Engine: drives
 
+// gsim's set_wire_drive is a plain memory write and the reference calls it once per input per eval
+// (crates/digilogic_netcode/src/server.rs:447-451), so the call itself does no CUDA work: drives are
+// queued on the host and reach the drive store in one upload + one launch before the next run (or before
+// any other call that writes drives, to keep the call order).
 int Engine::set_wire_drive(uint32_t wire, const uint32_t *p0, const uint32_t *p1, size_t words) {
     if (wire >= net_.n_wires()) return B2_ERR_INVALID_WIRE_ID;
     if (words && (!p0 || !p1)) return B2_ERR_NULL;
     int rc = ensure_lanes();
     if (rc) return rc;
-    const uint32_t width = net_.width[wire];
-    Planes8 p;
+    PendingDrive d;
+    d.wire = wire;
     for (uint32_t i = 0; i < 8; i++) {
-        p.p0[i] = i < words ? p0[i] : 0;
-        p.p1[i] = i < words ? p1[i] : 0;
+        d.p0[i] = i < words ? p0[i] : 0;
+        d.p1[i] = i < words ? p1[i] : 0;
     }
-    // row pointer tables for the bits of this wire (two passes: the first may grow the extra store)
-    if ((rc = ensure_rows_buffer(width))) return rc;
-    rows_key_ = ptrs_key_ = 0;
-    CU_TRY(cudaStreamSynchronize(CIN));  // a scatter kernel may still be reading the pointer tables
-    std::vector<uint64_t *> tv(width), tm(width);
-    for (int pass = 0; pass < 2; pass++)
-        for (uint32_t j = 0; j < width; j++)
-            if ((rc = drive_target(net_.bit_off[wire] + j, &tv[j], &tm[j]))) return rc;
-    const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
-    uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
-    CU_TRY(cudaMemcpyAsync(d_tv, tv.data(), (size_t)width * 8, cudaMemcpyHostToDevice, ST));
-    CU_TRY(cudaMemcpyAsync(d_tm, tm.data(), (size_t)width * 8, cudaMemcpyHostToDevice, ST));
+    pending_.push_back(d);
+    if (pending_.size() >= (1u << 16)) return flush_pending_drives();
+    return B2_OK;
+}
+
+int Engine::flush_pending_drives() {
+    if (pending_.empty()) return B2_OK;
+    int rc;
+    // one launch writes all queued bits concurrently, so a wire driven twice keeps only its last drive
+    if (pending_.size() > 1) {
+        std::unordered_map<uint32_t, size_t> last;
+        for (size_t i = 0; i < pending_.size(); i++) last[pending_[i].wire] = i;
+        if (last.size() != pending_.size()) {
+            size_t k = 0;
+            for (size_t i = 0; i < pending_.size(); i++)
+                if (last[pending_[i].wire] == i) pending_[k++] = pending_[i];
+            pending_.resize(k);
+        }
+    }
+    size_t n_bits = 0;
+    for (const PendingDrive &d : pending_) n_bits += net_.width[d.wire];
+    // two passes: the first may grow the extra store (drives on gate-driven nets) and move earlier rows
+    std::vector<PendingBit> bits(n_bits);
+    for (int pass = 0; pass < 2; pass++) {
+        size_t k = 0;
+        for (const PendingDrive &d : pending_)
+            for (uint32_t j = 0; j < net_.width[d.wire]; j++, k++) {
+                PendingBit &b = bits[k];
+                if ((rc = drive_target(net_.bit_off[d.wire] + j, &b.val, &b.vld))) return rc;
+                b.flags = ((d.p0[j >> 5] >> (j & 31)) & 1) | (((d.p1[j >> 5] >> (j & 31)) & 1) << 1);
+                b.pad = 0;
+            }
+    }
+    pending_.clear();
+    if (pend_cap_ < n_bits) {
+        CU_TRY(cudaStreamSynchronize(ST));
+        cudaFree(d_pend_);
+        d_pend_ = nullptr;
+        pend_cap_ = 0;
+        const size_t cap = std::max<size_t>(n_bits, 256);
+        CU_TRY(cudaMalloc((void **)&d_pend_, cap * sizeof(PendingBit)));
+        pend_cap_ = cap;
+    }
+    // pageable source: the call returns once the data is staged, so `bits` may go out of scope
+    CU_TRY(cudaMemcpyAsync(d_pend_, bits.data(), n_bits * sizeof(PendingBit), cudaMemcpyHostToDevice, ST));
     if ((rc = drives_begin())) return rc;
-    dim3 grid((stride_ + 255) / 256, width);
-    k_broadcast_drive<<<grid, 256, 0, ST>>>(d_tv, d_tm, p, width, stride_);
+    const uint32_t word_blocks = (stride_ + 255) / 256;
+    for (size_t done = 0; done < n_bits;) {  // grid.x is bounded; one launch covers any realistic flush
+        const size_t chunk = std::min<size_t>(n_bits - done, 0x7FFFFFFFull / word_blocks);
+        k_broadcast_bits<<<(uint32_t)(chunk * word_blocks), 256, 0, ST>>>((const PendingBit *)d_pend_ + done, (uint32_t)chunk, stride_,
+                                                                       word_blocks);
+        LAUNCHED();
+        done += chunk;
+    }
+    return drives_end();
+}
+
+// Lane 0 of every row, bit-packed, on the host: what get_wire_state serves from.  The reference reads
+// every net back after each eval, one call per net (crates/digilogic_netcode/src/server.rs:375-383); with
+// the snapshot that is one kernel and one copy per eval instead of a device round trip per net.
+int Engine::refresh_snapshot() {
+    if (snap_valid_) return B2_OK;
+    int rc = materialise_valid();
+    if (rc) return rc;
+    const size_t n_bytes = (size_t)net_.n_rows / 8 + 1;
+    if (pack_cap_ < 2 * n_bytes) {
+        CU_TRY(cudaStreamSynchronize(ST));
+        cudaFree(d_pack_);
+        d_pack_ = nullptr;
+        pack_cap_ = 0;
+        CU_TRY(cudaMalloc((void **)&d_pack_, 2 * n_bytes + 64));
+        pack_cap_ = 2 * n_bytes + 64;
+    }
+    snap_.resize(2 * n_bytes);
+    k_pack_lane0<<<(uint32_t)((n_bytes + 255) / 256), 256, 0, ST>>>(nullptr, net_.n_rows, val_[cur_], vld_[cur_], stride_, d_pack_,
+                                                                    d_pack_ + n_bytes, (uint32_t)n_bytes);
     LAUNCHED();
-    if ((rc = drives_end())) return rc;
-    CU_TRY(cudaStreamSynchronize(ST));  // tv/tm are stack-lifetime host buffers
+    CU_TRY(cudaMemcpyAsync(snap_.data(), d_pack_, 2 * n_bytes, cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaStreamSynchronize(ST));
+    snap_valid_ = true;
     return B2_OK;
 }
 
@@ -1310,6 +1436,7 @@ int Engine::set_wire_drive_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint3
     int rc = ensure_lanes();
     if (rc) return rc;
     if ((uint64_t)w0 + nw > T_) return B2_ERR_RANGE;
+    if ((rc = flush_pending_drives())) return rc;
     uint64_t *dv, *dm;
     if ((rc = drive_target(net_.bit_off[wire] + bit, &dv, &dm))) return rc;
     if ((rc = drives_begin())) return rc;
@@ -1368,6 +1495,7 @@ int Engine::set_drives_lanes(const uint32_t *wires, uint32_t n, const uint64_t *
     if (rc) return rc;
     if (n == 0) return B2_OK;
     if (src_stride < T_) return B2_ERR_RANGE;
+    if ((rc = flush_pending_drives())) return rc;
     if ((rc = upload_rows(wires, n, true))) return rc;
     if ((rc = ensure_stage(false, (size_t)n * T_))) return rc;
     // copy-in stream: wait until the main stream has consumed the previous drives (early in the
@@ -1392,6 +1520,7 @@ int Engine::fill_stimulus(const uint32_t *wires, uint32_t n, uint64_t seed, uint
     int rc = ensure_lanes();
     if (rc) return rc;
     if (n == 0) return B2_OK;
+    if ((rc = flush_pending_drives())) return rc;
     if ((rc = upload_rows(wires, n, true))) return rc;
     const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
     uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
@@ -1731,7 +1860,7 @@ uint32_t Engine::resident_wpc() const {
     return (uint32_t)(wpc ? wpc : 1);
 }
 
-int Engine::run_resident(uint64_t max_steps) {
+int Engine::run_resident(uint64_t max_steps, bool levelised) {
     const uint32_t wpc = resident_wpc();
     // step_sim calls gsim allows after begin_sim: max_steps + 1 with its `steps > max_steps` check
     const uint64_t N = opt_budget_inclusive_ ? max_steps : (max_steps == UINT64_MAX ? UINT64_MAX : max_steps + 1);
@@ -1760,6 +1889,9 @@ int Engine::run_resident(uint64_t max_steps) {
     a.n_lanes = n_lanes_;
     a.last = last;
     a.cold = cold_ ? 1 : 0;
+    a.levels = d_levels_;
+    a.n_levels = (uint32_t)net_.levels.size();
+    a.levelised = levelised ? 1 : 0;
     const size_t smem = ((size_t)net_.n_rows * wpc * 4 + (size_t)wpc * 5) * 8;
     if (!resident_attr_set_) {
         CU_TRY(cudaFuncSetAttribute(k_resident_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kResidentSmem + 4096)));
@@ -1787,6 +1919,10 @@ int Engine::run_resident(uint64_t max_steps) {
 int Engine::run(uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled, bool async) {
     int rc = ensure_lanes();
     if (rc) return -rc;
+    if ((rc = flush_pending_drives())) return -rc;
+    snap_valid_ = false;
+    // acyclic, single-driver, and the step budget covers the depth: the unique fixed point, level by level
+    const bool dag_ok = !net_.cyclic && max_steps >= (uint64_t)net_.depth + 1;
     int result;
     if (net_.multi_driver) {
         // two gate outputs on one wire are never High-Z: every lane conflicts on its first step
@@ -1798,10 +1934,10 @@ int Engine::run(uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled, boo
         last_mode_ = 0;
         last_apps_ = 0;
         result = B2_RUN_CONFLICT;
-    } else if (!net_.cyclic && max_steps >= (uint64_t)net_.depth + 1 && !(stride_ <= 4 && resident_wpc() && use_resident_)) {
+    } else if (dag_ok && !(stride_ <= 4 && resident_wpc() && use_resident_)) {
         result = run_levelised(async && !conflict && !unsettled);
     } else if (use_resident_ && resident_wpc()) {
-        result = run_resident(max_steps);  // small netlist: the whole run_sim loop on chip
+        result = run_resident(max_steps, dag_ok);  // small netlist: the whole run_sim loop (or level sweep) on chip
     } else {
         result = run_jacobi(max_steps);
     }
@@ -1845,24 +1981,12 @@ int Engine::get_wire_state(uint32_t wire, uint32_t *p0, uint32_t *p1, size_t wor
     int rc = ensure_lanes();
     if (rc) return rc;
     for (uint32_t i = 0; i < need; i++) p0[i] = p1[i] = 0;
-    if ((rc = materialise_valid())) return rc;
-    if (width == 1) {
-        uint64_t v = 0, m = 0;
-        const size_t o = (size_t)net_.row_of_bit[net_.bit_off[wire]] * stride_;
-        CU_TRY(cudaMemcpyAsync(&v, val_[cur_] + o, 8, cudaMemcpyDeviceToHost, ST));
-        CU_TRY(cudaMemcpyAsync(&m, vld_[cur_] + o, 8, cudaMemcpyDeviceToHost, ST));
-        CU_TRY(cudaStreamSynchronize(ST));
-        p0[0] = (uint32_t)(v & 1);
-        p1[0] = (uint32_t)(m & 1);
-        return B2_OK;
-    }
-    // wide wire: pack lane 0 of its bit rows on the device
-    uint8_t b0[32] = {0}, b1[32] = {0};
-    uint64_t bits = 0;
-    if ((rc = pack_sim_state(&wire, 1, b0, b1, sizeof(b0) + 1, &bits))) return rc;
+    if ((rc = refresh_snapshot())) return rc;
+    const uint8_t *s0 = snap_.data(), *s1 = snap_.data() + snap_.size() / 2;
     for (uint32_t j = 0; j < width; j++) {
-        p0[j >> 5] |= (uint32_t)((b0[j >> 3] >> (j & 7)) & 1) << (j & 31);
-        p1[j >> 5] |= (uint32_t)((b1[j >> 3] >> (j & 7)) & 1) << (j & 31);
+        const uint32_t row = net_.row_of_bit[net_.bit_off[wire] + j];
+        p0[j >> 5] |= (uint32_t)((s0[row >> 3] >> (row & 7)) & 1) << (j & 31);
+        p1[j >> 5] |= (uint32_t)((s1[row >> 3] >> (row & 7)) & 1) << (j & 31);
     }
     return B2_OK;
 }

@@ -76,7 +76,7 @@ class Engine {
     int upload_rows(const uint32_t *wires, uint32_t n, bool drive_rows);
     int run_levelised(bool async);
     int run_jacobi(uint64_t max_steps);
-    int run_resident(uint64_t max_steps);
+    int run_resident(uint64_t max_steps, bool levelised);
     int materialise_valid();
     uint32_t resident_wpc() const;
 
@@ -110,6 +110,7 @@ class Engine {
     // tri-state nets: resolve tables on the device; entry -> slot of its external drive (or -1)
     uint32_t *d_res_off_ = nullptr, *d_res_in_ = nullptr;
     int32_t *d_res_xslot_ = nullptr;
+    Level *d_levels_ = nullptr;
     std::vector<int32_t> res_xslot_;
     bool res_xslot_dirty_ = false;
     int sync_extra_tables();  // uploads d_extra_rows_ / d_res_xslot_ when they changed
@@ -132,6 +133,17 @@ class Engine {
     uint64_t rows_key_ = 0, ptrs_key_ = 0;  // hashes of the cached wire lists (0 = none)
     uint8_t *d_pack_ = nullptr;
     size_t pack_cap_ = 0;
+    // set_wire_drive queue (flushed before the next run) and the lane-0 snapshot get_wire_state reads
+    struct PendingDrive {
+        uint32_t wire, p0[8], p1[8];
+    };
+    std::vector<PendingDrive> pending_;
+    void *d_pend_ = nullptr;
+    size_t pend_cap_ = 0;
+    std::vector<uint8_t> snap_;  // [2][n_rows / 8 + 1]: value bits, then valid bits
+    bool snap_valid_ = false;
+    int flush_pending_drives();
+    int refresh_snapshot();
 
     bool cold_ = true;
     // valid-plane elision: d_kv_[row] = 1 while the row's valid plane is all-ones and not stored

@@ -189,3 +189,44 @@ def test_step_budget_switch_moves_with_the_oracle(resident):
                 pass
         finally:
             oracle.lib().go_set_config(0, 0, 0, 0)
+
+
+def test_drive_queue_order_and_state_snapshot():
+    """set_wire_drive is queued on the host and get_wire_state is served from a lane-0 snapshot: the
+    call order across the different drive setters still decides the value, a drive is invisible until
+    the next run_sim (gsim: drives and states are separate), and the snapshot follows every run."""
+    b = SimulatorBuilder()
+    a, c, o, w8, n8 = b.add_wire(), b.add_wire(), b.add_wire(), b.add_wire(8), b.add_wire(8)
+    b.add_xor_gate([a, c], o)
+    b.add_not_gate(w8, n8)
+    sim = b.build()
+    sim.set_lanes(128)
+    one, zero = LogicState(1, 1), LogicState(0, 1)
+    ones = np.full(2, (1 << 64) - 1, np.uint64)
+    sim.set_wire_drive(a, one)
+    sim.set_wire_drive(c, zero)
+    sim.set_wire_drive(a, zero)                      # last call wins inside the queue
+    assert sim.get_wire_state(o) == LogicState(0, 0)  # nothing ran yet: still High-Z
+    assert sim.run_sim(10) == SimulationRunResult.Ok
+    assert sim.get_wire_state(o) == zero and sim.get_wire_state(a) == zero
+    sim.set_wire_drive(a, one)
+    assert sim.get_wire_state(a) == zero              # drive queued, state unchanged until the run
+    sim.set_wire_drive_lanes(a, np.zeros(2, np.uint64), ones)   # a later lane-wise drive overrides the queued one
+    assert sim.run_sim(10) == SimulationRunResult.Ok
+    assert sim.get_wire_state(o) == zero
+    sim.set_wire_drive_lanes(a, np.zeros(2, np.uint64), ones)
+    sim.set_wire_drive(a, one)                       # ... and a later queued drive overrides the lane-wise one
+    sim.set_wire_drive(w8, LogicState(0x5A, 0xFF))
+    assert sim.run_sim(10) == SimulationRunResult.Ok
+    assert sim.get_wire_state(o) == one
+    assert sim.get_wire_state(n8) == LogicState(0xA5, 0xFF)
+    v, m = sim.get_wire_lanes(o)
+    assert (v == ones).all() and (m == ones).all()   # the queued drive went to every lane
+    for k in range(40):                               # many evals: the snapshot is refreshed after each run
+        sim.set_wire_drive(c, LogicState(k & 1, 1))
+        assert sim.run_sim(10) == SimulationRunResult.Ok
+        assert sim.get_wire_state(o) == LogicState(1 ^ (k & 1), 1)
+    sim.set_wire_drive(a, one)
+    sim.set_lanes(64)                                 # cold again: queued drives are dropped with the store
+    assert sim.run_sim(10) == SimulationRunResult.Ok
+    assert sim.get_wire_state(a) == LogicState(0, 0)
