@@ -274,6 +274,117 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
     }
 }
 
+// ---- unit-delay frontier as a compacted work list (gsim's component_update_queue, at row
+// granularity).  k_frontier_scan: one thread per fast gate decides whether the gate has to be evaluated in
+// this application — a fan-in row or its own row changed in the previous one — and appends it to the list
+// of its class with one warp-aggregated atomic.  k_eval_list then evaluates exactly the listed gates with
+// a persistent grid, so an application in which little changes costs a few microseconds instead of a
+// sweep of CTAs over every gate.
+__global__ void __launch_bounds__(256) k_frontier_scan(const uint32_t *fan0, const uint32_t *fan1, const uint32_t *fan2, uint32_t n_g2,
+                                                       uint32_t n_fast, uint32_t row_base, const uint8_t *chg_prev, uint32_t *list2,
+                                                       uint32_t *list3, uint32_t *counts) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool act = false;
+    if (g < n_fast) {
+        act = (chg_prev[fan0[g]] | chg_prev[fan1[g]] | chg_prev[row_base + g]) != 0;
+        if (g >= n_g2) act |= chg_prev[fan2[g]] != 0;
+    }
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const unsigned m2 = __ballot_sync(0xFFFFFFFFu, act && g < n_g2), m3 = __ballot_sync(0xFFFFFFFFu, act && g >= n_g2);
+    uint32_t b2 = 0, b3 = 0;
+    if (lane == 0) {
+        if (m2) b2 = atomicAdd(&counts[0], (uint32_t)__popc(m2));
+        if (m3) b3 = atomicAdd(&counts[1], (uint32_t)__popc(m3));
+    }
+    b2 = __shfl_sync(0xFFFFFFFFu, b2, 0);
+    b3 = __shfl_sync(0xFFFFFFFFu, b3, 0);
+    if (act) {
+        if (g < n_g2) list2[b2 + __popc(m2 & lt)] = g;
+        else list3[b3 + __popc(m3 & lt)] = g;
+    }
+}
+
+// Gates of `list[0 .. *count)` (one/two-input, or three-input with NIN = 3): B[row] = F(A), change detection
+// against A[row], changed-row flag.  Persistent: the grid is sized for the machine, CTAs stride over the list.
+template <int NIN>
+__global__ void __launch_bounds__(256, 3) k_eval_list(const Eval2Args a, const uint32_t *list, const uint32_t *count) {
+    constexpr int U = 2;
+    const uint32_t n = *count;
+    const uint32_t pb = blockIdx.x % a.pair_blocks, gbi = blockIdx.x / a.pair_blocks, gbs = gridDim.x / a.pair_blocks;
+    const uint32_t pair = pb * blockDim.x + threadIdx.x;
+    if (pair >= a.pairs || n == 0) return;
+    const size_t col = (size_t)pair * 2;
+    const uint32_t per = blockDim.y * U;
+    uint64_t dx = 0, dy = 0;
+    for (uint32_t base = gbi * per; base < n; base += gbs * per) {
+        uint32_t f0[U], f1[U], f2[U], kind[U], orow[U];
+        bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t idx = base + threadIdx.y + u * blockDim.y;
+            live[u] = idx < n;
+            const uint32_t g = list[live[u] ? idx : n - 1];
+            f0[u] = a.fan0[g];
+            f1[u] = a.fan1[g];
+            f2[u] = NIN == 3 ? a.fan2[g] : 0;
+            kind[u] = a.kind[g];
+            orow[u] = a.row_base + g;
+        }
+        ulonglong2 av[U], am[U], bv[U], bm[U], cv[U], cm[U], ov[U], om[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t r0 = (size_t)f0[u] * a.stride + col, r1 = (size_t)f1[u] * a.stride + col, o = (size_t)orow[u] * a.stride + col;
+            av[u] = ld_stream(a.in_val + r0);
+            bv[u] = ld_stream(a.in_val + r1);
+            am[u] = ld_stream(a.in_vld + r0);
+            bm[u] = ld_stream(a.in_vld + r1);
+            if (NIN == 3) {
+                const size_t r2 = (size_t)f2[u] * a.stride + col;
+                cv[u] = ld_stream(a.in_val + r2);
+                cm[u] = ld_stream(a.in_vld + r2);
+            }
+            ov[u] = ld_stream(a.in_val + o);
+            om[u] = ld_stream(a.in_vld + o);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            ulonglong2 rv, rm;
+            if (NIN == 3) {
+                const uint32_t base_kind = kind[u] >= K_NAND ? kind[u] - 3 : kind[u];
+                gate_word(base_kind, av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
+                gate_word(base_kind, av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
+                gate_word(base_kind, rv.x, rm.x, cv[u].x, cm[u].x, rv.x, rm.x);
+                gate_word(base_kind, rv.y, rm.y, cv[u].y, cm[u].y, rv.y, rm.y);
+                if (kind[u] >= K_NAND) {
+                    rv.x = ~rv.x | ~rm.x;
+                    rv.y = ~rv.y | ~rm.y;
+                }
+            } else {
+                gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
+                gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
+            }
+            bool ch = false;
+            if (live[u]) {
+                const size_t o = (size_t)orow[u] * a.stride + col;
+                st_pair(a.out_val + o, rv);
+                st_pair(a.out_vld + o, rm);
+                const uint64_t ex = (rv.x ^ ov[u].x) | (rm.x ^ om[u].x), ey = (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
+                dx |= ex;
+                dy |= ey;
+                ch = (ex | ey) != 0;
+            }
+            if (blockDim.x >= 32) {  // a whole warp on one gate: one ballot, one byte store
+                const unsigned any = __ballot_sync(__activemask(), ch);
+                if (any && (threadIdx.x & 31) == 0) a.chg_cur[orow[u]] = 1;
+            } else if (ch) {
+                a.chg_cur[orow[u]] = 1;
+            }
+        }
+    }
+    if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
+    if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
+}
+
 struct WideArgs {
     const uint32_t *off, *in;
     const uint8_t *kind, *nsel;
@@ -981,6 +1092,11 @@ void Engine::free_store() {
     cudaFree(d_rowchg_[0]);
     cudaFree(d_rowchg_[1]);
     d_rowchg_[0] = d_rowchg_[1] = nullptr;
+    cudaFree(d_act_list_[0]);
+    cudaFree(d_act_list_[1]);
+    cudaFree(d_act_counts_);
+    d_act_list_[0] = d_act_list_[1] = nullptr;
+    d_act_counts_ = nullptr;
     frontier_valid_ = false;
     cudaFree(d_kv_);
     cudaFree(d_all_valid_);
@@ -1069,6 +1185,7 @@ int Engine::ensure_device() {
         return B2_ERR_INVALID_ARG;
     }
     CU_TRY(cudaSetDevice(device_));
+    CU_TRY(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
     // the kernels are built for sm_100a only: fail loudly on anything else
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, k_clear_flags);
@@ -1757,7 +1874,10 @@ int Engine::run_jacobi(uint64_t max_steps) {
     if (use_frontier && !d_rowchg_[0]) {
         CU_TRY(cudaMalloc((void **)&d_rowchg_[0], net_.n_rows));
         CU_TRY(cudaMalloc((void **)&d_rowchg_[1], net_.n_rows));
-        store_bytes_ += 2 * (size_t)net_.n_rows;
+        CU_TRY(cudaMalloc((void **)&d_act_list_[0], (size_t)std::max<uint32_t>(net_.n_g2(), 1) * 4));
+        CU_TRY(cudaMalloc((void **)&d_act_list_[1], (size_t)std::max<uint32_t>(net_.n_g3(), 1) * 4));
+        CU_TRY(cudaMalloc((void **)&d_act_counts_, 2 * sizeof(uint32_t)));
+        store_bytes_ += 2 * (size_t)net_.n_rows + (size_t)net_.n_fast() * 4;
         frontier_valid_ = false;
     }
     if (!use_frontier) frontier_valid_ = false;
@@ -1778,21 +1898,45 @@ int Engine::run_jacobi(uint64_t max_steps) {
                                                                            stride_, pairs, sh.pair_blocks, nullptr, 0, chg_cur);
             LAUNCHED();
         }
-        if (net_.n_g2()) {
-            Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
-                        sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
-            const uint32_t per = sh.block.y * EVAL2_U;
-            const uint32_t gb = (net_.n_g2() + per - 1) / per;
-            k_eval2<EVAL2_U, true, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+        if (chg_prev && net_.n_fast()) {
+            // event-driven: compact the gates whose fan-in (or own row) changed, evaluate only those
+            CU_TRY(cudaMemsetAsync(d_act_counts_, 0, 2 * sizeof(uint32_t), ST));
+            k_frontier_scan<<<(net_.n_fast() + 255) / 256, 256, 0, ST>>>(d_fan0_, d_fan1_, d_fan2_, net_.n_g2(), net_.n_fast(), net_.n_src,
+                                                                         chg_prev, d_act_list_[0], d_act_list_[1], d_act_counts_);
             LAUNCHED();
-        }
-        if (net_.n_g3()) {
-            Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, net_.n_g2(), net_.n_fast(), net_.n_src, stride_,
-                        pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
             const uint32_t per = sh.block.y * 2;
-            const uint32_t gb = (net_.n_g3() + per - 1) / per;
-            k_eval2<2, true, false, 3><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
-            LAUNCHED();
+            const uint32_t gbs_max = std::max<uint32_t>(1, (uint32_t)(sm_count_ * 3 + sh.pair_blocks - 1) / sh.pair_blocks);
+            if (net_.n_g2()) {
+                Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
+                            sh.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
+                const uint32_t gbs = std::min<uint32_t>((net_.n_g2() + per - 1) / per, gbs_max);
+                k_eval_list<2><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, d_act_list_[0], d_act_counts_);
+                LAUNCHED();
+            }
+            if (net_.n_g3()) {
+                Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, net_.n_g2(), net_.n_fast(), net_.n_src, stride_,
+                            pairs, sh.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
+                const uint32_t gbs = std::min<uint32_t>((net_.n_g3() + per - 1) / per, gbs_max);
+                k_eval_list<3><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, d_act_list_[1], d_act_counts_ + 1);
+                LAUNCHED();
+            }
+        } else {
+            if (net_.n_g2()) {
+                Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
+                            sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
+                const uint32_t per = sh.block.y * EVAL2_U;
+                const uint32_t gb = (net_.n_g2() + per - 1) / per;
+                k_eval2<EVAL2_U, true, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                LAUNCHED();
+            }
+            if (net_.n_g3()) {
+                Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, net_.n_g2(), net_.n_fast(), net_.n_src, stride_,
+                            pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
+                const uint32_t per = sh.block.y * 2;
+                const uint32_t gb = (net_.n_g3() + per - 1) / per;
+                k_eval2<2, true, false, 3><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                LAUNCHED();
+            }
         }
         if (net_.n_wide()) {
             WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, AV, AM, BV, BM, d_changed_, 0, net_.n_wide(),

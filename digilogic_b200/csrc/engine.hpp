@@ -157,6 +157,8 @@ class Engine {
     bool opt_graph_ = true;
     // unit-delay changed-row frontier
     uint8_t *d_rowchg_[2] = {nullptr, nullptr};
+    uint32_t *d_act_list_[2] = {nullptr, nullptr}, *d_act_counts_ = nullptr;  // compacted work lists (one/two-input, three-input gates)
+    int sm_count_ = 148;
     int chg_w_ = 0;
     bool frontier_valid_ = false, opt_frontier_ = true;
     bool opt_budget_inclusive_ = false;  // SURVEY.md A.6-1 switch: `steps >= max_steps` instead of `>`
