@@ -615,8 +615,14 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
 //   on the last (check-only) application: unsettled = live.
 __global__ void __launch_bounds__(256) k_status_step(uint64_t *changed, uint64_t *conf_step, uint64_t *live,
                                                      uint64_t *conflict, uint64_t *unsettled, RunFlags *flags,
-                                                     uint32_t words, uint64_t n_lanes, int count_conflicts, int is_last) {
+                                                     uint32_t words, uint64_t n_lanes, int count_conflicts, int is_last,
+                                                     RunFlags *next_flags) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w == 0) {  // the slot of the next application (its previous content was read eight applications ago)
+        next_flags->any_live = 0;
+        next_flags->any_conflict = 0;
+        next_flags->any_unsettled = 0;
+    }
     uint64_t lv = 0, cf = 0, un = 0;
     if (w < words) {
         const uint64_t mask = lane_mask_of(w, n_lanes);
@@ -646,10 +652,10 @@ __global__ void __launch_bounds__(256) k_init_status(uint64_t *changed, uint64_t
                                                      uint64_t *unsettled, RunFlags *flags, uint32_t words, uint64_t n_lanes,
                                                      int all_conflict) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w == 0) {
-        flags->any_live = 0;
-        flags->any_conflict = all_conflict ? 1u : 0u;
-        flags->any_unsettled = 0;
+    if (w < 8) {  // all flag slots of the unit-delay loop; slot 0 doubles as the result of a run that never steps
+        flags[w].any_live = 0;
+        flags[w].any_conflict = (all_conflict && w == 0) ? 1u : 0u;
+        flags[w].any_unsettled = 0;
     }
     if (w >= words) return;
     const uint64_t mask = lane_mask_of(w, n_lanes);
@@ -1094,9 +1100,7 @@ void Engine::free_store() {
     d_rowchg_[0] = d_rowchg_[1] = nullptr;
     cudaFree(d_act_list_[0]);
     cudaFree(d_act_list_[1]);
-    cudaFree(d_act_counts_);
     d_act_list_[0] = d_act_list_[1] = nullptr;
-    d_act_counts_ = nullptr;
     frontier_valid_ = false;
     cudaFree(d_kv_);
     cudaFree(d_all_valid_);
@@ -1872,11 +1876,11 @@ int Engine::run_jacobi(uint64_t max_steps) {
     // Off when gate outputs carry external drives (their merge bypasses the flags).
     const bool use_frontier = opt_frontier_ && n_extra == 0;
     if (use_frontier && !d_rowchg_[0]) {
-        CU_TRY(cudaMalloc((void **)&d_rowchg_[0], net_.n_rows));
-        CU_TRY(cudaMalloc((void **)&d_rowchg_[1], net_.n_rows));
+        // each flag buffer carries the two list counters of its application behind the flags: one memset clears both
+        CU_TRY(cudaMalloc((void **)&d_rowchg_[0], rowchg_bytes()));
+        CU_TRY(cudaMalloc((void **)&d_rowchg_[1], rowchg_bytes()));
         CU_TRY(cudaMalloc((void **)&d_act_list_[0], (size_t)std::max<uint32_t>(net_.n_g2(), 1) * 4));
         CU_TRY(cudaMalloc((void **)&d_act_list_[1], (size_t)std::max<uint32_t>(net_.n_g3(), 1) * 4));
-        CU_TRY(cudaMalloc((void **)&d_act_counts_, 2 * sizeof(uint32_t)));
         store_bytes_ += 2 * (size_t)net_.n_rows + (size_t)net_.n_fast() * 4;
         frontier_valid_ = false;
     }
@@ -1891,7 +1895,8 @@ int Engine::run_jacobi(uint64_t max_steps) {
         // changed-row frontier: this application reads the flags of the previous one and writes its own
         uint8_t *chg_cur = use_frontier ? d_rowchg_[chg_w_] : nullptr;
         const uint8_t *chg_prev = (use_frontier && frontier_valid_) ? d_rowchg_[chg_w_ ^ 1] : nullptr;
-        if (use_frontier) CU_TRY(cudaMemsetAsync(chg_cur, 0, net_.n_rows, ST));
+        if (use_frontier) CU_TRY(cudaMemsetAsync(chg_cur, 0, rowchg_bytes(), ST));
+        uint32_t *act_counts = use_frontier ? (uint32_t *)(chg_cur + rowchg_bytes() - 8) : nullptr;
         if (net_.n_src) {
             const uint32_t rb = (net_.n_src + sh.block.y - 1) / sh.block.y;
             k_apply_drive<true><<<sh.pair_blocks * rb, sh.block, 0, ST>>>(drv_val_, drv_vld_, AV, AM, BV, BM, d_changed_, net_.n_src,
@@ -1900,9 +1905,8 @@ int Engine::run_jacobi(uint64_t max_steps) {
         }
         if (chg_prev && net_.n_fast()) {
             // event-driven: compact the gates whose fan-in (or own row) changed, evaluate only those
-            CU_TRY(cudaMemsetAsync(d_act_counts_, 0, 2 * sizeof(uint32_t), ST));
             k_frontier_scan<<<(net_.n_fast() + 255) / 256, 256, 0, ST>>>(d_fan0_, d_fan1_, d_fan2_, net_.n_g2(), net_.n_fast(), net_.n_src,
-                                                                         chg_prev, d_act_list_[0], d_act_list_[1], d_act_counts_);
+                                                                         chg_prev, d_act_list_[0], d_act_list_[1], act_counts);
             LAUNCHED();
             const uint32_t per = sh.block.y * 2;
             const uint32_t gbs_max = std::max<uint32_t>(1, (uint32_t)(sm_count_ * 3 + sh.pair_blocks - 1) / sh.pair_blocks);
@@ -1910,14 +1914,14 @@ int Engine::run_jacobi(uint64_t max_steps) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
                             sh.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
                 const uint32_t gbs = std::min<uint32_t>((net_.n_g2() + per - 1) / per, gbs_max);
-                k_eval_list<2><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, d_act_list_[0], d_act_counts_);
+                k_eval_list<2><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, d_act_list_[0], act_counts);
                 LAUNCHED();
             }
             if (net_.n_g3()) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, net_.n_g2(), net_.n_fast(), net_.n_src, stride_,
                             pairs, sh.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
                 const uint32_t gbs = std::min<uint32_t>((net_.n_g3() + per - 1) / per, gbs_max);
-                k_eval_list<3><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, d_act_list_[1], d_act_counts_ + 1);
+                k_eval_list<3><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, d_act_list_[1], act_counts + 1);
                 LAUNCHED();
             }
         } else {
@@ -1963,10 +1967,8 @@ int Engine::run_jacobi(uint64_t max_steps) {
         // kFlagLag applications later, so the device never waits for the host.  Applications queued
         // past the point where every lane has settled are no-ops on a fixed point.
         const uint32_t slot = (uint32_t)(k % kFlagSlots);
-        k_clear_flags<<<1, 1, 0, ST>>>(d_flags_ + slot);
-        LAUNCHED();
         k_status_step<<<sgrid, 256, 0, ST>>>(d_changed_, d_conf_step_, d_live_, d_conflict_, d_unsettled_, d_flags_ + slot, stride_,
-                                             n_lanes_, is_last ? 0 : 1, is_last ? 1 : 0);
+                                             n_lanes_, is_last ? 0 : 1, is_last ? 1 : 0, d_flags_ + (k + 1) % kFlagSlots);
         LAUNCHED();
         CU_TRY(cudaMemcpyAsync(h_flags_ + slot, d_flags_ + slot, sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
         CU_TRY(cudaEventRecord(EV(ev_flags_[slot]), ST));

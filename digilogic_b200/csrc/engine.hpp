@@ -157,7 +157,8 @@ class Engine {
     bool opt_graph_ = true;
     // unit-delay changed-row frontier
     uint8_t *d_rowchg_[2] = {nullptr, nullptr};
-    uint32_t *d_act_list_[2] = {nullptr, nullptr}, *d_act_counts_ = nullptr;  // compacted work lists (one/two-input, three-input gates)
+    uint32_t *d_act_list_[2] = {nullptr, nullptr};  // compacted work lists (one/two-input, three-input gates)
+    size_t rowchg_bytes() const { return (((size_t)net_.n_rows + 7) & ~(size_t)7) + 8; }  // flags, padding, two u32 list counters
     int sm_count_ = 148;
     int chg_w_ = 0;
     bool frontier_valid_ = false, opt_frontier_ = true;
