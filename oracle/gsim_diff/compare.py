@@ -28,6 +28,8 @@ def main(cases_path, dump_path):
                 b.add_not_gate(c["inputs"][0], c["output"])
             elif c["kind"] == "mux":
                 b.add_multiplexer(c["inputs"], c["select"], c["output"])
+            elif c["kind"] == "buffer":
+                b.add_buffer(c["inputs"][0], c["inputs"][1], c["output"])
             else:
                 b.add_gate(KIND[c["kind"]], c["inputs"], c["output"])
         sim = b.build()

@@ -42,6 +42,26 @@ def cases():
     out.append({"name": "mux_z_x", "wires": [1, 1, 1, 1], "comps": [{"kind": "mux", "inputs": [1, 2], "select": 0, "output": 3}],
                 "runs": [{"drives": [drive(0, s), drive(1, a), drive(2, b)], "max_steps": 10}
                          for s in (Z, X, L0, L1) for a in (Z, L1) for b in (X, L0)]})
+    # tri-state buffers (A.6-6): truth table, a shared bus with hand-over, floating bus,
+    # external drive on the bus, a buffer turning on against it, transient overlap through an inverter,
+    # gate-derived enables on a cold start
+    out.append({"name": "buffer_truth", "wires": [1, 1, 1], "comps": [{"kind": "buffer", "inputs": [0, 1], "output": 2}],
+                "runs": [{"drives": [drive(0, d), drive(1, e)], "max_steps": 10} for d in (Z, X, L0, L1) for e in (Z, X, L0, L1)]})
+    bus = [{"kind": "buffer", "inputs": [0, 2], "output": 4}, {"kind": "buffer", "inputs": [1, 3], "output": 4},
+           {"kind": "not", "inputs": [4], "output": 5}]
+    out.append({"name": "buffer_shared_bus", "wires": [1] * 6, "comps": bus,
+                "runs": [{"drives": d, "max_steps": 100} for d in (
+                    [drive(0, L1), drive(1, L0), drive(2, L1), drive(3, L0)], [drive(2, L0), drive(3, L1)], [drive(3, L0)],
+                    [drive(4, L1)], [drive(4, Z)], [drive(4, L0), drive(0, Z)], [drive(2, L1)])]})
+    out.append({"name": "buffer_transient_overlap", "wires": [1] * 5,
+                "comps": [{"kind": "not", "inputs": [2], "output": 3}, {"kind": "buffer", "inputs": [0, 2], "output": 4},
+                          {"kind": "buffer", "inputs": [1, 3], "output": 4}],
+                "runs": [{"drives": [drive(0, L1), drive(1, L0), drive(2, L0)], "max_steps": 100},
+                         {"drives": [drive(2, L1)], "max_steps": 100}]})
+    out.append({"name": "buffer_gate_derived_enables_cold", "wires": [1] * 6,
+                "comps": [{"kind": "not", "inputs": [2], "output": 3}, {"kind": "not", "inputs": [3], "output": 4},
+                          {"kind": "buffer", "inputs": [0, 3], "output": 5}, {"kind": "buffer", "inputs": [1, 4], "output": 5}],
+                "runs": [{"drives": [drive(0, L1), drive(1, L1), drive(2, L1)], "max_steps": 100}]})
     # random cyclic netlists, max_steps sweep
     rng = np.random.default_rng(1)
     for n in range(4):

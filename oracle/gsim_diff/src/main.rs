@@ -7,7 +7,7 @@ use std::num::NonZeroU8;
 
 #[derive(Deserialize)]
 struct Comp {
-    kind: String, // and | or | xor | nand | nor | xnor | not | mux
+    kind: String, // and | or | xor | nand | nor | xnor | not | mux | buffer (inputs = [data, enable])
     inputs: Vec<u32>,
     select: Option<u32>,
     output: u32,
@@ -56,6 +56,7 @@ fn main() {
                 "xnor" => builder.add_xnor_gate(&ins, o),
                 "not" => builder.add_not_gate(ins[0], o),
                 "mux" => builder.add_multiplexer(&ins, wires[c.select.unwrap() as usize], o),
+                "buffer" => builder.add_buffer(ins[0], ins[1], o),
                 k => panic!("unknown kind {k}"),
             };
             build_errors.push(r.err().map(|e| format!("{e:?}")));

@@ -23,6 +23,8 @@ def build(case, builder):
             builder.add_not_gate(c["inputs"][0], c["output"])
         elif c["kind"] == "mux":
             builder.add_multiplexer(c["inputs"], c["select"], c["output"])
+        elif c["kind"] == "buffer":
+            builder.add_buffer(c["inputs"][0], c["inputs"][1], c["output"])
         else:
             builder.add_gate(compare.KIND[c["kind"]], c["inputs"], c["output"])
     return builder.build()
@@ -45,7 +47,7 @@ def oracle_dump(cases):
 
 def test_harness_python_side(tmp_path):
     cases = make_cases.cases()
-    assert len(cases) >= 14
+    assert len(cases) >= 18
     cp, dp = tmp_path / "cases.json", tmp_path / "dump.json"
     cp.write_text(json.dumps(cases))
     dp.write_text(json.dumps(oracle_dump(cases)))
