@@ -281,33 +281,62 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
 // a persistent grid, so an application in which little changes costs a few microseconds instead of a
 // sweep of CTAs over every gate.
 __global__ void __launch_bounds__(256) k_frontier_scan(const uint32_t *fan0, const uint32_t *fan1, const uint32_t *fan2, uint32_t n_g2,
-                                                       uint32_t n_fast, uint32_t row_base, const uint8_t *chg_prev, uint32_t *list2,
-                                                       uint32_t *list3, uint32_t *counts) {
+                                                       uint32_t n_fast, uint32_t row_base, const uint8_t *kind, const uint8_t *chg_prev, uint4 *list2,
+                                                       uint4 *list3, uint32_t *list_copy, uint32_t *counts) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    bool act = false;
+    bool act = false, refresh = false;
+    uint4 e = make_uint4(0, 0, 0, 0);  // {gate | kind << 28, fan-in rows}: the evaluation needs no further index loads
     if (g < n_fast) {
-        act = (chg_prev[fan0[g]] | chg_prev[fan1[g]] | chg_prev[row_base + g]) != 0;
-        if (g >= n_g2) act |= chg_prev[fan2[g]] != 0;
+        e.y = fan0[g];
+        e.z = fan1[g];
+        e.w = g >= n_g2 ? fan2[g] : e.y;
+        e.x = g | ((uint32_t)kind[g] << 28);
+        act = (chg_prev[e.y] | chg_prev[e.z]) != 0;
+        if (g >= n_g2) act |= chg_prev[e.w] != 0;
+        // no fan-in changed but the gate's own row did: its value is final, only the other buffer's copy is stale
+        refresh = !act && chg_prev[row_base + g] != 0;
     }
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
-    const unsigned m2 = __ballot_sync(0xFFFFFFFFu, act && g < n_g2), m3 = __ballot_sync(0xFFFFFFFFu, act && g >= n_g2);
-    uint32_t b2 = 0, b3 = 0;
+    const unsigned m2 = __ballot_sync(0xFFFFFFFFu, act && g < n_g2), m3 = __ballot_sync(0xFFFFFFFFu, act && g >= n_g2),
+                   mc = __ballot_sync(0xFFFFFFFFu, refresh);
+    uint32_t b2 = 0, b3 = 0, bc = 0;
     if (lane == 0) {
         if (m2) b2 = atomicAdd(&counts[0], (uint32_t)__popc(m2));
         if (m3) b3 = atomicAdd(&counts[1], (uint32_t)__popc(m3));
+        if (mc) bc = atomicAdd(&counts[2], (uint32_t)__popc(mc));
     }
     b2 = __shfl_sync(0xFFFFFFFFu, b2, 0);
     b3 = __shfl_sync(0xFFFFFFFFu, b3, 0);
+    bc = __shfl_sync(0xFFFFFFFFu, bc, 0);
     if (act) {
-        if (g < n_g2) list2[b2 + __popc(m2 & lt)] = g;
-        else list3[b3 + __popc(m3 & lt)] = g;
+        if (g < n_g2) list2[b2 + __popc(m2 & lt)] = e;
+        else list3[b3 + __popc(m3 & lt)] = e;
+    } else if (refresh) {
+        list_copy[bc + __popc(mc & lt)] = row_base + g;
+    }
+}
+
+// Rows whose value did not change in this application but did in the previous one: B[row] = A[row] brings the
+// other buffer up to date (32 B per row-word instead of a full re-evaluation).
+__global__ void __launch_bounds__(256) k_copy_list(const uint32_t *rows, const uint32_t *count, const uint64_t *a_val,
+                                                   const uint64_t *a_vld, uint64_t *b_val, uint64_t *b_vld, uint32_t stride,
+                                                   uint32_t pairs, uint32_t pair_blocks) {
+    const uint32_t n = *count;
+    const uint32_t pb = blockIdx.x % pair_blocks, rbi = blockIdx.x / pair_blocks, rbs = gridDim.x / pair_blocks;
+    const uint32_t pair = pb * blockDim.x + threadIdx.x;
+    if (pair >= pairs) return;
+    for (uint32_t i = rbi * blockDim.y + threadIdx.y; i < n; i += rbs * blockDim.y) {
+        const size_t o = (size_t)rows[i] * stride + (size_t)pair * 2;
+        const ulonglong2 v = ld_stream(a_val + o), m = ld_stream(a_vld + o);
+        st_pair(b_val + o, v);
+        st_pair(b_vld + o, m);
     }
 }
 
 // Gates of `list[0 .. *count)` (one/two-input, or three-input with NIN = 3): B[row] = F(A), change detection
 // against A[row], changed-row flag.  Persistent: the grid is sized for the machine, CTAs stride over the list.
 template <int NIN>
-__global__ void __launch_bounds__(256, 3) k_eval_list(const Eval2Args a, const uint32_t *list, const uint32_t *count) {
+__global__ void __launch_bounds__(256, NIN == 3 ? 2 : 3) k_eval_list(const Eval2Args a, const uint4 *list, const uint32_t *count) {
     constexpr int U = 2;
     const uint32_t n = *count;
     const uint32_t pb = blockIdx.x % a.pair_blocks, gbi = blockIdx.x / a.pair_blocks, gbs = gridDim.x / a.pair_blocks;
@@ -316,19 +345,26 @@ __global__ void __launch_bounds__(256, 3) k_eval_list(const Eval2Args a, const u
     const size_t col = (size_t)pair * 2;
     const uint32_t per = blockDim.y * U;
     uint64_t dx = 0, dy = 0;
+    // list entries of the next iteration are fetched while the plane words of this one are in flight
+    uint4 nxt[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const uint32_t idx = gbi * per + threadIdx.y + u * blockDim.y;
+        nxt[u] = list[idx < n ? idx : n - 1];
+    }
     for (uint32_t base = gbi * per; base < n; base += gbs * per) {
         uint32_t f0[U], f1[U], f2[U], kind[U], orow[U];
         bool live[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const uint32_t idx = base + threadIdx.y + u * blockDim.y;
-            live[u] = idx < n;
-            const uint32_t g = list[live[u] ? idx : n - 1];
-            f0[u] = a.fan0[g];
-            f1[u] = a.fan1[g];
-            f2[u] = NIN == 3 ? a.fan2[g] : 0;
-            kind[u] = a.kind[g];
-            orow[u] = a.row_base + g;
+            live[u] = base + threadIdx.y + u * blockDim.y < n;
+            f0[u] = nxt[u].y;
+            f1[u] = nxt[u].z;
+            f2[u] = nxt[u].w;
+            kind[u] = nxt[u].x >> 28;
+            orow[u] = a.row_base + (nxt[u].x & 0x0FFFFFFFu);
+            const uint32_t idx = base + gbs * per + threadIdx.y + u * blockDim.y;
+            nxt[u] = list[idx < n ? idx : n - 1];
         }
         ulonglong2 av[U], am[U], bv[U], bm[U], cv[U], cm[U], ov[U], om[U];
 #pragma unroll
@@ -1098,9 +1134,10 @@ void Engine::free_store() {
     cudaFree(d_rowchg_[0]);
     cudaFree(d_rowchg_[1]);
     d_rowchg_[0] = d_rowchg_[1] = nullptr;
-    cudaFree(d_act_list_[0]);
-    cudaFree(d_act_list_[1]);
-    d_act_list_[0] = d_act_list_[1] = nullptr;
+    for (uint32_t *&p : d_act_list_) {
+        cudaFree(p);
+        p = nullptr;
+    }
     frontier_valid_ = false;
     cudaFree(d_kv_);
     cudaFree(d_all_valid_);
@@ -1190,6 +1227,10 @@ int Engine::ensure_device() {
     }
     CU_TRY(cudaSetDevice(device_));
     CU_TRY(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_list_[0], k_eval_list<2>, 256, 0));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_list_[1], k_eval_list<3>, 256, 0));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_list_[2], k_copy_list, 256, 0));
+    for (int &o : occ_list_) o = std::max(1, std::min(o, 4));
     // the kernels are built for sm_100a only: fail loudly on anything else
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, k_clear_flags);
@@ -1879,9 +1920,10 @@ int Engine::run_jacobi(uint64_t max_steps) {
         // each flag buffer carries the two list counters of its application behind the flags: one memset clears both
         CU_TRY(cudaMalloc((void **)&d_rowchg_[0], rowchg_bytes()));
         CU_TRY(cudaMalloc((void **)&d_rowchg_[1], rowchg_bytes()));
-        CU_TRY(cudaMalloc((void **)&d_act_list_[0], (size_t)std::max<uint32_t>(net_.n_g2(), 1) * 4));
-        CU_TRY(cudaMalloc((void **)&d_act_list_[1], (size_t)std::max<uint32_t>(net_.n_g3(), 1) * 4));
-        store_bytes_ += 2 * (size_t)net_.n_rows + (size_t)net_.n_fast() * 4;
+        CU_TRY(cudaMalloc((void **)&d_act_list_[0], (size_t)std::max<uint32_t>(net_.n_g2(), 1) * 16));
+        CU_TRY(cudaMalloc((void **)&d_act_list_[1], (size_t)std::max<uint32_t>(net_.n_g3(), 1) * 16));
+        CU_TRY(cudaMalloc((void **)&d_act_list_[2], (size_t)std::max<uint32_t>(net_.n_fast(), 1) * 4));
+        store_bytes_ += 2 * rowchg_bytes() + (size_t)net_.n_fast() * 20;
         frontier_valid_ = false;
     }
     if (!use_frontier) frontier_valid_ = false;
@@ -1896,8 +1938,9 @@ int Engine::run_jacobi(uint64_t max_steps) {
         uint8_t *chg_cur = use_frontier ? d_rowchg_[chg_w_] : nullptr;
         const uint8_t *chg_prev = (use_frontier && frontier_valid_) ? d_rowchg_[chg_w_ ^ 1] : nullptr;
         if (use_frontier) CU_TRY(cudaMemsetAsync(chg_cur, 0, rowchg_bytes(), ST));
-        uint32_t *act_counts = use_frontier ? (uint32_t *)(chg_cur + rowchg_bytes() - 8) : nullptr;
-        if (net_.n_src) {
+        uint32_t *act_counts = use_frontier ? (uint32_t *)(chg_cur + rowchg_bytes() - 16) : nullptr;
+        // Drives cannot change inside a run: after two applications both buffers hold them on the source rows.
+        if (net_.n_src && k < first_k + 2) {
             const uint32_t rb = (net_.n_src + sh.block.y - 1) / sh.block.y;
             k_apply_drive<true><<<sh.pair_blocks * rb, sh.block, 0, ST>>>(drv_val_, drv_vld_, AV, AM, BV, BM, d_changed_, net_.n_src,
                                                                            stride_, pairs, sh.pair_blocks, nullptr, 0, chg_cur);
@@ -1906,22 +1949,33 @@ int Engine::run_jacobi(uint64_t max_steps) {
         if (chg_prev && net_.n_fast()) {
             // event-driven: compact the gates whose fan-in (or own row) changed, evaluate only those
             k_frontier_scan<<<(net_.n_fast() + 255) / 256, 256, 0, ST>>>(d_fan0_, d_fan1_, d_fan2_, net_.n_g2(), net_.n_fast(), net_.n_src,
-                                                                         chg_prev, d_act_list_[0], d_act_list_[1], act_counts);
+                                                                         d_kind2_, chg_prev, (uint4 *)d_act_list_[0], (uint4 *)d_act_list_[1], d_act_list_[2],
+                                                                         act_counts);
             LAUNCHED();
             const uint32_t per = sh.block.y * 2;
-            const uint32_t gbs_max = std::max<uint32_t>(1, (uint32_t)(sm_count_ * 3 + sh.pair_blocks - 1) / sh.pair_blocks);
+            // persistent grids: exactly as many CTAs as are resident at once (a partial second wave would double the time)
+            auto slots = [&](int ctas_per_sm) { return std::max<uint32_t>(1, (uint32_t)(sm_count_ * ctas_per_sm) / sh.pair_blocks); };
+            uint32_t gbs_max = slots(occ_list_[0]);
             if (net_.n_g2()) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
                             sh.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
                 const uint32_t gbs = std::min<uint32_t>((net_.n_g2() + per - 1) / per, gbs_max);
-                k_eval_list<2><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, d_act_list_[0], act_counts);
+                k_eval_list<2><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[0], act_counts);
                 LAUNCHED();
             }
+            gbs_max = slots(occ_list_[1]);
             if (net_.n_g3()) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, net_.n_g2(), net_.n_fast(), net_.n_src, stride_,
                             pairs, sh.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
                 const uint32_t gbs = std::min<uint32_t>((net_.n_g3() + per - 1) / per, gbs_max);
-                k_eval_list<3><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, d_act_list_[1], act_counts + 1);
+                k_eval_list<3><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[1], act_counts + 1);
+                LAUNCHED();
+            }
+            gbs_max = slots(occ_list_[2]);
+            {
+                const uint32_t gbs = std::min<uint32_t>((net_.n_fast() + sh.block.y - 1) / sh.block.y, gbs_max);
+                k_copy_list<<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(d_act_list_[2], act_counts + 2, AV, AM, BV, BM, stride_, pairs,
+                                                                       sh.pair_blocks);
                 LAUNCHED();
             }
         } else {

@@ -157,9 +157,10 @@ class Engine {
     bool opt_graph_ = true;
     // unit-delay changed-row frontier
     uint8_t *d_rowchg_[2] = {nullptr, nullptr};
-    uint32_t *d_act_list_[2] = {nullptr, nullptr};  // compacted work lists (one/two-input, three-input gates)
-    size_t rowchg_bytes() const { return (((size_t)net_.n_rows + 7) & ~(size_t)7) + 8; }  // flags, padding, two u32 list counters
+    uint32_t *d_act_list_[3] = {nullptr, nullptr, nullptr};  // compacted work lists: one/two-input gates, three-input gates, rows to refresh
+    size_t rowchg_bytes() const { return (((size_t)net_.n_rows + 15) & ~(size_t)15) + 16; }  // flags, padding, the list counters
     int sm_count_ = 148;
+    int occ_list_[3] = {3, 2, 4};  // resident CTAs per SM of k_eval_list<2>, k_eval_list<3>, k_copy_list
     int chg_w_ = 0;
     bool frontier_valid_ = false, opt_frontier_ = true;
     bool opt_budget_inclusive_ = false;  // SURVEY.md A.6-1 switch: `steps >= max_steps` instead of `>`
