@@ -12,6 +12,7 @@
 // Ok iff W_k == W_{k-1} for some k <= N+2, MaxStepsReached otherwise (state W_{N+1}); a driver
 // conflict while computing W_k, k <= N+1, is Err.  For an acyclic single-driver netlist with
 // max_steps >= depth the fixed point is unique and is computed level by level in one pass.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -21,6 +22,8 @@
 
 #include "../../include/digilogic_b200.h"
 #include "engine.hpp"
+
+namespace cg = cooperative_groups;
 
 namespace b2 {
 
@@ -57,6 +60,15 @@ uint64_t kernel_launches() { return g_launches.load(); }
 __device__ __forceinline__ ulonglong2 ld_stream(const uint64_t *p) {
     ulonglong2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
+// Coherent variant for code that may run inside the device-side loop, where rows written by other CTAs
+// earlier in the same launch are read back after a grid barrier: .nc data must be read-only for the launch, and
+// a weak ld with L1::no_allocate was observed to return a stale row there (an SM re-reading a row it had read
+// two applications earlier), so these loads are volatile — served from L2.
+__device__ __forceinline__ ulonglong2 ld_row(const uint64_t *p) {
+    ulonglong2 r;
+    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
     return r;
 }
 // the same load, predicated off (result all-ones) when `skip`: no branch, no memory transaction
@@ -151,7 +163,8 @@ struct Eval2Args {
 // Changed-row frontier write: with a whole warp on one gate, one ballot and one byte store.
 __device__ __forceinline__ void mark_changed(uint8_t *chg, uint32_t row, bool changed) {
     if (blockDim.x >= 32) {
-        const unsigned any = __ballot_sync(0xFFFFFFFFu, changed);
+        // lanes past the end of a short row have returned: vote among the ones still here (lane 0 always is)
+        const unsigned any = __ballot_sync(__activemask(), changed);
         if (any && (threadIdx.x & 31) == 0) chg[row] = 1;
     } else if (changed) {
         chg[row] = 1;
@@ -280,10 +293,10 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
 // of its class with one warp-aggregated atomic.  k_eval_list then evaluates exactly the listed gates with
 // a persistent grid, so an application in which little changes costs a few microseconds instead of a
 // sweep of CTAs over every gate.
-__global__ void __launch_bounds__(256) k_frontier_scan(const uint32_t *fan0, const uint32_t *fan1, const uint32_t *fan2, uint32_t n_g2,
-                                                       uint32_t n_fast, uint32_t row_base, const uint8_t *kind, const uint8_t *chg_prev, uint4 *list2,
-                                                       uint4 *list3, uint32_t *list_copy, uint32_t *counts) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void frontier_scan_body(const uint32_t *fan0, const uint32_t *fan1, const uint32_t *fan2, uint32_t n_g2,
+                                                   uint32_t n_fast, uint32_t row_base, const uint8_t *kind, const uint8_t *chg_prev,
+                                                   uint4 *list2, uint4 *list3, uint32_t *list_copy, uint32_t *counts, uint32_t tid,
+                                                   uint32_t g) {
     bool act = false, refresh = false;
     uint4 e = make_uint4(0, 0, 0, 0);  // {gate | kind << 28, fan-in rows}: the evaluation needs no further index loads
     if (g < n_fast) {
@@ -291,12 +304,16 @@ __global__ void __launch_bounds__(256) k_frontier_scan(const uint32_t *fan0, con
         e.z = fan1[g];
         e.w = g >= n_g2 ? fan2[g] : e.y;
         e.x = g | ((uint32_t)kind[g] << 28);
-        act = (chg_prev[e.y] | chg_prev[e.z]) != 0;
-        if (g >= n_g2) act |= chg_prev[e.w] != 0;
-        // no fan-in changed but the gate's own row did: its value is final, only the other buffer's copy is stale
-        refresh = !act && chg_prev[row_base + g] != 0;
+        if (!chg_prev) {
+            act = true;  // flags not valid (first application after a reset): every gate is evaluated
+        } else {
+            act = (chg_prev[e.y] | chg_prev[e.z]) != 0;
+            if (g >= n_g2) act |= chg_prev[e.w] != 0;
+            // no fan-in changed but the gate's own row did: its value is final, only the other buffer's copy is stale
+            refresh = !act && chg_prev[row_base + g] != 0;
+        }
     }
-    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const uint32_t lane = tid & 31, lt = (1u << lane) - 1;
     const unsigned m2 = __ballot_sync(0xFFFFFFFFu, act && g < n_g2), m3 = __ballot_sync(0xFFFFFFFFu, act && g >= n_g2),
                    mc = __ballot_sync(0xFFFFFFFFu, refresh);
     uint32_t b2 = 0, b3 = 0, bc = 0;
@@ -316,30 +333,43 @@ __global__ void __launch_bounds__(256) k_frontier_scan(const uint32_t *fan0, con
     }
 }
 
+__global__ void __launch_bounds__(256) k_frontier_scan(const uint32_t *fan0, const uint32_t *fan1, const uint32_t *fan2, uint32_t n_g2,
+                                                       uint32_t n_fast, uint32_t row_base, const uint8_t *kind, const uint8_t *chg_prev, uint4 *list2,
+                                                       uint4 *list3, uint32_t *list_copy, uint32_t *counts) {
+    frontier_scan_body(fan0, fan1, fan2, n_g2, n_fast, row_base, kind, chg_prev, list2, list3, list_copy, counts, threadIdx.x,
+                       blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 // Rows whose value did not change in this application but did in the previous one: B[row] = A[row] brings the
 // other buffer up to date (32 B per row-word instead of a full re-evaluation).
-__global__ void __launch_bounds__(256) k_copy_list(const uint32_t *rows, const uint32_t *count, const uint64_t *a_val,
-                                                   const uint64_t *a_vld, uint64_t *b_val, uint64_t *b_vld, uint32_t stride,
-                                                   uint32_t pairs, uint32_t pair_blocks) {
+__device__ __forceinline__ void copy_list_body(const uint32_t *rows, const uint32_t *count, const uint64_t *a_val,
+                                               const uint64_t *a_vld, uint64_t *b_val, uint64_t *b_vld, uint32_t stride, uint32_t pairs,
+                                               uint32_t pair_blocks, uint32_t bid, uint32_t nblk) {
     const uint32_t n = *count;
-    const uint32_t pb = blockIdx.x % pair_blocks, rbi = blockIdx.x / pair_blocks, rbs = gridDim.x / pair_blocks;
+    const uint32_t pb = bid % pair_blocks, rbi = bid / pair_blocks, rbs = nblk / pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
     if (pair >= pairs) return;
     for (uint32_t i = rbi * blockDim.y + threadIdx.y; i < n; i += rbs * blockDim.y) {
         const size_t o = (size_t)rows[i] * stride + (size_t)pair * 2;
-        const ulonglong2 v = ld_stream(a_val + o), m = ld_stream(a_vld + o);
+        const ulonglong2 v = ld_row(a_val + o), m = ld_row(a_vld + o);
         st_pair(b_val + o, v);
         st_pair(b_vld + o, m);
     }
 }
 
+__global__ void __launch_bounds__(256) k_copy_list(const uint32_t *rows, const uint32_t *count, const uint64_t *a_val,
+                                                   const uint64_t *a_vld, uint64_t *b_val, uint64_t *b_vld, uint32_t stride,
+                                                   uint32_t pairs, uint32_t pair_blocks) {
+    copy_list_body(rows, count, a_val, a_vld, b_val, b_vld, stride, pairs, pair_blocks, blockIdx.x, gridDim.x);
+}
+
 // Gates of `list[0 .. *count)` (one/two-input, or three-input with NIN = 3): B[row] = F(A), change detection
 // against A[row], changed-row flag.  Persistent: the grid is sized for the machine, CTAs stride over the list.
 template <int NIN>
-__global__ void __launch_bounds__(256, NIN == 3 ? 2 : 3) k_eval_list(const Eval2Args a, const uint4 *list, const uint32_t *count) {
+__device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *list, const uint32_t *count, uint32_t bid, uint32_t nblk) {
     constexpr int U = 2;
     const uint32_t n = *count;
-    const uint32_t pb = blockIdx.x % a.pair_blocks, gbi = blockIdx.x / a.pair_blocks, gbs = gridDim.x / a.pair_blocks;
+    const uint32_t pb = bid % a.pair_blocks, gbi = bid / a.pair_blocks, gbs = nblk / a.pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
     if (pair >= a.pairs || n == 0) return;
     const size_t col = (size_t)pair * 2;
@@ -370,17 +400,17 @@ __global__ void __launch_bounds__(256, NIN == 3 ? 2 : 3) k_eval_list(const Eval2
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const size_t r0 = (size_t)f0[u] * a.stride + col, r1 = (size_t)f1[u] * a.stride + col, o = (size_t)orow[u] * a.stride + col;
-            av[u] = ld_stream(a.in_val + r0);
-            bv[u] = ld_stream(a.in_val + r1);
-            am[u] = ld_stream(a.in_vld + r0);
-            bm[u] = ld_stream(a.in_vld + r1);
+            av[u] = ld_row(a.in_val + r0);
+            bv[u] = ld_row(a.in_val + r1);
+            am[u] = ld_row(a.in_vld + r0);
+            bm[u] = ld_row(a.in_vld + r1);
             if (NIN == 3) {
                 const size_t r2 = (size_t)f2[u] * a.stride + col;
-                cv[u] = ld_stream(a.in_val + r2);
-                cm[u] = ld_stream(a.in_vld + r2);
+                cv[u] = ld_row(a.in_val + r2);
+                cm[u] = ld_row(a.in_vld + r2);
             }
-            ov[u] = ld_stream(a.in_val + o);
-            om[u] = ld_stream(a.in_vld + o);
+            ov[u] = ld_row(a.in_val + o);
+            om[u] = ld_row(a.in_vld + o);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -421,6 +451,11 @@ __global__ void __launch_bounds__(256, NIN == 3 ? 2 : 3) k_eval_list(const Eval2
     if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
 }
 
+template <int NIN>
+__global__ void __launch_bounds__(256, NIN == 3 ? 2 : 3) k_eval_list(const Eval2Args a, const uint4 *list, const uint32_t *count) {
+    eval_list_body<NIN>(a, list, count, blockIdx.x, gridDim.x);
+}
+
 struct WideArgs {
     const uint32_t *off, *in;
     const uint8_t *kind, *nsel;
@@ -436,13 +471,12 @@ struct WideArgs {
 
 __device__ __forceinline__ ulonglong2 ld_valid(const WideArgs &a, uint32_t row, size_t col) {
     if (a.kv && (*a.all_valid || a.kv[row])) return make_ulonglong2(~0ull, ~0ull);
-    return ld_stream(a.in_vld + (size_t)row * a.stride + col);
+    return ld_row(a.in_vld + (size_t)row * a.stride + col);
 }
 
 // n-ary gates (left fold, inverted kinds invert once at the end) and multiplexer slices.
 template <bool JACOBI>
-__global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
-    const uint32_t pb = blockIdx.x % a.pair_blocks, gb = blockIdx.x / a.pair_blocks;
+__device__ __forceinline__ void eval_wide_body(const WideArgs &a, uint32_t pb, uint32_t gb) {
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
     const uint32_t g = a.g_begin + gb * blockDim.y + threadIdx.y;
     if (pair >= a.pairs || g >= a.g_end) return;
@@ -467,13 +501,13 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
         for (uint32_t j = 0; b + ns + j < e; j++) {
             ulonglong2 match = make_ulonglong2(~0ull, ~0ull);
             for (uint32_t s = 0; s < ns; s++) {
-                const ulonglong2 sv = ld_stream(a.in_val + (size_t)a.in[b + s] * a.stride + col);
+                const ulonglong2 sv = ld_row(a.in_val + (size_t)a.in[b + s] * a.stride + col);
                 const uint64_t want = ((j >> s) & 1) ? ~0ull : 0ull;
                 match.x &= ~(sv.x ^ want);
                 match.y &= ~(sv.y ^ want);
             }
             const size_t r = (size_t)a.in[b + ns + j] * a.stride + col;
-            const ulonglong2 dv = ld_stream(a.in_val + r), dm = ld_valid(a, a.in[b + ns + j], col);
+            const ulonglong2 dv = ld_row(a.in_val + r), dm = ld_valid(a, a.in[b + ns + j], col);
             pv.x |= match.x & dv.x;
             pv.y |= match.y & dv.y;
             pm.x |= match.x & dm.x;
@@ -486,11 +520,11 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
     } else {
         const uint32_t base = kind >= K_NAND ? kind - 3 : kind;  // fold with the positive op
         size_t r = (size_t)a.in[b] * a.stride + col;
-        rv = ld_stream(a.in_val + r);
+        rv = ld_row(a.in_val + r);
         rm = ld_valid(a, a.in[b], col);
         for (uint32_t i = b + 1; i < e; i++) {
             r = (size_t)a.in[i] * a.stride + col;
-            const ulonglong2 xv = ld_stream(a.in_val + r), xm = ld_valid(a, a.in[i], col);
+            const ulonglong2 xv = ld_row(a.in_val + r), xm = ld_valid(a, a.in[i], col);
             gate_word(base, rv.x, rm.x, xv.x, xm.x, rv.x, rm.x);
             gate_word(base, rv.y, rm.y, xv.y, xm.y, rv.y, rm.y);
         }
@@ -501,7 +535,7 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
     }
     const size_t o = (size_t)(a.row_base + g) * a.stride + col;
     if (JACOBI) {
-        const ulonglong2 ov = ld_stream(a.in_val + o), om = ld_stream(a.in_vld + o);
+        const ulonglong2 ov = ld_row(a.in_val + o), om = ld_row(a.in_vld + o);
         const uint64_t dx = (rv.x ^ ov.x) | (rm.x ^ om.x), dy = (rv.y ^ ov.y) | (rm.y ^ om.y);
         if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
         if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
@@ -513,23 +547,26 @@ __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
     if (a.kv && pb == 0 && threadIdx.x == 0) a.kv[a.row_base + g] = 0;
 }
 
+template <bool JACOBI>
+__global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
+    eval_wide_body<JACOBI>(a, blockIdx.x % a.pair_blocks, blockIdx.x / a.pair_blocks);
+}
+
 // Source rows take their external drive: out[row] = D[row] (rows [0, n_rows) of both stores).
 // kv (nullable, pre-set to 1 per source row): cleared when any in-use lane-word of the row's
 // valid plane is not all-ones.
 template <bool JACOBI>
-__global__ void __launch_bounds__(256) k_apply_drive(const uint64_t *dval, const uint64_t *dvld, const uint64_t *old_val,
-                                                     const uint64_t *old_vld, uint64_t *out_val, uint64_t *out_vld,
-                                                     uint64_t *changed, uint32_t n_rows, uint32_t stride, uint32_t pairs,
-                                                     uint32_t pair_blocks, uint8_t *kv = nullptr, uint32_t words_in_use = 0,
-                                                     uint8_t *chg_cur = nullptr) {
-    const uint32_t pb = blockIdx.x % pair_blocks, rb = blockIdx.x / pair_blocks;
+__device__ __forceinline__ void apply_drive_body(const uint64_t *dval, const uint64_t *dvld, const uint64_t *old_val,
+                                                 const uint64_t *old_vld, uint64_t *out_val, uint64_t *out_vld, uint64_t *changed,
+                                                 uint32_t n_rows, uint32_t stride, uint32_t pairs, uint8_t *kv, uint32_t words_in_use,
+                                                 uint8_t *chg_cur, uint32_t pb, uint32_t rb) {
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
     const uint32_t row = rb * blockDim.y + threadIdx.y;
     if (pair >= pairs || row >= n_rows) return;
     const size_t col = (size_t)pair * 2, o = (size_t)row * stride + col;
-    const ulonglong2 v = ld_stream(dval + o), m = ld_stream(dvld + o);
+    const ulonglong2 v = ld_row(dval + o), m = ld_row(dvld + o);
     if (JACOBI) {
-        const ulonglong2 ov = ld_stream(old_val + o), om = ld_stream(old_vld + o);
+        const ulonglong2 ov = ld_row(old_val + o), om = ld_row(old_vld + o);
         const uint64_t dx = (v.x ^ ov.x) | (m.x ^ om.x), dy = (v.y ^ ov.y) | (m.y ^ om.y);
         if (dx) atomicOr((unsigned long long *)&changed[col], (unsigned long long)dx);
         if (dy) atomicOr((unsigned long long *)&changed[col + 1], (unsigned long long)dy);
@@ -541,6 +578,16 @@ __global__ void __launch_bounds__(256) k_apply_drive(const uint64_t *dval, const
         const bool bad = (col < words_in_use && m.x != ~0ull) || (col + 1 < words_in_use && m.y != ~0ull);
         if (bad) kv[row] = 0;
     }
+}
+
+template <bool JACOBI>
+__global__ void __launch_bounds__(256) k_apply_drive(const uint64_t *dval, const uint64_t *dvld, const uint64_t *old_val,
+                                                     const uint64_t *old_vld, uint64_t *out_val, uint64_t *out_vld,
+                                                     uint64_t *changed, uint32_t n_rows, uint32_t stride, uint32_t pairs,
+                                                     uint32_t pair_blocks, uint8_t *kv = nullptr, uint32_t words_in_use = 0,
+                                                     uint8_t *chg_cur = nullptr) {
+    apply_drive_body<JACOBI>(dval, dvld, old_val, old_vld, out_val, out_vld, changed, n_rows, stride, pairs, kv, words_in_use, chg_cur,
+                             blockIdx.x % pair_blocks, blockIdx.x / pair_blocks);
 }
 
 // all_valid = AND of the source rows' flags (one CTA)
@@ -609,8 +656,7 @@ struct ResolveArgs {
     int cold;
 };
 
-__global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
-    const uint32_t pb = blockIdx.x % a.pair_blocks, rb = blockIdx.x / a.pair_blocks;
+__device__ __forceinline__ void resolve_body(const ResolveArgs &a, uint32_t pb, uint32_t rb) {
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
     const uint32_t r = rb * blockDim.y + threadIdx.y;
     if (pair >= a.pairs || r >= a.n_res) return;
@@ -646,19 +692,16 @@ __global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
     st_pair(a.b_vld + o, m);
 }
 
+__global__ void __launch_bounds__(256) k_resolve(const ResolveArgs a) {
+    resolve_body(a, blockIdx.x % a.pair_blocks, blockIdx.x / a.pair_blocks);
+}
+
 // Per-lane bookkeeping after one application:
 //   conflict |= conf_step & live (only while k < last); live &= changed & ~conflict;
 //   on the last (check-only) application: unsettled = live.
-__global__ void __launch_bounds__(256) k_status_step(uint64_t *changed, uint64_t *conf_step, uint64_t *live,
-                                                     uint64_t *conflict, uint64_t *unsettled, RunFlags *flags,
-                                                     uint32_t words, uint64_t n_lanes, int count_conflicts, int is_last,
-                                                     RunFlags *next_flags) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w == 0) {  // the slot of the next application (its previous content was read eight applications ago)
-        next_flags->any_live = 0;
-        next_flags->any_conflict = 0;
-        next_flags->any_unsettled = 0;
-    }
+__device__ __forceinline__ void status_step_body(uint64_t *changed, uint64_t *conf_step, uint64_t *live, uint64_t *conflict,
+                                                 uint64_t *unsettled, RunFlags *flags, uint32_t words, uint64_t n_lanes,
+                                                 int count_conflicts, int is_last, uint32_t w, uint32_t lane) {
     uint64_t lv = 0, cf = 0, un = 0;
     if (w < words) {
         const uint64_t mask = lane_mask_of(w, n_lanes);
@@ -677,11 +720,25 @@ __global__ void __launch_bounds__(256) k_status_step(uint64_t *changed, uint64_t
     }
     const unsigned any_l = __ballot_sync(0xFFFFFFFFu, lv != 0), any_c = __ballot_sync(0xFFFFFFFFu, cf != 0),
                    any_u = __ballot_sync(0xFFFFFFFFu, un != 0);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (any_l) atomicOr(&flags->any_live, 1u);
         if (any_c) atomicOr(&flags->any_conflict, 1u);
         if (any_u) atomicOr(&flags->any_unsettled, 1u);
     }
+}
+
+__global__ void __launch_bounds__(256) k_status_step(uint64_t *changed, uint64_t *conf_step, uint64_t *live,
+                                                     uint64_t *conflict, uint64_t *unsettled, RunFlags *flags,
+                                                     uint32_t words, uint64_t n_lanes, int count_conflicts, int is_last,
+                                                     RunFlags *next_flags, const uint32_t *counts) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w == 0) {  // the slot of the next application (its previous content was read eight applications ago)
+        next_flags->any_live = 0;
+        next_flags->any_conflict = 0;
+        next_flags->any_unsettled = 0;
+        flags->active = counts ? counts[0] + counts[1] + counts[2] : 0xFFFFFFFFu;
+    }
+    status_step_body(changed, conf_step, live, conflict, unsettled, flags, words, n_lanes, count_conflicts, is_last, w, threadIdx.x & 31);
 }
 
 __global__ void __launch_bounds__(256) k_init_status(uint64_t *changed, uint64_t *conf_step, uint64_t *live, uint64_t *conflict,
@@ -792,6 +849,134 @@ __global__ void __launch_bounds__(256) k_pack_lane0(const uint32_t *rows, uint32
     }
     out0[byte] = (uint8_t)b0;
     out1[byte] = (uint8_t)b1;
+}
+
+// ---------------------------------------------------------------------------- device-side run_sim loop
+//
+// The whole unit-delay loop of one run_sim as ONE cooperative launch: per application the same phases as the
+// host-driven loop (drives -> frontier scan | listed gates, refresh copies, wide gates | tri-state resolve |
+// lane bookkeeping), separated by grid barriers instead of kernel boundaries, and the stop decision
+// ("no lane is live any more", or the step budget) is taken on the device.  An application in which little
+// happens — an oscillating latch in a few lanes, the tail of a settle — costs three grid barriers, not a dozen
+// launches and a host round trip.
+struct LoopResult {
+    uint64_t k;  // index of the last application performed
+    int32_t cur, chg_w;
+    uint32_t any_conflict, any_unsettled;
+    uint32_t bailed;  // 1: stopped before application k+1 because its work list is too long for this kernel; the host loop goes on
+    uint32_t pad;
+};
+
+struct LoopArgs {
+    const uint32_t *fan0, *fan1, *fan2;
+    const uint8_t *kind2;
+    WideArgs wide;     // netlist part; the plane pointers are set per application
+    ResolveArgs res;   // likewise
+    uint64_t *val[2], *vld[2];
+    const uint64_t *drv_val, *drv_vld;
+    uint8_t *chg[2];
+    uint4 *list2, *list3;
+    uint32_t *listc;
+    uint64_t *changed, *conf_step, *live, *conflict, *unsettled;
+    RunFlags *flags;  // kFlagSlots slots, all clear on entry
+    LoopResult *result;
+    uint32_t n_src, n_g2, n_fast, n_wide, n_res, stride, pairs, pair_blocks, rowchg_bytes;
+    uint64_t n_lanes, k0, last;
+    uint64_t bail_row_words;  // hand back to the host loop when listed gates x row words exceeds this
+    int32_t cur, chg_w, frontier_valid;
+};
+
+__global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t bid = blockIdx.x, nblk = gridDim.x;
+    const uint32_t pb = bid % a.pair_blocks, gbi = bid / a.pair_blocks, gbs = nblk / a.pair_blocks;
+    const uint32_t lt = threadIdx.y * blockDim.x + threadIdx.x;  // linear thread id: warps are 32 consecutive ones
+    uint64_t k = a.k0;
+    int cur = a.cur, cw = a.chg_w;
+    bool fv = a.frontier_valid != 0, bailed = false;
+    const uint64_t first_k = k + 1;
+    for (;;) {
+        k++;
+        const bool is_last = k == a.last;
+        const uint64_t *AV = a.val[cur], *AM = a.vld[cur];
+        uint64_t *BV = a.val[cur ^ 1], *BM = a.vld[cur ^ 1];
+        uint8_t *chg_cur = a.chg[cw];
+        const uint8_t *chg_prev = fv ? a.chg[cw ^ 1] : nullptr;
+        uint32_t *counts = (uint32_t *)(chg_cur + a.rowchg_bytes - 16);
+        RunFlags *flags = a.flags + (k % 8);
+
+        // ---- phase 1: drives (they cannot change inside a run: two applications fill both buffers), frontier scan
+        if (a.n_src && k < first_k + 2)
+            for (uint32_t rb = gbi; rb * blockDim.y < a.n_src; rb += gbs)
+                apply_drive_body<true>(a.drv_val, a.drv_vld, AV, AM, BV, BM, a.changed, a.n_src, a.stride, a.pairs, nullptr, 0, chg_cur,
+                                       pb, rb);
+        for (uint32_t base = bid * 256; base < a.n_fast; base += nblk * 256)
+            frontier_scan_body(a.fan0, a.fan1, a.fan2, a.n_g2, a.n_fast, a.n_src, a.kind2, chg_prev, a.list2, a.list3, a.listc, counts,
+                               lt, base + lt);
+        grid.sync();
+        if (k > first_k) {  // a long work list is better served by the separate, fully occupied kernels
+            const uint64_t listed = (uint64_t)counts[0] + counts[1] + counts[2];
+            if (listed * a.stride > a.bail_row_words) {
+                bailed = true;
+                k--;
+                break;
+            }
+        }
+
+        // ---- phase 2: the listed gates, the rows to refresh, the wide gates
+        {
+            Eval2Args e{a.fan0, a.fan1, a.fan2, a.kind2, AV, AM, BV, BM, a.changed, 0, a.n_fast, a.n_src, a.stride, a.pairs,
+                        a.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
+            if (a.n_g2) eval_list_body<2>(e, a.list2, counts, bid, nblk);
+            if (a.n_fast > a.n_g2) eval_list_body<3>(e, a.list3, counts + 1, bid, nblk);
+            copy_list_body(a.listc, counts + 2, AV, AM, BV, BM, a.stride, a.pairs, a.pair_blocks, bid, nblk);
+            if (a.n_wide) {
+                WideArgs w = a.wide;
+                w.in_val = AV; w.in_vld = AM; w.out_val = BV; w.out_vld = BM;
+                w.chg_prev = chg_prev; w.chg_cur = chg_cur;
+                for (uint32_t gb = gbi; gb * blockDim.y < a.n_wide; gb += gbs) eval_wide_body<true>(w, pb, gb);
+            }
+        }
+        grid.sync();
+        if (a.n_res) {  // tri-state nets see their drivers' rows of this application
+            ResolveArgs r = a.res;
+            r.a_val = AV; r.a_vld = AM; r.b_val = BV; r.b_vld = BM;
+            r.chg_cur = chg_cur;
+            for (uint32_t rb = gbi; rb * blockDim.y < a.n_res; rb += gbs) resolve_body(r, pb, rb);
+            grid.sync();
+        }
+
+        // ---- phase 3: lane bookkeeping; the flags of the previous application become the clean buffer of the next
+        for (uint32_t base = bid * 256; base < a.stride; base += nblk * 256)
+            status_step_body(a.changed, a.conf_step, a.live, a.conflict, a.unsettled, flags, a.stride, a.n_lanes, is_last ? 0 : 1,
+                             is_last ? 1 : 0, base + lt, lt & 31);
+        {
+            uint4 *z = (uint4 *)a.chg[cw ^ 1];
+            for (uint32_t i = bid * 256 + lt; i < a.rowchg_bytes / 16; i += nblk * 256) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        if (bid == 0 && lt == 0) {
+            RunFlags *nf = a.flags + ((k + 1) % 8);
+            nf->any_live = 0;
+            nf->any_conflict = 0;
+            nf->any_unsettled = 0;
+        }
+        grid.sync();
+        const uint32_t any_live = *(volatile uint32_t *)&flags->any_live;
+        fv = true;
+        cw ^= 1;
+        if (is_last) break;  // check-only application: the state stays W_{N+1}
+        cur ^= 1;
+        if (!any_live) break;
+    }
+    if (bid == 0 && lt == 0) {
+        const RunFlags *flags = a.flags + (k % 8);
+        a.result->k = k;
+        a.result->cur = cur;
+        a.result->chg_w = cw;
+        a.result->any_conflict = *(volatile uint32_t *)&flags->any_conflict;
+        a.result->any_unsettled = *(volatile uint32_t *)&flags->any_unsettled;
+        a.result->bailed = bailed ? 1u : 0u;
+    }
 }
 
 // ---------------------------------------------------------------------------- resident kernel
@@ -1104,6 +1289,8 @@ Engine::~Engine() {
         cudaFree(d_levels_);
         cudaFree(d_flags_);
         cudaFree(d_pend_);
+        cudaFree(d_loop_result_);
+        if (h_loop_result_) cudaFreeHost(h_loop_result_);
         cudaFree(d_max_apps_);
         if (h_flags_) cudaFreeHost(h_flags_);
         if (own_stream_ && stream_) cudaStreamDestroy(ST);
@@ -1231,6 +1418,14 @@ int Engine::ensure_device() {
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_list_[1], k_eval_list<3>, 256, 0));
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_list_[2], k_copy_list, 256, 0));
     for (int &o : occ_list_) o = std::max(1, std::min(o, 4));
+    {
+        int coop = 0, occ = 0;
+        CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_unit_delay_loop, 256, 0));
+        loop_ctas_ = coop ? (uint32_t)(std::min(occ, 2) * sm_count_) : 0;
+        CU_TRY(cudaMalloc((void **)&d_loop_result_, sizeof(LoopResult)));
+        CU_TRY(cudaMallocHost((void **)&h_loop_result_, sizeof(LoopResult)));
+    }
     // the kernels are built for sm_100a only: fail loudly on anything else
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, k_clear_flags);
@@ -1729,6 +1924,8 @@ int Engine::materialise_valid() {
 
 #define EVAL2_U 4
 static const uint32_t kFlagSlots = 8, kFlagLag = 2;
+// device-side loop: entered when listed gates x row words of an application is at most this, left above four times this
+static const uint64_t kLoopEntryRowWords = 1ull << 20;
 
 int Engine::run_levelised(bool async) {
     const uint32_t pairs = stride_ / 2;
@@ -1859,6 +2056,57 @@ int Engine::run_levelised(bool async) {
     return h_flags_->any_conflict ? B2_RUN_CONFLICT : B2_RUN_OK;
 }
 
+// Continues the unit-delay loop of the current run from application k+1 on the device (k_unit_delay_loop).
+// finished: the run ended there (result = its b2_run_result); otherwise the kernel handed back before an
+// application whose work list is long, and the host loop goes on from the returned k.
+int Engine::run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &result) {
+    const uint32_t pairs = stride_ / 2;
+    const Shape sh = shape_for(pairs);
+    const uint32_t n_res = net_.n_res(), res_base = net_.n_src + net_.n_fast() + net_.n_wide();
+    CU_TRY(cudaMemsetAsync(d_rowchg_[chg_w_], 0, rowchg_bytes(), ST));
+    LoopArgs la;
+    la.fan0 = d_fan0_; la.fan1 = d_fan1_; la.fan2 = d_fan2_; la.kind2 = d_kind2_;
+    la.wide = WideArgs{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, nullptr, nullptr, nullptr, nullptr, d_changed_, 0,
+                       net_.n_wide(), net_.n_src + net_.n_fast(), stride_, pairs, sh.pair_blocks, nullptr, nullptr, nullptr, nullptr};
+    la.res = ResolveArgs{d_res_off_, d_res_in_, d_res_xslot_, xdrv_val_, xdrv_vld_, nullptr, nullptr, nullptr, nullptr, d_changed_,
+                         d_conf_step_, nullptr, n_res, res_base, stride_, pairs, sh.pair_blocks, 0};
+    for (int i = 0; i < 2; i++) {
+        la.val[i] = val_[i];
+        la.vld[i] = vld_[i];
+        la.chg[i] = d_rowchg_[i];
+    }
+    la.drv_val = drv_val_; la.drv_vld = drv_vld_;
+    la.list2 = (uint4 *)d_act_list_[0]; la.list3 = (uint4 *)d_act_list_[1]; la.listc = d_act_list_[2];
+    la.changed = d_changed_; la.conf_step = d_conf_step_; la.live = d_live_; la.conflict = d_conflict_; la.unsettled = d_unsettled_;
+    la.flags = d_flags_;
+    la.result = d_loop_result_;
+    la.n_src = net_.n_src; la.n_g2 = net_.n_g2(); la.n_fast = net_.n_fast(); la.n_wide = net_.n_wide(); la.n_res = n_res;
+    la.stride = stride_; la.pairs = pairs; la.pair_blocks = sh.pair_blocks; la.rowchg_bytes = (uint32_t)rowchg_bytes();
+    la.n_lanes = n_lanes_; la.k0 = k; la.last = last;
+    la.bail_row_words = 4 * kLoopEntryRowWords;
+    la.cur = cur_; la.chg_w = chg_w_; la.frontier_valid = frontier_valid_ ? 1 : 0;
+    void *params[] = {&la};
+    const uint32_t grid = sh.pair_blocks * (loop_ctas_ / sh.pair_blocks);
+    CU_TRY(cudaLaunchCooperativeKernel((const void *)k_unit_delay_loop, dim3(grid), sh.block, params, 0, ST));
+    LAUNCHED();
+    CU_TRY(cudaMemcpyAsync(h_loop_result_, d_loop_result_, sizeof(LoopResult), cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaStreamSynchronize(ST));
+    const LoopResult *lr = (const LoopResult *)h_loop_result_;
+    last_apps_ += lr->k - k;
+    k = lr->k;
+    cur_ = lr->cur;
+    chg_w_ = lr->chg_w;
+    frontier_valid_ = true;
+    finished = lr->bailed == 0;
+    if (finished) {
+        if (k == last) frontier_valid_ = false;  // ended on the check-only application: the other buffer is one step ahead
+        h_flags_->any_conflict = lr->any_conflict;
+        h_flags_->any_unsettled = lr->any_unsettled;
+        result = lr->any_conflict ? B2_RUN_CONFLICT : (lr->any_unsettled ? B2_RUN_MAX_STEPS_REACHED : B2_RUN_OK);
+    }
+    return B2_OK;
+}
+
 int Engine::run_jacobi(uint64_t max_steps) {
     int rc = ensure_second_buffer();
     if (rc) return rc;
@@ -1927,8 +2175,26 @@ int Engine::run_jacobi(uint64_t max_steps) {
         frontier_valid_ = false;
     }
     if (!use_frontier) frontier_valid_ = false;
+    // Light applications (a short work list times the row length) run in the device-side loop, heavy ones as
+    // separate fully occupied kernels; the run moves between the two as the activity changes.
+    const bool device_ok = opt_device_loop_ && use_frontier && loop_ctas_ >= sh.pair_blocks;
+    bool want_device = device_ok && (uint64_t)net_.n_fast() * stride_ <= kLoopEntryRowWords;
     const uint64_t first_k = k + 1;
+    uint64_t lag_base = first_k;  // first application of the current host-driven stretch
+    uint32_t light_streak = 0;
     for (;;) {
+        if (want_device) {
+            bool finished = false;
+            int result = B2_RUN_OK;
+            if ((rc = run_device_loop(k, last, finished, result))) return rc;
+            if (finished) {
+                if ((rc = drives_end())) return rc;
+                return result;
+            }
+            want_device = false;
+            light_streak = 0;
+            lag_base = k + 1;
+        }
         k++;
         last_apps_++;
         const bool is_last = k == last;
@@ -2022,17 +2288,25 @@ int Engine::run_jacobi(uint64_t max_steps) {
         // past the point where every lane has settled are no-ops on a fixed point.
         const uint32_t slot = (uint32_t)(k % kFlagSlots);
         k_status_step<<<sgrid, 256, 0, ST>>>(d_changed_, d_conf_step_, d_live_, d_conflict_, d_unsettled_, d_flags_ + slot, stride_,
-                                             n_lanes_, is_last ? 0 : 1, is_last ? 1 : 0, d_flags_ + (k + 1) % kFlagSlots);
+                                             n_lanes_, is_last ? 0 : 1, is_last ? 1 : 0, d_flags_ + (k + 1) % kFlagSlots,
+                                             chg_prev ? act_counts : nullptr);
         LAUNCHED();
         CU_TRY(cudaMemcpyAsync(h_flags_ + slot, d_flags_ + slot, sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
         CU_TRY(cudaEventRecord(EV(ev_flags_[slot]), ST));
         if (!is_last) cur_ ^= 1;  // check-only last application: MaxStepsReached lanes keep W_{N+1}
         newest = slot;
         bool stop = is_last;
-        if (!stop && k >= first_k + kFlagLag) {
+        if (!stop && k >= lag_base + kFlagLag) {
             const uint32_t old = (uint32_t)((k - kFlagLag) % kFlagSlots);
             CU_TRY(cudaEventSynchronize(EV(ev_flags_[old])));
             if (!h_flags_[old].any_live) stop = true;
+            else if (device_ok && (uint64_t)h_flags_[old].active * stride_ <= kLoopEntryRowWords) {
+                // a long tail of light applications (oscillating lanes): worth a cooperative launch; a settle
+                // that is about to end is not
+                if (++light_streak >= 4) want_device = true;
+            } else {
+                light_streak = 0;
+            }
         }
         if (stop) break;
     }

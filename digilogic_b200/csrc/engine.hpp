@@ -17,8 +17,11 @@ const char *get_last_error();
 uint64_t kernel_launches();
 
 struct RunFlags {  // written by the status kernel, read by the host after each application
-    uint32_t any_live, any_conflict, any_unsettled, pad;
+    uint32_t any_live, any_conflict, any_unsettled;
+    uint32_t active;  // gates listed for this application (frontier lists); 0xFFFFFFFF: every gate was evaluated
 };
+
+struct LoopResult;
 
 class Engine {
    public:
@@ -61,6 +64,7 @@ class Engine {
     void set_use_graph(bool on) { opt_graph_ = on; }
     void set_budget_inclusive(bool on) { opt_budget_inclusive_ = on; }
     void set_use_frontier(bool on) { opt_frontier_ = on; frontier_valid_ = false; }
+    void set_device_loop(bool on) { opt_device_loop_ = on; }
     void set_eval_unroll(uint32_t u) { opt_u_ = (u == 2 || u == 4) ? u : 0; level_graph_key_ = 0; }
 
    private:
@@ -76,6 +80,7 @@ class Engine {
     int upload_rows(const uint32_t *wires, uint32_t n, bool drive_rows);
     int run_levelised(bool async);
     int run_jacobi(uint64_t max_steps);
+    int run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &result);
     int run_resident(uint64_t max_steps, bool levelised);
     int materialise_valid();
     uint32_t resident_wpc() const;
@@ -159,6 +164,11 @@ class Engine {
     uint8_t *d_rowchg_[2] = {nullptr, nullptr};
     uint32_t *d_act_list_[3] = {nullptr, nullptr, nullptr};  // compacted work lists: one/two-input gates, three-input gates, rows to refresh
     size_t rowchg_bytes() const { return (((size_t)net_.n_rows + 15) & ~(size_t)15) + 16; }  // flags, padding, the list counters
+    // device-side run_sim loop (k_unit_delay_loop): CTAs of one cooperative launch, result block
+    uint32_t loop_ctas_ = 0;
+    struct LoopResult *d_loop_result_ = nullptr;
+    void *h_loop_result_ = nullptr;
+    bool opt_device_loop_ = true;
     int sm_count_ = 148;
     int occ_list_[3] = {3, 2, 4};  // resident CTAs per SM of k_eval_list<2>, k_eval_list<3>, k_copy_list
     int chg_w_ = 0;

@@ -157,8 +157,11 @@ enum b2_option {
     B2_OPT_STEP_BUDGET_INCLUSIVE = 6, /* default 0.  gsim's run_sim is restated as `if steps > max_steps { MaxStepsReached }`
                                   (at most max_steps + 1 steps after begin_sim).  1 switches to `>=`, should the differential
                                   run against the real crate (oracle/gsim_diff) say so — SURVEY.md A.6-1. */
-    B2_OPT_FRONTIER = 5        /* default 1.  Unit-delay runs in HBM re-evaluate a gate only if one of its fan-in rows or
+    B2_OPT_FRONTIER = 5,       /* default 1.  Unit-delay runs in HBM re-evaluate a gate only if one of its fan-in rows or
                                   its own output row changed (on any lane) in the previous application. */
+    B2_OPT_DEVICE_LOOP = 7     /* default 1.  Unit-delay runs in HBM execute the whole run_sim loop in one cooperative launch
+                                  (grid barriers between the phases of an application, stop decision on the device);
+                                  0: one set of launches per application, stop decision on the host. */
 };
 int b2_sim_set_option(b2_sim *s, int option, int64_t value);
 /* Block until everything queued by this simulator has finished. */

@@ -81,7 +81,7 @@ def _drive_all(sims, wire, value, valid):
 
 
 @pytest.mark.parametrize("n_hazard,max_steps", [(0, 10_000), (3, 60)])
-@pytest.mark.parametrize("resident", [True, False])
+@pytest.mark.parametrize("resident", [True, False, "host"])
 def test_config4_sequential_vs_oracle(n_hazard, max_steps, resident):
     """Flip-flop LFSR chains + SR latches at reduced size: per-lane init pattern, then clocked
     steps (clk up, clk down = two run_sim calls).  After every call: per-lane result
@@ -93,7 +93,8 @@ def test_config4_sequential_vs_oracle(n_hazard, max_steps, resident):
     ob = seq.emit(oracle.Builder())
     sim = seq.emit(SimulatorBuilder()).build()
     assert sim.info.cyclic == 1 and sim.info.n_gates3 > 0
-    sim.set_option(sim.OPT_RESIDENT_KERNEL, int(resident))
+    sim.set_option(sim.OPT_RESIDENT_KERNEL, int(resident is True))
+    sim.set_option(sim.OPT_DEVICE_LOOP, int(resident != "host"))
     sim.set_lanes(n_lanes)
     lanes = oracle.Lanes(ob, n_lanes)
     both = (lanes, sim)
@@ -132,7 +133,7 @@ def test_config4_sequential_vs_oracle(n_hazard, max_steps, resident):
         _drive_all(both, seq.clk, zeros, ones)
         run_and_compare(("down", step))
     assert seen_unsettled == (n_hazard > 0)
-    assert sim.info.last_mode == (3 if resident else 2)
+    assert sim.info.last_mode == (3 if resident is True else 2)
 
 
 def test_config5_netlist_sampled_against_oracle():

@@ -31,7 +31,7 @@ def test_empty_and_gateless_netlists():
 
 
 @pytest.mark.parametrize("n_lanes", [1, 63, 65, 127, 129, 64 * 5 + 1])
-@pytest.mark.parametrize("resident", [True, False])
+@pytest.mark.parametrize("resident", [True, False, "host"])
 def test_ragged_lane_counts_and_oscillator(n_lanes, resident):
     """A ring of one inverter oscillates in lanes where the enable is 1 and holds where it is 0;
     lanes beyond n_lanes in the last word must not leak into the result."""
@@ -41,7 +41,8 @@ def test_ragged_lane_counts_and_oscillator(n_lanes, resident):
     nl.add_gate(AND, [d, d], q)        # q = d (repeated input), closes the loop
     ob = nl.replay(oracle.Builder())
     sim = nl.replay(SimulatorBuilder()).build()
-    sim.set_option(sim.OPT_RESIDENT_KERNEL, int(resident))
+    sim.set_option(sim.OPT_RESIDENT_KERNEL, int(resident is True))
+    sim.set_option(sim.OPT_DEVICE_LOOP, int(resident != "host"))
     sim.set_lanes(n_lanes)
     lanes = oracle.Lanes(ob, n_lanes)
     rng = np.random.default_rng(n_lanes)
@@ -230,3 +231,31 @@ def test_drive_queue_order_and_state_snapshot():
     sim.set_lanes(64)                                 # cold again: queued drives are dropped with the store
     assert sim.run_sim(10) == SimulationRunResult.Ok
     assert sim.get_wire_state(a) == LogicState(0, 0)
+
+
+def test_device_loop_is_deterministic_under_oscillation():
+    """Regression: inside the device-side loop a CTA re-reads rows that other CTAs rewrote two
+    applications earlier; with cached (weak) loads a stale row came back now and then on oscillating
+    lanes near the step budget.  The same run, repeated, must match the oracle every time."""
+    from helpers import random_netlist
+    for trial in range(6):
+        rng = np.random.default_rng(77 * 1 + 1)
+        nl, first_in = random_netlist(rng, 6, 48, cyclic=True, wide=True, mux=True)
+        n_lanes = 64 * 37
+        sim = nl.replay(SimulatorBuilder()).build()
+        sim.set_option(sim.OPT_RESIDENT_KERNEL, 0)
+        sim.set_lanes(n_lanes)
+        lanes = oracle.Lanes(nl.replay(oracle.Builder()), n_lanes)
+        mask = lane_mask(n_lanes)
+        for max_steps in [0, 1, 2, 3, 5, 8, 60, 7, 0, 1000]:
+            for i in range(6):
+                if rng.random() < 0.7:
+                    v, m = random_drive(rng, lanes.words)
+                    lanes.set_drive(first_in + i, v, m)
+                    sim.set_wire_drive_lanes(first_in + i, v, m)
+            status, _, _ = lanes.run(max_steps)
+            res, conflict, unsettled = sim.run_sim_lanes(max_steps)
+            assert (oracle.status_from_masks(conflict, unsettled, n_lanes) == status).all(), (trial, max_steps)
+            rv, rm = lanes.get_all(nl.n_wires)
+            gv, gm = sim.gather_wires_host(np.arange(nl.n_wires, dtype=np.uint32))
+            assert (((gv ^ rv) | (gm ^ rm)) & mask).max(initial=0) == 0, (trial, max_steps)

@@ -15,10 +15,13 @@ pytestmark = pytest.mark.gpu
 Z, X, L0, L1 = (0, 0), (1, 0), (0, 1), (1, 1)
 
 
-def both(nl: Netlist, n_lanes: int, resident: bool = True):
+def both(nl: Netlist, n_lanes: int, resident=True):
+    """resident: True = shared-memory kernel, False = HBM path with the device-side loop, "host" = HBM path with the
+    host-driven loop."""
     ob = nl.replay(oracle.Builder())
     sim = nl.replay(SimulatorBuilder()).build()
-    sim.set_option(sim.OPT_RESIDENT_KERNEL, int(resident))
+    sim.set_option(sim.OPT_RESIDENT_KERNEL, int(resident is True))
+    sim.set_option(sim.OPT_DEVICE_LOOP, int(resident != "host"))
     sim.set_lanes(n_lanes)
     return ob, sim
 
@@ -85,7 +88,7 @@ def test_single_lane_gsim_surface():
 @pytest.mark.parametrize("seed", range(4))
 @pytest.mark.parametrize("cyclic", [False, True])
 @pytest.mark.parametrize("n_lanes", [1, 100, 64 * 37])
-@pytest.mark.parametrize("resident", [True, False])
+@pytest.mark.parametrize("resident", [True, False, "host"])
 def test_random_netlists_vs_scalar_oracle(seed, cyclic, n_lanes, resident):
     """Random netlists (n-ary gates and muxes included), 4-state stimulus, warm restarts and a
     max_steps sweep that crosses the levelised/unit-delay switch."""
@@ -109,7 +112,7 @@ def test_random_netlists_vs_scalar_oracle(seed, cyclic, n_lanes, resident):
         rv, rm = lanes.get_all(nl.n_wires)
         compare_all_wires(sim, rv, rm, nl.n_wires, n_lanes)
         modes.add(sim.info.last_mode)
-    assert (3 in modes) == resident and (2 in modes) == (not resident), modes
+    assert (3 in modes) == (resident is True) and (2 in modes) == (resident is not True), modes
 
 
 @pytest.mark.parametrize("n_lanes,n_gates", [(64 * 64, 3000), (64 * 600, 500)])

@@ -13,25 +13,26 @@ from helpers import Netlist, bus_enable_drives, lane_mask, random_bus_netlist, r
 pytestmark = pytest.mark.gpu
 
 Z, X, L0, L1 = (0, 0), (1, 0), (0, 1), (1, 1)
-PATHS = [("resident", 1, 1), ("hbm-frontier", 0, 1), ("hbm-dense", 0, 0)]
+PATHS = [("resident", 1, 1, 1), ("hbm-device-loop", 0, 1, 1), ("hbm-host-loop", 0, 1, 0), ("hbm-dense", 0, 0, 0)]
 
 
-def engine(nl, n_lanes, resident, frontier):
+def engine(nl, n_lanes, resident, frontier, device_loop=1):
     sim = nl.replay(SimulatorBuilder()).build()
     sim.set_option(sim.OPT_RESIDENT_KERNEL, resident)
     sim.set_option(sim.OPT_FRONTIER, frontier)
+    sim.set_option(sim.OPT_DEVICE_LOOP, device_loop)
     sim.set_lanes(n_lanes)
     return sim
 
 
-@pytest.mark.parametrize("path,resident,frontier", PATHS)
-def test_buffer_truth_table(path, resident, frontier):
+@pytest.mark.parametrize("path,resident,frontier,device_loop", PATHS)
+def test_buffer_truth_table(path, resident, frontier, device_loop):
     nl = Netlist()
     d, e, o = nl.add_wire(), nl.add_wire(), nl.add_wire()
     nl.add_buffer(d, e, o)
     states = [Z, X, L0, L1]
     pack = lambda f, plane: np.array([sum(states[f(i)][plane] << i for i in range(16))], np.uint64)
-    sim = engine(nl, 16, resident, frontier)
+    sim = engine(nl, 16, resident, frontier, device_loop)
     bs = oracle.BitSliced(nl.replay(oracle.Builder()), 16, 3)
     for wire, f in ((d, lambda i: i // 4), (e, lambda i: i % 4)):
         sim.set_wire_drive_lanes(wire, pack(f, 0), pack(f, 1))
@@ -66,8 +67,8 @@ def test_buffer_validation_and_wide_buffer():
     assert sim.get_wire_state(o8) == LogicState(0, 0)
 
 
-@pytest.mark.parametrize("path,resident,frontier", PATHS)
-def test_shared_bus_single_lane(path, resident, frontier):
+@pytest.mark.parametrize("path,resident,frontier,device_loop", PATHS)
+def test_shared_bus_single_lane(path, resident, frontier, device_loop):
     """The scalar oracle's bus scenario (tests/test_tristate.py) replayed call for call."""
     def make(b):
         d0, d1, e0, e1, bus, nb = (b.add_wire() for _ in range(6))
@@ -84,6 +85,7 @@ def test_shared_bus_single_lane(path, resident, frontier):
     sim = gb.build()
     sim.set_option(sim.OPT_RESIDENT_KERNEL, resident)
     sim.set_option(sim.OPT_FRONTIER, frontier)
+    sim.set_option(sim.OPT_DEVICE_LOOP, device_loop)
     d0, d1, e0, e1, bus, nb = w
     script = [
         [(d0, L1), (d1, L0), (e0, L1), (e1, L0)],
@@ -108,15 +110,15 @@ def test_shared_bus_single_lane(path, resident, frontier):
     assert results == [0, 0, 0, 0, 0, 0, 2]
 
 
-@pytest.mark.parametrize("path,resident,frontier", PATHS)
-def test_transient_conflict_lanes(path, resident, frontier):
+@pytest.mark.parametrize("path,resident,frontier,device_loop", PATHS)
+def test_transient_conflict_lanes(path, resident, frontier, device_loop):
     nl = Netlist()
     d0, d1, en, nen, bus = (nl.add_wire() for _ in range(5))
     nl.add_not_gate(en, nen)
     nl.add_buffer(d0, en, bus)
     nl.add_buffer(d1, nen, bus)
     n_lanes = 200
-    sim = engine(nl, n_lanes, resident, frontier)
+    sim = engine(nl, n_lanes, resident, frontier, device_loop)
     bs = oracle.BitSliced(nl.replay(oracle.Builder()), n_lanes, 5)
     words = bs.words
     ones, zeros = np.full(words, (1 << 64) - 1, np.uint64), np.zeros(words, np.uint64)
@@ -139,15 +141,15 @@ def test_transient_conflict_lanes(path, resident, frontier):
 @pytest.mark.parametrize("seed", range(5))
 @pytest.mark.parametrize("cyclic", [False, True])
 @pytest.mark.parametrize("n_lanes", [100, 64 * 9])
-@pytest.mark.parametrize("path,resident,frontier", PATHS)
-def test_random_bus_netlists_vs_bitsliced(seed, cyclic, n_lanes, path, resident, frontier):
+@pytest.mark.parametrize("path,resident,frontier,device_loop", PATHS)
+def test_random_bus_netlists_vs_bitsliced(seed, cyclic, n_lanes, path, resident, frontier, device_loop):
     """Random netlists with multi-driver buses: per-lane run result and every wire against the dense CPU
     model (itself checked against the event-driven restatement in tests/test_tristate.py), over warm
     restarts and a max_steps sweep.  Lanes that have conflicted are out of contract from then on."""
     rng = np.random.default_rng(9000 + 10 * seed + cyclic)
     n_in, n_gates, n_bus = 6, 40, 5
     nl, first_in, groups = random_bus_netlist(rng, n_in, n_gates, n_bus, cyclic=cyclic)
-    sim = engine(nl, n_lanes, resident, frontier)
+    sim = engine(nl, n_lanes, resident, frontier, device_loop)
     bs = oracle.BitSliced(nl.replay(oracle.Builder()), n_lanes, nl.n_wires)
     words = bs.words
     m = lane_mask(n_lanes)
