@@ -103,10 +103,12 @@ def config4(args):
     from digilogic_b200 import SimulationRunResult, SimulatorBuilder, netgen
     bits, chains, latches = args.bits, args.chains, args.latches
     n_lanes = args.lanes
-    seq = netgen.sequential(n_latches=latches, n_chains=chains, bits=bits, n_hazard=0)
+    seq = netgen.sequential(n_latches=latches, n_chains=chains, bits=bits, n_hazard=args.hazard)
+    ok_results = (SimulationRunResult.Ok,) if args.hazard == 0 else (SimulationRunResult.Ok, SimulationRunResult.MaxStepsReached)
     taps = [bits - 1, bits - 2, bits - 4, bits - 5]
     sim = seq.emit(SimulatorBuilder()).build()
     sim.set_option(sim.OPT_RESIDENT_KERNEL, 0 if args.no_resident else 1)
+    sim.set_option(sim.OPT_DEVICE_LOOP, 0 if args.host_loop else 1)
     sim.set_lanes(n_lanes)
     words = (n_lanes + 63) // 64
     ones, zeros = np.full(words, ALL1, np.uint64), np.zeros(words, np.uint64)
@@ -122,10 +124,10 @@ def config4(args):
 
     def run():
         res, _, _ = sim.run_sim_lanes(10_000, masks=False)
-        assert res == SimulationRunResult.Ok
+        assert res in ok_results
         if lanes is not None:
             status, _, _ = lanes.run(10_000)
-            assert (status == 0).all()
+            assert int(status.max()) <= int(res)
         return sim.info.last_applications
 
     drive(seq.clk, zeros, ones)
@@ -139,6 +141,7 @@ def config4(args):
     run()
     sim.synchronize()
     apps = 0
+    unsettled_runs = 0
     t_gpu = 0.0
     for step in range(args.clocks):
         for level in (ones, zeros):
@@ -146,11 +149,12 @@ def config4(args):
             t0 = time.perf_counter()
             res, _, _ = sim.run_sim_lanes(10_000, masks=False)
             t_gpu += time.perf_counter() - t0
-            assert res == SimulationRunResult.Ok
+            assert res in ok_results
+            unsettled_runs += res == SimulationRunResult.MaxStepsReached
             apps += sim.info.last_applications
             if lanes is not None:
                 status, _, _ = lanes.run(10_000)
-                assert (status == 0).all()
+                assert int(status.max()) <= int(res)
     # every lane, every chain: state after `clocks` clock edges == software LFSR of its start pattern
     lane_ids = np.arange(n_lanes)
     bad = 0
@@ -179,6 +183,7 @@ def config4(args):
                       "applications_total": apps, "seconds_in_run_sim": t_gpu, "ms_per_run_sim": 1e3 * t_gpu / runs,
                       "gate_lane_evals_per_s": seq.n_gates * n_lanes * runs / t_gpu,
                       "gate_lane_steps_per_s": seq.n_gates * n_lanes * apps / t_gpu, "mode": info.last_mode,
+                      "hazard_latches": args.hazard, "runs_ending_max_steps_reached": int(unsettled_runs),
                       "lfsr_mismatches": int(bad), "lanes_checked_vs_software_lfsr": int(len(sample_lanes)),
                       "oracle_lanes": 0 if lanes is None else n_oracle, "all_wires_equal_oracle": oracle_ok}))
     assert bad == 0 and oracle_ok in (None, True)
@@ -263,6 +268,8 @@ def main():
     ap.add_argument("--chains", type=int, default=64)
     ap.add_argument("--latches", type=int, default=4096)
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--hazard", type=int, default=0, help="config 4: latches whose S'/R' can rise together (lanes that oscillate until max_steps)")
+    ap.add_argument("--host-loop", action="store_true", help="config 4: B2_OPT_DEVICE_LOOP = 0")
     ap.add_argument("--no-resident", action="store_true")
     args = ap.parse_args()
     if args.lanes is None:
