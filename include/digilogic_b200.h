@@ -176,7 +176,10 @@ uint64_t b2_sim_max_lanes(const b2_sim *s, uint64_t bytes);
 
 /* LogicState::from_bit_planes(&p0[..words], &p1[..words]) + Simulator::set_wire_drive(wire, &state)
    (lib.rs:194-214).  plane words are little-endian u32, missing words are High-Z.  With more
-   than one lane the drive is applied to every lane. */
+   than one lane the drive is applied to every lane.  Like gsim's, the call is a host-side write: the
+   drive is validated and queued, and reaches the device in one upload + one launch before the next
+   run (or before any other drive setter, so the call order still decides); the last drive per wire
+   wins.  A device error of that deferred upload is reported by the run. */
 int b2_set_wire_drive(b2_sim *s, uint32_t wire, const uint32_t *plane0, const uint32_t *plane1, size_t words);
 
 /* Simulator::run_sim(max_steps)  (lib.rs:216-219).  Returns b2_run_result of lane 0 when one
@@ -184,7 +187,10 @@ int b2_set_wire_drive(b2_sim *s, uint32_t wire, const uint32_t *plane0, const ui
 int b2_run_sim(b2_sim *s, uint64_t max_steps);
 
 /* Simulator::get_wire_state(wire) + LogicState::to_bit_planes(width)  (lib.rs:228-230): lane 0.
-   Writes ceil(width/32) words per plane; `words` is the capacity of each buffer. */
+   Writes ceil(width/32) words per plane; `words` is the capacity of each buffer.  The reference reads
+   every net back after each eval, one call per net (netcode server.rs:375-383): the first call after a
+   run takes a bit-packed snapshot of lane 0 of all wires (one launch + one copy), later calls are host
+   reads of that snapshot. */
 int b2_get_wire_state(b2_sim *s, uint32_t wire, uint32_t *plane0, uint32_t *plane1, size_t words);
 
 /* ---- batch-lane extension (no reference counterpart: gsim has one lane per Simulator) ---- */

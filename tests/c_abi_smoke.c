@@ -43,6 +43,30 @@ int main(void) {
     b2_sim_free(s);
     b2_builder_free(b);
 
+    /* two tri-state buffers on one bus (gsim add_buffer): hand-over, floating bus, conflict */
+    b = b2_builder_new();
+    uint32_t d0, d1, e0, e1, bus;
+    CHECK(b2_add_wire(b, 1, &d0) == B2_OK && b2_add_wire(b, 1, &d1) == B2_OK && b2_add_wire(b, 1, &e0) == B2_OK);
+    CHECK(b2_add_wire(b, 1, &e1) == B2_OK && b2_add_wire(b, 1, &bus) == B2_OK);
+    CHECK(b2_add_buffer(b, d0, e0, 99, &cell) == B2_ERR_INVALID_WIRE_ID);
+    CHECK(b2_add_buffer(b, d0, e0, bus, &cell) == B2_OK && b2_add_buffer(b, d1, e1, bus, &cell) == B2_OK);
+    s = b2_build(b);
+    CHECK(s != NULL && b2_sim_get_info(s, &info) == B2_OK && info.cyclic); /* tri-state nets: unit-delay path only */
+    CHECK(b2_set_wire_drive(s, d0, &one, &one, 1) == B2_OK && b2_set_wire_drive(s, d1, &zero, &one, 1) == B2_OK);
+    CHECK(b2_set_wire_drive(s, e0, &one, &one, 1) == B2_OK && b2_set_wire_drive(s, e1, &zero, &one, 1) == B2_OK);
+    CHECK(b2_run_sim(s, 100) == B2_RUN_OK);
+    CHECK(b2_get_wire_state(s, bus, &p0, &p1, 1) == B2_OK && p0 == 1 && p1 == 1);
+    CHECK(b2_set_wire_drive(s, e0, &zero, &one, 1) == B2_OK && b2_set_wire_drive(s, e1, &one, &one, 1) == B2_OK);
+    CHECK(b2_run_sim(s, 100) == B2_RUN_OK);
+    CHECK(b2_get_wire_state(s, bus, &p0, &p1, 1) == B2_OK && p0 == 0 && p1 == 1);
+    CHECK(b2_set_wire_drive(s, e1, &zero, &one, 1) == B2_OK);
+    CHECK(b2_run_sim(s, 100) == B2_RUN_OK);
+    CHECK(b2_get_wire_state(s, bus, &p0, &p1, 1) == B2_OK && p0 == 0 && p1 == 0); /* nobody drives: High-Z */
+    CHECK(b2_set_wire_drive(s, e0, &one, &one, 1) == B2_OK && b2_set_wire_drive(s, e1, &one, &one, 1) == B2_OK);
+    CHECK(b2_run_sim(s, 100) == B2_RUN_CONFLICT);
+    b2_sim_free(s);
+    b2_builder_free(b);
+
     /* the SimServer mirror: a NAND latch driven like the GUI client drives it */
     b2_server *sv = b2_server_new();
     const uint64_t id = 42;
