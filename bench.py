@@ -22,6 +22,8 @@ roofline   = k_eval2 (the per-level gate kernel): 48 algorithmic bytes per gate 
 cpu_baseline = the scalar event-driven gsim restatement (oracle/gsim_oracle.c, "port") on the
              host cores over a bounded lane sample of the same netlist
 valid_elision = secondary figure (never the headline): the same job with B2_OPT_VALID_ELISION
+unit_delay = secondary figure: BASELINE config 4 (flip-flop LFSR chains + SR latches, feedback) on the
+             unit-delay path — 65 536 lanes, 20 clocked steps = 40 run_sim(10_000) calls, wall time of the calls
 """
 from __future__ import annotations
 
@@ -68,6 +70,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-elision-probe", action="store_true", help="skip the secondary run with B2_OPT_VALID_ELISION")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-unit-delay-probe", action="store_true", help="skip the secondary config-4 (feedback) run")
     return ap.parse_args()
 
 
@@ -364,6 +367,10 @@ def run_b200(args):
         e2e = run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words_local, w_begin, barrier,
                       (out_v, out_m))
 
+    unit_delay = None
+    if rank == 0 and world == 1 and not args.no_unit_delay_probe:
+        unit_delay = unit_delay_probe(args)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
@@ -380,12 +387,67 @@ def run_b200(args):
             "dtype": "u64 bit-planes (value+valid)", "data": "synthetic",
             "config": config_dict(args, world, {"tiles_per_step": n_tiles, "row_stride_words": info.row_stride,
                                                 "store_bytes": info.store_bytes * len(sims), "compile_s": round(compile_s, 3)}),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "valid_elision": elision, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "valid_elision": elision, "unit_delay": unit_delay, "gpu_launches": int(launches), "clocks": clocks,
             "output_checksum": f"{checksum:#018x}",
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def unit_delay_probe(args, n_lanes=65536, clocks=20):
+    """BASELINE config 4 at full netlist size on the unit-delay path (feedback: latches and flip-flops), a short
+    clocked run; every lane's LFSR state is checked against a software LFSR afterwards."""
+    import time
+    import numpy as np
+    from digilogic_b200 import SimulationRunResult, SimulatorBuilder, netgen
+    bits = chains = 64
+    seq = netgen.sequential(n_latches=4096, n_chains=chains, bits=bits, n_hazard=0)
+    taps = [bits - 1, bits - 2, bits - 4, bits - 5]
+    sim = seq.emit(SimulatorBuilder()).build()
+    sim.set_lanes(n_lanes)
+    words = n_lanes // 64
+    all1 = np.uint64(0xFFFFFFFFFFFFFFFF)
+    ones, zeros = np.full(words, all1, np.uint64), np.zeros(words, np.uint64)
+    rng = np.random.default_rng(4)
+    patterns = [rng.integers(0, 1 << 64, words, dtype=np.uint64) for _ in range(bits)]
+    sim.set_wire_drive_lanes(seq.clk, zeros, ones)
+    for b in range(bits):
+        sim.set_wire_drive_lanes(seq.preset_n[b], ~patterns[b], ones)
+        sim.set_wire_drive_lanes(seq.clear_n[b], patterns[b], ones)
+    sim.run_sim_lanes(args.max_steps, masks=False)
+    for b in range(bits):
+        sim.set_wire_drive_lanes(seq.preset_n[b], ones, ones)
+        sim.set_wire_drive_lanes(seq.clear_n[b], ones, ones)
+    sim.run_sim_lanes(args.max_steps, masks=False)
+    sim.synchronize()
+    apps, t = 0, 0.0
+    for _ in range(clocks):
+        for level in (ones, zeros):
+            sim.set_wire_drive_lanes(seq.clk, level, ones)
+            t0 = time.perf_counter()
+            res, _, _ = sim.run_sim_lanes(args.max_steps, masks=False)   # returns when the run has settled on the device
+            t += time.perf_counter() - t0
+            assert res == SimulationRunResult.Ok
+            apps += sim.info.last_applications
+    # lane-word 0 of chain 0 against a software Fibonacci LFSR
+    q = np.stack([np.unpackbits(sim.get_wire_lanes(seq.q[0][b])[0][:1].view(np.uint8), bitorder="little") for b in range(bits)])
+    start = np.stack([np.unpackbits(patterns[b][:1].view(np.uint8), bitorder="little") for b in range(bits)])
+    ok = True
+    for lane in range(64):
+        st = sum(int(start[b][lane]) << b for b in range(bits))
+        for _ in range(clocks):
+            fb = 0
+            for tp in taps:
+                fb ^= (st >> tp) & 1
+            st = ((st << 1) | fb) & ((1 << bits) - 1)
+        ok &= st == sum(int(q[b][lane]) << b for b in range(bits))
+    runs = 2 * clocks
+    return {"workload": f"BASELINE config 4: {chains} LFSR chains x {bits} NAND flip-flops + 4096 SR latches ({seq.n_gates} gates, feedback), "
+                        f"{n_lanes} lanes, {clocks} clocked steps = {runs} run_sim({args.max_steps}) calls",
+            "value": seq.n_gates * n_lanes * runs / t, "unit": UNIT, "ms_per_run_sim": 1e3 * t / runs,
+            "gate_lane_steps_per_s": seq.n_gates * n_lanes * apps / t, "applications": int(apps),
+            "lfsr_state_matches_software": bool(ok)}
 
 
 def run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words_local, w_begin, barrier, dev_out):

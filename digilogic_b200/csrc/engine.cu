@@ -877,6 +877,7 @@ struct LoopArgs {
     uint8_t *chg[2];
     uint4 *list2, *list3;
     uint32_t *listc;
+    uint32_t *cnt;  // list counters, [2][4]: application parity x {one/two-input, three-input, refresh, -}; zero on entry
     uint64_t *changed, *conf_step, *live, *conflict, *unsettled;
     RunFlags *flags;  // kFlagSlots slots, all clear on entry
     LoopResult *result;
@@ -893,27 +894,24 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
     const uint32_t lt = threadIdx.y * blockDim.x + threadIdx.x;  // linear thread id: warps are 32 consecutive ones
     uint64_t k = a.k0;
     int cur = a.cur, cw = a.chg_w;
-    bool fv = a.frontier_valid != 0, bailed = false;
+    bool bailed = false;
     const uint64_t first_k = k + 1;
+    // The work lists of application k are built at the end of application k-1 (their counters: a.cnt + 4 * (k & 1)),
+    // so an application is two grid barriers: [drives, listed gates, refresh copies, wide gates] | [tri-state resolve |]
+    // [lane bookkeeping, flag clean-up, scan for the next application].  Prologue: the scan for the first one.
+    for (uint32_t base = bid * 256; base < a.n_fast; base += nblk * 256)
+        frontier_scan_body(a.fan0, a.fan1, a.fan2, a.n_g2, a.n_fast, a.n_src, a.kind2, a.frontier_valid ? a.chg[cw ^ 1] : nullptr,
+                           a.list2, a.list3, a.listc, a.cnt + 4 * (first_k & 1), lt, base + lt);
+    grid.sync();
     for (;;) {
         k++;
         const bool is_last = k == a.last;
         const uint64_t *AV = a.val[cur], *AM = a.vld[cur];
         uint64_t *BV = a.val[cur ^ 1], *BM = a.vld[cur ^ 1];
         uint8_t *chg_cur = a.chg[cw];
-        const uint8_t *chg_prev = fv ? a.chg[cw ^ 1] : nullptr;
-        uint32_t *counts = (uint32_t *)(chg_cur + a.rowchg_bytes - 16);
+        const uint8_t *chg_prev = (k > first_k || a.frontier_valid) ? a.chg[cw ^ 1] : nullptr;
+        const uint32_t *counts = a.cnt + 4 * (k & 1);
         RunFlags *flags = a.flags + (k % 8);
-
-        // ---- phase 1: drives (they cannot change inside a run: two applications fill both buffers), frontier scan
-        if (a.n_src && k < first_k + 2)
-            for (uint32_t rb = gbi; rb * blockDim.y < a.n_src; rb += gbs)
-                apply_drive_body<true>(a.drv_val, a.drv_vld, AV, AM, BV, BM, a.changed, a.n_src, a.stride, a.pairs, nullptr, 0, chg_cur,
-                                       pb, rb);
-        for (uint32_t base = bid * 256; base < a.n_fast; base += nblk * 256)
-            frontier_scan_body(a.fan0, a.fan1, a.fan2, a.n_g2, a.n_fast, a.n_src, a.kind2, chg_prev, a.list2, a.list3, a.listc, counts,
-                               lt, base + lt);
-        grid.sync();
         if (k > first_k) {  // a long work list is better served by the separate, fully occupied kernels
             const uint64_t listed = (uint64_t)counts[0] + counts[1] + counts[2];
             if (listed * a.stride > a.bail_row_words) {
@@ -923,7 +921,13 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
             }
         }
 
-        // ---- phase 2: the listed gates, the rows to refresh, the wide gates
+        // ---- phase A: drives (they cannot change inside a run: two applications fill both buffers), the listed
+        //      gates, the rows to refresh, the wide gates
+        if (a.n_src && k < first_k + 2)
+            for (uint32_t rb = gbi; rb * blockDim.y < a.n_src; rb += gbs)
+                apply_drive_body<true>(a.drv_val, a.drv_vld, AV, AM, BV, BM, a.changed, a.n_src, a.stride, a.pairs, nullptr, 0, chg_cur,
+                                       pb, rb);
+        if (bid == 0 && lt < 4) a.cnt[4 * ((k + 1) & 1) + lt] = 0;  // counters of the next application (last read an application ago)
         {
             Eval2Args e{a.fan0, a.fan1, a.fan2, a.kind2, AV, AM, BV, BM, a.changed, 0, a.n_fast, a.n_src, a.stride, a.pairs,
                         a.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
@@ -946,7 +950,8 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
             grid.sync();
         }
 
-        // ---- phase 3: lane bookkeeping; the flags of the previous application become the clean buffer of the next
+        // ---- phase B: lane bookkeeping; the flags of the previous application become the clean buffer of the next;
+        //      the work lists of the next application from the flags of this one
         for (uint32_t base = bid * 256; base < a.stride; base += nblk * 256)
             status_step_body(a.changed, a.conf_step, a.live, a.conflict, a.unsettled, flags, a.stride, a.n_lanes, is_last ? 0 : 1,
                              is_last ? 1 : 0, base + lt, lt & 31);
@@ -960,9 +965,12 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
             nf->any_conflict = 0;
             nf->any_unsettled = 0;
         }
+        if (!is_last)
+            for (uint32_t base = bid * 256; base < a.n_fast; base += nblk * 256)
+                frontier_scan_body(a.fan0, a.fan1, a.fan2, a.n_g2, a.n_fast, a.n_src, a.kind2, chg_cur, a.list2, a.list3, a.listc,
+                                   a.cnt + 4 * ((k + 1) & 1), lt, base + lt);
         grid.sync();
         const uint32_t any_live = *(volatile uint32_t *)&flags->any_live;
-        fv = true;
         cw ^= 1;
         if (is_last) break;  // check-only application: the state stays W_{N+1}
         cur ^= 1;
@@ -1423,7 +1431,7 @@ int Engine::ensure_device() {
         CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_unit_delay_loop, 256, 0));
         loop_ctas_ = coop ? (uint32_t)(std::min(occ, 2) * sm_count_) : 0;
-        CU_TRY(cudaMalloc((void **)&d_loop_result_, sizeof(LoopResult)));
+        CU_TRY(cudaMalloc((void **)&d_loop_result_, sizeof(LoopResult) + 8 * sizeof(uint32_t)));
         CU_TRY(cudaMallocHost((void **)&h_loop_result_, sizeof(LoopResult)));
     }
     // the kernels are built for sm_100a only: fail loudly on anything else
@@ -2077,6 +2085,8 @@ int Engine::run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &res
     }
     la.drv_val = drv_val_; la.drv_vld = drv_vld_;
     la.list2 = (uint4 *)d_act_list_[0]; la.list3 = (uint4 *)d_act_list_[1]; la.listc = d_act_list_[2];
+    la.cnt = (uint32_t *)(d_loop_result_ + 1);  // behind the result block
+    CU_TRY(cudaMemsetAsync(la.cnt, 0, 8 * sizeof(uint32_t), ST));
     la.changed = d_changed_; la.conf_step = d_conf_step_; la.live = d_live_; la.conflict = d_conflict_; la.unsettled = d_unsettled_;
     la.flags = d_flags_;
     la.result = d_loop_result_;
