@@ -82,6 +82,20 @@ int b2_add_buffer(b2_builder *b, uint32_t input, uint32_t enable, uint32_t outpu
     GUARD_END(B2_ERR_OUT_OF_MEMORY)
 }
 
+int b2_add_slice(b2_builder *b, uint32_t input, uint32_t offset, uint32_t output, uint32_t *out_cell) {
+    if (!b) return B2_ERR_NULL;
+    GUARD_BEGIN
+    return b->b.add_slice(input, offset, output, out_cell);
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
+int b2_add_merge(b2_builder *b, const uint32_t *inputs, size_t n, uint32_t output, uint32_t *out_cell) {
+    if (!b || (n && !inputs)) return B2_ERR_NULL;
+    GUARD_BEGIN
+    return b->b.add_merge(inputs, n, output, out_cell);
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
 int b2_add_mux(b2_builder *b, const uint32_t *inputs, size_t n, uint32_t select, uint32_t output, uint32_t *out_cell) {
     if (!b || (n && !inputs)) return B2_ERR_NULL;
     GUARD_BEGIN

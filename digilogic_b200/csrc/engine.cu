@@ -112,6 +112,10 @@ __device__ __forceinline__ void gate_word(uint32_t kind, u64 av, u64 am, u64 bv,
             rv = (en1 & (av | ~am)) | ~bm;
             return;
         }
+        case K_COPY:  // one bit of a slice / merge: the input, High-Z read as X
+            rm = am;
+            rv = av | ~am;
+            return;
         default:  // K_NOT (single input)
             m = am;
             v = av;

@@ -79,6 +79,25 @@ int Builder::add_buffer(uint32_t in, uint32_t enable, uint32_t output, uint32_t 
     return push(*this, K_BUF, both, 2, 0, output, cell);
 }
 
+// gsim SimulatorBuilder::add_slice / add_merge (bit re-wiring; no call site in the reference, but
+// `OffsetOutOfRange` of its error map, crates/digilogic_gsim/src/lib.rs:55-66, belongs to add_slice)
+int Builder::add_slice(uint32_t in, uint32_t offset, uint32_t output, uint32_t *cell) {
+    if (output >= width.size() || in >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    if ((uint64_t)offset + width[output] > width[in]) return B2_ERR_OFFSET_OUT_OF_RANGE;
+    return push(*this, K_SLICE, &in, 1, offset, output, cell);
+}
+
+int Builder::add_merge(const uint32_t *in, size_t n, uint32_t output, uint32_t *cell) {
+    if (output >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    for (size_t i = 0; i < n; i++)
+        if (in[i] >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    if (n < 1) return B2_ERR_TOO_FEW_INPUTS;
+    size_t total = 0;
+    for (size_t i = 0; i < n; i++) total += width[in[i]];
+    if (total != width[output]) return B2_ERR_WIRE_WIDTH_MISMATCH;
+    return push(*this, K_MERGE, in, n, 0, output, cell);
+}
+
 // ---------------------------------------------------------------------------- compiler
 
 namespace {
@@ -127,6 +146,14 @@ void compile(const Builder &b, Compiled &c) {
             if (cp.kind == K_BUF) {
                 bin.push_back(c.bit_off[in[0]] + j);  // data bit j
                 bin.push_back(c.bit_off[in[1]]);      // the one enable bit
+            } else if (cp.kind == K_SLICE) {
+                g.kind = K_COPY;
+                bin.push_back(c.bit_off[in[0]] + cp.select + j);
+            } else if (cp.kind == K_MERGE) {
+                g.kind = K_COPY;
+                uint32_t k = 0, lo = 0;  // the input that holds output bit j
+                while (lo + b.width[in[k]] <= j) lo += b.width[in[k++]];
+                bin.push_back(c.bit_off[in[k]] + (j - lo));
             } else {
                 for (uint32_t i = 0; i < cp.n_inputs; i++) bin.push_back(c.bit_off[in[i]] + j);
             }

@@ -13,14 +13,16 @@ namespace b2 {
 
 enum Kind : uint8_t {
     K_AND = 0, K_OR = 1, K_XOR = 2, K_NAND = 3, K_NOR = 4, K_XNOR = 5, K_NOT = 6, K_MUX = 7,
-    K_BUF = 8  // tri-state buffer: inputs = {data, enable}; the only component whose output can be High-Z
+    K_BUF = 8,   // tri-state buffer: inputs = {data, enable}; the only component whose output can be High-Z
+    K_COPY = 9,  // one bit of a slice / merge: output = input, High-Z read as X
+    K_SLICE = 10, K_MERGE = 11  // builder-level only (bit-blasted into K_COPY)
 };
 
 struct Component {
     uint8_t kind;
     uint32_t n_inputs;  // data inputs
     uint32_t in_off;    // into Builder::inputs
-    uint32_t select;    // mux only
+    uint32_t select;    // mux: select wire; slice: bit offset
     uint32_t output;
 };
 
@@ -35,6 +37,8 @@ struct Builder {
     int add_not(uint32_t in, uint32_t output, uint32_t *cell);
     int add_mux(const uint32_t *in, size_t n, uint32_t select, uint32_t output, uint32_t *cell);
     int add_buffer(uint32_t in, uint32_t enable, uint32_t output, uint32_t *cell);
+    int add_slice(uint32_t in, uint32_t offset, uint32_t output, uint32_t *cell);
+    int add_merge(const uint32_t *in, size_t n, uint32_t output, uint32_t *cell);
 };
 
 // One level of the levelised order: one/two-input gates [g2_begin, g2_end), three-input gates

@@ -177,6 +177,19 @@ class SimulatorBuilder:
         _check(self._lib.b2_add_buffer(self._h, input, enable, output, C.byref(cell)), "add_buffer")
         return cell.value
 
+    def add_slice(self, input, offset, output):
+        """gsim ``SimulatorBuilder::add_slice``: output = input[offset .. offset + width(output))."""
+        cell = C.c_uint32()
+        _check(self._lib.b2_add_slice(self._h, input, offset, output, C.byref(cell)), "add_slice")
+        return cell.value
+
+    def add_merge(self, inputs, output):
+        """gsim ``SimulatorBuilder::add_merge``: output = inputs concatenated, inputs[0] in the low bits."""
+        arr = (C.c_uint32 * len(inputs))(*inputs)
+        cell = C.c_uint32()
+        _check(self._lib.b2_add_merge(self._h, arr, len(inputs), output, C.byref(cell)), "add_merge")
+        return cell.value
+
     def add_gates2(self, kinds, in0, in1, out):
         """Bulk add of one/two-input gates (batch extension)."""
         kinds = np.ascontiguousarray(kinds, np.uint8)

@@ -97,6 +97,14 @@ int b2_add_mux(b2_builder *b, const uint32_t *inputs, size_t n, uint32_t select,
    always run the unit-delay path.  Errors: InvalidWireId, WireWidthMismatch (input vs output),
    WireWidthIncompatible (enable wider than one bit). */
 int b2_add_buffer(b2_builder *b, uint32_t input, uint32_t enable, uint32_t output, uint32_t *out_cell);
+/* SimulatorBuilder::add_slice(input, offset, output) and add_merge(inputs, output) — bit re-wiring components of
+   gsim, one step of delay like every component, High-Z input bits read as X (no call site in the reference;
+   `OffsetOutOfRange` of its error map, lib.rs:55-66, belongs to add_slice).
+   slice: output = input[offset .. offset + width(output)); OffsetOutOfRange when that exceeds the input.
+   merge: output = inputs concatenated, inputs[0] in the low bits; TooFewInputs for none, WireWidthMismatch
+   when the widths do not add up to the output's. */
+int b2_add_slice(b2_builder *b, uint32_t input, uint32_t offset, uint32_t output, uint32_t *out_cell);
+int b2_add_merge(b2_builder *b, const uint32_t *inputs, size_t n, uint32_t output, uint32_t *out_cell);
 /* Batch extension: n one- or two-input gates at once (kinds[i] in B2_AND..B2_NOT; in1 ignored
    for B2_NOT), validated exactly like the single calls; stops at the first error. */
 int b2_add_gates2(b2_builder *b, const uint8_t *kinds, const uint32_t *in0, const uint32_t *in1, const uint32_t *out, size_t n);

@@ -26,6 +26,8 @@ extern "C" {
     pub fn b2_add_gate(b: *mut B2Builder, kind: c_int, inputs: *const u32, n: usize, output: u32, out_cell: *mut u32) -> c_int; // add_*_gate :95
     pub fn b2_add_not(b: *mut B2Builder, input: u32, output: u32, out_cell: *mut u32) -> c_int; // add_not_gate :165
     pub fn b2_add_buffer(b: *mut B2Builder, input: u32, enable: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_buffer (no call site in digilogic_gsim yet)
+    pub fn b2_add_slice(b: *mut B2Builder, input: u32, offset: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_slice
+    pub fn b2_add_merge(b: *mut B2Builder, inputs: *const u32, n: usize, output: u32, out_cell: *mut u32) -> c_int; // gsim add_merge
     pub fn b2_add_mux(b: *mut B2Builder, inputs: *const u32, n: usize, select: u32, output: u32, out_cell: *mut u32) -> c_int; // add_multiplexer :190
     pub fn b2_build(b: *mut B2Builder) -> *mut B2Sim; // mem::take(builder).build()             :127
     pub fn b2_sim_free(s: *mut B2Sim);

@@ -152,6 +152,10 @@ static inline void eval_comp(const bs_sim *s, const comp_t *cp, const uint64_t *
     } else if (cp->kind == GO_NOT) {
         uint64_t a = wv[(size_t)in[0] * T + k]; m = wm[(size_t)in[0] * T + k];
         v = ~a | ~m;
+    } else if (cp->kind == GO_SLICE || cp->kind == GO_MERGE) {
+        /* 1-bit wires: a slice at offset 0 or a merge of one input is a copy; High-Z reads X */
+        uint64_t a = wv[(size_t)in[0] * T + k]; m = wm[(size_t)in[0] * T + k];
+        v = a | ~m;
     } else if (cp->kind == GO_BUF) {
         /* enable 1: the input, High-Z read as X; enable 0: High-Z (0,0); enable Z/X: X (1,0) */
         uint64_t a = wv[(size_t)in[0] * T + k], am = wm[(size_t)in[0] * T + k];

@@ -30,6 +30,10 @@ def main(cases_path, dump_path):
                 b.add_multiplexer(c["inputs"], c["select"], c["output"])
             elif c["kind"] == "buffer":
                 b.add_buffer(c["inputs"][0], c["inputs"][1], c["output"])
+            elif c["kind"] == "slice":
+                b.add_slice(c["inputs"][0], c["select"], c["output"])
+            elif c["kind"] == "merge":
+                b.add_merge(c["inputs"], c["output"])
             else:
                 b.add_gate(KIND[c["kind"]], c["inputs"], c["output"])
         sim = b.build()

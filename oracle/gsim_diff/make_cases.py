@@ -62,6 +62,12 @@ def cases():
                 "comps": [{"kind": "not", "inputs": [2], "output": 3}, {"kind": "not", "inputs": [3], "output": 4},
                           {"kind": "buffer", "inputs": [0, 3], "output": 5}, {"kind": "buffer", "inputs": [1, 4], "output": 5}],
                 "runs": [{"drives": [drive(0, L1), drive(1, L1), drive(2, L1)], "max_steps": 100}]})
+    # slices and merges (A.6-7: High-Z bits of the input read X): an 8-bit wire cut in two and swapped
+    out.append({"name": "slice_merge_swap", "wires": [8, 3, 5, 8],
+                "comps": [{"kind": "slice", "inputs": [0], "select": 0, "output": 1}, {"kind": "slice", "inputs": [0], "select": 3, "output": 2},
+                          {"kind": "merge", "inputs": [2, 1], "output": 3}],
+                "runs": [{"drives": [[0, [v], [m]]], "max_steps": ms} for v, m, ms in
+                         ((0xA5, 0xFF, 10), (0xFF, 0x0F, 10), (0x00, 0x00, 10), (0x3C, 0xFF, 0), (0x3C, 0xFF, 1))]})
     # random cyclic netlists, max_steps sweep
     rng = np.random.default_rng(1)
     for n in range(4):

@@ -7,7 +7,7 @@ use std::num::NonZeroU8;
 
 #[derive(Deserialize)]
 struct Comp {
-    kind: String, // and | or | xor | nand | nor | xnor | not | mux | buffer (inputs = [data, enable])
+    kind: String, // and | or | xor | nand | nor | xnor | not | mux | buffer (inputs = [data, enable]) | slice (select = offset) | merge
     inputs: Vec<u32>,
     select: Option<u32>,
     output: u32,
@@ -57,6 +57,8 @@ fn main() {
                 "not" => builder.add_not_gate(ins[0], o),
                 "mux" => builder.add_multiplexer(&ins, wires[c.select.unwrap() as usize], o),
                 "buffer" => builder.add_buffer(ins[0], ins[1], o),
+                "slice" => builder.add_slice(ins[0], c.select.unwrap() as u8, o),
+                "merge" => builder.add_merge(&ins, o),
                 k => panic!("unknown kind {k}"),
             };
             build_errors.push(r.err().map(|e| format!("{e:?}")));

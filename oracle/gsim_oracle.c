@@ -39,7 +39,7 @@
 
 #include "gsim_oracle.h"
 
-static go_config_t g_cfg = {0, 0, 0, 0, 0};
+static go_config_t g_cfg = {0, 0, 0, 0, 0, 0};
 
 void go_set_config(int steps_check_ge, int conflict_needs_disagree, int mux_z_passthrough, int initial_undefined) {
     g_cfg.steps_check_ge = steps_check_ge;
@@ -48,6 +48,7 @@ void go_set_config(int steps_check_ge, int conflict_needs_disagree, int mux_z_pa
     g_cfg.initial_undefined = initial_undefined;
 }
 void go_set_buffer_z_passthrough(int on) { g_cfg.buffer_z_passthrough = on; }
+void go_set_copy_z_passthrough(int on) { g_cfg.copy_z_passthrough = on; }
 
 /* ------------------------------------------------------------------ builder */
 
@@ -137,6 +138,24 @@ int go_add_buffer(go_builder *b, uint32_t input, uint32_t enable, uint32_t outpu
     if (b->width[enable] != 1) return GO_ERR_WIRE_WIDTH_INCOMPATIBLE;
     uint32_t in[2] = {input, enable};
     return push_comp(b, GO_BUF, in, 2, 0, output, cell);
+}
+
+/* add_slice(input, offset, output) / add_merge(inputs, output): bit re-wiring components of gsim (no call
+   site in the reference; `OffsetOutOfRange` in the reference's error map, lib.rs:55-66, is theirs). */
+int go_add_slice(go_builder *b, uint32_t input, uint32_t offset, uint32_t output, uint32_t *cell) {
+    if (output >= b->n_wires || input >= b->n_wires) return GO_ERR_INVALID_WIRE_ID;
+    if ((uint64_t)offset + b->width[output] > b->width[input]) return GO_ERR_OFFSET_OUT_OF_RANGE;
+    return push_comp(b, GO_SLICE, &input, 1, offset, output, cell);
+}
+
+int go_add_merge(go_builder *b, const uint32_t *inputs, uint32_t n, uint32_t output, uint32_t *cell) {
+    if (output >= b->n_wires) return GO_ERR_INVALID_WIRE_ID;
+    for (uint32_t i = 0; i < n; i++) if (inputs[i] >= b->n_wires) return GO_ERR_INVALID_WIRE_ID;
+    if (n < 1) return GO_ERR_TOO_FEW_INPUTS;
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < n; i++) total += b->width[inputs[i]];
+    if (total != b->width[output]) return GO_ERR_WIRE_WIDTH_MISMATCH;
+    return push_comp(b, GO_MERGE, inputs, n, 0, output, cell);
 }
 
 /* Bulk 2-input gate add used by the large generators (same validation per gate). */
@@ -329,6 +348,22 @@ static int eval_component(go_sim *s, uint32_t c) {
     } else if (cp->kind == GO_NOT) {
         const atom_t *a = s->state + s->atom_off[in[0]];
         for (uint32_t i = 0; i < na; i++) res[i] = op_not(a[i]);
+    } else if (cp->kind == GO_SLICE || cp->kind == GO_MERGE) {
+        /* bit j of the output = one bit of one input; High-Z bits read X unless A.6-7 says otherwise */
+        for (uint32_t i = 0; i < na; i++) { res[i].state = 0; res[i].valid = 0; }
+        uint32_t j = 0;
+        for (uint32_t k = 0; k < cp->n_inputs; k++) {
+            const atom_t *a = s->state + s->atom_off[in[k]];
+            uint32_t lo = cp->kind == GO_SLICE ? cp->select : 0;
+            uint32_t cnt = cp->kind == GO_SLICE ? width : s->width[in[k]];
+            for (uint32_t t = 0; t < cnt; t++, j++) {
+                uint32_t sb = lo + t;
+                uint32_t st = (a[sb >> 5].state >> (sb & 31)) & 1, vl = (a[sb >> 5].valid >> (sb & 31)) & 1;
+                if (!vl && !g_cfg.copy_z_passthrough) st = 1;
+                res[j >> 5].state |= st << (j & 31);
+                res[j >> 5].valid |= vl << (j & 31);
+            }
+        }
     } else if (cp->kind == GO_BUF) {
         /* enable = 1: the input (High-Z bits read X); enable = 0: High-Z; enable Z/X: Undefined */
         const atom_t *a = s->state + s->atom_off[in[0]];

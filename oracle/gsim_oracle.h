@@ -8,7 +8,9 @@
 typedef struct { uint32_t state, valid; } atom_t;
 
 enum { GO_AND = 0, GO_OR = 1, GO_XOR = 2, GO_NAND = 3, GO_NOR = 4, GO_XNOR = 5, GO_NOT = 6, GO_MUX = 7,
-       GO_BUF = 8 /* tri-state buffer: inputs[0] = data, inputs[1] = 1-bit enable */ };
+       GO_BUF = 8,  /* tri-state buffer: inputs[0] = data, inputs[1] = 1-bit enable */
+       GO_SLICE = 9,  /* output = input[offset .. offset + width(output)); offset in `select` */
+       GO_MERGE = 10  /* output = inputs concatenated, inputs[0] in the low bits */ };
 
 /* AddComponentError ordinals, names pinned by crates/digilogic_gsim/src/lib.rs:55-66 */
 enum {
@@ -32,6 +34,7 @@ typedef struct {
     int mux_z_passthrough;     /* A.6-4: 0 => Z on selected input reads X (default) */
     int initial_undefined;     /* A.6-5: 0 => High-Z initial state (default) */
     int buffer_z_passthrough;  /* A.6-6: 0 => an enabled buffer passes a High-Z input bit on as X (default), 1 => as Z */
+    int copy_z_passthrough;    /* A.6-7: 0 => slices and merges pass a High-Z input bit on as X (default: only buffers output Z) */
 } go_config_t;
 
 typedef struct {

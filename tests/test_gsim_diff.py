@@ -25,6 +25,10 @@ def build(case, builder):
             builder.add_multiplexer(c["inputs"], c["select"], c["output"])
         elif c["kind"] == "buffer":
             builder.add_buffer(c["inputs"][0], c["inputs"][1], c["output"])
+        elif c["kind"] == "slice":
+            builder.add_slice(c["inputs"][0], c["select"], c["output"])
+        elif c["kind"] == "merge":
+            builder.add_merge(c["inputs"], c["output"])
         else:
             builder.add_gate(compare.KIND[c["kind"]], c["inputs"], c["output"])
     return builder.build()
@@ -47,7 +51,7 @@ def oracle_dump(cases):
 
 def test_harness_python_side(tmp_path):
     cases = make_cases.cases()
-    assert len(cases) >= 18
+    assert len(cases) >= 19
     cp, dp = tmp_path / "cases.json", tmp_path / "dump.json"
     cp.write_text(json.dumps(cases))
     dp.write_text(json.dumps(oracle_dump(cases)))
