@@ -112,6 +112,10 @@ __device__ __forceinline__ void gate_word(uint32_t kind, u64 av, u64 am, u64 bv,
             rv = (en1 & (av | ~am)) | ~bm;
             return;
         }
+        case K_RAW:  // hidden raw copy (a register's clock one step ago): High-Z stays High-Z
+            rm = am;
+            rv = av;
+            return;
         case K_COPY:  // one bit of a slice / merge: the input, High-Z read as X
             rm = am;
             rv = av | ~am;
@@ -124,6 +128,18 @@ __device__ __forceinline__ void gate_word(uint32_t kind, u64 av, u64 am, u64 bv,
     if (kind >= K_NAND) v = ~v;
     rv = v | ~m;  // not-valid lanes carry the canonical X = (1,0)
     rm = m;
+}
+
+// One register bit (gsim add_register restated): rising edge = the clock was a valid 0 one step ago
+// (pc) and is a valid 1 now (c); enable 1 loads the data bit (High-Z reads X), enable 0 keeps, enable Z/X makes the stored
+// value Undefined.  The stored value is the register's own row (o); a row that is still High-Z has never been written and
+// stands for the initial Undefined.
+__device__ __forceinline__ void reg_word(u64 dv, u64 dm, u64 ev, u64 em, u64 cv, u64 cm, u64 pcv, u64 pcm, u64 ov, u64 om, u64 &rv,
+                                         u64 &rm) {
+    const u64 edge = pcm & ~pcv & cm & cv;
+    const u64 take = edge & ev & em, keep = ~edge | (edge & ~ev & em), undef = edge & ~em;
+    rm = (take & dm) | (keep & om);
+    rv = (take & (dv | ~dm)) | (keep & (ov | ~om)) | undef;
 }
 
 __device__ __forceinline__ uint64_t lane_mask_of(uint32_t w, uint64_t n_lanes) {
@@ -278,8 +294,10 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
             if (KV && !allv && pb == 0 && threadIdx.x == 0) a.kv[orow[u]] = okv ? 1 : 0;
             if (JACOBI) {
                 const uint64_t ex = (rv.x ^ ov[u].x) | (rm.x ^ om[u].x), ey = (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
-                dx |= ex;
-                dy |= ey;
+                if (kind[u] != K_RAW) {  // a register's clock history is internal state: it keeps no lane alive
+                    dx |= ex;
+                    dy |= ey;
+                }
                 ch = (ex | ey) != 0;
             }
         }
@@ -439,8 +457,10 @@ __device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *
                 st_pair(a.out_val + o, rv);
                 st_pair(a.out_vld + o, rm);
                 const uint64_t ex = (rv.x ^ ov[u].x) | (rm.x ^ om[u].x), ey = (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
-                dx |= ex;
-                dy |= ey;
+                if (kind[u] != K_RAW) {  // a register's clock history is internal state: it keeps no lane alive
+                    dx |= ex;
+                    dy |= ey;
+                }
                 ch = (ex | ey) != 0;
             }
             if (blockDim.x >= 32) {  // a whole warp on one gate: one ballot, one byte store
@@ -493,7 +513,16 @@ __device__ __forceinline__ void eval_wide_body(const WideArgs &a, uint32_t pb, u
         if (!act) return;  // warp-uniform when a warp sits on one gate
     }
     ulonglong2 rv, rm;
-    if (kind == K_MUX) {
+    if (kind == K_REG) {
+        const size_t rd = (size_t)a.in[b] * a.stride + col, re = (size_t)a.in[b + 1] * a.stride + col,
+                     rc = (size_t)a.in[b + 2] * a.stride + col, rp = (size_t)a.in[b + 3] * a.stride + col,
+                     ro = (size_t)(a.row_base + g) * a.stride + col;
+        const ulonglong2 dv = ld_row(a.in_val + rd), dm = ld_row(a.in_vld + rd), ev = ld_row(a.in_val + re), em = ld_row(a.in_vld + re),
+                         cv = ld_row(a.in_val + rc), cm = ld_row(a.in_vld + rc), pv = ld_row(a.in_val + rp), pm = ld_row(a.in_vld + rp),
+                         ov = ld_row(a.in_val + ro), om = ld_row(a.in_vld + ro);
+        reg_word(dv.x, dm.x, ev.x, em.x, cv.x, cm.x, pv.x, pm.x, ov.x, om.x, rv.x, rm.x);
+        reg_word(dv.y, dm.y, ev.y, em.y, cv.y, cm.y, pv.y, pm.y, ov.y, om.y, rv.y, rm.y);
+    } else if (kind == K_MUX) {
         const uint32_t ns = a.nsel[g];
         ulonglong2 allv = make_ulonglong2(~0ull, ~0ull);
         for (uint32_t s = 0; s < ns; s++) {
@@ -1030,7 +1059,11 @@ struct ResidentArgs {
 __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g, const uint64_t *av, const uint64_t *am, uint32_t wpc,
                                                uint32_t j, u64 &rv, u64 &rm) {
     const uint32_t b = a.woff[g], e = a.woff[g + 1], kind = a.wkind[g];
-    if (kind == K_MUX) {
+    if (kind == K_REG) {
+        const size_t rd = (size_t)a.win[b] * wpc + j, re = (size_t)a.win[b + 1] * wpc + j, rc = (size_t)a.win[b + 2] * wpc + j,
+                     rp = (size_t)a.win[b + 3] * wpc + j, ro = (size_t)(a.n_src + a.n_g2 + a.n_g3 + g) * wpc + j;
+        reg_word(av[rd], am[rd], av[re], am[re], av[rc], am[rc], av[rp], am[rp], av[ro], am[ro], rv, rm);
+    } else if (kind == K_MUX) {
         const uint32_t ns = a.wnsel[g];
         u64 allv = ~0ull, pv = 0, pm = 0;
         for (uint32_t s = 0; s < ns; s++) allv &= am[(size_t)a.win[b + s] * wpc + j];
@@ -1172,6 +1205,7 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
             for (size_t i = tid; i < n_items; i += nt) {
                 const uint32_t row = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
                 u64 rv, rm;
+                bool counts = true;
                 if (row < a.n_src) {
                     rv = rm = 0;
                     if (w < a.stride) {
@@ -1182,6 +1216,7 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
                     const uint32_t g = row - a.n_src;
                     const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j;
                     gate_word(a.kind2[g], AV[r0], AM[r0], AV[r1], AM[r1], rv, rm);
+                    counts = a.kind2[g] != K_RAW;  // a register's clock history is internal state: it keeps no lane alive
                 } else if (row < a.n_src + a.n_g2 + a.n_g3) {
                     const uint32_t g = row - a.n_src, kind = a.kind2[g], base = kind >= K_NAND ? kind - 3 : kind;
                     const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j, r2 = (size_t)a.fan2[g] * wpc + j;
@@ -1194,7 +1229,7 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
                 const u64 d = (rv ^ AV[i]) | (rm ^ AM[i]);
                 BV[i] = rv;
                 BM[i] = rm;
-                if (d) atomicOr((unsigned long long *)&s_changed[j], d);
+                if (d && counts) atomicOr((unsigned long long *)&s_changed[j], d);
             }
             __syncthreads();
             // ---- tri-state nets: wire = resolve(drive, driver rows of B), conflict where two are not High-Z

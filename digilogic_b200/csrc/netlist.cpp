@@ -98,6 +98,17 @@ int Builder::add_merge(const uint32_t *in, size_t n, uint32_t output, uint32_t *
     return push(*this, K_MERGE, in, n, 0, output, cell);
 }
 
+// gsim SimulatorBuilder::add_register(data_in, data_out, enable, clock) — no call site in the reference (the Yosys
+// importer's Dff/Dffe arms are todo!(), crates/digilogic_serde/src/yosys.rs:199-200); SURVEY.md 8f row f4.
+int Builder::add_register(uint32_t data_in, uint32_t data_out, uint32_t enable, uint32_t clock, uint32_t *cell) {
+    if (data_in >= width.size() || data_out >= width.size() || enable >= width.size() || clock >= width.size())
+        return B2_ERR_INVALID_WIRE_ID;
+    if (width[data_in] != width[data_out]) return B2_ERR_WIRE_WIDTH_MISMATCH;
+    if (width[enable] != 1 || width[clock] != 1) return B2_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    const uint32_t in[3] = {data_in, enable, clock};
+    return push(*this, K_REG, in, 3, 0, data_out, cell);
+}
+
 // ---------------------------------------------------------------------------- compiler
 
 namespace {
@@ -106,9 +117,11 @@ struct BitGate {
     uint8_t kind;
     uint8_t nsel;
     uint32_t in_off, n_in;  // into bit_inputs (mux: select bits first)
-    uint32_t out;           // bit-net
+    uint32_t out;           // bit-net, or NO_NET for a hidden gate (it has a row but drives no wire)
     uint32_t level;
 };
+const uint32_t NO_NET = 0xFFFFFFFFu;
+const uint32_t HIDDEN = 0x80000000u;  // a bit_inputs entry with this bit set names the row of gate (entry & ~HIDDEN)
 }  // namespace
 
 void compile(const Builder &b, Compiled &c) {
@@ -128,9 +141,25 @@ void compile(const Builder &b, Compiled &c) {
     size_t est = 0;
     for (const Component &cp : b.comps) est += b.width[cp.output];
     gates.reserve(est);
+    c.has_state = false;
     for (const Component &cp : b.comps) {
         const uint32_t *in = b.inputs.data() + cp.in_off;
         const uint32_t wout = b.width[cp.output];
+        uint32_t prev_clock_gate = 0;
+        if (cp.kind == K_REG) {
+            // the register's view of its clock one step ago: a hidden raw copy of the clock wire
+            c.has_state = true;
+            BitGate h;
+            h.kind = K_RAW;
+            h.nsel = 0;
+            h.in_off = (uint32_t)bin.size();
+            h.n_in = 1;
+            h.out = NO_NET;
+            h.level = 0;
+            bin.push_back(c.bit_off[in[2]]);
+            prev_clock_gate = (uint32_t)gates.size();
+            gates.push_back(h);
+        }
         for (uint32_t j = 0; j < wout; j++) {
             BitGate g;
             g.kind = cp.kind;
@@ -146,6 +175,11 @@ void compile(const Builder &b, Compiled &c) {
             if (cp.kind == K_BUF) {
                 bin.push_back(c.bit_off[in[0]] + j);  // data bit j
                 bin.push_back(c.bit_off[in[1]]);      // the one enable bit
+            } else if (cp.kind == K_REG) {
+                bin.push_back(c.bit_off[in[0]] + j);  // data bit j
+                bin.push_back(c.bit_off[in[1]]);      // enable
+                bin.push_back(c.bit_off[in[2]]);      // clock
+                bin.push_back(HIDDEN | prev_clock_gate);
             } else if (cp.kind == K_SLICE) {
                 g.kind = K_COPY;
                 bin.push_back(c.bit_off[in[0]] + cp.select + j);
@@ -173,6 +207,7 @@ void compile(const Builder &b, Compiled &c) {
     c.has_tristate = false;
     for (uint32_t g = 0; g < G; g++) {
         const uint32_t bn = gates[g].out;
+        if (bn == NO_NET) continue;
         if (gates[g].kind == K_BUF) {
             tri[bn] = 1;
             c.has_tristate = true;
@@ -189,6 +224,7 @@ void compile(const Builder &b, Compiled &c) {
     for (uint32_t g = 0; g < G; g++)
         for (uint32_t i = 0; i < gates[g].n_in; i++) {
             uint32_t bn = bin[gates[g].in_off + i];
+            if (bn & HIDDEN) continue;  // registers: the netlist is evaluated step by step anyway (has_state)
             if (driver[bn] != NONE) {
                 indeg[g]++;
                 cons_off[bn + 2]++;
@@ -199,6 +235,7 @@ void compile(const Builder &b, Compiled &c) {
     for (uint32_t g = 0; g < G; g++)
         for (uint32_t i = 0; i < gates[g].n_in; i++) {
             uint32_t bn = bin[gates[g].in_off + i];
+            if (bn & HIDDEN) continue;
             if (driver[bn] != NONE) cons[cons_off[bn + 1]++] = g;
         }
     std::vector<uint32_t> queue;
@@ -213,7 +250,7 @@ void compile(const Builder &b, Compiled &c) {
         const uint32_t g = queue[h];
         depth = std::max(depth, gates[g].level);
         // only the registered driver of a net propagates (multi-driver netlists never simulate)
-        if (driver[gates[g].out] != g) continue;
+        if (gates[g].out == NO_NET || driver[gates[g].out] != g) continue;
         const uint32_t bn = gates[g].out;
         for (uint32_t k = cons_off[bn]; k < cons_off[bn + 1]; k++) {
             const uint32_t h2 = cons[k];
@@ -221,7 +258,7 @@ void compile(const Builder &b, Compiled &c) {
             if (--indeg[h2] == 0) queue.push_back(h2);
         }
     }
-    c.cyclic = queue.size() != G || c.has_tristate;
+    c.cyclic = queue.size() != G || c.has_tristate || c.has_state;
     c.depth = c.cyclic ? 0 : depth;
     if (c.cyclic)
         for (auto &g : gates) g.level = 1;  // one pseudo-level: unit-delay evaluation only
@@ -257,7 +294,7 @@ void compile(const Builder &b, Compiled &c) {
     if (c.has_tristate) {
         std::vector<uint32_t> cnt((size_t)nb + 1, 0);
         for (uint32_t g = 0; g < G; g++)
-            if (tri[gates[g].out]) cnt[gates[g].out]++;
+            if (gates[g].out != NO_NET && tri[gates[g].out]) cnt[gates[g].out]++;
         c.res_off.push_back(0);
         for (uint32_t i = 0; i < nb; i++)
             if (tri[i]) {
@@ -268,10 +305,11 @@ void compile(const Builder &b, Compiled &c) {
         c.res_in.resize(c.res_off.back());
         std::vector<uint32_t> fill(c.res_off.begin(), c.res_off.end() - 1);
         for (uint32_t g = 0; g < G; g++)  // creation order, like gsim's driver lists
-            if (tri[gates[g].out]) c.res_in[fill[c.res_of_bit[gates[g].out]]++] = gate_row[g];
+            if (gates[g].out != NO_NET && tri[gates[g].out]) c.res_in[fill[c.res_of_bit[gates[g].out]]++] = gate_row[g];
     }
 
     // ---- SoA emission
+    auto row_of = [&](uint32_t entry) { return (entry & HIDDEN) ? gate_row[entry & ~HIDDEN] : c.row_of_bit[entry]; };
     uint32_t n2 = 0;
     while (n2 < G && !is_wide(order[n2])) n2++;
     c.fan0.resize(n2);
@@ -282,9 +320,9 @@ void compile(const Builder &b, Compiled &c) {
     for (uint32_t k = 0; k < n2; k++) {
         const BitGate &g = gates[order[k]];
         c.kind2[k] = g.kind;
-        c.fan0[k] = c.row_of_bit[bin[g.in_off]];
-        c.fan1[k] = g.n_in > 1 ? c.row_of_bit[bin[g.in_off + 1]] : c.fan0[k];
-        c.fan2[k] = g.n_in > 2 ? c.row_of_bit[bin[g.in_off + 2]] : c.fan0[k];
+        c.fan0[k] = row_of(bin[g.in_off]);
+        c.fan1[k] = g.n_in > 1 ? row_of(bin[g.in_off + 1]) : c.fan0[k];
+        c.fan2[k] = g.n_in > 2 ? row_of(bin[g.in_off + 2]) : c.fan0[k];
         if (g.n_in <= 2) c.n_two = k + 1;
     }
     const uint32_t nw = G - n2;
@@ -297,7 +335,7 @@ void compile(const Builder &b, Compiled &c) {
         c.wide_kind[k] = g.kind;
         c.wide_nsel[k] = g.nsel;
         c.wide_off[k] = (uint32_t)c.wide_in.size();
-        for (uint32_t i = 0; i < g.n_in; i++) c.wide_in.push_back(c.row_of_bit[bin[g.in_off + i]]);
+        for (uint32_t i = 0; i < g.n_in; i++) c.wide_in.push_back(row_of(bin[g.in_off + i]));
     }
     c.wide_off[nw] = (uint32_t)c.wide_in.size();
 

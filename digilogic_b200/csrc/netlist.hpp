@@ -15,7 +15,9 @@ enum Kind : uint8_t {
     K_AND = 0, K_OR = 1, K_XOR = 2, K_NAND = 3, K_NOR = 4, K_XNOR = 5, K_NOT = 6, K_MUX = 7,
     K_BUF = 8,   // tri-state buffer: inputs = {data, enable}; the only component whose output can be High-Z
     K_COPY = 9,  // one bit of a slice / merge: output = input, High-Z read as X
-    K_SLICE = 10, K_MERGE = 11  // builder-level only (bit-blasted into K_COPY)
+    K_SLICE = 10, K_MERGE = 11,  // builder-level only (bit-blasted into K_COPY)
+    K_REG = 12,  // register bit: inputs = {data bit, enable, clock, previous-clock row}; reads its own row as the stored value
+    K_RAW = 13   // hidden one-input gate: raw copy (High-Z stays High-Z) — a register's view of its clock one step ago
 };
 
 struct Component {
@@ -38,6 +40,7 @@ struct Builder {
     int add_mux(const uint32_t *in, size_t n, uint32_t select, uint32_t output, uint32_t *cell);
     int add_buffer(uint32_t in, uint32_t enable, uint32_t output, uint32_t *cell);
     int add_slice(uint32_t in, uint32_t offset, uint32_t output, uint32_t *cell);
+    int add_register(uint32_t data_in, uint32_t data_out, uint32_t enable, uint32_t clock, uint32_t *cell);
     int add_merge(const uint32_t *in, size_t n, uint32_t output, uint32_t *cell);
 };
 
@@ -68,7 +71,7 @@ struct Compiled {
     // cyclic: unit-delay evaluation only — feedback, or tri-state nets (their conflicts can be transient,
     // so the steps have to be walked exactly).  multi_driver: some net has two drivers that are never
     // High-Z, so every run conflicts.
-    bool cyclic = false, multi_driver = false, has_tristate = false;
+    bool cyclic = false, multi_driver = false, has_tristate = false, has_state = false;  // has_state: registers
     // Tri-state nets (every net with a buffer among its drivers): each driver keeps its own output row
     // (the gate's implicit row) and the wire gets a resolved row  n_src + n_gates + r  computed by
     // k_resolve from the driver rows res_in[res_off[r] .. res_off[r+1]) and the net's external drive.

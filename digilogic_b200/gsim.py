@@ -177,6 +177,12 @@ class SimulatorBuilder:
         _check(self._lib.b2_add_buffer(self._h, input, enable, output, C.byref(cell)), "add_buffer")
         return cell.value
 
+    def add_register(self, data_in, data_out, enable, clock):
+        """gsim ``SimulatorBuilder::add_register``: loads data_in on a rising clock edge while enable is 1."""
+        cell = C.c_uint32()
+        _check(self._lib.b2_add_register(self._h, data_in, data_out, enable, clock, C.byref(cell)), "add_register")
+        return cell.value
+
     def add_slice(self, input, offset, output):
         """gsim ``SimulatorBuilder::add_slice``: output = input[offset .. offset + width(output))."""
         cell = C.c_uint32()

@@ -97,6 +97,14 @@ int b2_add_mux(b2_builder *b, const uint32_t *inputs, size_t n, uint32_t select,
    always run the unit-delay path.  Errors: InvalidWireId, WireWidthMismatch (input vs output),
    WireWidthIncompatible (enable wider than one bit). */
 int b2_add_buffer(b2_builder *b, uint32_t input, uint32_t enable, uint32_t output, uint32_t *out_cell);
+/* SimulatorBuilder::add_register(data_in, data_out, enable, clock) — gsim's clocked register (no call site in the
+   reference: SimServer has no such method and the Yosys importer's Dff/Dffe arms are todo!(),
+   crates/digilogic_serde/src/yosys.rs:199-200).  Restated (parity unpinned like the rest): on a rising clock edge — the
+   register's previous update saw a valid 0, this one sees a valid 1 — enable = 1 loads data_in (High-Z bits read X),
+   enable = 0 keeps the value, enable Z/X makes it Undefined; data_out carries the stored value, Undefined until the first
+   load.  enable and clock are one bit wide (WireWidthIncompatible), data_in as wide as data_out (WireWidthMismatch).
+   Netlists with registers always run the unit-delay path. */
+int b2_add_register(b2_builder *b, uint32_t data_in, uint32_t data_out, uint32_t enable, uint32_t clock, uint32_t *out_cell);
 /* SimulatorBuilder::add_slice(input, offset, output) and add_merge(inputs, output) — bit re-wiring components of
    gsim, one step of delay like every component, High-Z input bits read as X (no call site in the reference;
    `OffsetOutOfRange` of its error map, lib.rs:55-66, belongs to add_slice).

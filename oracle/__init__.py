@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libgsim_oracle.so")
 
-AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX, BUF, SLICE, MERGE = range(11)
+AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX, BUF, SLICE, MERGE, REG = range(12)
 RUN_OK, RUN_MAX_STEPS, RUN_CONFLICT = 0, 1, 2
 ERR_NAMES = {
     0: "Ok", 1: "TooManyComponents", 2: "InvalidWireId", 3: "WireWidthMismatch",
@@ -59,6 +59,7 @@ def lib():
             "go_add_buffer": (C.c_int, [vp, u32, u32, u32, pu32]),
             "go_set_buffer_z_passthrough": (None, [C.c_int]),
             "go_set_copy_z_passthrough": (None, [C.c_int]),
+            "go_add_register": (C.c_int, [vp, u32, u32, u32, u32, pu32]),
             "go_add_slice": (C.c_int, [vp, u32, u32, u32, pu32]),
             "go_add_merge": (C.c_int, [vp, pu32, u32, u32, pu32]),
             "go_add_gates2": (C.c_int, [vp, vp, vp, vp, vp, u32]),
@@ -175,6 +176,13 @@ class Builder:
     def add_buffer(self, input, enable, output):
         cell = C.c_uint32()
         rc = lib().go_add_buffer(self._h, input, enable, output, C.byref(cell))
+        if rc:
+            raise OracleError(rc)
+        return cell.value
+
+    def add_register(self, data_in, data_out, enable, clock):
+        cell = C.c_uint32()
+        rc = lib().go_add_register(self._h, data_in, data_out, enable, clock, C.byref(cell))
         if rc:
             raise OracleError(rc)
         return cell.value

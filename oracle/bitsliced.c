@@ -38,6 +38,10 @@ typedef struct {
     uint64_t *bv, *bm;      /* state B (scratch) */
     uint64_t *ov, *om;      /* component outputs O = F(W) of the previous application [comp][words] */
     int multi;              /* some wire has two or more drivers */
+    /* registers: stored value and previous clock (raw copy of the clock wire, so High-Z/X = "unknown"), current and
+       next; the next ones are committed together with state B (never on the check-only application) */
+    uint64_t *rdv, *rdm, *rpv, *rpm, *ndv, *ndm, *npv, *npm;
+    int has_reg;
     int cold;
     int topo;               /* component order is topological and single-driver: DAG fast check allowed */
     uint64_t applications;  /* G applications performed by the last run */
@@ -90,6 +94,10 @@ bs_sim *bs_new(const go_builder *b, uint32_t n_lanes) {
     s->bv = (uint64_t *)calloc(n, 8); s->bm = (uint64_t *)calloc(n, 8);
     size_t nc = (size_t)(C ? C : 1) * (s->words ? s->words : 1);
     s->ov = (uint64_t *)calloc(nc, 8); s->om = (uint64_t *)calloc(nc, 8);
+    s->rdv = (uint64_t *)malloc(nc * 8); s->rdm = (uint64_t *)calloc(nc, 8); s->rpv = (uint64_t *)calloc(nc, 8); s->rpm = (uint64_t *)calloc(nc, 8);
+    s->ndv = (uint64_t *)malloc(nc * 8); s->ndm = (uint64_t *)calloc(nc, 8); s->npv = (uint64_t *)calloc(nc, 8); s->npm = (uint64_t *)calloc(nc, 8);
+    memset(s->rdv, 0xFF, nc * 8); memset(s->ndv, 0xFF, nc * 8);  /* stored value starts Undefined (1,0), clock history unknown */
+    for (uint32_t c = 0; c < C; c++) if (s->comps[c].kind == GO_REG) s->has_reg = 1;
     s->cold = 1;
     /* topological + single-driver check */
     s->topo = 1;
@@ -103,7 +111,7 @@ bs_sim *bs_new(const go_builder *b, uint32_t n_lanes) {
         const comp_t *cp = &s->comps[c];
         for (uint32_t i = 0; i < cp->n_inputs; i++) if (!ready[s->inputs[cp->in_off + i]]) s->topo = 0;
         if (cp->kind == GO_MUX && !ready[cp->select]) s->topo = 0;
-        if (cp->kind == GO_BUF) s->topo = 0;  /* transient conflicts / Z outputs: unit-delay model only */
+        if (cp->kind == GO_BUF || cp->kind == GO_REG) s->topo = 0;  /* transient conflicts, Z outputs, state: unit-delay model only */
         ready[cp->output] = 1;
     }
     free(ready);
@@ -113,7 +121,8 @@ bs_sim *bs_new(const go_builder *b, uint32_t n_lanes) {
 void bs_free(bs_sim *s) {
     if (!s) return;
     free(s->comps); free(s->inputs); free(s->drivers_off); free(s->drivers);
-    free(s->dv); free(s->dm); free(s->av); free(s->am); free(s->bv); free(s->bm); free(s->ov); free(s->om); free(s);
+    free(s->dv); free(s->dm); free(s->av); free(s->am); free(s->bv); free(s->bm); free(s->ov); free(s->om);
+    free(s->rdv); free(s->rdm); free(s->rpv); free(s->rpm); free(s->ndv); free(s->ndm); free(s->npv); free(s->npm); free(s);
 }
 
 int bs_is_topological(const bs_sim *s) { return s->topo; }
@@ -136,6 +145,7 @@ void bs_get_all(const bs_sim *s, uint64_t *value, uint64_t *valid) {
 
 /* F_c(W) for one 64-lane word k, reading planes (wv, wm). */
 static inline void eval_comp(const bs_sim *s, const comp_t *cp, const uint64_t *wv, const uint64_t *wm, uint32_t k, uint64_t *ov, uint64_t *om) {
+    const uint32_t ci = (uint32_t)(cp - s->comps);
     const uint32_t *in = s->inputs + cp->in_off;
     uint32_t T = s->words;
     uint64_t v, m;
@@ -152,6 +162,18 @@ static inline void eval_comp(const bs_sim *s, const comp_t *cp, const uint64_t *
     } else if (cp->kind == GO_NOT) {
         uint64_t a = wv[(size_t)in[0] * T + k]; m = wm[(size_t)in[0] * T + k];
         v = ~a | ~m;
+    } else if (cp->kind == GO_REG) {
+        /* rising edge = previous clock a valid 0, clock now a valid 1; enable 1 loads (High-Z reads X), 0 keeps,
+           Z/X makes the value Undefined.  Writes the next stored value / clock history (committed with state B). */
+        size_t si = (size_t)ci * T + k;
+        uint64_t dv = wv[(size_t)in[0] * T + k], dm = wm[(size_t)in[0] * T + k];
+        uint64_t ev = wv[(size_t)in[1] * T + k], em = wm[(size_t)in[1] * T + k];
+        uint64_t cv = wv[(size_t)in[2] * T + k], cm = wm[(size_t)in[2] * T + k];
+        uint64_t edge = s->rpm[si] & ~s->rpv[si] & cm & cv;
+        uint64_t take = edge & ev & em, keep = ~edge | (edge & ~ev & em), undef = edge & ~em;
+        m = (take & dm) | (keep & s->rdm[si]);
+        v = (take & (dv | ~dm)) | (keep & s->rdv[si]) | undef;
+        s->ndv[si] = v; s->ndm[si] = m; s->npv[si] = cv; s->npm[si] = cm;
     } else if (cp->kind == GO_SLICE || cp->kind == GO_MERGE) {
         /* 1-bit wires: a slice at offset 0 or a merge of one input is a copy; High-Z reads X */
         uint64_t a = wv[(size_t)in[0] * T + k]; m = wm[(size_t)in[0] * T + k];
@@ -246,6 +268,10 @@ void bs_run(bs_sim *s, uint64_t max_steps, uint64_t *conflict, uint64_t *unsettl
         uint64_t *t;
         t = s->av; s->av = s->bv; s->bv = t;
         t = s->am; s->am = s->bm; s->bm = t;
+        if (s->has_reg) {
+            t = s->rdv; s->rdv = s->ndv; s->ndv = t;  t = s->rdm; s->rdm = s->ndm; s->ndm = t;
+            t = s->rpv; s->rpv = s->npv; s->npv = t;  t = s->rpm; s->rpm = s->npm; s->npm = t;
+        }
         if (!any) break;
     }
     free(live);

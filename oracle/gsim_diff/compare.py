@@ -34,6 +34,8 @@ def main(cases_path, dump_path):
                 b.add_slice(c["inputs"][0], c["select"], c["output"])
             elif c["kind"] == "merge":
                 b.add_merge(c["inputs"], c["output"])
+            elif c["kind"] == "register":
+                b.add_register(c["inputs"][0], c["output"], c["inputs"][1], c["inputs"][2])
             else:
                 b.add_gate(KIND[c["kind"]], c["inputs"], c["output"])
         sim = b.build()

@@ -68,6 +68,20 @@ def cases():
                           {"kind": "merge", "inputs": [2, 1], "output": 3}],
                 "runs": [{"drives": [[0, [v], [m]]], "max_steps": ms} for v, m, ms in
                          ((0xA5, 0xFF, 10), (0xFF, 0x0F, 10), (0x00, 0x00, 10), (0x3C, 0xFF, 0), (0x3C, 0xFF, 1))]})
+    # registers (A.6-8..): Undefined until the first load, rising edge, enable 0 / X, High-Z data bit, X and Z on the clock,
+    # and a toggle flip-flop (q -> NOT -> d) whose settle takes more than one step
+    reg = [{"kind": "register", "inputs": [0, 2, 3], "output": 1}]
+    out.append({"name": "register_script", "wires": [4, 4, 1, 1], "comps": reg,
+                "runs": [{"drives": d, "max_steps": ms} for ms in (10,) for d in (
+                    [[0, [0b1010], [0xF]], drive(2, L1), drive(3, L0)], [drive(3, L1)], [[0, [0b0101], [0xF]]], [drive(3, L0)], [drive(3, L1)],
+                    [drive(3, L0), drive(2, L0)], [drive(3, L1), [0, [0xF], [0xF]]], [drive(3, L0), drive(2, X)], [drive(3, L1)],
+                    [drive(3, L0), drive(2, L1), [0, [0b0011], [0b0111]]], [drive(3, L1)], [drive(3, X)], [drive(3, L1), [0, [0], [0xF]]],
+                    [drive(3, L0)], [drive(3, L1)], [drive(3, Z)], [drive(3, L0)], [drive(3, L1), drive(2, Z)])]})
+    out.append({"name": "register_toggle", "wires": [1, 1, 1, 1],
+                "comps": [{"kind": "not", "inputs": [1], "output": 0}, {"kind": "register", "inputs": [0, 2, 3], "output": 1}],
+                "runs": [{"drives": d, "max_steps": ms} for d, ms in (
+                    ([drive(2, L1), drive(3, L0)], 10), ([drive(3, L1)], 10), ([drive(3, L0)], 0), ([drive(3, L1)], 0), ([drive(3, L0)], 1),
+                    ([drive(3, L1)], 1), ([drive(3, L0)], 10), ([drive(3, L1)], 10))]})
     # random cyclic netlists, max_steps sweep
     rng = np.random.default_rng(1)
     for n in range(4):

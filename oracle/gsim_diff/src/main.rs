@@ -7,7 +7,7 @@ use std::num::NonZeroU8;
 
 #[derive(Deserialize)]
 struct Comp {
-    kind: String, // and | or | xor | nand | nor | xnor | not | mux | buffer (inputs = [data, enable]) | slice (select = offset) | merge
+    kind: String, // and | or | xor | nand | nor | xnor | not | mux | buffer (inputs = [data, enable]) | slice (select = offset) | merge | register (inputs = [data_in, enable, clock])
     inputs: Vec<u32>,
     select: Option<u32>,
     output: u32,
@@ -59,6 +59,7 @@ fn main() {
                 "buffer" => builder.add_buffer(ins[0], ins[1], o),
                 "slice" => builder.add_slice(ins[0], c.select.unwrap() as u8, o),
                 "merge" => builder.add_merge(&ins, o),
+                "register" => builder.add_register(ins[0], o, ins[1], ins[2]),
                 k => panic!("unknown kind {k}"),
             };
             build_errors.push(r.err().map(|e| format!("{e:?}")));

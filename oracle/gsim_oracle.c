@@ -158,6 +158,19 @@ int go_add_merge(go_builder *b, const uint32_t *inputs, uint32_t n, uint32_t out
     return push_comp(b, GO_MERGE, inputs, n, 0, output, cell);
 }
 
+/* add_register(data_in, data_out, enable, clock): gsim's clocked register (no call site in the reference;
+   the Yosys importer's Dff/Dffe arms are todo!(), crates/digilogic_serde/src/yosys.rs:199-200).  Restated:
+   on a rising clock edge (previous update saw a valid 0, this one a valid 1) enable = 1 loads data_in
+   (High-Z bits read X), enable = 0 keeps, enable Z/X makes the stored value Undefined; the output is the
+   stored value, Undefined until the first load. */
+int go_add_register(go_builder *b, uint32_t data_in, uint32_t data_out, uint32_t enable, uint32_t clock, uint32_t *cell) {
+    if (data_in >= b->n_wires || data_out >= b->n_wires || enable >= b->n_wires || clock >= b->n_wires) return GO_ERR_INVALID_WIRE_ID;
+    if (b->width[data_in] != b->width[data_out]) return GO_ERR_WIRE_WIDTH_MISMATCH;
+    if (b->width[enable] != 1 || b->width[clock] != 1) return GO_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    uint32_t in[3] = {data_in, enable, clock};
+    return push_comp(b, GO_REG, in, 3, 0, data_out, cell);
+}
+
 /* Bulk 2-input gate add used by the large generators (same validation per gate). */
 int go_add_gates2(go_builder *b, const uint8_t *kinds, const uint32_t *in0, const uint32_t *in1, const uint32_t *out, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) {
@@ -176,6 +189,15 @@ static void init_state(go_sim *s) {
     if (g_cfg.initial_undefined) { init.state = 0xFFFFFFFFu; init.valid = 0; }
     for (uint32_t i = 0; i < s->n_watoms; i++) { s->drive[i].state = 0; s->drive[i].valid = 0; s->state[i] = init; }
     for (uint32_t i = 0; i < s->n_catoms; i++) s->output[i] = init;
+    /* a register holds Undefined until its first load; its clock history starts unknown */
+    for (uint32_t c = 0; c < s->n_comps; c++) {
+        uint32_t w = s->comps[c].output;
+        for (uint32_t i = 0; i < s->natoms[w]; i++) {
+            uint32_t top = (i == (uint32_t)s->natoms[w] - 1 && (s->width[w] & 31)) ? (1u << (s->width[w] & 31)) - 1 : 0xFFFFFFFFu;
+            s->rdata[s->catom_off[c] + i].state = top; s->rdata[s->catom_off[c] + i].valid = 0;
+        }
+        s->rprev[c] = -1;
+    }
     if (g_cfg.initial_undefined) {
         for (uint32_t w = 0; w < s->n_wires; w++) {
             uint32_t top = s->width[w] & 31;
@@ -209,6 +231,8 @@ go_sim *go_build(const go_builder *b) {
     s->drive = (atom_t *)malloc((s->n_watoms ? s->n_watoms : 1) * sizeof(atom_t));
     s->state = (atom_t *)malloc((s->n_watoms ? s->n_watoms : 1) * sizeof(atom_t));
     s->output = (atom_t *)malloc((s->n_catoms ? s->n_catoms : 1) * sizeof(atom_t));
+    s->rdata = (atom_t *)malloc((s->n_catoms ? s->n_catoms : 1) * sizeof(atom_t));
+    s->rprev = (int8_t *)malloc(C ? C : 1);
 
     /* drivers CSR */
     s->drivers_off = (uint32_t *)calloc((size_t)W + 2, sizeof(uint32_t));
@@ -248,7 +272,7 @@ void go_sim_free(go_sim *s) {
         free(s->driving_off); free(s->driving); free(s->drivers_off); free(s->drivers);
         free(s->atom_off); free(s->catom_off);
     }
-    free(s->drive); free(s->state); free(s->output);
+    free(s->drive); free(s->state); free(s->output); free(s->rdata); free(s->rprev);
     free(s->wq); free(s->cq); free(s->tmp); free(s);
 }
 
@@ -261,6 +285,7 @@ go_sim *go_sim_clone(const go_sim *src) {
     uint32_t W = s->n_wires, C = s->n_comps;
 #define DUP(field, count, type) do { size_t n_ = (size_t)(count); if (!n_) n_ = 1; s->field = (type *)malloc(n_ * sizeof(type)); memcpy(s->field, src->field, n_ * sizeof(type)); } while (0)
     DUP(drive, s->n_watoms, atom_t); DUP(state, s->n_watoms, atom_t); DUP(output, s->n_catoms, atom_t);
+    DUP(rdata, s->n_catoms, atom_t); DUP(rprev, C, int8_t);
 #undef DUP
     size_t qcap = (size_t)(src->driving_off[W] > W ? src->driving_off[W] : W) + C + 16;
     s->wq = (uint32_t *)malloc(qcap * sizeof(uint32_t));
@@ -364,6 +389,18 @@ static int eval_component(go_sim *s, uint32_t c) {
                 res[j >> 5].valid |= vl << (j & 31);
             }
         }
+    } else if (cp->kind == GO_REG) {
+        const atom_t *d = s->state + s->atom_off[in[0]];
+        const atom_t en = s->state[s->atom_off[in[1]]], ck = s->state[s->atom_off[in[2]]];
+        atom_t *data = s->rdata + s->catom_off[c];
+        if (s->rprev[c] == 0 && (ck.valid & 1) && (ck.state & 1)) {          /* rising edge */
+            for (uint32_t i = 0; i < na; i++) {
+                if (!(en.valid & 1)) { data[i].state = 0xFFFFFFFFu; data[i].valid = 0; }
+                else if (en.state & 1) { data[i].state = d[i].state | ~d[i].valid; data[i].valid = d[i].valid; }
+            }
+        }
+        s->rprev[c] = (ck.valid & 1) ? (int8_t)(ck.state & 1) : -1;
+        for (uint32_t i = 0; i < na; i++) res[i] = data[i];
     } else if (cp->kind == GO_BUF) {
         /* enable = 1: the input (High-Z bits read X); enable = 0: High-Z; enable Z/X: Undefined */
         const atom_t *a = s->state + s->atom_off[in[0]];

@@ -10,7 +10,8 @@ typedef struct { uint32_t state, valid; } atom_t;
 enum { GO_AND = 0, GO_OR = 1, GO_XOR = 2, GO_NAND = 3, GO_NOR = 4, GO_XNOR = 5, GO_NOT = 6, GO_MUX = 7,
        GO_BUF = 8,  /* tri-state buffer: inputs[0] = data, inputs[1] = 1-bit enable */
        GO_SLICE = 9,  /* output = input[offset .. offset + width(output)); offset in `select` */
-       GO_MERGE = 10  /* output = inputs concatenated, inputs[0] in the low bits */ };
+       GO_MERGE = 10, /* output = inputs concatenated, inputs[0] in the low bits */
+       GO_REG = 11    /* register: inputs = {data_in, enable (1 bit), clock (1 bit)}; loads data_in on a rising clock edge */ };
 
 /* AddComponentError ordinals, names pinned by crates/digilogic_gsim/src/lib.rs:55-66 */
 enum {
@@ -71,6 +72,8 @@ typedef struct {
     uint32_t *catom_off;               /* per component output */
     uint32_t n_watoms, n_catoms;
     atom_t *drive, *state, *output;
+    atom_t *rdata;                     /* registers: stored value, parallel to output[] (other components: unused) */
+    int8_t *rprev;                     /* registers: clock at the previous update: -1 unknown, 0, 1 */
     /* queues */
     uint32_t *wq, *cq, *tmp;
     uint32_t n_wq, n_cq;

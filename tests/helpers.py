@@ -2,7 +2,7 @@
 engine's builder (both expose the gsim SimulatorBuilder method names)."""
 import numpy as np
 
-AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX, BUF = range(9)
+AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX, BUF, SLICE, MERGE, REG = range(12)
 ALL1 = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
@@ -34,6 +34,9 @@ class Netlist:
     def add_buffer(self, input, enable, output):
         self.ops.append((BUF, [input, enable], None, output))
 
+    def add_register(self, data_in, data_out, enable, clock):
+        self.ops.append((REG, [data_in, enable, clock], None, data_out))
+
     @property
     def n_wires(self):
         return len(self.widths)
@@ -41,7 +44,7 @@ class Netlist:
     def replay(self, builder):
         for w in self.widths:
             builder.add_wire(w)
-        simple = all(k not in (MUX, BUF) and len(i) <= 2 for k, i, _, _ in self.ops)
+        simple = all(k not in (MUX, BUF, REG) and len(i) <= 2 for k, i, _, _ in self.ops)
         if simple and len(self.ops) > 64:
             kinds = np.array([k for k, _, _, _ in self.ops], np.uint8)
             in0 = np.array([i[0] for _, i, _, _ in self.ops], np.uint32)
@@ -56,6 +59,8 @@ class Netlist:
                 builder.add_not_gate(inputs[0], output)
             elif kind == BUF:
                 builder.add_buffer(inputs[0], inputs[1], output)
+            elif kind == REG:
+                builder.add_register(inputs[0], output, inputs[1], inputs[2])
             else:
                 builder.add_gate(kind, inputs, output)
         return builder
@@ -136,6 +141,28 @@ def bus_enable_drives(rng, group, words, p_bad=0.03):
         return np.packbits(bits.reshape(words, 64), axis=1, bitorder="little").view(np.uint64).reshape(words)
 
     return [(pack(val[j]), pack(vld[j])) for j in range(k)]
+
+
+def random_register_netlist(rng, n_in, n_gates, p_reg=0.25):
+    """Random cyclic netlist in which about `p_reg` of the components are registers whose data, enable and clock
+    come from arbitrary wires (inputs, gates, other registers).  Returns (netlist, first_in)."""
+    nl = Netlist()
+    first_in = nl.add_wires(n_in)
+    first_g = nl.add_wires(n_gates)
+    n_w = n_in + n_gates
+    for g in range(n_gates):
+        if rng.random() < p_reg:
+            d, en, ck = (int(x) for x in rng.integers(0, n_w, 3))
+            if rng.random() < 0.5:
+                ck = int(rng.integers(0, n_in))       # half of the clocks straight from an input
+            nl.add_register(d, first_g + g, en, ck)
+            continue
+        kind = int(rng.integers(0, 7))
+        if kind == NOT:
+            nl.add_not_gate(int(rng.integers(0, n_w)), first_g + g)
+        else:
+            nl.add_gate(kind, [int(x) for x in rng.integers(0, n_w, 2)], first_g + g)
+    return nl, first_in
 
 
 def random_drive(rng, words, four_state=True):

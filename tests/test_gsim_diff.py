@@ -29,6 +29,8 @@ def build(case, builder):
             builder.add_slice(c["inputs"][0], c["select"], c["output"])
         elif c["kind"] == "merge":
             builder.add_merge(c["inputs"], c["output"])
+        elif c["kind"] == "register":
+            builder.add_register(c["inputs"][0], c["output"], c["inputs"][1], c["inputs"][2])
         else:
             builder.add_gate(compare.KIND[c["kind"]], c["inputs"], c["output"])
     return builder.build()
@@ -51,7 +53,7 @@ def oracle_dump(cases):
 
 def test_harness_python_side(tmp_path):
     cases = make_cases.cases()
-    assert len(cases) >= 19
+    assert len(cases) >= 21
     cp, dp = tmp_path / "cases.json", tmp_path / "dump.json"
     cp.write_text(json.dumps(cases))
     dp.write_text(json.dumps(oracle_dump(cases)))
