@@ -82,6 +82,13 @@ int b2_add_buffer(b2_builder *b, uint32_t input, uint32_t enable, uint32_t outpu
     GUARD_END(B2_ERR_OUT_OF_MEMORY)
 }
 
+int b2_add_horizontal_gate(b2_builder *b, int kind, uint32_t input, uint32_t output, uint32_t *out_cell) {
+    if (!b) return B2_ERR_NULL;
+    GUARD_BEGIN
+    return b->b.add_horizontal_gate(kind, input, output, out_cell);
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
 int b2_add_register(b2_builder *b, uint32_t data_in, uint32_t data_out, uint32_t enable, uint32_t clock, uint32_t *out_cell) {
     if (!b) return B2_ERR_NULL;
     GUARD_BEGIN

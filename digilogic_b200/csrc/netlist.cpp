@@ -98,6 +98,15 @@ int Builder::add_merge(const uint32_t *in, size_t n, uint32_t output, uint32_t *
     return push(*this, K_MERGE, in, n, 0, output, cell);
 }
 
+// gsim SimulatorBuilder::add_horizontal_{and,or,xor,nand,nor,xnor}_gate(input, output): reduction over the bits of one wire
+// (the Yosys importer's ReduceAnd/Or/Xor/Xnor/Bool arms are todo!(), crates/digilogic_serde/src/yosys.rs:163-167)
+int Builder::add_horizontal_gate(int kind, uint32_t in, uint32_t output, uint32_t *cell) {
+    if (kind < K_AND || kind > K_XNOR) return B2_ERR_INVALID_ARG;
+    if (output >= width.size() || in >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    if (width[output] != 1) return B2_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    return push(*this, K_HGATE, &in, 1, (uint32_t)kind, output, cell);
+}
+
 // gsim SimulatorBuilder::add_register(data_in, data_out, enable, clock) — no call site in the reference (the Yosys
 // importer's Dff/Dffe arms are todo!(), crates/digilogic_serde/src/yosys.rs:199-200); SURVEY.md 8f row f4.
 int Builder::add_register(uint32_t data_in, uint32_t data_out, uint32_t enable, uint32_t clock, uint32_t *cell) {
@@ -175,6 +184,15 @@ void compile(const Builder &b, Compiled &c) {
             if (cp.kind == K_BUF) {
                 bin.push_back(c.bit_off[in[0]] + j);  // data bit j
                 bin.push_back(c.bit_off[in[1]]);      // the one enable bit
+            } else if (cp.kind == K_HGATE) {
+                const uint32_t wi = b.width[in[0]];
+                if (wi == 1) {  // one bit: the bit itself (High-Z read as X), inverted for NAND / NOR / XNOR
+                    g.kind = cp.select >= K_NAND ? K_NOT : K_COPY;
+                    bin.push_back(c.bit_off[in[0]]);
+                } else {
+                    g.kind = (uint8_t)cp.select;
+                    for (uint32_t t = 0; t < wi; t++) bin.push_back(c.bit_off[in[0]] + t);
+                }
             } else if (cp.kind == K_REG) {
                 bin.push_back(c.bit_off[in[0]] + j);  // data bit j
                 bin.push_back(c.bit_off[in[1]]);      // enable

@@ -177,6 +177,19 @@ class SimulatorBuilder:
         _check(self._lib.b2_add_buffer(self._h, input, enable, output, C.byref(cell)), "add_buffer")
         return cell.value
 
+    def add_horizontal_gate(self, kind, input, output):
+        """gsim ``add_horizontal_{and,or,xor,nand,nor,xnor}_gate``: the gate folded over all bits of one wire."""
+        cell = C.c_uint32()
+        _check(self._lib.b2_add_horizontal_gate(self._h, kind, input, output, C.byref(cell)), "add_horizontal_gate")
+        return cell.value
+
+    def add_horizontal_and_gate(self, input, output): return self.add_horizontal_gate(AND, input, output)
+    def add_horizontal_or_gate(self, input, output): return self.add_horizontal_gate(OR, input, output)
+    def add_horizontal_xor_gate(self, input, output): return self.add_horizontal_gate(XOR, input, output)
+    def add_horizontal_nand_gate(self, input, output): return self.add_horizontal_gate(NAND, input, output)
+    def add_horizontal_nor_gate(self, input, output): return self.add_horizontal_gate(NOR, input, output)
+    def add_horizontal_xnor_gate(self, input, output): return self.add_horizontal_gate(XNOR, input, output)
+
     def add_register(self, data_in, data_out, enable, clock):
         """gsim ``SimulatorBuilder::add_register``: loads data_in on a rising clock edge while enable is 1."""
         cell = C.c_uint32()

@@ -97,6 +97,11 @@ int b2_add_mux(b2_builder *b, const uint32_t *inputs, size_t n, uint32_t select,
    always run the unit-delay path.  Errors: InvalidWireId, WireWidthMismatch (input vs output),
    WireWidthIncompatible (enable wider than one bit). */
 int b2_add_buffer(b2_builder *b, uint32_t input, uint32_t enable, uint32_t output, uint32_t *out_cell);
+/* SimulatorBuilder::add_horizontal_{and,or,xor,nand,nor,xnor}_gate(input, output): the one-bit output is the gate folded over
+   all bits of `input` (kind = B2_AND .. B2_XNOR); compiled into an ordinary n-ary gate over the input's bit rows.  No call site
+   in the reference (Yosys ReduceAnd/Or/Xor/Xnor/Bool are todo!(), crates/digilogic_serde/src/yosys.rs:163-167).
+   Errors: InvalidWireId; WireWidthIncompatible when the output is wider than one bit. */
+int b2_add_horizontal_gate(b2_builder *b, int kind, uint32_t input, uint32_t output, uint32_t *out_cell);
 /* SimulatorBuilder::add_register(data_in, data_out, enable, clock) — gsim's clocked register (no call site in the
    reference: SimServer has no such method and the Yosys importer's Dff/Dffe arms are todo!(),
    crates/digilogic_serde/src/yosys.rs:199-200).  Restated (parity unpinned like the rest): on a rising clock edge — the

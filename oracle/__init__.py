@@ -60,6 +60,7 @@ def lib():
             "go_set_buffer_z_passthrough": (None, [C.c_int]),
             "go_set_copy_z_passthrough": (None, [C.c_int]),
             "go_add_register": (C.c_int, [vp, u32, u32, u32, u32, pu32]),
+            "go_add_horizontal_gate": (C.c_int, [vp, C.c_int, u32, u32, pu32]),
             "go_add_slice": (C.c_int, [vp, u32, u32, u32, pu32]),
             "go_add_merge": (C.c_int, [vp, pu32, u32, u32, pu32]),
             "go_add_gates2": (C.c_int, [vp, vp, vp, vp, vp, u32]),
@@ -179,6 +180,20 @@ class Builder:
         if rc:
             raise OracleError(rc)
         return cell.value
+
+    def add_horizontal_gate(self, kind, input, output):
+        cell = C.c_uint32()
+        rc = lib().go_add_horizontal_gate(self._h, kind, input, output, C.byref(cell))
+        if rc:
+            raise OracleError(rc)
+        return cell.value
+
+    def add_horizontal_and_gate(self, input, output): return self.add_horizontal_gate(AND, input, output)
+    def add_horizontal_or_gate(self, input, output): return self.add_horizontal_gate(OR, input, output)
+    def add_horizontal_xor_gate(self, input, output): return self.add_horizontal_gate(XOR, input, output)
+    def add_horizontal_nand_gate(self, input, output): return self.add_horizontal_gate(NAND, input, output)
+    def add_horizontal_nor_gate(self, input, output): return self.add_horizontal_gate(NOR, input, output)
+    def add_horizontal_xnor_gate(self, input, output): return self.add_horizontal_gate(XNOR, input, output)
 
     def add_register(self, data_in, data_out, enable, clock):
         cell = C.c_uint32()

@@ -174,6 +174,10 @@ static inline void eval_comp(const bs_sim *s, const comp_t *cp, const uint64_t *
         m = (take & dm) | (keep & s->rdm[si]);
         v = (take & (dv | ~dm)) | (keep & s->rdv[si]) | undef;
         s->ndv[si] = v; s->ndm[si] = m; s->npv[si] = cv; s->npm[si] = cm;
+    } else if (cp->kind == GO_HGATE) {
+        /* 1-bit wires: a reduction over one bit is the bit itself (High-Z read as X), inverted for NAND/NOR/XNOR */
+        uint64_t a = wv[(size_t)in[0] * T + k]; m = wm[(size_t)in[0] * T + k];
+        v = (cp->select >= GO_NAND ? ~a : a) | ~m;
     } else if (cp->kind == GO_SLICE || cp->kind == GO_MERGE) {
         /* 1-bit wires: a slice at offset 0 or a merge of one input is a copy; High-Z reads X */
         uint64_t a = wv[(size_t)in[0] * T + k]; m = wm[(size_t)in[0] * T + k];

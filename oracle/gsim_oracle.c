@@ -171,6 +171,16 @@ int go_add_register(go_builder *b, uint32_t data_in, uint32_t data_out, uint32_t
     return push_comp(b, GO_REG, in, 3, 0, data_out, cell);
 }
 
+/* add_horizontal_{and,or,xor,nand,nor,xnor}_gate(input, output): the 1-bit output is the gate function folded over
+   all bits of the input wire (gsim's reduction gates; the Yosys importer's ReduceAnd/Or/Xor/Xnor/Bool arms are todo!(),
+   crates/digilogic_serde/src/yosys.rs:163-167). */
+int go_add_horizontal_gate(go_builder *b, int kind, uint32_t input, uint32_t output, uint32_t *cell) {
+    if (kind < GO_AND || kind > GO_XNOR) return GO_ERR_INVALID_INPUT_COUNT;
+    if (output >= b->n_wires || input >= b->n_wires) return GO_ERR_INVALID_WIRE_ID;
+    if (b->width[output] != 1) return GO_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    return push_comp(b, GO_HGATE, &input, 1, (uint32_t)kind, output, cell);
+}
+
 /* Bulk 2-input gate add used by the large generators (same validation per gate). */
 int go_add_gates2(go_builder *b, const uint8_t *kinds, const uint32_t *in0, const uint32_t *in1, const uint32_t *out, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) {
@@ -389,6 +399,18 @@ static int eval_component(go_sim *s, uint32_t c) {
                 res[j >> 5].valid |= vl << (j & 31);
             }
         }
+    } else if (cp->kind == GO_HGATE) {
+        const atom_t *a = s->state + s->atom_off[in[0]];
+        const uint32_t wi = s->width[in[0]], k = cp->select;
+        atom_t acc = {a[0].state & 1, a[0].valid & 1};
+        for (uint32_t t = 1; t < wi; t++) {
+            atom_t bit = {(a[t >> 5].state >> (t & 31)) & 1, (a[t >> 5].valid >> (t & 31)) & 1};
+            acc = (k == GO_AND || k == GO_NAND) ? op_and(acc, bit) : (k == GO_OR || k == GO_NOR) ? op_or(acc, bit) : op_xor(acc, bit);
+            acc.state &= 1; acc.valid &= 1;
+        }
+        if (wi == 1) { acc.state |= ~acc.valid & 1; }   /* a single bit: the bit itself, High-Z read as X */
+        if (k >= GO_NAND) acc = op_not(acc);
+        res[0].state = acc.state & 1; res[0].valid = acc.valid & 1;
     } else if (cp->kind == GO_REG) {
         const atom_t *d = s->state + s->atom_off[in[0]];
         const atom_t en = s->state[s->atom_off[in[1]]], ck = s->state[s->atom_off[in[2]]];

@@ -106,3 +106,87 @@ def test_slice_merge_on_gpu_against_oracle(resident):
             assert int(sim.run_sim(max_steps)) == ref.run_sim(max_steps)
             for name, wire in w.items():
                 assert sim.get_wire_state(wire) == LogicState(*ref.get_wire_state(wire)), (max_steps, hex(value), name)
+
+
+# ------------------------------------------------------------------------------- reduction ("horizontal") gates
+from oracle import AND, NAND, NOR, OR, XNOR, XOR  # noqa: E402
+
+H_WIDTHS = [1, 2, 3, 8, 40]
+H_KINDS = [AND, OR, XOR, NAND, NOR, XNOR]
+
+
+def reduce_model(kind, value, valid, width):
+    """Kleene reduction over the bits (High-Z / X = unknown)."""
+    bits = [(((value >> i) & 1) if (valid >> i) & 1 else None) for i in range(width)]
+    base = {AND: AND, NAND: AND, OR: OR, NOR: OR, XOR: XOR, XNOR: XOR}[kind]
+    if base == AND:
+        r = 0 if 0 in bits else (None if None in bits else 1)
+    elif base == OR:
+        r = 1 if 1 in bits else (None if None in bits else 0)
+    else:
+        r = None if None in bits else sum(bits) & 1
+    if r is not None and kind in (NAND, NOR, XNOR):
+        r ^= 1
+    return (1, 0) if r is None else (r, 1)
+
+
+def build_reductions(b):
+    ins, outs = [], {}
+    for w in H_WIDTHS:
+        i = b.add_wire(w)
+        ins.append(i)
+        for k in H_KINDS:
+            o = b.add_wire(1)
+            b.add_horizontal_gate(k, i, o)
+            outs[(w, k)] = o
+    return ins, outs
+
+
+def reduction_stimuli(rng, width, n=12):
+    full = (1 << width) - 1
+    cases = [(0, full), (full, full), (0, 0), (full, 0)]
+    for _ in range(n):
+        v = int(rng.integers(0, 1 << 62)) & full
+        m = full if rng.random() < 0.5 else (int(rng.integers(0, 1 << 62)) | int(rng.integers(0, 1 << 62))) & full
+        cases.append((v, m))
+    return cases
+
+
+def test_horizontal_gates_on_oracle():
+    b = oracle.Builder()
+    w8, w2 = b.add_wire(8), b.add_wire(2)
+    with pytest.raises(oracle.OracleError, match="WireWidthIncompatible"):
+        b.add_horizontal_gate(AND, w8, w2)
+    with pytest.raises(oracle.OracleError, match="InvalidWireId"):
+        b.add_horizontal_gate(AND, 99, w2)
+    b = oracle.Builder()
+    ins, outs = build_reductions(b)
+    sim = b.build()
+    rng = np.random.default_rng(11)
+    for w, i in zip(H_WIDTHS, ins):
+        for v, m in reduction_stimuli(rng, w):
+            sim.set_wire_drive(i, v, m)
+            assert sim.run_sim(10) == oracle.RUN_OK
+            for k in H_KINDS:
+                assert sim.get_wire_state(outs[(w, k)]) == reduce_model(k, v, m, w), (w, k, hex(v), hex(m))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [1, 0])
+def test_horizontal_gates_on_gpu_against_oracle(resident):
+    from digilogic_b200 import LogicState, SimulatorBuilder
+    ob, gb = oracle.Builder(), SimulatorBuilder()
+    ins, outs = build_reductions(ob)
+    build_reductions(gb)
+    ref, sim = ob.build(), gb.build()
+    sim.set_option(sim.OPT_RESIDENT_KERNEL, resident)
+    rng = np.random.default_rng(12)
+    for rnd in range(10):
+        for w, i in zip(H_WIDTHS, ins):
+            v, m = reduction_stimuli(rng, w, n=1)[-1]
+            ref.set_wire_drive(i, v, m)
+            sim.set_wire_drive(i, LogicState(v, m))
+        ms = (10, 0, 1)[rnd % 3]
+        assert int(sim.run_sim(ms)) == ref.run_sim(ms)
+        for key, o in outs.items():
+            assert sim.get_wire_state(o) == LogicState(*ref.get_wire_state(o)), (rnd, key)
