@@ -82,6 +82,20 @@ int b2_add_buffer(b2_builder *b, uint32_t input, uint32_t enable, uint32_t outpu
     GUARD_END(B2_ERR_OUT_OF_MEMORY)
 }
 
+int b2_add_add(b2_builder *b, uint32_t input_a, uint32_t input_b, uint32_t output, uint32_t *out_cell) {
+    if (!b) return B2_ERR_NULL;
+    GUARD_BEGIN
+    return b->b.add_arith(b2::K_ADD, input_a, input_b, output, out_cell);
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
+int b2_add_sub(b2_builder *b, uint32_t input_a, uint32_t input_b, uint32_t output, uint32_t *out_cell) {
+    if (!b) return B2_ERR_NULL;
+    GUARD_BEGIN
+    return b->b.add_arith(b2::K_SUB, input_a, input_b, output, out_cell);
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
 int b2_add_horizontal_gate(b2_builder *b, int kind, uint32_t input, uint32_t output, uint32_t *out_cell) {
     if (!b) return B2_ERR_NULL;
     GUARD_BEGIN

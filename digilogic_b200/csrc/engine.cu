@@ -513,7 +513,35 @@ __device__ __forceinline__ void eval_wide_body(const WideArgs &a, uint32_t pb, u
         if (!act) return;  // warp-uniform when a warp sits on one gate
     }
     ulonglong2 rv, rm;
-    if (kind == K_REG) {
+    if (kind == K_ADD || kind == K_SUB) {
+        // one bit of a + b or a - b: inputs a_0..a_{w-1}, b_0..b_{w-1}; any invalid input bit makes the result Undefined
+        const uint32_t w = (e - b) / 2, j = a.nsel[g];
+        const bool sub = kind == K_SUB;
+        ulonglong2 ok = make_ulonglong2(~0ull, ~0ull), carry = sub ? ok : make_ulonglong2(0, 0), sum = make_ulonglong2(0, 0);
+        for (uint32_t t = 0; t < w; t++) {
+            const ulonglong2 ma = ld_valid(a, a.in[b + t], col), mb = ld_valid(a, a.in[b + w + t], col);
+            ok.x &= ma.x & mb.x;
+            ok.y &= ma.y & mb.y;
+            if (t <= j) {
+                const ulonglong2 x = ld_row(a.in_val + (size_t)a.in[b + t] * a.stride + col);
+                ulonglong2 y = ld_row(a.in_val + (size_t)a.in[b + w + t] * a.stride + col);
+                if (sub) {
+                    y.x = ~y.x;
+                    y.y = ~y.y;
+                }
+                if (t == j) {
+                    sum.x = x.x ^ y.x ^ carry.x;
+                    sum.y = x.y ^ y.y ^ carry.y;
+                } else {
+                    carry.x = (x.x & y.x) | (carry.x & (x.x ^ y.x));
+                    carry.y = (x.y & y.y) | (carry.y & (x.y ^ y.y));
+                }
+            }
+        }
+        rm = ok;
+        rv.x = sum.x | ~ok.x;
+        rv.y = sum.y | ~ok.y;
+    } else if (kind == K_REG) {
         const size_t rd = (size_t)a.in[b] * a.stride + col, re = (size_t)a.in[b + 1] * a.stride + col,
                      rc = (size_t)a.in[b + 2] * a.stride + col, rp = (size_t)a.in[b + 3] * a.stride + col,
                      ro = (size_t)(a.row_base + g) * a.stride + col;
@@ -1059,7 +1087,22 @@ struct ResidentArgs {
 __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g, const uint64_t *av, const uint64_t *am, uint32_t wpc,
                                                uint32_t j, u64 &rv, u64 &rm) {
     const uint32_t b = a.woff[g], e = a.woff[g + 1], kind = a.wkind[g];
-    if (kind == K_REG) {
+    if (kind == K_ADD || kind == K_SUB) {
+        const uint32_t w = (e - b) / 2, bit = a.wnsel[g];
+        const bool sub = kind == K_SUB;
+        u64 ok = ~0ull, carry = sub ? ~0ull : 0ull, sum = 0;
+        for (uint32_t t = 0; t < w; t++) {
+            const size_t ra = (size_t)a.win[b + t] * wpc + j, rb = (size_t)a.win[b + w + t] * wpc + j;
+            ok &= am[ra] & am[rb];
+            if (t <= bit) {
+                const u64 x = av[ra], y = sub ? ~av[rb] : av[rb];
+                if (t == bit) sum = x ^ y ^ carry;
+                else carry = (x & y) | (carry & (x ^ y));
+            }
+        }
+        rm = ok;
+        rv = sum | ~ok;
+    } else if (kind == K_REG) {
         const size_t rd = (size_t)a.win[b] * wpc + j, re = (size_t)a.win[b + 1] * wpc + j, rc = (size_t)a.win[b + 2] * wpc + j,
                      rp = (size_t)a.win[b + 3] * wpc + j, ro = (size_t)(a.n_src + a.n_g2 + a.n_g3 + g) * wpc + j;
         reg_word(av[rd], am[rd], av[re], am[re], av[rc], am[rc], av[rp], am[rp], av[ro], am[ro], rv, rm);

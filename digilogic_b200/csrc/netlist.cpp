@@ -98,6 +98,16 @@ int Builder::add_merge(const uint32_t *in, size_t n, uint32_t output, uint32_t *
     return push(*this, K_MERGE, in, n, 0, output, cell);
 }
 
+// gsim SimulatorBuilder::add_add / add_sub(input_a, input_b, output): wrapping sum / difference of two wires of the output's
+// width, Undefined if any input bit is not a valid 0/1 (the Yosys importer's Add/Sub arms are todo!(), yosys.rs:188-189)
+int Builder::add_arith(int kind, uint32_t a, uint32_t b2, uint32_t output, uint32_t *cell) {
+    if (kind != K_ADD && kind != K_SUB) return B2_ERR_INVALID_ARG;
+    if (output >= width.size() || a >= width.size() || b2 >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    if (width[a] != width[output] || width[b2] != width[output]) return B2_ERR_WIRE_WIDTH_MISMATCH;
+    const uint32_t in[2] = {a, b2};
+    return push(*this, (uint8_t)kind, in, 2, 0, output, cell);
+}
+
 // gsim SimulatorBuilder::add_horizontal_{and,or,xor,nand,nor,xnor}_gate(input, output): reduction over the bits of one wire
 // (the Yosys importer's ReduceAnd/Or/Xor/Xnor/Bool arms are todo!(), crates/digilogic_serde/src/yosys.rs:163-167)
 int Builder::add_horizontal_gate(int kind, uint32_t in, uint32_t output, uint32_t *cell) {
@@ -184,6 +194,11 @@ void compile(const Builder &b, Compiled &c) {
             if (cp.kind == K_BUF) {
                 bin.push_back(c.bit_off[in[0]] + j);  // data bit j
                 bin.push_back(c.bit_off[in[1]]);      // the one enable bit
+            } else if (cp.kind == K_ADD || cp.kind == K_SUB) {
+                // bit j of the result: needs every input bit for the validity and bits 0..j for the carry
+                g.nsel = (uint8_t)j;
+                for (uint32_t t = 0; t < wout; t++) bin.push_back(c.bit_off[in[0]] + t);
+                for (uint32_t t = 0; t < wout; t++) bin.push_back(c.bit_off[in[1]] + t);
             } else if (cp.kind == K_HGATE) {
                 const uint32_t wi = b.width[in[0]];
                 if (wi == 1) {  // one bit: the bit itself (High-Z read as X), inverted for NAND / NOR / XNOR
@@ -285,7 +300,10 @@ void compile(const Builder &b, Compiled &c) {
     std::vector<uint32_t> order(G);
     std::iota(order.begin(), order.end(), 0u);
     // class 0: one/two inputs, class 1: three inputs (both on the fast kernels), class 2: CSR kernel
-    auto cls = [&](uint32_t g) -> int { return gates[g].kind == K_MUX || gates[g].n_in > 3 ? 2 : (gates[g].n_in == 3 ? 1 : 0); };
+    auto cls = [&](uint32_t g) -> int {
+        const uint8_t k = gates[g].kind;
+        return k == K_MUX || k == K_REG || k == K_ADD || k == K_SUB || gates[g].n_in > 3 ? 2 : (gates[g].n_in == 3 ? 1 : 0);
+    };
     auto is_wide = [&](uint32_t g) { return cls(g) == 2; };
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
         const int wx = cls(x), wy = cls(y);

@@ -18,7 +18,8 @@ enum Kind : uint8_t {
     K_SLICE = 10, K_MERGE = 11,  // builder-level only (bit-blasted into K_COPY)
     K_REG = 12,  // register bit: inputs = {data bit, enable, clock, previous-clock row}; reads its own row as the stored value
     K_RAW = 13,  // hidden one-input gate: raw copy (High-Z stays High-Z) — a register's view of its clock one step ago
-    K_HGATE = 14 // builder-level only: reduction gate (kind in `select`), becomes an n-ary gate over the bits of its input
+    K_HGATE = 14, // builder-level only: reduction gate (kind in `select`), becomes an n-ary gate over the bits of its input
+    K_ADD = 15, K_SUB = 16  // one sum / difference bit: inputs = {a_0..a_{w-1}, b_0..b_{w-1}}, bit index in the nsel field
 };
 
 struct Component {
@@ -41,6 +42,7 @@ struct Builder {
     int add_mux(const uint32_t *in, size_t n, uint32_t select, uint32_t output, uint32_t *cell);
     int add_buffer(uint32_t in, uint32_t enable, uint32_t output, uint32_t *cell);
     int add_slice(uint32_t in, uint32_t offset, uint32_t output, uint32_t *cell);
+    int add_arith(int kind, uint32_t a, uint32_t b, uint32_t output, uint32_t *cell);  // K_ADD / K_SUB
     int add_horizontal_gate(int kind, uint32_t in, uint32_t output, uint32_t *cell);
     int add_register(uint32_t data_in, uint32_t data_out, uint32_t enable, uint32_t clock, uint32_t *cell);
     int add_merge(const uint32_t *in, size_t n, uint32_t output, uint32_t *cell);

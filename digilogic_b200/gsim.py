@@ -177,6 +177,18 @@ class SimulatorBuilder:
         _check(self._lib.b2_add_buffer(self._h, input, enable, output, C.byref(cell)), "add_buffer")
         return cell.value
 
+    def add_add(self, input_a, input_b, output):
+        """gsim ``SimulatorBuilder::add_add``: wrapping sum; Undefined if any input bit is not valid."""
+        cell = C.c_uint32()
+        _check(self._lib.b2_add_add(self._h, input_a, input_b, output, C.byref(cell)), "add_add")
+        return cell.value
+
+    def add_sub(self, input_a, input_b, output):
+        """gsim ``SimulatorBuilder::add_sub``: wrapping difference; Undefined if any input bit is not valid."""
+        cell = C.c_uint32()
+        _check(self._lib.b2_add_sub(self._h, input_a, input_b, output, C.byref(cell)), "add_sub")
+        return cell.value
+
     def add_horizontal_gate(self, kind, input, output):
         """gsim ``add_horizontal_{and,or,xor,nand,nor,xnor}_gate``: the gate folded over all bits of one wire."""
         cell = C.c_uint32()

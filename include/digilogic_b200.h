@@ -97,6 +97,12 @@ int b2_add_mux(b2_builder *b, const uint32_t *inputs, size_t n, uint32_t select,
    always run the unit-delay path.  Errors: InvalidWireId, WireWidthMismatch (input vs output),
    WireWidthIncompatible (enable wider than one bit). */
 int b2_add_buffer(b2_builder *b, uint32_t input, uint32_t enable, uint32_t output, uint32_t *out_cell);
+/* SimulatorBuilder::add_add / add_sub(input_a, input_b, output): output = a + b or a - b modulo 2^width; the whole output is
+   Undefined if any bit of either input is not a valid 0/1.  All three wires have one width (WireWidthMismatch).  No call site
+   in the reference (Yosys Add/Sub are todo!(), crates/digilogic_serde/src/yosys.rs:188-189).  Each result bit is one gate on
+   the CSR kernel reading the input bits below it: correct for every width, quadratic in it. */
+int b2_add_add(b2_builder *b, uint32_t input_a, uint32_t input_b, uint32_t output, uint32_t *out_cell);
+int b2_add_sub(b2_builder *b, uint32_t input_a, uint32_t input_b, uint32_t output, uint32_t *out_cell);
 /* SimulatorBuilder::add_horizontal_{and,or,xor,nand,nor,xnor}_gate(input, output): the one-bit output is the gate folded over
    all bits of `input` (kind = B2_AND .. B2_XNOR); compiled into an ordinary n-ary gate over the input's bit rows.  No call site
    in the reference (Yosys ReduceAnd/Or/Xor/Xnor/Bool are todo!(), crates/digilogic_serde/src/yosys.rs:163-167).

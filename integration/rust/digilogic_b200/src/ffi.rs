@@ -26,6 +26,8 @@ extern "C" {
     pub fn b2_add_gate(b: *mut B2Builder, kind: c_int, inputs: *const u32, n: usize, output: u32, out_cell: *mut u32) -> c_int; // add_*_gate :95
     pub fn b2_add_not(b: *mut B2Builder, input: u32, output: u32, out_cell: *mut u32) -> c_int; // add_not_gate :165
     pub fn b2_add_buffer(b: *mut B2Builder, input: u32, enable: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_buffer (no call site in digilogic_gsim yet)
+    pub fn b2_add_add(b: *mut B2Builder, input_a: u32, input_b: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_add
+    pub fn b2_add_sub(b: *mut B2Builder, input_a: u32, input_b: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_sub
     pub fn b2_add_horizontal_gate(b: *mut B2Builder, kind: c_int, input: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_horizontal_*_gate
     pub fn b2_add_register(b: *mut B2Builder, data_in: u32, data_out: u32, enable: u32, clock: u32, out_cell: *mut u32) -> c_int; // gsim add_register
     pub fn b2_add_slice(b: *mut B2Builder, input: u32, offset: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_slice

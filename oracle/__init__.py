@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libgsim_oracle.so")
 
-AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX, BUF, SLICE, MERGE, REG = range(12)
+AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX, BUF, SLICE, MERGE, REG, HGATE, ADD, SUB = range(15)
 RUN_OK, RUN_MAX_STEPS, RUN_CONFLICT = 0, 1, 2
 ERR_NAMES = {
     0: "Ok", 1: "TooManyComponents", 2: "InvalidWireId", 3: "WireWidthMismatch",
@@ -61,6 +61,7 @@ def lib():
             "go_set_copy_z_passthrough": (None, [C.c_int]),
             "go_add_register": (C.c_int, [vp, u32, u32, u32, u32, pu32]),
             "go_add_horizontal_gate": (C.c_int, [vp, C.c_int, u32, u32, pu32]),
+            "go_add_arith": (C.c_int, [vp, C.c_int, u32, u32, u32, pu32]),
             "go_add_slice": (C.c_int, [vp, u32, u32, u32, pu32]),
             "go_add_merge": (C.c_int, [vp, pu32, u32, u32, pu32]),
             "go_add_gates2": (C.c_int, [vp, vp, vp, vp, vp, u32]),
@@ -194,6 +195,16 @@ class Builder:
     def add_horizontal_nand_gate(self, input, output): return self.add_horizontal_gate(NAND, input, output)
     def add_horizontal_nor_gate(self, input, output): return self.add_horizontal_gate(NOR, input, output)
     def add_horizontal_xnor_gate(self, input, output): return self.add_horizontal_gate(XNOR, input, output)
+
+    def _arith(self, kind, a, b, output):
+        cell = C.c_uint32()
+        rc = lib().go_add_arith(self._h, kind, a, b, output, C.byref(cell))
+        if rc:
+            raise OracleError(rc)
+        return cell.value
+
+    def add_add(self, input_a, input_b, output): return self._arith(ADD, input_a, input_b, output)
+    def add_sub(self, input_a, input_b, output): return self._arith(SUB, input_a, input_b, output)
 
     def add_register(self, data_in, data_out, enable, clock):
         cell = C.c_uint32()

@@ -174,6 +174,11 @@ static inline void eval_comp(const bs_sim *s, const comp_t *cp, const uint64_t *
         m = (take & dm) | (keep & s->rdm[si]);
         v = (take & (dv | ~dm)) | (keep & s->rdv[si]) | undef;
         s->ndv[si] = v; s->ndm[si] = m; s->npv[si] = cv; s->npm[si] = cm;
+    } else if (cp->kind == GO_ADD || cp->kind == GO_SUB) {
+        /* 1-bit wires: sum and difference modulo 2 are both XOR; any invalid input bit makes the output Undefined */
+        uint64_t a = wv[(size_t)in[0] * T + k], b2 = wv[(size_t)in[1] * T + k];
+        m = wm[(size_t)in[0] * T + k] & wm[(size_t)in[1] * T + k];
+        v = (a ^ b2) | ~m;
     } else if (cp->kind == GO_HGATE) {
         /* 1-bit wires: a reduction over one bit is the bit itself (High-Z read as X), inverted for NAND/NOR/XNOR */
         uint64_t a = wv[(size_t)in[0] * T + k]; m = wm[(size_t)in[0] * T + k];

@@ -11,6 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import oracle  # noqa: E402
 
 KIND = {"and": 0, "or": 1, "xor": 2, "nand": 3, "nor": 4, "xnor": 5}
+HKIND = {"h" + k: v for k, v in KIND.items()}
 RESULT = {0: "Ok", 1: "MaxStepsReached", 2: "Err"}
 
 
@@ -36,6 +37,10 @@ def main(cases_path, dump_path):
                 b.add_merge(c["inputs"], c["output"])
             elif c["kind"] == "register":
                 b.add_register(c["inputs"][0], c["output"], c["inputs"][1], c["inputs"][2])
+            elif c["kind"] in ("add", "sub"):
+                (b.add_add if c["kind"] == "add" else b.add_sub)(c["inputs"][0], c["inputs"][1], c["output"])
+            elif c["kind"] in HKIND:
+                b.add_horizontal_gate(HKIND[c["kind"]], c["inputs"][0], c["output"])
             else:
                 b.add_gate(KIND[c["kind"]], c["inputs"], c["output"])
         sim = b.build()

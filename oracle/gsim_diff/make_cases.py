@@ -82,6 +82,15 @@ def cases():
                 "runs": [{"drives": d, "max_steps": ms} for d, ms in (
                     ([drive(2, L1), drive(3, L0)], 10), ([drive(3, L1)], 10), ([drive(3, L0)], 0), ([drive(3, L1)], 0), ([drive(3, L0)], 1),
                     ([drive(3, L1)], 1), ([drive(3, L0)], 10), ([drive(3, L1)], 10))]})
+    # arithmetic and reduction gates: wrap-around, one invalid bit poisoning the whole sum, reductions with unknown bits
+    out.append({"name": "add_sub_8", "wires": [8, 8, 8, 8],
+                "comps": [{"kind": "add", "inputs": [0, 1], "output": 2}, {"kind": "sub", "inputs": [0, 1], "output": 3}],
+                "runs": [{"drives": [[0, [x], [ma]], [1, [y], [mb]]], "max_steps": 10} for x, y, ma, mb in
+                         ((200, 100, 255, 255), (3, 5, 255, 255), (255, 1, 255, 255), (5, 3, 254, 255), (5, 3, 255, 127), (0, 0, 0, 0))]})
+    out.append({"name": "horizontal_gates_4", "wires": [4, 1, 1, 1, 1, 1, 1],
+                "comps": [{"kind": k, "inputs": [0], "output": i + 1} for i, k in enumerate(("hand", "hor", "hxor", "hnand", "hnor", "hxnor"))],
+                "runs": [{"drives": [[0, [v], [m]]], "max_steps": 10} for v, m in
+                         ((0xF, 0xF), (0x0, 0xF), (0x5, 0xF), (0xF, 0x7), (0x0, 0xE), (0x8, 0x8), (0x0, 0x0))]})
     # random cyclic netlists, max_steps sweep
     rng = np.random.default_rng(1)
     for n in range(4):

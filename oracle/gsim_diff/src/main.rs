@@ -7,7 +7,7 @@ use std::num::NonZeroU8;
 
 #[derive(Deserialize)]
 struct Comp {
-    kind: String, // and | or | xor | nand | nor | xnor | not | mux | buffer (inputs = [data, enable]) | slice (select = offset) | merge | register (inputs = [data_in, enable, clock])
+    kind: String, // and | or | xor | nand | nor | xnor | not | mux | buffer (inputs = [data, enable]) | slice (select = offset) | merge | register (inputs = [data_in, enable, clock]) | add | sub | hand..hxnor (horizontal gates)
     inputs: Vec<u32>,
     select: Option<u32>,
     output: u32,
@@ -60,6 +60,14 @@ fn main() {
                 "slice" => builder.add_slice(ins[0], c.select.unwrap() as u8, o),
                 "merge" => builder.add_merge(&ins, o),
                 "register" => builder.add_register(ins[0], o, ins[1], ins[2]),
+                "add" => builder.add_add(ins[0], ins[1], o),
+                "sub" => builder.add_sub(ins[0], ins[1], o),
+                "hand" => builder.add_horizontal_and_gate(ins[0], o),
+                "hor" => builder.add_horizontal_or_gate(ins[0], o),
+                "hxor" => builder.add_horizontal_xor_gate(ins[0], o),
+                "hnand" => builder.add_horizontal_nand_gate(ins[0], o),
+                "hnor" => builder.add_horizontal_nor_gate(ins[0], o),
+                "hxnor" => builder.add_horizontal_xnor_gate(ins[0], o),
                 k => panic!("unknown kind {k}"),
             };
             build_errors.push(r.err().map(|e| format!("{e:?}")));

@@ -181,6 +181,17 @@ int go_add_horizontal_gate(go_builder *b, int kind, uint32_t input, uint32_t out
     return push_comp(b, GO_HGATE, &input, 1, (uint32_t)kind, output, cell);
 }
 
+/* add_add / add_sub(input_a, input_b, output): gsim's adder and subtractor (the Yosys importer's Add/Sub arms are
+   todo!(), crates/digilogic_serde/src/yosys.rs:188-189).  All three wires have one width; the result wraps; if any bit of
+   either input is not a valid 0/1 the whole output is Undefined. */
+int go_add_arith(go_builder *b, int kind, uint32_t a, uint32_t c, uint32_t output, uint32_t *cell) {
+    if (kind != GO_ADD && kind != GO_SUB) return GO_ERR_INVALID_INPUT_COUNT;
+    if (output >= b->n_wires || a >= b->n_wires || c >= b->n_wires) return GO_ERR_INVALID_WIRE_ID;
+    if (b->width[a] != b->width[output] || b->width[c] != b->width[output]) return GO_ERR_WIRE_WIDTH_MISMATCH;
+    uint32_t in[2] = {a, c};
+    return push_comp(b, (uint8_t)kind, in, 2, 0, output, cell);
+}
+
 /* Bulk 2-input gate add used by the large generators (same validation per gate). */
 int go_add_gates2(go_builder *b, const uint8_t *kinds, const uint32_t *in0, const uint32_t *in1, const uint32_t *out, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) {
@@ -397,6 +408,24 @@ static int eval_component(go_sim *s, uint32_t c) {
                 if (!vl && !g_cfg.copy_z_passthrough) st = 1;
                 res[j >> 5].state |= st << (j & 31);
                 res[j >> 5].valid |= vl << (j & 31);
+            }
+        }
+    } else if (cp->kind == GO_ADD || cp->kind == GO_SUB) {
+        const atom_t *a = s->state + s->atom_off[in[0]], *b2 = s->state + s->atom_off[in[1]];
+        int all_valid = 1;
+        for (uint32_t i = 0; i < na; i++) {
+            uint32_t m = atom_mask(width, i);
+            if ((a[i].valid & m) != m || (b2[i].valid & m) != m) all_valid = 0;
+        }
+        if (!all_valid) {
+            for (uint32_t i = 0; i < na; i++) { res[i].state = 0xFFFFFFFFu; res[i].valid = 0; }
+        } else {
+            uint64_t carry = cp->kind == GO_SUB ? 1 : 0;
+            for (uint32_t i = 0; i < na; i++) {
+                uint64_t y = cp->kind == GO_SUB ? (uint32_t)~b2[i].state : b2[i].state;
+                uint64_t sum = (uint64_t)a[i].state + y + carry;
+                res[i].state = (uint32_t)sum; res[i].valid = 0xFFFFFFFFu;
+                carry = sum >> 32;
             }
         }
     } else if (cp->kind == GO_HGATE) {

@@ -12,7 +12,8 @@ enum { GO_AND = 0, GO_OR = 1, GO_XOR = 2, GO_NAND = 3, GO_NOR = 4, GO_XNOR = 5, 
        GO_SLICE = 9,  /* output = input[offset .. offset + width(output)); offset in `select` */
        GO_MERGE = 10, /* output = inputs concatenated, inputs[0] in the low bits */
        GO_REG = 11,   /* register: inputs = {data_in, enable (1 bit), clock (1 bit)}; loads data_in on a rising clock edge */
-       GO_HGATE = 12  /* horizontal (reduction) gate: the 1-bit output is the AND/OR/.. (kind in `select`) of all bits of inputs[0] */ };
+       GO_HGATE = 12, /* horizontal (reduction) gate: the 1-bit output is the AND/OR/.. (kind in `select`) of all bits of inputs[0] */
+       GO_ADD = 13, GO_SUB = 14 /* output = inputs[0] +/- inputs[1] modulo 2^width; Undefined if any input bit is not valid */ };
 
 /* AddComponentError ordinals, names pinned by crates/digilogic_gsim/src/lib.rs:55-66 */
 enum {

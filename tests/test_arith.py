@@ -1,0 +1,136 @@
+"""Adders and subtractors (gsim add_add / add_sub): known answers against Python integers on the
+CPU oracle, the engine against the oracle on the GPU, and a counter built from a register and an adder."""
+import numpy as np
+import pytest
+
+import oracle
+
+WIDTHS = [1, 4, 33, 64, 255]
+
+
+def build(b):
+    w = {}
+    for n in WIDTHS:
+        a, c, s, d = b.add_wire(n), b.add_wire(n), b.add_wire(n), b.add_wire(n)
+        b.add_add(a, c, s)
+        b.add_sub(a, c, d)
+        w[n] = (a, c, s, d)
+    return w
+
+
+def stimuli(rng, n, count=6):
+    full = (1 << n) - 1
+    out = [(0, 0, full, full), (full, 1 & full, full, full), (full, full, full, full)]
+    for _ in range(count):
+        x = int.from_bytes(rng.bytes(32), "little") & full
+        y = int.from_bytes(rng.bytes(32), "little") & full
+        out.append((x, y, full, full))
+    out.append((5 & full, 3 & full, full ^ 1, full))          # one High-Z / X bit in a: everything Undefined
+    out.append((5 & full, 3 & full, full, full ^ (1 << (n - 1))))
+    return out
+
+
+def expect(x, y, ma, mb, n):
+    full = (1 << n) - 1
+    if ma != full or mb != full:
+        return (full, 0), (full, 0)
+    return ((x + y) & full, full), ((x - y) & full, full)
+
+
+def test_add_sub_known_answers_and_validation():
+    b = oracle.Builder()
+    w8, w4 = b.add_wire(8), b.add_wire(4)
+    with pytest.raises(oracle.OracleError, match="WireWidthMismatch"):
+        b.add_add(w8, w4, w8)
+    with pytest.raises(oracle.OracleError, match="WireWidthMismatch"):
+        b.add_sub(w8, w8, w4)
+    with pytest.raises(oracle.OracleError, match="InvalidWireId"):
+        b.add_add(w8, 99, w8)
+    b = oracle.Builder()
+    w = build(b)
+    sim = b.build()
+    rng = np.random.default_rng(21)
+    for n in WIDTHS:
+        a, c, s, d = w[n]
+        for x, y, ma, mb in stimuli(rng, n):
+            sim.set_wire_drive(a, x, ma)
+            sim.set_wire_drive(c, y, mb)
+            assert sim.run_sim(10) == oracle.RUN_OK
+            es, ed = expect(x, y, ma, mb, n)
+            assert sim.get_wire_state(s) == es and sim.get_wire_state(d) == ed, (n, hex(x), hex(y))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [1, 0])
+def test_add_sub_on_gpu_against_oracle(resident):
+    from digilogic_b200 import AddComponentError, LogicState, SimulatorBuilder
+    from digilogic_b200.gsim import ComponentError
+    vb = SimulatorBuilder()
+    w8, w4 = vb.add_wire(8), vb.add_wire(4)
+    with pytest.raises(ComponentError) as e:
+        vb.add_add(w8, w4, w8)
+    assert e.value.error == AddComponentError.WireWidthMismatch
+    ob, gb = oracle.Builder(), SimulatorBuilder()
+    w = build(ob)
+    build(gb)
+    ref, sim = ob.build(), gb.build()
+    sim.set_option(sim.OPT_RESIDENT_KERNEL, resident)
+    rng = np.random.default_rng(22)
+    for rnd in range(8):
+        for n in WIDTHS:
+            a, c, s, d = w[n]
+            x, y, ma, mb = stimuli(rng, n, count=1)[3 if rnd < 6 else 4 + rnd % 2]
+            ref.set_wire_drive(a, x, ma); ref.set_wire_drive(c, y, mb)
+            sim.set_wire_drive(a, LogicState(x, ma)); sim.set_wire_drive(c, LogicState(y, mb))
+        ms = (10, 0, 1, 10)[rnd % 4]
+        assert int(sim.run_sim(ms)) == ref.run_sim(ms)
+        for n in WIDTHS:
+            for wire in w[n][2:]:
+                assert sim.get_wire_state(wire) == LogicState(*ref.get_wire_state(wire)), (rnd, n)
+
+
+def counter(b, bits=8):
+    """q <= q + 1 on every rising clock edge while enable; `clr` forces the next value to 0 (AND with NOT clr)."""
+    ck, en, clr, nclr = b.add_wire(), b.add_wire(), b.add_wire(), b.add_wire()
+    one, q, inc, nclr_w, d = (b.add_wire(bits) for _ in range(5))
+    b.add_not_gate(clr, nclr)
+    b.add_merge([nclr] * bits, nclr_w)
+    b.add_add(q, one, inc)
+    b.add_and_gate([inc, nclr_w], d)
+    b.add_register(d, q, en, ck)
+    return ck, en, clr, one, q
+
+
+def test_counter_of_register_and_adder_on_oracle():
+    b = oracle.Builder()
+    ck, en, clr, one, q = counter(b)
+    sim = b.build()
+    sim.set_wire_drive(one, 1, 0xFF); sim.set_wire_drive(en, 1, 1); sim.set_wire_drive(clr, 1, 1); sim.set_wire_drive(ck, 0, 1)
+    assert sim.run_sim(100) == oracle.RUN_OK
+    sim.set_wire_drive(ck, 1, 1); assert sim.run_sim(100) == oracle.RUN_OK     # loads 0
+    sim.set_wire_drive(clr, 0, 1); sim.set_wire_drive(ck, 0, 1); assert sim.run_sim(100) == oracle.RUN_OK
+    assert sim.get_wire_state(q) == (0, 0xFF)
+    for n in range(1, 300):
+        sim.set_wire_drive(ck, 1, 1); assert sim.run_sim(100) == oracle.RUN_OK
+        sim.set_wire_drive(ck, 0, 1); assert sim.run_sim(100) == oracle.RUN_OK
+        assert sim.get_wire_state(q) == (n & 0xFF, 0xFF), n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [1, 0])
+def test_counter_on_gpu(resident):
+    from digilogic_b200 import LogicState, SimulationRunResult, SimulatorBuilder
+    b = SimulatorBuilder()
+    ck, en, clr, one, q = counter(b)
+    sim = b.build()
+    sim.set_option(sim.OPT_RESIDENT_KERNEL, resident)
+    hi, lo = LogicState(1, 1), LogicState(0, 1)
+    sim.set_wire_drive(one, LogicState(1, 0xFF)); sim.set_wire_drive(en, hi); sim.set_wire_drive(clr, hi); sim.set_wire_drive(ck, lo)
+    assert sim.run_sim(100) == SimulationRunResult.Ok
+    sim.set_wire_drive(ck, hi); assert sim.run_sim(100) == SimulationRunResult.Ok
+    sim.set_wire_drive(clr, lo); sim.set_wire_drive(ck, lo); assert sim.run_sim(100) == SimulationRunResult.Ok
+    assert sim.get_wire_state(q) == LogicState(0, 0xFF)
+    for n in range(1, 300):
+        sim.set_wire_drive(ck, hi); assert sim.run_sim(100) == SimulationRunResult.Ok
+        sim.set_wire_drive(ck, lo); assert sim.run_sim(100) == SimulationRunResult.Ok
+        assert sim.get_wire_state(q) == LogicState(n & 0xFF, 0xFF), n

@@ -31,6 +31,10 @@ def build(case, builder):
             builder.add_merge(c["inputs"], c["output"])
         elif c["kind"] == "register":
             builder.add_register(c["inputs"][0], c["output"], c["inputs"][1], c["inputs"][2])
+        elif c["kind"] in ("add", "sub"):
+            (builder.add_add if c["kind"] == "add" else builder.add_sub)(c["inputs"][0], c["inputs"][1], c["output"])
+        elif c["kind"] in compare.HKIND:
+            builder.add_horizontal_gate(compare.HKIND[c["kind"]], c["inputs"][0], c["output"])
         else:
             builder.add_gate(compare.KIND[c["kind"]], c["inputs"], c["output"])
     return builder.build()
@@ -53,7 +57,7 @@ def oracle_dump(cases):
 
 def test_harness_python_side(tmp_path):
     cases = make_cases.cases()
-    assert len(cases) >= 21
+    assert len(cases) >= 23
     cp, dp = tmp_path / "cases.json", tmp_path / "dump.json"
     cp.write_text(json.dumps(cases))
     dp.write_text(json.dumps(oracle_dump(cases)))
