@@ -500,9 +500,25 @@ __device__ __forceinline__ ulonglong2 ld_valid(const WideArgs &a, uint32_t row, 
 
 // n-ary gates (left fold, inverted kinds invert once at the end) and multiplexer slices.
 template <bool JACOBI>
+__device__ __forceinline__ void eval_wide_gate(const WideArgs &a, uint32_t pb, uint32_t g);
+
+template <bool JACOBI>
 __device__ __forceinline__ void eval_wide_body(const WideArgs &a, uint32_t pb, uint32_t gb) {
+    eval_wide_gate<JACOBI>(a, pb, a.g_begin + gb * blockDim.y + threadIdx.y);
+}
+
+// wide gates named by a work list (unit-delay frontier): the scan has already decided that they have to be evaluated
+__device__ __forceinline__ void eval_wide_list_body(WideArgs a, const uint32_t *list, const uint32_t *count, uint32_t bid,
+                                                    uint32_t nblk) {
+    const uint32_t n = *count;
+    const uint32_t pb = bid % a.pair_blocks, gbi = bid / a.pair_blocks, gbs = nblk / a.pair_blocks;
+    a.chg_prev = nullptr;
+    for (uint32_t i = gbi * blockDim.y + threadIdx.y; i < n; i += gbs * blockDim.y) eval_wide_gate<true>(a, pb, list[i]);
+}
+
+template <bool JACOBI>
+__device__ __forceinline__ void eval_wide_gate(const WideArgs &a, uint32_t pb, uint32_t g) {
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
-    const uint32_t g = a.g_begin + gb * blockDim.y + threadIdx.y;
     if (pair >= a.pairs || g >= a.g_end) return;
     const size_t col = (size_t)pair * 2;
     const uint32_t b = a.off[g], e = a.off[g + 1];
@@ -611,6 +627,38 @@ __device__ __forceinline__ void eval_wide_body(const WideArgs &a, uint32_t pb, u
 template <bool JACOBI>
 __global__ void __launch_bounds__(256) k_eval_wide(const WideArgs a) {
     eval_wide_body<JACOBI>(a, blockIdx.x % a.pair_blocks, blockIdx.x / a.pair_blocks);
+}
+
+__global__ void __launch_bounds__(256) k_eval_wide_list(const WideArgs a, const uint32_t *list, const uint32_t *count) {
+    eval_wide_list_body(a, list, count, blockIdx.x, gridDim.x);
+}
+
+// Frontier scan of the wide gates (n-ary gates, mux slices, registers, adder bits): listed when an input row or the
+// gate's own row changed in the previous application (chg_prev == nullptr: all of them).
+__device__ __forceinline__ void frontier_scan_wide_body(const uint32_t *off, const uint32_t *in, uint32_t n_wide, uint32_t row_base,
+                                                        const uint8_t *chg_prev, uint32_t *list, uint32_t *count, uint32_t tid,
+                                                        uint32_t g) {
+    bool act = false;
+    if (g < n_wide) {
+        if (!chg_prev) {
+            act = true;
+        } else {
+            uint32_t any = chg_prev[row_base + g];
+            for (uint32_t i = off[g]; i < off[g + 1] && !any; i++) any |= chg_prev[in[i]];
+            act = any != 0;
+        }
+    }
+    const uint32_t lane = tid & 31;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, act);
+    uint32_t base = 0;
+    if (lane == 0 && m) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (act) list[base + __popc(m & ((1u << lane) - 1))] = g;
+}
+
+__global__ void __launch_bounds__(256) k_frontier_scan_wide(const uint32_t *off, const uint32_t *in, uint32_t n_wide, uint32_t row_base,
+                                                            const uint8_t *chg_prev, uint32_t *list, uint32_t *count) {
+    frontier_scan_wide_body(off, in, n_wide, row_base, chg_prev, list, count, threadIdx.x, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // Source rows take their external drive: out[row] = D[row] (rows [0, n_rows) of both stores).
@@ -797,7 +845,7 @@ __global__ void __launch_bounds__(256) k_status_step(uint64_t *changed, uint64_t
         next_flags->any_live = 0;
         next_flags->any_conflict = 0;
         next_flags->any_unsettled = 0;
-        flags->active = counts ? counts[0] + counts[1] + counts[2] : 0xFFFFFFFFu;
+        flags->active = counts ? counts[0] + counts[1] + counts[2] + counts[3] : 0xFFFFFFFFu;
     }
     status_step_body(changed, conf_step, live, conflict, unsettled, flags, words, n_lanes, count_conflicts, is_last, w, threadIdx.x & 31);
 }
@@ -937,7 +985,7 @@ struct LoopArgs {
     const uint64_t *drv_val, *drv_vld;
     uint8_t *chg[2];
     uint4 *list2, *list3;
-    uint32_t *listc;
+    uint32_t *listc, *listw;
     uint32_t *cnt;  // list counters, [2][4]: application parity x {one/two-input, three-input, refresh, -}; zero on entry
     uint64_t *changed, *conf_step, *live, *conflict, *unsettled;
     RunFlags *flags;  // kFlagSlots slots, all clear on entry
@@ -963,6 +1011,9 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
     for (uint32_t base = bid * 256; base < a.n_fast; base += nblk * 256)
         frontier_scan_body(a.fan0, a.fan1, a.fan2, a.n_g2, a.n_fast, a.n_src, a.kind2, a.frontier_valid ? a.chg[cw ^ 1] : nullptr,
                            a.list2, a.list3, a.listc, a.cnt + 4 * (first_k & 1), lt, base + lt);
+    for (uint32_t base = bid * 256; base < a.n_wide; base += nblk * 256)
+        frontier_scan_wide_body(a.wide.off, a.wide.in, a.n_wide, a.wide.row_base, a.frontier_valid ? a.chg[cw ^ 1] : nullptr, a.listw,
+                                a.cnt + 4 * (first_k & 1) + 3, lt, base + lt);
     grid.sync();
     for (;;) {
         k++;
@@ -974,7 +1025,7 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
         const uint32_t *counts = a.cnt + 4 * (k & 1);
         RunFlags *flags = a.flags + (k % 8);
         if (k > first_k) {  // a long work list is better served by the separate, fully occupied kernels
-            const uint64_t listed = (uint64_t)counts[0] + counts[1] + counts[2];
+            const uint64_t listed = (uint64_t)counts[0] + counts[1] + counts[2] + counts[3];
             if (listed * a.stride > a.bail_row_words) {
                 bailed = true;
                 k--;
@@ -998,8 +1049,8 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
             if (a.n_wide) {
                 WideArgs w = a.wide;
                 w.in_val = AV; w.in_vld = AM; w.out_val = BV; w.out_vld = BM;
-                w.chg_prev = chg_prev; w.chg_cur = chg_cur;
-                for (uint32_t gb = gbi; gb * blockDim.y < a.n_wide; gb += gbs) eval_wide_body<true>(w, pb, gb);
+                w.chg_prev = nullptr; w.chg_cur = chg_cur;
+                eval_wide_list_body(w, a.listw, counts + 3, bid, nblk);
             }
         }
         grid.sync();
@@ -1030,6 +1081,10 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
             for (uint32_t base = bid * 256; base < a.n_fast; base += nblk * 256)
                 frontier_scan_body(a.fan0, a.fan1, a.fan2, a.n_g2, a.n_fast, a.n_src, a.kind2, chg_cur, a.list2, a.list3, a.listc,
                                    a.cnt + 4 * ((k + 1) & 1), lt, base + lt);
+        if (!is_last)
+            for (uint32_t base = bid * 256; base < a.n_wide; base += nblk * 256)
+                frontier_scan_wide_body(a.wide.off, a.wide.in, a.n_wide, a.wide.row_base, chg_cur, a.listw, a.cnt + 4 * ((k + 1) & 1) + 3,
+                                        lt, base + lt);
         grid.sync();
         const uint32_t any_live = *(volatile uint32_t *)&flags->any_live;
         cw ^= 1;
@@ -1507,6 +1562,7 @@ int Engine::ensure_device() {
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_list_[0], k_eval_list<2>, 256, 0));
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_list_[1], k_eval_list<3>, 256, 0));
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_list_[2], k_copy_list, 256, 0));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_list_[3], k_eval_wide_list, 256, 0));
     for (int &o : occ_list_) o = std::max(1, std::min(o, 4));
     {
         int coop = 0, occ = 0;
@@ -2167,6 +2223,7 @@ int Engine::run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &res
     }
     la.drv_val = drv_val_; la.drv_vld = drv_vld_;
     la.list2 = (uint4 *)d_act_list_[0]; la.list3 = (uint4 *)d_act_list_[1]; la.listc = d_act_list_[2];
+    la.listw = d_act_list_[3];
     la.cnt = (uint32_t *)(d_loop_result_ + 1);  // behind the result block
     CU_TRY(cudaMemsetAsync(la.cnt, 0, 8 * sizeof(uint32_t), ST));
     la.changed = d_changed_; la.conf_step = d_conf_step_; la.live = d_live_; la.conflict = d_conflict_; la.unsettled = d_unsettled_;
@@ -2263,14 +2320,15 @@ int Engine::run_jacobi(uint64_t max_steps) {
         CU_TRY(cudaMalloc((void **)&d_act_list_[0], (size_t)std::max<uint32_t>(net_.n_g2(), 1) * 16));
         CU_TRY(cudaMalloc((void **)&d_act_list_[1], (size_t)std::max<uint32_t>(net_.n_g3(), 1) * 16));
         CU_TRY(cudaMalloc((void **)&d_act_list_[2], (size_t)std::max<uint32_t>(net_.n_fast(), 1) * 4));
-        store_bytes_ += 2 * rowchg_bytes() + (size_t)net_.n_fast() * 20;
+        CU_TRY(cudaMalloc((void **)&d_act_list_[3], (size_t)std::max<uint32_t>(net_.n_wide(), 1) * 4));
+        store_bytes_ += 2 * rowchg_bytes() + (size_t)net_.n_fast() * 20 + (size_t)net_.n_wide() * 4;
         frontier_valid_ = false;
     }
     if (!use_frontier) frontier_valid_ = false;
     // Light applications (a short work list times the row length) run in the device-side loop, heavy ones as
     // separate fully occupied kernels; the run moves between the two as the activity changes.
     const bool device_ok = opt_device_loop_ && use_frontier && loop_ctas_ >= sh.pair_blocks;
-    bool want_device = device_ok && (uint64_t)net_.n_fast() * stride_ <= kLoopEntryRowWords;
+    bool want_device = device_ok && (uint64_t)(net_.n_fast() + net_.n_wide()) * stride_ <= kLoopEntryRowWords;
     const uint64_t first_k = k + 1;
     uint64_t lag_base = first_k;  // first application of the current host-driven stretch
     uint32_t light_streak = 0;
@@ -2357,9 +2415,20 @@ int Engine::run_jacobi(uint64_t max_steps) {
         if (net_.n_wide()) {
             WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, AV, AM, BV, BM, d_changed_, 0, net_.n_wide(),
                        net_.n_src + net_.n_fast(), stride_, pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
-            const uint32_t gb = (net_.n_wide() + sh.block.y - 1) / sh.block.y;
-            k_eval_wide<true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
-            LAUNCHED();
+            if (chg_prev) {  // event-driven: list the wide gates with a changed input, evaluate the list
+                k_frontier_scan_wide<<<(net_.n_wide() + 255) / 256, 256, 0, ST>>>(d_wide_off_, d_wide_in_, net_.n_wide(),
+                                                                                  net_.n_src + net_.n_fast(), chg_prev, d_act_list_[3],
+                                                                                  act_counts + 3);
+                LAUNCHED();
+                const uint32_t slots_w = std::max<uint32_t>(1, (uint32_t)(sm_count_ * occ_list_[3]) / sh.pair_blocks);
+                const uint32_t gbs = std::min<uint32_t>((net_.n_wide() + sh.block.y - 1) / sh.block.y, slots_w);
+                k_eval_wide_list<<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, d_act_list_[3], act_counts + 3);
+                LAUNCHED();
+            } else {
+                const uint32_t gb = (net_.n_wide() + sh.block.y - 1) / sh.block.y;
+                k_eval_wide<true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                LAUNCHED();
+            }
         }
         if (use_frontier) {
             frontier_valid_ = true;

@@ -162,7 +162,7 @@ class Engine {
     bool opt_graph_ = true;
     // unit-delay changed-row frontier
     uint8_t *d_rowchg_[2] = {nullptr, nullptr};
-    uint32_t *d_act_list_[3] = {nullptr, nullptr, nullptr};  // compacted work lists: one/two-input gates, three-input gates, rows to refresh
+    uint32_t *d_act_list_[4] = {nullptr, nullptr, nullptr, nullptr};  // compacted work lists: one/two-input gates, three-input gates, rows to refresh, wide gates
     size_t rowchg_bytes() const { return (((size_t)net_.n_rows + 15) & ~(size_t)15) + 16; }  // flags, padding, the list counters
     // device-side run_sim loop (k_unit_delay_loop): CTAs of one cooperative launch, result block
     uint32_t loop_ctas_ = 0;
@@ -170,7 +170,7 @@ class Engine {
     void *h_loop_result_ = nullptr;
     bool opt_device_loop_ = true;
     int sm_count_ = 148;
-    int occ_list_[3] = {3, 2, 4};  // resident CTAs per SM of k_eval_list<2>, k_eval_list<3>, k_copy_list
+    int occ_list_[4] = {3, 2, 4, 4};  // resident CTAs per SM of k_eval_list<2>, k_eval_list<3>, k_copy_list, k_eval_wide_list
     int chg_w_ = 0;
     bool frontier_valid_ = false, opt_frontier_ = true;
     bool opt_budget_inclusive_ = false;  // SURVEY.md A.6-1 switch: `steps >= max_steps` instead of `>`
