@@ -194,6 +194,67 @@ def config4(args):
     assert bad == 0 and oracle_ok in (None, True)
 
 
+def config4_registers(args):
+    """Config 4 rebuilt with gsim's register component instead of NAND flip-flops (same LFSR chains and SR latches)."""
+    from digilogic_b200 import SimulationRunResult, SimulatorBuilder, netgen
+    bits, chains, latches = args.bits, args.chains, args.latches
+    n_lanes = args.lanes
+    seq = netgen.sequential_registers(n_latches=latches, n_chains=chains, bits=bits)
+    taps = [bits - 1, bits - 2, bits - 4, bits - 5]
+    sim = seq.emit(SimulatorBuilder()).build()
+    sim.set_option(sim.OPT_RESIDENT_KERNEL, 0 if args.no_resident else 1)
+    sim.set_option(sim.OPT_DEVICE_LOOP, 0 if args.host_loop else 1)
+    sim.set_lanes(n_lanes)
+    words = (n_lanes + 63) // 64
+    ones, zeros = np.full(words, ALL1, np.uint64), np.zeros(words, np.uint64)
+    rng = np.random.default_rng(4)
+    patterns = [rng.integers(0, 1 << 64, words, dtype=np.uint64) for _ in range(bits)]
+
+    def run():
+        res, _, _ = sim.run_sim_lanes(10_000, masks=False)
+        assert res == SimulationRunResult.Ok
+        return sim.info.last_applications
+
+    sim.set_wire_drive_lanes(seq.enable, ones, ones)
+    sim.set_wire_drive_lanes(seq.load, ones, ones)
+    sim.set_wire_drive_lanes(seq.clk, zeros, ones)
+    for b in range(bits):
+        sim.set_wire_drive_lanes(seq.init[b], patterns[b], ones)
+    run()
+    sim.set_wire_drive_lanes(seq.clk, ones, ones)
+    run()
+    sim.set_wire_drive_lanes(seq.load, zeros, ones)
+    sim.set_wire_drive_lanes(seq.clk, zeros, ones)
+    run()
+    sim.synchronize()
+    apps, t_gpu = 0, 0.0
+    for _ in range(args.clocks):
+        for level in (ones, zeros):
+            sim.set_wire_drive_lanes(seq.clk, level, ones)
+            t0 = time.perf_counter()
+            apps += run()
+            t_gpu += time.perf_counter() - t0
+    lane_ids = np.arange(n_lanes)
+    half = 2048 if args.clocks <= 1000 else 256
+    sample = lane_ids if n_lanes <= 2 * half else np.concatenate([lane_ids[:half], lane_ids[-half:]])
+    pat_bits = [unpack(p, n_lanes) for p in patterns]
+    bad = 0
+    for c in range(chains):
+        start = np.zeros(len(sample), np.uint64)
+        got = np.zeros(len(sample), np.uint64)
+        for b in range(bits):
+            start |= pat_bits[(b + c) % bits][sample].astype(np.uint64) << np.uint64(b)
+            got |= unpack(sim.get_wire_lanes(seq.q[c][b])[0], n_lanes)[sample].astype(np.uint64) << np.uint64(b)
+        bad += int((software_lfsr(start, bits, taps, args.clocks) != got).sum())
+    runs = 2 * args.clocks
+    print(json.dumps({"config": "4 (registers)", "workload": f"{chains} LFSR chains x {bits} registers (gsim add_register) + {latches} SR latches, "
+                      f"{args.clocks} clocked steps ({runs} run_sim(10_000) calls), {n_lanes} lanes", "components": seq.n_gates,
+                      "lanes": n_lanes, "run_sim_calls": runs, "applications_total": apps, "seconds_in_run_sim": t_gpu,
+                      "ms_per_run_sim": 1e3 * t_gpu / runs, "component_lane_evals_per_s": seq.n_gates * n_lanes * runs / t_gpu,
+                      "mode": sim.info.last_mode, "lfsr_mismatches": int(bad), "lanes_checked_vs_software_lfsr": int(len(sample))}))
+    assert bad == 0
+
+
 def config5(args):
     import torch
     import torch.distributed as dist
@@ -275,12 +336,13 @@ def main():
     ap.add_argument("--no-oracle", action="store_true")
     ap.add_argument("--hazard", type=int, default=0, help="config 4: latches whose S'/R' can rise together (lanes that oscillate until max_steps)")
     ap.add_argument("--host-loop", action="store_true", help="config 4: B2_OPT_DEVICE_LOOP = 0")
+    ap.add_argument("--registers", action="store_true", help="config 4 built from gsim registers instead of NAND flip-flops")
     ap.add_argument("--no-resident", action="store_true")
     args = ap.parse_args()
     if args.lanes is None:
         args.lanes = {2: 1 << 20, 4: 65536, 5: 1 << 23}[args.config]
 
-    {2: config2, 4: config4, 5: config5}[args.config](args)
+    {2: config2, 4: config4_registers if args.registers else config4, 5: config5}[args.config](args)
 
 
 if __name__ == "__main__":

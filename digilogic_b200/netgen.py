@@ -243,3 +243,73 @@ def sequential(n_latches=4096, n_chains=64, bits=64, n_hazard=0, taps=None) -> S
         latch_q.append((lq, lqn))
     return SequentialNetlist(n_wires=n_w, clk=clk, preset_n=preset_n, clear_n=clear_n, q=q, latch_q=latch_q,
                              hazard_latches=hazard, ops=ops, n_gates=len(ops))
+
+
+@dataclass
+class RegisterLfsrNetlist:
+    """BASELINE config 4 rebuilt with gsim's own sequential component: Fibonacci LFSR chains out of one-bit registers
+    (`add_register`) with a synchronous load path, plus NAND SR latches fed by q / NOT q of the flip-flops."""
+    n_wires: int
+    clk: int
+    enable: int
+    load: int
+    init: list                # per bit position: load value input wire
+    q: list                   # q[chain][bit]
+    latch_q: list
+    ops: list                 # (kind, [inputs], output); kind "reg": inputs = [d, enable, clock]
+    n_gates: int = 0
+
+    def emit(self, builder):
+        first = builder.add_wires(self.n_wires)
+        assert first == 0
+        for kind, ins, out in self.ops:
+            if kind == "reg":
+                builder.add_register(ins[0], out, ins[1], ins[2])
+            elif kind == NOT:
+                builder.add_not_gate(ins[0], out)
+            else:
+                builder.add_gate(kind, ins, out)
+        return builder
+
+
+def sequential_registers(n_latches=4096, n_chains=64, bits=64, taps=None) -> RegisterLfsrNetlist:
+    """Chain c, bit b loads init[(b + c) % bits] while `load` is 1 and shifts otherwise: d = (next AND NOT load) OR
+    (init AND load), q <= d on the rising clock edge while `enable`."""
+    if taps is None:
+        taps = [bits - 1, bits - 2, bits - 4, bits - 5] if bits >= 8 else [bits - 1, bits - 2]
+    n_w = 0
+
+    def wire():
+        nonlocal n_w
+        n_w += 1
+        return n_w - 1
+
+    ops = []
+    clk, enable, load, nload = wire(), wire(), wire(), wire()
+    ops.append((NOT, [load], nload))
+    init = [wire() for _ in range(bits)]
+    q = [[wire() for _ in range(bits)] for _ in range(n_chains)]
+    nq = [[wire() for _ in range(bits)] for _ in range(n_chains)]
+    for c in range(n_chains):
+        fb = q[c][taps[0]]
+        for t in taps[1:]:
+            x = wire()
+            ops.append((XOR, [fb, q[c][t]], x))
+            fb = x
+        for b in range(bits):
+            nxt = fb if b == 0 else q[c][b - 1]
+            a, l, d = wire(), wire(), wire()
+            ops.append((AND, [nxt, nload], a))
+            ops.append((AND, [init[(b + c) % bits], load], l))
+            ops.append((OR, [a, l], d))
+            ops.append(("reg", [d, enable, clk], q[c][b]))
+            ops.append((NOT, [q[c][b]], nq[c][b]))
+    latch_q = []
+    for j in range(n_latches):
+        c, b = j % n_chains, (j // n_chains) % bits
+        lq, lqn = wire(), wire()
+        ops.append((NAND, [q[c][b], lqn], lq))
+        ops.append((NAND, [nq[c][b], lq], lqn))
+        latch_q.append((lq, lqn))
+    return RegisterLfsrNetlist(n_wires=n_w, clk=clk, enable=enable, load=load, init=init, q=q, latch_q=latch_q, ops=ops,
+                               n_gates=len(ops))
