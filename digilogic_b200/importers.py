@@ -7,7 +7,10 @@ and 2 — SURVEY.md §8 row f1.
   positions (crates/digilogic_serde/src/digital.rs:111-215).  Element names:
   crates/digilogic_serde/src/digital/circuitfile.rs:55-79.
 * Yosys JSON: 1-bit `$and/$or/$xor/$not` cells joined by bit ids
-  (crates/digilogic_serde/src/yosys.rs:115-243, schema yosys/netlist.rs:159-196).
+  (crates/digilogic_serde/src/yosys.rs:115-243, schema yosys/netlist.rs:159-196).  Beyond what the reference translates
+  today, the cell types its importer already names but `todo!()`s (yosys.rs:160-211) map onto the engine's wider component
+  set (SURVEY.md §8 row f4): `$xnor`, `$mux`, `$reduce_and/or/xor/xnor/bool`, `$logic_not`, `$tribuf`, `$dff`, `$dffe`;
+  constant bits "0"/"1" become two extra input nets (`const_nets`) the caller drives.
 
 Both produce an `ImportedCircuit`, whose `emit()` issues the same calls the GUI client sends
 (crates/digilogic_netcode/src/client.rs:288-427): one 1-bit net per net, then one gate per
@@ -20,6 +23,7 @@ import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
 
 AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX = range(8)
+BUF, REG = "buf", "reg"   # gates-list kinds beyond the reference's: tri-state buffer [A, EN], register [D, EN, CLK]
 
 # port name -> (dx, dy, is_input), in the reference's port order
 _GATE2 = [("A", 0, 0, True), ("B", 0, 40, True), ("Y", 80, 20, False)]
@@ -29,7 +33,8 @@ DIG_SYMBOLS = {
     "In": (None, [("Y", 0, 0, False)]), "Out": (None, [("A", 0, 0, True)]),
     "Multiplexer": (MUX, [("S", 20, 40, True), ("A", 0, 0, True), ("B", 0, 40, True), ("Y", 40, 20, False)]),
 }
-YOSYS_CELLS = {"$and": AND, "$or": OR, "$xor": XOR, "$not": NOT}
+YOSYS_CELLS = {"$and": AND, "$or": OR, "$xor": XOR, "$not": NOT, "$xnor": XNOR}
+YOSYS_REDUCE = {"$reduce_and": AND, "$reduce_or": OR, "$reduce_bool": OR, "$reduce_xor": XOR, "$reduce_xnor": XNOR, "$logic_not": NOR}
 
 
 @dataclass
@@ -39,6 +44,7 @@ class ImportedCircuit:
     gates: list = field(default_factory=list)      # (kind, [input nets], output net); mux inputs = [S, A, B]
     inputs: dict = field(default_factory=dict)     # label -> [nets] (LSB first)
     outputs: dict = field(default_factory=dict)
+    const_nets: dict = field(default_factory=dict)  # net -> 0 / 1: constants of the source file, to be driven by the caller
 
     def emit(self, builder):
         """Same sequence as the client's build: AddNet{width:1} per net, then the gates."""
@@ -47,6 +53,10 @@ class ImportedCircuit:
         for kind, ins, out in self.gates:
             if kind == MUX:
                 builder.add_multiplexer(ins[1:], ins[0], out)
+            elif kind == BUF:
+                builder.add_buffer(ins[0], ins[1], out)
+            elif kind == REG:
+                builder.add_register(ins[0], out, ins[1], ins[2])
             elif kind == NOT:
                 builder.add_not_gate(ins[0], out)
             else:
@@ -204,14 +214,22 @@ def load_yosys(text: str, module: str | None = None) -> ImportedCircuit:
     mod = mods[module]
     net_of = {}
 
+    circ = ImportedCircuit(module, 0)
+
     def net(bit):
         if not isinstance(bit, int):
-            raise ValueError("constant bits are not supported (the reference importer todo!()s on them)")
+            # "0" / "1": the reference importer todo!()s on constants; here they are shared nets the caller drives
+            if bit not in ("0", "1"):
+                raise ValueError(f"constant bit {bit!r} is not supported")
+            key = ("const", bit)
+            if key not in net_of:
+                net_of[key] = len(net_of)
+                circ.const_nets[net_of[key]] = int(bit)
+            return net_of[key]
         if bit not in net_of:
             net_of[bit] = len(net_of)
         return net_of[bit]
 
-    circ = ImportedCircuit(module, 0)
     for pname, port in mod.get("ports", {}).items():
         nets = [net(b) for b in port["bits"]]
         if port["direction"] == "input":
@@ -222,14 +240,34 @@ def load_yosys(text: str, module: str | None = None) -> ImportedCircuit:
             raise ValueError("inout ports are not supported")
     for cname, cell in mod.get("cells", {}).items():
         ctype = cell["type"]
-        if ctype not in YOSYS_CELLS:
-            raise ValueError(f"unsupported cell type {ctype!r} ({cname})")
-        kind = YOSYS_CELLS[ctype]
         conn = cell["connections"]
-        width = len(conn["Y"])
-        for j in range(width):
-            ins = [net(conn["A"][j])] if kind == NOT else [net(conn["A"][j]), net(conn["B"][j])]
-            circ.gates.append((kind, ins, net(conn["Y"][j])))
+        params = cell.get("parameters", {})
+        if ctype in YOSYS_CELLS:
+            kind = YOSYS_CELLS[ctype]
+            for j in range(len(conn["Y"])):
+                ins = [net(conn["A"][j])] if kind == NOT else [net(conn["A"][j]), net(conn["B"][j])]
+                circ.gates.append((kind, ins, net(conn["Y"][j])))
+        elif ctype in YOSYS_REDUCE:
+            # one output bit from all bits of A (further Y bits, if any, are constant 0 in Yosys and not produced here)
+            kind, a = YOSYS_REDUCE[ctype], [net(b) for b in conn["A"]]
+            if len(a) == 1:
+                a = a * 2          # the builder's gates take two inputs or more; x op x = x for AND/OR, handled for XOR below
+                kind = {XOR: OR, XNOR: NOR}.get(kind, kind)
+            circ.gates.append((kind, a, net(conn["Y"][0])))
+        elif ctype == "$mux":      # Y = S ? B : A
+            for j in range(len(conn["Y"])):
+                circ.gates.append((MUX, [net(conn["S"][0]), net(conn["A"][j]), net(conn["B"][j])], net(conn["Y"][j])))
+        elif ctype == "$tribuf":   # Y = EN ? A : z
+            for j in range(len(conn["Y"])):
+                circ.gates.append((BUF, [net(conn["A"][j]), net(conn["EN"][0])], net(conn["Y"][j])))
+        elif ctype in ("$dff", "$dffe"):
+            if int(str(params.get("CLK_POLARITY", "1")), 2) != 1 or int(str(params.get("EN_POLARITY", "1")), 2) != 1:
+                raise ValueError(f"{ctype} with a negative clock or enable polarity is not supported ({cname})")
+            en = net(conn["EN"][0]) if ctype == "$dffe" else net("1")
+            for j in range(len(conn["Q"])):
+                circ.gates.append((REG, [net(conn["D"][j]), en, net(conn["CLK"][0])], net(conn["Q"][j])))
+        else:
+            raise ValueError(f"unsupported cell type {ctype!r} ({cname})")
     circ.n_nets = len(net_of)
     return circ
 
