@@ -55,4 +55,42 @@ seq = netgen.sequential(n_latches=8, n_chains=2, bits=8, n_hazard=1)
 q = seq.emit(SimulatorBuilder()).build()
 q.set_lanes(200)
 q.run_sim_lanes(30)
+# tri-state buses, registers, wide lists: resident kernel, device-side loop, host loop, dense
+from helpers import bus_enable_drives, random_bus_netlist, random_register_netlist  # noqa: E402
+for resident, frontier, device_loop in ((1, 1, 1), (0, 1, 1), (0, 1, 0), (0, 0, 0)):
+    for kind in ("bus", "reg"):
+        if kind == "bus":
+            nl, first_in, groups = random_bus_netlist(rng, 6, 40, 4)
+        else:
+            nl, first_in = random_register_netlist(rng, 6, 40)
+            groups = []
+        sim = nl.replay(SimulatorBuilder()).build()
+        sim.set_option(sim.OPT_RESIDENT_KERNEL, resident)
+        sim.set_option(sim.OPT_FRONTIER, frontier)
+        sim.set_option(sim.OPT_DEVICE_LOOP, device_loop)
+        n_lanes = 64 * 5 + 3
+        sim.set_lanes(n_lanes)
+        words = (n_lanes + 63) // 64
+        for ms in (0, 2, 40, 1000):
+            for i in range(6):
+                v, m = random_drive(rng, words)
+                sim.set_wire_drive_lanes(first_in + i, v, m)
+            for grp in groups:
+                for e, (v, m) in zip(grp, bus_enable_drives(rng, grp, words)):
+                    sim.set_wire_drive_lanes(e, v, m)
+            sim.run_sim_lanes(ms)
+            sim.gather_wires_host(np.arange(nl.n_wires, dtype=np.uint32))
+# the single-lane server path: queued drives, snapshot reads, slices / merges / adders / reductions
+b = SimulatorBuilder()
+x, y, ssum, lo, red = b.add_wire(12), b.add_wire(12), b.add_wire(12), b.add_wire(4), b.add_wire(1)
+b.add_add(x, y, ssum)
+b.add_slice(ssum, 8, lo)
+b.add_horizontal_gate(2, lo, red)
+s = b.build()
+for k in range(20):
+    s.set_wire_drive(x, LogicState(k * 37, 0xFFF))
+    s.set_wire_drive(y, LogicState(k * 91, 0xFFF))
+    s.run_sim(100)
+    assert s.get_wire_state(ssum) == LogicState((k * 37 + k * 91) & 0xFFF, 0xFFF)
+    s.get_wire_state(red)
 print("sanitizer probe done")
