@@ -160,3 +160,99 @@ def test_config5_netlist_sampled_against_oracle():
     ref_v = np.stack([bs.get(int(w))[0] for w in some])
     ref_m = np.stack([bs.get(int(w))[1] for w in some])
     assert (gv[:, sample] == ref_v).all() and (gm[:, sample] == ref_m).all()
+
+
+def test_config4_full_netlist_lfsr_property():
+    """BASELINE config 4 at its full netlist size (64 chains x 64 NAND flip-flops + 4096 latches) and lane count: after a
+    few clocked steps every sampled lane's LFSR state equals a software LFSR of its start pattern (size-independent
+    property; the wire-by-wire oracle comparison runs at reduced size above)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks"))
+    import configs
+    bits = chains = 64
+    n_lanes, clocks = 65536, 12
+    seq = netgen.sequential(n_latches=4096, n_chains=chains, bits=bits)
+    taps = [bits - 1, bits - 2, bits - 4, bits - 5]
+    sim = seq.emit(SimulatorBuilder()).build()
+    sim.set_lanes(n_lanes)
+    words = n_lanes // 64
+    ones, zeros = np.full(words, ALL1, np.uint64), np.zeros(words, np.uint64)
+    rng = np.random.default_rng(4)
+    patterns = [rng.integers(0, 1 << 64, words, dtype=np.uint64) for _ in range(bits)]
+
+    def run():
+        res, _, _ = sim.run_sim_lanes(10_000, masks=False)
+        assert res == SimulationRunResult.Ok
+
+    sim.set_wire_drive_lanes(seq.clk, zeros, ones)
+    for b in range(bits):
+        sim.set_wire_drive_lanes(seq.preset_n[b], ~patterns[b], ones)
+        sim.set_wire_drive_lanes(seq.clear_n[b], patterns[b], ones)
+    run()
+    for b in range(bits):
+        sim.set_wire_drive_lanes(seq.preset_n[b], ones, ones)
+        sim.set_wire_drive_lanes(seq.clear_n[b], ones, ones)
+    run()
+    for _ in range(clocks):
+        sim.set_wire_drive_lanes(seq.clk, ones, ones); run()
+        sim.set_wire_drive_lanes(seq.clk, zeros, ones); run()
+    assert sim.info.last_mode == 2
+    sample = np.concatenate([np.arange(128), np.arange(n_lanes - 128, n_lanes)])
+    pat_bits = [configs.unpack(p, n_lanes) for p in patterns]
+    for c in range(0, chains, 7):
+        start = np.zeros(len(sample), np.uint64)
+        got = np.zeros(len(sample), np.uint64)
+        for b in range(bits):
+            start |= pat_bits[(b + c) % bits][sample].astype(np.uint64) << np.uint64(b)
+            got |= configs.unpack(sim.get_wire_lanes(seq.q[c][b])[0], n_lanes)[sample].astype(np.uint64) << np.uint64(b)
+        assert (configs.software_lfsr(start, bits, taps, clocks) == got).all(), c
+
+
+@pytest.mark.parametrize("kind", ["gates", "registers", "buses"])
+def test_unit_delay_paths_agree_at_scale(kind):
+    """The three HBM unit-delay paths (device-side loop, host loop with work lists, dense) on one netlist of a few
+    thousand components and 19 200 lanes — beyond what the CPU models check quickly — must leave every wire of every lane
+    and both status masks identical, run after run."""
+    from helpers import bus_enable_drives, random_bus_netlist, random_drive, random_netlist, random_register_netlist
+    rng = np.random.default_rng({"gates": 1, "registers": 2, "buses": 3}[kind])
+    n_in, n_gates, n_lanes = 16, 3000, 64 * 300
+    groups = []
+    if kind == "gates":
+        nl, first_in = random_netlist(rng, n_in, n_gates, cyclic=True, wide=True, mux=True)
+    elif kind == "registers":
+        nl, first_in = random_register_netlist(rng, n_in, n_gates)
+    else:
+        nl, first_in, groups = random_bus_netlist(rng, n_in, n_gates, 40)
+    sims = []
+    for frontier, device_loop in ((1, 1), (1, 0), (0, 0)):
+        s = nl.replay(SimulatorBuilder()).build()
+        s.set_option(s.OPT_RESIDENT_KERNEL, 0)
+        s.set_option(s.OPT_FRONTIER, frontier)
+        s.set_option(s.OPT_DEVICE_LOOP, device_loop)
+        s.set_lanes(n_lanes)
+        sims.append(s)
+    words = n_lanes // 64
+    wires = np.arange(nl.n_wires, dtype=np.uint32)
+    dirty = np.zeros(words, np.uint64)
+    for rnd, max_steps in enumerate([0, 3, 40, 7, 1, 500, 12]):
+        for i in range(n_in):
+            if rng.random() < 0.6:
+                v, m = random_drive(rng, words, four_state=rnd % 3 == 0)
+                for s in sims:
+                    s.set_wire_drive_lanes(first_in + i, v, m)
+        for grp in groups:
+            for e, (v, m) in zip(grp, bus_enable_drives(rng, grp, words, p_bad=0.002)):
+                for s in sims:
+                    s.set_wire_drive_lanes(e, v, m)
+        outs = []
+        for s in sims:
+            res, conflict, unsettled = s.run_sim_lanes(max_steps)
+            gv, gm = s.gather_wires_host(wires)
+            outs.append((int(res), conflict, unsettled, gv, gm))
+        keep = ~(dirty | outs[0][1])        # lanes that conflicted are outside the contract from then on
+        for o in outs[1:]:
+            assert ((o[1] ^ outs[0][1]) & ~dirty).max() == 0 and ((o[2] ^ outs[0][2]) & keep).max() == 0, (rnd, max_steps)
+            assert ((o[3] ^ outs[0][3]) & keep).max() == 0 and ((o[4] ^ outs[0][4]) & keep).max() == 0, (rnd, max_steps)
+        dirty |= outs[0][1]
+    assert (~dirty).any()
