@@ -142,6 +142,14 @@ __device__ __forceinline__ void reg_word(u64 dv, u64 dm, u64 ev, u64 em, u64 cv,
     rv = (take & (dv | ~dm)) | (keep & (ov | ~om)) | undef;
 }
 
+// Driver conflict between two operands of a wire: both not High-Z; with `lenient` (the A.6-2
+// alternative) two valid operands that agree do not conflict.
+__device__ __forceinline__ u64 conflict_of(u64 av, u64 am, u64 bv, u64 bm, int lenient) {
+    u64 c = (av | am) & (bv | bm);
+    if (lenient) c &= ~(am & bm & ~(av ^ bv));
+    return c;
+}
+
 __device__ __forceinline__ uint64_t lane_mask_of(uint32_t w, uint64_t n_lanes) {
     const uint64_t lo = (uint64_t)w * 64;
     if (lo + 64 <= n_lanes) return ~0ull;
@@ -725,7 +733,7 @@ __global__ void __launch_bounds__(256) k_materialise_valid(uint64_t *vld, uint8_
 // component outputs still High-Z): the row simply takes the drive.
 __global__ void __launch_bounds__(256) k_extra_drive(const uint32_t *rows, uint32_t n, const uint64_t *xval,
                                                      const uint64_t *xvld, uint64_t *val, uint64_t *vld, uint64_t *conf,
-                                                     uint32_t stride, int mode) {
+                                                     uint32_t stride, int mode, int lenient = 0) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= stride) return;
     uint64_t c = 0;
@@ -738,7 +746,7 @@ __global__ void __launch_bounds__(256) k_extra_drive(const uint32_t *rows, uint3
             vld[o] = dm;
         } else {
             const uint64_t gv = val[o], gm = vld[o];
-            c |= (dv | dm) & (gv | gm);
+            c |= conflict_of(dv, dm, gv, gm, lenient);
             val[o] = gv | dv;
             vld[o] = gm | dm;
         }
@@ -763,6 +771,7 @@ struct ResolveArgs {
     uint8_t *chg_cur;
     uint32_t n_res, row_base, stride, pairs, pair_blocks;
     int cold;
+    int lenient;  // A.6-2 alternative: agreeing valid drivers do not conflict
 };
 
 __device__ __forceinline__ void resolve_body(const ResolveArgs &a, uint32_t pb, uint32_t rb) {
@@ -782,8 +791,8 @@ __device__ __forceinline__ void resolve_body(const ResolveArgs &a, uint32_t pb, 
         for (uint32_t i = a.off[r]; i < a.off[r + 1]; i++) {
             const size_t o = (size_t)a.in[i] * a.stride + col;
             const ulonglong2 ov = *(const ulonglong2 *)(a.b_val + o), om = *(const ulonglong2 *)(a.b_vld + o);
-            cx |= (v.x | m.x) & (ov.x | om.x);
-            cy |= (v.y | m.y) & (ov.y | om.y);
+            cx |= conflict_of(v.x, m.x, ov.x, om.x, a.lenient);
+            cy |= conflict_of(v.y, m.y, ov.y, om.y, a.lenient);
             v.x |= ov.x; v.y |= ov.y;
             m.x |= om.x; m.y |= om.y;
         }
@@ -1137,6 +1146,7 @@ struct ResidentArgs {
     const Level *levels;
     uint32_t n_levels;
     int levelised;
+    int lenient;  // A.6-2 alternative: agreeing valid drivers do not conflict
 };
 
 __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g, const uint64_t *av, const uint64_t *am, uint32_t wpc,
@@ -1261,7 +1271,7 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
             if (w < a.stride && a.xrows[x] != 0xFFFFFFFFu) {
                 const size_t r = (size_t)a.xrows[x] * wpc + j;
                 const u64 dv = a.xval[(size_t)x * a.stride + w], dm = a.xvld[(size_t)x * a.stride + w];
-                const u64 c = (dv | dm) & (AV[r] | AM[r]);
+                const u64 c = conflict_of(dv, dm, AV[r], AM[r], a.lenient);
                 AV[r] |= dv;
                 AM[r] |= dm;
                 if (c) atomicOr((unsigned long long *)&s_conflict[j], c);
@@ -1342,7 +1352,7 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
                     }
                     for (uint32_t q = a.res_off[r]; q < a.res_off[r + 1]; q++) {
                         const size_t o = (size_t)a.res_in[q] * wpc + j;
-                        c |= (v | m) & (BV[o] | BM[o]);
+                        c |= conflict_of(v, m, BV[o], BM[o], a.lenient);
                         v |= BV[o];
                         m |= BM[o];
                     }
@@ -1362,7 +1372,7 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
                     if (w < a.stride && a.xrows[x] != 0xFFFFFFFFu) {
                         const size_t r = (size_t)a.xrows[x] * wpc + j;
                         const u64 dv = a.xval[(size_t)x * a.stride + w], dm = a.xvld[(size_t)x * a.stride + w];
-                        const u64 c = (dv | dm) & (BV[r] | BM[r]);
+                        const u64 c = conflict_of(dv, dm, BV[r], BM[r], a.lenient);
                         BV[r] |= dv;
                         BM[r] |= dm;
                         if (c) atomicOr((unsigned long long *)&s_conf[j], c);
@@ -2192,7 +2202,7 @@ int Engine::run_levelised(bool async) {
     k_clear_flags<<<1, 1, 0, ST>>>(d_flags_);
     LAUNCHED();
     k_extra_drive<<<(stride_ + 255) / 256, 256, 0, ST>>>(d_extra_rows_, (uint32_t)extra_rows_.size(), xdrv_val_, xdrv_vld_, V, M,
-                                                         d_conflict_, stride_, 0);
+                                                         d_conflict_, stride_, 0, opt_lenient_ ? 1 : 0);
     LAUNCHED();
     k_levelised_status<<<(stride_ + 255) / 256, 256, 0, ST>>>(d_conflict_, d_unsettled_, d_flags_, stride_, n_lanes_);
     LAUNCHED();
@@ -2215,7 +2225,7 @@ int Engine::run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &res
     la.wide = WideArgs{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, nullptr, nullptr, nullptr, nullptr, d_changed_, 0,
                        net_.n_wide(), net_.n_src + net_.n_fast(), stride_, pairs, sh.pair_blocks, nullptr, nullptr, nullptr, nullptr};
     la.res = ResolveArgs{d_res_off_, d_res_in_, d_res_xslot_, xdrv_val_, xdrv_vld_, nullptr, nullptr, nullptr, nullptr, d_changed_,
-                         d_conf_step_, nullptr, n_res, res_base, stride_, pairs, sh.pair_blocks, 0};
+                         d_conf_step_, nullptr, n_res, res_base, stride_, pairs, sh.pair_blocks, 0, opt_lenient_ ? 1 : 0};
     for (int i = 0; i < 2; i++) {
         la.val[i] = val_[i];
         la.vld[i] = vld_[i];
@@ -2296,7 +2306,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
         }
         if (n_res) {
             ResolveArgs ra{d_res_off_, d_res_in_, d_res_xslot_, xdrv_val_, xdrv_vld_, V, M, V, M, nullptr, d_conf_step_, nullptr,
-                           n_res, res_base, stride_, pairs, sh.pair_blocks, 1};
+                           n_res, res_base, stride_, pairs, sh.pair_blocks, 1, opt_lenient_ ? 1 : 0};
             k_resolve<<<sh.pair_blocks * res_gb, sh.block, 0, ST>>>(ra);
             LAUNCHED();
         }
@@ -2436,12 +2446,13 @@ int Engine::run_jacobi(uint64_t max_steps) {
         }
         if (n_res) {
             ResolveArgs ra{d_res_off_, d_res_in_, d_res_xslot_, xdrv_val_, xdrv_vld_, AV, AM, BV, BM, d_changed_, d_conf_step_, chg_cur,
-                           n_res, res_base, stride_, pairs, sh.pair_blocks, 0};
+                           n_res, res_base, stride_, pairs, sh.pair_blocks, 0, opt_lenient_ ? 1 : 0};
             k_resolve<<<sh.pair_blocks * res_gb, sh.block, 0, ST>>>(ra);
             LAUNCHED();
         }
         if (n_extra) {
-            k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_slots, xdrv_val_, xdrv_vld_, BV, BM, d_conf_step_, stride_, 0);
+            k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_slots, xdrv_val_, xdrv_vld_, BV, BM, d_conf_step_, stride_, 0,
+                                                 opt_lenient_ ? 1 : 0);
             LAUNCHED();
         }
         // The lane bookkeeping of application k goes to flag slot k % kFlagSlots; the host reads it
@@ -2527,6 +2538,7 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
     a.levels = d_levels_;
     a.n_levels = (uint32_t)net_.levels.size();
     a.levelised = levelised ? 1 : 0;
+    a.lenient = opt_lenient_ ? 1 : 0;
     const size_t smem = ((size_t)net_.n_rows * wpc * 4 + (size_t)wpc * 5) * 8;
     if (!resident_attr_set_) {
         CU_TRY(cudaFuncSetAttribute(k_resident_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kResidentSmem + 4096)));

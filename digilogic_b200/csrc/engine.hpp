@@ -65,6 +65,12 @@ class Engine {
     void set_budget_inclusive(bool on) { opt_budget_inclusive_ = on; }
     void set_use_frontier(bool on) { opt_frontier_ = on; frontier_valid_ = false; }
     void set_device_loop(bool on) { opt_device_loop_ = on; }
+    // SURVEY.md A.6-2 alternative (agreeing valid drivers do not conflict); refused for netlists with two firm drivers on a net
+    bool set_lenient_conflicts(bool on) {
+        if (on && net_.multi_driver) return false;
+        opt_lenient_ = on;
+        return true;
+    }
     void set_eval_unroll(uint32_t u) { opt_u_ = (u == 2 || u == 4) ? u : 0; level_graph_key_ = 0; }
 
    private:
@@ -173,6 +179,7 @@ class Engine {
     int occ_list_[4] = {3, 2, 4, 4};  // resident CTAs per SM of k_eval_list<2>, k_eval_list<3>, k_copy_list, k_eval_wide_list
     int chg_w_ = 0;
     bool frontier_valid_ = false, opt_frontier_ = true;
+    bool opt_lenient_ = false;
     bool opt_budget_inclusive_ = false;  // SURVEY.md A.6-1 switch: `steps >= max_steps` instead of `>`
     uint32_t opt_u_ = 0;  // 0 = automatic gates-per-thread choice in k_eval2
     bool use_resident_ = true, resident_attr_set_ = false;

@@ -186,6 +186,10 @@ enum b2_option {
                                   run against the real crate (oracle/gsim_diff) say so — SURVEY.md A.6-1. */
     B2_OPT_FRONTIER = 5,       /* default 1.  Unit-delay runs in HBM re-evaluate a gate only if one of its fan-in rows or
                                   its own output row changed (on any lane) in the previous application. */
+    B2_OPT_CONFLICT_NEEDS_DISAGREE = 8, /* default 0.  gsim's driver conflict is restated as "two operands of a wire are not
+                                  High-Z" (SURVEY.md A.6-2); 1 selects the alternative reading in which two valid operands that
+                                  agree do not conflict — the oracle's `conflict_needs_disagree` switch, for the day a run of real
+                                  gsim decides.  Refused (InvalidArgument) for a netlist with two plain gates on one net. */
     B2_OPT_DEVICE_LOOP = 7     /* default 1.  Unit-delay runs in HBM execute the whole run_sim loop in one cooperative launch
                                   (grid barriers between the phases of an application, stop decision on the device);
                                   0: one set of launches per application, stop decision on the host. */

@@ -187,3 +187,46 @@ def test_random_bus_netlists_vs_bitsliced(seed, cyclic, n_lanes, path, resident,
         seen.add("u" if (u & m).any() else "-")
     assert modes == ({3} if resident else {2}), modes
     assert (m & ~dirty).any(), "every lane conflicted: the comparison is vacuous"
+
+
+@pytest.mark.parametrize("path,resident,frontier,device_loop", PATHS)
+def test_conflict_predicate_switch_follows_the_oracle(path, resident, frontier, device_loop):
+    """SURVEY.md A.6-2 is one switch in the oracle (`conflict_needs_disagree`) and one option in the engine
+    (B2_OPT_CONFLICT_NEEDS_DISAGREE): under the alternative reading two valid drivers that agree do not conflict."""
+    nl = Netlist()
+    d0, d1, e0, e1, bus, a, c, o = (nl.add_wire() for _ in range(8))
+    nl.add_buffer(d0, e0, bus)
+    nl.add_buffer(d1, e1, bus)
+    nl.add_gate(0, [a, c], o)                      # AND whose output also gets an external drive
+    n_lanes = 256
+    words = n_lanes // 64
+    rng = np.random.default_rng(17)
+    ones = np.full(words, (1 << 64) - 1, np.uint64)
+    try:
+        for lenient in (1, 0):
+            oracle.lib().go_set_config(0, lenient, 0, 0)
+            sim = engine(nl, n_lanes, resident, frontier, device_loop)
+            sim.set_option(sim.OPT_CONFLICT_NEEDS_DISAGREE, lenient)
+            lanes = oracle.Lanes(nl.replay(oracle.Builder()), n_lanes)
+            for rnd in range(4):
+                for w in (d0, d1, e0, e1, a, c, o):
+                    v = rng.integers(0, 1 << 64, words, dtype=np.uint64)
+                    m = ones if w != o else rng.integers(0, 1 << 64, words, dtype=np.uint64)   # o: High-Z on about half the lanes
+                    sim.set_wire_drive_lanes(w, v & m, m)
+                    lanes.set_drive(w, v & m, m)
+                status, _, _ = lanes.run(100)
+                res, conflict, unsettled = sim.run_sim_lanes(100)
+                got = oracle.status_from_masks(conflict, unsettled, n_lanes)
+                assert (got == status).all(), (lenient, rnd)
+                assert (status == oracle.RUN_CONFLICT).any() and (status == oracle.RUN_OK).any()
+                break  # one run per simulator: lanes that conflicted are out of contract afterwards
+    finally:
+        oracle.lib().go_set_config(0, 0, 0, 0)
+    # a netlist with two plain gates on one net keeps the strict reading
+    b = SimulatorBuilder()
+    x, y, z = b.add_wire(), b.add_wire(), b.add_wire()
+    b.add_and_gate([x, y], z)
+    b.add_or_gate([x, y], z)
+    s = b.build()
+    with pytest.raises(Exception):
+        s.set_option(s.OPT_CONFLICT_NEEDS_DISAGREE, 1)
