@@ -1030,7 +1030,6 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
         const uint64_t *AV = a.val[cur], *AM = a.vld[cur];
         uint64_t *BV = a.val[cur ^ 1], *BM = a.vld[cur ^ 1];
         uint8_t *chg_cur = a.chg[cw];
-        const uint8_t *chg_prev = (k > first_k || a.frontier_valid) ? a.chg[cw ^ 1] : nullptr;
         const uint32_t *counts = a.cnt + 4 * (k & 1);
         RunFlags *flags = a.flags + (k % 8);
         if (k > first_k) {  // a long work list is better served by the separate, fully occupied kernels
