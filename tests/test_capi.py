@@ -107,6 +107,33 @@ def test_compile_info_levels():
     assert i.n_sources == 10 and i.n_rows == 10 + 11 and i.n_gates2 == 2 + 8 and i.n_gates3 == 1 and i.n_gates_wide == 0
 
 
+def test_compile_info_of_the_wider_component_set():
+    """Row layout of tri-state nets, registers, slices, adders (host-only: b2_build needs no device)."""
+    b = d.SimulatorBuilder()
+    d0, d1, e0, e1, bus, nb = (b.add_wire() for _ in range(6))
+    b.add_buffer(d0, e0, bus)
+    b.add_buffer(d1, e1, bus)
+    b.add_not_gate(bus, nb)
+    i = b.build().info
+    # 4 sources, 3 gate rows (each buffer keeps its own row) + 1 resolved row for the bus; unit-delay path only
+    assert (i.n_sources, i.n_gates2, i.n_rows, i.cyclic, i.multi_driver) == (4, 3, 4 + 3 + 1, 1, 0)
+    b = d.SimulatorBuilder()
+    din, q, en, ck = b.add_wire(4), b.add_wire(4), b.add_wire(), b.add_wire()
+    b.add_register(din, q, en, ck)
+    i = b.build().info
+    # 6 source bits; one hidden previous-clock gate (fast class) + 4 register bits (CSR class)
+    assert (i.n_sources, i.n_gates2, i.n_gates_wide, i.n_rows, i.cyclic) == (6, 1, 4, 6 + 5, 1)
+    b = d.SimulatorBuilder()
+    x, y, sm, hi, par = b.add_wire(8), b.add_wire(8), b.add_wire(8), b.add_wire(4), b.add_wire(1)
+    b.add_add(x, y, sm)
+    b.add_slice(sm, 4, hi)
+    b.add_horizontal_gate(d.gsim.XOR, hi, par)
+    i = b.build().info
+    # adder bits on the CSR class (8), slice bits are one-input fast gates (4), the 4-input reduction is a CSR gate;
+    # acyclic: adder (1) -> slice (2) -> reduction (3)
+    assert (i.n_sources, i.n_gates2, i.n_gates_wide, i.cyclic, i.depth) == (16, 4, 8 + 1, 0, 3)
+
+
 def test_build_takes_the_builder():
     b = d.SimulatorBuilder()
     a = b.add_wire()
