@@ -60,6 +60,21 @@ def config2(args):
         pv, pm = sim.gather_wires_host(outs)
     dt = (time.perf_counter() - t0) / reps
     assert res == SimulationRunResult.Ok and (pm == ALL1).all()
+    # the same with page-locked host planes (what a caller that cares about throughput hands in)
+    words = n_lanes // 64
+    pin = [torch.empty((len(wires), words), dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    pout = [torch.empty((len(outs), words), dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    pin_v, pin_m = (t.numpy().view(np.uint64) for t in pin)
+    out_v, out_m = (t.numpy().view(np.uint64) for t in pout)
+    pin_v[:] = value
+    pin_m[:] = valid
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sim.set_drives_lanes(wires, pin_v, pin_m)
+        res, conflict, unsettled = sim.run_sim_lanes(10_000, masks=False)
+        sim.gather_wires_host(outs, out_v, out_m)
+    dt_pinned = (time.perf_counter() - t0) / reps
+    assert res == SimulationRunResult.Ok and (out_v == pv).all() and (out_m == ALL1).all()
     # the settle alone (drives already in HBM), CUDA events on the simulator's stream
     st = torch.cuda.Stream()
     sim.set_stream(st.cuda_stream)
@@ -82,7 +97,8 @@ def config2(args):
     info = sim.info
     print(json.dumps({"config": 2, "workload": "32x32 array multiplier via Yosys JSON, 2^20 random vectors, host planes in and out",
                       "gates": len(circ.gates), "depth": info.depth, "lanes": n_lanes, "seconds_e2e": dt,
-                      "gate_lane_evals_per_s": len(circ.gates) * n_lanes / dt, "settle_ms_device": settle_ms,
+                      "gate_lane_evals_per_s": len(circ.gates) * n_lanes / dt, "seconds_e2e_pinned_host_planes": dt_pinned,
+                      "gate_lane_evals_per_s_pinned": len(circ.gates) * n_lanes / dt_pinned, "settle_ms_device": settle_ms,
                       "gate_lane_evals_per_s_device": len(circ.gates) * n_lanes / (settle_ms * 1e-3), "product_exact_on_every_lane": ok,
                       "mode": info.last_mode}))
     assert ok
