@@ -165,6 +165,44 @@ def random_register_netlist(rng, n_in, n_gates, p_reg=0.25):
     return nl, first_in
 
 
+def random_mixed_netlist(rng, n_in, n_gates, n_bus):
+    """Everything at once: plain gates, muxes, registers, single buffers, and `n_bus` multi-driver buses with
+    dedicated enable inputs (see bus_enable_drives); cyclic.  Returns (netlist, first_in, enable_groups)."""
+    nl = Netlist()
+    first_in = nl.add_wires(n_in)
+    first_g = nl.add_wires(n_gates)
+    first_bus = nl.add_wires(n_bus)
+    n_w = n_in + n_gates + n_bus
+
+    def pick():
+        return int(rng.integers(0, n_w))
+
+    for g in range(n_gates):
+        r = rng.random()
+        out = first_g + g
+        if r < 0.15:
+            ck = int(rng.integers(0, n_in)) if rng.random() < 0.5 else pick()
+            nl.add_register(pick(), out, pick(), ck)
+        elif r < 0.25:
+            nl.add_buffer(pick(), pick(), out)
+        elif r < 0.35:
+            nl.add_multiplexer([pick(), pick()], pick(), out)
+        else:
+            kind = int(rng.integers(0, 7))
+            if kind == NOT:
+                nl.add_not_gate(pick(), out)
+            else:
+                n = int(rng.integers(3, 6)) if rng.random() < 0.2 else 2
+                nl.add_gate(kind, [pick() for _ in range(n)], out)
+    groups = []
+    for b in range(n_bus):
+        en = [nl.add_wire() for _ in range(int(rng.integers(2, 4)))]
+        for e in en:
+            nl.add_buffer(pick(), e, first_bus + b)
+        groups.append(en)
+    return nl, first_in, groups
+
+
 def random_drive(rng, words, four_state=True):
     value = rng.integers(0, 1 << 64, words, dtype=np.uint64)
     if four_state:

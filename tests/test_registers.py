@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import Netlist, lane_mask, random_drive, random_register_netlist
+from helpers import Netlist, bus_enable_drives, lane_mask, random_drive, random_mixed_netlist, random_register_netlist
 
 Z, X, L0, L1 = (0, 0), (1, 0), (0, 1), (1, 1)
 ALL = (1 << 64) - 1
@@ -145,6 +145,55 @@ def test_scalar_vs_bitsliced_random_register_netlists(seed):
         assert (sv == dv).all() and (sm == dm).all(), (rnd, max_steps)
 
 
+def _mixed_rounds(rng, nl, first_in, groups, n_in, words, set_all, run_all):
+    """Drives and runs shared by the CPU and GPU mixed tests; yields after every run."""
+    for rnd, max_steps in enumerate([0, 1, 2, 3, 5, 8, 50, 7, 0, 2, 1000, 4]):
+        for i in range(n_in):
+            if rng.random() < 0.7:
+                v, m = random_drive(rng, words, four_state=rnd % 4 == 0)
+                set_all(first_in + i, v, m)
+        for grp in groups:
+            if rnd == 0 or rng.random() < 0.5:
+                for e, (v, m) in zip(grp, bus_enable_drives(rng, grp, words)):
+                    set_all(e, v, m)
+        yield rnd, max_steps, run_all(max_steps)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_scalar_vs_bitsliced_mixed_netlists(seed):
+    """Gates, muxes, registers, buffers and multi-driver buses in one cyclic netlist: event-driven restatement against
+    the dense model; lanes that have conflicted are out of contract from then on."""
+    rng = np.random.default_rng(6100 + seed)
+    n_in, n_gates, n_bus, n_lanes = 6, 40, 3, 128
+    nl, first_in, groups = random_mixed_netlist(rng, n_in, n_gates, n_bus)
+    b = nl.replay(oracle.Builder())
+    lanes = oracle.Lanes(b, n_lanes)
+    bs = oracle.BitSliced(b, n_lanes, nl.n_wires)
+    clean = np.ones(n_lanes, bool)
+
+    def set_all(w, v, m):
+        lanes.set_drive(w, v, m)
+        bs.set_drive(w, v, m)
+
+    def run_all(ms):
+        st, _, _ = lanes.run(ms)
+        c, u = bs.run(ms)
+        return st, oracle.status_from_masks(c, u, n_lanes)
+
+    compared = 0
+    for rnd, ms, (st, st2) in _mixed_rounds(rng, nl, first_in, groups, n_in, lanes.words, set_all, run_all):
+        assert (st2[clean] == st[clean]).all(), (rnd, ms)
+        clean &= st != oracle.RUN_CONFLICT
+        keep = np.zeros(lanes.words, np.uint64)
+        for l in np.nonzero(clean)[0]:
+            keep[l // 64] |= np.uint64(1 << (l % 64))
+        sv, sm = lanes.get_all(nl.n_wires)
+        dv, dm = bs.get_all()
+        assert (((sv ^ dv) | (sm ^ dm)) & keep[None, :] == 0).all(), (rnd, ms)
+        compared += int(clean.sum())
+    assert compared > 2 * n_lanes
+
+
 # ---------------------------------------------------------------------------------------------- GPU
 PATHS = [("resident", 1, 1, 1), ("hbm-device-loop", 0, 1, 1), ("hbm-host-loop", 0, 1, 0), ("hbm-dense", 0, 0, 0)]
 
@@ -250,3 +299,36 @@ def test_random_register_netlists_on_gpu(seed, n_lanes, path, resident, frontier
         rv, rm = bs.get_all()
         gv, gm = sim.gather_wires_host(np.arange(nl.n_wires, dtype=np.uint32))
         assert ((gv ^ rv) & m).max() == 0 and ((gm ^ rm) & m).max() == 0, (rnd, max_steps)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("path,resident,frontier,device_loop", PATHS)
+def test_mixed_netlists_on_gpu(seed, path, resident, frontier, device_loop):
+    """The same mix on the engine against the dense CPU model."""
+    rng = np.random.default_rng(6300 + seed)
+    n_in, n_gates, n_bus, n_lanes = 6, 48, 3, 64 * 7 + 5
+    nl, first_in, groups = random_mixed_netlist(rng, n_in, n_gates, n_bus)
+    sim = _engine(nl, n_lanes, resident, frontier, device_loop)
+    bs = oracle.BitSliced(nl.replay(oracle.Builder()), n_lanes, nl.n_wires)
+    m = lane_mask(n_lanes)
+    dirty = np.zeros(bs.words, np.uint64)
+
+    def set_all(w, v, vm):
+        sim.set_wire_drive_lanes(w, v, vm)
+        bs.set_drive(w, v, vm)
+
+    def run_all(ms):
+        res, conflict, unsettled = sim.run_sim_lanes(ms)
+        c, u = bs.run(ms)
+        return conflict, unsettled, c, u
+
+    for rnd, ms, (conflict, unsettled, c, u) in _mixed_rounds(rng, nl, first_in, groups, n_in, bs.words, set_all, run_all):
+        keep = m & ~dirty
+        assert ((conflict ^ c) & keep).max() == 0 and ((unsettled ^ u) & keep).max() == 0, (rnd, ms)
+        dirty |= c
+        keep = m & ~dirty
+        rv, rm = bs.get_all()
+        gv, gm = sim.gather_wires_host(np.arange(nl.n_wires, dtype=np.uint32))
+        assert ((gv ^ rv) & keep).max() == 0 and ((gm ^ rm) & keep).max() == 0, (rnd, ms)
+    assert (m & ~dirty).any()
