@@ -1146,6 +1146,9 @@ struct ResidentArgs {
     uint32_t n_levels;
     int levelised;
     int lenient;  // A.6-2 alternative: agreeing valid drivers do not conflict
+    // small runs (the one-lane server path) also leave the bit-packed lane-0 snapshot get_wire_state reads (CTA 0 packs it)
+    uint8_t *snap0, *snap1;
+    uint32_t snap_bytes;
 };
 
 __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g, const uint64_t *av, const uint64_t *am, uint32_t wpc,
@@ -1409,6 +1412,20 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
             a.vld[(size_t)row * a.stride + w] = AM[i];
         }
     }
+    if (a.snap0 && blockIdx.x == 0) {  // lane 0 = bit 0 of the first lane-word, which CTA 0 holds
+        for (uint32_t byte = tid; byte < a.snap_bytes; byte += nt) {
+            uint32_t b0 = 0, b1 = 0;
+            for (uint32_t j = 0; j < 8; j++) {
+                const uint32_t row = byte * 8 + j;
+                if (row < a.n_rows) {
+                    b0 |= (uint32_t)(AV[(size_t)row * wpc] & 1) << j;
+                    b1 |= (uint32_t)(AM[(size_t)row * wpc] & 1) << j;
+                }
+            }
+            a.snap0[byte] = (uint8_t)b0;
+            a.snap1[byte] = (uint8_t)b1;
+        }
+    }
     if (tid < wpc && w0 + tid < a.stride) {
         a.conflict[w0 + tid] = s_conflict[tid];
         a.unsettled[w0 + tid] = s_unsettled[tid];
@@ -1445,7 +1462,6 @@ Engine::~Engine() {
         cudaFree(d_pend_);
         cudaFree(d_loop_result_);
         if (h_loop_result_) cudaFreeHost(h_loop_result_);
-        cudaFree(d_max_apps_);
         if (h_flags_) cudaFreeHost(h_flags_);
         if (own_stream_ && stream_) cudaStreamDestroy(ST);
         if (cin_stream_) cudaStreamDestroy(CIN);
@@ -1850,8 +1866,10 @@ int Engine::sync_extra_tables() {
 int Engine::set_wire_drive(uint32_t wire, const uint32_t *p0, const uint32_t *p1, size_t words) {
     if (wire >= net_.n_wires()) return B2_ERR_INVALID_WIRE_ID;
     if (words && (!p0 || !p1)) return B2_ERR_NULL;
-    int rc = ensure_lanes();
-    if (rc) return rc;
+    if (!device_ready_ || n_lanes_ == 0) {  // first use: device and store; afterwards the call is pure host work
+        int rc = ensure_lanes();
+        if (rc) return rc;
+    }
     PendingDrive d;
     d.wire = wire;
     for (uint32_t i = 0; i < 8; i++) {
@@ -2500,6 +2518,7 @@ uint32_t Engine::resident_wpc() const {
     if (per_word > kResidentSmem) return 0;
     size_t wpc = kResidentSmem / per_word;
     const size_t spread = ((size_t)stride_ + 147) / 148;  // enough CTAs to cover the SMs first
+    if (stride_ <= 2 && wpc >= stride_) return stride_;   // one lane-word (+ its padding word): one CTA, which also packs the snapshot
     if (wpc > spread) wpc = spread;
     if (wpc > 64) wpc = 64;
     return (uint32_t)(wpc ? wpc : 1);
@@ -2515,10 +2534,8 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
     if ((rc = materialise_valid())) return rc;
     if ((rc = drives_begin())) return rc;
     if ((rc = sync_extra_tables())) return rc;
-    if (!d_max_apps_) CU_TRY(cudaMalloc((void **)&d_max_apps_, 8));
-    CU_TRY(cudaMemsetAsync(d_max_apps_, 0, 8, ST));
-    k_clear_flags<<<1, 1, 0, ST>>>(d_flags_);
-    LAUNCHED();
+    // flag slot 0 takes the run's flags, slot 1 the application count: one clear before, one copy after the kernel
+    CU_TRY(cudaMemsetAsync(d_flags_, 0, 2 * sizeof(RunFlags), ST));
     ResidentArgs a;
     a.fan0 = d_fan0_; a.fan1 = d_fan1_; a.fan2 = d_fan2_; a.kind2 = d_kind2_;
     a.woff = d_wide_off_; a.win = d_wide_in_; a.wkind = d_wide_kind_; a.wnsel = d_wide_nsel_;
@@ -2528,7 +2545,7 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
     a.val = val_[cur_]; a.vld = vld_[cur_];
     a.conflict = d_conflict_; a.unsettled = d_unsettled_;
     a.flags = d_flags_;
-    a.max_apps = d_max_apps_;
+    a.max_apps = (unsigned long long *)(d_flags_ + 1);
     a.n_src = net_.n_src; a.n_g2 = net_.n_g2(); a.n_g3 = net_.n_g3(); a.n_wide = net_.n_wide(); a.n_extra = n_extra; a.n_rows = net_.n_rows;
     a.stride = stride_; a.wpc = wpc;
     a.n_lanes = n_lanes_;
@@ -2546,17 +2563,35 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
     const size_t items = (size_t)net_.n_rows * wpc;
     const uint32_t threads = items >= 1024 ? 1024 : (items >= 256 ? 512 : 128);
     const uint32_t ctas = (stride_ + wpc - 1) / wpc;
+    const size_t snap_bytes = (size_t)net_.n_rows / 8 + 1;
+    const bool with_snapshot = T_ <= 64;  // interactive-sized runs: get_wire_state will want lane 0 next
+    a.snap0 = a.snap1 = nullptr;
+    a.snap_bytes = 0;
+    if (with_snapshot) {
+        if (pack_cap_ < 2 * snap_bytes) {
+            CU_TRY(cudaStreamSynchronize(ST));
+            cudaFree(d_pack_);
+            d_pack_ = nullptr;
+            pack_cap_ = 0;
+            CU_TRY(cudaMalloc((void **)&d_pack_, 2 * snap_bytes + 64));
+            pack_cap_ = 2 * snap_bytes + 64;
+        }
+        a.snap0 = d_pack_;
+        a.snap1 = d_pack_ + snap_bytes;
+        a.snap_bytes = (uint32_t)snap_bytes;
+        snap_.resize(2 * snap_bytes);
+    }
     k_resident_run<<<ctas, threads, smem, ST>>>(a);
     LAUNCHED();
-    unsigned long long apps = 0;
-    CU_TRY(cudaMemcpyAsync(h_flags_, d_flags_, sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
-    CU_TRY(cudaMemcpyAsync(&apps, d_max_apps_, 8, cudaMemcpyDeviceToHost, ST));
+    CU_TRY(cudaMemcpyAsync(h_flags_, d_flags_, 2 * sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
+    if (with_snapshot) CU_TRY(cudaMemcpyAsync(snap_.data(), d_pack_, 2 * snap_bytes, cudaMemcpyDeviceToHost, ST));
     if ((rc = drives_end())) return rc;
     CU_TRY(cudaStreamSynchronize(ST));
+    snap_valid_ = with_snapshot;
     cold_ = false;
     frontier_valid_ = false;
     last_mode_ = 3;
-    last_apps_ = apps;
+    last_apps_ = *(const unsigned long long *)(h_flags_ + 1);
     if (h_flags_->any_conflict) return B2_RUN_CONFLICT;
     if (h_flags_->any_unsettled) return B2_RUN_MAX_STEPS_REACHED;
     return B2_RUN_OK;
@@ -2624,10 +2659,12 @@ int Engine::get_wire_state(uint32_t wire, uint32_t *p0, uint32_t *p1, size_t wor
     if (!p0 || !p1) return B2_ERR_NULL;
     const uint32_t width = net_.width[wire], need = (width + 31) / 32;
     if (words < need) return B2_ERR_RANGE;
-    int rc = ensure_lanes();
-    if (rc) return rc;
+    if (!snap_valid_) {  // (the common case — every net read back after one eval — touches no CUDA call at all)
+        int rc = ensure_lanes();
+        if (rc) return rc;
+        if ((rc = refresh_snapshot())) return rc;
+    }
     for (uint32_t i = 0; i < need; i++) p0[i] = p1[i] = 0;
-    if ((rc = refresh_snapshot())) return rc;
     const uint8_t *s0 = snap_.data(), *s1 = snap_.data() + snap_.size() / 2;
     for (uint32_t j = 0; j < width; j++) {
         const uint32_t row = net_.row_of_bit[net_.bit_off[wire] + j];

@@ -183,7 +183,6 @@ class Engine {
     bool opt_budget_inclusive_ = false;  // SURVEY.md A.6-1 switch: `steps >= max_steps` instead of `>`
     uint32_t opt_u_ = 0;  // 0 = automatic gates-per-thread choice in k_eval2
     bool use_resident_ = true, resident_attr_set_ = false;
-    unsigned long long *d_max_apps_ = nullptr;
     uint32_t last_mode_ = 0;
     uint64_t last_apps_ = 0;
 };
