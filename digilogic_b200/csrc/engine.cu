@@ -2263,7 +2263,17 @@ int Engine::run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &res
     la.cur = cur_; la.chg_w = chg_w_; la.frontier_valid = frontier_valid_ ? 1 : 0;
     void *params[] = {&la};
     const uint32_t grid = sh.pair_blocks * (loop_ctas_ / sh.pair_blocks);
-    CU_TRY(cudaLaunchCooperativeKernel((const void *)k_unit_delay_loop, dim3(grid), sh.block, params, 0, ST));
+    {
+        // A refused cooperative launch (co-residency cannot be granted, e.g. under a restricted SM partition) is not an
+        // error of the run: the host-driven loop does the same work, so this engine stays on it from now on.
+        const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_unit_delay_loop, dim3(grid), sh.block, params, 0, ST);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            loop_ctas_ = 0;
+            finished = false;
+            return B2_OK;
+        }
+    }
     LAUNCHED();
     CU_TRY(cudaMemcpyAsync(h_loop_result_, d_loop_result_, sizeof(LoopResult), cudaMemcpyDeviceToHost, ST));
     CU_TRY(cudaStreamSynchronize(ST));
@@ -2354,7 +2364,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
     if (!use_frontier) frontier_valid_ = false;
     // Light applications (a short work list times the row length) run in the device-side loop, heavy ones as
     // separate fully occupied kernels; the run moves between the two as the activity changes.
-    const bool device_ok = opt_device_loop_ && use_frontier && loop_ctas_ >= sh.pair_blocks;
+    bool device_ok = opt_device_loop_ && use_frontier && loop_ctas_ >= sh.pair_blocks;
     bool want_device = device_ok && (uint64_t)(net_.n_fast() + net_.n_wide()) * stride_ <= kLoopEntryRowWords;
     const uint64_t first_k = k + 1;
     uint64_t lag_base = first_k;  // first application of the current host-driven stretch
@@ -2371,6 +2381,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
             want_device = false;
             light_streak = 0;
             lag_base = k + 1;
+            if (loop_ctas_ == 0) device_ok = false;  // the cooperative launch was refused
         }
         k++;
         last_apps_++;
