@@ -2349,7 +2349,8 @@ int Engine::run_jacobi(uint64_t max_steps) {
     // its own output row, changed in the previous application.  The flags persist across runs — a settled
     // run leaves them all zero, so the next run starts from just the source rows whose drive changed.
     // Off when gate outputs carry external drives (their merge bypasses the flags).
-    const bool use_frontier = opt_frontier_ && n_extra == 0;
+    // (work-list entries pack the gate index into 28 bits next to its kind)
+    const bool use_frontier = opt_frontier_ && n_extra == 0 && net_.n_fast() < (1u << 28);
     if (use_frontier && !d_rowchg_[0]) {
         // each flag buffer carries the two list counters of its application behind the flags: one memset clears both
         CU_TRY(cudaMalloc((void **)&d_rowchg_[0], rowchg_bytes()));
