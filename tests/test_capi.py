@@ -66,14 +66,29 @@ def test_same_validation_as_oracle():
     widths = [1, 1, 1, 2, 2, 4, 8, 1]
     for w in widths:
         assert gb.add_wire(w) == ob.add_wire(w)
-    for _ in range(300):
-        kind = int(rng.integers(0, 8))
+    for _ in range(1500):
+        kind = int(rng.integers(0, 15))
         n = int(rng.integers(0, 5))
         ins = [int(x) for x in rng.integers(0, len(widths) + 1, n)]
         out = int(rng.integers(0, len(widths) + 1))
         sel = int(rng.integers(0, len(widths) + 1))
+        x, y, off = (int(v) for v in rng.integers(0, len(widths) + 1, 3))
         def call(b):
             try:
+                if kind == 14:
+                    return ("ok", b.add_horizontal_gate(off % 6, x, out))
+                if kind == 13:
+                    return ("ok", b.add_sub(x, y, out))
+                if kind == 12:
+                    return ("ok", b.add_add(x, y, out))
+                if kind == 11:
+                    return ("ok", b.add_register(x, out, y, sel))
+                if kind == 10:
+                    return ("ok", b.add_merge(ins, out))
+                if kind == 9:
+                    return ("ok", b.add_slice(x, off, out))
+                if kind == 8:
+                    return ("ok", b.add_buffer(x, y, out))
                 if kind == 7:
                     return ("ok", b.add_multiplexer(ins, sel, out))
                 if kind == 6:
