@@ -1,0 +1,92 @@
+// Host-only fuzz of the netlist compiler (digilogic_b200/csrc/netlist.cpp), built with -fsanitize=address,undefined by
+// tests/test_capi.py: random builder calls over every component kind (valid and invalid), then compile() and a check
+// of the invariants the kernels rely on — every row index in range, implicit output rows, level ranges, resolve tables.
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include "../digilogic_b200/csrc/netlist.hpp"
+#include "../include/digilogic_b200.h"
+
+using namespace b2;
+
+#define REQUIRE(c)                                                     \
+    do {                                                               \
+        if (!(c)) {                                                    \
+            std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); \
+            return 1;                                                  \
+        }                                                              \
+    } while (0)
+
+int main(int argc, char **argv) {
+    const int rounds = argc > 1 ? std::atoi(argv[1]) : 200;
+    std::mt19937 rng(12345);
+    auto rnd = [&](uint32_t n) { return (uint32_t)(rng() % n); };
+    for (int r = 0; r < rounds; r++) {
+        Builder b;
+        const uint32_t n_wires = 4 + rnd(40);
+        for (uint32_t i = 0; i < n_wires; i++) {
+            uint32_t id;
+            const uint8_t w = rnd(4) == 0 ? (uint8_t)(1 + rnd(40)) : (uint8_t)(1 + rnd(3));
+            REQUIRE(b.add_wire(w, &id) == B2_OK && id == i);
+        }
+        const uint32_t n_calls = rnd(120);
+        for (uint32_t k = 0; k < n_calls; k++) {
+            uint32_t in[8], cell;
+            const uint32_t n = rnd(6);
+            for (uint32_t i = 0; i < 8; i++) in[i] = rnd(n_wires + 1);  // sometimes one past the end
+            const uint32_t out = rnd(n_wires + 1), x = rnd(n_wires + 1), y = rnd(n_wires + 1), z = rnd(n_wires + 1);
+            switch (rnd(10)) {
+                case 0: b.add_not(x, out, &cell); break;
+                case 1: b.add_mux(in, n, x, out, &cell); break;
+                case 2: b.add_buffer(x, y, out, &cell); break;
+                case 3: b.add_slice(x, rnd(8), out, &cell); break;
+                case 4: b.add_merge(in, n, out, &cell); break;
+                case 5: b.add_register(x, out, y, z, &cell); break;
+                case 6: b.add_arith(rnd(2) ? K_ADD : K_SUB, x, y, out, &cell); break;
+                case 7: b.add_horizontal_gate((int)rnd(6), x, out, &cell); break;
+                default: b.add_gate((int)rnd(6), in, n, out, &cell); break;
+            }
+        }
+        Compiled c;
+        compile(b, c);
+        REQUIRE(c.n_rows >= c.n_src);
+        REQUIRE(c.fan0.size() == c.kind2.size() && c.fan1.size() == c.kind2.size() && c.fan2.size() == c.kind2.size());
+        REQUIRE(c.n_two <= c.kind2.size());
+        REQUIRE(c.n_rows == c.n_src + c.n_fast() + c.n_wide() + c.n_res());
+        for (uint32_t g = 0; g < c.n_fast(); g++) REQUIRE(c.fan0[g] < c.n_rows && c.fan1[g] < c.n_rows && c.fan2[g] < c.n_rows);
+        REQUIRE(c.wide_off.size() == (size_t)c.n_wide() + 1 && c.wide_off.back() == c.wide_in.size());
+        for (uint32_t v : c.wide_in) REQUIRE(v < c.n_rows);
+        for (uint32_t g = 0; g < c.n_wide(); g++) {
+            const uint32_t n_in = c.wide_off[g + 1] - c.wide_off[g];
+            if (c.wide_kind[g] == K_REG) REQUIRE(n_in == 4);
+            if (c.wide_kind[g] == K_ADD || c.wide_kind[g] == K_SUB) REQUIRE(n_in % 2 == 0 && c.wide_nsel[g] < n_in / 2);
+            if (c.wide_kind[g] == K_MUX) REQUIRE(n_in == c.wide_nsel[g] + (1u << c.wide_nsel[g]));
+        }
+        REQUIRE(c.row_of_bit.size() == c.bit_off.back());
+        for (uint32_t v : c.row_of_bit) REQUIRE(v < c.n_rows);
+        if (c.n_res()) {
+            REQUIRE(c.has_tristate && c.cyclic && c.res_off.back() == c.res_in.size());
+            for (uint32_t v : c.res_in) REQUIRE(v >= c.n_src && v < c.n_src + c.n_fast() + c.n_wide());
+        }
+        for (size_t i = 0; i < c.res_of_bit.size(); i++)
+            if (c.res_of_bit[i] >= 0) REQUIRE(c.row_of_bit[i] == c.n_src + c.n_fast() + c.n_wide() + (uint32_t)c.res_of_bit[i]);
+        if (c.has_state || c.has_tristate) REQUIRE(c.cyclic);
+        if (!c.cyclic) {
+            REQUIRE(c.levels.size() == c.depth);
+            uint32_t k2 = 0, k3 = c.n_two, kw = 0;
+            for (const Level &lv : c.levels) {
+                REQUIRE(lv.g2_begin == k2 && lv.g2_end >= k2 && lv.g3_begin == k3 && lv.g3_end >= k3 && lv.wide_begin == kw);
+                k2 = lv.g2_end; k3 = lv.g3_end; kw = lv.wide_end;
+                // a gate only reads rows of earlier levels (or sources)
+                for (uint32_t g = lv.g2_begin; g < lv.g2_end; g++) REQUIRE(c.fan0[g] < c.n_src + lv.g2_begin || c.fan0[g] >= c.n_src + c.n_two);
+            }
+            REQUIRE(k2 == c.n_two && k3 == c.n_fast() && kw == c.n_wide());
+        } else {
+            REQUIRE(c.levels.size() <= 1);
+        }
+    }
+    std::printf("netlist_fuzz ok (%d rounds)\n", rounds);
+    return 0;
+}

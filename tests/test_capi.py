@@ -5,6 +5,7 @@ product fails loudly, not quietly, without a GPU."""
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -147,6 +148,18 @@ def test_compile_info_of_the_wider_component_set():
     # adder bits on the CSR class (8), slice bits are one-input fast gates (4), the 4-input reduction is a CSR gate;
     # acyclic: adder (1) -> slice (2) -> reduction (3)
     assert (i.n_sources, i.n_gates2, i.n_gates_wide, i.cyclic, i.depth) == (16, 4, 8 + 1, 0, 3)
+
+
+def test_netlist_compiler_fuzz_under_sanitizers(tmp_path):
+    """tests/netlist_fuzz.cpp: random builder calls over every component kind, compile(), invariants of the SoA arrays —
+    host-only, built with AddressSanitizer + UBSan."""
+    exe = str(tmp_path / "netlist_fuzz")
+    res = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", exe,
+                          os.path.join(ROOT, "tests", "netlist_fuzz.cpp"), os.path.join(ROOT, "digilogic_b200", "csrc", "netlist.cpp")],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe, "300"], capture_output=True, text=True)
+    assert run.returncode == 0 and "netlist_fuzz ok" in run.stdout, run.stderr[-2000:]
 
 
 def test_build_takes_the_builder():
