@@ -7,18 +7,20 @@
 Workload (config.workload): BASELINE config 3 — synthetic random combinational DAG, 1M gates,
 depth 200, fan-in 2, 4096 inputs, 2^24 stimulus lanes per GPU, 4-state engine with two-valued
 stimulus generated on the device from (seed, input, global lane-word).  One step = one settle
-(run_sim to the fixed point) of every lane of the batch, tile by tile (256 lane-words per tile,
-two simulator replicas on two CUDA streams taking alternate tiles), plus extraction of the 1024
-designated output rows.  At N GPUs every rank runs the same per-GPU batch on its own lane range
-(weak scaling) and the packed output planes are all-gathered once per step with NCCL.
+(run_sim to the fixed point) of every lane of the batch plus extraction of the 1024 designated
+output rows = ONE call of the C ABI's batch runner (b2_batch_run_generated) = one launch of the
+persistent level-sweep kernel (digilogic_b200/csrc/sweep.cuh).  At N GPUs every rank runs the same
+per-GPU batch on its own lane range (weak scaling); the output rows are stored into every rank's
+gathered planes over NVLink by the sweep kernel itself (--nccl-gather: by ncclAllGather afterwards).
 
 value      = G * L_total / max-over-ranks device time                (gate-lane evals/s)
-e2e        = the same through the C ABI with HOST buffers: pinned-host stimulus planes in,
-             output planes out, copies inside the timed region (overlapped with the settles)
-roofline   = k_eval2 (the per-level gate kernel): 48 algorithmic bytes per gate per 64-lane
-             word / its effective launch duration (timed region / launches: the
-             replicas' launches overlap), against MEASURED_PEAKS.json; traffic = DRAM bytes per
-             launch from the committed ncu capture (profiles/traffic.json)
+e2e        = the same through the C ABI with HOST buffers (b2_batch_run_planes): pinned-host stimulus
+             planes in, output planes out, both moved inside the timed region every step
+roofline   = k_sweep: 48 algorithmic bytes per gate per 64-lane word / launch duration
+             (CUDA events), against MEASURED_PEAKS.json; traffic / dram_frac = DRAM bytes of the same
+             kernel from the committed ncu capture (profiles/traffic.json)
+shard_check (N > 1) = rank 0 settles a tile of another rank's lanes itself and compares with the gathered planes
+config5    (N > 1) = secondary: BASELINE config 5 (10M gates, 2^26 lanes sharded over the N GPUs)
 cpu_baseline = the scalar event-driven gsim restatement (oracle/gsim_oracle.c, "port") on the
              host cores over a bounded lane sample of the same netlist
 valid_elision = secondary figure (never the headline): the same job with B2_OPT_VALID_ELISION
@@ -58,15 +60,19 @@ def parse_args():
     ap.add_argument("--outputs", type=int, default=1024)
     ap.add_argument("--lanes", type=int, default=1 << 24, help="stimulus lanes per GPU")
     ap.add_argument("--tile-words", type=int, default=0,
-                    help="64-lane words resident per tile and replica (0 = batch.auto_tile_words: 256 for this netlist)")
-    ap.add_argument("--host-threads", type=int, default=1,
-                    help="1: one host thread per replica issues its launches (0 for runs under ncu)")
-    ap.add_argument("--streams", type=int, default=2, help="simulator replicas on separate CUDA streams, alternating tiles")
+                    help="64-lane words per tile and slot of the level sweep (0 = batch.auto_sweep_shape)")
+    ap.add_argument("--slots", type=int, default=0, help="tiles in flight in the level sweep (0 = batch.auto_sweep_shape)")
+    ap.add_argument("--task-iters", type=int, default=1, help="256-thread iterations per gate task of the sweep")
+    ap.add_argument("--unroll", type=int, default=4, help="gates per thread of the one/two-input class in the sweep (2 or 4)")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="resident CTAs per SM of the sweep (0 = as many as fit)")
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="N > 1: move the output planes with ncclAllGather after the sweep instead of storing them into the peers' "
+                         "planes from the sweep kernel (the baseline the fused gather is compared with)")
+    ap.add_argument("--no-config5", action="store_true", help="N > 1: skip the secondary config-5 settle")
     ap.add_argument("--max-steps", type=int, default=10_000)
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-ring-tiles", type=int, default=0, help="host stimulus ring size in tiles (0 = whole batch on 1 GPU, 2^20 lanes otherwise)")
     ap.add_argument("--cpu-lanes-per-core", type=int, default=24)
-    ap.add_argument("--valid-elision", action="store_true", help="experiment: run the main timed loop with B2_OPT_VALID_ELISION (not the headline configuration)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-elision-probe", action="store_true", help="skip the secondary run with B2_OPT_VALID_ELISION")
     ap.add_argument("--no-cpu", action="store_true")
@@ -142,10 +148,9 @@ def config_dict(args, n_gpus, extra=None):
         "gates": args.gates, "depth": args.depth, "inputs": args.inputs, "outputs": args.outputs,
         "lanes_per_gpu": args.lanes, "lanes_total": args.lanes * n_gpus, "tile_words": args.tile_words,
         "max_steps": args.max_steps, "seed": hex(SEED),
-        "streams": args.streams,
-        "cache": "no flush: every step streams the whole wire store of each replica (GBs, far beyond the 126 MB L2) "
-                 "200 levels deep; what L2 keeps between consecutive level kernels is part of the design (DESIGN.md §6)",
-        "parallelism": f"lane-sharded x{n_gpus}, full netlist replica per GPU, one NCCL all-gather of output planes per step",
+        "cache": "no flush: every step streams the whole wire store of each slot (GBs, far beyond the 126 MB L2) "
+                 "200 levels deep; what L2 keeps between consecutive levels is part of the design (DESIGN.md §6)",
+        "parallelism": f"lane-sharded x{n_gpus}, full netlist replica per GPU, output planes gathered into every rank each step",
     }
     if extra:
         cfg.update(extra)
@@ -253,64 +258,63 @@ def run_b200(args):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)   # the harness's channel for two 128-byte blobs and the timing reduction
 
     from digilogic_b200 import SimulatorBuilder, SimulationRunResult
-    from digilogic_b200.batch import InterleavedRunner, gather_output_planes, reduce_worst, shard_words
+    from digilogic_b200.batch import Batch, auto_sweep_shape, setup_comm, shard_words
     from digilogic_b200.gsim import kernel_launches
 
     gen = build_netlist(args)
     t0 = time.perf_counter()
-    first = gen.emit(SimulatorBuilder()).build()
+    sim = gen.emit(SimulatorBuilder()).build()            # compiled once; every slot shares the one device copy
     compile_s = time.perf_counter() - t0
-    stream = torch.cuda.Stream(device=dev)   # timing events, output planes and the collective live on this stream
+    stream = torch.cuda.Stream(device=dev)   # the batch runs on this stream; the timing events are recorded on it
     torch.cuda.set_stream(stream)
 
     words_local = args.lanes // 64
     total_words = words_local * world
     w_begin, w_end = shard_words(total_words, world, rank)
-    from digilogic_b200.batch import auto_tile_words
-    tile = min(args.tile_words, words_local) if args.tile_words else auto_tile_words(first, words_local)
-    args.tile_words = tile
-    assert words_local % tile == 0
-    made = []
-
-    def make_sim():
-        sim = first if not made else gen.emit(SimulatorBuilder()).build()
-        made.append(sim)
-        sim.set_device(local_rank)
-        return sim
-
-    runner = InterleavedRunner(make_sim, gen.inputs, gen.outputs, tile, args.streams, args.max_steps, device=dev,
-                               host_threads=bool(args.host_threads))
-    sims = runner.sims
-    sim = sims[0]
-    if args.valid_elision:
-        for x in sims:
-            x.set_option(x.OPT_VALID_ELISION, 1)
-        args.no_elision_probe = True
+    auto_tile, auto_slots = auto_sweep_shape(sim, words_local)
+    tile = min(args.tile_words, words_local) if args.tile_words else auto_tile
+    slots = args.slots or auto_slots
+    args.tile_words, args.slots = tile, slots
+    batch = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=local_rank, stream=stream.cuda_stream)
+    batch.set_option(Batch.OPT_TASK_ITERS, args.task_iters)
+    batch.set_option(Batch.OPT_UNROLL, args.unroll)
+    if args.ctas_per_sm:
+        batch.set_option(Batch.OPT_CTAS_PER_SM, args.ctas_per_sm)
     info = sim.info
     n_out = len(gen.outputs)
-    out_v = torch.zeros((n_out, words_local), dtype=torch.int64, device=dev)
-    out_m = torch.zeros_like(out_v)
+    out_v = out_m = None
+    if world > 1:
+        # gathered planes [world, n_out, words_local] on every rank; with the peers' planes mapped (CUDA IPC) the sweep
+        # kernel's output tasks store this rank's rows into all of them over NVLink
+        setup_comm(batch, words_local, local_rank, map_peers=not args.nccl_gather)
+    else:
+        out_v = torch.zeros((n_out, words_local), dtype=torch.int64, device=dev)
+        out_m = torch.zeros_like(out_v)
 
-    def step(record=False):
-        worst = runner.run_generated(w_begin, words_local, SEED, 0, out_v, out_m, 0)
-        if world > 1:
-            gv, gm = gather_output_planes(out_v, out_m, world)
-            worst = reduce_worst(worst, dev)
-            return worst, gv, gm
-        return worst, out_v, out_m
+    def step():
+        # ONE C call per step: stimulus, settle, output rows to their destinations, (N > 1) the ranks meet
+        batch.run_generated(SEED, 0, w_begin, words_local, args.max_steps, out_v, out_m)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def planes():
+        if world > 1:
+            return tuple(torch.as_tensor(x, device=dev) for x in batch.gathered())
+        return out_v, out_m
+
     for _ in range(args.warmup):
-        worst, gv, gm = step()
+        step()
+    worst = batch.wait()
     barrier()
     assert worst == SimulationRunResult.Ok
+    binfo = batch.info
+    assert binfo.sweep == 1, "config 3 is acyclic: the level-sweep kernel must be the path that runs"
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -320,11 +324,13 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        worst, gv, gm = step(record=True)
+        step()
     e1.record(stream)
+    worst = batch.wait()
     barrier()
     launches = kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    assert worst == SimulationRunResult.Ok
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -332,70 +338,89 @@ def run_b200(args):
     ms = float(t.item())
 
     # a checksum of the outputs, so that the timed work is observable (and comparable across N)
-    checksum = int((gv.to(torch.int64).sum() ^ gm.to(torch.int64).sum()).item()) & 0xFFFFFFFFFFFFFFFF
+    gv, gm = planes()
+    checksum = int((gv.sum() ^ gm.sum()).item()) & 0xFFFFFFFFFFFFFFFF
+
+    # N > 1: rank 0 settles one tile of ANOTHER rank's lane range itself and compares it with what that rank gathered
+    shard_check = None
+    if world > 1:
+        other = world - 1
+        chk_words = min(tile, words_local)
+        ob, _ = shard_words(total_words, world, other)
+        probe = Batch(sim, gen.inputs, gen.outputs, chk_words, 1, device=local_rank, stream=stream.cuda_stream)
+        pv = torch.zeros((n_out, chk_words), dtype=torch.int64, device=dev)
+        pm = torch.zeros_like(pv)
+        probe.run_generated(SEED, 0, ob + words_local - chk_words, chk_words, args.max_steps, pv, pm)   # the other rank's last tile
+        probe.wait()
+        ok = torch.equal(gv[other][:, words_local - chk_words:], pv) and torch.equal(gm[other][:, words_local - chk_words:], pm)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)     # every rank checks its copy of the gathered planes
+        shard_check = bool(flag.item())
+        del probe
 
     gate_lane_evals = float(args.gates) * args.lanes * world * args.steps
     value = gate_lane_evals / (ms * 1e-3)
 
-    # roofline of the dominant kernel (k_eval2, one launch per level per tile).  With several replicas in
-    # flight the launches overlap, so the per-launch duration is the effective one: timed region / launches
-    # (the few other kernels of a step, 0.6 % of it, are charged to k_eval2).
-    n_tiles = words_local // tile
-    eval_launches = n_tiles * info.depth * args.steps
-    avg_launch_s = ms * 1e-3 / eval_launches
-    gate_words_per_launch = (args.gates / info.depth) * info.row_stride
-    algo_bytes_per_launch = ALGO_BYTES_PER_GATE_WORD * gate_words_per_launch
+    # roofline of the dominant kernel: k_sweep, ONE launch per step and GPU (stimulus, all levels of all tiles, output rows).
+    # Algorithmic bytes: 48 B per gate per 64-lane word; the stimulus and output rows add 16 B per row-word.
+    n_tiles = -(-words_local // tile)
+    launch_s = ms * 1e-3 / args.steps
+    gate_words = float(args.gates) * words_local
+    algo_bytes = ALGO_BYTES_PER_GATE_WORD * gate_words + 16.0 * (len(gen.inputs) + n_out) * words_local
     peak, peak_kind = load_peaks()
-    achieved = algo_bytes_per_launch / avg_launch_s / 1e9
+    achieved = algo_bytes / launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "kernel": "k_eval2<4,false,false>",
-                "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
-                "launches_timed": eval_launches,
-                "note": "effective launch duration (timed region / launches; replicas overlap). frac > 1: a level's output rows are "
-                        "still in L2 when the next level reads them, so about a third of the algorithmic fan-in bytes never reach HBM "
-                        "(see traffic)"}
+                "traffic": None, "dram_frac": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                "kernel": f"k_sweep<{args.unroll}>", "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": launch_s * 1e3,
+                "launches_timed": args.steps,
+                "note": "one launch = one step on one GPU; duration = CUDA events around the timed launches / steps. frac is the "
+                        "algorithmic fraction (> 1 because a level's output rows are still in L2 when the next level reads them); "
+                        "dram_frac = measured DRAM bytes of the same kernel (ncu, profiles/traffic.json, scaled per gate-word) / "
+                        "duration / peak is the physical one"}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
             with open(traffic_path) as f:
                 tj = json.load(f)
-            if tj.get("tile_words") == tile and tj.get("gates") == args.gates and tj.get("streams", 1) == args.streams:
-                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+            if (tj.get("kernel", "").startswith("k_sweep") and tj.get("tile_words") == tile and tj.get("slots") == slots
+                    and tj.get("gates") == args.gates):
+                roofline["traffic"] = tj["dram_bytes_per_gate_word"] * gate_words
+                roofline["dram_frac"] = roofline["traffic"] / launch_s / 1e9 / peak
+                roofline["l2_hit_rate_pct"] = tj.get("l2_hit_rate_pct")
         except Exception:
             pass
 
-    # secondary figure, not the headline: the same job with valid-plane elision (rows that are provably
-    # valid on every lane keep no valid plane in HBM: 24 B instead of 48 B per gate-word; bit-identical results)
-    elision = None
-    if not args.no_elision_probe:
-        for x in sims:
-            x.set_option(x.OPT_VALID_ELISION, 1)
-        worst, gv2, gm2 = step()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        n_el = max(1, min(args.steps, 2))
-        for _ in range(n_el):
-            worst, gv2, gm2 = step()
-        f1.record(stream)
-        barrier()
-        ms2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        ms2 = float(ms2.item())
-        cs2 = int((gv2.to(torch.int64).sum() ^ gm2.to(torch.int64).sum()).item()) & 0xFFFFFFFFFFFFFFFF
-        elision = {"value": float(args.gates) * args.lanes * world * n_el / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / n_el,
-                   "steps": n_el, "bytes_per_gate_word": 24, "output_checksum_equal": cs2 == checksum,
-                   "note": "B2_OPT_VALID_ELISION=1; all stimulus lanes valid, so no valid plane is read or written"}
-        for x in sims:
-            x.set_option(x.OPT_VALID_ELISION, 0)
-        step()   # back to plain two-plane rows before the end-to-end leg
-        barrier()
+    config5 = None
+    if world > 1 and not args.no_config5:
+        config5 = config5_probe(args, torch, dist, world, rank, local_rank, dev, stream)
 
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words_local, w_begin, barrier,
-                      (out_v, out_m))
+        e2e = run_e2e(args, torch, dist, batch, sim, gen, world, rank, dev, words_local, barrier)
+
+    # secondary figure, not the headline: B2_OPT_VALID_ELISION on the simulator-replica path of the batch runner (rows that are
+    # provably valid on every lane keep no valid plane in HBM: 24 B instead of 48 B per gate-word; bit-identical results)
+    elision = None
+    if world == 1 and not args.no_elision_probe:
+        sim.set_option(sim.OPT_VALID_ELISION, 1)
+        eb = Batch(sim, gen.inputs, gen.outputs, 256, 2, device=local_rank, stream=stream.cuda_stream)
+        eb.set_option(Batch.OPT_SWEEP, 0)
+        ev2, em2 = torch.zeros_like(out_v), torch.zeros_like(out_m)
+        eb.run_generated(SEED, 0, w_begin, words_local, args.max_steps, ev2, em2)
+        eb.wait()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        eb.run_generated(SEED, 0, w_begin, words_local, args.max_steps, ev2, em2)
+        f1.record(stream)
+        eb.wait()
+        ms2 = f0.elapsed_time(f1)
+        cs2 = int((ev2.sum() ^ em2.sum()).item()) & 0xFFFFFFFFFFFFFFFF
+        elision = {"value": float(args.gates) * args.lanes / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "steps": 1,
+                   "bytes_per_gate_word": 24, "output_checksum_equal": cs2 == checksum,
+                   "note": "B2_OPT_VALID_ELISION=1 on the per-level kernels (simulator replicas, tile 256 x 2, one issuing thread); "
+                           "all stimulus lanes valid, so no valid plane is read or written"}
+        sim.set_option(sim.OPT_VALID_ELISION, 0)
+        del eb, ev2, em2
 
     unit_delay = None
     if rank == 0 and world == 1 and not args.no_unit_delay_probe:
@@ -413,20 +438,72 @@ def run_b200(args):
         cpu["bitsliced"] = {"value": vb, "unit": UNIT, "cores": cores,
                             "sample": f"{cores * 512} lanes, {dtb:.2f} s, dense 64-lane bit-sliced CPU model (oracle/bitsliced.c), one "
                                       f"levelised pass per thread: a best-CPU context figure, not gsim's algorithm"}
+        cpu["gpu_over_scalar_port"] = value / v
+        cpu["gpu_over_bitsliced_cpu"] = value / vb
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 bit-planes (value+valid)", "data": "synthetic",
-            "config": config_dict(args, world, {"tiles_per_step": n_tiles, "row_stride_words": info.row_stride,
-                                                "store_bytes": info.store_bytes * len(sims), "compile_s": round(compile_s, 3)}),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "valid_elision": elision, "unit_delay": unit_delay, "gpu_launches": int(launches), "clocks": clocks,
-            "output_checksum": f"{checksum:#018x}",
+            "config": config_dict(args, world, {"tiles_per_step": n_tiles, "slots": slots, "row_stride_words": tile,
+                                                "store_bytes": binfo.store_bytes, "compile_s": round(compile_s, 3),
+                                                "grid_ctas": binfo.grid_ctas, "gates_per_task": binfo.gates_per_task,
+                                                "tasks_per_tile": binfo.tasks_per_pass,
+                                                "gather": None if world == 1 else ("ncclAllGather" if args.nccl_gather else
+                                                                                   "fused: sweep output tasks store into every rank's planes over NVLink (CUDA IPC)")}),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "valid_elision": elision, "unit_delay": unit_delay,
+            "gpu_launches": int(launches), "clocks": clocks, "output_checksum": f"{checksum:#018x}",
         }
+        if shard_check is not None:
+            line["shard_check"] = shard_check
+        if config5 is not None:
+            line["config5"] = config5
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def config5_probe(args, torch, dist, world, rank, local_rank, dev, stream, total_lanes=1 << 26):
+    """Secondary key at N > 1: BASELINE config 5 — 10M-gate DAG, 2^26 lanes sharded contiguously over the N GPUs, output
+    planes gathered into every rank — one warm-up on an eighth of the shard, then one timed settle of the whole shard."""
+    from digilogic_b200 import SimulatorBuilder, netgen
+    from digilogic_b200.batch import Batch, auto_sweep_shape, setup_comm, shard_words
+    gates, depth, n_in, n_out = 10_000_000, 200, 16384, 1024
+    t0 = time.perf_counter()
+    gen = netgen.random_dag(n_gates=gates, depth=depth, n_inputs=n_in, n_outputs=n_out, seed=0xD1610005)
+    sim = gen.emit(SimulatorBuilder()).build()
+    build_s = time.perf_counter() - t0
+    words_local = total_lanes // 64 // world
+    w_begin, _ = shard_words(words_local * world, world, rank)
+    tile, slots = auto_sweep_shape(sim, words_local)
+    batch = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=local_rank, stream=stream.cuda_stream)
+    setup_comm(batch, words_local, local_rank, map_peers=not args.nccl_gather)
+    batch.run_generated(0xD1610005, 0, w_begin, max(words_local // 8, tile), args.max_steps)
+    batch.wait()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    batch.run_generated(0xD1610005, 0, w_begin, words_local, args.max_steps)
+    e1.record(stream)
+    worst = batch.wait()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    gv, gm = (torch.as_tensor(x, device=dev) for x in batch.gathered())
+    checksum = int((gv.sum() ^ gm.sum()).item()) & 0xFFFFFFFFFFFFFFFF
+    peak, _ = load_peaks()
+    value = float(gates) * total_lanes / (ms * 1e-3)
+    out = {"workload": f"BASELINE config 5: random DAG, {gates} gates, depth {depth}, {n_in} inputs, {total_lanes} lanes sharded over "
+                       f"{world} GPUs ({words_local * 64} per GPU), {n_out} output rows gathered into every rank",
+           "value": value, "unit": UNIT, "ms": ms, "steps": 1, "result": int(worst), "tile_words": tile, "slots": slots,
+           "roofline_frac_per_gpu": ALGO_BYTES_PER_GATE_WORD * gates * words_local / (ms * 1e-3) / 1e9 / peak,
+           "netgen_and_compile_s": round(build_s, 1), "store_bytes": batch.info.store_bytes,
+           "output_checksum": f"{checksum:#018x}"}
+    del batch
+    return out
 
 
 def unit_delay_probe(args, n_lanes=65536, clocks=20):
@@ -484,45 +561,43 @@ def unit_delay_probe(args, n_lanes=65536, clocks=20):
             "lfsr_state_matches_software": bool(ok)}
 
 
-def run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words_local, w_begin, barrier, dev_out):
-    """Same metric through the C ABI with host buffers (b2_set_drives_lanes / b2_gather_wires_host_async):
-    every tile's stimulus planes are copied from pinned host memory and its output planes back to
-    pinned host memory inside the timed region."""
+def run_e2e(args, torch, dist, batch, batch_sim, gen, world, rank, dev, words_local, barrier):
+    """Same metric through the C ABI with HOST buffers: one b2_batch_run_planes call per step reads the stimulus planes from
+    page-locked host memory (the sweep kernel's stimulus tasks load them over PCIe) and writes the output planes back to
+    page-locked host memory (its output tasks store them over PCIe) — both inside the timed region, both every step."""
     n_in, n_out = len(gen.inputs), len(gen.outputs)
-    tile = runner.tile_words
-    # One GPU: host planes for the whole batch (17.2 + 4.3 GB).  Several GPUs share one host: a ring of
-    # 2^20 lanes (1.3 GB) per rank bounds the pinned memory; every tile is still copied in and out.
-    ring_tiles = args.e2e_ring_tiles or (words_local // tile if world == 1 else max(8, 16384 // tile))
-    ring_tiles = min(ring_tiles, words_local // tile)
-    ring_words = ring_tiles * tile
+    tile = args.tile_words
+    # One GPU: host planes for the whole batch (17.2 + 4.3 GB).  Several GPUs share one host: a ring of a quarter of the
+    # shard (2^22 lanes, 5.4 GB per rank) bounds the pinned memory; every tile is still read and written over PCIe.
+    ring_words = args.e2e_ring_tiles * tile if args.e2e_ring_tiles else (words_local if world == 1 else max(words_local // 4, tile))
+    ring_words = min(ring_words, words_local)
     try:
         hin_v = torch.empty((n_in, ring_words), dtype=torch.int64, pin_memory=True)
         hin_m = torch.empty((n_in, ring_words), dtype=torch.int64, pin_memory=True)
-        hout_v = torch.empty((n_out, ring_words), dtype=torch.int64, pin_memory=True)
-        hout_m = torch.empty((n_out, ring_words), dtype=torch.int64, pin_memory=True)
+        hout_v = torch.zeros((n_out, ring_words), dtype=torch.int64, pin_memory=True)
+        hout_m = torch.zeros((n_out, ring_words), dtype=torch.int64, pin_memory=True)
     except Exception as ex:  # not enough pinnable host memory on this box
         return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
-    # host stimulus = the same counter-based words, produced once on the device and copied out before
-    # the timed region (numpy generation of 17 GB would take minutes): after a settle the source rows
-    # of the store hold the drives, so gathering the input rows returns the stimulus planes
-    torch.cuda.synchronize()
-    for w0 in range(0, ring_words, tile):
-        sim.fill_stimulus(gen.inputs, SEED, lane_word_base=w_begin + w0, mode=0)
-        sim.run_sim_lanes_async(args.max_steps)
-        sim.gather_wires_ptr(gen.inputs, hin_v.data_ptr() + 8 * w0, hin_m.data_ptr() + 8 * w0, ring_words, device=False)
-    sim.synchronize()
-    inv, inm, outv, outm = hin_v.numpy(), hin_m.numpy(), hout_v.numpy(), hout_m.numpy()
-    worst = runner.run_host(inv, inm, outv, outm, words_local)  # warm-up
+    # host stimulus = the same counter-based words, produced once on the device before the timed region (numpy generation of
+    # 17 GB would take minutes): a helper batch whose "outputs" are the input wires stores them straight into the pinned planes
+    from digilogic_b200.batch import Batch
+    w_begin = rank * words_local
+    helper = Batch(batch_sim, gen.inputs, gen.inputs, tile, args.slots, device=dev.index)
+    helper.run_generated(SEED, 0, w_begin, ring_words, args.max_steps, hin_v, hin_m)
+    helper.wait()
+    del helper
+    ring = ring_words if ring_words < words_local else 0
+
+    def step():
+        batch.run_planes(hin_v, hin_m, words_local, args.max_steps, hout_v, hout_m, in_ring_words=ring, out_ring_words=ring)
+
+    step()
+    worst = batch.wait()      # warm-up
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        if world > 1:
-            # host planes go to this rank's host memory; the cross-rank gather moves the device copies
-            from digilogic_b200.batch import gather_output_planes
-            worst = runner.run_host(inv, inm, outv, outm, words_local, dev_out[0], dev_out[1])
-            gather_output_planes(dev_out[0], dev_out[1], world)
-        else:
-            worst = runner.run_host(inv, inm, outv, outm, words_local)   # returns after the last D2H copy
+        step()
+    worst = max(worst, batch.wait())   # returns when the last output row is in host memory (and, N > 1, the ranks have met)
     barrier()
     ms = (time.perf_counter() - t0) * 1e3   # host clock: the path ends in host memory
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -530,10 +605,12 @@ def run_e2e(args, torch, dist, sim, runner, gen, world, rank, dev, stream, words
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = float(args.gates) * args.lanes * world * args.e2e_steps / (ms * 1e-3)
+    outv, outm = hout_v.numpy(), hout_m.numpy()
     return {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(n_in * words_local * 16),
             "d2h_bytes_per_step": int(n_out * words_local * 16), "ms_per_step": ms / args.e2e_steps, "steps": args.e2e_steps,
-            "result": int(worst), "host_ring_tiles": ring_tiles, "tiles_per_step": words_local // tile,
-            "overlap": "H2D of a replica's next tile and D2H of its previous one overlap the settles (engine copy streams)",
+            "result": int(worst), "host_ring_words": ring_words, "tiles_per_step": -(-words_local // tile),
+            "path": "b2_batch_run_planes: zero-copy PCIe reads of the pinned stimulus planes by the sweep kernel's stimulus tasks, "
+                    "zero-copy PCIe stores of the output rows by its output tasks; one C call per step",
             "host_checksum": f"{int(outv.sum() ^ outm.sum()) & 0xFFFFFFFFFFFFFFFF:#018x}"}
 
 

@@ -21,6 +21,14 @@ class SimInfo(C.Structure):
     ]
 
 
+class BatchInfo(C.Structure):
+    _fields_ = [
+        ("tile_words", u32), ("n_slots", u32), ("sweep", u32), ("tasks_per_pass", u32), ("grid_ctas", u32),
+        ("gates_per_task", u32), ("n_ranks", u32), ("rank", u32), ("peers_mapped", u32), ("pad", u32),
+        ("store_bytes", u64), ("words_local", u64), ("last_tiles", u64), ("last_tickets", u64),
+    ]
+
+
 SIGNATURES = {
     "b2_last_error": (C.c_char_p, []),
     "b2_version": (C.c_char_p, []),
@@ -64,6 +72,25 @@ SIGNATURES = {
     "b2_gather_wires_host": (i32, [vp, vp, u32, vp, vp, sz]),
     "b2_gather_wires_host_async": (i32, [vp, vp, u32, vp, vp, sz]),
     "b2_pack_sim_state": (i32, [vp, vp, u32, vp, vp, sz, pu64]),
+    "b2_builder_set_option": (i32, [vp, i32, C.c_int64]),
+    "b2_sim_clone": (vp, [vp]),
+    "b2_batch_new": (i32, [vp, vp, u32, vp, u32, u32, u32, C.POINTER(vp)]),
+    "b2_batch_free": (None, [vp]),
+    "b2_batch_set_device": (i32, [vp, i32]),
+    "b2_batch_set_stream": (i32, [vp, vp]),
+    "b2_batch_set_option": (i32, [vp, i32, C.c_int64]),
+    "b2_batch_get_info": (i32, [vp, C.POINTER(BatchInfo)]),
+    "b2_batch_run_generated": (i32, [vp, u64, i32, u64, u64, u64, vp, vp, sz, sz]),
+    "b2_batch_run_planes": (i32, [vp, vp, vp, sz, sz, u64, u64, vp, vp, sz, sz]),
+    "b2_batch_wait": (i32, [vp, C.POINTER(i32)]),
+    "b2_comm_get_unique_id": (i32, [vp]),
+    "b2_comm_init_rank": (i32, [C.POINTER(vp), i32, i32, vp, i32]),
+    "b2_comm_free": (None, [vp]),
+    "b2_batch_bind_comm": (i32, [vp, vp, u64]),
+    "b2_batch_export_gather_handle": (i32, [vp, vp]),
+    "b2_batch_import_gather_handles": (i32, [vp, vp]),
+    "b2_batch_gather_outputs": (i32, [vp]),
+    "b2_batch_gathered": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "b2_server_new": (vp, []),
     "b2_server_free": (None, [vp]),
     "b2_server_max_clients": (u64, [vp]),

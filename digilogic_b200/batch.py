@@ -1,17 +1,20 @@
-"""Lane-tiled batch runs and stimulus-sharded multi-GPU runs.
+"""Lane-tiled batch runs and stimulus-sharded multi-GPU runs: a ctypes shim over the C ABI's batch runner.
 
-A batch of L stimulus lanes is L independent gsim simulators of one netlist.  One GPU holds a
-full netlist replica and a wire-state store of `tile_words` 64-lane words; the batch is
-processed tile by tile (stimulus in -> settle -> designated output rows out).  Across GPUs the
-lane-words are split into contiguous ranges, one per rank, with no traffic between GPUs until
-the packed output planes are all-gathered once at the end (NCCL over NVLink; `gloo` in the CPU
-tests).  torch is used for device buffers, streams and the collective only.
+A batch of L stimulus lanes is L independent gsim simulators of one netlist.  Everything that moves data or launches work
+— the tiling of the lanes, the slots that work on alternate tiles, the persistent level-sweep kernel, the replicas for
+netlists with feedback, the gather of the output planes into every GPU over NVLink or NCCL — lives behind
+``b2_batch_*`` / ``b2_comm_*`` (include/digilogic_b200.h, digilogic_b200/csrc/batch.cu).  What is left here is argument
+marshalling, the pure arithmetic of sharding and tile choice, and the two small blobs a host has to pass between ranks
+(NCCL unique id, CUDA IPC handles), for which this harness uses torch.distributed.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
-from .gsim import Simulator, SimulationRunResult
+from . import _ffi
+from .gsim import B200Error, Simulator, SimulationRunResult, _check, _p
 
 
 def shard_words(total_words: int, world_size: int, rank: int) -> tuple[int, int]:
@@ -55,183 +58,196 @@ def auto_tile_words(sim: Simulator, n_words: int, l2_level_bytes: int = 20 << 20
     return max(1, min(t, n_words))
 
 
-class BatchRunner:
-    """Runs a lane batch through one simulator replica, tile by tile."""
+def auto_sweep_shape(sim: Simulator, n_words: int, l2_budget_bytes: int = 40 << 20) -> tuple[int, int]:
+    """(tile_words, n_slots) for the level-sweep kernel.  The slots in flight are interleaved level by level, so the rows
+    one level writes (gates per level x 16 B x tile_words x n_slots) are what L2 has to keep until the next level has read
+    them: that product is held near `l2_budget_bytes` of the 126 MB L2 (measured optimum, profiles/README.md) with at least
+    four slots, so that a slot's next level never waits for its previous one, and tiles of 32 .. 512 words."""
+    info = sim.info
+    if info.cyclic or info.depth == 0:
+        return min(max(n_words, 2), 512), 2
+    per_level = max((info.n_gates2 + info.n_gates3 + info.n_gates_wide) / info.depth, 1.0)
+    in_flight = max(int(l2_budget_bytes / (16.0 * per_level)), 128)       # lane-words over all slots
+    slots = 4
+    t = max(32, min(in_flight // slots, 512))
+    t = 1 << (t.bit_length() - 1)
+    while t > 2 and n_words % t:
+        t >>= 1
+    return max(2, min(t, n_words + (n_words & 1))), slots
 
-    def __init__(self, sim: Simulator, inputs, outputs, tile_words: int, max_steps: int = 10_000):
-        self.sim = sim
+
+class _DeviceArray:
+    """A device buffer owned by the C library, exposed through __cuda_array_interface__ (torch.as_tensor accepts it)."""
+
+    def __init__(self, ptr: int, shape, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+        self._owner = owner
+
+
+def _planes(value, valid):
+    """(value_ptr, valid_ptr, stride_words) of a pair of [n, words] planes: torch tensors (device or pinned host), numpy
+    arrays, or None."""
+    if value is None:
+        return None, None, 0
+    if hasattr(value, "data_ptr"):
+        assert value.dim() == 2 and valid.dim() == 2 and value.stride(1) == 1 and valid.stride(0) == value.stride(0)
+        return value.data_ptr(), valid.data_ptr(), value.stride(0)
+    assert value.ndim == 2 and value.strides[1] == 8 and valid.strides[0] == value.strides[0]
+    return value.ctypes.data, valid.ctypes.data, value.strides[0] // 8
+
+
+class Comm:
+    """b2_comm: an NCCL communicator made by the C library (ncclGetUniqueId / ncclCommInitRank)."""
+
+    def __init__(self, n_ranks: int, rank: int, unique_id: bytes, device: int):
+        self._lib = _ffi.lib()
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(self._lib.b2_comm_init_rank(C.byref(h), n_ranks, rank, buf, device), "b2_comm_init_rank")
+        self._h = h
+        self.n_ranks, self.rank = n_ranks, rank
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(_ffi.lib().b2_comm_get_unique_id(buf), "b2_comm_get_unique_id")
+        return bytes(buf)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.b2_comm_free(self._h)
+            self._h = None
+
+
+class Batch:
+    """b2_batch: runs lane batches of one compiled netlist (see include/digilogic_b200.h)."""
+
+    OPT_SWEEP, OPT_TASK_ITERS, OPT_UNROLL, OPT_CTAS_PER_SM, OPT_AUTO_GATHER = 1, 2, 3, 4, 5
+
+    def __init__(self, sim: Simulator, inputs, outputs, tile_words: int, n_slots: int = 1, device: int | None = None,
+                 stream: int | None = None):
+        self._lib = _ffi.lib()
         self.inputs = np.ascontiguousarray(inputs, np.uint32)
         self.outputs = np.ascontiguousarray(outputs, np.uint32)
-        self.tile_words = int(tile_words)
-        self.max_steps = int(max_steps)
-        sim.set_lanes(self.tile_words * 64)
+        h = C.c_void_p()
+        _check(self._lib.b2_batch_new(sim._h, _p(self.inputs), self.inputs.size, _p(self.outputs), self.outputs.size,
+                                      int(tile_words), int(n_slots), C.byref(h)), "b2_batch_new")
+        self._h = h
+        self._comm = None
+        if device is not None:
+            _check(self._lib.b2_batch_set_device(self._h, device), "b2_batch_set_device")
+        if stream is not None:
+            _check(self._lib.b2_batch_set_stream(self._h, C.c_void_p(stream)), "b2_batch_set_stream")
 
-    # -- device-resident stimulus (generated on the GPU from the global lane-word index)
-    def run_generated(self, word_begin: int, n_words: int, seed: int, mode: int, out_value, out_valid,
-                      out_word0: int = 0, record_events=None) -> SimulationRunResult:
-        """out_value/out_valid: device tensors [n_outputs, >= out_word0 + n_words] (int64 storage)."""
-        assert n_words % self.tile_words == 0, "batch must be a whole number of tiles"
-        worst = SimulationRunResult.Ok
-        stride = out_value.stride(0)
-        base_v, base_m = out_value.data_ptr(), out_valid.data_ptr()
-        for w0, _ in plan_tiles(n_words, self.tile_words):
-            self.sim.fill_stimulus(self.inputs, seed, lane_word_base=word_begin + w0, mode=mode)
-            if record_events is not None:
-                record_events("start")
-            r = self.sim.run_sim_lanes_async(self.max_steps)
-            if record_events is not None:
-                record_events("end")
-            worst = max(worst, r)
-            off = (out_word0 + w0) * 8
-            self.sim.gather_wires_ptr(self.outputs, base_v + off, base_m + off, stride, device=True)
-        return worst
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.b2_batch_free(self._h)
+            self._h = None
 
-    # -- host stimulus through the C ABI (end-to-end path: H2D copies and D2H read-back included)
-    def run_host(self, in_value, in_valid, out_value, out_valid, n_words: int | None = None,
-                 dev_out_value=None, dev_out_valid=None) -> SimulationRunResult:
-        """in_*: host arrays [n_inputs, ring_words]; out_*: host arrays [n_outputs, ring_words] (numpy
-        views of pinned memory).  n_words lane-words are processed; if that is more than the host
-        arrays hold, the arrays are used as a ring (tile i reads/writes slot i mod ring).  The drives
-        of tile i+1 are uploaded while tile i settles, and the outputs of tile i are copied out
-        while tile i+1 settles (the engine's copy streams); the call returns after the last copy.
-        dev_out_*: optional device tensors [n_outputs, n_words] that also receive the output planes
-        (multi-GPU runs all-gather those with NCCL)."""
-        ring_words = in_value.shape[1]
-        n_words = ring_words if n_words is None else n_words
-        assert n_words % self.tile_words == 0 and ring_words % self.tile_words == 0
-        assert out_value.shape[1] == ring_words
-        worst = SimulationRunResult.Ok
-        in_stride, out_stride = in_value.strides[0] // 8, out_value.strides[0] // 8
-        tiles = plan_tiles(n_words, self.tile_words)
-
-        def upload(w0):
-            o = 8 * (w0 % ring_words)
-            self.sim.set_drives_lanes_ptr(self.inputs, in_value.ctypes.data + o, in_valid.ctypes.data + o, in_stride)
-
-        upload(tiles[0][0])
-        for i, (w0, _) in enumerate(tiles):
-            r = self.sim.run_sim_lanes_async(self.max_steps)
-            worst = max(worst, r)
-            if i + 1 < len(tiles):
-                upload(tiles[i + 1][0])
-            o = 8 * (w0 % ring_words)
-            self.sim.gather_wires_ptr(self.outputs, out_value.ctypes.data + o, out_valid.ctypes.data + o, out_stride,
-                                      device=False, async_=True)
-            if dev_out_value is not None:
-                self.sim.gather_wires_ptr(self.outputs, dev_out_value.data_ptr() + 8 * w0, dev_out_valid.data_ptr() + 8 * w0,
-                                          dev_out_value.stride(0), device=True)
-        self.sim.synchronize()
-        return worst
-
-
-class InterleavedRunner:
-    """K simulator replicas of one netlist on K CUDA streams, taking alternate lane tiles of a batch.
-
-    Small tiles keep a level's output rows in the 126 MB L2 until the next level reads them (a
-    third of the fan-in traffic never reaches HBM), but a single stream of small kernels is
-    launch-gap bound; with K tiles in flight the gaps and kernel tails of one tile are filled by
-    the others.  The replicas share nothing but the GPU: lanes are independent simulators."""
-
-    def __init__(self, make_sim, inputs, outputs, tile_words: int, n_streams: int, max_steps: int = 10_000, device=None,
-                 host_threads: bool = True):
-        import torch
-        from concurrent.futures import ThreadPoolExecutor
-        self.torch = torch
-        self.pool = ThreadPoolExecutor(max_workers=n_streams) if (host_threads and n_streams > 1) else None
-        self.streams = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
-        self.runners = []
-        for st in self.streams:
-            sim = make_sim()
-            sim.set_stream(st.cuda_stream)
-            self.runners.append(BatchRunner(sim, inputs, outputs, tile_words, max_steps))
-        self.tile_words = int(tile_words)
+    def set_option(self, option: int, value: int):
+        _check(self._lib.b2_batch_set_option(self._h, option, value), "b2_batch_set_option")
 
     @property
-    def sims(self):
-        return [r.sim for r in self.runners]
+    def info(self) -> _ffi.BatchInfo:
+        out = _ffi.BatchInfo()
+        _check(self._lib.b2_batch_get_info(self._h, C.byref(out)), "b2_batch_get_info")
+        return out
 
-    def run_generated(self, word_begin: int, n_words: int, seed: int, mode: int, out_value, out_valid,
-                      out_word0: int = 0) -> SimulationRunResult:
-        """Same contract as BatchRunner.run_generated; work is forked from and joined to the
-        caller's current stream, so events recorded there bracket it."""
-        assert n_words % self.tile_words == 0
-        main = self.torch.cuda.current_stream()
-        for st in self.streams:
-            st.wait_stream(main)
-        k = len(self.runners)
-        tiles = plan_tiles(n_words, self.tile_words)
+    def run_generated(self, seed: int, mode: int, word_begin: int, n_words: int, max_steps: int = 10_000, out_value=None,
+                      out_valid=None, out_ring_words: int = 0):
+        """Queues one settle of lanes [0, 64 n_words) with device-generated stimulus (global lane-word word_begin + w)."""
+        pv, pm, stride = _planes(out_value, out_valid)
+        _check(self._lib.b2_batch_run_generated(self._h, seed, mode, word_begin, n_words, max_steps, C.c_void_p(pv), C.c_void_p(pm),
+                                                stride, out_ring_words), "b2_batch_run_generated")
 
-        def drive(j):
-            # host_threads=True (default): one host thread per replica, so that the replicas' launches are issued
-            # in parallel (ctypes releases the GIL during C-ABI calls).  A/B on one box, tile 256 x 2 replicas:
-            # 1401 ms per step with threads, 1680 ms with one thread issuing both replicas' graphs.
-            w = SimulationRunResult.Ok
-            for w0, nw in tiles[j::k]:
-                w = max(w, self.runners[j].run_generated(word_begin + w0, nw, seed, mode, out_value, out_valid, out_word0 + w0))
-            return w
+    def run_planes(self, in_value, in_valid, n_words: int, max_steps: int = 10_000, out_value=None, out_valid=None,
+                   in_ring_words: int = 0, out_ring_words: int = 0):
+        """Queues one settle with stimulus planes [n_inputs, words] (device memory, or host memory read in place)."""
+        iv, im, istride = _planes(in_value, in_valid)
+        pv, pm, stride = _planes(out_value, out_valid)
+        _check(self._lib.b2_batch_run_planes(self._h, C.c_void_p(iv), C.c_void_p(im), istride, in_ring_words, n_words, max_steps,
+                                             C.c_void_p(pv), C.c_void_p(pm), stride, out_ring_words), "b2_batch_run_planes")
 
-        if self.pool is not None and k > 1:
-            worst = max(self.pool.map(drive, range(k)))
-        else:
-            worst = max(drive(j) for j in range(k))
-        for st in self.streams:
-            main.wait_stream(st)
-        return worst
+    def wait(self) -> SimulationRunResult:
+        worst = C.c_int()
+        _check(self._lib.b2_batch_wait(self._h, C.byref(worst)), "b2_batch_wait")
+        return SimulationRunResult(worst.value)
+
+    # ---- multi-GPU
+    def bind_comm(self, comm: Comm, words_local: int):
+        _check(self._lib.b2_batch_bind_comm(self._h, comm._h, words_local), "b2_batch_bind_comm")
+        self._comm = comm
+        self._words_local = words_local
+
+    def export_gather_handle(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(self._lib.b2_batch_export_gather_handle(self._h, buf), "b2_batch_export_gather_handle")
+        return bytes(buf)
+
+    def import_gather_handles(self, handles: list[bytes]):
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(self._lib.b2_batch_import_gather_handles(self._h, buf), "b2_batch_import_gather_handles")
+
+    def gather_outputs(self):
+        _check(self._lib.b2_batch_gather_outputs(self._h), "b2_batch_gather_outputs")
+
+    def gathered(self):
+        """(value, valid) device arrays [n_ranks, n_outputs, words_local] (int64 storage) of this rank's gathered planes."""
+        pv, pm = C.c_void_p(), C.c_void_p()
+        _check(self._lib.b2_batch_gathered(self._h, C.byref(pv), C.byref(pm)), "b2_batch_gathered")
+        shape = (self._comm.n_ranks, self.outputs.size, self._words_local)
+        return _DeviceArray(pv.value, shape, self), _DeviceArray(pm.value, shape, self)
 
 
-    def run_host(self, in_value, in_valid, out_value, out_valid, n_words: int | None = None,
-                 dev_out_value=None, dev_out_valid=None) -> SimulationRunResult:
-        """Same contract as BatchRunner.run_host (host planes in, host planes out, optional ring),
-        with the K replicas' upload -> settle -> read-back pipelines interleaved tile by tile."""
-        ring_words = in_value.shape[1]
-        n_words = ring_words if n_words is None else n_words
-        tw = self.tile_words
-        assert n_words % tw == 0 and ring_words % tw == 0 and out_value.shape[1] == ring_words
-        main = self.torch.cuda.current_stream()
-        for st in self.streams:
-            st.wait_stream(main)
-        in_stride, out_stride = in_value.strides[0] // 8, out_value.strides[0] // 8
-        tiles = plan_tiles(n_words, tw)
-        k = len(self.runners)
+def setup_comm(batch: Batch, words_local: int, device: int, map_peers: bool = True) -> Comm:
+    """Creates the C library's communicator over the ranks of an initialised torch.distributed group and binds it: the
+    NCCL unique id travels rank 0 -> all, the CUDA IPC handles of the gathered planes all -> all (object collectives)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    comm = Comm(world, rank, box[0], device)
+    batch.bind_comm(comm, words_local)
+    if map_peers and world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, batch.export_gather_handle())
+        batch.import_gather_handles(handles)
+    return comm
 
-        def drive(j):
-            # replica j's pipeline over its tiles: upload(next) while the current tile settles, read-back async
-            r = self.runners[j]
-            mine = tiles[j::k]
-            w = SimulationRunResult.Ok
 
-            def upload(w0):
-                o = 8 * (w0 % ring_words)
-                r.sim.set_drives_lanes_ptr(r.inputs, in_value.ctypes.data + o, in_valid.ctypes.data + o, in_stride)
+# ------------------------------------------------------------------------------------------------------------------
+# Harness helpers kept from round 1 (same call shapes; the work happens in the C library)
 
-            if mine:
-                upload(mine[0][0])
-            for i, (w0, _) in enumerate(mine):
-                w = max(w, r.sim.run_sim_lanes_async(r.max_steps))
-                if i + 1 < len(mine):
-                    upload(mine[i + 1][0])    # waits for this replica's drives to be consumed, not for its settle
-                o = 8 * (w0 % ring_words)
-                r.sim.gather_wires_ptr(r.outputs, out_value.ctypes.data + o, out_valid.ctypes.data + o, out_stride,
-                                       device=False, async_=True)
-                if dev_out_value is not None:
-                    r.sim.gather_wires_ptr(r.outputs, dev_out_value.data_ptr() + 8 * w0, dev_out_valid.data_ptr() + 8 * w0,
-                                           dev_out_value.stride(0), device=True)
-            r.sim.synchronize()
-            return w
+class BatchRunner:
+    """One slot, tile by tile: the round-1 call shape over b2_batch."""
 
-        if self.pool is not None and k > 1:
-            worst = max(self.pool.map(drive, range(k)))
-        else:
-            worst = max(drive(j) for j in range(k))
-        for st in self.streams:
-            main.wait_stream(st)
-        return worst
+    def __init__(self, sim: Simulator, inputs, outputs, tile_words: int, max_steps: int = 10_000, n_slots: int = 1,
+                 stream: int | None = None):
+        self.sim = sim
+        self.tile_words = int(tile_words)
+        self.max_steps = int(max_steps)
+        self.batch = Batch(sim, inputs, outputs, tile_words, n_slots, stream=stream)
+        self.inputs, self.outputs = self.batch.inputs, self.batch.outputs
+
+    def run_generated(self, word_begin: int, n_words: int, seed: int, mode: int, out_value, out_valid, out_word0: int = 0):
+        ov = out_value[:, out_word0:] if out_word0 else out_value
+        om = out_valid[:, out_word0:] if out_word0 else out_valid
+        self.batch.run_generated(seed, mode, word_begin, n_words, self.max_steps, ov, om)
+        return self.batch.wait()
+
+    def run_host(self, in_value, in_valid, out_value, out_valid, n_words: int | None = None):
+        ring = in_value.shape[1]
+        n_words = ring if n_words is None else n_words
+        self.batch.run_planes(in_value, in_valid, n_words, self.max_steps, out_value, out_valid,
+                              in_ring_words=ring if n_words > ring else 0, out_ring_words=ring if n_words > ring else 0)
+        return self.batch.wait()
 
 
 def gather_output_planes(local_value, local_valid, world_size: int):
-    """All-gather of the packed output planes: [n_out, words_local] per rank ->
-    [world_size, n_out, words_local] (rank-major = lane-word order, since ranks own contiguous
-    lane-word ranges).  NCCL on GPU tensors, gloo on CPU tensors."""
+    """torch.distributed all-gather of packed output planes [n_out, words_local] -> [world, n_out, words_local] (the
+    rank-major layout of the C library's gathered planes).  Used by the CPU (gloo) test of the sharding arithmetic and as
+    the independent check of b2_batch_gather_outputs on GPUs; the product path gathers inside the C library."""
     import torch
     import torch.distributed as dist
 
@@ -239,14 +255,13 @@ def gather_output_planes(local_value, local_valid, world_size: int):
         return local_value.unsqueeze(0), local_valid.unsqueeze(0)
     gv = torch.empty((world_size,) + tuple(local_value.shape), dtype=local_value.dtype, device=local_value.device)
     gm = torch.empty_like(gv)
-    # the output is the concatenation of the ranks' planes along dim 0 (the form gloo also accepts)
     dist.all_gather_into_tensor(gv.view(-1, local_value.shape[-1]), local_value.contiguous())
     dist.all_gather_into_tensor(gm.view(-1, local_valid.shape[-1]), local_valid.contiguous())
     return gv, gm
 
 
 def reduce_worst(worst: SimulationRunResult, device) -> SimulationRunResult:
-    """MAX all-reduce of the run result (conflict > max-steps > ok) over ranks."""
+    """MAX all-reduce of the run result (conflict > max-steps > ok) over ranks (torch.distributed; harness only)."""
     import torch
     import torch.distributed as dist
 
@@ -255,3 +270,7 @@ def reduce_worst(worst: SimulationRunResult, device) -> SimulationRunResult:
     t = torch.tensor([int(worst)], dtype=torch.int32, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return SimulationRunResult(int(t.item()))
+
+
+__all__ = ["Batch", "BatchRunner", "Comm", "B200Error", "auto_sweep_shape", "auto_tile_words", "choose_tile_words",
+           "gather_output_planes", "plan_tiles", "reduce_worst", "setup_comm", "shard_words"]

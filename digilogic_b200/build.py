@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdigilogic_b200.so")
-SOURCES = ["engine.cu", "netlist.cpp", "capi.cpp"]
-HEADERS = ["engine.hpp", "netlist.hpp", os.path.join("..", "..", "include", "digilogic_b200.h")]
+SOURCES = ["engine.cu", "batch.cu", "netlist.cpp", "capi.cpp"]
+HEADERS = ["engine.hpp", "netlist.hpp", "batch.hpp", "sweep.cuh", "device_ops.cuh", "capi_types.hpp", os.path.join("..", "..", "include", "digilogic_b200.h")]
 
 
 def _nvcc() -> str:
@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [
         _nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-        "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-o", LIB_PATH,
+        "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-o", LIB_PATH, "-ldl",
     ] + [os.path.join(CSRC, f) for f in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

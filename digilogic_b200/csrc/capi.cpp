@@ -10,12 +10,7 @@
 #include "engine.hpp"
 #include "netlist.hpp"
 
-struct b2_builder {
-    b2::Builder b;
-};
-struct b2_sim {
-    std::unique_ptr<b2::Engine> e;
-};
+#include "capi_types.hpp"
 
 #define GUARD_BEGIN try {
 #define GUARD_END(err)                        \
@@ -49,10 +44,7 @@ int b2_add_wires(b2_builder *b, uint8_t width, uint32_t n, uint32_t *out_first) 
     if (!b) return B2_ERR_NULL;
     if (width == 0) return B2_ERR_INVALID_ARG;
     GUARD_BEGIN
-    if (b->b.width.size() + (size_t)n > 0xFFFFFFFFull) return B2_ERR_OUT_OF_WIRES;
-    if (out_first) *out_first = (uint32_t)b->b.width.size();
-    b->b.width.insert(b->b.width.end(), n, width);
-    return B2_OK;
+    return b->b.add_wires(width, n, out_first);
     GUARD_END(B2_ERR_OUT_OF_MEMORY)
 }
 
@@ -136,6 +128,9 @@ int b2_add_gates2(b2_builder *b, const uint8_t *kinds, const uint32_t *in0, cons
     GUARD_BEGIN
     b->b.comps.reserve(b->b.comps.size() + n);
     b->b.inputs.reserve(b->b.inputs.size() + 2 * n);
+    // all or nothing: on the first invalid entry the builder is rolled back to its state before the call
+    const size_t comps0 = b->b.comps.size(), inputs0 = b->b.inputs.size();
+    const uint64_t gates0 = b->b.total_bit_gates, bin0 = b->b.total_bit_inputs;
     for (size_t i = 0; i < n; i++) {
         int rc;
         if (kinds[i] == B2_NOT) {
@@ -144,7 +139,13 @@ int b2_add_gates2(b2_builder *b, const uint8_t *kinds, const uint32_t *in0, cons
             const uint32_t in[2] = {in0[i], in1[i]};
             rc = b->b.add_gate(kinds[i], in, 2, out[i], nullptr);
         }
-        if (rc) return rc;
+        if (rc) {
+            b->b.comps.resize(comps0);
+            b->b.inputs.resize(inputs0);
+            b->b.total_bit_gates = gates0;
+            b->b.total_bit_inputs = bin0;
+            return rc;
+        }
     }
     return B2_OK;
     GUARD_END(B2_ERR_OUT_OF_MEMORY)
@@ -157,7 +158,9 @@ b2_sim *b2_build(b2_builder *b) {
         b2::compile(b->b, c);
         auto *s = new b2_sim();
         s->e.reset(new b2::Engine(std::move(c)));
+        const uint32_t sem = b->b.sem_flags;
         b->b = b2::Builder();  // std::mem::take(builder)
+        b->b.sem_flags = sem;  // the switches describe the engine's reading of gsim, not one netlist: they stay
         return s;
     } catch (...) {
         return nullptr;
@@ -165,6 +168,33 @@ b2_sim *b2_build(b2_builder *b) {
 }
 
 void b2_sim_free(b2_sim *s) { delete s; }
+
+b2_sim *b2_sim_clone(const b2_sim *s) {
+    if (!s) return nullptr;
+    try {
+        auto *c = new b2_sim();
+        c->e.reset(new b2::Engine(s->e->share()));
+        c->e->copy_options_from(*s->e);
+        return c;
+    } catch (...) {
+        return nullptr;
+    }
+}
+
+int b2_builder_set_option(b2_builder *b, int option, int64_t value) {
+    if (!b) return B2_ERR_NULL;
+    uint32_t bit;
+    switch (option) {
+        case B2_BOPT_MUX_Z_PASSTHROUGH: bit = b2::SEM_MUX_Z; break;
+        case B2_BOPT_INITIAL_UNDEFINED: bit = b2::SEM_INIT_X; break;
+        case B2_BOPT_BUFFER_Z_PASSTHROUGH: bit = b2::SEM_BUF_Z; break;
+        case B2_BOPT_COPY_Z_PASSTHROUGH: bit = b2::SEM_COPY_Z; break;
+        default: return B2_ERR_INVALID_ARG;
+    }
+    if (value) b->b.sem_flags |= bit;
+    else b->b.sem_flags &= ~bit;
+    return B2_OK;
+}
 
 // ------------------------------------------------------------------ simulator
 int b2_sim_get_info(const b2_sim *s, b2_sim_info *out) {

@@ -22,6 +22,7 @@
 
 #include "../../include/digilogic_b200.h"
 #include "engine.hpp"
+#include "device_ops.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -34,6 +35,7 @@ static std::atomic<uint64_t> g_launches{0};
 void set_last_error(const std::string &msg) { g_last_error = msg; }
 const char *get_last_error() { return g_last_error.c_str(); }
 uint64_t kernel_launches() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 #define CU_TRY(expr)                                                                                  \
     do {                                                                                              \
@@ -54,115 +56,6 @@ uint64_t kernel_launches() { return g_launches.load(); }
 #define CIN ((cudaStream_t)cin_stream_)
 #define COUT ((cudaStream_t)cout_stream_)
 #define EV(x) ((cudaEvent_t)(x))
-
-// ---------------------------------------------------------------------------- device helpers
-
-__device__ __forceinline__ ulonglong2 ld_stream(const uint64_t *p) {
-    ulonglong2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
-    return r;
-}
-// Coherent variant for code that may run inside the device-side loop, where rows written by other CTAs
-// earlier in the same launch are read back after a grid barrier: .nc data must be read-only for the launch, and
-// a weak ld with L1::no_allocate was observed to return a stale row there (an SM re-reading a row it had read
-// two applications earlier), so these loads are volatile — served from L2.
-__device__ __forceinline__ ulonglong2 ld_row(const uint64_t *p) {
-    ulonglong2 r;
-    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
-    return r;
-}
-// the same load, predicated off (result all-ones) when `skip`: no branch, no memory transaction
-__device__ __forceinline__ ulonglong2 ld_stream_unless(const uint64_t *p, bool skip) {
-    ulonglong2 r = make_ulonglong2(~0ull, ~0ull);
-    asm volatile(
-        "{ .reg .pred q; setp.eq.u32 q, %3, 0; @q ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2]; }"
-        : "+l"(r.x), "+l"(r.y)
-        : "l"(p), "r"((uint32_t)skip));
-    return r;
-}
-__device__ __forceinline__ void st_pair(uint64_t *p, ulonglong2 v) {
-    asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
-}
-
-// 4-state gate on one 64-lane word: k1 = known one, k0 = known zero.
-typedef unsigned long long u64;  // the element type of ulonglong2
-__device__ __forceinline__ void gate_word(uint32_t kind, u64 av, u64 am, u64 bv, u64 bm, u64 &rv, u64 &rm) {
-    u64 v, m;
-    switch (kind) {
-        case K_AND:
-        case K_NAND: {
-            const u64 k1 = (av & am) & (bv & bm), k0 = (~av & am) | (~bv & bm);
-            m = k0 | k1;
-            v = k1;
-        } break;
-        case K_OR:
-        case K_NOR: {
-            const u64 k1 = (av & am) | (bv & bm), k0 = (~av & am) & (~bv & bm);
-            m = k0 | k1;
-            v = k1;
-        } break;
-        case K_XOR:
-        case K_XNOR:
-            m = am & bm;
-            v = av ^ bv;
-            break;
-        case K_BUF: {  // a = data, b = enable.  enable 1: the data (High-Z reads X); 0: High-Z; Z/X: X
-            const u64 en1 = bv & bm;
-            rm = en1 & am;
-            rv = (en1 & (av | ~am)) | ~bm;
-            return;
-        }
-        case K_RAW:  // hidden raw copy (a register's clock one step ago): High-Z stays High-Z
-            rm = am;
-            rv = av;
-            return;
-        case K_COPY:  // one bit of a slice / merge: the input, High-Z read as X
-            rm = am;
-            rv = av | ~am;
-            return;
-        default:  // K_NOT (single input)
-            m = am;
-            v = av;
-            break;
-    }
-    if (kind >= K_NAND) v = ~v;
-    rv = v | ~m;  // not-valid lanes carry the canonical X = (1,0)
-    rm = m;
-}
-
-// One register bit (gsim add_register restated): rising edge = the clock was a valid 0 one step ago
-// (pc) and is a valid 1 now (c); enable 1 loads the data bit (High-Z reads X), enable 0 keeps, enable Z/X makes the stored
-// value Undefined.  The stored value is the register's own row (o); a row that is still High-Z has never been written and
-// stands for the initial Undefined.
-__device__ __forceinline__ void reg_word(u64 dv, u64 dm, u64 ev, u64 em, u64 cv, u64 cm, u64 pcv, u64 pcm, u64 ov, u64 om, u64 &rv,
-                                         u64 &rm) {
-    const u64 edge = pcm & ~pcv & cm & cv;
-    const u64 take = edge & ev & em, keep = ~edge | (edge & ~ev & em), undef = edge & ~em;
-    rm = (take & dm) | (keep & om);
-    rv = (take & (dv | ~dm)) | (keep & (ov | ~om)) | undef;
-}
-
-// Driver conflict between two operands of a wire: both not High-Z; with `lenient` (the A.6-2
-// alternative) two valid operands that agree do not conflict.
-__device__ __forceinline__ u64 conflict_of(u64 av, u64 am, u64 bv, u64 bm, int lenient) {
-    u64 c = (av | am) & (bv | bm);
-    if (lenient) c &= ~(am & bm & ~(av ^ bv));
-    return c;
-}
-
-__device__ __forceinline__ uint64_t lane_mask_of(uint32_t w, uint64_t n_lanes) {
-    const uint64_t lo = (uint64_t)w * 64;
-    if (lo + 64 <= n_lanes) return ~0ull;
-    if (lo >= n_lanes) return 0ull;
-    return (1ull << (n_lanes - lo)) - 1;
-}
-
-__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
-    uint64_t z = x + 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
 
 // ---------------------------------------------------------------------------- kernels
 //
@@ -186,6 +79,7 @@ struct Eval2Args {
     const uint8_t *chg_prev;          // unit delay: row -> changed in the previous application (nullptr: evaluate every gate)
     uint8_t *chg_cur;                 // unit delay: row -> changed in this application (the frontier of the next one)
     const uint32_t *all_valid;        // KV: 1 if every source row of this run is known valid (then every row is)
+    uint32_t sem = 0;                 // SemFlags of the netlist (SURVEY.md A.6-4..7 switches)
 };
 
 // Changed-row frontier write: with a whole warp on one gate, one ballot and one byte store.
@@ -281,17 +175,17 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
         ulonglong2 rv, rm;
         if (NIN == 3) {
             const uint32_t base = kind[u] >= K_NAND ? kind[u] - 3 : kind[u];  // fold with the positive op
-            gate_word(base, av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
-            gate_word(base, av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
-            gate_word(base, rv.x, rm.x, cv[u].x, cm[u].x, rv.x, rm.x);
-            gate_word(base, rv.y, rm.y, cv[u].y, cm[u].y, rv.y, rm.y);
+            gate_word(base, av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x, a.sem);
+            gate_word(base, av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y, a.sem);
+            gate_word(base, rv.x, rm.x, cv[u].x, cm[u].x, rv.x, rm.x, a.sem);
+            gate_word(base, rv.y, rm.y, cv[u].y, cm[u].y, rv.y, rm.y, a.sem);
             if (kind[u] >= K_NAND) {
                 rv.x = ~rv.x | ~rm.x;
                 rv.y = ~rv.y | ~rm.y;
             }
         } else {
-            gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
-            gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
+            gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x, a.sem);
+            gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y, a.sem);
         }
         bool ch = false;
         if (live[u] && act[u]) {
@@ -323,6 +217,10 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
 // of its class with one warp-aggregated atomic.  k_eval_list then evaluates exactly the listed gates with
 // a persistent grid, so an application in which little changes costs a few microseconds instead of a
 // sweep of CTAs over every gate.
+// Changed-row flags are written by other CTAs earlier in the same launch when the scan runs inside the device-side
+// loop: read them past L1 (volatile), like the rows themselves.
+__device__ __forceinline__ uint32_t ld_flag(const uint8_t *p) { return *(const volatile uint8_t *)p; }
+
 __device__ __forceinline__ void frontier_scan_body(const uint32_t *fan0, const uint32_t *fan1, const uint32_t *fan2, uint32_t n_g2,
                                                    uint32_t n_fast, uint32_t row_base, const uint8_t *kind, const uint8_t *chg_prev,
                                                    uint4 *list2, uint4 *list3, uint32_t *list_copy, uint32_t *counts, uint32_t tid,
@@ -337,10 +235,10 @@ __device__ __forceinline__ void frontier_scan_body(const uint32_t *fan0, const u
         if (!chg_prev) {
             act = true;  // flags not valid (first application after a reset): every gate is evaluated
         } else {
-            act = (chg_prev[e.y] | chg_prev[e.z]) != 0;
-            if (g >= n_g2) act |= chg_prev[e.w] != 0;
+            act = (ld_flag(chg_prev + e.y) | ld_flag(chg_prev + e.z)) != 0;
+            if (g >= n_g2) act |= ld_flag(chg_prev + e.w) != 0;
             // no fan-in changed but the gate's own row did: its value is final, only the other buffer's copy is stale
-            refresh = !act && chg_prev[row_base + g] != 0;
+            refresh = !act && ld_flag(chg_prev + row_base + g) != 0;
         }
     }
     const uint32_t lane = tid & 31, lt = (1u << lane) - 1;
@@ -447,17 +345,17 @@ __device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *
             ulonglong2 rv, rm;
             if (NIN == 3) {
                 const uint32_t base_kind = kind[u] >= K_NAND ? kind[u] - 3 : kind[u];
-                gate_word(base_kind, av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
-                gate_word(base_kind, av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
-                gate_word(base_kind, rv.x, rm.x, cv[u].x, cm[u].x, rv.x, rm.x);
-                gate_word(base_kind, rv.y, rm.y, cv[u].y, cm[u].y, rv.y, rm.y);
+                gate_word(base_kind, av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x, a.sem);
+                gate_word(base_kind, av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y, a.sem);
+                gate_word(base_kind, rv.x, rm.x, cv[u].x, cm[u].x, rv.x, rm.x, a.sem);
+                gate_word(base_kind, rv.y, rm.y, cv[u].y, cm[u].y, rv.y, rm.y, a.sem);
                 if (kind[u] >= K_NAND) {
                     rv.x = ~rv.x | ~rm.x;
                     rv.y = ~rv.y | ~rm.y;
                 }
             } else {
-                gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x);
-                gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y);
+                gate_word(kind[u], av[u].x, am[u].x, bv[u].x, bm[u].x, rv.x, rm.x, a.sem);
+                gate_word(kind[u], av[u].y, am[u].y, bv[u].y, bm[u].y, rv.y, rm.y, a.sem);
             }
             bool ch = false;
             if (live[u]) {
@@ -488,28 +386,6 @@ __global__ void __launch_bounds__(256, NIN == 3 ? 2 : 3) k_eval_list(const Eval2
     eval_list_body<NIN>(a, list, count, blockIdx.x, gridDim.x);
 }
 
-struct WideArgs {
-    const uint32_t *off, *in;
-    const uint8_t *kind, *nsel;
-    const uint64_t *in_val, *in_vld;
-    uint64_t *out_val, *out_vld;
-    uint64_t *changed;
-    uint32_t g_begin, g_end, row_base, stride, pairs, pair_blocks;
-    uint8_t *kv;  // nullable: rows whose valid plane is elided (read as all-ones); outputs are always stored
-    const uint8_t *chg_prev;  // unit-delay frontier, as in Eval2Args
-    uint8_t *chg_cur;
-    const uint32_t *all_valid;  // as in Eval2Args (nullable)
-};
-
-__device__ __forceinline__ ulonglong2 ld_valid(const WideArgs &a, uint32_t row, size_t col) {
-    if (a.kv && (*a.all_valid || a.kv[row])) return make_ulonglong2(~0ull, ~0ull);
-    return ld_row(a.in_vld + (size_t)row * a.stride + col);
-}
-
-// n-ary gates (left fold, inverted kinds invert once at the end) and multiplexer slices.
-template <bool JACOBI>
-__device__ __forceinline__ void eval_wide_gate(const WideArgs &a, uint32_t pb, uint32_t g);
-
 template <bool JACOBI>
 __device__ __forceinline__ void eval_wide_body(const WideArgs &a, uint32_t pb, uint32_t gb) {
     eval_wide_gate<JACOBI>(a, pb, a.g_begin + gb * blockDim.y + threadIdx.y);
@@ -522,114 +398,6 @@ __device__ __forceinline__ void eval_wide_list_body(WideArgs a, const uint32_t *
     const uint32_t pb = bid % a.pair_blocks, gbi = bid / a.pair_blocks, gbs = nblk / a.pair_blocks;
     a.chg_prev = nullptr;
     for (uint32_t i = gbi * blockDim.y + threadIdx.y; i < n; i += gbs * blockDim.y) eval_wide_gate<true>(a, pb, list[i]);
-}
-
-template <bool JACOBI>
-__device__ __forceinline__ void eval_wide_gate(const WideArgs &a, uint32_t pb, uint32_t g) {
-    const uint32_t pair = pb * blockDim.x + threadIdx.x;
-    if (pair >= a.pairs || g >= a.g_end) return;
-    const size_t col = (size_t)pair * 2;
-    const uint32_t b = a.off[g], e = a.off[g + 1];
-    const uint32_t kind = a.kind[g];
-    if (JACOBI && a.chg_prev) {
-        uint32_t act = a.chg_prev[a.row_base + g];
-        for (uint32_t i = b; i < e; i++) act |= a.chg_prev[a.in[i]];
-        if (!act) return;  // warp-uniform when a warp sits on one gate
-    }
-    ulonglong2 rv, rm;
-    if (kind == K_ADD || kind == K_SUB) {
-        // one bit of a + b or a - b: inputs a_0..a_{w-1}, b_0..b_{w-1}; any invalid input bit makes the result Undefined
-        const uint32_t w = (e - b) / 2, j = a.nsel[g];
-        const bool sub = kind == K_SUB;
-        ulonglong2 ok = make_ulonglong2(~0ull, ~0ull), carry = sub ? ok : make_ulonglong2(0, 0), sum = make_ulonglong2(0, 0);
-        for (uint32_t t = 0; t < w; t++) {
-            const ulonglong2 ma = ld_valid(a, a.in[b + t], col), mb = ld_valid(a, a.in[b + w + t], col);
-            ok.x &= ma.x & mb.x;
-            ok.y &= ma.y & mb.y;
-            if (t <= j) {
-                const ulonglong2 x = ld_row(a.in_val + (size_t)a.in[b + t] * a.stride + col);
-                ulonglong2 y = ld_row(a.in_val + (size_t)a.in[b + w + t] * a.stride + col);
-                if (sub) {
-                    y.x = ~y.x;
-                    y.y = ~y.y;
-                }
-                if (t == j) {
-                    sum.x = x.x ^ y.x ^ carry.x;
-                    sum.y = x.y ^ y.y ^ carry.y;
-                } else {
-                    carry.x = (x.x & y.x) | (carry.x & (x.x ^ y.x));
-                    carry.y = (x.y & y.y) | (carry.y & (x.y ^ y.y));
-                }
-            }
-        }
-        rm = ok;
-        rv.x = sum.x | ~ok.x;
-        rv.y = sum.y | ~ok.y;
-    } else if (kind == K_REG) {
-        const size_t rd = (size_t)a.in[b] * a.stride + col, re = (size_t)a.in[b + 1] * a.stride + col,
-                     rc = (size_t)a.in[b + 2] * a.stride + col, rp = (size_t)a.in[b + 3] * a.stride + col,
-                     ro = (size_t)(a.row_base + g) * a.stride + col;
-        const ulonglong2 dv = ld_row(a.in_val + rd), dm = ld_row(a.in_vld + rd), ev = ld_row(a.in_val + re), em = ld_row(a.in_vld + re),
-                         cv = ld_row(a.in_val + rc), cm = ld_row(a.in_vld + rc), pv = ld_row(a.in_val + rp), pm = ld_row(a.in_vld + rp),
-                         ov = ld_row(a.in_val + ro), om = ld_row(a.in_vld + ro);
-        reg_word(dv.x, dm.x, ev.x, em.x, cv.x, cm.x, pv.x, pm.x, ov.x, om.x, rv.x, rm.x);
-        reg_word(dv.y, dm.y, ev.y, em.y, cv.y, cm.y, pv.y, pm.y, ov.y, om.y, rv.y, rm.y);
-    } else if (kind == K_MUX) {
-        const uint32_t ns = a.nsel[g];
-        ulonglong2 allv = make_ulonglong2(~0ull, ~0ull);
-        for (uint32_t s = 0; s < ns; s++) {
-            const ulonglong2 m = ld_valid(a, a.in[b + s], col);
-            allv.x &= m.x;
-            allv.y &= m.y;
-        }
-        ulonglong2 pv = make_ulonglong2(0, 0), pm = make_ulonglong2(0, 0);
-        for (uint32_t j = 0; b + ns + j < e; j++) {
-            ulonglong2 match = make_ulonglong2(~0ull, ~0ull);
-            for (uint32_t s = 0; s < ns; s++) {
-                const ulonglong2 sv = ld_row(a.in_val + (size_t)a.in[b + s] * a.stride + col);
-                const uint64_t want = ((j >> s) & 1) ? ~0ull : 0ull;
-                match.x &= ~(sv.x ^ want);
-                match.y &= ~(sv.y ^ want);
-            }
-            const size_t r = (size_t)a.in[b + ns + j] * a.stride + col;
-            const ulonglong2 dv = ld_row(a.in_val + r), dm = ld_valid(a, a.in[b + ns + j], col);
-            pv.x |= match.x & dv.x;
-            pv.y |= match.y & dv.y;
-            pm.x |= match.x & dm.x;
-            pm.y |= match.y & dm.y;
-        }
-        rm.x = allv.x & pm.x;
-        rm.y = allv.y & pm.y;
-        rv.x = (allv.x & pv.x) | ~rm.x;  // Z on the selected input reads X; invalid select -> X
-        rv.y = (allv.y & pv.y) | ~rm.y;
-    } else {
-        const uint32_t base = kind >= K_NAND ? kind - 3 : kind;  // fold with the positive op
-        size_t r = (size_t)a.in[b] * a.stride + col;
-        rv = ld_row(a.in_val + r);
-        rm = ld_valid(a, a.in[b], col);
-        for (uint32_t i = b + 1; i < e; i++) {
-            r = (size_t)a.in[i] * a.stride + col;
-            const ulonglong2 xv = ld_row(a.in_val + r), xm = ld_valid(a, a.in[i], col);
-            gate_word(base, rv.x, rm.x, xv.x, xm.x, rv.x, rm.x);
-            gate_word(base, rv.y, rm.y, xv.y, xm.y, rv.y, rm.y);
-        }
-        if (kind >= K_NAND) {
-            rv.x = ~rv.x | ~rm.x;
-            rv.y = ~rv.y | ~rm.y;
-        }
-    }
-    const size_t o = (size_t)(a.row_base + g) * a.stride + col;
-    if (JACOBI) {
-        const ulonglong2 ov = ld_row(a.in_val + o), om = ld_row(a.in_vld + o);
-        const uint64_t dx = (rv.x ^ ov.x) | (rm.x ^ om.x), dy = (rv.y ^ ov.y) | (rm.y ^ om.y);
-        if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
-        if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
-        if (a.chg_cur && (dx | dy)) a.chg_cur[a.row_base + g] = 1;
-    }
-    st_pair(a.out_val + o, rv);
-    if (a.kv && *a.all_valid) return;  // valid fan-ins give a valid output: its plane stays elided
-    st_pair(a.out_vld + o, rm);
-    if (a.kv && pb == 0 && threadIdx.x == 0) a.kv[a.row_base + g] = 0;
 }
 
 template <bool JACOBI>
@@ -651,8 +419,8 @@ __device__ __forceinline__ void frontier_scan_wide_body(const uint32_t *off, con
         if (!chg_prev) {
             act = true;
         } else {
-            uint32_t any = chg_prev[row_base + g];
-            for (uint32_t i = off[g]; i < off[g + 1] && !any; i++) any |= chg_prev[in[i]];
+            uint32_t any = ld_flag(chg_prev + row_base + g);
+            for (uint32_t i = off[g]; i < off[g + 1] && !any; i++) any |= ld_flag(chg_prev + in[i]);
             act = any != 0;
         }
     }
@@ -790,7 +558,7 @@ __device__ __forceinline__ void resolve_body(const ResolveArgs &a, uint32_t pb, 
     if (!a.cold)
         for (uint32_t i = a.off[r]; i < a.off[r + 1]; i++) {
             const size_t o = (size_t)a.in[i] * a.stride + col;
-            const ulonglong2 ov = *(const ulonglong2 *)(a.b_val + o), om = *(const ulonglong2 *)(a.b_vld + o);
+            const ulonglong2 ov = ld_row(a.b_val + o), om = ld_row(a.b_vld + o);  // written by other CTAs earlier in this launch
             cx |= conflict_of(v.x, m.x, ov.x, om.x, a.lenient);
             cy |= conflict_of(v.y, m.y, ov.y, om.y, a.lenient);
             v.x |= ov.x; v.y |= ov.y;
@@ -798,7 +566,7 @@ __device__ __forceinline__ void resolve_body(const ResolveArgs &a, uint32_t pb, 
         }
     const size_t o = (size_t)(a.row_base + r) * a.stride + col;
     if (a.changed) {
-        const ulonglong2 pv = *(const ulonglong2 *)(a.a_val + o), pm = *(const ulonglong2 *)(a.a_vld + o);
+        const ulonglong2 pv = ld_row(a.a_val + o), pm = ld_row(a.a_vld + o);
         const uint64_t dx = (v.x ^ pv.x) | (m.x ^ pm.x), dy = (v.y ^ pv.y) | (m.y ^ pm.y);
         if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
         if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
@@ -1003,6 +771,7 @@ struct LoopArgs {
     uint64_t n_lanes, k0, last;
     uint64_t bail_row_words;  // hand back to the host loop when listed gates x row words exceeds this
     int32_t cur, chg_w, frontier_valid;
+    uint32_t sem;  // SemFlags of the netlist
 };
 
 __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
@@ -1051,6 +820,7 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
         {
             Eval2Args e{a.fan0, a.fan1, a.fan2, a.kind2, AV, AM, BV, BM, a.changed, 0, a.n_fast, a.n_src, a.stride, a.pairs,
                         a.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
+            e.sem = a.sem;
             if (a.n_g2) eval_list_body<2>(e, a.list2, counts, bid, nblk);
             if (a.n_fast > a.n_g2) eval_list_body<3>(e, a.list3, counts + 1, bid, nblk);
             copy_list_body(a.listc, counts + 2, AV, AM, BV, BM, a.stride, a.pairs, a.pair_blocks, bid, nblk);
@@ -1149,6 +919,7 @@ struct ResidentArgs {
     // small runs (the one-lane server path) also leave the bit-packed lane-0 snapshot get_wire_state reads (CTA 0 packs it)
     uint8_t *snap0, *snap1;
     uint32_t snap_bytes;
+    uint32_t sem;  // SemFlags of the netlist
 };
 
 __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g, const uint64_t *av, const uint64_t *am, uint32_t wpc,
@@ -1185,7 +956,7 @@ __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g
             pm |= match & am[r];
         }
         rm = allv & pm;
-        rv = (allv & pv) | ~rm;
+        rv = (allv & pv) | ((a.sem & SEM_MUX_Z) ? ~allv : ~rm);  // A.6-4: High-Z on the selected input reads X, or passes through
     } else {
         const uint32_t base = kind >= K_NAND ? kind - 3 : kind;
         size_t r = (size_t)a.win[b] * wpc + j;
@@ -1193,7 +964,7 @@ __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g
         rm = am[r];
         for (uint32_t i = b + 1; i < e; i++) {
             r = (size_t)a.win[i] * wpc + j;
-            gate_word(base, rv, rm, av[r], am[r], rv, rm);
+            gate_word(base, rv, rm, av[r], am[r], rv, rm, a.sem);
         }
         if (kind >= K_NAND) rv = ~rv | ~rm;
     }
@@ -1248,13 +1019,13 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
                 if (gi < n2) {
                     const uint32_t g = lv.g2_begin + gi;
                     const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j;
-                    gate_word(a.kind2[g], AV[r0], AM[r0], AV[r1], AM[r1], rv, rm);
+                    gate_word(a.kind2[g], AV[r0], AM[r0], AV[r1], AM[r1], rv, rm, a.sem);
                     row = a.n_src + g;
                 } else if (gi < n2 + n3) {
                     const uint32_t g = lv.g3_begin + (gi - n2), kind = a.kind2[g], base = kind >= K_NAND ? kind - 3 : kind;
                     const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j, r2 = (size_t)a.fan2[g] * wpc + j;
-                    gate_word(base, AV[r0], AM[r0], AV[r1], AM[r1], rv, rm);
-                    gate_word(base, rv, rm, AV[r2], AM[r2], rv, rm);
+                    gate_word(base, AV[r0], AM[r0], AV[r1], AM[r1], rv, rm, a.sem);
+                    gate_word(base, rv, rm, AV[r2], AM[r2], rv, rm, a.sem);
                     if (kind >= K_NAND) rv = ~rv | ~rm;
                     row = a.n_src + g;
                 } else {
@@ -1325,13 +1096,13 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
                 } else if (row < a.n_src + a.n_g2) {
                     const uint32_t g = row - a.n_src;
                     const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j;
-                    gate_word(a.kind2[g], AV[r0], AM[r0], AV[r1], AM[r1], rv, rm);
+                    gate_word(a.kind2[g], AV[r0], AM[r0], AV[r1], AM[r1], rv, rm, a.sem);
                     counts = a.kind2[g] != K_RAW;  // a register's clock history is internal state: it keeps no lane alive
                 } else if (row < a.n_src + a.n_g2 + a.n_g3) {
                     const uint32_t g = row - a.n_src, kind = a.kind2[g], base = kind >= K_NAND ? kind - 3 : kind;
                     const size_t r0 = (size_t)a.fan0[g] * wpc + j, r1 = (size_t)a.fan1[g] * wpc + j, r2 = (size_t)a.fan2[g] * wpc + j;
-                    gate_word(base, AV[r0], AM[r0], AV[r1], AM[r1], rv, rm);
-                    gate_word(base, rv, rm, AV[r2], AM[r2], rv, rm);
+                    gate_word(base, AV[r0], AM[r0], AV[r1], AM[r1], rv, rm, a.sem);
+                    gate_word(base, rv, rm, AV[r2], AM[r2], rv, rm, a.sem);
                     if (kind >= K_NAND) rv = ~rv | ~rm;
                 } else {
                     wide_gate_word(a, row - a.n_src - a.n_g2 - a.n_g3, AV, AM, wpc, j, rv, rm);
@@ -1437,40 +1208,91 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
 
 // ---------------------------------------------------------------------------- Engine: setup
 
-Engine::Engine(Compiled &&net) : net_(std::move(net)) {}
+Engine::Engine(Compiled &&net) : share_(std::make_shared<NetShare>(std::move(net))), net_(share_->net) {}
+Engine::Engine(std::shared_ptr<NetShare> share) : share_(std::move(share)), net_(share_->net) {}
 
+void Engine::copy_options_from(const Engine &o) {
+    device_ = device_ready_ ? device_ : o.device_;
+    use_resident_ = o.use_resident_;
+    opt_elision_ = o.opt_elision_;
+    opt_graph_ = o.opt_graph_;
+    opt_frontier_ = o.opt_frontier_;
+    opt_device_loop_ = o.opt_device_loop_;
+    opt_lenient_ = o.opt_lenient_;
+    opt_budget_inclusive_ = o.opt_budget_inclusive_;
+    opt_u_ = o.opt_u_;
+    opt_period2_ = o.opt_period2_;
+    opt_flags_ = o.opt_flags_;
+}
+
+DeviceNet::~DeviceNet() {
+    if (device < 0) return;
+    cudaSetDevice(device);
+    cudaFree(fan0);
+    cudaFree(fan1);
+    cudaFree(fan2);
+    cudaFree(kind2);
+    cudaFree(wide_off);
+    cudaFree(wide_in);
+    cudaFree(wide_kind);
+    cudaFree(wide_nsel);
+    cudaFree(res_off);
+    cudaFree(res_in);
+    cudaFree(levels);
+}
+
+template <typename Tv>
+static int upload(Tv **dst, const std::vector<Tv> &src) {
+    const size_t n = src.size() ? src.size() : 1;
+    CU_TRY(cudaMalloc((void **)dst, n * sizeof(Tv)));
+    if (src.size()) CU_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(Tv), cudaMemcpyHostToDevice));
+    return B2_OK;
+}
+
+std::shared_ptr<DeviceNet> NetShare::acquire(int device, int &rc) {
+    std::lock_guard<std::mutex> lock(m);
+    rc = B2_OK;
+    auto it = on_device.find(device);
+    if (it != on_device.end())
+        if (auto sp = it->second.lock()) return sp;
+    auto d = std::make_shared<DeviceNet>();
+    d->device = device;  // from here on the destructor frees whatever was allocated
+    if ((rc = upload(&d->fan0, net.fan0)) || (rc = upload(&d->fan1, net.fan1)) || (rc = upload(&d->fan2, net.fan2)) ||
+        (rc = upload(&d->kind2, net.kind2)) || (rc = upload(&d->wide_off, net.wide_off)) || (rc = upload(&d->wide_in, net.wide_in)) ||
+        (rc = upload(&d->wide_kind, net.wide_kind)) || (rc = upload(&d->wide_nsel, net.wide_nsel)) ||
+        (rc = upload(&d->res_off, net.res_off)) || (rc = upload(&d->res_in, net.res_in)) || (rc = upload(&d->levels, net.levels)))
+        return nullptr;
+    on_device[device] = d;
+    return d;
+}
+
+// Frees whatever was allocated, whether or not ensure_device() ran to its end (a failure midway leaves
+// device_ready_ false with some of the per-engine objects alive).
 Engine::~Engine() {
-    if (device_ready_) {
-        cudaSetDevice(device_);
-        cudaStreamSynchronize(ST);
-        if (cin_stream_) cudaStreamSynchronize(CIN);
-        if (cout_stream_) cudaStreamSynchronize(COUT);
-        free_store();
-        cudaFree(d_fan0_);
-        cudaFree(d_fan1_);
-        cudaFree(d_fan2_);
-        cudaFree(d_kind2_);
-        cudaFree(d_wide_off_);
-        cudaFree(d_wide_in_);
-        cudaFree(d_wide_kind_);
-        cudaFree(d_wide_nsel_);
-        cudaFree(d_res_off_);
-        cudaFree(d_res_in_);
-        cudaFree(d_res_xslot_);
-        cudaFree(d_levels_);
-        cudaFree(d_flags_);
-        cudaFree(d_pend_);
-        cudaFree(d_loop_result_);
-        if (h_loop_result_) cudaFreeHost(h_loop_result_);
-        if (h_flags_) cudaFreeHost(h_flags_);
-        if (own_stream_ && stream_) cudaStreamDestroy(ST);
-        if (cin_stream_) cudaStreamDestroy(CIN);
-        if (cout_stream_) cudaStreamDestroy(COUT);
-        for (void *e : {ev_drive_consumed_, ev_drives_ready_, ev_gathered_, ev_out_free_})
-            if (e) cudaEventDestroy(EV(e));
-        for (void *e : ev_flags_)
-            if (e) cudaEventDestroy(EV(e));
+    if (device_ < 0) return;
+    if (cudaSetDevice(device_) != cudaSuccess) {
+        cudaGetLastError();
+        return;
     }
+    if (stream_set_) cudaStreamSynchronize(ST);
+    if (cin_stream_) cudaStreamSynchronize(CIN);
+    if (cout_stream_) cudaStreamSynchronize(COUT);
+    free_store();
+    dnet_.reset();
+    cudaFree(d_res_xslot_);
+    cudaFree(d_flags_);
+    cudaFree(d_pend_);
+    cudaFree(d_loop_result_);
+    if (h_loop_result_) cudaFreeHost(h_loop_result_);
+    if (h_flags_) cudaFreeHost(h_flags_);
+    if (own_stream_ && stream_) cudaStreamDestroy(ST);
+    if (cin_stream_) cudaStreamDestroy(CIN);
+    if (cout_stream_) cudaStreamDestroy(COUT);
+    for (void *e : {ev_drive_consumed_, ev_drives_ready_, ev_gathered_, ev_out_free_})
+        if (e) cudaEventDestroy(EV(e));
+    for (void *e : ev_flags_)
+        if (e) cudaEventDestroy(EV(e));
+    cudaGetLastError();
 }
 
 void Engine::free_store() {
@@ -1554,14 +1376,6 @@ int Engine::set_stream(void *stream) {
     return B2_OK;
 }
 
-template <typename Tv>
-static int upload(Tv **dst, const std::vector<Tv> &src) {
-    const size_t n = src.size() ? src.size() : 1;
-    CU_TRY(cudaMalloc((void **)dst, n * sizeof(Tv)));
-    if (src.size()) CU_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(Tv), cudaMemcpyHostToDevice));
-    return B2_OK;
-}
-
 int Engine::ensure_device() {
     if (device_ready_) {
         CU_TRY(cudaSetDevice(device_));
@@ -1594,8 +1408,8 @@ int Engine::ensure_device() {
         CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_unit_delay_loop, 256, 0));
         loop_ctas_ = coop ? (uint32_t)(std::min(occ, 2) * sm_count_) : 0;
-        CU_TRY(cudaMalloc((void **)&d_loop_result_, sizeof(LoopResult) + 8 * sizeof(uint32_t)));
-        CU_TRY(cudaMallocHost((void **)&h_loop_result_, sizeof(LoopResult)));
+        if (!d_loop_result_) CU_TRY(cudaMalloc((void **)&d_loop_result_, sizeof(LoopResult) + 8 * sizeof(uint32_t)));
+        if (!h_loop_result_) CU_TRY(cudaMallocHost((void **)&h_loop_result_, sizeof(LoopResult)));
     }
     // the kernels are built for sm_100a only: fail loudly on anything else
     cudaFuncAttributes fa;
@@ -1613,39 +1427,39 @@ int Engine::ensure_device() {
         stream_set_ = true;
     }
     int rc;
-    if ((rc = upload(&d_fan0_, net_.fan0))) return rc;
-    if ((rc = upload(&d_fan1_, net_.fan1))) return rc;
-    if ((rc = upload(&d_fan2_, net_.fan2))) return rc;
-    if ((rc = upload(&d_kind2_, net_.kind2))) return rc;
-    if ((rc = upload(&d_wide_off_, net_.wide_off))) return rc;
-    if ((rc = upload(&d_wide_in_, net_.wide_in))) return rc;
-    if ((rc = upload(&d_wide_kind_, net_.wide_kind))) return rc;
-    if ((rc = upload(&d_wide_nsel_, net_.wide_nsel))) return rc;
-    if ((rc = upload(&d_res_off_, net_.res_off))) return rc;
-    if ((rc = upload(&d_res_in_, net_.res_in))) return rc;
-    res_xslot_.assign(net_.n_res(), -1);
-    if ((rc = upload(&d_res_xslot_, res_xslot_))) return rc;
-    if ((rc = upload(&d_levels_, net_.levels))) return rc;
-    res_xslot_dirty_ = false;
-    CU_TRY(cudaMalloc((void **)&d_flags_, 8 * sizeof(RunFlags)));
+    if (!dnet_) {  // one copy of the netlist per device, shared with every replica of this build
+        dnet_ = share_->acquire(device_, rc);
+        if (!dnet_) return rc;
+        d_fan0_ = dnet_->fan0; d_fan1_ = dnet_->fan1; d_fan2_ = dnet_->fan2; d_kind2_ = dnet_->kind2;
+        d_wide_off_ = dnet_->wide_off; d_wide_in_ = dnet_->wide_in; d_wide_kind_ = dnet_->wide_kind; d_wide_nsel_ = dnet_->wide_nsel;
+        d_res_off_ = dnet_->res_off; d_res_in_ = dnet_->res_in; d_levels_ = dnet_->levels;
+    }
+    // a retry after a failure midway finds the earlier objects and keeps them
+    if (!d_res_xslot_) {
+        res_xslot_.assign(net_.n_res(), -1);
+        if ((rc = upload(&d_res_xslot_, res_xslot_))) return rc;
+        res_xslot_dirty_ = false;
+    }
+    if (!d_flags_) CU_TRY(cudaMalloc((void **)&d_flags_, 8 * sizeof(RunFlags)));
     CU_TRY(cudaMemset(d_flags_, 0, 8 * sizeof(RunFlags)));
-    CU_TRY(cudaMallocHost((void **)&h_flags_, 8 * sizeof(RunFlags)));
+    if (!h_flags_) CU_TRY(cudaMallocHost((void **)&h_flags_, 8 * sizeof(RunFlags)));
     for (int i = 0; i < 8; i++) {
+        if (ev_flags_[i]) continue;
         cudaEvent_t ev;
         CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         ev_flags_[i] = ev;
     }
-    {
-        cudaStream_t a, b;
+    for (void **st : {&cin_stream_, &cout_stream_}) {
+        if (*st) continue;
+        cudaStream_t a;
         CU_TRY(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
-        CU_TRY(cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking));
-        cin_stream_ = a;
-        cout_stream_ = b;
-        for (void **e : {&ev_drive_consumed_, &ev_drives_ready_, &ev_gathered_, &ev_out_free_}) {
-            cudaEvent_t ev;
-            CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            *e = ev;
-        }
+        *st = a;
+    }
+    for (void **e : {&ev_drive_consumed_, &ev_drives_ready_, &ev_gathered_, &ev_out_free_}) {
+        if (*e) continue;
+        cudaEvent_t ev;
+        CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        *e = ev;
     }
     device_ready_ = true;
     return B2_OK;
@@ -1728,10 +1542,19 @@ int Engine::set_lanes(uint64_t n_lanes) {
         T_ = stride_ = 0;
         return rc;
     }
-    CU_TRY(cudaMalloc((void **)&d_kv_, net_.n_rows ? net_.n_rows : 1));
-    CU_TRY(cudaMemsetAsync(d_kv_, 0, net_.n_rows ? net_.n_rows : 1, ST));
-    CU_TRY(cudaMalloc((void **)&d_all_valid_, 4));
-    CU_TRY(cudaMemsetAsync(d_all_valid_, 0, 4, ST));
+    auto alloc_flags = [&]() -> int {
+        CU_TRY(cudaMalloc((void **)&d_kv_, net_.n_rows ? net_.n_rows : 1));
+        CU_TRY(cudaMemsetAsync(d_kv_, 0, net_.n_rows ? net_.n_rows : 1, ST));
+        CU_TRY(cudaMalloc((void **)&d_all_valid_, 4));
+        CU_TRY(cudaMemsetAsync(d_all_valid_, 0, 4, ST));
+        return B2_OK;
+    };
+    if ((rc = alloc_flags())) {  // unwind: no half-built store stays behind
+        free_store();
+        n_lanes_ = 0;
+        T_ = stride_ = 0;
+        return rc;
+    }
     store_bytes_ += net_.n_rows;
     cur_ = 0;
     cold_ = true;
@@ -1808,20 +1631,31 @@ int Engine::drive_target(uint32_t bitnet, uint64_t **val, uint64_t **vld) {
         if (slot >= extra_cap_) {
             const uint32_t cap = extra_cap_ ? extra_cap_ * 2 : 64;
             uint64_t *nv = nullptr, *nm = nullptr;
-            CU_TRY(cudaMalloc((void **)&nv, (size_t)cap * stride_ * 8));
-            CU_TRY(cudaMalloc((void **)&nm, (size_t)cap * stride_ * 8));
-            CU_TRY(cudaMemsetAsync(nv, 0, (size_t)cap * stride_ * 8, ST));
-            CU_TRY(cudaMemsetAsync(nm, 0, (size_t)cap * stride_ * 8, ST));
-            if (extra_cap_) {
-                CU_TRY(cudaMemcpyAsync(nv, xdrv_val_, (size_t)extra_cap_ * stride_ * 8, cudaMemcpyDeviceToDevice, ST));
-                CU_TRY(cudaMemcpyAsync(nm, xdrv_vld_, (size_t)extra_cap_ * stride_ * 8, cudaMemcpyDeviceToDevice, ST));
+            uint32_t *nr = nullptr;
+            auto grow = [&]() -> int {
+                CU_TRY(cudaMalloc((void **)&nv, (size_t)cap * stride_ * 8));
+                CU_TRY(cudaMalloc((void **)&nm, (size_t)cap * stride_ * 8));
+                CU_TRY(cudaMalloc((void **)&nr, (size_t)cap * 4));
+                CU_TRY(cudaMemsetAsync(nv, 0, (size_t)cap * stride_ * 8, ST));
+                CU_TRY(cudaMemsetAsync(nm, 0, (size_t)cap * stride_ * 8, ST));
+                if (extra_cap_) {
+                    CU_TRY(cudaMemcpyAsync(nv, xdrv_val_, (size_t)extra_cap_ * stride_ * 8, cudaMemcpyDeviceToDevice, ST));
+                    CU_TRY(cudaMemcpyAsync(nm, xdrv_vld_, (size_t)extra_cap_ * stride_ * 8, cudaMemcpyDeviceToDevice, ST));
+                }
+                CU_TRY(cudaStreamSynchronize(ST));
+                return B2_OK;
+            };
+            if (int grc = grow()) {  // the old store stays as it was
+                cudaFree(nv);
+                cudaFree(nm);
+                cudaFree(nr);
+                return grc;
             }
-            CU_TRY(cudaStreamSynchronize(ST));
             cudaFree(xdrv_val_);
             cudaFree(xdrv_vld_);
             cudaFree(d_extra_rows_);
-            d_extra_rows_ = nullptr;
-            CU_TRY(cudaMalloc((void **)&d_extra_rows_, (size_t)cap * 4));
+            d_extra_rows_ = nr;
+            extra_rows_dirty_ = true;
             xdrv_val_ = nv;
             xdrv_vld_ = nm;
             ptrs_key_ = 0;
@@ -1994,6 +1828,14 @@ int Engine::upload_rows(const uint32_t *wires, uint32_t n, bool drive_rows) {
     for (uint32_t i = 0; i < n; i++)
         if (wires[i] >= net_.n_wires()) return B2_ERR_INVALID_WIRE_ID;
     const uint64_t key = hash_wires(wires, n);
+    // a hash hit counts only if the cached list is the same list (two lists can share a hash)
+    std::vector<uint32_t> &cached = drive_rows ? ptrs_wires_ : rows_wires_;
+    const bool same = cached.size() == n && (n == 0 || std::memcmp(cached.data(), wires, (size_t)n * 4) == 0);
+    if (!same) {
+        if (drive_rows) ptrs_key_ = 0;
+        else rows_key_ = 0;
+        cached.assign(wires, wires + n);
+    }
     if (!drive_rows) {
         if (rows_key_ == key) return B2_OK;
         std::vector<uint32_t> rows(n);
@@ -2031,8 +1873,9 @@ int Engine::set_drives_lanes(const uint32_t *wires, uint32_t n, const uint64_t *
     // copy-in stream: wait until the main stream has consumed the previous drives (early in the
     // previous settle), then H2D + scatter while that settle is still running
     CU_TRY(cudaStreamWaitEvent(CIN, EV(ev_drive_consumed_), 0));
-    CU_TRY(cudaMemcpy2DAsync(stage_val_[0], (size_t)T_ * 8, value, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyHostToDevice, CIN));
-    CU_TRY(cudaMemcpy2DAsync(stage_vld_[0], (size_t)T_ * 8, valid, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyHostToDevice, CIN));
+    // (the planes may also be device memory: the batch runner passes either)
+    CU_TRY(cudaMemcpy2DAsync(stage_val_[0], (size_t)T_ * 8, value, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyDefault, CIN));
+    CU_TRY(cudaMemcpy2DAsync(stage_vld_[0], (size_t)T_ * 8, valid, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyDefault, CIN));
     const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
     uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
     dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
@@ -2144,6 +1987,7 @@ int Engine::run_levelised(bool async) {
             if (lv.g2_end > lv.g2_begin) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
                             sh.pair_blocks, d_kv_, nullptr, nullptr, d_all_valid_};
+                a.sem = net_.sem_flags;
                 // U gates per thread: 4 when the level still fills the machine several times over, else 2
                 // (more, smaller CTAs: a level of a small tile is only a wave or two of work)
                 const uint32_t n_g = lv.g2_end - lv.g2_begin;
@@ -2167,6 +2011,7 @@ int Engine::run_levelised(bool async) {
             if (lv.g3_end > lv.g3_begin) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, V, M, V, M, nullptr, lv.g3_begin, lv.g3_end, net_.n_src, stride_, pairs,
                             sh.pair_blocks, d_kv_, nullptr, nullptr, d_all_valid_};
+                a.sem = net_.sem_flags;
                 const uint32_t per = sh.block.y * 2;
                 const uint32_t gb = (lv.g3_end - lv.g3_begin + per - 1) / per;
                 if (kv)
@@ -2178,6 +2023,7 @@ int Engine::run_levelised(bool async) {
             if (lv.wide_end > lv.wide_begin) {
                 WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, V, M, V, M, nullptr, lv.wide_begin, lv.wide_end,
                            net_.n_src + net_.n_fast(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr, nullptr, nullptr, d_all_valid_};
+                a.sem = net_.sem_flags;
                 const uint32_t gb = (lv.wide_end - lv.wide_begin + sh.block.y - 1) / sh.block.y;
                 k_eval_wide<false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
                 nodes++;
@@ -2260,6 +2106,8 @@ int Engine::run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &res
     la.stride = stride_; la.pairs = pairs; la.pair_blocks = sh.pair_blocks; la.rowchg_bytes = (uint32_t)rowchg_bytes();
     la.n_lanes = n_lanes_; la.k0 = k; la.last = last;
     la.bail_row_words = 4 * kLoopEntryRowWords;
+    la.sem = net_.sem_flags;
+    la.wide.sem = net_.sem_flags;
     la.cur = cur_; la.chg_w = chg_w_; la.frontier_valid = frontier_valid_ ? 1 : 0;
     void *params[] = {&la};
     const uint32_t grid = sh.pair_blocks * (loop_ctas_ / sh.pair_blocks);
@@ -2414,6 +2262,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
             if (net_.n_g2()) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
                             sh.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
+                a.sem = net_.sem_flags;
                 const uint32_t gbs = std::min<uint32_t>((net_.n_g2() + per - 1) / per, gbs_max);
                 k_eval_list<2><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[0], act_counts);
                 LAUNCHED();
@@ -2422,6 +2271,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
             if (net_.n_g3()) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, net_.n_g2(), net_.n_fast(), net_.n_src, stride_,
                             pairs, sh.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
+                a.sem = net_.sem_flags;
                 const uint32_t gbs = std::min<uint32_t>((net_.n_g3() + per - 1) / per, gbs_max);
                 k_eval_list<3><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[1], act_counts + 1);
                 LAUNCHED();
@@ -2437,6 +2287,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
             if (net_.n_g2()) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
                             sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
+                a.sem = net_.sem_flags;
                 const uint32_t per = sh.block.y * EVAL2_U;
                 const uint32_t gb = (net_.n_g2() + per - 1) / per;
                 k_eval2<EVAL2_U, true, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
@@ -2445,6 +2296,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
             if (net_.n_g3()) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, net_.n_g2(), net_.n_fast(), net_.n_src, stride_,
                             pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
+                a.sem = net_.sem_flags;
                 const uint32_t per = sh.block.y * 2;
                 const uint32_t gb = (net_.n_g3() + per - 1) / per;
                 k_eval2<2, true, false, 3><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
@@ -2454,6 +2306,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
         if (net_.n_wide()) {
             WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, AV, AM, BV, BM, d_changed_, 0, net_.n_wide(),
                        net_.n_src + net_.n_fast(), stride_, pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
+            a.sem = net_.sem_flags;
             if (chg_prev) {  // event-driven: list the wide gates with a changed input, evaluate the list
                 k_frontier_scan_wide<<<(net_.n_wide() + 255) / 256, 256, 0, ST>>>(d_wide_off_, d_wide_in_, net_.n_wide(),
                                                                                   net_.n_src + net_.n_fast(), chg_prev, d_act_list_[3],
@@ -2567,6 +2420,7 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
     a.n_levels = (uint32_t)net_.levels.size();
     a.levelised = levelised ? 1 : 0;
     a.lenient = opt_lenient_ ? 1 : 0;
+    a.sem = net_.sem_flags;
     const size_t smem = ((size_t)net_.n_rows * wpc * 4 + (size_t)wpc * 5) * 8;
     if (!resident_attr_set_) {
         CU_TRY(cudaFuncSetAttribute(k_resident_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kResidentSmem + 4096)));
@@ -2714,6 +2568,13 @@ int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uin
     CU_TRY(cudaMemcpy2DAsync(valid, dst_stride * 8, stage_vld_[1], (size_t)T_ * 8, (size_t)T_ * 8, n, cudaMemcpyDeviceToHost, COUT));
     CU_TRY(cudaEventRecord(EV(ev_out_free_), COUT));
     if (!async) CU_TRY(cudaStreamSynchronize(COUT));
+    return B2_OK;
+}
+
+// The main stream waits for the last asynchronous read-back (gather_wires(..., async)) of this simulator.
+int Engine::join_copies() {
+    if (!device_ready_) return B2_OK;
+    CU_TRY(cudaStreamWaitEvent(ST, EV(ev_out_free_), 0));
     return B2_OK;
 }
 

@@ -4,6 +4,9 @@
 // crates/digilogic_gsim/src/lib.rs:209-230 (set_wire_drive, run_sim, get_wire_state).
 #pragma once
 #include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -23,14 +26,40 @@ struct RunFlags {  // written by the status kernel, read by the host after each 
 
 struct LoopResult;
 
+// The compiled netlist on one device: index and kind arrays the kernels stream.  Read-only after the upload
+// and shared by every simulator replica built from one b2_build (b2_sim_clone, b2_batch).
+struct DeviceNet {
+    int device = -1;
+    uint32_t *fan0 = nullptr, *fan1 = nullptr, *fan2 = nullptr, *wide_off = nullptr, *wide_in = nullptr;
+    uint8_t *kind2 = nullptr, *wide_kind = nullptr, *wide_nsel = nullptr;
+    uint32_t *res_off = nullptr, *res_in = nullptr;
+    Level *levels = nullptr;
+    ~DeviceNet();
+};
+
+// One compiled netlist (host arrays) and its per-device copies.
+struct NetShare {
+    explicit NetShare(Compiled &&c) : net(std::move(c)) {}
+    const Compiled net;
+    std::mutex m;
+    std::map<int, std::weak_ptr<DeviceNet>> on_device;
+    // the device copy for `device` (current CUDA device must be `device`); uploaded on first use; rc = b2_status
+    std::shared_ptr<DeviceNet> acquire(int device, int &rc);
+};
+
 class Engine {
    public:
     explicit Engine(Compiled &&net);
+    explicit Engine(std::shared_ptr<NetShare> share);  // a replica: shares the netlist and its device copy
     ~Engine();
     Engine(const Engine &) = delete;
     Engine &operator=(const Engine &) = delete;
 
     const Compiled &net() const { return net_; }
+    const std::shared_ptr<NetShare> &share() const { return share_; }
+    int device() const { return device_; }
+    // engine options as set so far (copied into replicas)
+    void copy_options_from(const Engine &o);
 
     int set_device(int device);
     int set_stream(void *stream);
@@ -50,6 +79,7 @@ class Engine {
     int get_wire_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint32_t nw, uint64_t *value, uint64_t *valid);
     int gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid, size_t dst_stride, bool dst_is_device,
                      bool async = false);
+    int join_copies();
     int pack_sim_state(const uint32_t *wires, uint32_t n, uint8_t *p0, uint8_t *p1, size_t cap, uint64_t *bit_len);
 
     // info
@@ -91,7 +121,9 @@ class Engine {
     int materialise_valid();
     uint32_t resident_wpc() const;
 
-    Compiled net_;
+    std::shared_ptr<NetShare> share_;
+    const Compiled &net_;
+    std::shared_ptr<DeviceNet> dnet_;
     int device_ = -1;
     bool device_ready_ = false;
     void *stream_ = nullptr;  // cudaStream_t
@@ -101,7 +133,7 @@ class Engine {
     uint32_t T_ = 0, stride_ = 0;
     uint64_t store_bytes_ = 0;
 
-    // netlist on the device
+    // netlist on the device (aliases into dnet_, which owns them)
     uint32_t *d_fan0_ = nullptr, *d_fan1_ = nullptr, *d_fan2_ = nullptr, *d_wide_off_ = nullptr, *d_wide_in_ = nullptr;
     uint8_t *d_kind2_ = nullptr, *d_wide_kind_ = nullptr, *d_wide_nsel_ = nullptr;
 
@@ -142,6 +174,7 @@ class Engine {
     uint32_t *d_rows_ = nullptr;
     uint32_t rows_cap_ = 0;
     uint64_t rows_key_ = 0, ptrs_key_ = 0;  // hashes of the cached wire lists (0 = none)
+    std::vector<uint32_t> rows_wires_, ptrs_wires_;  // the cached lists themselves (a hash hit is confirmed against them)
     uint8_t *d_pack_ = nullptr;
     size_t pack_cap_ = 0;
     // set_wire_drive queue (flushed before the next run) and the lane-0 snapshot get_wire_state reads
@@ -182,6 +215,8 @@ class Engine {
     bool opt_lenient_ = false;
     bool opt_budget_inclusive_ = false;  // SURVEY.md A.6-1 switch: `steps >= max_steps` instead of `>`
     uint32_t opt_u_ = 0;  // 0 = automatic gates-per-thread choice in k_eval2
+    bool opt_period2_ = true;   // unit-delay loops fast-forward over an exact period-2 oscillation
+    uint32_t opt_flags_ = 0;    // SemFlags: the reconstructed points of SURVEY.md A.6-4..7, one bit each
     bool use_resident_ = true, resident_attr_set_ = false;
     uint32_t last_mode_ = 0;
     uint64_t last_apps_ = 0;

@@ -13,10 +13,15 @@ namespace b2 {
 // crates/digilogic_gsim/src/lib.rs:55-66.
 
 int Builder::add_wire(uint8_t w, uint32_t *out) {
+    return add_wires(w, 1, out);
+}
+
+int Builder::add_wires(uint8_t w, uint32_t n, uint32_t *first) {
     if (w == 0) return B2_ERR_INVALID_ARG;
-    if (width.size() >= 0xFFFFFFFFull) return B2_ERR_OUT_OF_WIRES;
-    if (out) *out = (uint32_t)width.size();
-    width.push_back(w);
+    if (width.size() + (uint64_t)n > 0xFFFFFFFFull || total_bits + (uint64_t)n * w > kMaxBits) return B2_ERR_OUT_OF_WIRES;
+    if (first) *first = (uint32_t)width.size();
+    width.insert(width.end(), n, w);
+    total_bits += (uint64_t)n * w;
     return B2_OK;
 }
 
@@ -28,6 +33,27 @@ int Builder::wire_width(uint32_t wire, uint8_t *out) const {
 
 static int push(Builder &b, uint8_t kind, const uint32_t *in, size_t n, uint32_t select, uint32_t output, uint32_t *cell) {
     if (b.comps.size() >= 0xFFFFFFFFull || b.inputs.size() + n >= 0xFFFFFFFFull) return B2_ERR_TOO_MANY_COMPONENTS;
+    // what compile() makes of this component: 1-bit gates and their inputs (same case analysis as its bit-blast loop)
+    const uint64_t wout = b.width[output];
+    uint64_t bit_gates = wout, bit_inputs;
+    switch (kind) {
+        case K_MUX: bit_inputs = wout * (n + b.width[select]); break;
+        case K_BUF: bit_inputs = wout * 2; break;
+        case K_ADD:
+        case K_SUB: bit_inputs = wout * 2 * wout; break;
+        case K_HGATE: bit_inputs = b.width[in[0]] > 2 ? b.width[in[0]] : 2; break;
+        case K_REG:
+            bit_gates = wout + 1;
+            bit_inputs = wout * 4 + 1;
+            break;
+        case K_SLICE:
+        case K_MERGE: bit_inputs = wout; break;
+        default: bit_inputs = wout * n; break;
+    }
+    if (b.total_bit_gates + bit_gates > Builder::kMaxBitGates || b.total_bit_inputs + bit_inputs > Builder::kMaxBitInputs)
+        return B2_ERR_TOO_MANY_COMPONENTS;
+    b.total_bit_gates += bit_gates;
+    b.total_bit_inputs += bit_inputs;
     Component c;
     c.kind = kind;
     c.n_inputs = (uint32_t)n;
@@ -146,6 +172,7 @@ const uint32_t HIDDEN = 0x80000000u;  // a bit_inputs entry with this bit set na
 void compile(const Builder &b, Compiled &c) {
     const uint32_t W = (uint32_t)b.width.size();
     c.width = b.width;
+    c.sem_flags = b.sem_flags;
     c.bit_off.resize((size_t)W + 1);
     uint32_t nb = 0;
     for (uint32_t w = 0; w < W; w++) {
@@ -202,7 +229,12 @@ void compile(const Builder &b, Compiled &c) {
             } else if (cp.kind == K_HGATE) {
                 const uint32_t wi = b.width[in[0]];
                 if (wi == 1) {  // one bit: the bit itself (High-Z read as X), inverted for NAND / NOR / XNOR
-                    g.kind = cp.select >= K_NAND ? K_NOT : K_COPY;
+                    if (cp.select >= K_NAND) {
+                        g.kind = K_NOT;
+                    } else {  // OR(a, a): never High-Z, whatever SEM_COPY_Z says about slices and merges
+                        g.kind = K_OR;
+                        bin.push_back(c.bit_off[in[0]]);
+                    }
                     bin.push_back(c.bit_off[in[0]]);
                 } else {
                     g.kind = (uint8_t)cp.select;
@@ -241,7 +273,9 @@ void compile(const Builder &b, Compiled &c) {
     for (uint32_t g = 0; g < G; g++) {
         const uint32_t bn = gates[g].out;
         if (bn == NO_NET) continue;
-        if (gates[g].kind == K_BUF) {
+        // components whose output can be High-Z: buffers, and under the A.6-4 / A.6-7 alternatives multiplexers / slices and merges
+        const uint8_t gk = gates[g].kind;
+        if (gk == K_BUF || (gk == K_MUX && (b.sem_flags & SEM_MUX_Z)) || (gk == K_COPY && (b.sem_flags & SEM_COPY_Z))) {
             tri[bn] = 1;
             c.has_tristate = true;
         } else if (++n_firm[bn] > 1) {

@@ -22,6 +22,16 @@ enum Kind : uint8_t {
     K_ADD = 15, K_SUB = 16  // one sum / difference bit: inputs = {a_0..a_{w-1}, b_0..b_{w-1}}, bit index in the nsel field
 };
 
+// The points of gsim's behaviour that were reconstructed without its source, one switch each, default
+// off = the reading the oracle's defaults take (oracle/gsim_oracle.c go_config).  They are properties of a netlist's
+// components, set on the builder (b2_builder_set_option) and compiled in.
+enum SemFlags : uint32_t {
+    SEM_MUX_Z = 1,   // A.6-4: a multiplexer passes a High-Z selected input on as High-Z (default: as X)
+    SEM_INIT_X = 2,  // A.6-5: wires and component outputs start Undefined (default: High-Z)
+    SEM_BUF_Z = 4,   // A.6-6: an enabled buffer passes a High-Z input bit on as High-Z (default: as X)
+    SEM_COPY_Z = 8   // A.6-7: slices and merges pass a High-Z input bit on as High-Z (default: as X)
+};
+
 struct Component {
     uint8_t kind;
     uint32_t n_inputs;  // data inputs
@@ -34,8 +44,14 @@ struct Builder {
     std::vector<uint8_t> width;
     std::vector<Component> comps;
     std::vector<uint32_t> inputs;
+    // Running 64-bit totals of what compile() will bit-blast: the compiled arrays index bit-nets, 1-bit gates and
+    // their inputs with 32 bits (bit 31 of a bit-net index is a flag), so the builder refuses to grow past these.
+    uint32_t sem_flags = 0;  // SemFlags
+    uint64_t total_bits = 0, total_bit_gates = 0, total_bit_inputs = 0;
+    static constexpr uint64_t kMaxBits = 1ull << 30, kMaxBitGates = 1ull << 30, kMaxBitInputs = 1ull << 31;
 
     int add_wire(uint8_t w, uint32_t *out);
+    int add_wires(uint8_t w, uint32_t n, uint32_t *first);
     int wire_width(uint32_t wire, uint8_t *out) const;
     int add_gate(int kind, const uint32_t *in, size_t n, uint32_t output, uint32_t *cell);
     int add_not(uint32_t in, uint32_t output, uint32_t *cell);
@@ -63,6 +79,7 @@ struct Compiled {
     std::vector<uint32_t> row_of_bit;  // bit-net -> store row
     std::vector<uint8_t> bit_driven;   // bit-net has a gate driver
     uint32_t n_rows = 0, n_src = 0;
+    uint32_t sem_flags = 0;  // SemFlags of the builder
     // fast gates (one to three inputs), in row order: n_g2 one/two-input gates, then n_g3 three-input gates
     std::vector<uint32_t> fan0, fan1, fan2;  // store rows (fan2 = fan0 for gates with fewer inputs)
     std::vector<uint8_t> kind2;

@@ -229,6 +229,12 @@ class SimulatorBuilder:
         out = np.ascontiguousarray(out, np.uint32)
         _check(self._lib.b2_add_gates2(self._h, _p(kinds), _p(in0), _p(in1), _p(out), len(kinds)), "add_gates2")
 
+    OPT_MUX_Z_PASSTHROUGH, OPT_INITIAL_UNDEFINED, OPT_BUFFER_Z_PASSTHROUGH, OPT_COPY_Z_PASSTHROUGH = 1, 2, 3, 4
+
+    def set_option(self, option: int, value: int):
+        """b2_builder_set_option: the reconstructed points of gsim's behaviour, one switch each."""
+        _check(self._lib.b2_builder_set_option(self._h, option, value), "builder.set_option")
+
     def build(self) -> "Simulator":
         """SimulatorBuilder::build() (lib.rs:127); leaves this builder empty."""
         h = self._lib.b2_build(self._h)
@@ -248,6 +254,13 @@ class Simulator:
         if getattr(self, "_h", None):
             self._lib.b2_sim_free(self._h)
             self._h = None
+
+    def clone(self) -> "Simulator":
+        """b2_sim_clone: another simulator of the same compiled netlist (shared host arrays and device copy)."""
+        h = self._lib.b2_sim_clone(self._h)
+        if not h:
+            raise MemoryError("b2_sim_clone failed")
+        return Simulator(h)
 
     # ---- gsim surface
     def get_wire_width(self, wire: int) -> int:

@@ -73,7 +73,10 @@ uint64_t b2_kernel_launches(void);
 b2_builder *b2_builder_new(void);
 void b2_builder_free(b2_builder *b);
 
-/* SimulatorBuilder::add_wire(width) -> Option<WireId>  (lib.rs:135-139). width 1..255. */
+/* SimulatorBuilder::add_wire(width) -> Option<WireId>  (lib.rs:135-139). width 1..255.
+   Capacity: the compiled netlist indexes 1-bit nets and 1-bit gates with 32 bits, so a builder holds at most
+   2^30 wire bits (B2_ERR_OUT_OF_WIRES beyond) and 2^30 bit-blasted gates / 2^31 bit-blasted gate inputs
+   (B2_ERR_TOO_MANY_COMPONENTS beyond) — counted in 64 bits as components are added, never wrapped. */
 int b2_add_wire(b2_builder *b, uint8_t width, uint32_t *out_wire);
 /* Batch extension: n wires of one width with consecutive ids starting at *out_first. */
 int b2_add_wires(b2_builder *b, uint8_t width, uint32_t n, uint32_t *out_first);
@@ -125,7 +128,8 @@ int b2_add_register(b2_builder *b, uint32_t data_in, uint32_t data_out, uint32_t
 int b2_add_slice(b2_builder *b, uint32_t input, uint32_t offset, uint32_t output, uint32_t *out_cell);
 int b2_add_merge(b2_builder *b, const uint32_t *inputs, size_t n, uint32_t output, uint32_t *out_cell);
 /* Batch extension: n one- or two-input gates at once (kinds[i] in B2_AND..B2_NOT; in1 ignored
-   for B2_NOT), validated exactly like the single calls; stops at the first error. */
+   for B2_NOT), validated exactly like the single calls.  All or nothing: on the first invalid entry
+   its error is returned and the builder is left as it was before the call. */
 int b2_add_gates2(b2_builder *b, const uint8_t *kinds, const uint32_t *in0, const uint32_t *in1, const uint32_t *out, size_t n);
 
 /* SimulatorBuilder::build()  (lib.rs:123-133): compiles the netlist (bit-blast, driver
@@ -134,6 +138,26 @@ int b2_add_gates2(b2_builder *b, const uint8_t *kinds, const uint32_t *in0, cons
    allocated.  Returns NULL only on allocation failure or b == NULL. */
 b2_sim *b2_build(b2_builder *b);
 void b2_sim_free(b2_sim *s);
+
+/* Builder options: the points of gsim 1.1.4's behaviour that were reconstructed without its source,
+   one switch each, default 0 = the reading oracle/gsim_oracle.c takes by default.  They exist so that a verdict from the real
+   crate (oracle/gsim_diff) is followed by flipping a switch, not by editing a kernel; each is tested on every device path in
+   lockstep with the oracle's matching switch.  (A.6-1 and A.6-2 are simulator options: B2_OPT_STEP_BUDGET_INCLUSIVE,
+   B2_OPT_CONFLICT_NEEDS_DISAGREE.)  The switches survive b2_build, which otherwise leaves the builder empty. */
+enum b2_builder_option {
+    B2_BOPT_MUX_Z_PASSTHROUGH = 1,    /* A.6-4: a multiplexer passes a High-Z bit of the selected input on as High-Z (default: X).
+                                         Its output can then float, so a net with a multiplexer among its drivers is resolved
+                                         per step like a tri-state net */
+    B2_BOPT_INITIAL_UNDEFINED = 2,    /* A.6-5: wires and component outputs start Undefined (default: High-Z) */
+    B2_BOPT_BUFFER_Z_PASSTHROUGH = 3, /* A.6-6: an enabled buffer passes a High-Z input bit on as High-Z (default: X) */
+    B2_BOPT_COPY_Z_PASSTHROUGH = 4    /* A.6-7: slices and merges pass a High-Z input bit on as High-Z (default: X) */
+};
+int b2_builder_set_option(b2_builder *b, int option, int64_t value);
+
+/* A second simulator of the same compiled netlist (batch extension): it shares the host arrays and the device copy of the
+   netlist with `s` — nothing is recompiled or uploaded again — and has its own lanes, wire-state store, drives and stream.
+   Options set on `s` so far are copied.  NULL on allocation failure. */
+b2_sim *b2_sim_clone(const b2_sim *s);
 
 /* ------------------------------------------------------------------------------------
  * Simulator — replaces gsim::Simulator
@@ -274,6 +298,87 @@ int b2_gather_wires_host_async(b2_sim *s, const uint32_t *wires, uint32_t n, uin
    invariant, lib.rs:168).  *out_bit_len receives the total bit count. */
 int b2_pack_sim_state(b2_sim *s, const uint32_t *wires, uint32_t n, uint8_t *plane0, uint8_t *plane1, size_t cap_bytes,
                       uint64_t *out_bit_len);
+
+/* ------------------------------------------------------------------------------------
+ * Batch runner and multi-GPU gather (no reference counterpart: gsim runs one stimulus vector per Simulator::run_sim,
+ * crates/digilogic_gsim/src/lib.rs:216-219; a batch of L lanes is L such runs of one netlist).
+ *
+ * b2_batch owns what a host would otherwise script around b2_sim: the tiling of the lanes, `n_slots` wire-state stores that
+ * work on alternate tiles, the stimulus source and the destinations of the designated output rows.  For an acyclic
+ * single-driver netlist whose inputs are undriven nets and a step budget that covers its depth (the conditions of the
+ * levelised path of b2_run_sim_lanes) a whole batch is ONE launch of the persistent level-sweep kernel (csrc/sweep.cuh);
+ * every other case (feedback, tri-state nets, registers, drives on gate outputs, max_steps below the depth) runs tile by tile
+ * on `n_slots` simulator replicas that share the device copy of the netlist, with exactly the semantics of b2_run_sim_lanes.
+ * Inputs and outputs are 1-bit wires.  All work is queued on the batch's stream; b2_batch_wait blocks.
+ * ---------------------------------------------------------------------------------- */
+typedef struct b2_batch b2_batch;
+typedef struct b2_comm b2_comm;   /* an NCCL communicator, one rank per GPU */
+
+typedef struct b2_batch_info {
+    uint32_t tile_words, n_slots;
+    uint32_t sweep;            /* 1: the level-sweep kernel serves this netlist; 0: simulator replicas */
+    uint32_t tasks_per_pass;   /* sweep: tasks of one tile (after the first run) */
+    uint32_t grid_ctas, gates_per_task;
+    uint32_t n_ranks, rank, peers_mapped;
+    uint32_t pad;
+    uint64_t store_bytes;
+    uint64_t words_local;      /* lane-words per rank of the gathered planes (0 without a communicator) */
+    uint64_t last_tiles, last_tickets;
+} b2_batch_info;
+
+enum b2_batch_option {
+    B2_BATCH_OPT_SWEEP = 1,       /* default 1; 0: always use the simulator replicas */
+    B2_BATCH_OPT_TASK_ITERS = 2,  /* default 1: 256-thread iterations per gate task of the sweep (tuning) */
+    B2_BATCH_OPT_UNROLL = 3,      /* default 4: gates per thread of the one/two-input class in the sweep (2 or 4) */
+    B2_BATCH_OPT_CTAS_PER_SM = 4, /* default 0 = as many as fit */
+    B2_BATCH_OPT_AUTO_GATHER = 5  /* default 1: with a communicator bound every run ends with b2_batch_gather_outputs, so a
+                                     step is one call; 0: the host calls it */
+};
+
+/* `sim` names the compiled netlist (and the engine options to copy); it is not modified and may be freed afterwards.
+   tile_words: 64-lane words per tile and slot (even; the sweep takes at most 512); n_slots: tiles in flight (1..64). */
+int b2_batch_new(const b2_sim *sim, const uint32_t *inputs, uint32_t n_inputs, const uint32_t *outputs, uint32_t n_outputs,
+                 uint32_t tile_words, uint32_t n_slots, b2_batch **out);
+void b2_batch_free(b2_batch *b);
+int b2_batch_set_device(b2_batch *b, int device);
+int b2_batch_set_stream(b2_batch *b, void *stream);   /* cudaStream_t, used as given */
+int b2_batch_set_option(b2_batch *b, int option, int64_t value);
+int b2_batch_get_info(b2_batch *b, b2_batch_info *out);
+
+/* One settle (run_sim(max_steps) on every lane) of lanes [0, 64 * n_words) of the batch, queued on the batch's stream.
+   Stimulus: generated on the device exactly like b2_fill_stimulus (input i = position in `inputs`, global lane-word
+   lane_word_begin + w), or read from planes [n_inputs][in_stride_words] in device memory or in host memory (page-locked
+   memory is read in place over PCIe by the kernel; pageable memory is page-locked for the duration of the run).
+   Outputs: planes [n_outputs][out_stride_words], device or host memory, may be NULL when a communicator is bound.
+   *_ring_words (0 = none): the planes hold that many words per row and are used as a ring (a multiple of tile_words).
+   With a communicator bound, the output rows also go to this rank's share of the gathered planes — on every rank whose
+   planes are mapped (b2_batch_import_gather_handles), stored over NVLink by the task that reads the rows. */
+int b2_batch_run_generated(b2_batch *b, uint64_t seed, int mode, uint64_t lane_word_begin, uint64_t n_words, uint64_t max_steps,
+                           uint64_t *out_value, uint64_t *out_valid, size_t out_stride_words, size_t out_ring_words);
+int b2_batch_run_planes(b2_batch *b, const uint64_t *in_value, const uint64_t *in_valid, size_t in_stride_words, size_t in_ring_words,
+                        uint64_t n_words, uint64_t max_steps, uint64_t *out_value, uint64_t *out_valid, size_t out_stride_words,
+                        size_t out_ring_words);
+/* Blocks until everything queued has finished (including a pending gather); *out_worst (may be NULL) = worst b2_run_result
+   over all lanes (and, with a communicator, all ranks) since the previous wait. */
+int b2_batch_wait(b2_batch *b, int *out_worst);
+
+/* Multi-GPU (lanes shard over GPUs, a full netlist replica per GPU, no traffic during the settle, the output
+   planes gathered at the end).  The host moves two small blobs between the ranks by whatever channel it has: the 128-byte
+   NCCL unique id (rank 0 -> all) and one 128-byte handle of each rank's gathered planes (all -> all). */
+int b2_comm_get_unique_id(uint8_t id[128]);                                   /* ncclGetUniqueId */
+int b2_comm_init_rank(b2_comm **out, int n_ranks, int rank, const uint8_t id[128], int device);  /* ncclCommInitRank */
+void b2_comm_free(b2_comm *c);
+/* Allocates this rank's gathered planes [n_ranks][n_outputs][words_local] (value and valid) and binds the communicator. */
+int b2_batch_bind_comm(b2_batch *b, b2_comm *comm, uint64_t words_local);
+/* CUDA IPC handles of this rank's gathered planes (value: bytes 0-63, valid: 64-127) / the handles of all ranks
+   [n_ranks][128] in rank order: from then on every run stores its output rows into all ranks' planes directly. */
+int b2_batch_export_gather_handle(b2_batch *b, uint8_t handle[128]);
+int b2_batch_import_gather_handles(b2_batch *b, const uint8_t *handles);
+/* Completes the gather of the last run (SURVEY.md 8b `b2_gather_outputs(sim, ncclComm...)`): with mapped peers the rows
+   are already in place and the ranks only meet (a MAX all-reduce of the run result); otherwise ncclAllGather moves them. */
+int b2_batch_gather_outputs(b2_batch *b);
+/* Device pointers of this rank's gathered planes, valid after b2_batch_gather_outputs in stream order. */
+int b2_batch_gathered(b2_batch *b, uint64_t **dev_value, uint64_t **dev_valid);
 
 /* ------------------------------------------------------------------------------------
  * Server — mirrors `impl SimServer for GsimServer` (crates/digilogic_gsim/src/lib.rs:101-239;

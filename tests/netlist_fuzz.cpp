@@ -21,6 +21,26 @@ using namespace b2;
 
 int main(int argc, char **argv) {
     const int rounds = argc > 1 ? std::atoi(argv[1]) : 200;
+    {   // capacity: bit totals are counted in 64 bits and refused at the limits, never wrapped
+        Builder b;
+        uint32_t first = 0, cell = 0;
+        const uint32_t n_fit = (uint32_t)(Builder::kMaxBits / 255);
+        REQUIRE(b.add_wires(255, n_fit, &first) == B2_OK && first == 0);
+        REQUIRE(b.total_bits == (uint64_t)n_fit * 255);
+        REQUIRE(b.add_wires(255, 1, &first) == B2_ERR_OUT_OF_WIRES);       // 2^30 bits reached
+        REQUIRE(b.add_wires(255, 0xFFFFFFFFu, &first) == B2_ERR_OUT_OF_WIRES);
+        REQUIRE(b.width.size() == n_fit);
+        uint32_t added = 0;
+        int rc = B2_OK;
+        while ((rc = b.add_arith(K_ADD, 0, 1, 2, &cell)) == B2_OK) added++;  // 255 x 510 bit-blasted inputs each
+        REQUIRE(rc == B2_ERR_TOO_MANY_COMPONENTS);
+        REQUIRE(added == Builder::kMaxBitInputs / (255ull * 510ull));
+        REQUIRE(b.total_bit_inputs <= Builder::kMaxBitInputs && b.total_bit_gates <= Builder::kMaxBitGates);
+        const uint32_t in8[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+        while ((rc = b.add_gate(K_AND, in8, 8, 9, &cell)) == B2_OK) added++;  // 255 x 8 more each, up to the same limit
+        REQUIRE(rc == B2_ERR_TOO_MANY_COMPONENTS && b.comps.size() == added);
+        REQUIRE(b.total_bit_inputs <= Builder::kMaxBitInputs && b.total_bit_inputs + 255 * 8 > Builder::kMaxBitInputs);
+    }
     std::mt19937 rng(12345);
     auto rnd = [&](uint32_t n) { return (uint32_t)(rng() % n); };
     for (int r = 0; r < rounds; r++) {
