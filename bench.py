@@ -8,17 +8,20 @@ Workload (config.workload): BASELINE config 3 — synthetic random combinational
 depth 200, fan-in 2, 4096 inputs, 2^24 stimulus lanes per GPU, 4-state engine with two-valued
 stimulus generated on the device from (seed, input, global lane-word).  One step = one settle
 (run_sim to the fixed point) of every lane of the batch plus extraction of the 1024 designated
-output rows = ONE call of the C ABI's batch runner (b2_batch_run_generated) = one launch of the
-persistent level-sweep kernel (digilogic_b200/csrc/sweep.cuh).  At N GPUs every rank runs the same
-per-GPU batch on its own lane range (weak scaling); the output rows are stored into every rank's
-gathered planes over NVLink by the sweep kernel itself (--nccl-gather: by ncclAllGather afterwards).
+output rows = ONE call of the C ABI's batch runner (b2_batch_run_generated): tiles of 256 lane-words
+on three simulator replicas that share one device copy of the netlist, each replaying its level sweep
+from a CUDA graph on its own stream (--sweep: the persistent level-sweep kernel instead, one launch
+per step).  At N GPUs every rank runs the same per-GPU batch on its own lane range (weak scaling); the
+output rows of every tile are stored into every rank's gathered planes over NVLink by the kernel that
+reads them (CUDA IPC mappings; --nccl-gather: by ncclAllGather after the last tile).
 
 value      = G * L_total / max-over-ranks device time                (gate-lane evals/s)
 e2e        = the same through the C ABI with HOST buffers (b2_batch_run_planes): pinned-host stimulus
              planes in, output planes out, both moved inside the timed region every step
-roofline   = k_sweep: 48 algorithmic bytes per gate per 64-lane word / launch duration
-             (CUDA events), against MEASURED_PEAKS.json; traffic / dram_frac = DRAM bytes of the same
-             kernel from the committed ncu capture (profiles/traffic.json)
+roofline   = k_eval2<2,false,false>, the per-level gate kernel: 48 algorithmic bytes per gate per 64-lane
+             word / its effective launch duration (timed region / launches: the replicas'
+             launches overlap), against MEASURED_PEAKS.json; traffic / dram_frac = DRAM bytes of one whole
+             step with all replicas running (ncu range replay, profiles/traffic.json) per launch
 shard_check (N > 1) = rank 0 settles a tile of another rank's lanes itself and compares with the gathered planes
 config5    (N > 1) = secondary: BASELINE config 5 (10M gates, 2^26 lanes sharded over the N GPUs)
 cpu_baseline = the scalar event-driven gsim restatement (oracle/gsim_oracle.c, "port") on the
@@ -60,8 +63,9 @@ def parse_args():
     ap.add_argument("--outputs", type=int, default=1024)
     ap.add_argument("--lanes", type=int, default=1 << 24, help="stimulus lanes per GPU")
     ap.add_argument("--tile-words", type=int, default=0,
-                    help="64-lane words per tile and slot of the level sweep (0 = batch.auto_sweep_shape)")
-    ap.add_argument("--slots", type=int, default=0, help="tiles in flight in the level sweep (0 = batch.auto_sweep_shape)")
+                    help="64-lane words per tile and slot (0 = batch.auto_batch_shape: 256 for this netlist)")
+    ap.add_argument("--slots", type=int, default=0, help="tiles in flight = simulator replicas (0 = batch.auto_batch_shape: 3)")
+    ap.add_argument("--sweep", action="store_true", help="use the persistent level-sweep kernel (B2_BATCH_OPT_SWEEP) instead of the replicas")
     ap.add_argument("--task-iters", type=int, default=1, help="256-thread iterations per gate task of the sweep")
     ap.add_argument("--unroll", type=int, default=4, help="gates per thread of the one/two-input class in the sweep (2 or 4)")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="resident CTAs per SM of the sweep (0 = as many as fit)")
@@ -261,7 +265,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)   # the harness's channel for two 128-byte blobs and the timing reduction
 
     from digilogic_b200 import SimulatorBuilder, SimulationRunResult
-    from digilogic_b200.batch import Batch, auto_sweep_shape, setup_comm, shard_words
+    from digilogic_b200.batch import Batch, auto_batch_shape, setup_comm, shard_words
     from digilogic_b200.gsim import kernel_launches
 
     gen = build_netlist(args)
@@ -274,11 +278,12 @@ def run_b200(args):
     words_local = args.lanes // 64
     total_words = words_local * world
     w_begin, w_end = shard_words(total_words, world, rank)
-    auto_tile, auto_slots = auto_sweep_shape(sim, words_local)
+    auto_tile, auto_slots = auto_batch_shape(sim, words_local)
     tile = min(args.tile_words, words_local) if args.tile_words else auto_tile
     slots = args.slots or auto_slots
     args.tile_words, args.slots = tile, slots
     batch = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=local_rank, stream=stream.cuda_stream)
+    batch.set_option(Batch.OPT_SWEEP, 1 if args.sweep else 0)
     batch.set_option(Batch.OPT_TASK_ITERS, args.task_iters)
     batch.set_option(Batch.OPT_UNROLL, args.unroll)
     if args.ctas_per_sm:
@@ -287,8 +292,8 @@ def run_b200(args):
     n_out = len(gen.outputs)
     out_v = out_m = None
     if world > 1:
-        # gathered planes [world, n_out, words_local] on every rank; with the peers' planes mapped (CUDA IPC) the sweep
-        # kernel's output tasks store this rank's rows into all of them over NVLink
+        # gathered planes [world, n_out, words_local] on every rank; with the peers' planes mapped (CUDA IPC) the kernel that
+        # reads a tile's output rows stores them into all of them over NVLink
         setup_comm(batch, words_local, local_rank, map_peers=not args.nccl_gather)
     else:
         out_v = torch.zeros((n_out, words_local), dtype=torch.int64, device=dev)
@@ -314,7 +319,7 @@ def run_b200(args):
     barrier()
     assert worst == SimulationRunResult.Ok
     binfo = batch.info
-    assert binfo.sweep == 1, "config 3 is acyclic: the level-sweep kernel must be the path that runs"
+    assert binfo.sweep == (1 if args.sweep else 0)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -361,30 +366,39 @@ def run_b200(args):
     gate_lane_evals = float(args.gates) * args.lanes * world * args.steps
     value = gate_lane_evals / (ms * 1e-3)
 
-    # roofline of the dominant kernel: k_sweep, ONE launch per step and GPU (stimulus, all levels of all tiles, output rows).
-    # Algorithmic bytes: 48 B per gate per 64-lane word; the stimulus and output rows add 16 B per row-word.
+    # roofline of the dominant kernel.  Replicas: k_eval2, one launch per level per tile; the replicas' launches overlap, so
+    # the per-launch duration is the effective one, timed region / launches (the few other kernels of a tile — stimulus,
+    # drives, output rows: 0.6 % of a step — are charged to it).  --sweep: k_sweep, one launch per step.
+    # Algorithmic bytes: 48 B per gate per 64-lane word.
     n_tiles = -(-words_local // tile)
-    launch_s = ms * 1e-3 / args.steps
     gate_words = float(args.gates) * words_local
-    algo_bytes = ALGO_BYTES_PER_GATE_WORD * gate_words + 16.0 * (len(gen.inputs) + n_out) * words_local
+    step_s = ms * 1e-3 / args.steps
+    if args.sweep:
+        kernel, launches_per_step = f"k_sweep<{args.unroll}>", 1
+    else:
+        per_level_ctas4 = -(-(args.gates // info.depth) // (max(256 // max(tile // 2, 1), 1) * 4)) * max((tile // 2 + 255) // 256, 1)
+        kernel = "k_eval2<4,false,false>" if per_level_ctas4 >= 148 * 3 * 4 else "k_eval2<2,false,false>"   # Engine::run_levelised's rule
+        launches_per_step = n_tiles * info.depth
+    launch_s = step_s / launches_per_step
+    algo_bytes = ALGO_BYTES_PER_GATE_WORD * gate_words / launches_per_step
     peak, peak_kind = load_peaks()
     achieved = algo_bytes / launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "dram_frac": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-                "kernel": f"k_sweep<{args.unroll}>", "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": launch_s * 1e3,
-                "launches_timed": args.steps,
-                "note": "one launch = one step on one GPU; duration = CUDA events around the timed launches / steps. frac is the "
-                        "algorithmic fraction (> 1 because a level's output rows are still in L2 when the next level reads them); "
-                        "dram_frac = measured DRAM bytes of the same kernel (ncu, profiles/traffic.json, scaled per gate-word) / "
-                        "duration / peak is the physical one"}
+                "kernel": kernel, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_us": launch_s * 1e6,
+                "launches_timed": launches_per_step * args.steps,
+                "note": "effective launch duration (timed region / launches; the replicas overlap). frac is the ALGORITHMIC fraction: "
+                        "> 1 because a level's output rows are still in L2 when the next level reads them. dram_frac = measured DRAM "
+                        "bytes (traffic: one whole step with all replicas running, ncu range replay, per launch) / duration / peak "
+                        "is the physical fraction"}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
             with open(traffic_path) as f:
                 tj = json.load(f)
-            if (tj.get("kernel", "").startswith("k_sweep") and tj.get("tile_words") == tile and tj.get("slots") == slots
-                    and tj.get("gates") == args.gates):
-                roofline["traffic"] = tj["dram_bytes_per_gate_word"] * gate_words
+            if (tj.get("engine") == ("sweep" if args.sweep else "replicas") and tj.get("tile_words") == tile
+                    and tj.get("slots") == slots and tj.get("gates") == args.gates):
+                roofline["traffic"] = tj["dram_bytes_per_gate_word"] * gate_words / launches_per_step
                 roofline["dram_frac"] = roofline["traffic"] / launch_s / 1e9 / peak
                 roofline["l2_hit_rate_pct"] = tj.get("l2_hit_rate_pct")
         except Exception:
@@ -403,8 +417,7 @@ def run_b200(args):
     elision = None
     if world == 1 and not args.no_elision_probe:
         sim.set_option(sim.OPT_VALID_ELISION, 1)
-        eb = Batch(sim, gen.inputs, gen.outputs, 256, 2, device=local_rank, stream=stream.cuda_stream)
-        eb.set_option(Batch.OPT_SWEEP, 0)
+        eb = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=local_rank, stream=stream.cuda_stream)
         ev2, em2 = torch.zeros_like(out_v), torch.zeros_like(out_m)
         eb.run_generated(SEED, 0, w_begin, words_local, args.max_steps, ev2, em2)
         eb.wait()
@@ -417,7 +430,7 @@ def run_b200(args):
         cs2 = int((ev2.sum() ^ em2.sum()).item()) & 0xFFFFFFFFFFFFFFFF
         elision = {"value": float(args.gates) * args.lanes / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "steps": 1,
                    "bytes_per_gate_word": 24, "output_checksum_equal": cs2 == checksum,
-                   "note": "B2_OPT_VALID_ELISION=1 on the per-level kernels (simulator replicas, tile 256 x 2, one issuing thread); "
+                   "note": "B2_OPT_VALID_ELISION=1 on the per-level kernels (same batch shape); "
                            "all stimulus lanes valid, so no valid plane is read or written"}
         sim.set_option(sim.OPT_VALID_ELISION, 0)
         del eb, ev2, em2
@@ -451,7 +464,8 @@ def run_b200(args):
                                                 "grid_ctas": binfo.grid_ctas, "gates_per_task": binfo.gates_per_task,
                                                 "tasks_per_tile": binfo.tasks_per_pass,
                                                 "gather": None if world == 1 else ("ncclAllGather" if args.nccl_gather else
-                                                                                   "fused: sweep output tasks store into every rank's planes over NVLink (CUDA IPC)")}),
+                                                                                   "fused: the kernel that reads a tile's output rows stores them into every rank's planes over NVLink (CUDA IPC)"),
+                                                "engine": "sweep" if args.sweep else "replicas"}),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "valid_elision": elision, "unit_delay": unit_delay,
             "gpu_launches": int(launches), "clocks": clocks, "output_checksum": f"{checksum:#018x}",
         }
@@ -468,7 +482,7 @@ def config5_probe(args, torch, dist, world, rank, local_rank, dev, stream, total
     """Secondary key at N > 1: BASELINE config 5 — 10M-gate DAG, 2^26 lanes sharded contiguously over the N GPUs, output
     planes gathered into every rank — one warm-up on an eighth of the shard, then one timed settle of the whole shard."""
     from digilogic_b200 import SimulatorBuilder, netgen
-    from digilogic_b200.batch import Batch, auto_sweep_shape, setup_comm, shard_words
+    from digilogic_b200.batch import Batch, auto_batch_shape, setup_comm, shard_words
     gates, depth, n_in, n_out = 10_000_000, 200, 16384, 1024
     t0 = time.perf_counter()
     gen = netgen.random_dag(n_gates=gates, depth=depth, n_inputs=n_in, n_outputs=n_out, seed=0xD1610005)
@@ -476,7 +490,7 @@ def config5_probe(args, torch, dist, world, rank, local_rank, dev, stream, total
     build_s = time.perf_counter() - t0
     words_local = total_lanes // 64 // world
     w_begin, _ = shard_words(words_local * world, world, rank)
-    tile, slots = auto_sweep_shape(sim, words_local)
+    tile, slots = auto_batch_shape(sim, words_local)
     batch = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=local_rank, stream=stream.cuda_stream)
     setup_comm(batch, words_local, local_rank, map_peers=not args.nccl_gather)
     batch.run_generated(0xD1610005, 0, w_begin, max(words_local // 8, tile), args.max_steps)
@@ -562,9 +576,9 @@ def unit_delay_probe(args, n_lanes=65536, clocks=20):
 
 
 def run_e2e(args, torch, dist, batch, batch_sim, gen, world, rank, dev, words_local, barrier):
-    """Same metric through the C ABI with HOST buffers: one b2_batch_run_planes call per step reads the stimulus planes from
-    page-locked host memory (the sweep kernel's stimulus tasks load them over PCIe) and writes the output planes back to
-    page-locked host memory (its output tasks store them over PCIe) — both inside the timed region, both every step."""
+    """Same metric through the C ABI with HOST buffers: one b2_batch_run_planes call per step copies every tile's stimulus planes
+    from page-locked host memory and its output planes back to page-locked host memory — both inside the timed region, both
+    every step, on the replicas' copy streams while other tiles settle."""
     n_in, n_out = len(gen.inputs), len(gen.outputs)
     tile = args.tile_words
     # One GPU: host planes for the whole batch (17.2 + 4.3 GB).  Several GPUs share one host: a ring of a quarter of the
@@ -609,8 +623,8 @@ def run_e2e(args, torch, dist, batch, batch_sim, gen, world, rank, dev, words_lo
     return {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(n_in * words_local * 16),
             "d2h_bytes_per_step": int(n_out * words_local * 16), "ms_per_step": ms / args.e2e_steps, "steps": args.e2e_steps,
             "result": int(worst), "host_ring_words": ring_words, "tiles_per_step": -(-words_local // tile),
-            "path": "b2_batch_run_planes: zero-copy PCIe reads of the pinned stimulus planes by the sweep kernel's stimulus tasks, "
-                    "zero-copy PCIe stores of the output rows by its output tasks; one C call per step",
+            "path": "b2_batch_run_planes, one C call per step: H2D of a tile's stimulus planes and D2H of its output planes on the "
+                    "replicas' copy streams, overlapped with the settles of the other tiles",
             "host_checksum": f"{int(outv.sum() ^ outm.sum()) & 0xFFFFFFFFFFFFFFFF:#018x}"}
 
 

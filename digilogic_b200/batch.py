@@ -58,22 +58,10 @@ def auto_tile_words(sim: Simulator, n_words: int, l2_level_bytes: int = 20 << 20
     return max(1, min(t, n_words))
 
 
-def auto_sweep_shape(sim: Simulator, n_words: int, l2_budget_bytes: int = 40 << 20) -> tuple[int, int]:
-    """(tile_words, n_slots) for the level-sweep kernel.  The slots in flight are interleaved level by level, so the rows
-    one level writes (gates per level x 16 B x tile_words x n_slots) are what L2 has to keep until the next level has read
-    them: that product is held near `l2_budget_bytes` of the 126 MB L2 (measured optimum, profiles/README.md) with at least
-    four slots, so that a slot's next level never waits for its previous one, and tiles of 32 .. 512 words."""
-    info = sim.info
-    if info.cyclic or info.depth == 0:
-        return min(max(n_words, 2), 512), 2
-    per_level = max((info.n_gates2 + info.n_gates3 + info.n_gates_wide) / info.depth, 1.0)
-    in_flight = max(int(l2_budget_bytes / (16.0 * per_level)), 128)       # lane-words over all slots
-    slots = 4
-    t = max(32, min(in_flight // slots, 512))
-    t = 1 << (t.bit_length() - 1)
-    while t > 2 and n_words % t:
-        t >>= 1
-    return max(2, min(t, n_words + (n_words & 1))), slots
+def auto_batch_shape(sim: Simulator, n_words: int) -> tuple[int, int]:
+    """(tile_words, n_slots) for the batch runner: `auto_tile_words` and three slots — with three tiles in flight the launch
+    gaps and kernel tails of one tile's level sweep are filled by the others (profiles/README.md: 256 x 3 on config 3)."""
+    return auto_tile_words(sim, n_words), 3
 
 
 class _DeviceArray:
@@ -272,5 +260,5 @@ def reduce_worst(worst: SimulationRunResult, device) -> SimulationRunResult:
     return SimulationRunResult(int(t.item()))
 
 
-__all__ = ["Batch", "BatchRunner", "Comm", "B200Error", "auto_sweep_shape", "auto_tile_words", "choose_tile_words",
+__all__ = ["Batch", "BatchRunner", "Comm", "B200Error", "auto_batch_shape", "auto_tile_words", "choose_tile_words",
            "gather_output_planes", "plan_tiles", "reduce_worst", "setup_comm", "shard_words"]

@@ -622,6 +622,9 @@ int Batch::run_replicas(int stim_mode, uint64_t seed, uint64_t word_begin, const
     for (uint64_t t = 0; t < n_tiles; t++) {
         Engine &e = *replicas_[t % K_];
         const uint64_t w0 = t * T_;
+        // a slot is reused by later tiles, i.e. by other lanes: where state survives a run (feedback, registers) every tile
+        // starts as a freshly built simulator — a batch run is one run_sim of L new simulators
+        if (net_.cyclic) e.reset_cold();
         if (stim_mode < 2) {
             if ((rc = e.fill_stimulus(inputs_.data(), n_in, seed, word_begin + w0, stim_mode))) return rc;
         } else {

@@ -38,7 +38,7 @@ class Comm {
 
 struct BatchInfo {
     uint32_t tile_words, n_slots;
-    uint32_t sweep;            // 1: the persistent level-sweep kernel serves this netlist, 0: simulator replicas (unit-delay capable)
+    uint32_t sweep;            // 1: the persistent level-sweep kernel is selected and serves this netlist, 0: simulator replicas
     uint32_t tasks_per_pass;   // sweep: tasks of one tile
     uint32_t grid_ctas, gates_per_task;
     uint32_t n_ranks, rank, peers_mapped;
@@ -49,11 +49,12 @@ struct BatchInfo {
 };
 
 enum BatchOption {
-    BATCH_OPT_SWEEP = 1,       // default 1: use the level-sweep kernel when the netlist allows it
+    BATCH_OPT_SWEEP = 1,       // default 0; 1: use the persistent level-sweep kernel when the netlist allows it
     BATCH_OPT_TASK_ITERS = 2,  // default 1: iterations (of 256 threads x U gates) per gate task
     BATCH_OPT_UNROLL = 3,      // default 4: gates per thread of the one/two-input class (2 or 4)
     BATCH_OPT_CTAS_PER_SM = 4, // default 0 = occupancy limit
-    BATCH_OPT_AUTO_GATHER = 5  // default 1: with a communicator bound, every run ends with gather_outputs()
+    BATCH_OPT_AUTO_GATHER = 5, // default 1: with a communicator bound, every run ends with gather_outputs()
+    BATCH_OPT_LOAD_MODE = 6    // experiment: 0 strong row loads (default), 1 weak L1-no-allocate row loads
 };
 
 class Batch {
@@ -108,7 +109,7 @@ class Batch {
     bool own_stream_ = false, stream_set_ = false;
     int sm_count_ = 148;
     // options
-    bool opt_sweep_ = true;
+    bool opt_sweep_ = false;
     uint32_t opt_iters_ = 1, opt_unroll_ = 4, opt_ctas_per_sm_ = 0;
     bool opt_auto_gather_ = true;
     // sweep state

@@ -142,8 +142,8 @@ __device__ __forceinline__ ulonglong2 ld_valid(const WideArgs &a, uint32_t row, 
 
 // n-ary gates (left fold, inverted kinds invert once at the end) and multiplexer slices.
 template <bool JACOBI>
-__device__ __forceinline__ void eval_wide_gate(const WideArgs &a, uint32_t pb, uint32_t g) {
-    const uint32_t pair = pb * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void eval_wide_gate(const WideArgs &a, uint32_t pb, uint32_t g, uint32_t x = 0xFFFFFFFFu) {
+    const uint32_t pair = x != 0xFFFFFFFFu ? x : pb * blockDim.x + threadIdx.x;
     if (pair >= a.pairs || g >= a.g_end) return;
     const size_t col = (size_t)pair * 2;
     const uint32_t b = a.off[g], e = a.off[g + 1];

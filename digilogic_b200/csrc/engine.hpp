@@ -80,6 +80,8 @@ class Engine {
     int gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid, size_t dst_stride, bool dst_is_device,
                      bool async = false);
     int join_copies();
+    // every lane back to the state of a freshly built simulator (wires and component outputs as at build time); drives are kept
+    void reset_cold() { cold_ = true; frontier_valid_ = false; snap_valid_ = false; }
     int pack_sim_state(const uint32_t *wires, uint32_t n, uint8_t *p0, uint8_t *p1, size_t cap, uint64_t *bit_len);
 
     // info

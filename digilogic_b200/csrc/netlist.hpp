@@ -23,7 +23,7 @@ enum Kind : uint8_t {
 };
 
 // The points of gsim's behaviour that were reconstructed without its source, one switch each, default
-// off = the reading the oracle's defaults take (oracle/gsim_oracle.c go_config).  They are properties of a netlist's
+// off = the reading the CPU checker takes by default (its go_config switches; the product never links it).  They are properties of a netlist's
 // components, set on the builder (b2_builder_set_option) and compiled in.
 enum SemFlags : uint32_t {
     SEM_MUX_Z = 1,   // A.6-4: a multiplexer passes a High-Z selected input on as High-Z (default: as X)

@@ -303,12 +303,14 @@ int b2_pack_sim_state(b2_sim *s, const uint32_t *wires, uint32_t n, uint8_t *pla
  * Batch runner and multi-GPU gather (no reference counterpart: gsim runs one stimulus vector per Simulator::run_sim,
  * crates/digilogic_gsim/src/lib.rs:216-219; a batch of L lanes is L such runs of one netlist).
  *
- * b2_batch owns what a host would otherwise script around b2_sim: the tiling of the lanes, `n_slots` wire-state stores that
- * work on alternate tiles, the stimulus source and the destinations of the designated output rows.  For an acyclic
- * single-driver netlist whose inputs are undriven nets and a step budget that covers its depth (the conditions of the
- * levelised path of b2_run_sim_lanes) a whole batch is ONE launch of the persistent level-sweep kernel (csrc/sweep.cuh);
- * every other case (feedback, tri-state nets, registers, drives on gate outputs, max_steps below the depth) runs tile by tile
- * on `n_slots` simulator replicas that share the device copy of the netlist, with exactly the semantics of b2_run_sim_lanes.
+ * b2_batch owns what a host would otherwise script around b2_sim: the tiling of the lanes, `n_slots` simulator replicas
+ * (sharing ONE device copy of the compiled netlist) that work on alternate tiles on their own CUDA streams, the stimulus
+ * source and the destinations of the designated output rows.  Every tile runs with exactly the semantics of
+ * b2_run_sim_lanes (levelised pass replayed from a CUDA graph for an acyclic netlist, unit-delay loop otherwise).
+ * B2_BATCH_OPT_SWEEP selects an alternative engine for acyclic single-driver netlists whose inputs are undriven nets and a
+ * step budget that covers the depth: the persistent level-sweep kernel (csrc/sweep.cuh), one launch per batch, which also
+ * reads page-locked host stimulus in place and stores output rows into peer GPUs itself; on BASELINE config 3 it is 8-15 %
+ * slower than the replicas (profiles/README.md), so it is not the default.
  * Inputs and outputs are 1-bit wires.  All work is queued on the batch's stream; b2_batch_wait blocks.
  * ---------------------------------------------------------------------------------- */
 typedef struct b2_batch b2_batch;
@@ -316,7 +318,7 @@ typedef struct b2_comm b2_comm;   /* an NCCL communicator, one rank per GPU */
 
 typedef struct b2_batch_info {
     uint32_t tile_words, n_slots;
-    uint32_t sweep;            /* 1: the level-sweep kernel serves this netlist; 0: simulator replicas */
+    uint32_t sweep;            /* 1: the level-sweep kernel is selected and serves this netlist; 0: simulator replicas */
     uint32_t tasks_per_pass;   /* sweep: tasks of one tile (after the first run) */
     uint32_t grid_ctas, gates_per_task;
     uint32_t n_ranks, rank, peers_mapped;
@@ -327,7 +329,7 @@ typedef struct b2_batch_info {
 } b2_batch_info;
 
 enum b2_batch_option {
-    B2_BATCH_OPT_SWEEP = 1,       /* default 1; 0: always use the simulator replicas */
+    B2_BATCH_OPT_SWEEP = 1,       /* default 0; 1: the persistent level-sweep kernel where the netlist allows it */
     B2_BATCH_OPT_TASK_ITERS = 2,  /* default 1: 256-thread iterations per gate task of the sweep (tuning) */
     B2_BATCH_OPT_UNROLL = 3,      /* default 4: gates per thread of the one/two-input class in the sweep (2 or 4) */
     B2_BATCH_OPT_CTAS_PER_SM = 4, /* default 0 = as many as fit */
@@ -346,13 +348,18 @@ int b2_batch_set_option(b2_batch *b, int option, int64_t value);
 int b2_batch_get_info(b2_batch *b, b2_batch_info *out);
 
 /* One settle (run_sim(max_steps) on every lane) of lanes [0, 64 * n_words) of the batch, queued on the batch's stream.
+   Every lane is a freshly built simulator (gsim: SimulatorBuilder::build() then one run_sim): the slots are reused from tile to
+   tile, so no state is carried from one run to the next — a clocked sequence over resident lanes is what b2_sim_set_lanes +
+   b2_run_sim_lanes are for.
    Stimulus: generated on the device exactly like b2_fill_stimulus (input i = position in `inputs`, global lane-word
-   lane_word_begin + w), or read from planes [n_inputs][in_stride_words] in device memory or in host memory (page-locked
-   memory is read in place over PCIe by the kernel; pageable memory is page-locked for the duration of the run).
+   lane_word_begin + w), or read from planes [n_inputs][in_stride_words] in device memory or in host memory (copied tile by
+   tile on a copy stream while earlier tiles settle; the sweep engine reads page-locked memory in place over PCIe and
+   page-locks pageable memory for the duration of the run).
    Outputs: planes [n_outputs][out_stride_words], device or host memory, may be NULL when a communicator is bound.
    *_ring_words (0 = none): the planes hold that many words per row and are used as a ring (a multiple of tile_words).
    With a communicator bound, the output rows also go to this rank's share of the gathered planes — on every rank whose
-   planes are mapped (b2_batch_import_gather_handles), stored over NVLink by the task that reads the rows. */
+   planes are mapped (b2_batch_import_gather_handles), stored over NVLink by the kernel that reads the rows of a tile,
+   while the other slots' tiles settle. */
 int b2_batch_run_generated(b2_batch *b, uint64_t seed, int mode, uint64_t lane_word_begin, uint64_t n_words, uint64_t max_steps,
                            uint64_t *out_value, uint64_t *out_valid, size_t out_stride_words, size_t out_ring_words);
 int b2_batch_run_planes(b2_batch *b, const uint64_t *in_value, const uint64_t *in_valid, size_t in_stride_words, size_t in_ring_words,

@@ -64,6 +64,7 @@ int main(void) {
     for (int i = 0; i <= NBITS; i++) outputs[i] = s0 + i;
     b2_batch *bt = NULL;
     CHECK(b2_batch_new(sim, inputs, 2 * NBITS, outputs, NBITS + 1, 32, 2, &bt) == B2_OK);
+    CHECK(b2_batch_set_option(bt, B2_BATCH_OPT_SWEEP, 1) == B2_OK); /* first the level-sweep kernel */
     b2_sim_free(sim); /* the batch keeps the compiled netlist alive */
     b2_builder_free(b);
 

@@ -221,7 +221,7 @@ def test_no_cpu_fallback():
     """Without a CUDA device the engine must refuse, and nothing in the product imports the oracle."""
     for root, _, files in os.walk(os.path.join(ROOT, "digilogic_b200")):
         for f in files:
-            if f.endswith((".py", ".cpp", ".cu", ".hpp", ".h")):
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
                 assert "gsim_oracle" not in src and "bitsliced.c" not in src, f

@@ -41,13 +41,14 @@ def test_sweep_matches_oracle_on_every_wire(tile, slots, iters, unroll):
     assert not sim.info.cyclic
     words = tile * (2 * slots + 1) + (tile // 2 + 1 if tile > 2 else 1)      # short last tile, partial last group
     b = Batch(sim, inputs, all_wires, tile, slots)
+    b.set_option(Batch.OPT_SWEEP, 1)
     b.set_option(Batch.OPT_TASK_ITERS, iters)
     b.set_option(Batch.OPT_UNROLL, unroll)
     ov = np.zeros((nl.n_wires, words), np.uint64)
     om = np.zeros_like(ov)
     b.run_generated(0xABCD, 1, 77, words, 10_000, ov, om)
     assert b.wait() == SimulationRunResult.Ok
-    assert b.info.sweep == 1 and b.info.last_tiles == -(-words // (tile + (tile & 1)))
+    assert b.info.sweep == 1 and b.info.last_tiles == -(-words // b.info.tile_words)
     rv, rm = _oracle_dag(nl, nl.n_wires, inputs, words, 0xABCD, 77, 1)
     assert (ov == rv).all() and (om == rm).all()
     # a second run on the same slots (their rows are reused) with other stimulus
@@ -85,7 +86,8 @@ def test_sweep_equals_levelised_engine_and_replicas():
     assert (gm != ALL1).any(), "4-state stimulus must leave some X outputs"
 
 
-def test_sweep_planes_from_device_pinned_and_pageable_host():
+@pytest.mark.parametrize("sweep", [1, 0])
+def test_planes_from_device_pinned_and_pageable_host(sweep):
     import torch
     gen = netgen.random_dag(n_gates=20_000, depth=20, n_inputs=128, n_outputs=64, seed=5)
     sim = gen.emit(d.SimulatorBuilder()).build()
@@ -94,7 +96,8 @@ def test_sweep_planes_from_device_pinned_and_pageable_host():
     rv, rm = _oracle_dag(gen, gen.n_wires, gen.inputs, words, 99, 0, 1)
     want_v, want_m = rv[gen.outputs], rm[gen.outputs]
     b = Batch(sim, gen.inputs, gen.outputs, tile, 3)
-    # pageable host in, pageable host out (the library page-locks them for the run)
+    b.set_option(Batch.OPT_SWEEP, sweep)
+    # pageable host in, pageable host out (the sweep page-locks them for the run; the replicas stage them)
     ov, om = np.zeros((64, words), np.uint64), np.zeros((64, words), np.uint64)
     b.run_planes(v, m, words, 10_000, ov, om)
     assert b.wait() == SimulationRunResult.Ok
@@ -107,6 +110,7 @@ def test_sweep_planes_from_device_pinned_and_pageable_host():
     b.run_planes(pv, pm, words, 10_000, dv, dm)
     assert b.wait() == SimulationRunResult.Ok
     assert (dv.cpu().numpy().view(np.uint64) == want_v).all() and (dm.cpu().numpy().view(np.uint64) == want_m).all()
+    assert b.info.sweep == sweep
     # device in, pinned host out; odd strides (scalar path)
     gv = torch.zeros((128, words + 1), dtype=torch.int64, device="cuda")
     gm = torch.zeros_like(gv)
@@ -119,8 +123,8 @@ def test_sweep_planes_from_device_pinned_and_pageable_host():
     assert (hv.numpy().view(np.uint64)[:, :words] == want_v).all() and (hm.numpy().view(np.uint64)[:, :words] == want_m).all()
     # rings: the stimulus planes hold one tile group and are re-read, the output ring keeps the last lap
     ring = 2 * tile
-    b.run_planes(v[:, :ring].copy(), m[:, :ring].copy(), 3 * ring, 10_000, ov[:, :ring], om[:, :ring], in_ring_words=ring,
-                 out_ring_words=ring)
+    rv_, rm_ = v[:, :ring].copy(), m[:, :ring].copy()      # (kept alive: the run reads them after the call has returned)
+    b.run_planes(rv_, rm_, 3 * ring, 10_000, ov[:, :ring], om[:, :ring], in_ring_words=ring, out_ring_words=ring)
     assert b.wait() == SimulationRunResult.Ok
     assert (ov[:, :ring] == want_v[:, :ring]).all() and (om[:, :ring] == want_m[:, :ring]).all()
 
@@ -174,6 +178,7 @@ def test_single_rank_comm_gathers_into_own_planes():
     sim = gen.emit(d.SimulatorBuilder()).build()
     words = 64
     b = Batch(sim, gen.inputs, gen.outputs, 32, 2, device=0)
+    b.set_option(Batch.OPT_SWEEP, 1)
     comm = Comm(1, 0, Comm.unique_id(), 0)
     b.bind_comm(comm, words)
     b.run_generated(9, 0, 0, words)          # with a communicator bound, a run ends with b2_batch_gather_outputs
@@ -199,7 +204,7 @@ def test_batch_argument_errors():
         b.run_generated(1, 0, 0, 64, 100, ov, ov.copy(), out_ring_words=24)   # a ring that tiles would straddle
 
 
-def _two_rank_worker(rank, world, port, words_local, map_peers, q):
+def _two_rank_worker(rank, world, port, words_local, map_peers, sweep, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     import torch
@@ -210,6 +215,7 @@ def _two_rank_worker(rank, world, port, words_local, map_peers, q):
     gen = netgen.random_dag(n_gates=20_000, depth=20, n_inputs=128, n_outputs=64, seed=5)
     sim = gen.emit(d.SimulatorBuilder()).build()
     b = Batch(sim, gen.inputs, gen.outputs, 32, 3, device=rank)
+    b.set_option(Batch.OPT_SWEEP, sweep)
     setup_comm(b, words_local, rank, map_peers=map_peers)
     w0, _ = shard_words(words_local * world, world, rank)
     lv = torch.zeros((64, words_local), dtype=torch.int64, device="cuda")
@@ -225,10 +231,10 @@ def _two_rank_worker(rank, world, port, words_local, map_peers, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("map_peers", [True, False])
-def test_two_gpus_gathered_planes_equal_the_unsharded_batch(map_peers):
+@pytest.mark.parametrize("map_peers,sweep", [(True, 0), (False, 0), (True, 1), (False, 1)])
+def test_two_gpus_gathered_planes_equal_the_unsharded_batch(map_peers, sweep):
     """N = 2 on hardware: lane-sharded runs, output rows stored into the peer's planes over NVLink by the sweep kernel
-    (map_peers) or moved by ncclAllGather; both equal torch.distributed's all-gather and the unsharded oracle batch."""
+    (map_peers) or moved by ncclAllGather, on either engine; both equal torch.distributed's all-gather and the unsharded oracle batch."""
     import socket
     import torch
     import torch.multiprocessing as mp
@@ -240,7 +246,7 @@ def test_two_gpus_gathered_planes_equal_the_unsharded_batch(map_peers):
     world, words_local = 2, 96
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_two_rank_worker, args=(r, world, port, words_local, map_peers, q)) for r in range(world)]
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, world, port, words_local, map_peers, sweep, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
