@@ -59,9 +59,12 @@ def auto_tile_words(sim: Simulator, n_words: int, l2_level_bytes: int = 20 << 20
 
 
 def auto_batch_shape(sim: Simulator, n_words: int) -> tuple[int, int]:
-    """(tile_words, n_slots) for the batch runner: `auto_tile_words` and three slots — with three tiles in flight the launch
-    gaps and kernel tails of one tile's level sweep are filled by the others (profiles/README.md: 256 x 3 on config 3)."""
-    return auto_tile_words(sim, n_words), 3
+    """(tile_words, n_slots) for the batch runner: three slots — with three tiles in flight the launch gaps and kernel tails
+    of one tile's level sweep are filled by the others — and a tile small enough that TWO levels of all three slots
+    (gates per level x 16 B x tile_words x 3 x 2) stay in L2: the next level reads the rows a level wrote from L2, and rows
+    that are dead after that are dropped from L2 before they are written back (B2_BATCH_OPT_DISCARD).  Config 3 (5000 gates
+    per level) -> 128 x 3 (measured optimum, profiles/README.md), config 5 (50 000 per level) -> 32 x 3."""
+    return auto_tile_words(sim, n_words, l2_level_bytes=10 << 20), 3
 
 
 class _DeviceArray:
@@ -110,7 +113,7 @@ class Comm:
 class Batch:
     """b2_batch: runs lane batches of one compiled netlist (see include/digilogic_b200.h)."""
 
-    OPT_SWEEP, OPT_TASK_ITERS, OPT_UNROLL, OPT_CTAS_PER_SM, OPT_AUTO_GATHER = 1, 2, 3, 4, 5
+    OPT_SWEEP, OPT_TASK_ITERS, OPT_UNROLL, OPT_CTAS_PER_SM, OPT_AUTO_GATHER, OPT_DISCARD = 1, 2, 3, 4, 5, 6
 
     def __init__(self, sim: Simulator, inputs, outputs, tile_words: int, n_slots: int = 1, device: int | None = None,
                  stream: int | None = None):

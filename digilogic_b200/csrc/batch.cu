@@ -217,6 +217,10 @@ int Batch::set_option(int option, int64_t value) {
             opt_ctas_per_sm_ = (uint32_t)value;
             return B2_OK;
         case BATCH_OPT_AUTO_GATHER: opt_auto_gather_ = value != 0; return B2_OK;
+        case BATCH_OPT_DISCARD:
+            opt_discard_ = value != 0;
+            for (auto &e : replicas_) e->set_discard(opt_discard_, outputs_.data(), (uint32_t)outputs_.size());
+            return B2_OK;
         default: return B2_ERR_INVALID_ARG;
     }
 }
@@ -359,6 +363,7 @@ int Batch::ensure_replicas() {
         revents_.push_back(ev);
         std::unique_ptr<Engine> e(new Engine(share_));
         e->copy_options_from(*proto_);
+        e->set_discard(opt_discard_, outputs_.data(), (uint32_t)outputs_.size());
         if ((rc = e->set_device(device_)) || (rc = e->set_stream(s)) || (rc = e->set_lanes((uint64_t)T_ * 64))) return rc;
         store_bytes_ += e->store_bytes();
         replicas_.push_back(std::move(e));

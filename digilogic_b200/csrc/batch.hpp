@@ -54,7 +54,7 @@ enum BatchOption {
     BATCH_OPT_UNROLL = 3,      // default 4: gates per thread of the one/two-input class (2 or 4)
     BATCH_OPT_CTAS_PER_SM = 4, // default 0 = occupancy limit
     BATCH_OPT_AUTO_GATHER = 5, // default 1: with a communicator bound, every run ends with gather_outputs()
-    BATCH_OPT_LOAD_MODE = 6    // experiment: 0 strong row loads (default), 1 weak L1-no-allocate row loads
+    BATCH_OPT_DISCARD = 6      // default 1: replicas drop rows from L2 once their last reader has run (outputs are kept)
 };
 
 class Batch {
@@ -111,7 +111,7 @@ class Batch {
     // options
     bool opt_sweep_ = false;
     uint32_t opt_iters_ = 1, opt_unroll_ = 4, opt_ctas_per_sm_ = 0;
-    bool opt_auto_gather_ = true;
+    bool opt_auto_gather_ = true, opt_discard_ = true;
     // sweep state
     bool sweep_eligible_ = false, sweep_ready_ = false;
     uint64_t *val_ = nullptr, *vld_ = nullptr;

@@ -16,6 +16,16 @@ __device__ __forceinline__ ulonglong2 ld_stream(const uint64_t *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
     return r;
 }
+// The same load; with `first` the line is inserted into L2 with evict-first priority (a one-off read of a row written long
+// ago must not displace the rows the previous level has just written).  `first` is warp-uniform when a warp sits on one gate.
+__device__ __forceinline__ ulonglong2 ld_stream_hint(const uint64_t *p, uint32_t first, uint64_t policy) {
+    ulonglong2 r;
+    if (first)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(r.x), "=l"(r.y) : "l"(p), "l"(policy));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
 // Coherent variant for code that may run inside the device-side loop, where rows written by other CTAs
 // earlier in the same launch are read back after a grid barrier: .nc data must be read-only for the launch, and
 // a weak ld with L1::no_allocate was observed to return a stale row there (an SM re-reading a row it had read

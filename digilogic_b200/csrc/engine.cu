@@ -80,6 +80,12 @@ struct Eval2Args {
     uint8_t *chg_cur;                 // unit delay: row -> changed in this application (the frontier of the next one)
     const uint32_t *all_valid;        // KV: 1 if every source row of this run is known valid (then every row is)
     uint32_t sem = 0;                 // SemFlags of the netlist (SURVEY.md A.6-4..7 switches)
+    const uint8_t *far = nullptr;     // levelised pass: per gate, bit i = fan-in i was written long ago (L2 evict-first read)
+    // levelised pass with discard: two row ranges whose last reader has run (dead rows of the two levels below): dropped from L2
+    uint32_t disc_begin[2] = {0, 0}, disc_end[2] = {0, 0};
+    // gates [now_begin, now_end) of this launch drive rows that no gate and no output reads: each 128-byte line is dropped
+    // from L2 right after the warp has stored it
+    uint32_t now_begin = 0, now_end = 0;
 };
 
 // Changed-row frontier write: with a whole warp on one gate, one ballot and one byte store.
@@ -100,9 +106,27 @@ __device__ __forceinline__ void mark_changed(uint8_t *chg, uint32_t row, bool ch
 // full two-plane path; the result is bit-identical either way.
 // NIN = 3: three-input gates, ((a op b) op c) with one inversion at the end for NAND/NOR/XNOR.
 template <int U, bool JACOBI, bool KV, int NIN = 2>
-__global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a) {
+__global__ void __launch_bounds__(256, JACOBI ? 2 : ((U == 2 && NIN == 2 && !KV) ? 5 : 3)) k_eval2(const Eval2Args a) {
     const uint32_t pb = blockIdx.x % a.pair_blocks, gb = blockIdx.x / a.pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
+    if (!JACOBI) {
+        // Rows nobody will read again: invalidate their L2 lines without write-back, so they never cost HBM bandwidth (the level
+        // that read them last ran in an earlier launch on this stream).  One 128-byte line per plane per thread and round.
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+            if (a.disc_end[r] > a.disc_begin[r]) {
+                // (by the CTAs that start first: the sooner a dead line is dropped, the likelier it has not been written back yet)
+                const uint64_t lines = (uint64_t)(a.disc_end[r] - a.disc_begin[r]) * (a.stride >> 4);
+                const uint32_t n_cta = min(gridDim.x, 296u);
+                if (blockIdx.x >= n_cta) break;
+                const uint64_t nt = (uint64_t)n_cta * 256;
+                for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.y * blockDim.x + threadIdx.x; i < lines; i += nt) {
+                    const size_t w = (size_t)a.disc_begin[r] * a.stride + i * 16;
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_val + w) : "memory");
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_vld + w) : "memory");
+                }
+            }
+    }
     if (pair >= a.pairs) return;
     const size_t col = (size_t)pair * 2;
     const uint32_t g0 = a.g_begin + gb * (blockDim.y * U) + threadIdx.y;
@@ -110,8 +134,10 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
     // Explicit phases, each a fully unrolled loop over the U gates of this thread, so that every
     // dependent step (indices -> elision flags -> plane words) costs one memory round trip for all
     // U gates together; loads are branch-free (tail gates are clamped, elided planes predicated off).
-    uint32_t f0[U], f1[U], f2[U], kind[U], orow[U];
+    uint32_t f0[U], f1[U], f2[U], kind[U], orow[U], far[U];
     bool live[U];
+    uint64_t pol_first = 0;
+    if (!JACOBI && !KV) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const uint32_t g = g0 + u * blockDim.y;
@@ -122,6 +148,7 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
         f2[u] = NIN == 3 ? a.fan2[gg] : 0;
         kind[u] = a.kind[gg];
         orow[u] = a.row_base + gg;
+        if (!JACOBI && !KV) far[u] = a.far ? a.far[gg] : 0;
     }
     bool k0[U], k1[U], k2[U], act[U];
     bool any_act = false;
@@ -158,14 +185,19 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
             ov[u] = ld_stream_unless(a.in_val + o, skip);
             om[u] = ld_stream_unless(a.in_vld + o, skip);
         } else {
-            av[u] = ld_stream(a.in_val + r0);
-            bv[u] = ld_stream(a.in_val + r1);
+            if (KV) {
+                av[u] = ld_stream(a.in_val + r0);
+                bv[u] = ld_stream(a.in_val + r1);
+            } else {
+                av[u] = ld_stream_hint(a.in_val + r0, far[u] & 1, pol_first);
+                bv[u] = ld_stream_hint(a.in_val + r1, far[u] & 2, pol_first);
+            }
             if (KV) {
                 am[u] = ld_stream_unless(a.in_vld + r0, k0[u]);
                 bm[u] = ld_stream_unless(a.in_vld + r1, k1[u]);
             } else {
-                am[u] = ld_stream(a.in_vld + r0);
-                bm[u] = ld_stream(a.in_vld + r1);
+                am[u] = ld_stream_hint(a.in_vld + r0, far[u] & 1, pol_first);
+                bm[u] = ld_stream_hint(a.in_vld + r1, far[u] & 2, pol_first);
             }
         }
     }
@@ -193,6 +225,10 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : 3) k_eval2(const Eval2Args a
             const bool okv = KV && k0[u] && k1[u] && k2[u];
             st_pair(a.out_val + o, rv);
             if (!okv) st_pair(a.out_vld + o, rm);
+            if (!JACOBI && !KV && (pair & 7) == 0 && orow[u] - a.row_base >= a.now_begin && orow[u] - a.row_base < a.now_end) {
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_val + o) : "memory");
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_vld + o) : "memory");
+            }
             if (KV && !allv && pb == 0 && threadIdx.x == 0) a.kv[orow[u]] = okv ? 1 : 0;
             if (JACOBI) {
                 const uint64_t ex = (rv.x ^ ov[u].x) | (rm.x ^ om[u].x), ey = (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
@@ -1222,6 +1258,10 @@ void Engine::copy_options_from(const Engine &o) {
     opt_budget_inclusive_ = o.opt_budget_inclusive_;
     opt_u_ = o.opt_u_;
     opt_period2_ = o.opt_period2_;
+    opt_l2_hints_ = o.opt_l2_hints_;
+    opt_discard_ = o.opt_discard_;
+    disc_short_ = o.disc_short_;
+    disc_never_ = o.disc_never_;
     opt_flags_ = o.opt_flags_;
 }
 
@@ -1232,6 +1272,7 @@ DeviceNet::~DeviceNet() {
     cudaFree(fan1);
     cudaFree(fan2);
     cudaFree(kind2);
+    cudaFree(far2);
     cudaFree(wide_off);
     cudaFree(wide_in);
     cudaFree(wide_kind);
@@ -1258,7 +1299,7 @@ std::shared_ptr<DeviceNet> NetShare::acquire(int device, int &rc) {
     auto d = std::make_shared<DeviceNet>();
     d->device = device;  // from here on the destructor frees whatever was allocated
     if ((rc = upload(&d->fan0, net.fan0)) || (rc = upload(&d->fan1, net.fan1)) || (rc = upload(&d->fan2, net.fan2)) ||
-        (rc = upload(&d->kind2, net.kind2)) || (rc = upload(&d->wide_off, net.wide_off)) || (rc = upload(&d->wide_in, net.wide_in)) ||
+        (rc = upload(&d->kind2, net.kind2)) || (rc = upload(&d->far2, net.far2)) || (rc = upload(&d->wide_off, net.wide_off)) || (rc = upload(&d->wide_in, net.wide_in)) ||
         (rc = upload(&d->wide_kind, net.wide_kind)) || (rc = upload(&d->wide_nsel, net.wide_nsel)) ||
         (rc = upload(&d->res_off, net.res_off)) || (rc = upload(&d->res_in, net.res_in)) || (rc = upload(&d->levels, net.levels)))
         return nullptr;
@@ -1430,7 +1471,7 @@ int Engine::ensure_device() {
     if (!dnet_) {  // one copy of the netlist per device, shared with every replica of this build
         dnet_ = share_->acquire(device_, rc);
         if (!dnet_) return rc;
-        d_fan0_ = dnet_->fan0; d_fan1_ = dnet_->fan1; d_fan2_ = dnet_->fan2; d_kind2_ = dnet_->kind2;
+        d_fan0_ = dnet_->fan0; d_fan1_ = dnet_->fan1; d_fan2_ = dnet_->fan2; d_kind2_ = dnet_->kind2; d_far2_ = dnet_->far2;
         d_wide_off_ = dnet_->wide_off; d_wide_in_ = dnet_->wide_in; d_wide_kind_ = dnet_->wide_kind; d_wide_nsel_ = dnet_->wide_nsel;
         d_res_off_ = dnet_->res_off; d_res_in_ = dnet_->res_in; d_levels_ = dnet_->levels;
     }
@@ -1968,7 +2009,7 @@ int Engine::run_levelised(bool async) {
     // CUDA graph and replayed per run, which takes the per-launch CPU cost and most of the
     // launch-to-launch gap out of small tiles (hundreds of levels of a few microseconds each).
     const bool want_graph = opt_graph_ && net_.levels.size() >= 8;
-    const uint64_t gkey = ((uint64_t)(uintptr_t)V) ^ ((uint64_t)stride_ << 1) ^ (kv ? 1u : 0u);
+    const uint64_t gkey = ((uint64_t)(uintptr_t)V) ^ ((uint64_t)stride_ << 2) ^ (kv ? 1u : 0u) ^ (opt_l2_hints_ ? 2u : 0u) ^ (opt_discard_ ? 8u : 0u);
     if (want_graph && level_graph_exec_ && level_graph_key_ == gkey) {
         CU_TRY(cudaGraphLaunch((cudaGraphExec_t)level_graph_exec_, ST));
         g_launches.fetch_add(level_graph_nodes_, std::memory_order_relaxed);
@@ -1988,6 +2029,18 @@ int Engine::run_levelised(bool async) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
                             sh.pair_blocks, d_kv_, nullptr, nullptr, d_all_valid_};
                 a.sem = net_.sem_flags;
+                a.far = opt_l2_hints_ ? d_far2_ : nullptr;
+                if (opt_discard_ && !kv && stride_ % 16 == 0) {
+                    const size_t li = (size_t)(&lv - net_.levels.data());
+                    if (li < disc_never_.size() && stride_ >= 16) {  // rows of this level that nobody reads (gate indices)
+                        a.now_begin = disc_never_[li].begin - net_.n_src;
+                        a.now_end = disc_never_[li].end - net_.n_src;
+                    }
+                    if (li >= 2 && li - 2 < disc_short_.size()) {  // rows two levels below whose only readers were the level below
+                        a.disc_begin[1] = disc_short_[li - 2].begin;
+                        a.disc_end[1] = disc_short_[li - 2].end;
+                    }
+                }
                 // U gates per thread: 4 when the level still fills the machine several times over, else 2
                 // (more, smaller CTAs: a level of a small tile is only a wave or two of work)
                 const uint32_t n_g = lv.g2_end - lv.g2_begin;
@@ -2569,6 +2622,35 @@ int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uin
     CU_TRY(cudaEventRecord(EV(ev_out_free_), COUT));
     if (!async) CU_TRY(cudaStreamSynchronize(COUT));
     return B2_OK;
+}
+
+void Engine::set_discard(bool on, const uint32_t *keep_wires, uint32_t n) {
+    opt_discard_ = on && !net_.cyclic;
+    level_graph_key_ = 0;
+    disc_short_.clear();
+    disc_never_.clear();
+    if (!opt_discard_) return;
+    std::vector<uint32_t> keep;
+    for (uint32_t i = 0; i < n; i++)
+        if (keep_wires[i] < net_.n_wires())
+            for (uint32_t j = 0; j < net_.width[keep_wires[i]]; j++) keep.push_back(net_.row_of_bit[net_.bit_off[keep_wires[i]] + j]);
+    std::sort(keep.begin(), keep.end());
+    // the largest stretch of [b, e) without a kept row
+    auto largest_gap = [&](uint32_t b, uint32_t e) -> RowRange {
+        RowRange best{b, b};
+        uint32_t start = b;
+        auto it = std::lower_bound(keep.begin(), keep.end(), b);
+        for (; it != keep.end() && *it < e; ++it) {
+            if (*it - start > best.end - best.begin) best = RowRange{start, *it};
+            start = *it + 1;
+        }
+        if (e - start > best.end - best.begin) best = RowRange{start, e};
+        return best;
+    };
+    for (const Level &lv : net_.levels) {
+        disc_short_.push_back(largest_gap(net_.n_src + lv.g2_short, net_.n_src + lv.g2_never));
+        disc_never_.push_back(largest_gap(net_.n_src + lv.g2_never, net_.n_src + lv.g2_end));
+    }
 }
 
 // The main stream waits for the last asynchronous read-back (gather_wires(..., async)) of this simulator.

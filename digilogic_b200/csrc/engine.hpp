@@ -31,7 +31,7 @@ struct LoopResult;
 struct DeviceNet {
     int device = -1;
     uint32_t *fan0 = nullptr, *fan1 = nullptr, *fan2 = nullptr, *wide_off = nullptr, *wide_in = nullptr;
-    uint8_t *kind2 = nullptr, *wide_kind = nullptr, *wide_nsel = nullptr;
+    uint8_t *kind2 = nullptr, *far2 = nullptr, *wide_kind = nullptr, *wide_nsel = nullptr;
     uint32_t *res_off = nullptr, *res_in = nullptr;
     Level *levels = nullptr;
     ~DeviceNet();
@@ -94,6 +94,11 @@ class Engine {
     void set_use_resident(bool on) { use_resident_ = on; }
     void set_valid_elision(bool on) { opt_elision_ = on; }
     void set_use_graph(bool on) { opt_graph_ = on; }
+    void set_l2_hints(bool on) { opt_l2_hints_ = on; level_graph_key_ = 0; }
+    // Levelised runs of this simulator need not keep rows after their last reader, except the rows of `keep_wires` (the batch
+    // runner's designated outputs): dead rows are dropped from L2 (discard.global.L2) before they are written back to HBM.
+    // After such a run only the kept wires (and rows read two or more levels above their gate) may be read back.
+    void set_discard(bool on, const uint32_t *keep_wires, uint32_t n);
     void set_budget_inclusive(bool on) { opt_budget_inclusive_ = on; }
     void set_use_frontier(bool on) { opt_frontier_ = on; frontier_valid_ = false; }
     void set_device_loop(bool on) { opt_device_loop_ = on; }
@@ -137,7 +142,7 @@ class Engine {
 
     // netlist on the device (aliases into dnet_, which owns them)
     uint32_t *d_fan0_ = nullptr, *d_fan1_ = nullptr, *d_fan2_ = nullptr, *d_wide_off_ = nullptr, *d_wide_in_ = nullptr;
-    uint8_t *d_kind2_ = nullptr, *d_wide_kind_ = nullptr, *d_wide_nsel_ = nullptr;
+    uint8_t *d_kind2_ = nullptr, *d_far2_ = nullptr, *d_wide_kind_ = nullptr, *d_wide_nsel_ = nullptr;
 
     // wire-state store: two buffers (second one only for unit-delay runs), separate planes
     uint64_t *val_[2] = {nullptr, nullptr}, *vld_[2] = {nullptr, nullptr};
@@ -217,6 +222,10 @@ class Engine {
     bool opt_lenient_ = false;
     bool opt_budget_inclusive_ = false;  // SURVEY.md A.6-1 switch: `steps >= max_steps` instead of `>`
     uint32_t opt_u_ = 0;  // 0 = automatic gates-per-thread choice in k_eval2
+    bool opt_discard_ = false;
+    struct RowRange { uint32_t begin, end; };
+    std::vector<RowRange> disc_short_, disc_never_;  // per level: rows of the one/two-input class that may be dropped
+    bool opt_l2_hints_ = false;  // levelised pass: evict-first hint on fan-ins produced long ago (Compiled::far2)
     bool opt_period2_ = true;   // unit-delay loops fast-forward over an exact period-2 oscillation
     uint32_t opt_flags_ = 0;    // SemFlags: the reconstructed points of SURVEY.md A.6-4..7, one bit each
     bool use_resident_ = true, resident_attr_set_ = false;

@@ -339,10 +339,22 @@ void compile(const Builder &b, Compiled &c) {
         return k == K_MUX || k == K_REG || k == K_ADD || k == K_SUB || gates[g].n_in > 3 ? 2 : (gates[g].n_in == 3 ? 1 : 0);
     };
     auto is_wide = [&](uint32_t g) { return cls(g) == 2; };
+    // acyclic: lifetime class of the row of gate g — 0: read two or more levels above, 1: last reader in the level directly
+    // above, 2: no reader
+    std::vector<uint8_t> short_lived(G, 0);
+    if (!c.cyclic)
+        for (uint32_t g = 0; g < G; g++) {
+            const uint32_t bn = gates[g].out;
+            uint32_t last = 0;
+            if (bn != NO_NET && driver[bn] == g)
+                for (uint32_t k = cons_off[bn]; k < cons_off[bn + 1]; k++) last = std::max(last, gates[cons[k]].level);
+            short_lived[g] = last == 0 ? 2 : (last <= gates[g].level + 1 ? 1 : 0);
+        }
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
         const int wx = cls(x), wy = cls(y);
         if (wx != wy) return wx < wy;
         if (gates[x].level != gates[y].level) return gates[x].level < gates[y].level;
+        if (short_lived[x] != short_lived[y]) return short_lived[x] < short_lived[y];
         return gates[x].kind < gates[y].kind;
     });
 
@@ -387,8 +399,17 @@ void compile(const Builder &b, Compiled &c) {
     c.fan2.resize(n2);
     c.kind2.resize(n2);
     c.n_two = 0;
+    c.far2.assign(n2, 0);
+    // level of the producer of a fan-in entry: 0 for a source
+    auto level_of = [&](uint32_t entry) -> uint32_t {
+        if (entry & HIDDEN) return gates[entry & ~HIDDEN].level;
+        return driver[entry] == NONE ? 0u : gates[driver[entry]].level;
+    };
     for (uint32_t k = 0; k < n2; k++) {
         const BitGate &g = gates[order[k]];
+        if (!c.cyclic)
+            for (uint32_t i = 0; i < g.n_in && i < 3; i++)
+                if (level_of(bin[g.in_off + i]) + 1 < g.level) c.far2[k] |= (uint8_t)(1u << i);
         c.kind2[k] = g.kind;
         c.fan0[k] = row_of(bin[g.in_off]);
         c.fan1[k] = g.n_in > 1 ? row_of(bin[g.in_off + 1]) : c.fan0[k];
@@ -412,26 +433,26 @@ void compile(const Builder &b, Compiled &c) {
     // ---- level table
     c.levels.clear();
     const uint32_t n_levels = c.cyclic ? (G ? 1u : 0u) : depth;
-    c.levels.assign(n_levels, Level{0, 0, 0, 0, 0, 0});
+    c.levels.assign(n_levels, Level{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
     {
-        uint32_t k = 0;
-        for (uint32_t l = 1; l <= n_levels; l++) {
-            c.levels[l - 1].g2_begin = k;
-            while (k < c.n_two && gates[order[k]].level == l) k++;
-            c.levels[l - 1].g2_end = k;
-        }
-        k = c.n_two;
-        for (uint32_t l = 1; l <= n_levels; l++) {
-            c.levels[l - 1].g3_begin = k;
-            while (k < n2 && gates[order[k]].level == l) k++;
-            c.levels[l - 1].g3_end = k;
-        }
-        k = 0;
-        for (uint32_t l = 1; l <= n_levels; l++) {
-            c.levels[l - 1].wide_begin = k;
-            while (k < nw && gates[order[n2 + k]].level == l) k++;
-            c.levels[l - 1].wide_end = k;
-        }
+        // one class: [begin, end) of every level, and the first short-lived gate inside it
+        auto ranges = [&](uint32_t first, uint32_t last, uint32_t base, uint32_t Level::*begin, uint32_t Level::*end,
+                          uint32_t Level::*shrt, uint32_t Level::*never) {
+            uint32_t k = first;
+            for (uint32_t l = 1; l <= n_levels; l++) {
+                Level &lv = c.levels[l - 1];
+                lv.*begin = k - base;
+                while (k < last && gates[order[k]].level == l && short_lived[order[k]] == 0) k++;
+                lv.*shrt = k - base;
+                while (k < last && gates[order[k]].level == l && short_lived[order[k]] == 1) k++;
+                lv.*never = k - base;
+                while (k < last && gates[order[k]].level == l) k++;
+                lv.*end = k - base;
+            }
+        };
+        ranges(0, c.n_two, 0, &Level::g2_begin, &Level::g2_end, &Level::g2_short, &Level::g2_never);
+        ranges(c.n_two, n2, 0, &Level::g3_begin, &Level::g3_end, &Level::g3_short, &Level::g3_never);
+        ranges(n2, G, n2, &Level::wide_begin, &Level::wide_end, &Level::wide_short, &Level::wide_never);
     }
 }
 

@@ -70,6 +70,12 @@ struct Builder {
 //   row(fast gate i) = n_src + i,   row(wide gate j) = n_src + n_g2 + n_g3 + j.
 struct Level {
     uint32_t g2_begin, g2_end, g3_begin, g3_end, wide_begin, wide_end;
+    // Inside a level the gates of a class are ordered by the lifetime of their rows: [begin, short) are read two or more
+    // levels above, [short, never) only by the level directly above, [never, end) by no gate at all.  Once their last
+    // reader has run, such rows are dead to a level sweep; the batch runner uses this to drop them from L2 instead of letting
+    // them be written to HBM (Engine::set_discard).
+    uint32_t g2_short, g3_short, wide_short;
+    uint32_t g2_never, g3_never, wide_never;
 };
 
 struct Compiled {
@@ -83,6 +89,10 @@ struct Compiled {
     // fast gates (one to three inputs), in row order: n_g2 one/two-input gates, then n_g3 three-input gates
     std::vector<uint32_t> fan0, fan1, fan2;  // store rows (fan2 = fan0 for gates with fewer inputs)
     std::vector<uint8_t> kind2;
+    // acyclic netlists: bit i set = fan-in i was produced more than one level below the gate (or is a source below level 1),
+    // i.e. long ago in a level sweep: the kernels read it with an L2 evict-first hint, so that the stream of such one-off
+    // reads does not push the rows the previous level has just written out of L2
+    std::vector<uint8_t> far2;
     uint32_t n_two = 0;
     // wide gates (n-ary, mux slices), CSR over store rows; mux: first n_sel entries are select bits
     std::vector<uint32_t> wide_off, wide_in;

@@ -214,6 +214,9 @@ enum b2_option {
                                   High-Z" (SURVEY.md A.6-2); 1 selects the alternative reading in which two valid operands that
                                   agree do not conflict — the oracle's `conflict_needs_disagree` switch, for the day a run of real
                                   gsim decides.  Refused (InvalidArgument) for a netlist with two plain gates on one net. */
+    B2_OPT_L2_HINTS = 9,       /* default 1.  Levelised pass: fan-in rows produced more than one level below the reading gate are
+                                  loaded with an L2 evict-first hint (createpolicy + ld.L2::cache_hint), so that these one-off reads
+                                  do not displace the rows the previous level has just written and the next kernel re-reads. */
     B2_OPT_DEVICE_LOOP = 7     /* default 1.  Unit-delay runs in HBM execute the whole run_sim loop in one cooperative launch
                                   (grid barriers between the phases of an application, stop decision on the device);
                                   0: one set of launches per application, stop decision on the host. */
@@ -333,6 +336,10 @@ enum b2_batch_option {
     B2_BATCH_OPT_TASK_ITERS = 2,  /* default 1: 256-thread iterations per gate task of the sweep (tuning) */
     B2_BATCH_OPT_UNROLL = 3,      /* default 4: gates per thread of the one/two-input class in the sweep (2 or 4) */
     B2_BATCH_OPT_CTAS_PER_SM = 4, /* default 0 = as many as fit */
+    B2_BATCH_OPT_DISCARD = 6,     /* default 1: a batch run only hands out the designated output rows, so the replicas do not keep a
+                                     row after its last reader: rows read by nobody, or only by the level directly above, are
+                                     dropped from L2 (discard.global.L2) by a later level's kernel before they are written back to
+                                     HBM.  Every gate is still evaluated and its row written; outputs are bit-identical (tested). */
     B2_BATCH_OPT_AUTO_GATHER = 5  /* default 1: with a communicator bound every run ends with b2_batch_gather_outputs, so a
                                      step is one call; 0: the host calls it */
 };

@@ -98,11 +98,32 @@ int main(int argc, char **argv) {
             uint32_t k2 = 0, k3 = c.n_two, kw = 0;
             for (const Level &lv : c.levels) {
                 REQUIRE(lv.g2_begin == k2 && lv.g2_end >= k2 && lv.g3_begin == k3 && lv.g3_end >= k3 && lv.wide_begin == kw);
+                REQUIRE(lv.g2_short >= lv.g2_begin && lv.g2_short <= lv.g2_end && lv.g3_short >= lv.g3_begin && lv.g3_short <= lv.g3_end);
+                REQUIRE(lv.wide_short >= lv.wide_begin && lv.wide_short <= lv.wide_end);
+                REQUIRE(lv.g2_never >= lv.g2_short && lv.g2_never <= lv.g2_end && lv.g3_never >= lv.g3_short && lv.g3_never <= lv.g3_end);
+                REQUIRE(lv.wide_never >= lv.wide_short && lv.wide_never <= lv.wide_end);
                 k2 = lv.g2_end; k3 = lv.g3_end; kw = lv.wide_end;
                 // a gate only reads rows of earlier levels (or sources)
                 for (uint32_t g = lv.g2_begin; g < lv.g2_end; g++) REQUIRE(c.fan0[g] < c.n_src + lv.g2_begin || c.fan0[g] >= c.n_src + c.n_two);
             }
             REQUIRE(k2 == c.n_two && k3 == c.n_fast() && kw == c.n_wide());
+            // short-lived rows: nobody more than one level above reads them (the batch runner drops them from L2 after that level)
+            std::vector<uint32_t> row_level(c.n_rows, 0), row_short(c.n_rows, 0), row_never(c.n_rows, 0);
+            for (uint32_t l = 0; l < c.levels.size(); l++) {
+                const Level &lv = c.levels[l];
+                for (uint32_t g = lv.g2_begin; g < lv.g2_end; g++) { row_level[c.n_src + g] = l + 1; row_short[c.n_src + g] = g >= lv.g2_short; row_never[c.n_src + g] = g >= lv.g2_never; }
+                for (uint32_t g = lv.g3_begin; g < lv.g3_end; g++) { row_level[c.n_src + g] = l + 1; row_short[c.n_src + g] = g >= lv.g3_short; row_never[c.n_src + g] = g >= lv.g3_never; }
+                for (uint32_t g = lv.wide_begin; g < lv.wide_end; g++) {
+                    row_level[c.n_src + c.n_fast() + g] = l + 1;
+                    row_short[c.n_src + c.n_fast() + g] = g >= lv.wide_short;
+                    row_never[c.n_src + c.n_fast() + g] = g >= lv.wide_never;
+                }
+            }
+            auto reads_ok = [&](uint32_t reader_row, uint32_t r) { return !row_never[r] && (!row_short[r] || row_level[reader_row] <= row_level[r] + 1); };
+            for (uint32_t g = 0; g < c.n_fast(); g++)
+                REQUIRE(reads_ok(c.n_src + g, c.fan0[g]) && reads_ok(c.n_src + g, c.fan1[g]) && reads_ok(c.n_src + g, c.fan2[g]));
+            for (uint32_t g = 0; g < c.n_wide(); g++)
+                for (uint32_t i = c.wide_off[g]; i < c.wide_off[g + 1]; i++) REQUIRE(reads_ok(c.n_src + c.n_fast() + g, c.wide_in[i]));
         } else {
             REQUIRE(c.levels.size() <= 1);
         }
