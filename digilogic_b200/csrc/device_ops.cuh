@@ -143,6 +143,7 @@ struct WideArgs {
     uint8_t *chg_cur;
     const uint32_t *all_valid;  // as in Eval2Args (nullable)
     uint32_t sem = 0;           // SemFlags of the netlist
+    uint32_t *p2diff = nullptr; // device-side loop: period-2 detector (see Eval2Args)
 };
 
 __device__ __forceinline__ ulonglong2 ld_valid(const WideArgs &a, uint32_t row, size_t col) {
@@ -254,6 +255,10 @@ __device__ __forceinline__ void eval_wide_gate(const WideArgs &a, uint32_t pb, u
         if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
         if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
         if (a.chg_cur && (dx | dy)) a.chg_cur[a.row_base + g] = 1;
+        if (a.p2diff) {
+            const ulonglong2 pv = ld_row(a.out_val + o), pm = ld_row(a.out_vld + o);
+            if ((rv.x ^ pv.x) | (rm.x ^ pm.x) | (rv.y ^ pv.y) | (rm.y ^ pm.y)) *a.p2diff = 1;
+        }
     }
     st_pair(a.out_val + o, rv);
     if (a.kv && *a.all_valid) return;  // valid fan-ins give a valid output: its plane stays elided

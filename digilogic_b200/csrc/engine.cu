@@ -86,6 +86,9 @@ struct Eval2Args {
     // gates [now_begin, now_end) of this launch drive rows that no gate and no output reads: each 128-byte line is dropped
     // from L2 right after the warp has stored it
     uint32_t now_begin = 0, now_end = 0;
+    // device-side loop: set to 1 when a row written by this application differs from what the buffer held (the state two
+    // applications ago) — the period-2 detector of k_unit_delay_loop; nullptr elsewhere
+    uint32_t *p2diff = nullptr;
 };
 
 // Changed-row frontier write: with a whole warp on one gate, one ballot and one byte store.
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(256) k_frontier_scan(const uint32_t *fan0, con
 // other buffer up to date (32 B per row-word instead of a full re-evaluation).
 __device__ __forceinline__ void copy_list_body(const uint32_t *rows, const uint32_t *count, const uint64_t *a_val,
                                                const uint64_t *a_vld, uint64_t *b_val, uint64_t *b_vld, uint32_t stride, uint32_t pairs,
-                                               uint32_t pair_blocks, uint32_t bid, uint32_t nblk) {
+                                               uint32_t pair_blocks, uint32_t bid, uint32_t nblk, uint32_t *p2diff = nullptr) {
     const uint32_t n = *count;
     const uint32_t pb = bid % pair_blocks, rbi = bid / pair_blocks, rbs = nblk / pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
@@ -316,6 +319,10 @@ __device__ __forceinline__ void copy_list_body(const uint32_t *rows, const uint3
     for (uint32_t i = rbi * blockDim.y + threadIdx.y; i < n; i += rbs * blockDim.y) {
         const size_t o = (size_t)rows[i] * stride + (size_t)pair * 2;
         const ulonglong2 v = ld_row(a_val + o), m = ld_row(a_vld + o);
+        if (p2diff) {
+            const ulonglong2 pv = ld_row(b_val + o), pm = ld_row(b_vld + o);
+            if ((v.x ^ pv.x) | (m.x ^ pm.x) | (v.y ^ pv.y) | (m.y ^ pm.y)) *p2diff = 1;
+        }
         st_pair(b_val + o, v);
         st_pair(b_vld + o, m);
     }
@@ -338,7 +345,7 @@ __device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *
     if (pair >= a.pairs || n == 0) return;
     const size_t col = (size_t)pair * 2;
     const uint32_t per = blockDim.y * U;
-    uint64_t dx = 0, dy = 0;
+    uint64_t dx = 0, dy = 0, d2 = 0;
     // list entries of the next iteration are fetched while the plane words of this one are in flight
     uint4 nxt[U];
 #pragma unroll
@@ -396,6 +403,10 @@ __device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *
             bool ch = false;
             if (live[u]) {
                 const size_t o = (size_t)orow[u] * a.stride + col;
+                if (a.p2diff) {  // what this buffer held = the row two applications ago
+                    const ulonglong2 pv = ld_row(a.out_val + o), pm = ld_row(a.out_vld + o);
+                    d2 |= (rv.x ^ pv.x) | (rm.x ^ pm.x) | (rv.y ^ pv.y) | (rm.y ^ pm.y);
+                }
                 st_pair(a.out_val + o, rv);
                 st_pair(a.out_vld + o, rm);
                 const uint64_t ex = (rv.x ^ ov[u].x) | (rm.x ^ om[u].x), ey = (rv.y ^ ov[u].y) | (rm.y ^ om[u].y);
@@ -415,6 +426,7 @@ __device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *
     }
     if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
     if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
+    if (d2) *a.p2diff = 1;
 }
 
 template <int NIN>
@@ -576,6 +588,7 @@ struct ResolveArgs {
     uint32_t n_res, row_base, stride, pairs, pair_blocks;
     int cold;
     int lenient;  // A.6-2 alternative: agreeing valid drivers do not conflict
+    uint32_t *p2diff = nullptr;  // as in Eval2Args
 };
 
 __device__ __forceinline__ void resolve_body(const ResolveArgs &a, uint32_t pb, uint32_t rb) {
@@ -610,6 +623,10 @@ __device__ __forceinline__ void resolve_body(const ResolveArgs &a, uint32_t pb, 
     }
     if (cx) atomicOr((unsigned long long *)&a.conf[col], (unsigned long long)cx);
     if (cy) atomicOr((unsigned long long *)&a.conf[col + 1], (unsigned long long)cy);
+    if (a.p2diff) {
+        const ulonglong2 pv = ld_row(a.b_val + o), pm = ld_row(a.b_vld + o);
+        if ((v.x ^ pv.x) | (m.x ^ pm.x) | (v.y ^ pv.y) | (m.y ^ pm.y)) *a.p2diff = 1;
+    }
     st_pair(a.b_val + o, v);
     st_pair(a.b_vld + o, m);
 }
@@ -787,6 +804,7 @@ struct LoopResult {
     uint32_t any_conflict, any_unsettled;
     uint32_t bailed;  // 1: stopped before application k+1 because its work list is too long for this kernel; the host loop goes on
     uint32_t pad;
+    uint64_t skipped;  // applications fast-forwarded over (exact period-2 oscillation), included in k
 };
 
 struct LoopArgs {
@@ -808,6 +826,7 @@ struct LoopArgs {
     uint64_t bail_row_words;  // hand back to the host loop when listed gates x row words exceeds this
     int32_t cur, chg_w, frontier_valid;
     uint32_t sem;  // SemFlags of the netlist
+    uint32_t *p2;  // period-2 detector, kFlagSlots words (slot = application % kFlagSlots), zero on entry; nullptr = off
 };
 
 __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
@@ -815,7 +834,7 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
     const uint32_t bid = blockIdx.x, nblk = gridDim.x;
     const uint32_t pb = bid % a.pair_blocks, gbi = bid / a.pair_blocks, gbs = nblk / a.pair_blocks;
     const uint32_t lt = threadIdx.y * blockDim.x + threadIdx.x;  // linear thread id: warps are 32 consecutive ones
-    uint64_t k = a.k0;
+    uint64_t k = a.k0, skipped = 0;
     int cur = a.cur, cw = a.chg_w;
     bool bailed = false;
     const uint64_t first_k = k + 1;
@@ -837,6 +856,7 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
         uint8_t *chg_cur = a.chg[cw];
         const uint32_t *counts = a.cnt + 4 * (k & 1);
         RunFlags *flags = a.flags + (k % 8);
+        uint32_t *p2 = a.p2 ? a.p2 + (k % 8) : nullptr;
         if (k > first_k) {  // a long work list is better served by the separate, fully occupied kernels
             const uint64_t listed = (uint64_t)counts[0] + counts[1] + counts[2] + counts[3];
             if (listed * a.stride > a.bail_row_words) {
@@ -857,13 +877,15 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
             Eval2Args e{a.fan0, a.fan1, a.fan2, a.kind2, AV, AM, BV, BM, a.changed, 0, a.n_fast, a.n_src, a.stride, a.pairs,
                         a.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
             e.sem = a.sem;
+            e.p2diff = p2;
             if (a.n_g2) eval_list_body<2>(e, a.list2, counts, bid, nblk);
             if (a.n_fast > a.n_g2) eval_list_body<3>(e, a.list3, counts + 1, bid, nblk);
-            copy_list_body(a.listc, counts + 2, AV, AM, BV, BM, a.stride, a.pairs, a.pair_blocks, bid, nblk);
+            copy_list_body(a.listc, counts + 2, AV, AM, BV, BM, a.stride, a.pairs, a.pair_blocks, bid, nblk, p2);
             if (a.n_wide) {
                 WideArgs w = a.wide;
                 w.in_val = AV; w.in_vld = AM; w.out_val = BV; w.out_vld = BM;
                 w.chg_prev = nullptr; w.chg_cur = chg_cur;
+                w.p2diff = p2;
                 eval_wide_list_body(w, a.listw, counts + 3, bid, nblk);
             }
         }
@@ -872,6 +894,7 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
             ResolveArgs r = a.res;
             r.a_val = AV; r.a_vld = AM; r.b_val = BV; r.b_vld = BM;
             r.chg_cur = chg_cur;
+            r.p2diff = p2;
             for (uint32_t rb = gbi; rb * blockDim.y < a.n_res; rb += gbs) resolve_body(r, pb, rb);
             grid.sync();
         }
@@ -890,6 +913,7 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
             nf->any_live = 0;
             nf->any_conflict = 0;
             nf->any_unsettled = 0;
+            if (a.p2) a.p2[(k + 1) % 8] = 0;
         }
         if (!is_last)
             for (uint32_t base = bid * 256; base < a.n_fast; base += nblk * 256)
@@ -905,6 +929,30 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
         if (is_last) break;  // check-only application: the state stays W_{N+1}
         cur ^= 1;
         if (!any_live) break;
+        // Exact period-2 oscillation: every row this application wrote equals what its buffer held, i.e. W_k = W_{k-2} on all
+        // rows (rows not listed are equal by the frontier invariant) and the drives have been in both buffers since the
+        // second application of this launch.  G is a function of the state alone, so W_{k+2j} = W_k and W_{k+2j+1} = W_{k-1}
+        // for all j, with the conflicts, live lanes, changed-row flags and work lists of applications k-1 and k repeating:
+        // jumping ahead by an even number of applications is the identity on everything this loop keeps.  Only the flag slots
+        // indexed by the application number have to be brought along.
+        if (p2 && k >= first_k + 2 && *(volatile uint32_t *)p2 == 0) {
+            const uint64_t jump = ((a.last - 1 - k) / 2) * 2;
+            if (jump >= 8) {
+                const uint64_t k2 = k + jump;
+                if (bid == 0 && lt == 0) {
+                    RunFlags *dst = a.flags + (k2 % 8), *nf = a.flags + ((k2 + 1) % 8);
+                    *dst = *flags;  // (conflict flags are cumulative: the final read finds them in the slot of the last application)
+                    nf->any_live = 0;
+                    nf->any_conflict = 0;
+                    nf->any_unsettled = 0;
+                    a.p2[k2 % 8] = 0;
+                    a.p2[(k2 + 1) % 8] = 0;
+                }
+                skipped += jump;
+                k = k2;
+                grid.sync();
+            }
+        }
     }
     if (bid == 0 && lt == 0) {
         const RunFlags *flags = a.flags + (k % 8);
@@ -914,6 +962,7 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
         a.result->any_conflict = *(volatile uint32_t *)&flags->any_conflict;
         a.result->any_unsettled = *(volatile uint32_t *)&flags->any_unsettled;
         a.result->bailed = bailed ? 1u : 0u;
+        a.result->skipped = skipped;
     }
 }
 
@@ -956,6 +1005,7 @@ struct ResidentArgs {
     uint8_t *snap0, *snap1;
     uint32_t snap_bytes;
     uint32_t sem;  // SemFlags of the netlist
+    int period2;   // B2_OPT_PERIOD2_SKIP
 };
 
 __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g, const uint64_t *av, const uint64_t *am, uint32_t wpc,
@@ -1014,7 +1064,8 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
     uint64_t *AV = smem, *AM = smem + plane, *BV = smem + 2 * plane, *BM = smem + 3 * plane;
     uint64_t *s_changed = smem + 4 * plane, *s_conf = s_changed + wpc, *s_live = s_conf + wpc, *s_conflict = s_live + wpc,
              *s_unsettled = s_conflict + wpc;
-    __shared__ unsigned s_any;
+    __shared__ unsigned s_any, s_p2[2];
+    if (threadIdx.x < 2) s_p2[threadIdx.x] = 0;
 
     // ---- load: the current state, or the cold start W_1 = resolve(D, all outputs High-Z) = D
     //      (a levelised pass recomputes every row: only the source rows are loaded, from their drives)
@@ -1029,6 +1080,8 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
             } else if (row < a.n_src) {
                 v = a.dval[o];
                 m = a.dvld[o];
+            } else if (a.sem & SEM_INIT_X) {
+                v = ~0ull;  // A.6-5 alternative: component outputs start Undefined
             }
         }
         AV[i] = v;
@@ -1089,19 +1142,40 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
         __syncthreads();
         if (tid < wpc) s_conflict[tid] &= s_live[tid];  // lanes in use
     } else if (a.cold) {
+        const bool init_x = (a.sem & SEM_INIT_X) != 0;  // outputs start Undefined: they take part in W_1 and can conflict there
         for (size_t i = tid; i < (size_t)a.n_extra * wpc; i += nt) {
             const uint32_t x = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
             if (w < a.stride && a.xrows[x] != 0xFFFFFFFFu) {
-                AV[(size_t)a.xrows[x] * wpc + j] = a.xval[(size_t)x * a.stride + w];
-                AM[(size_t)a.xrows[x] * wpc + j] = a.xvld[(size_t)x * a.stride + w];
+                const size_t r = (size_t)a.xrows[x] * wpc + j;
+                const u64 dv = a.xval[(size_t)x * a.stride + w], dm = a.xvld[(size_t)x * a.stride + w];
+                if (init_x) {
+                    const u64 c = conflict_of(dv, dm, AV[r], AM[r], a.lenient);
+                    AV[r] |= dv;
+                    AM[r] |= dm;
+                    if (c) atomicOr((unsigned long long *)&s_conf[j], c);
+                } else {
+                    AV[r] = dv;
+                    AM[r] = dm;
+                }
             }
         }
         for (size_t i = tid; i < (size_t)a.n_res * wpc; i += nt) {
             const uint32_t r = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
             const int32_t slot = a.res_xslot[r];
+            u64 v = 0, m = 0, c = 0;
             if (w < a.stride && slot >= 0) {
-                AV[(size_t)(res_base + r) * wpc + j] = a.xval[(size_t)slot * a.stride + w];
-                AM[(size_t)(res_base + r) * wpc + j] = a.xvld[(size_t)slot * a.stride + w];
+                v = a.xval[(size_t)slot * a.stride + w];
+                m = a.xvld[(size_t)slot * a.stride + w];
+            }
+            if (init_x)
+                for (uint32_t q = a.res_off[r]; q < a.res_off[r + 1]; q++) {  // every driver contributes an Undefined
+                    c |= conflict_of(v, m, ~0ull, 0, a.lenient);
+                    v = ~0ull;
+                }
+            if (w < a.stride && (slot >= 0 || init_x)) {
+                AV[(size_t)(res_base + r) * wpc + j] = v;
+                AM[(size_t)(res_base + r) * wpc + j] = m;
+                if (c) atomicOr((unsigned long long *)&s_conf[j], c);
             }
         }
         __syncthreads();
@@ -1118,6 +1192,7 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
             k++;
             apps++;
             const bool is_last = k == a.last;
+            u64 d2 = 0;  // does this application write anything that differs from the state two applications ago?
             // ---- B = G(A)
             for (size_t i = tid; i < n_items; i += nt) {
                 const uint32_t row = (uint32_t)(i / wpc), j = (uint32_t)(i % wpc), w = w0 + j;
@@ -1144,10 +1219,12 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
                     wide_gate_word(a, row - a.n_src - a.n_g2 - a.n_g3, AV, AM, wpc, j, rv, rm);
                 }
                 const u64 d = (rv ^ AV[i]) | (rm ^ AM[i]);
+                d2 |= (rv ^ BV[i]) | (rm ^ BM[i]);
                 BV[i] = rv;
                 BM[i] = rm;
                 if (d && counts) atomicOr((unsigned long long *)&s_changed[j], d);
             }
+            if (d2) s_p2[k & 1] = 1;
             __syncthreads();
             // ---- tri-state nets: wire = resolve(drive, driver rows of B), conflict where two are not High-Z
             if (a.n_res) {
@@ -1190,7 +1267,10 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
                 __syncthreads();
             }
             // ---- per-lane bookkeeping (same rules as k_status_step)
-            if (tid == 0) s_any = 0;
+            if (tid == 0) {
+                s_any = 0;
+                s_p2[(k + 1) & 1] = 0;
+            }
             __syncthreads();
             if (tid < wpc) {
                 u64 cf = s_conflict[tid], lv = s_live[tid];
@@ -1209,6 +1289,13 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
             t = AV; AV = BV; BV = t;
             t = AM; AM = BM; BM = t;
             if (!s_any) break;
+            // Exact period-2 oscillation (W_k = W_{k-2} on every gate and source row; tri-state rows follow from them): the
+            // step function depends on the state alone, so jumping ahead by an even number of applications changes nothing
+            // this loop keeps — see k_unit_delay_loop.  apps >= 3: the buffer compared with was written by this launch.
+            if (a.period2 && apps >= 3 && a.n_extra == 0 && !s_p2[k & 1]) {
+                const uint64_t jump = ((a.last - 1 - k) / 2) * 2;
+                if (jump >= 8) k += jump;
+            }
         }
     }
     // ---- write back
@@ -1449,7 +1536,7 @@ int Engine::ensure_device() {
         CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_unit_delay_loop, 256, 0));
         loop_ctas_ = coop ? (uint32_t)(std::min(occ, 2) * sm_count_) : 0;
-        if (!d_loop_result_) CU_TRY(cudaMalloc((void **)&d_loop_result_, sizeof(LoopResult) + 8 * sizeof(uint32_t)));
+        if (!d_loop_result_) CU_TRY(cudaMalloc((void **)&d_loop_result_, sizeof(LoopResult) + 16 * sizeof(uint32_t)));
         if (!h_loop_result_) CU_TRY(cudaMallocHost((void **)&h_loop_result_, sizeof(LoopResult)));
     }
     // the kernels are built for sm_100a only: fail loudly on anything else
@@ -1597,6 +1684,8 @@ int Engine::set_lanes(uint64_t n_lanes) {
         return rc;
     }
     store_bytes_ += net_.n_rows;
+    // A.6-5 alternative: wires read Undefined (1, 0) instead of High-Z (0, 0) until the first run
+    if (net_.sem_flags & SEM_INIT_X) CU_TRY(cudaMemsetAsync(val_[0], 0xFF, row_words * 8, ST));
     cur_ = 0;
     cold_ = true;
     last_mode_ = 0;
@@ -2150,8 +2239,9 @@ int Engine::run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &res
     la.drv_val = drv_val_; la.drv_vld = drv_vld_;
     la.list2 = (uint4 *)d_act_list_[0]; la.list3 = (uint4 *)d_act_list_[1]; la.listc = d_act_list_[2];
     la.listw = d_act_list_[3];
-    la.cnt = (uint32_t *)(d_loop_result_ + 1);  // behind the result block
-    CU_TRY(cudaMemsetAsync(la.cnt, 0, 8 * sizeof(uint32_t), ST));
+    la.cnt = (uint32_t *)(d_loop_result_ + 1);  // behind the result block: 8 list counters, then the 8 period-2 words
+    CU_TRY(cudaMemsetAsync(la.cnt, 0, 16 * sizeof(uint32_t), ST));
+    la.p2 = opt_period2_ ? la.cnt + 8 : nullptr;
     la.changed = d_changed_; la.conf_step = d_conf_step_; la.live = d_live_; la.conflict = d_conflict_; la.unsettled = d_unsettled_;
     la.flags = d_flags_;
     la.result = d_loop_result_;
@@ -2179,7 +2269,7 @@ int Engine::run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &res
     CU_TRY(cudaMemcpyAsync(h_loop_result_, d_loop_result_, sizeof(LoopResult), cudaMemcpyDeviceToHost, ST));
     CU_TRY(cudaStreamSynchronize(ST));
     const LoopResult *lr = (const LoopResult *)h_loop_result_;
-    last_apps_ += lr->k - k;
+    last_apps_ += lr->k - k - lr->skipped;
     k = lr->k;
     cur_ = lr->cur;
     chg_w_ = lr->chg_w;
@@ -2220,7 +2310,10 @@ int Engine::run_jacobi(uint64_t max_steps) {
         // W_1 = resolve(D, all outputs High-Z) = D
         uint64_t *V = val_[cur_], *M = vld_[cur_];
         const size_t row_words = (size_t)net_.n_rows * stride_;
-        CU_TRY(cudaMemsetAsync(V, 0, row_words * 8, ST));
+        // (A.6-5 alternative: component outputs start Undefined instead of High-Z, so every driven wire is X in W_1 and a drive
+        //  on it — or a second driver — conflicts right there; the conflict words are counted by the first bookkeeping step)
+        const bool init_x = (net_.sem_flags & SEM_INIT_X) != 0;
+        CU_TRY(cudaMemsetAsync(V, init_x ? 0xFF : 0, row_words * 8, ST));
         CU_TRY(cudaMemsetAsync(M, 0, row_words * 8, ST));
         if (net_.n_src) {
             const uint32_t rb = (net_.n_src + sh.block.y - 1) / sh.block.y;
@@ -2229,12 +2322,13 @@ int Engine::run_jacobi(uint64_t max_steps) {
             LAUNCHED();
         }
         if (n_extra) {
-            k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_slots, xdrv_val_, xdrv_vld_, V, M, d_conf_step_, stride_, 1);
+            k_extra_drive<<<sgrid, 256, 0, ST>>>(d_extra_rows_, n_slots, xdrv_val_, xdrv_vld_, V, M, d_conf_step_, stride_, init_x ? 0 : 1,
+                                                 opt_lenient_ ? 1 : 0);
             LAUNCHED();
         }
         if (n_res) {
             ResolveArgs ra{d_res_off_, d_res_in_, d_res_xslot_, xdrv_val_, xdrv_vld_, V, M, V, M, nullptr, d_conf_step_, nullptr,
-                           n_res, res_base, stride_, pairs, sh.pair_blocks, 1, opt_lenient_ ? 1 : 0};
+                           n_res, res_base, stride_, pairs, sh.pair_blocks, init_x ? 0 : 1, opt_lenient_ ? 1 : 0};
             k_resolve<<<sh.pair_blocks * res_gb, sh.block, 0, ST>>>(ra);
             LAUNCHED();
         }
@@ -2474,6 +2568,7 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
     a.levelised = levelised ? 1 : 0;
     a.lenient = opt_lenient_ ? 1 : 0;
     a.sem = net_.sem_flags;
+    a.period2 = opt_period2_ ? 1 : 0;
     const size_t smem = ((size_t)net_.n_rows * wpc * 4 + (size_t)wpc * 5) * 8;
     if (!resident_attr_set_) {
         CU_TRY(cudaFuncSetAttribute(k_resident_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kResidentSmem + 4096)));

@@ -102,6 +102,7 @@ class Engine {
     void set_budget_inclusive(bool on) { opt_budget_inclusive_ = on; }
     void set_use_frontier(bool on) { opt_frontier_ = on; frontier_valid_ = false; }
     void set_device_loop(bool on) { opt_device_loop_ = on; }
+    void set_period2_skip(bool on) { opt_period2_ = on; }
     // SURVEY.md A.6-2 alternative (agreeing valid drivers do not conflict); refused for netlists with two firm drivers on a net
     bool set_lenient_conflicts(bool on) {
         if (on && net_.multi_driver) return false;

@@ -217,6 +217,11 @@ enum b2_option {
     B2_OPT_L2_HINTS = 9,       /* default 1.  Levelised pass: fan-in rows produced more than one level below the reading gate are
                                   loaded with an L2 evict-first hint (createpolicy + ld.L2::cache_hint), so that these one-off reads
                                   do not displace the rows the previous level has just written and the next kernel re-reads. */
+    B2_OPT_PERIOD2_SKIP = 10,  /* default 1.  Unit-delay loops (device-side loop, resident kernel) detect an exact period-2 oscillation
+                                  — every row an application writes equals the row two applications earlier — and jump ahead by an
+                                  even number of applications: the state, lane results and step accounting are those of walking
+                                  every step (the step function depends on the state alone), an oscillating latch under
+                                  max_steps = 10 000 costs a dozen applications instead of 10 003. */
     B2_OPT_DEVICE_LOOP = 7     /* default 1.  Unit-delay runs in HBM execute the whole run_sim loop in one cooperative launch
                                   (grid barriers between the phases of an application, stop decision on the device);
                                   0: one set of launches per application, stop decision on the host. */
