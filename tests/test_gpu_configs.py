@@ -136,6 +136,61 @@ def test_config4_sequential_vs_oracle(n_hazard, max_steps, resident):
     assert sim.info.last_mode == (3 if resident is True else 2)
 
 
+@pytest.mark.parametrize("device_loop", [1, 0])
+def test_config4_full_size_with_hazard_latches_vs_oracle(device_loop):
+    """BASELINE config 4 as SURVEY.md 8d specifies it, at full netlist size: 64 chains x 64 NAND flip-flops + 4096 SR latches,
+    8 of them hazard latches (S' and R' can rise together: unit-delay oscillation until the step budget), 65 536 lanes with a
+    per-lane preset pattern, run_sim(10_000) per clock edge.  After every call: the per-lane result (Ok / MaxStepsReached) and
+    EVERY wire of 128 sampled lanes (two lane-words) equal the scalar oracle, which walks all 10 001 steps of an oscillating
+    lane; over all lanes some must oscillate.  device_loop = 0 is the control that walks every step on the GPU too."""
+    n_lanes, bits, max_steps = 65_536, 64, 10_000
+    sample = [0, 517]                                   # lane-words compared wire for wire
+    seq = netgen.sequential(n_latches=4096, n_chains=64, bits=bits, n_hazard=8)
+    sim = seq.emit(SimulatorBuilder()).build()
+    sim.set_option(sim.OPT_DEVICE_LOOP, device_loop)
+    sim.set_lanes(n_lanes)
+    lanes = oracle.Lanes(seq.emit(oracle.Builder()), 64 * len(sample))
+    words = n_lanes // 64
+    rng = np.random.default_rng(44)
+    ones, zeros = np.full(words, ALL1, np.uint64), np.zeros(words, np.uint64)
+    all_wires = np.arange(seq.n_wires, dtype=np.uint32)
+    unsettled_lanes = 0
+
+    def drive(wire, value, valid):
+        sim.set_wire_drive_lanes(wire, value, valid)
+        lanes.set_drive(wire, value[sample], valid[sample])
+
+    def run_and_compare(tag):
+        nonlocal unsettled_lanes
+        status, _, _ = lanes.run(max_steps, threads=8)
+        res, conflict, unsettled = sim.run_sim_lanes(max_steps)
+        assert not conflict.any(), tag
+        got = oracle.status_from_masks(conflict[sample], unsettled[sample], 64 * len(sample))
+        assert (got == status).all(), tag
+        unsettled_lanes += int(sum(bin(int(x)).count("1") for x in unsettled))
+        assert int(res) == (1 if unsettled.any() else 0), tag
+        rv, rm = lanes.get_all(seq.n_wires)
+        gv, gm = sim.gather_wires_host(all_wires)
+        assert (gv[:, sample] == rv).all() and (gm[:, sample] == rm).all(), tag
+
+    drive(seq.clk, zeros, ones)
+    for b in range(bits):
+        pattern = rng.integers(0, 1 << 64, words, dtype=np.uint64)
+        drive(seq.preset_n[b], ~pattern, ones)
+        drive(seq.clear_n[b], pattern, ones)
+    run_and_compare("init")
+    for b in range(bits):
+        drive(seq.preset_n[b], ones, ones)
+        drive(seq.clear_n[b], ones, ones)
+    run_and_compare("release")
+    for step in range(3):                               # 6 run_sim(10_000) calls
+        drive(seq.clk, ones, ones)
+        run_and_compare(("up", step))
+        drive(seq.clk, zeros, ones)
+        run_and_compare(("down", step))
+    assert unsettled_lanes > 0, "no lane oscillated: the hazard latches were not exercised"
+
+
 def test_config5_netlist_sampled_against_oracle():
     """10M gates, depth 200, 16 384 inputs (BASELINE config 5): one 32-word tile from the end of the
     2^26-lane batch, two of its lane-words re-computed by the CPU bit-sliced model — every 997th wire

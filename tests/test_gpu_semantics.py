@@ -49,10 +49,12 @@ def engine_builder(on):
     return b
 
 
-def circuit(b, rng, cyclic):
+def circuit(b, rng, cyclic, multi=True):
     """Multiplexers (1- and 2-bit select, 4-bit data), buffers onto a shared bus and onto plain wires, slices and merges of
     4-bit wires, reduction gates and plain gates reading all of them; a multiplexer and a buffer share one net (legal only when
-    multiplexers can float); with `cyclic`, gates feed back.  Returns (input wires, all wires with widths)."""
+    multiplexers can float); with `cyclic`, gates feed back.  multi = False leaves every net with one driver (with outputs
+    that start Undefined, two drivers on a net conflict in the first wire update of every lane).  Returns (input wires, all
+    wires with widths)."""
     ins1 = [b.add_wire(1) for _ in range(8)]
     ins4 = [b.add_wire(4) for _ in range(4)]
     wires = [(w, 1) for w in ins1] + [(w, 4) for w in ins4]
@@ -67,13 +69,15 @@ def circuit(b, rng, cyclic):
     m2 = new(4); b.add_multiplexer([ins4[0], ins4[1], ins4[2], m1], sel2, m2)
     bus = new(4)
     b.add_buffer(ins4[2], ins1[3], bus)
-    b.add_buffer(m2, ins1[4], bus)
+    if multi:
+        b.add_buffer(m2, ins1[4], bus)
     lone = new(4); b.add_buffer(ins4[3], ins1[5], lone)
     sl = new(2); b.add_slice(bus, 1, sl)
     mg = new(4); b.add_merge([sl, ins1[6], ins1[7]], mg)
     shared = new(1)                                        # a multiplexer and a buffer on one net
     b.add_multiplexer([ins1[6], ins1[7]], ins1[0], shared)
-    b.add_buffer(ins1[1], ins1[2], shared)
+    if multi:
+        b.add_buffer(ins1[1], ins1[2], shared)
     g1 = new(4); b.add_xor_gate([mg, lone], g1)
     g2 = new(4); b.add_nand_gate([m1, bus, g1], g2)
     r1 = new(1); b.add_horizontal_or_gate(g2, r1)
@@ -89,6 +93,7 @@ def circuit(b, rng, cyclic):
 
 def drive_all(rng, targets, ins1, ins4, words, p_z=0.35):
     """Random 4-state drives, High-Z (0, 0) with probability p_z per lane and bit."""
+    last = {}
     for w, width in [(w, 1) for w in ins1] + [(w, 4) for w in ins4]:
         for bit in range(width):
             v, m = random_drive(rng, words)
@@ -97,6 +102,17 @@ def drive_all(rng, targets, ins1, ins4, words, p_z=0.35):
                 z |= rng.integers(0, 1 << 64, words, dtype=np.uint64) & rng.integers(0, 1 << 64, words, dtype=np.uint64) \
                     & rng.integers(0, 1 << 64, words, dtype=np.uint64)
             v, m = v & ~z, m & ~z
+            if w == ins1[3]:
+                m = np.full(words, ALL1, np.uint64)        # a valid enable (an X enable makes its buffer drive X)
+            if w in (ins1[2], ins1[4]):
+                # enables of the second driver of a shared net: on in few lanes only, so that conflicts (which end a lane's
+                # comparable life, A.6-3) stay rare — ins1[4] is mostly the complement of ins1[3], ins1[2] mostly 0
+                rare = rng.integers(0, 1 << 64, words, dtype=np.uint64)
+                for _ in range(4):
+                    rare &= rng.integers(0, 1 << 64, words, dtype=np.uint64)
+                v = ((~last.get(ins1[3], v)) if w == ins1[4] else np.zeros(words, np.uint64)) | rare
+                m = np.full(words, ALL1, np.uint64)
+            last[w] = v
             for t in targets:
                 if isinstance(t, oracle.Lanes):
                     t.set_drive(w, v, m, bit)
@@ -106,7 +122,7 @@ def drive_all(rng, targets, ins1, ins4, words, p_z=0.35):
 
 def make_sim(on, rng_seed, cyclic, n_lanes, path):
     b = engine_builder(on)
-    ins1, ins4, wires = circuit(b, np.random.default_rng(rng_seed), cyclic)
+    ins1, ins4, wires = circuit(b, np.random.default_rng(rng_seed), cyclic, "init_x" not in on)
     sim = b.build()
     sim.set_option(sim.OPT_RESIDENT_KERNEL, int(path == "resident"))
     sim.set_option(sim.OPT_DEVICE_LOOP, int(path in ("resident", "device")))
@@ -122,23 +138,31 @@ def test_switches_in_lockstep_with_the_oracle(on, cyclic, path):
     n_lanes = 64 * 3 + 17
     with oracle_config(on):
         ob = oracle.Builder()
-        circuit(ob, np.random.default_rng(5), cyclic)
+        circuit(ob, np.random.default_rng(5), cyclic, "init_x" not in on)
         lanes = oracle.Lanes(ob, n_lanes)
         sim, ins1, ins4, wires = make_sim(on, 5, cyclic, n_lanes, path)
         rng = np.random.default_rng(42 + len(on))
         mask = lane_mask(n_lanes)
+        alive = np.ones(n_lanes, bool)                    # lanes that have never conflicted: what happens after a conflict is
+        seen = set()                                      # outside the contract (A.6-3), in this run and in every later one
         for rnd, max_steps in enumerate([0, 1, 2, 40, 3, 1000, 17, 10_000]):
             drive_all(rng, [lanes, sim], ins1, ins4, lanes.words)
             status, _, _ = lanes.run(max_steps)
             res, conflict, unsettled = sim.run_sim_lanes(max_steps)
-            assert (oracle.status_from_masks(conflict, unsettled, n_lanes) == status).all(), (rnd, max_steps)
-            assert int(res) == int(status.max())
-            clean = mask & ~conflict                      # the state after a conflict is outside the contract (A.6-3)
+            got = oracle.status_from_masks(conflict, unsettled, n_lanes)
+            assert (got[alive] == status[alive]).all(), (rnd, max_steps)
+            seen |= set(int(x) for x in status[alive])
+            alive &= status != 2
+            assert alive.sum() > n_lanes // 4, "too few lanes left to compare"
+            alive_w = np.packbits(np.pad(alive, (0, lanes.words * 64 - n_lanes)).reshape(lanes.words, 64), axis=1,
+                                  bitorder="little").view(np.uint64).reshape(lanes.words)
+            clean = mask & alive_w
             for w, width in wires:
                 for bit in range(width):
                     rv, rm = lanes.get(w, bit)
                     gv, gm = sim.get_wire_lanes(w, bit=bit)
                     assert (((gv ^ rv) | (gm ^ rm)) & clean).max(initial=0) == 0, (rnd, max_steps, w, bit)
+        assert (2 in seen) == ("init_x" not in on), "lanes must conflict exactly where a net has two drivers"
 
 
 @pytest.mark.parametrize("on", COMBOS, ids=lambda c: "+".join(c) or "default")
