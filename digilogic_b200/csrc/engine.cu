@@ -737,37 +737,57 @@ __global__ void __launch_bounds__(256) k_broadcast_bits(const PendingBit *bits, 
 
 __global__ void __launch_bounds__(256) k_fill_stimulus(uint64_t *const *row_val, uint64_t *const *row_vld, uint32_t n,
                                                        uint32_t words, uint64_t seed, uint64_t word_base, int mode) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    // one 128-bit pair of lane-words per thread (rows are 16-byte aligned and hold an even number of words)
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y;
     if (w >= words || i >= n) return;
-    const uint64_t v = splitmix64(seed ^ ((uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull) ^ ((word_base + w) * 0xD1B54A32D192ED03ull));
-    const uint64_t m = mode == 0 ? ~0ull : (splitmix64(v ^ 1) | splitmix64(v ^ 2));
-    row_val[i][w] = v;
-    row_vld[i][w] = m;
+    const uint64_t k = seed ^ ((uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull);
+    ulonglong2 v, m;
+    v.x = splitmix64(k ^ ((word_base + w) * 0xD1B54A32D192ED03ull));
+    v.y = splitmix64(k ^ ((word_base + w + 1) * 0xD1B54A32D192ED03ull));
+    m.x = mode == 0 ? ~0ull : (splitmix64(v.x ^ 1) | splitmix64(v.x ^ 2));
+    m.y = mode == 0 ? ~0ull : (splitmix64(v.y ^ 1) | splitmix64(v.y ^ 2));
+    st_pair(row_val[i] + w, v);
+    st_pair(row_vld[i] + w, m);
 }
 
-// rows[] of (val, vld) -> dense planes [n][dst_stride]
+// rows[] of (val, vld) -> dense planes [n][dst_stride].  VEC: one 128-bit pair of lane-words per thread (every offset
+// even, every base 16-byte aligned — checked by the caller); the destination may be peer-GPU memory (the fused output gather).
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_gather_rows(const uint32_t *rows, uint32_t n, const uint64_t *val, const uint64_t *vld,
                                                      uint64_t *dst_val, uint64_t *dst_vld, uint32_t stride, uint32_t word0,
                                                      uint32_t n_words, size_t dst_stride, const uint8_t *kv,
                                                      const uint32_t *all_valid) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) * (VEC ? 2 : 1);
     const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y;
     if (w >= n_words || i >= n) return;
-    const size_t s = (size_t)rows[i] * stride + word0 + w;
-    dst_val[(size_t)i * dst_stride + w] = val[s];
-    dst_vld[(size_t)i * dst_stride + w] = (kv && (*all_valid || kv[rows[i]])) ? ~0ull : vld[s];
+    const size_t s = (size_t)rows[i] * stride + word0 + w, o = (size_t)i * dst_stride + w;
+    const bool elided = kv && (*all_valid || kv[rows[i]]);
+    if (VEC) {
+        st_pair(dst_val + o, ld_stream(val + s));
+        st_pair(dst_vld + o, elided ? make_ulonglong2(~0ull, ~0ull) : ld_stream(vld + s));
+    } else {
+        dst_val[o] = val[s];
+        dst_vld[o] = elided ? ~0ull : vld[s];
+    }
 }
 
 // dense planes [n][src_stride] -> drive rows given by pointer tables
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_scatter_rows(uint64_t *const *row_val, uint64_t *const *row_vld, uint32_t n,
                                                       const uint64_t *src_val, const uint64_t *src_vld, uint32_t words,
                                                       size_t src_stride) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) * (VEC ? 2 : 1);
     const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y;
     if (w >= words || i >= n) return;
-    row_val[i][w] = src_val[(size_t)i * src_stride + w];
-    row_vld[i][w] = src_vld[(size_t)i * src_stride + w];
+    const size_t s = (size_t)i * src_stride + w;
+    if (VEC) {
+        st_pair(row_val[i] + w, ld_stream(src_val + s));
+        st_pair(row_vld[i] + w, ld_stream(src_vld + s));
+    } else {
+        row_val[i][w] = src_val[s];
+        row_vld[i][w] = src_vld[s];
+    }
 }
 
 // SimState bit-packing of lane 0 (reference crates/digilogic_netcode/src/lib.rs:241-270): bit k
@@ -2008,8 +2028,13 @@ int Engine::set_drives_lanes(const uint32_t *wires, uint32_t n, const uint64_t *
     CU_TRY(cudaMemcpy2DAsync(stage_vld_[0], (size_t)T_ * 8, valid, src_stride * 8, (size_t)T_ * 8, n, cudaMemcpyDefault, CIN));
     const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
     uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
-    dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
-    k_scatter_rows<<<grid, block, 0, CIN>>>(d_tv, d_tm, n, stage_val_[0], stage_vld_[0], T_, T_);
+    if (T_ % 2 == 0) {  // rows, staging planes and T_ are all even: 128-bit accesses
+        dim3 block(64, 4), grid((T_ / 2 + 63) / 64, (n + 3) / 4);
+        k_scatter_rows<true><<<grid, block, 0, CIN>>>(d_tv, d_tm, n, stage_val_[0], stage_vld_[0], T_, T_);
+    } else {
+        dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
+        k_scatter_rows<false><<<grid, block, 0, CIN>>>(d_tv, d_tm, n, stage_val_[0], stage_vld_[0], T_, T_);
+    }
     LAUNCHED();
     CU_TRY(cudaEventRecord(EV(ev_drives_ready_), CIN));
     cin_pending_ = true;
@@ -2028,7 +2053,7 @@ int Engine::fill_stimulus(const uint32_t *wires, uint32_t n, uint64_t seed, uint
     const size_t idx_bytes = (((size_t)rows_cap_ * 4) + 15) & ~(size_t)15;
     uint64_t **d_tv = (uint64_t **)((char *)d_rows_ + idx_bytes), **d_tm = d_tv + rows_cap_;
     if ((rc = drives_begin())) return rc;
-    dim3 block(64, 4), grid((stride_ + 63) / 64, (n + 3) / 4);
+    dim3 block(64, 4), grid((stride_ / 2 + 63) / 64, (n + 3) / 4);  // stride_ is even
     k_fill_stimulus<<<grid, block, 0, ST>>>(d_tv, d_tm, n, stride_, seed, word_base, mode);
     LAUNCHED();
     if ((rc = drives_end())) return rc;
@@ -2696,10 +2721,19 @@ int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uin
     if (n == 0) return B2_OK;
     if (dst_stride < T_) return B2_ERR_RANGE;
     if ((rc = upload_rows(wires, n, false))) return rc;
-    dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
+    auto launch = [&](uint64_t *dv, uint64_t *dm, size_t dstride) {
+        const uint8_t *kvp = elided_ ? d_kv_ : nullptr;
+        const bool vec = T_ % 2 == 0 && dstride % 2 == 0 && (((uintptr_t)dv | (uintptr_t)dm) & 15) == 0;
+        if (vec) {
+            dim3 block(64, 4), grid((T_ / 2 + 63) / 64, (n + 3) / 4);
+            k_gather_rows<true><<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], dv, dm, stride_, 0, T_, dstride, kvp, d_all_valid_);
+        } else {
+            dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
+            k_gather_rows<false><<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], dv, dm, stride_, 0, T_, dstride, kvp, d_all_valid_);
+        }
+    };
     if (dst_is_device) {
-        k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], value, valid, stride_, 0, T_, dst_stride, elided_ ? d_kv_ : nullptr,
-                                              d_all_valid_);
+        launch(value, valid, dst_stride);
         LAUNCHED();
         return B2_OK;
     }
@@ -2707,8 +2741,7 @@ int Engine::gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uin
     // main stream: gather into the out-stage once the previous D2H has drained it;
     // copy-out stream: D2H while the main stream goes on with the next tile
     CU_TRY(cudaStreamWaitEvent(ST, EV(ev_out_free_), 0));
-    k_gather_rows<<<grid, block, 0, ST>>>(d_rows_, n, val_[cur_], vld_[cur_], stage_val_[1], stage_vld_[1], stride_, 0, T_, T_,
-                                          elided_ ? d_kv_ : nullptr, d_all_valid_);
+    launch(stage_val_[1], stage_vld_[1], T_);
     LAUNCHED();
     CU_TRY(cudaEventRecord(EV(ev_gathered_), ST));
     CU_TRY(cudaStreamWaitEvent(COUT, EV(ev_gathered_), 0));

@@ -1,4 +1,4 @@
-"""The caller side of the drop-in boundary, restated for the harness: the netcode `Adapter` and
+"""TEST HARNESS (not part of the product package).  The caller side of the drop-in boundary, restated: the netcode `Adapter` and
 `process_message` (reference crates/digilogic_netcode/src/server.rs:233-470) and the msgpack wire
 form of `ClientMessage` / `ServerMessage` / `SimState` (crates/digilogic_netcode/src/lib.rs:87-179),
 so that a client session can be replayed byte for byte against any `SimServer` implementation —
@@ -14,8 +14,8 @@ from __future__ import annotations
 
 import msgpack
 
-from .server import ServerError, ServerErrorException
-from .sim_state import SimState
+from digilogic_b200.server import ServerError, ServerErrorException
+from digilogic_b200.sim_state import SimState
 
 GATE_KINDS = {"AddAndGate": "add_and_gate", "AddOrGate": "add_or_gate", "AddXorGate": "add_xor_gate",
               "AddNandGate": "add_nand_gate", "AddNorGate": "add_nor_gate", "AddXnorGate": "add_xnor_gate"}

@@ -277,3 +277,46 @@ def test_auto_tile_words():
     mul = netgen.array_multiplier(32).emit(d.SimulatorBuilder()).build()
     assert auto_tile_words(mul, 16384) == 4096
     assert auto_tile_words(mul, 96) == 32 and auto_tile_words(mul, 7) == 1
+
+
+def test_batch_and_clone_host_side_without_a_device():
+    """b2_sim_clone, b2_batch_new and the option setters are host-only; running needs a device (no CPU path)."""
+    from digilogic_b200.batch import Batch, auto_batch_shape
+    from digilogic_b200.gsim import B200Error, ComponentError
+    gen = netgen.random_dag(n_gates=200_000, depth=40, n_inputs=64, n_outputs=16)          # 5000 gates per level, like config 3
+    sim = gen.emit(d.SimulatorBuilder()).build()
+    assert auto_batch_shape(sim, 262144) == (128, 3)
+    c = sim.clone()
+    assert c.info.n_rows == sim.info.n_rows and c.info.depth == sim.info.depth == 40
+    b = Batch(sim, gen.inputs, gen.outputs, 128, 3)
+    b.set_option(Batch.OPT_SWEEP, 1)
+    b.set_option(Batch.OPT_DISCARD, 0)
+    assert b.info.sweep == 1 and b.info.tile_words == 128 and b.info.n_slots == 3
+    with pytest.raises(B200Error):
+        b.set_option(Batch.OPT_UNROLL, 3)
+    with pytest.raises(ComponentError):
+        Batch(sim, [gen.n_wires], gen.outputs, 128, 3)                                     # InvalidWireId
+    if not _has_gpu():
+        out = np.zeros((16, 128), np.uint64)
+        with pytest.raises(B200Error) as e:
+            b.run_generated(1, 0, 0, 128, 10_000, out, out.copy())
+        assert e.value.code == 18                                                          # B2_ERR_NO_DEVICE
+    wide = d.SimulatorBuilder()
+    w4, o4 = wide.add_wire(4), wide.add_wire(4)
+    wide.add_not_gate(w4, o4)
+    with pytest.raises(ComponentError):
+        Batch(wide.build(), [w4], [o4], 32, 1)                                             # lane planes carry 1-bit wires
+
+
+def test_builder_switches_survive_build():
+    b = d.SimulatorBuilder()
+    b.set_option(b.OPT_MUX_Z_PASSTHROUGH, 1)
+    with pytest.raises(d.gsim.B200Error):
+        b.set_option(99, 1)
+    a, o = b.add_wire(), b.add_wire()
+    b.add_not_gate(a, o)
+    first = b.build()
+    s, x, y, z = (b.add_wire() for _ in range(4))          # the builder is empty again, the switches are not
+    b.add_multiplexer([x, y], s, z)
+    second = b.build()
+    assert first.info.cyclic == 0 and second.info.cyclic == 1   # a multiplexer that can float makes its net a resolved net

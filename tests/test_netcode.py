@@ -7,7 +7,8 @@ import os
 import msgpack
 import pytest
 
-from digilogic_b200 import importers, netcode
+from digilogic_b200 import importers
+import netcode_harness as netcode
 from digilogic_b200.server import ServerError, ServerErrorException
 from digilogic_b200.sim_state import SimState
 
