@@ -47,6 +47,8 @@ def main():
         sweep = f[6] if len(f) > 6 else 1
         hints = f[7] if len(f) > 7 else 0
         discard = f[8] if len(f) > 8 else 1
+        pdl = f[9] if len(f) > 9 else 0
+        sim.set_option(sim.OPT_PDL, pdl)
         sim.set_option(sim.OPT_L2_HINTS, hints)
         b = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=0, stream=stream.cuda_stream)
         b.set_option(Batch.OPT_TASK_ITERS, iters)
@@ -67,7 +69,7 @@ def main():
         cs = int((ov.sum() ^ om.sum()).item()) & 0xFFFFFFFFFFFFFFFF
         first = cs if first is None else first
         info = b.info
-        print(json.dumps({"tile": tile, "slots": slots, "iters": iters, "unroll": unroll, "ctas_per_sm": ctas, "ld_mode": ld_mode, "sweep": sweep, "l2_hints": hints, "discard": discard, "grid": info.grid_ctas,
+        print(json.dumps({"tile": tile, "slots": slots, "iters": iters, "unroll": unroll, "ctas_per_sm": ctas, "ld_mode": ld_mode, "sweep": sweep, "l2_hints": hints, "discard": discard, "pdl": pdl, "grid": info.grid_ctas,
                           "ms": round(ms, 2), "evals_per_s": args.gates * args.lanes / (ms * 1e-3),
                           "algo_frac": 48.0 * args.gates * words / (ms * 1e-3) / 1e9 / peak, "checksum_equal": cs == first,
                           "checksum": f"{cs:#018x}"}), flush=True)

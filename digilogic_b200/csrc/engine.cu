@@ -86,6 +86,7 @@ struct Eval2Args {
     // gates [now_begin, now_end) of this launch drive rows that no gate and no output reads: each 128-byte line is dropped
     // from L2 right after the warp has stored it
     uint32_t now_begin = 0, now_end = 0;
+    uint32_t pdl = 0;  // levelised pass launched with programmatic stream serialisation: 1 = release dependents early, 2 = late
     // device-side loop: set to 1 when a row written by this application differs from what the buffer held (the state two
     // applications ago) — the period-2 detector of k_unit_delay_loop; nullptr elsewhere
     uint32_t *p2diff = nullptr;
@@ -112,24 +113,11 @@ template <int U, bool JACOBI, bool KV, int NIN = 2>
 __global__ void __launch_bounds__(256, JACOBI ? 2 : ((U == 2 && NIN == 2 && !KV) ? 5 : 3)) k_eval2(const Eval2Args a) {
     const uint32_t pb = blockIdx.x % a.pair_blocks, gb = blockIdx.x / a.pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
-    if (!JACOBI) {
-        // Rows nobody will read again: invalidate their L2 lines without write-back, so they never cost HBM bandwidth (the level
-        // that read them last ran in an earlier launch on this stream).  One 128-byte line per plane per thread and round.
-#pragma unroll
-        for (int r = 0; r < 2; r++)
-            if (a.disc_end[r] > a.disc_begin[r]) {
-                // (by the CTAs that start first: the sooner a dead line is dropped, the likelier it has not been written back yet)
-                const uint64_t lines = (uint64_t)(a.disc_end[r] - a.disc_begin[r]) * (a.stride >> 4);
-                const uint32_t n_cta = min(gridDim.x, 296u);
-                if (blockIdx.x >= n_cta) break;
-                const uint64_t nt = (uint64_t)n_cta * 256;
-                for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.y * blockDim.x + threadIdx.x; i < lines; i += nt) {
-                    const size_t w = (size_t)a.disc_begin[r] * a.stride + i * 16;
-                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_val + w) : "memory");
-                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_vld + w) : "memory");
-                }
-            }
-    }
+    // Programmatic dependent launch (levelised pass, a.pdl): the next level's kernel of this stream may be launched while
+    // this one runs — early: as soon as every CTA of this grid has started; late: when every CTA is about to finish — and
+    // overlaps its launch and its index loads (which depend on nothing this grid writes) with this grid's tail; it does not
+    // touch a row before griddepcontrol.wait below, i.e. before this grid has completed and its writes are visible.
+    if (!JACOBI && a.pdl == 1) asm volatile("griddepcontrol.launch_dependents;");
     if (pair >= a.pairs) return;
     const size_t col = (size_t)pair * 2;
     const uint32_t g0 = a.g_begin + gb * (blockDim.y * U) + threadIdx.y;
@@ -153,6 +141,26 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : ((U == 2 && NIN == 2 && !KV)
         orow[u] = a.row_base + gg;
         if (!JACOBI && !KV) far[u] = a.far ? a.far[gg] : 0;
     }
+    if (!JACOBI && a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!JACOBI) {
+        // Rows nobody will read again: invalidate their L2 lines without write-back, so they never cost HBM bandwidth (the level
+        // that read them last ran in an earlier launch on this stream).  One 128-byte line per plane per thread and round.
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+            if (a.disc_end[r] > a.disc_begin[r]) {
+                // (by the CTAs that start first: the sooner a dead line is dropped, the likelier it has not been written back yet)
+                const uint64_t lines = (uint64_t)(a.disc_end[r] - a.disc_begin[r]) * (a.stride >> 4);
+                const uint32_t n_cta = min(gridDim.x, 296u);
+                if (blockIdx.x >= n_cta) break;
+                const uint64_t nt = (uint64_t)n_cta * 256;
+                for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.y * blockDim.x + threadIdx.x; i < lines; i += nt) {
+                    const size_t w = (size_t)a.disc_begin[r] * a.stride + i * 16;
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_val + w) : "memory");
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_vld + w) : "memory");
+                }
+            }
+    }
+
     bool k0[U], k1[U], k2[U], act[U];
     bool any_act = false;
     const bool allv = KV && *a.all_valid != 0;  // uniform: with all drives valid no per-row flag is read or written
@@ -248,6 +256,7 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : ((U == 2 && NIN == 2 && !KV)
         if (dx) atomicOr((unsigned long long *)&a.changed[col], (unsigned long long)dx);
         if (dy) atomicOr((unsigned long long *)&a.changed[col + 1], (unsigned long long)dy);
     }
+    if (!JACOBI && a.pdl == 2) asm volatile("griddepcontrol.launch_dependents;");
 }
 
 // ---- unit-delay frontier as a compacted work list (gsim's component_update_queue, at row
@@ -1366,6 +1375,7 @@ void Engine::copy_options_from(const Engine &o) {
     opt_u_ = o.opt_u_;
     opt_period2_ = o.opt_period2_;
     opt_l2_hints_ = o.opt_l2_hints_;
+    opt_pdl_ = o.opt_pdl_;
     opt_discard_ = o.opt_discard_;
     disc_short_ = o.disc_short_;
     disc_never_ = o.disc_never_;
@@ -2123,7 +2133,7 @@ int Engine::run_levelised(bool async) {
     // CUDA graph and replayed per run, which takes the per-launch CPU cost and most of the
     // launch-to-launch gap out of small tiles (hundreds of levels of a few microseconds each).
     const bool want_graph = opt_graph_ && net_.levels.size() >= 8;
-    const uint64_t gkey = ((uint64_t)(uintptr_t)V) ^ ((uint64_t)stride_ << 2) ^ (kv ? 1u : 0u) ^ (opt_l2_hints_ ? 2u : 0u) ^ (opt_discard_ ? 8u : 0u);
+    const uint64_t gkey = ((uint64_t)(uintptr_t)V) ^ ((uint64_t)stride_ << 2) ^ (kv ? 1u : 0u) ^ (opt_l2_hints_ ? 2u : 0u) ^ (opt_discard_ ? 8u : 0u) ^ ((uint64_t)opt_pdl_ << 4);
     if (want_graph && level_graph_exec_ && level_graph_key_ == gkey) {
         CU_TRY(cudaGraphLaunch((cudaGraphExec_t)level_graph_exec_, ST));
         g_launches.fetch_add(level_graph_nodes_, std::memory_order_relaxed);
@@ -2162,17 +2172,25 @@ int Engine::run_levelised(bool async) {
                 const uint32_t U = (opt_u_ ? opt_u_ : (ctas4 >= 148 * 3 * 4 ? 4u : 2u));
                 const uint32_t per = sh.block.y * U;
                 const uint32_t gb = (n_g + per - 1) / per;
-                if (U == 4) {
-                    if (kv)
-                        k_eval2<4, false, true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
-                    else
-                        k_eval2<4, false, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
-                } else {
-                    if (kv)
-                        k_eval2<2, false, true><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
-                    else
-                        k_eval2<2, false, false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
-                }
+                a.pdl = kv ? 0 : opt_pdl_;
+                auto launch = [&](void (*kern)(const Eval2Args)) {
+                    if (!a.pdl) {
+                        kern<<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
+                        return;
+                    }
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(sh.pair_blocks * gb);
+                    cfg.blockDim = sh.block;
+                    cfg.stream = ST;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = 1;
+                    cudaLaunchKernelEx(&cfg, kern, a);
+                };
+                if (U == 4) launch(kv ? k_eval2<4, false, true> : k_eval2<4, false, false>);
+                else launch(kv ? k_eval2<2, false, true> : k_eval2<2, false, false>);
                 nodes++;
             }
             if (lv.g3_end > lv.g3_begin) {

@@ -103,6 +103,7 @@ class Engine {
     void set_use_frontier(bool on) { opt_frontier_ = on; frontier_valid_ = false; }
     void set_device_loop(bool on) { opt_device_loop_ = on; }
     void set_period2_skip(bool on) { opt_period2_ = on; }
+    void set_pdl(uint32_t mode) { opt_pdl_ = mode <= 2 ? mode : 0; level_graph_key_ = 0; }
     // SURVEY.md A.6-2 alternative (agreeing valid drivers do not conflict); refused for netlists with two firm drivers on a net
     bool set_lenient_conflicts(bool on) {
         if (on && net_.multi_driver) return false;
@@ -226,7 +227,8 @@ class Engine {
     bool opt_discard_ = false;
     struct RowRange { uint32_t begin, end; };
     std::vector<RowRange> disc_short_, disc_never_;  // per level: rows of the one/two-input class that may be dropped
-    bool opt_l2_hints_ = false;  // levelised pass: evict-first hint on fan-ins produced long ago (Compiled::far2)
+    bool opt_l2_hints_ = false;
+    uint32_t opt_pdl_ = 2;  // programmatic dependent launch between the level kernels: 0 off, 1 early release, 2 late release  // levelised pass: evict-first hint on fan-ins produced long ago (Compiled::far2)
     bool opt_period2_ = true;   // unit-delay loops fast-forward over an exact period-2 oscillation
     uint32_t opt_flags_ = 0;    // SemFlags: the reconstructed points of SURVEY.md A.6-4..7, one bit each
     bool use_resident_ = true, resident_attr_set_ = false;

@@ -312,6 +312,7 @@ class Simulator:
     OPT_CONFLICT_NEEDS_DISAGREE = 8
     OPT_L2_HINTS = 9
     OPT_PERIOD2_SKIP = 10
+    OPT_PDL = 11
 
     def set_option(self, option: int, value: int):
         _check(self._lib.b2_sim_set_option(self._h, option, value), "set_option")

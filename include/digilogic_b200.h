@@ -217,6 +217,9 @@ enum b2_option {
     B2_OPT_L2_HINTS = 9,       /* default 1.  Levelised pass: fan-in rows produced more than one level below the reading gate are
                                   loaded with an L2 evict-first hint (createpolicy + ld.L2::cache_hint), so that these one-off reads
                                   do not displace the rows the previous level has just written and the next kernel re-reads. */
+    B2_OPT_PDL = 11,           /* Levelised pass: consecutive level kernels of a simulator are launched with programmatic stream
+                                  serialisation (griddepcontrol): the next level's launch and index loads overlap this level's tail.
+                                  0 off, 1 dependents released when every CTA has started, 2 (default) when every CTA is about to finish. */
     B2_OPT_PERIOD2_SKIP = 10,  /* default 1.  Unit-delay loops (device-side loop, resident kernel) detect an exact period-2 oscillation
                                   — every row an application writes equals the row two applications earlier — and jump ahead by an
                                   even number of applications: the state, lane results and step accounting are those of walking
