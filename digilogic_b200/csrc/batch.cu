@@ -639,21 +639,25 @@ int Batch::run_replicas(int stim_mode, uint64_t seed, uint64_t word_begin, const
         const int r = e.run(max_steps, nullptr, nullptr, true);
         if (r < 0) return -r;
         worst = std::max(worst, r);
-        if (out_val && n_out) {
-            const uint64_t w = out_ring ? w0 % out_ring : w0;
-            if ((rc = e.gather_wires(outputs_.data(), n_out, out_val + w, out_vld + w, out_stride, !out_is_host, true))) return rc;
-        }
-        if (comm_ && n_out) {
-            const uint64_t plane = (uint64_t)n_out * words_local_;
-            uint64_t *gv = gat_val_ + (uint64_t)comm_->rank() * plane + w0, *gm = gat_vld_ + (uint64_t)comm_->rank() * plane + w0;
-            if ((rc = e.gather_wires(outputs_.data(), n_out, gv, gm, words_local_, true, true))) return rc;
-            if (peers_mapped_)
-                for (int p = 0; p < comm_->n_ranks(); p++) {
-                    if (p == comm_->rank()) continue;
-                    if ((rc = e.gather_wires(outputs_.data(), n_out, peer_val_[p] + (uint64_t)comm_->rank() * plane + w0,
-                                             peer_vld_[p] + (uint64_t)comm_->rank() * plane + w0, words_local_, true, true)))
-                        return rc;
+        if (n_out) {
+            // every device destination of the tile's output rows — the caller's planes, this rank's share of the gathered planes
+            // on this GPU and on every peer whose planes are mapped — is served by ONE kernel on the replica's side stream
+            // (rows read once, 128-bit stores, peers over NVLink) while the replica's stream goes on with its next tile
+            std::vector<Engine::GatherDst> dsts;
+            if (out_val) {
+                const uint64_t w = out_ring ? w0 % out_ring : w0;
+                if (out_is_host) {
+                    if ((rc = e.gather_wires(outputs_.data(), n_out, out_val + w, out_vld + w, out_stride, false, true))) return rc;
+                } else {
+                    dsts.push_back(Engine::GatherDst{out_val + w, out_vld + w, out_stride});
                 }
+            }
+            if (comm_) {
+                const uint64_t plane = (uint64_t)n_out * words_local_, off = (uint64_t)comm_->rank() * plane + w0;
+                for (int p = 0; p < comm_->n_ranks(); p++)
+                    if (peer_val_[p]) dsts.push_back(Engine::GatherDst{peer_val_[p] + off, peer_vld_[p] + off, words_local_});
+            }
+            if (!dsts.empty() && (rc = e.gather_wires_multi(outputs_.data(), n_out, dsts.data(), (uint32_t)dsts.size()))) return rc;
         }
     }
     for (uint32_t k = 0; k < K_; k++) {

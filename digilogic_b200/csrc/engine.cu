@@ -781,6 +781,39 @@ __global__ void __launch_bounds__(256) k_gather_rows(const uint32_t *rows, uint3
     }
 }
 
+// the same rows to up to kMaxGatherDst destinations: read once, stored to every destination (own planes, peer GPUs' planes)
+static const uint32_t kMaxGatherDst = 9;
+struct GatherDsts {
+    uint64_t *val[kMaxGatherDst], *vld[kMaxGatherDst];
+    uint64_t stride[kMaxGatherDst];
+    uint32_t n;
+};
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_gather_rows_multi(const uint32_t *rows, uint32_t n, const uint64_t *val, const uint64_t *vld,
+                                                           uint32_t stride, uint32_t n_words, const GatherDsts d, const uint8_t *kv,
+                                                           const uint32_t *all_valid) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) * (VEC ? 2 : 1);
+    const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (w >= n_words || i >= n) return;
+    const size_t s = (size_t)rows[i] * stride + w;
+    const bool elided = kv && (*all_valid || kv[rows[i]]);
+    if (VEC) {
+        const ulonglong2 v = ld_stream(val + s), m = elided ? make_ulonglong2(~0ull, ~0ull) : ld_stream(vld + s);
+        for (uint32_t k = 0; k < d.n; k++) {
+            const size_t o = (size_t)i * d.stride[k] + w;
+            st_pair(d.val[k] + o, v);
+            st_pair(d.vld[k] + o, m);
+        }
+    } else {
+        const uint64_t v = val[s], m = elided ? ~0ull : vld[s];
+        for (uint32_t k = 0; k < d.n; k++) {
+            const size_t o = (size_t)i * d.stride[k] + w;
+            d.val[k][o] = v;
+            d.vld[k][o] = m;
+        }
+    }
+}
+
 // dense planes [n][src_stride] -> drive rows given by pointer tables
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_scatter_rows(uint64_t *const *row_val, uint64_t *const *row_vld, uint32_t n,
@@ -1446,7 +1479,11 @@ Engine::~Engine() {
     if (own_stream_ && stream_) cudaStreamDestroy(ST);
     if (cin_stream_) cudaStreamDestroy(CIN);
     if (cout_stream_) cudaStreamDestroy(COUT);
-    for (void *e : {ev_drive_consumed_, ev_drives_ready_, ev_gathered_, ev_out_free_})
+    if (side_stream_) {
+        cudaStreamSynchronize((cudaStream_t)side_stream_);
+        cudaStreamDestroy((cudaStream_t)side_stream_);
+    }
+    for (void *e : {ev_drive_consumed_, ev_drives_ready_, ev_gathered_, ev_out_free_, ev_settled_, ev_side_done_})
         if (e) cudaEventDestroy(EV(e));
     for (void *e : ev_flags_)
         if (e) cudaEventDestroy(EV(e));
@@ -2658,6 +2695,10 @@ int Engine::run(uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled, boo
     int rc = ensure_lanes();
     if (rc) return -rc;
     if ((rc = flush_pending_drives())) return -rc;
+    if (side_pending_) {  // a gather of the previous run's rows may still be reading the store on the side stream
+        if (cudaStreamWaitEvent(ST, EV(ev_side_done_), 0) != cudaSuccess) return -B2_ERR_CUDA;
+        side_pending_ = false;
+    }
     snap_valid_ = false;
     // acyclic, single-driver, and the step budget covers the depth: the unique fixed point, level by level
     const bool dag_ok = !net_.cyclic && max_steps >= (uint64_t)net_.depth + 1;
@@ -2799,10 +2840,59 @@ void Engine::set_discard(bool on, const uint32_t *keep_wires, uint32_t n) {
     }
 }
 
-// The main stream waits for the last asynchronous read-back (gather_wires(..., async)) of this simulator.
+int Engine::gather_wires_multi(const uint32_t *wires, uint32_t n, const GatherDst *dsts, uint32_t n_dst) {
+    if (n && (!wires || !dsts)) return B2_ERR_NULL;
+    int rc = ensure_lanes();
+    if (rc) return rc;
+    if (n == 0 || n_dst == 0) return B2_OK;
+    if ((rc = upload_rows(wires, n, false))) return rc;
+    if (!side_stream_) {
+        cudaStream_t st;
+        CU_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        side_stream_ = st;
+        for (void **e : {&ev_settled_, &ev_side_done_}) {
+            cudaEvent_t ev;
+            CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            *e = ev;
+        }
+    }
+    cudaStream_t side = (cudaStream_t)side_stream_;
+    CU_TRY(cudaEventRecord(EV(ev_settled_), ST));
+    CU_TRY(cudaStreamWaitEvent(side, EV(ev_settled_), 0));
+    const uint8_t *kvp = elided_ ? d_kv_ : nullptr;
+    for (uint32_t first = 0; first < n_dst; first += kMaxGatherDst) {
+        GatherDsts d;
+        d.n = std::min<uint32_t>(kMaxGatherDst, n_dst - first);
+        bool vec = T_ % 2 == 0;
+        for (uint32_t k = 0; k < d.n; k++) {
+            d.val[k] = dsts[first + k].val;
+            d.vld[k] = dsts[first + k].vld;
+            d.stride[k] = dsts[first + k].stride;
+            if (d.stride[k] < T_) return B2_ERR_RANGE;
+            vec = vec && d.stride[k] % 2 == 0 && (((uintptr_t)d.val[k] | (uintptr_t)d.vld[k]) & 15) == 0;
+        }
+        if (vec) {
+            dim3 block(64, 4), grid((T_ / 2 + 63) / 64, (n + 3) / 4);
+            k_gather_rows_multi<true><<<grid, block, 0, side>>>(d_rows_, n, val_[cur_], vld_[cur_], stride_, T_, d, kvp, d_all_valid_);
+        } else {
+            dim3 block(64, 4), grid((T_ + 63) / 64, (n + 3) / 4);
+            k_gather_rows_multi<false><<<grid, block, 0, side>>>(d_rows_, n, val_[cur_], vld_[cur_], stride_, T_, d, kvp, d_all_valid_);
+        }
+        LAUNCHED();
+    }
+    CU_TRY(cudaEventRecord(EV(ev_side_done_), side));
+    side_pending_ = true;
+    return B2_OK;
+}
+
+// The main stream waits for the last asynchronous read-backs (gather_wires(..., async), gather_wires_multi) of this simulator.
 int Engine::join_copies() {
     if (!device_ready_) return B2_OK;
     CU_TRY(cudaStreamWaitEvent(ST, EV(ev_out_free_), 0));
+    if (side_pending_) {
+        CU_TRY(cudaStreamWaitEvent(ST, EV(ev_side_done_), 0));
+        side_pending_ = false;
+    }
     return B2_OK;
 }
 

@@ -79,6 +79,14 @@ class Engine {
     int get_wire_lanes(uint32_t wire, uint32_t bit, uint32_t w0, uint32_t nw, uint64_t *value, uint64_t *valid);
     int gather_wires(const uint32_t *wires, uint32_t n, uint64_t *value, uint64_t *valid, size_t dst_stride, bool dst_is_device,
                      bool async = false);
+    // Output rows of bit 0 of n wires to several DEVICE destinations at once (own planes, peer GPUs' planes) with one kernel on
+    // a side stream: the rows are read once, and the simulator's stream goes on with its next run meanwhile (the next run's
+    // first write to the store waits for the side stream).
+    struct GatherDst {
+        uint64_t *val, *vld;
+        uint64_t stride;
+    };
+    int gather_wires_multi(const uint32_t *wires, uint32_t n, const GatherDst *dsts, uint32_t n_dst);
     int join_copies();
     // every lane back to the state of a freshly built simulator (wires and component outputs as at build time); drives are kept
     void reset_cold() { cold_ = true; frontier_valid_ = false; snap_valid_ = false; }
@@ -178,6 +186,8 @@ class Engine {
     void *cin_stream_ = nullptr, *cout_stream_ = nullptr;                  // cudaStream_t
     void *ev_drive_consumed_ = nullptr, *ev_drives_ready_ = nullptr;       // cudaEvent_t
     void *ev_gathered_ = nullptr, *ev_out_free_ = nullptr;
+    void *side_stream_ = nullptr, *ev_settled_ = nullptr, *ev_side_done_ = nullptr;  // gather_wires_multi
+    bool side_pending_ = false;
     bool cin_pending_ = false;
     void *ev_flags_[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t *d_rows_ = nullptr;
