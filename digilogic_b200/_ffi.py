@@ -46,6 +46,9 @@ SIGNATURES = {
     "b2_add_horizontal_gate": (i32, [vp, i32, u32, u32, pu32]),
     "b2_add_add": (i32, [vp, u32, u32, u32, pu32]),
     "b2_add_sub": (i32, [vp, u32, u32, u32, pu32]),
+    "b2_add_mul": (i32, [vp, u32, u32, u32, pu32]),
+    "b2_add_compare": (i32, [vp, i32, u32, u32, u32, pu32]),
+    "b2_add_shift": (i32, [vp, i32, u32, u32, u32, pu32]),
     "b2_add_slice": (i32, [vp, u32, u32, u32, pu32]),
     "b2_add_merge": (i32, [vp, pu32, sz, u32, pu32]),
     "b2_add_gates2": (i32, [vp, vp, vp, vp, vp, sz]),

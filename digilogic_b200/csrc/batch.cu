@@ -534,7 +534,7 @@ int Batch::run_sweep(int stim_mode, uint64_t seed, uint64_t word_begin, const ui
     SweepArgs a;
     std::memset(&a, 0, sizeof(a));
     a.fan0 = dnet_->fan0; a.fan1 = dnet_->fan1; a.fan2 = dnet_->fan2; a.kind2 = dnet_->kind2;
-    a.wide_off = dnet_->wide_off; a.wide_in = dnet_->wide_in; a.wide_kind = dnet_->wide_kind; a.wide_nsel = dnet_->wide_nsel;
+    a.wide_off = dnet_->wide_off; a.wide_in = dnet_->wide_in; a.wide_kind = dnet_->wide_kind; a.wide_nsel = dnet_->wide_nsel; a.wide_aux = dnet_->wide_aux;
     a.val = val_; a.vld = vld_;
     a.slot_words = (uint64_t)std::max<uint32_t>(net_.n_rows, 1) * T_;
     a.segs = d_segs_; a.seg_task0 = d_seg_task0_;

@@ -88,6 +88,29 @@ int b2_add_sub(b2_builder *b, uint32_t input_a, uint32_t input_b, uint32_t outpu
     GUARD_END(B2_ERR_OUT_OF_MEMORY)
 }
 
+int b2_add_mul(b2_builder *b, uint32_t input_a, uint32_t input_b, uint32_t output, uint32_t *out_cell) {
+    if (!b) return B2_ERR_NULL;
+    GUARD_BEGIN
+    return b->b.add_arith(b2::K_MUL, input_a, input_b, output, out_cell);
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
+int b2_add_compare(b2_builder *b, int op, uint32_t input_a, uint32_t input_b, uint32_t output, uint32_t *out_cell) {
+    if (!b) return B2_ERR_NULL;
+    GUARD_BEGIN
+    return b->b.add_compare(op, input_a, input_b, output, out_cell);
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
+int b2_add_shift(b2_builder *b, int kind, uint32_t input, uint32_t amount, uint32_t output, uint32_t *out_cell) {
+    if (!b) return B2_ERR_NULL;
+    GUARD_BEGIN
+    const int k = kind == B2_SHIFT_LEFT ? b2::K_SHL : kind == B2_SHIFT_LOGICAL_RIGHT ? b2::K_LSHR : kind == B2_SHIFT_ARITHMETIC_RIGHT ? b2::K_ASHR : -1;
+    if (k < 0) return B2_ERR_INVALID_ARG;
+    return b->b.add_shift(k, input, amount, output, out_cell);
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
 int b2_add_horizontal_gate(b2_builder *b, int kind, uint32_t input, uint32_t output, uint32_t *out_cell) {
     if (!b) return B2_ERR_NULL;
     GUARD_BEGIN

@@ -108,6 +108,74 @@ __device__ __forceinline__ void reg_word(u64 dv, u64 dm, u64 ev, u64 em, u64 cv,
     rv = (take & (dv | ~dm)) | (keep & (ov | ~om)) | undef;
 }
 
+// Multiplier, comparator and shifter bits (gsim add_mul, add_compare_*, add_*_shift restated) on one
+// 64-lane word.  val(i) / vld(i): value / valid word of the gate's i-th input entry (layout: see netlist.hpp Kind).  Any input
+// bit that is not a valid 0/1 makes the result Undefined, like add / sub.  Correct for every width up to 255; the multiplier
+// is cubic in the width per wire (a bit-sliced column adder per result bit) — these components are not on any hot path.
+template <class FV, class FM>
+__device__ __forceinline__ void arith_word(uint32_t kind, uint32_t n_in, uint32_t nsel, uint32_t aux, FV val, FM vld, u64 &rv, u64 &rm) {
+    u64 ok = ~0ull;
+    for (uint32_t i = 0; i < n_in; i++) ok &= vld(i);
+    u64 r = 0;
+    if (kind == K_MUL) {
+        const uint32_t w = n_in / 2, j = nsel;
+        u64 cnt[10];  // bit-sliced counter of the current column: sum of its partial products + the carries of the columns below
+#pragma unroll
+        for (int k = 0; k < 10; k++) cnt[k] = 0;
+        for (uint32_t c = 0; c <= j; c++) {
+            for (uint32_t i = 0; i <= c; i++) {
+                u64 carry = val(i) & val(w + c - i);
+#pragma unroll
+                for (int k = 0; k < 10; k++) {
+                    const u64 t = cnt[k] & carry;
+                    cnt[k] ^= carry;
+                    carry = t;
+                }
+            }
+            if (c == j) r = cnt[0];
+#pragma unroll
+            for (int k = 0; k < 9; k++) cnt[k] = cnt[k + 1];
+            cnt[9] = 0;
+        }
+    } else if (kind == K_CMP) {
+        const uint32_t w = n_in / 2;
+        u64 lt = 0, eq = ~0ull;  // unsigned, from the top bit down
+        for (uint32_t t = w; t-- > 0;) {
+            const u64 x = val(t), y = val(w + t);
+            lt |= eq & ~x & y;
+            eq &= ~(x ^ y);
+        }
+        if (aux >= CMP_LTS) {  // signs differ: the negative operand is the smaller one
+            const u64 sx = val(w - 1), diff = sx ^ val(2 * w - 1);
+            lt = (diff & sx) | (~diff & lt);
+        }
+        switch (aux) {
+            case CMP_EQ: r = eq; break;
+            case CMP_NE: r = ~eq; break;
+            case CMP_LTU:
+            case CMP_LTS: r = lt; break;
+            case CMP_GTU:
+            case CMP_GTS: r = ~lt & ~eq; break;
+            case CMP_LEU:
+            case CMP_LES: r = lt | eq; break;
+            default: r = ~lt; break;
+        }
+    } else {  // K_SHL / K_LSHR / K_ASHR: result bit j = the source bit of whichever amount the lane holds
+        const uint32_t k = aux, w = n_in - k, j = nsel;
+        const u64 sign = kind == K_ASHR ? val(w - 1) : 0;
+        for (uint32_t amt = 0; amt < (1u << k); amt++) {
+            u64 match = ~0ull;
+            for (uint32_t s = 0; s < k; s++) match &= ((amt >> s) & 1) ? val(w + s) : ~val(w + s);
+            u64 src;
+            if (kind == K_SHL) src = j >= amt ? val(j - amt) : 0;
+            else src = j + amt < w ? val(j + amt) : sign;
+            r |= match & src;
+        }
+    }
+    rm = ok;
+    rv = r | ~ok;
+}
+
 // Driver conflict between two operands of a wire: both not High-Z; with `lenient` (the A.6-2
 // alternative) two valid operands that agree do not conflict.
 __device__ __forceinline__ u64 conflict_of(u64 av, u64 am, u64 bv, u64 bm, int lenient) {
@@ -144,6 +212,7 @@ struct WideArgs {
     const uint32_t *all_valid;  // as in Eval2Args (nullable)
     uint32_t sem = 0;           // SemFlags of the netlist
     uint32_t *p2diff = nullptr; // device-side loop: period-2 detector (see Eval2Args)
+    const uint8_t *aux = nullptr; // per gate: comparator op / width of a shift amount
 };
 
 __device__ __forceinline__ ulonglong2 ld_valid(const WideArgs &a, uint32_t row, size_t col) {
@@ -193,6 +262,14 @@ __device__ __forceinline__ void eval_wide_gate(const WideArgs &a, uint32_t pb, u
         rm = ok;
         rv.x = sum.x | ~ok.x;
         rv.y = sum.y | ~ok.y;
+    } else if (kind >= K_MUL && kind <= K_ASHR) {
+        const uint32_t n_in = e - b, nsel = a.nsel[g], aux = a.aux ? a.aux[g] : 0;
+        auto vx = [&](uint32_t i) { return (u64) * (const volatile uint64_t *)(a.in_val + (size_t)a.in[b + i] * a.stride + col); };
+        auto vy = [&](uint32_t i) { return (u64) * (const volatile uint64_t *)(a.in_val + (size_t)a.in[b + i] * a.stride + col + 1); };
+        auto mx = [&](uint32_t i) { return (u64)ld_valid(a, a.in[b + i], col).x; };
+        auto my = [&](uint32_t i) { return (u64)ld_valid(a, a.in[b + i], col).y; };
+        arith_word(kind, n_in, nsel, aux, vx, mx, rv.x, rm.x);
+        arith_word(kind, n_in, nsel, aux, vy, my, rv.y, rm.y);
     } else if (kind == K_REG) {
         const size_t rd = (size_t)a.in[b] * a.stride + col, re = (size_t)a.in[b + 1] * a.stride + col,
                      rc = (size_t)a.in[b + 2] * a.stride + col, rp = (size_t)a.in[b + 3] * a.stride + col,

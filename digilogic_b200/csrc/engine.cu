@@ -1040,7 +1040,7 @@ struct ResidentArgs {
     const uint32_t *fan0, *fan1, *fan2;
     const uint8_t *kind2;
     const uint32_t *woff, *win;
-    const uint8_t *wkind, *wnsel;
+    const uint8_t *wkind, *wnsel, *waux;
     const uint32_t *res_off, *res_in; // tri-state nets: driver rows per resolved row (see k_resolve)
     const int32_t *res_xslot;
     uint32_t n_res;
@@ -1088,6 +1088,10 @@ __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g
         }
         rm = ok;
         rv = sum | ~ok;
+    } else if (kind >= K_MUL && kind <= K_ASHR) {
+        auto v = [&](uint32_t i) { return (u64)av[(size_t)a.win[b + i] * wpc + j]; };
+        auto m = [&](uint32_t i) { return (u64)am[(size_t)a.win[b + i] * wpc + j]; };
+        arith_word(kind, e - b, a.wnsel[g], a.waux[g], v, m, rv, rm);
     } else if (kind == K_REG) {
         const size_t rd = (size_t)a.win[b] * wpc + j, re = (size_t)a.win[b + 1] * wpc + j, rc = (size_t)a.win[b + 2] * wpc + j,
                      rp = (size_t)a.win[b + 3] * wpc + j, ro = (size_t)(a.n_src + a.n_g2 + a.n_g3 + g) * wpc + j;
@@ -1427,6 +1431,7 @@ DeviceNet::~DeviceNet() {
     cudaFree(wide_in);
     cudaFree(wide_kind);
     cudaFree(wide_nsel);
+    cudaFree(wide_aux);
     cudaFree(res_off);
     cudaFree(res_in);
     cudaFree(levels);
@@ -1450,7 +1455,7 @@ std::shared_ptr<DeviceNet> NetShare::acquire(int device, int &rc) {
     d->device = device;  // from here on the destructor frees whatever was allocated
     if ((rc = upload(&d->fan0, net.fan0)) || (rc = upload(&d->fan1, net.fan1)) || (rc = upload(&d->fan2, net.fan2)) ||
         (rc = upload(&d->kind2, net.kind2)) || (rc = upload(&d->far2, net.far2)) || (rc = upload(&d->wide_off, net.wide_off)) || (rc = upload(&d->wide_in, net.wide_in)) ||
-        (rc = upload(&d->wide_kind, net.wide_kind)) || (rc = upload(&d->wide_nsel, net.wide_nsel)) ||
+        (rc = upload(&d->wide_kind, net.wide_kind)) || (rc = upload(&d->wide_nsel, net.wide_nsel)) || (rc = upload(&d->wide_aux, net.wide_aux)) ||
         (rc = upload(&d->res_off, net.res_off)) || (rc = upload(&d->res_in, net.res_in)) || (rc = upload(&d->levels, net.levels)))
         return nullptr;
     on_device[device] = d;
@@ -1626,7 +1631,7 @@ int Engine::ensure_device() {
         dnet_ = share_->acquire(device_, rc);
         if (!dnet_) return rc;
         d_fan0_ = dnet_->fan0; d_fan1_ = dnet_->fan1; d_fan2_ = dnet_->fan2; d_kind2_ = dnet_->kind2; d_far2_ = dnet_->far2;
-        d_wide_off_ = dnet_->wide_off; d_wide_in_ = dnet_->wide_in; d_wide_kind_ = dnet_->wide_kind; d_wide_nsel_ = dnet_->wide_nsel;
+        d_wide_off_ = dnet_->wide_off; d_wide_in_ = dnet_->wide_in; d_wide_kind_ = dnet_->wide_kind; d_wide_nsel_ = dnet_->wide_nsel; d_wide_aux_ = dnet_->wide_aux;
         d_res_off_ = dnet_->res_off; d_res_in_ = dnet_->res_in; d_levels_ = dnet_->levels;
     }
     // a retry after a failure midway finds the earlier objects and keeps them
@@ -2245,6 +2250,7 @@ int Engine::run_levelised(bool async) {
             if (lv.wide_end > lv.wide_begin) {
                 WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, V, M, V, M, nullptr, lv.wide_begin, lv.wide_end,
                            net_.n_src + net_.n_fast(), stride_, pairs, sh.pair_blocks, kv ? d_kv_ : nullptr, nullptr, nullptr, d_all_valid_};
+                a.aux = d_wide_aux_;
                 a.sem = net_.sem_flags;
                 const uint32_t gb = (lv.wide_end - lv.wide_begin + sh.block.y - 1) / sh.block.y;
                 k_eval_wide<false><<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
@@ -2331,6 +2337,7 @@ int Engine::run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &res
     la.bail_row_words = 4 * kLoopEntryRowWords;
     la.sem = net_.sem_flags;
     la.wide.sem = net_.sem_flags;
+    la.wide.aux = d_wide_aux_;
     la.cur = cur_; la.chg_w = chg_w_; la.frontier_valid = frontier_valid_ ? 1 : 0;
     void *params[] = {&la};
     const uint32_t grid = sh.pair_blocks * (loop_ctas_ / sh.pair_blocks);
@@ -2533,6 +2540,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
         if (net_.n_wide()) {
             WideArgs a{d_wide_off_, d_wide_in_, d_wide_kind_, d_wide_nsel_, AV, AM, BV, BM, d_changed_, 0, net_.n_wide(),
                        net_.n_src + net_.n_fast(), stride_, pairs, sh.pair_blocks, nullptr, chg_prev, chg_cur, nullptr};
+            a.aux = d_wide_aux_;
             a.sem = net_.sem_flags;
             if (chg_prev) {  // event-driven: list the wide gates with a changed input, evaluate the list
                 k_frontier_scan_wide<<<(net_.n_wide() + 255) / 256, 256, 0, ST>>>(d_wide_off_, d_wide_in_, net_.n_wide(),
@@ -2630,7 +2638,7 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
     CU_TRY(cudaMemsetAsync(d_flags_, 0, 2 * sizeof(RunFlags), ST));
     ResidentArgs a;
     a.fan0 = d_fan0_; a.fan1 = d_fan1_; a.fan2 = d_fan2_; a.kind2 = d_kind2_;
-    a.woff = d_wide_off_; a.win = d_wide_in_; a.wkind = d_wide_kind_; a.wnsel = d_wide_nsel_;
+    a.woff = d_wide_off_; a.win = d_wide_in_; a.wkind = d_wide_kind_; a.wnsel = d_wide_nsel_; a.waux = d_wide_aux_;
     a.xrows = d_extra_rows_; a.xval = xdrv_val_; a.xvld = xdrv_vld_;
     a.res_off = d_res_off_; a.res_in = d_res_in_; a.res_xslot = d_res_xslot_; a.n_res = net_.n_res();
     a.dval = drv_val_; a.dvld = drv_vld_;

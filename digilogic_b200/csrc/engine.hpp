@@ -31,7 +31,7 @@ struct LoopResult;
 struct DeviceNet {
     int device = -1;
     uint32_t *fan0 = nullptr, *fan1 = nullptr, *fan2 = nullptr, *wide_off = nullptr, *wide_in = nullptr;
-    uint8_t *kind2 = nullptr, *far2 = nullptr, *wide_kind = nullptr, *wide_nsel = nullptr;
+    uint8_t *kind2 = nullptr, *far2 = nullptr, *wide_kind = nullptr, *wide_nsel = nullptr, *wide_aux = nullptr;
     uint32_t *res_off = nullptr, *res_in = nullptr;
     Level *levels = nullptr;
     ~DeviceNet();
@@ -152,6 +152,7 @@ class Engine {
 
     // netlist on the device (aliases into dnet_, which owns them)
     uint32_t *d_fan0_ = nullptr, *d_fan1_ = nullptr, *d_fan2_ = nullptr, *d_wide_off_ = nullptr, *d_wide_in_ = nullptr;
+    uint8_t *d_wide_aux_ = nullptr;
     uint8_t *d_kind2_ = nullptr, *d_far2_ = nullptr, *d_wide_kind_ = nullptr, *d_wide_nsel_ = nullptr;
 
     // wire-state store: two buffers (second one only for unit-delay runs), separate planes

@@ -40,7 +40,12 @@ static int push(Builder &b, uint8_t kind, const uint32_t *in, size_t n, uint32_t
         case K_MUX: bit_inputs = wout * (n + b.width[select]); break;
         case K_BUF: bit_inputs = wout * 2; break;
         case K_ADD:
-        case K_SUB: bit_inputs = wout * 2 * wout; break;
+        case K_SUB:
+        case K_MUL: bit_inputs = wout * 2 * wout; break;
+        case K_CMP: bit_inputs = 2ull * b.width[in[0]]; break;
+        case K_SHL:
+        case K_LSHR:
+        case K_ASHR: bit_inputs = wout * (wout + b.width[in[1]]); break;
         case K_HGATE: bit_inputs = b.width[in[0]] > 2 ? b.width[in[0]] : 2; break;
         case K_REG:
             bit_gates = wout + 1;
@@ -127,10 +132,34 @@ int Builder::add_merge(const uint32_t *in, size_t n, uint32_t output, uint32_t *
 // gsim SimulatorBuilder::add_add / add_sub(input_a, input_b, output): wrapping sum / difference of two wires of the output's
 // width, Undefined if any input bit is not a valid 0/1 (the Yosys importer's Add/Sub arms are todo!(), yosys.rs:188-189)
 int Builder::add_arith(int kind, uint32_t a, uint32_t b2, uint32_t output, uint32_t *cell) {
-    if (kind != K_ADD && kind != K_SUB) return B2_ERR_INVALID_ARG;
+    if (kind != K_ADD && kind != K_SUB && kind != K_MUL) return B2_ERR_INVALID_ARG;
     if (output >= width.size() || a >= width.size() || b2 >= width.size()) return B2_ERR_INVALID_WIRE_ID;
     if (width[a] != width[output] || width[b2] != width[output]) return B2_ERR_WIRE_WIDTH_MISMATCH;
     const uint32_t in[2] = {a, b2};
+    return push(*this, (uint8_t)kind, in, 2, 0, output, cell);
+}
+
+// gsim's comparators add_compare_{equal,not_equal,less_than,greater_than,less_than_or_equal,greater_than_or_equal}{,_signed}
+// (the Yosys importer's Lt/Le/Eq/Ne/Ge/Gt arms are todo!(), crates/digilogic_serde/src/yosys.rs:182-187): inputs of one width,
+// a one-bit output, Undefined if any input bit is not a valid 0/1
+int Builder::add_compare(int op, uint32_t a, uint32_t b2, uint32_t output, uint32_t *cell) {
+    if (op < CMP_EQ || op > CMP_GES) return B2_ERR_INVALID_ARG;
+    if (output >= width.size() || a >= width.size() || b2 >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    if (width[a] != width[b2]) return B2_ERR_WIRE_WIDTH_MISMATCH;
+    if (width[output] != 1) return B2_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    const uint32_t in[2] = {a, b2};
+    return push(*this, K_CMP, in, 2, (uint32_t)op, output, cell);
+}
+
+// gsim's shifters add_left_shift / add_logical_right_shift / add_arithmetic_right_shift(input, shift_amount, output) (Yosys
+// Shl/Sshl/Shr/Sshr are todo!(), yosys.rs:174-177): output as wide as the input, the amount an unsigned value of at most 8 bits;
+// amounts >= width shift everything out; Undefined if any bit of either input is not a valid 0/1
+int Builder::add_shift(int kind, uint32_t a, uint32_t amount, uint32_t output, uint32_t *cell) {
+    if (kind != K_SHL && kind != K_LSHR && kind != K_ASHR) return B2_ERR_INVALID_ARG;
+    if (output >= width.size() || a >= width.size() || amount >= width.size()) return B2_ERR_INVALID_WIRE_ID;
+    if (width[a] != width[output]) return B2_ERR_WIRE_WIDTH_MISMATCH;
+    if (width[amount] > 8) return B2_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    const uint32_t in[2] = {a, amount};
     return push(*this, (uint8_t)kind, in, 2, 0, output, cell);
 }
 
@@ -161,6 +190,7 @@ namespace {
 struct BitGate {
     uint8_t kind;
     uint8_t nsel;
+    uint8_t aux;
     uint32_t in_off, n_in;  // into bit_inputs (mux: select bits first)
     uint32_t out;           // bit-net, or NO_NET for a hidden gate (it has a row but drives no wire)
     uint32_t level;
@@ -198,6 +228,7 @@ void compile(const Builder &b, Compiled &c) {
             BitGate h;
             h.kind = K_RAW;
             h.nsel = 0;
+            h.aux = 0;
             h.in_off = (uint32_t)bin.size();
             h.n_in = 1;
             h.out = NO_NET;
@@ -210,6 +241,7 @@ void compile(const Builder &b, Compiled &c) {
             BitGate g;
             g.kind = cp.kind;
             g.nsel = 0;
+            g.aux = 0;
             g.in_off = (uint32_t)bin.size();
             g.out = c.bit_off[cp.output] + j;
             g.level = 0;
@@ -221,11 +253,20 @@ void compile(const Builder &b, Compiled &c) {
             if (cp.kind == K_BUF) {
                 bin.push_back(c.bit_off[in[0]] + j);  // data bit j
                 bin.push_back(c.bit_off[in[1]]);      // the one enable bit
-            } else if (cp.kind == K_ADD || cp.kind == K_SUB) {
-                // bit j of the result: needs every input bit for the validity and bits 0..j for the carry
+            } else if (cp.kind == K_ADD || cp.kind == K_SUB || cp.kind == K_MUL) {
+                // bit j of the result: needs every input bit for the validity and bits 0..j for the carries
                 g.nsel = (uint8_t)j;
                 for (uint32_t t = 0; t < wout; t++) bin.push_back(c.bit_off[in[0]] + t);
                 for (uint32_t t = 0; t < wout; t++) bin.push_back(c.bit_off[in[1]] + t);
+            } else if (cp.kind == K_CMP) {
+                g.aux = (uint8_t)cp.select;
+                for (uint32_t t = 0; t < b.width[in[0]]; t++) bin.push_back(c.bit_off[in[0]] + t);
+                for (uint32_t t = 0; t < b.width[in[1]]; t++) bin.push_back(c.bit_off[in[1]] + t);
+            } else if (cp.kind == K_SHL || cp.kind == K_LSHR || cp.kind == K_ASHR) {
+                g.nsel = (uint8_t)j;
+                g.aux = b.width[in[1]];
+                for (uint32_t t = 0; t < wout; t++) bin.push_back(c.bit_off[in[0]] + t);
+                for (uint32_t t = 0; t < b.width[in[1]]; t++) bin.push_back(c.bit_off[in[1]] + t);
             } else if (cp.kind == K_HGATE) {
                 const uint32_t wi = b.width[in[0]];
                 if (wi == 1) {  // one bit: the bit itself (High-Z read as X), inverted for NAND / NOR / XNOR
@@ -336,7 +377,7 @@ void compile(const Builder &b, Compiled &c) {
     // class 0: one/two inputs, class 1: three inputs (both on the fast kernels), class 2: CSR kernel
     auto cls = [&](uint32_t g) -> int {
         const uint8_t k = gates[g].kind;
-        return k == K_MUX || k == K_REG || k == K_ADD || k == K_SUB || gates[g].n_in > 3 ? 2 : (gates[g].n_in == 3 ? 1 : 0);
+        return k == K_MUX || k == K_REG || (k >= K_ADD && k <= K_ASHR) || gates[g].n_in > 3 ? 2 : (gates[g].n_in == 3 ? 1 : 0);
     };
     auto is_wide = [&](uint32_t g) { return cls(g) == 2; };
     // acyclic: lifetime class of the row of gate g — 0: read two or more levels above, 1: last reader in the level directly
@@ -419,12 +460,14 @@ void compile(const Builder &b, Compiled &c) {
     const uint32_t nw = G - n2;
     c.wide_kind.resize(nw);
     c.wide_nsel.resize(nw);
+    c.wide_aux.resize(nw);
     c.wide_off.assign((size_t)nw + 1, 0);
     c.wide_in.clear();
     for (uint32_t k = 0; k < nw; k++) {
         const BitGate &g = gates[order[n2 + k]];
         c.wide_kind[k] = g.kind;
         c.wide_nsel[k] = g.nsel;
+        c.wide_aux[k] = g.aux;
         c.wide_off[k] = (uint32_t)c.wide_in.size();
         for (uint32_t i = 0; i < g.n_in; i++) c.wide_in.push_back(row_of(bin[g.in_off + i]));
     }

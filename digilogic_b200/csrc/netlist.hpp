@@ -19,8 +19,13 @@ enum Kind : uint8_t {
     K_REG = 12,  // register bit: inputs = {data bit, enable, clock, previous-clock row}; reads its own row as the stored value
     K_RAW = 13,  // hidden one-input gate: raw copy (High-Z stays High-Z) — a register's view of its clock one step ago
     K_HGATE = 14, // builder-level only: reduction gate (kind in `select`), becomes an n-ary gate over the bits of its input
-    K_ADD = 15, K_SUB = 16  // one sum / difference bit: inputs = {a_0..a_{w-1}, b_0..b_{w-1}}, bit index in the nsel field
+    K_ADD = 15, K_SUB = 16, // one sum / difference bit: inputs = {a_0..a_{w-1}, b_0..b_{w-1}}, bit index in the nsel field
+    K_MUL = 17,  // one product bit: inputs as for K_ADD, bit index in nsel
+    K_CMP = 18,  // comparator (one bit): inputs = {a_0..a_{w-1}, b_0..b_{w-1}}, CmpOp in the aux field
+    K_SHL = 19, K_LSHR = 20, K_ASHR = 21  // one bit of a shifted wire: inputs = {a_0..a_{w-1}, amount_0..amount_{k-1}}, bit index in nsel, k in aux
 };
+
+enum CmpOp : uint8_t { CMP_EQ = 0, CMP_NE = 1, CMP_LTU = 2, CMP_GTU = 3, CMP_LEU = 4, CMP_GEU = 5, CMP_LTS = 6, CMP_GTS = 7, CMP_LES = 8, CMP_GES = 9 };
 
 // The points of gsim's behaviour that were reconstructed without its source, one switch each, default
 // off = the reading the CPU checker takes by default (its go_config switches; the product never links it).  They are properties of a netlist's
@@ -58,7 +63,9 @@ struct Builder {
     int add_mux(const uint32_t *in, size_t n, uint32_t select, uint32_t output, uint32_t *cell);
     int add_buffer(uint32_t in, uint32_t enable, uint32_t output, uint32_t *cell);
     int add_slice(uint32_t in, uint32_t offset, uint32_t output, uint32_t *cell);
-    int add_arith(int kind, uint32_t a, uint32_t b, uint32_t output, uint32_t *cell);  // K_ADD / K_SUB
+    int add_arith(int kind, uint32_t a, uint32_t b, uint32_t output, uint32_t *cell);  // K_ADD / K_SUB / K_MUL
+    int add_compare(int op, uint32_t a, uint32_t b, uint32_t output, uint32_t *cell);
+    int add_shift(int kind, uint32_t a, uint32_t amount, uint32_t output, uint32_t *cell);  // K_SHL / K_LSHR / K_ASHR
     int add_horizontal_gate(int kind, uint32_t in, uint32_t output, uint32_t *cell);
     int add_register(uint32_t data_in, uint32_t data_out, uint32_t enable, uint32_t clock, uint32_t *cell);
     int add_merge(const uint32_t *in, size_t n, uint32_t output, uint32_t *cell);
@@ -96,7 +103,7 @@ struct Compiled {
     uint32_t n_two = 0;
     // wide gates (n-ary, mux slices), CSR over store rows; mux: first n_sel entries are select bits
     std::vector<uint32_t> wide_off, wide_in;
-    std::vector<uint8_t> wide_kind, wide_nsel;
+    std::vector<uint8_t> wide_kind, wide_nsel, wide_aux;  // aux: comparator op / width of a shift amount
     std::vector<Level> levels;         // acyclic: one per level (1..depth); cyclic: a single entry
     uint32_t depth = 0;
     // cyclic: unit-delay evaluation only — feedback, or tri-state nets (their conflicts can be transient,

@@ -60,7 +60,7 @@ struct SweepArgs {
     const uint32_t *fan0, *fan1, *fan2;
     const uint8_t *kind2;
     const uint32_t *wide_off, *wide_in;
-    const uint8_t *wide_kind, *wide_nsel;
+    const uint8_t *wide_kind, *wide_nsel, *wide_aux;
     uint64_t *val, *vld;          // K slots back to back, slot_words apart
     uint64_t slot_words;          // n_rows * T
     const SweepSeg *segs;
@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(256, U2 == 4 ? 3 : 4) k_sweep(const SweepArgs 
                     WideArgs w{a.wide_off, a.wide_in, a.wide_kind, a.wide_nsel, V, M, V, M, nullptr, begin, end, a.n_src + a.n_fast,
                                a.T, a.pairs, 1, nullptr, nullptr, nullptr, nullptr};
                     w.sem = a.sem;
+                    w.aux = a.wide_aux;
                     for (uint32_t g = begin + threadIdx.y; g < end; g += blockDim.y) eval_wide_gate<false>(w, 0, g);
                 } break;
                 case SEG_STIM: sweep_stimulus(a, V, M, begin, end, w0, tile_words); break;

@@ -11,6 +11,7 @@ from . import _ffi
 from ._ffi import SimInfo
 
 AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX = range(8)
+CMP_EQ, CMP_NE, CMP_LTU, CMP_GTU, CMP_LEU, CMP_GEU, CMP_LTS, CMP_GTS, CMP_LES, CMP_GES = range(10)
 
 
 class AddComponentError(enum.IntEnum):
@@ -188,6 +189,39 @@ class SimulatorBuilder:
         cell = C.c_uint32()
         _check(self._lib.b2_add_sub(self._h, input_a, input_b, output, C.byref(cell)), "add_sub")
         return cell.value
+
+    def add_mul(self, input_a, input_b, output):
+        """gsim ``SimulatorBuilder::add_mul``: wrapping product; Undefined if any input bit is not valid."""
+        cell = C.c_uint32()
+        _check(self._lib.b2_add_mul(self._h, input_a, input_b, output, C.byref(cell)), "add_mul")
+        return cell.value
+
+    def add_compare(self, op, input_a, input_b, output):
+        """gsim ``add_compare_*``: op = CMP_EQ .. CMP_GES; one-bit output, Undefined if any input bit is not valid."""
+        cell = C.c_uint32()
+        _check(self._lib.b2_add_compare(self._h, op, input_a, input_b, output, C.byref(cell)), "add_compare")
+        return cell.value
+
+    def add_compare_equal(self, a, b, o): return self.add_compare(CMP_EQ, a, b, o)
+    def add_compare_not_equal(self, a, b, o): return self.add_compare(CMP_NE, a, b, o)
+    def add_compare_less_than(self, a, b, o): return self.add_compare(CMP_LTU, a, b, o)
+    def add_compare_greater_than(self, a, b, o): return self.add_compare(CMP_GTU, a, b, o)
+    def add_compare_less_than_or_equal(self, a, b, o): return self.add_compare(CMP_LEU, a, b, o)
+    def add_compare_greater_than_or_equal(self, a, b, o): return self.add_compare(CMP_GEU, a, b, o)
+    def add_compare_less_than_signed(self, a, b, o): return self.add_compare(CMP_LTS, a, b, o)
+    def add_compare_greater_than_signed(self, a, b, o): return self.add_compare(CMP_GTS, a, b, o)
+    def add_compare_less_than_or_equal_signed(self, a, b, o): return self.add_compare(CMP_LES, a, b, o)
+    def add_compare_greater_than_or_equal_signed(self, a, b, o): return self.add_compare(CMP_GES, a, b, o)
+
+    def add_shift(self, kind, input, amount, output):
+        """kind: "shl" / "lshr" / "ashr" (gsim add_left_shift / add_logical_right_shift / add_arithmetic_right_shift)."""
+        cell = C.c_uint32()
+        _check(self._lib.b2_add_shift(self._h, {"shl": 0, "lshr": 1, "ashr": 2}[kind], input, amount, output, C.byref(cell)), "add_shift")
+        return cell.value
+
+    def add_left_shift(self, input, amount, output): return self.add_shift("shl", input, amount, output)
+    def add_logical_right_shift(self, input, amount, output): return self.add_shift("lshr", input, amount, output)
+    def add_arithmetic_right_shift(self, input, amount, output): return self.add_shift("ashr", input, amount, output)
 
     def add_horizontal_gate(self, kind, input, output):
         """gsim ``add_horizontal_{and,or,xor,nand,nor,xnor}_gate``: the gate folded over all bits of one wire."""

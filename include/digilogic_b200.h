@@ -106,6 +106,22 @@ int b2_add_buffer(b2_builder *b, uint32_t input, uint32_t enable, uint32_t outpu
    the CSR kernel reading the input bits below it: correct for every width, quadratic in it. */
 int b2_add_add(b2_builder *b, uint32_t input_a, uint32_t input_b, uint32_t output, uint32_t *out_cell);
 int b2_add_sub(b2_builder *b, uint32_t input_a, uint32_t input_b, uint32_t output, uint32_t *out_cell);
+/* SimulatorBuilder::add_mul(input_a, input_b, output): output = a * b modulo 2^width, Undefined if any input bit is not a valid 0/1;
+   one width for all three wires (WireWidthMismatch).  No call site in the reference (Yosys Mul is todo!(), yosys.rs:190).  Each
+   result bit is one gate on the CSR kernel with a bit-sliced column adder: correct for every width, cubic in it per wire. */
+int b2_add_mul(b2_builder *b, uint32_t input_a, uint32_t input_b, uint32_t output, uint32_t *out_cell);
+/* SimulatorBuilder::add_compare_{equal,not_equal,less_than,greater_than,less_than_or_equal,greater_than_or_equal}{,_signed}
+   (input_a, input_b, output): inputs of one width (WireWidthMismatch), a one-bit output (WireWidthIncompatible), Undefined if any
+   input bit is not a valid 0/1.  No call site in the reference (Yosys Lt/Le/Eq/Ne/Ge/Gt are todo!(), yosys.rs:182-187). */
+enum b2_compare_op { B2_CMP_EQ = 0, B2_CMP_NE = 1, B2_CMP_LTU = 2, B2_CMP_GTU = 3, B2_CMP_LEU = 4, B2_CMP_GEU = 5,
+                     B2_CMP_LTS = 6, B2_CMP_GTS = 7, B2_CMP_LES = 8, B2_CMP_GES = 9 };
+int b2_add_compare(b2_builder *b, int op, uint32_t input_a, uint32_t input_b, uint32_t output, uint32_t *out_cell);
+/* SimulatorBuilder::add_left_shift / add_logical_right_shift / add_arithmetic_right_shift(input, shift_amount, output): output as
+   wide as the input (WireWidthMismatch), the amount an unsigned value of at most 8 bits (WireWidthIncompatible); amounts >= width
+   shift everything out (zeros, or the sign); Undefined if any bit of either input is not a valid 0/1.  No call site in the
+   reference (Yosys Shl/Sshl/Shr/Sshr are todo!(), yosys.rs:174-177). */
+enum b2_shift_kind { B2_SHIFT_LEFT = 0, B2_SHIFT_LOGICAL_RIGHT = 1, B2_SHIFT_ARITHMETIC_RIGHT = 2 };
+int b2_add_shift(b2_builder *b, int kind, uint32_t input, uint32_t amount, uint32_t output, uint32_t *out_cell);
 /* SimulatorBuilder::add_horizontal_{and,or,xor,nand,nor,xnor}_gate(input, output): the one-bit output is the gate folded over
    all bits of `input` (kind = B2_AND .. B2_XNOR); compiled into an ordinary n-ary gate over the input's bit rows.  No call site
    in the reference (Yosys ReduceAnd/Or/Xor/Xnor/Bool are todo!(), crates/digilogic_serde/src/yosys.rs:163-167).

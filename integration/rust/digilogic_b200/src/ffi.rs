@@ -67,6 +67,9 @@ extern "C" {
     pub fn b2_add_buffer(b: *mut B2Builder, input: u32, enable: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_buffer (no call site in digilogic_gsim yet)
     pub fn b2_add_add(b: *mut B2Builder, input_a: u32, input_b: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_add
     pub fn b2_add_sub(b: *mut B2Builder, input_a: u32, input_b: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_sub
+    pub fn b2_add_mul(b: *mut B2Builder, input_a: u32, input_b: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_mul
+    pub fn b2_add_compare(b: *mut B2Builder, op: c_int, input_a: u32, input_b: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_compare_* (op = B2_CMP_*)
+    pub fn b2_add_shift(b: *mut B2Builder, kind: c_int, input: u32, amount: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_{left,logical_right,arithmetic_right}_shift
     pub fn b2_add_horizontal_gate(b: *mut B2Builder, kind: c_int, input: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_horizontal_*_gate
     pub fn b2_add_register(b: *mut B2Builder, data_in: u32, data_out: u32, enable: u32, clock: u32, out_cell: *mut u32) -> c_int; // gsim add_register
     pub fn b2_add_slice(b: *mut B2Builder, input: u32, offset: u32, output: u32, out_cell: *mut u32) -> c_int; // gsim add_slice

@@ -21,6 +21,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libgsim_oracle.so")
 
 AND, OR, XOR, NAND, NOR, XNOR, NOT, MUX, BUF, SLICE, MERGE, REG, HGATE, ADD, SUB = range(15)
+SHL, LSHR, ASHR = "shl", "lshr", "ashr"
+CMP_EQ, CMP_NE, CMP_LTU, CMP_GTU, CMP_LEU, CMP_GEU, CMP_LTS, CMP_GTS, CMP_LES, CMP_GES = range(10)
 RUN_OK, RUN_MAX_STEPS, RUN_CONFLICT = 0, 1, 2
 ERR_NAMES = {
     0: "Ok", 1: "TooManyComponents", 2: "InvalidWireId", 3: "WireWidthMismatch",
@@ -62,6 +64,9 @@ def lib():
             "go_add_register": (C.c_int, [vp, u32, u32, u32, u32, pu32]),
             "go_add_horizontal_gate": (C.c_int, [vp, C.c_int, u32, u32, pu32]),
             "go_add_arith": (C.c_int, [vp, C.c_int, u32, u32, u32, pu32]),
+            "go_add_mul": (C.c_int, [vp, u32, u32, u32, pu32]),
+            "go_add_compare": (C.c_int, [vp, C.c_int, u32, u32, u32, pu32]),
+            "go_add_shift": (C.c_int, [vp, C.c_int, u32, u32, u32, pu32]),
             "go_add_slice": (C.c_int, [vp, u32, u32, u32, pu32]),
             "go_add_merge": (C.c_int, [vp, pu32, u32, u32, pu32]),
             "go_add_gates2": (C.c_int, [vp, vp, vp, vp, vp, u32]),
@@ -205,6 +210,33 @@ class Builder:
 
     def add_add(self, input_a, input_b, output): return self._arith(ADD, input_a, input_b, output)
     def add_sub(self, input_a, input_b, output): return self._arith(SUB, input_a, input_b, output)
+
+    def add_mul(self, input_a, input_b, output):
+        cell = C.c_uint32()
+        rc = lib().go_add_mul(self._h, input_a, input_b, output, C.byref(cell))
+        if rc:
+            raise OracleError(rc)
+        return cell.value
+
+    def add_compare(self, op, input_a, input_b, output):
+        """op: CMP_EQ .. CMP_GES (gsim add_compare_{equal,not_equal,less_than,...}{,_signed})."""
+        cell = C.c_uint32()
+        rc = lib().go_add_compare(self._h, op, input_a, input_b, output, C.byref(cell))
+        if rc:
+            raise OracleError(rc)
+        return cell.value
+
+    def add_shift(self, kind, input, amount, output):
+        """kind: SHL / LSHR / ASHR (gsim add_left_shift / add_logical_right_shift / add_arithmetic_right_shift)."""
+        cell = C.c_uint32()
+        rc = lib().go_add_shift(self._h, {SHL: 17, LSHR: 18, ASHR: 19}[kind], input, amount, output, C.byref(cell))
+        if rc:
+            raise OracleError(rc)
+        return cell.value
+
+    def add_left_shift(self, input, amount, output): return self.add_shift(SHL, input, amount, output)
+    def add_logical_right_shift(self, input, amount, output): return self.add_shift(LSHR, input, amount, output)
+    def add_arithmetic_right_shift(self, input, amount, output): return self.add_shift(ASHR, input, amount, output)
 
     def add_register(self, data_in, data_out, enable, clock):
         cell = C.c_uint32()

@@ -192,6 +192,40 @@ int go_add_arith(go_builder *b, int kind, uint32_t a, uint32_t c, uint32_t outpu
     return push_comp(b, (uint8_t)kind, in, 2, 0, output, cell);
 }
 
+/* add_mul(input_a, input_b, output): gsim's multiplier (Yosys Mul is todo!() in the reference, crates/digilogic_serde/src/yosys.rs:190).
+   Restated like add / sub: one width for all three wires, the product wraps, any invalid input bit makes the output Undefined. */
+int go_add_mul(go_builder *b, uint32_t a, uint32_t c, uint32_t output, uint32_t *cell) {
+    if (output >= b->n_wires || a >= b->n_wires || c >= b->n_wires) return GO_ERR_INVALID_WIRE_ID;
+    if (b->width[a] != b->width[output] || b->width[c] != b->width[output]) return GO_ERR_WIRE_WIDTH_MISMATCH;
+    uint32_t in[2] = {a, c};
+    return push_comp(b, GO_MUL, in, 2, 0, output, cell);
+}
+
+/* add_compare_{equal,not_equal,less_than,greater_than,less_than_or_equal,greater_than_or_equal}{,_signed}(input_a, input_b, output):
+   gsim's comparators (Yosys Lt/Le/Eq/Ne/Ge/Gt are todo!() in the reference, yosys.rs:182-187).  Restated: the inputs have one
+   width (WireWidthMismatch), the output is one bit (WireWidthIncompatible); any invalid input bit makes it Undefined. */
+int go_add_compare(go_builder *b, int op, uint32_t a, uint32_t c, uint32_t output, uint32_t *cell) {
+    if (op < GO_CMP_EQ || op > GO_CMP_GES) return GO_ERR_INVALID_INPUT_COUNT;
+    if (output >= b->n_wires || a >= b->n_wires || c >= b->n_wires) return GO_ERR_INVALID_WIRE_ID;
+    if (b->width[a] != b->width[c]) return GO_ERR_WIRE_WIDTH_MISMATCH;
+    if (b->width[output] != 1) return GO_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    uint32_t in[2] = {a, c};
+    return push_comp(b, GO_CMP, in, 2, (uint32_t)op, output, cell);
+}
+
+/* add_left_shift / add_logical_right_shift / add_arithmetic_right_shift(input, shift_amount, output): gsim's shifters (Yosys
+   Shl/Sshl/Shr/Sshr are todo!() in the reference, yosys.rs:174-177).  Restated: output as wide as the input (WireWidthMismatch),
+   the amount an unsigned value of at most 8 bits (WireWidthIncompatible); amounts >= width shift everything out (zeros, or the
+   sign for the arithmetic shift); any invalid bit of either input makes the output Undefined. */
+int go_add_shift(go_builder *b, int kind, uint32_t a, uint32_t amount, uint32_t output, uint32_t *cell) {
+    if (kind != GO_SHL && kind != GO_LSHR && kind != GO_ASHR) return GO_ERR_INVALID_INPUT_COUNT;
+    if (output >= b->n_wires || a >= b->n_wires || amount >= b->n_wires) return GO_ERR_INVALID_WIRE_ID;
+    if (b->width[a] != b->width[output]) return GO_ERR_WIRE_WIDTH_MISMATCH;
+    if (b->width[amount] > 8) return GO_ERR_WIRE_WIDTH_INCOMPATIBLE;
+    uint32_t in[2] = {a, amount};
+    return push_comp(b, (uint8_t)kind, in, 2, 0, output, cell);
+}
+
 /* Bulk 2-input gate add used by the large generators (same validation per gate). */
 int go_add_gates2(go_builder *b, const uint8_t *kinds, const uint32_t *in0, const uint32_t *in1, const uint32_t *out, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) {
@@ -427,6 +461,57 @@ static int eval_component(go_sim *s, uint32_t c) {
                 res[i].state = (uint32_t)sum; res[i].valid = 0xFFFFFFFFu;
                 carry = sum >> 32;
             }
+        }
+    } else if (cp->kind == GO_MUL || cp->kind == GO_CMP || cp->kind == GO_SHL || cp->kind == GO_LSHR || cp->kind == GO_ASHR) {
+        const uint32_t wa = s->width[in[0]], wb = s->width[in[1]], naa = s->natoms[in[0]], nab = s->natoms[in[1]];
+        const atom_t *a = s->state + s->atom_off[in[0]], *b2 = s->state + s->atom_off[in[1]];
+        int all_valid = 1;
+        uint32_t av[GO_MAX_ATOMS] = {0}, bv[GO_MAX_ATOMS] = {0}, rv[GO_MAX_ATOMS] = {0};
+        for (uint32_t i = 0; i < naa; i++) { uint32_t m = atom_mask((uint8_t)wa, i); if ((a[i].valid & m) != m) all_valid = 0; av[i] = a[i].state & m; }
+        for (uint32_t i = 0; i < nab; i++) { uint32_t m = atom_mask((uint8_t)wb, i); if ((b2[i].valid & m) != m) all_valid = 0; bv[i] = b2[i].state & m; }
+        if (!all_valid) {
+            for (uint32_t i = 0; i < na; i++) { res[i].state = 0xFFFFFFFFu; res[i].valid = 0; }
+        } else {
+            #define BIT(x, t) (((x)[(t) >> 5] >> ((t) & 31)) & 1u)
+            if (cp->kind == GO_MUL) {
+                for (uint32_t i = 0; i < naa; i++) {
+                    uint64_t carry = 0;
+                    for (uint32_t j = 0; i + j < GO_MAX_ATOMS; j++) {
+                        uint64_t t = (uint64_t)av[i] * bv[j] + rv[i + j] + carry;
+                        rv[i + j] = (uint32_t)t;
+                        carry = t >> 32;
+                    }
+                }
+            } else if (cp->kind == GO_CMP) {
+                int lt = 0, eq = 1;                         /* unsigned, from the top bit down */
+                for (int t = (int)wa - 1; t >= 0 && eq; t--) {
+                    uint32_t x = BIT(av, (uint32_t)t), y = BIT(bv, (uint32_t)t);
+                    if (x != y) { eq = 0; lt = x < y; }
+                }
+                const uint32_t op = cp->select;
+                if (op >= GO_CMP_LTS && !eq && BIT(av, wa - 1) != BIT(bv, wa - 1)) lt = BIT(av, wa - 1);   /* signs differ: the negative one is less */
+                int r;
+                switch (op) {
+                case GO_CMP_EQ: r = eq; break;
+                case GO_CMP_NE: r = !eq; break;
+                case GO_CMP_LTU: case GO_CMP_LTS: r = lt; break;
+                case GO_CMP_GTU: case GO_CMP_GTS: r = !lt && !eq; break;
+                case GO_CMP_LEU: case GO_CMP_LES: r = lt || eq; break;
+                default: r = !lt; break;
+                }
+                rv[0] = (uint32_t)r;
+            } else {
+                const uint32_t amt = bv[0];                /* at most 8 bits wide */
+                const uint32_t sign = cp->kind == GO_ASHR ? BIT(av, wa - 1) : 0;
+                for (uint32_t j = 0; j < wa; j++) {
+                    uint32_t bit;
+                    if (cp->kind == GO_SHL) bit = j >= amt ? BIT(av, j - amt) : 0;
+                    else bit = (uint64_t)j + amt < wa ? BIT(av, j + amt) : sign;
+                    rv[j >> 5] |= bit << (j & 31);
+                }
+            }
+            #undef BIT
+            for (uint32_t i = 0; i < na; i++) { res[i].state = rv[i]; res[i].valid = 0xFFFFFFFFu; }
         }
     } else if (cp->kind == GO_HGATE) {
         const atom_t *a = s->state + s->atom_off[in[0]];

@@ -13,7 +13,14 @@ enum { GO_AND = 0, GO_OR = 1, GO_XOR = 2, GO_NAND = 3, GO_NOR = 4, GO_XNOR = 5, 
        GO_MERGE = 10, /* output = inputs concatenated, inputs[0] in the low bits */
        GO_REG = 11,   /* register: inputs = {data_in, enable (1 bit), clock (1 bit)}; loads data_in on a rising clock edge */
        GO_HGATE = 12, /* horizontal (reduction) gate: the 1-bit output is the AND/OR/.. (kind in `select`) of all bits of inputs[0] */
-       GO_ADD = 13, GO_SUB = 14 /* output = inputs[0] +/- inputs[1] modulo 2^width; Undefined if any input bit is not valid */ };
+       GO_ADD = 13, GO_SUB = 14, /* output = inputs[0] +/- inputs[1] modulo 2^width; Undefined if any input bit is not valid */
+       GO_MUL = 15,   /* output = inputs[0] * inputs[1] modulo 2^width; Undefined if any input bit is not valid */
+       GO_CMP = 16,   /* 1-bit output = inputs[0] <op> inputs[1], op (GO_CMP_*) in `select`; Undefined if any input bit is not valid */
+       GO_SHL = 17, GO_LSHR = 18, GO_ASHR = 19 /* output = inputs[0] shifted by the unsigned value of inputs[1] (zero / sign fill;
+                         amounts >= width shift everything out); Undefined if any bit of either input is not valid */ };
+
+enum { GO_CMP_EQ = 0, GO_CMP_NE = 1, GO_CMP_LTU = 2, GO_CMP_GTU = 3, GO_CMP_LEU = 4, GO_CMP_GEU = 5,
+       GO_CMP_LTS = 6, GO_CMP_GTS = 7, GO_CMP_LES = 8, GO_CMP_GES = 9 };
 
 /* AddComponentError ordinals, names pinned by crates/digilogic_gsim/src/lib.rs:55-66 */
 enum {

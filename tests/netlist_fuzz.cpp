@@ -57,7 +57,10 @@ int main(int argc, char **argv) {
             const uint32_t n = rnd(6);
             for (uint32_t i = 0; i < 8; i++) in[i] = rnd(n_wires + 1);  // sometimes one past the end
             const uint32_t out = rnd(n_wires + 1), x = rnd(n_wires + 1), y = rnd(n_wires + 1), z = rnd(n_wires + 1);
-            switch (rnd(10)) {
+            switch (rnd(13)) {
+                case 10: b.add_arith(K_MUL, x, y, out, &cell); break;
+                case 11: b.add_compare((int)rnd(11), x, y, out, &cell); break;
+                case 12: b.add_shift(K_SHL + (int)rnd(3), x, y, out, &cell); break;
                 case 0: b.add_not(x, out, &cell); break;
                 case 1: b.add_mux(in, n, x, out, &cell); break;
                 case 2: b.add_buffer(x, y, out, &cell); break;
@@ -77,11 +80,14 @@ int main(int argc, char **argv) {
         REQUIRE(c.n_rows == c.n_src + c.n_fast() + c.n_wide() + c.n_res());
         for (uint32_t g = 0; g < c.n_fast(); g++) REQUIRE(c.fan0[g] < c.n_rows && c.fan1[g] < c.n_rows && c.fan2[g] < c.n_rows);
         REQUIRE(c.wide_off.size() == (size_t)c.n_wide() + 1 && c.wide_off.back() == c.wide_in.size());
+        REQUIRE(c.wide_aux.size() == c.n_wide());
         for (uint32_t v : c.wide_in) REQUIRE(v < c.n_rows);
         for (uint32_t g = 0; g < c.n_wide(); g++) {
             const uint32_t n_in = c.wide_off[g + 1] - c.wide_off[g];
             if (c.wide_kind[g] == K_REG) REQUIRE(n_in == 4);
-            if (c.wide_kind[g] == K_ADD || c.wide_kind[g] == K_SUB) REQUIRE(n_in % 2 == 0 && c.wide_nsel[g] < n_in / 2);
+            if (c.wide_kind[g] == K_ADD || c.wide_kind[g] == K_SUB || c.wide_kind[g] == K_MUL) REQUIRE(n_in % 2 == 0 && c.wide_nsel[g] < n_in / 2);
+            if (c.wide_kind[g] == K_CMP) REQUIRE(n_in % 2 == 0 && n_in >= 2 && c.wide_aux[g] <= CMP_GES);
+            if (c.wide_kind[g] >= K_SHL && c.wide_kind[g] <= K_ASHR) REQUIRE(c.wide_aux[g] <= 8 && n_in > c.wide_aux[g] && c.wide_nsel[g] < n_in - c.wide_aux[g]);
             if (c.wide_kind[g] == K_MUX) REQUIRE(n_in == c.wide_nsel[g] + (1u << c.wide_nsel[g]));
         }
         REQUIRE(c.row_of_bit.size() == c.bit_off.back());

@@ -134,3 +134,128 @@ def test_counter_on_gpu(resident):
         sim.set_wire_drive(ck, hi); assert sim.run_sim(100) == SimulationRunResult.Ok
         sim.set_wire_drive(ck, lo); assert sim.run_sim(100) == SimulationRunResult.Ok
         assert sim.get_wire_state(q) == LogicState(n & 0xFF, 0xFF), n
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# multiplier, comparators, shifters (gsim add_mul / add_compare_* / add_*_shift)
+
+WIDTHS2 = [1, 3, 8, 33, 64, 100]
+
+
+def build2(b):
+    w = {}
+    for n in WIDTHS2:
+        a, c, p = b.add_wire(n), b.add_wire(n), b.add_wire(n)
+        amt = b.add_wire(min(8, max(1, n.bit_length())))
+        cmps = [b.add_wire(1) for _ in range(10)]
+        shl, lshr, ashr = b.add_wire(n), b.add_wire(n), b.add_wire(n)
+        b.add_mul(a, c, p)
+        for op in range(10):
+            b.add_compare(op, a, c, cmps[op])
+        b.add_left_shift(a, amt, shl)
+        b.add_logical_right_shift(a, amt, lshr)
+        b.add_arithmetic_right_shift(a, amt, ashr)
+        w[n] = (a, c, amt, p, cmps, shl, lshr, ashr)
+    return w
+
+
+def _signed(x, n):
+    return x - (1 << n) if x >> (n - 1) else x
+
+
+def expect2(x, y, sh, n):
+    full = (1 << n) - 1
+    sx, sy = _signed(x, n), _signed(y, n)
+    cmps = [x == y, x != y, x < y, x > y, x <= y, x >= y, sx < sy, sx > sy, sx <= sy, sx >= sy]
+    return (x * y) & full, [int(v) for v in cmps], (x << sh) & full, x >> sh, (sx >> sh) & full
+
+
+def test_mul_compare_shift_known_answers_and_validation():
+    b = oracle.Builder()
+    w8, w4, w1, w9 = b.add_wire(8), b.add_wire(4), b.add_wire(1), b.add_wire(9)
+    with pytest.raises(oracle.OracleError, match="WireWidthMismatch"):
+        b.add_mul(w8, w4, w8)
+    with pytest.raises(oracle.OracleError, match="WireWidthMismatch"):
+        b.add_compare(oracle.CMP_LTU, w8, w4, w1)
+    with pytest.raises(oracle.OracleError, match="WireWidthIncompatible"):
+        b.add_compare(oracle.CMP_EQ, w8, w8, w4)
+    with pytest.raises(oracle.OracleError, match="WireWidthIncompatible"):
+        b.add_left_shift(w8, w9, w8)
+    with pytest.raises(oracle.OracleError, match="WireWidthMismatch"):
+        b.add_logical_right_shift(w8, w4, w4)
+    b = oracle.Builder()
+    w = build2(b)
+    sim = b.build()
+    rng = np.random.default_rng(5)
+    for n in WIDTHS2:
+        a, c, amt, p, cmps, shl, lshr, ashr = w[n]
+        full, aw = (1 << n) - 1, sim.get_wire_width(amt)
+        for k in range(30):
+            x = int.from_bytes(rng.bytes(16), "little") & full
+            y = x if k % 5 == 0 else int.from_bytes(rng.bytes(16), "little") & full
+            sh = int(rng.integers(0, 1 << aw))
+            sim.set_wire_drive(a, x, full); sim.set_wire_drive(c, y, full); sim.set_wire_drive(amt, sh, (1 << aw) - 1)
+            assert sim.run_sim(10) == oracle.RUN_OK
+            ep, ec, el, er, ea = expect2(x, y, sh, n)
+            assert sim.get_wire_state(p) == (ep, full), (n, x, y)
+            assert [sim.get_wire_state(o) for o in cmps] == [(v, 1) for v in ec], (n, x, y)
+            assert sim.get_wire_state(shl) == (el, full) and sim.get_wire_state(lshr) == (er, full) and sim.get_wire_state(ashr) == (ea, full)
+        sim.set_wire_drive(amt, 0, (1 << aw) - 2 if aw > 1 else 0)          # an invalid amount bit: the shifts are Undefined
+        sim.set_wire_drive(c, 1, full ^ 1)                                  # an invalid operand bit: product and comparisons
+        assert sim.run_sim(10) == oracle.RUN_OK
+        assert sim.get_wire_state(p) == (full, 0) and sim.get_wire_state(cmps[4]) == (1, 0) and sim.get_wire_state(ashr) == (full, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["resident", "device", "host", "dense"])
+def test_mul_compare_shift_on_gpu_against_oracle(path):
+    """Every lane its own operands (4-state: some lanes carry an X or Z bit), all four device paths, against the scalar oracle."""
+    from digilogic_b200 import AddComponentError, SimulatorBuilder
+    from digilogic_b200.gsim import ComponentError
+    from helpers import lane_mask
+    vb = SimulatorBuilder()
+    w8, w4, w1, w9 = vb.add_wire(8), vb.add_wire(4), vb.add_wire(1), vb.add_wire(9)
+    for fn, err in [(lambda: vb.add_mul(w8, w4, w8), AddComponentError.WireWidthMismatch),
+                    (lambda: vb.add_compare(2, w8, w8, w4), AddComponentError.WireWidthIncompatible),
+                    (lambda: vb.add_left_shift(w8, w9, w8), AddComponentError.WireWidthIncompatible),
+                    (lambda: vb.add_arithmetic_right_shift(w8, w4, w4), AddComponentError.WireWidthMismatch)]:
+        with pytest.raises(ComponentError) as e:
+            fn()
+        assert e.value.error == err
+    n_lanes = 64 + 37
+    ob, gb = oracle.Builder(), SimulatorBuilder()
+    w = build2(ob)
+    build2(gb)
+    lanes, sim = oracle.Lanes(ob, n_lanes), gb.build()
+    sim.set_option(sim.OPT_RESIDENT_KERNEL, int(path == "resident"))
+    sim.set_option(sim.OPT_DEVICE_LOOP, int(path in ("resident", "device")))
+    sim.set_option(sim.OPT_FRONTIER, int(path != "dense"))
+    sim.set_lanes(n_lanes)
+    rng = np.random.default_rng(8)
+    mask = lane_mask(n_lanes)
+    words = lanes.words
+    for rnd in range(3):
+        for n in WIDTHS2:
+            a, c, amt = w[n][:3]
+            for wire, width in ((a, n), (c, n), (amt, min(8, max(1, n.bit_length())))):
+                for bit in range(width):
+                    v = rng.integers(0, 1 << 64, words, dtype=np.uint64)
+                    bad = rng.integers(0, 1 << 64, words, dtype=np.uint64)
+                    for _ in range(6 if width > 8 else 3):                   # rare invalid bits: most lanes stay fully valid
+                        bad &= rng.integers(0, 1 << 64, words, dtype=np.uint64)
+                    m = ~bad
+                    lanes.set_drive(wire, v, m, bit)
+                    sim.set_wire_drive_lanes(wire, v, m, bit=bit)
+        status, _, _ = lanes.run(20)
+        res, conflict, unsettled = sim.run_sim_lanes(20)
+        assert (status == 0).all() and int(res) == 0
+        valid_products = 0
+        for n in WIDTHS2:
+            a, c, amt, p, cmps, shl, lshr, ashr = w[n]
+            for wire, width in [(p, n), (shl, n), (lshr, n), (ashr, n)] + [(o, 1) for o in cmps]:
+                for bit in range(width):
+                    rv, rm = lanes.get(wire, bit)
+                    gv, gm = sim.get_wire_lanes(wire, bit=bit)
+                    assert (((gv ^ rv) | (gm ^ rm)) & mask).max(initial=0) == 0, (rnd, n, wire, bit)
+                    valid_products += int(rm[0] != 0) if wire == p else 0
+        assert valid_products > 0
