@@ -9,8 +9,10 @@ and 2 — SURVEY.md §8 row f1.
 * Yosys JSON: 1-bit `$and/$or/$xor/$not` cells joined by bit ids
   (crates/digilogic_serde/src/yosys.rs:115-243, schema yosys/netlist.rs:159-196).  Beyond what the reference translates
   today, the cell types its importer already names but `todo!()`s (yosys.rs:160-211) map onto the engine's wider component
-  set (SURVEY.md §8 row f4): `$xnor`, `$mux`, `$reduce_and/or/xor/xnor/bool`, `$logic_not`, `$tribuf`, `$dff`, `$dffe`;
-  constant bits "0"/"1" become two extra input nets (`const_nets`) the caller drives.
+  set: `$xnor`, `$mux`, `$pmux`, `$reduce_and/or/xor/xnor/bool`, `$logic_not/and/or`, `$tribuf`, `$dff`,
+  `$dffe`, `$sdff`, `$sdffe`, `$sdffce`, `$dlatch`, and — through gsim's word-level components, on wide wires that `emit()`
+  merges from and slices back into the 1-bit nets — `$add`, `$sub`, `$neg`, `$mul`, `$lt/$le/$eq/$ne/$ge/$gt`,
+  `$shl/$sshl/$shr/$sshr`; constant bits "0"/"1" become two extra input nets (`const_nets`) the caller drives.
 
 Both produce an `ImportedCircuit`, whose `emit()` issues the same calls the GUI client sends
 (crates/digilogic_netcode/src/client.rs:288-427): one 1-bit net per net, then one gate per
@@ -34,6 +36,8 @@ DIG_SYMBOLS = {
     "Multiplexer": (MUX, [("S", 20, 40, True), ("A", 0, 0, True), ("B", 0, 40, True), ("Y", 40, 20, False)]),
 }
 YOSYS_CELLS = {"$and": AND, "$or": OR, "$xor": XOR, "$not": NOT, "$xnor": XNOR}
+# cell -> (unsigned, signed) comparator op of the engine (b2_compare_op)
+YOSYS_COMPARE = {"$eq": (0, 0), "$ne": (1, 1), "$lt": (2, 6), "$gt": (3, 7), "$le": (4, 8), "$ge": (5, 9)}
 YOSYS_REDUCE = {"$reduce_and": AND, "$reduce_or": OR, "$reduce_bool": OR, "$reduce_xor": XOR, "$reduce_xnor": XNOR, "$logic_not": NOR}
 
 
@@ -45,6 +49,8 @@ class ImportedCircuit:
     inputs: dict = field(default_factory=dict)     # label -> [nets] (LSB first)
     outputs: dict = field(default_factory=dict)
     const_nets: dict = field(default_factory=dict)  # net -> 0 / 1: constants of the source file, to be driven by the caller
+    # word-level components: (op, [operand bit-net lists], [output bit nets]); op = "add" "sub" "mul" ("cmp", CMP_*) "shl" "lshr" "ashr"
+    wide: list = field(default_factory=list)
 
     def emit(self, builder):
         """Same sequence as the client's build: AddNet{width:1} per net, then the gates."""
@@ -61,15 +67,43 @@ class ImportedCircuit:
                 builder.add_not_gate(ins[0], out)
             else:
                 builder.add_gate(kind, ins, out)
+        for op, operands, outs in self.wide:
+            # operand bits -> one wide wire each (add_merge), the component, result bits back onto the 1-bit nets (add_slice)
+            ws = []
+            for bits in operands:
+                w = builder.add_wire(len(bits))
+                builder.add_merge(list(bits), w)
+                ws.append(w)
+            cmp_op = None
+            if isinstance(op, tuple):
+                op, cmp_op = op
+            y = builder.add_wire(1 if op == "cmp" else len(operands[0]))
+            if op == "add":
+                builder.add_add(ws[0], ws[1], y)
+            elif op == "sub":
+                builder.add_sub(ws[0], ws[1], y)
+            elif op == "mul":
+                builder.add_mul(ws[0], ws[1], y)
+            elif op == "cmp":
+                builder.add_compare(cmp_op, ws[0], ws[1], y)
+            else:
+                builder.add_shift(op, ws[0], ws[1], y)
+            for j, out in enumerate(outs):
+                builder.add_slice(y, j, out)
         return builder
 
     def to_json(self) -> dict:
-        return {"name": self.name, "n_nets": self.n_nets, "gates": [[k, list(i), o] for k, i, o in self.gates],
-                "inputs": self.inputs, "outputs": self.outputs}
+        d = {"name": self.name, "n_nets": self.n_nets, "gates": [[k, list(i), o] for k, i, o in self.gates],
+             "inputs": self.inputs, "outputs": self.outputs}
+        if self.wide:
+            d["wide"] = [[list(op) if isinstance(op, tuple) else op, [list(x) for x in ops], list(outs)] for op, ops, outs in self.wide]
+        return d
 
     @classmethod
     def from_json(cls, d: dict) -> "ImportedCircuit":
-        return cls(d["name"], d["n_nets"], [(k, list(i), o) for k, i, o in d["gates"]], dict(d["inputs"]), dict(d["outputs"]))
+        c = cls(d["name"], d["n_nets"], [(k, list(i), o) for k, i, o in d["gates"]], dict(d["inputs"]), dict(d["outputs"]))
+        c.wide = [(tuple(op) if isinstance(op, list) else op, [list(x) for x in ops], list(outs)) for op, ops, outs in d.get("wide", [])]
+        return c
 
 
 # ------------------------------------------------------------------------------ Digital .dig
@@ -217,6 +251,10 @@ def load_yosys(text: str, module: str | None = None) -> ImportedCircuit:
     circ = ImportedCircuit(module, 0)
 
     def net(bit):
+        if isinstance(bit, tuple):       # an internal net of a lowered cell
+            if bit not in net_of:
+                net_of[bit] = len(net_of)
+            return net_of[bit]
         if not isinstance(bit, int):
             # "0" / "1": the reference importer todo!()s on constants; here they are shared nets the caller drives
             if bit not in ("0", "1"):
@@ -238,10 +276,41 @@ def load_yosys(text: str, module: str | None = None) -> ImportedCircuit:
             circ.outputs[pname] = nets
         else:
             raise ValueError("inout ports are not supported")
+    def tmp():
+        return net(("tmp", len(net_of)))
+
     for cname, cell in mod.get("cells", {}).items():
         ctype = cell["type"]
         conn = cell["connections"]
         params = cell.get("parameters", {})
+
+        def flag(name):
+            v = params.get(name, 0)
+            return int(v, 2) if isinstance(v, str) else int(v)
+
+        def polarity(name):
+            v = params.get(name, 1)
+            return int(v, 2) if isinstance(v, str) else int(v)
+
+        def positive(bit, pol_name):
+            """the net of `bit`, inverted when the cell's polarity parameter says active-low"""
+            if polarity(pol_name) == 1:
+                return net(bit)
+            inv = tmp()
+            circ.gates.append((NOT, [net(bit)], inv))
+            return inv
+
+        def param_bits(name, width):
+            v = params.get(name, 0)
+            text = v if isinstance(v, str) else format(int(v), "b")
+            text = text.zfill(width)[-width:]
+            return [int(ch) for ch in reversed(text)]          # LSB first
+
+        def extend(bits, signed_param, width):
+            """operand bits as nets, extended to `width` with its sign bit (signed) or constant 0, or truncated"""
+            nets = [net(b) for b in bits][:width]
+            pad = nets[-1] if signed_param and flag(signed_param) and nets else net("0")
+            return nets + [pad] * (width - len(nets))
         if ctype in YOSYS_CELLS:
             kind = YOSYS_CELLS[ctype]
             for j in range(len(conn["Y"])):
@@ -266,6 +335,64 @@ def load_yosys(text: str, module: str | None = None) -> ImportedCircuit:
             en = net(conn["EN"][0]) if ctype == "$dffe" else net("1")
             for j in range(len(conn["Q"])):
                 circ.gates.append((REG, [net(conn["D"][j]), en, net(conn["CLK"][0])], net(conn["Q"][j])))
+        elif ctype in ("$sdff", "$sdffe", "$sdffce"):
+            # synchronous reset: the value loaded is SRST ? SRST_VALUE : D; $sdffe resets whether enabled or not, $sdffce only
+            # when enabled
+            if polarity("CLK_POLARITY") != 1:
+                raise ValueError(f"{ctype} with a negative clock polarity is not supported ({cname})")
+            width = len(conn["Q"])
+            rst = positive(conn["SRST"][0], "SRST_POLARITY")
+            value = param_bits("SRST_VALUE", width)
+            en = positive(conn["EN"][0], "EN_POLARITY") if ctype != "$sdff" else net("1")
+            if ctype == "$sdffe":
+                both = tmp()
+                circ.gates.append((OR, [en, rst], both))
+                en = both
+            for j in range(width):
+                d = tmp()
+                circ.gates.append((MUX, [rst, net(conn["D"][j]), net(str(value[j]))], d))
+                circ.gates.append((REG, [d, en, net(conn["CLK"][0])], net(conn["Q"][j])))
+        elif ctype == "$dlatch":   # transparent while EN: Q = EN ? D : Q
+            en = positive(conn["EN"][0], "EN_POLARITY")
+            for j in range(len(conn["Q"])):
+                q = net(conn["Q"][j])
+                circ.gates.append((MUX, [en, q, net(conn["D"][j])], q))
+        elif ctype == "$pmux":     # Y = A unless a select bit is set: then that slice of B (selects are one-hot in valid designs)
+            width = len(conn["Y"])
+            cur = [net(b) for b in conn["A"]]
+            for i, sbit in enumerate(conn["S"]):
+                last = i == len(conn["S"]) - 1
+                nxt = [net(conn["Y"][j]) if last else tmp() for j in range(width)]
+                for j in range(width):
+                    circ.gates.append((MUX, [net(sbit), cur[j], net(conn["B"][i * width + j])], nxt[j]))
+                cur = nxt
+        elif ctype in ("$logic_and", "$logic_or"):
+            a, b = tmp(), tmp()
+            for src, dst in ((conn["A"], a), (conn["B"], b)):
+                bits = [net(x) for x in src]
+                circ.gates.append((OR, bits if len(bits) > 1 else bits * 2, dst))
+            circ.gates.append((AND if ctype == "$logic_and" else OR, [a, b], net(conn["Y"][0])))
+        elif ctype in ("$add", "$sub", "$mul", "$neg"):
+            width = len(conn["Y"])
+            if width > 255:
+                raise ValueError(f"{ctype} wider than 255 bits ({cname})")
+            if ctype == "$neg":
+                ops = [[net("0")] * width, extend(conn["A"], "A_SIGNED", width)]
+            else:
+                ops = [extend(conn["A"], "A_SIGNED", width), extend(conn["B"], "B_SIGNED", width)]
+            circ.wide.append(({"$add": "add", "$sub": "sub", "$mul": "mul", "$neg": "sub"}[ctype], ops, [net(b) for b in conn["Y"]]))
+        elif ctype in YOSYS_COMPARE:
+            width = max(len(conn["A"]), len(conn["B"]))
+            signed = flag("A_SIGNED") and flag("B_SIGNED")
+            op = YOSYS_COMPARE[ctype][1 if signed else 0]
+            ops = [extend(conn["A"], "A_SIGNED" if signed else None, width), extend(conn["B"], "B_SIGNED" if signed else None, width)]
+            circ.wide.append((("cmp", op), ops, [net(conn["Y"][0])]))   # further Y bits are constant 0 in Yosys and not produced
+        elif ctype in ("$shl", "$sshl", "$shr", "$sshr"):
+            width = len(conn["Y"])
+            if len(conn["B"]) > 8:
+                raise ValueError(f"{ctype} with a shift amount wider than 8 bits ({cname})")
+            op = "shl" if ctype in ("$shl", "$sshl") else ("ashr" if ctype == "$sshr" and flag("A_SIGNED") else "lshr")
+            circ.wide.append((op, [extend(conn["A"], "A_SIGNED", width), [net(b) for b in conn["B"]]], [net(b) for b in conn["Y"]]))
         else:
             raise ValueError(f"unsupported cell type {ctype!r} ({cname})")
     circ.n_nets = len(net_of)

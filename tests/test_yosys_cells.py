@@ -137,3 +137,136 @@ def test_shift_register_from_dff_cells_on_gpu():
 
     shift_check(lambda c: c.emit(SimulatorBuilder()).build(), lambda s, n, st: s.set_wire_drive(n, LogicState(*st)),
                 lambda s: s.run_sim(1000), get)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# word-level cells ($add $sub $neg $mul, comparisons, shifts), $pmux, $logic_and/or, $sdff*, $dlatch
+
+def alu_json():
+    """a = bits 10..17 (8), b = 20..25 (6, signed in the signed cells), sh = 30..32, s = 40..42 (pmux selects), clk 2, rst 3, en 4."""
+    cells = {}
+
+    def cell(name, typ, conn, **params):
+        cells[name] = {"hide_name": 1, "type": typ, "parameters": {k: (v if isinstance(v, str) else format(v, "b")) for k, v in params.items()},
+                       "attributes": {}, "port_directions": {}, "connections": conn}
+
+    a, b, sh, s = list(range(10, 18)), list(range(20, 26)), [30, 31, 32], [40, 41, 42]
+    out = {}
+
+    def y(name, width):
+        base = 100 + 20 * len(out)
+        out[name] = list(range(base, base + width))
+        return out[name]
+
+    cell("add", "$add", {"A": a, "B": b, "Y": y("sum", 9)}, A_SIGNED=0, B_SIGNED=0)
+    cell("sub", "$sub", {"A": a, "B": b, "Y": y("diff", 8)}, A_SIGNED=1, B_SIGNED=1)
+    cell("mul", "$mul", {"A": a, "B": b, "Y": y("prod", 14)}, A_SIGNED=0, B_SIGNED=0)
+    cell("neg", "$neg", {"A": b, "Y": y("negb", 7)}, A_SIGNED=1)
+    cell("lt", "$lt", {"A": a, "B": b, "Y": y("lt_s", 1)}, A_SIGNED=1, B_SIGNED=1)
+    cell("ge", "$ge", {"A": a, "B": b, "Y": y("ge_u", 1)}, A_SIGNED=0, B_SIGNED=0)
+    cell("eq", "$eq", {"A": a, "B": b, "Y": y("eq", 1)}, A_SIGNED=0, B_SIGNED=0)
+    cell("shl", "$shl", {"A": a, "B": sh, "Y": y("shl", 8)}, A_SIGNED=0, B_SIGNED=0)
+    cell("sshr", "$sshr", {"A": a, "B": sh, "Y": y("sshr", 8)}, A_SIGNED=1, B_SIGNED=0)
+    cell("shr", "$shr", {"A": a, "B": sh, "Y": y("shr", 8)}, A_SIGNED=0, B_SIGNED=0)
+    cell("pm", "$pmux", {"A": a[:4], "B": a[4:8] + b[:4] + [b[4], b[5], "1", "0"], "S": s, "Y": y("pm", 4)}, WIDTH=4, S_WIDTH=3)
+    cell("land", "$logic_and", {"A": a, "B": sh, "Y": y("land", 1)})
+    cell("lor", "$logic_or", {"A": sh, "B": s, "Y": y("lor", 1)})
+    cell("ff1", "$sdff", {"CLK": [2], "SRST": [3], "D": a[:4], "Q": y("q_sdff", 4)}, CLK_POLARITY=1, SRST_POLARITY=1, SRST_VALUE="1010", WIDTH=4)
+    cell("ff2", "$sdffe", {"CLK": [2], "SRST": [3], "EN": [4], "D": a[:4], "Q": y("q_sdffe", 4)}, CLK_POLARITY=1, SRST_POLARITY=1,
+         EN_POLARITY=1, SRST_VALUE="0110", WIDTH=4)
+    cell("ff3", "$sdffce", {"CLK": [2], "SRST": [3], "EN": [4], "D": a[:4], "Q": y("q_sdffce", 4)}, CLK_POLARITY=1, SRST_POLARITY=0,
+         EN_POLARITY=1, SRST_VALUE="0001", WIDTH=4)
+    cell("lat", "$dlatch", {"EN": [4], "D": b[:3], "Q": y("q_lat", 3)}, EN_POLARITY=1, WIDTH=3)
+    ports = {"a": {"direction": "input", "bits": a}, "b": {"direction": "input", "bits": b}, "sh": {"direction": "input", "bits": sh},
+             "s": {"direction": "input", "bits": s}, "clk": {"direction": "input", "bits": [2]}, "rst": {"direction": "input", "bits": [3]},
+             "en": {"direction": "input", "bits": [4]}}
+    ports.update({k: {"direction": "output", "bits": v} for k, v in out.items()})
+    return json.dumps({"creator": "test", "modules": {"alu": {"attributes": {"top": "1".zfill(32)}, "ports": ports, "cells": cells, "netnames": {}}}})
+
+
+def _s(x, n):
+    return x - (1 << n) if x >> (n - 1) else x
+
+
+def alu_model(a, b, sh, s):
+    """Yosys semantics of the combinational cells (operands extended to the result width, signed where both are)."""
+    sa, sb = _s(a, 8), _s(b, 6)
+    pm = a & 15
+    for i, choice in enumerate([(a >> 4) & 15, b & 15, ((b >> 4) & 3) | 4]):      # last case: {0, 1, b5, b4}
+        if (s >> i) & 1:
+            pm = choice
+    return {"sum": (a + b) & 0x1FF, "diff": (sa - sb) & 0xFF, "prod": (a * b) & 0x3FFF, "negb": (-sb) & 0x7F, "lt_s": int(sa < sb),
+            "ge_u": int(a >= b), "eq": int(a == b), "shl": (a << sh) & 0xFF, "sshr": (sa >> sh) & 0xFF, "shr": a >> sh, "pm": pm,
+            "land": int(a != 0 and sh != 0), "lor": int(sh != 0 or s != 0)}
+
+
+def test_word_level_cells_on_the_oracle():
+    circ = importers.load_yosys(alu_json())
+    assert len(circ.wide) == 10 and circ.to_json()["wide"] and importers.ImportedCircuit.from_json(circ.to_json()).wide == circ.wide
+    sim = circ.emit(oracle.Builder()).build()
+    for n, v in circ.const_nets.items():
+        sim.set_wire_drive(n, v, 1)
+    rng = np.random.default_rng(12)
+
+    def drive(name, value):
+        for j, n in enumerate(circ.inputs[name]):
+            sim.set_wire_drive(n, (value >> j) & 1, 1)
+
+    def read(name):
+        bits = [sim.get_wire_state(n) for n in circ.outputs[name]]
+        assert all(m == 1 for _, m in bits), (name, bits)
+        return sum(v << j for j, (v, _) in enumerate(bits))
+
+    drive("clk", 0); drive("rst", 0); drive("en", 0)
+    for k in range(60):
+        a, b, sh = (int(x) for x in (rng.integers(0, 256), rng.integers(0, 64), rng.integers(0, 8)))
+        s = [0, 1, 2, 4, 0][k % 5]
+        drive("a", a); drive("b", b); drive("sh", sh); drive("s", s)
+        assert sim.run_sim(1000) == oracle.RUN_OK
+        want = alu_model(a, b, sh, s)
+        got = {k_: read(k_) for k_ in want}
+        assert got == want, (a, b, sh, s)
+    # sequential cells: reset value with and without enable, load, hold; the latch follows b while en and holds after
+    def clock():
+        assert sim.run_sim(1000) == oracle.RUN_OK                                 # the new inputs settle before the edge
+        drive("clk", 1); assert sim.run_sim(1000) == oracle.RUN_OK
+        drive("clk", 0); assert sim.run_sim(1000) == oracle.RUN_OK
+
+    drive("a", 0b0111); drive("b", 0b101); drive("rst", 1); drive("en", 0); clock()
+    assert read("q_sdff") == 0b1010 and read("q_sdffe") == 0b0110                 # $sdffe resets without its enable
+    drive("rst", 0); drive("en", 1); clock()                                      # rst = 0 is ACTIVE for ff3 (SRST_POLARITY 0)
+    assert read("q_sdff") == 0b0111 and read("q_sdffe") == 0b0111 and read("q_sdffce") == 0b0001 and read("q_lat") == 0b101
+    drive("rst", 1); drive("en", 0); drive("a", 0b1100); drive("b", 0b010); clock()
+    assert read("q_sdff") == 0b1010 and read("q_sdffe") == 0b0110 and read("q_sdffce") == 0b0001 and read("q_lat") == 0b101
+    drive("rst", 0); drive("en", 0); clock()
+    assert read("q_sdff") == 0b1100 and read("q_sdffe") == 0b0110 and read("q_sdffce") == 0b0001   # not enabled: no reset, no load
+    drive("rst", 1); drive("en", 1); clock()                                      # ff3: reset inactive, enabled: loads
+    assert read("q_sdffce") == 0b1100 and read("q_lat") == 0b010
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [1, 0])
+def test_word_level_cells_on_gpu_against_oracle(resident):
+    from digilogic_b200 import LogicState, SimulatorBuilder
+    circ = importers.load_yosys(alu_json())
+    ref = circ.emit(oracle.Builder()).build()
+    sim = circ.emit(SimulatorBuilder()).build()
+    sim.set_option(sim.OPT_RESIDENT_KERNEL, resident)
+    n_wires = sim.info.n_wires
+
+    def drive(net, v, m=1):
+        ref.set_wire_drive(net, v, m)
+        sim.set_wire_drive(net, LogicState(v, m))
+
+    for n, v in circ.const_nets.items():
+        drive(n, v)
+    rng = np.random.default_rng(13)
+    all_inputs = [n for nets in circ.inputs.values() for n in nets]
+    for rnd in range(40):
+        for n in all_inputs:
+            v, m = int(rng.integers(0, 2)), int(rng.random() > 0.03)             # now and then an X / Z input bit
+            drive(n, v, m)
+        ms = (1000, 1000, 3, 0)[rnd % 4]
+        assert int(sim.run_sim(ms)) == ref.run_sim(ms), rnd
+        for w in range(n_wires):
+            assert sim.get_wire_state(w) == LogicState(*ref.get_wire_state(w)), (rnd, w)
