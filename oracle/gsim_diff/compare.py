@@ -39,6 +39,13 @@ def main(cases_path, dump_path):
                 b.add_register(c["inputs"][0], c["output"], c["inputs"][1], c["inputs"][2])
             elif c["kind"] in ("add", "sub"):
                 (b.add_add if c["kind"] == "add" else b.add_sub)(c["inputs"][0], c["inputs"][1], c["output"])
+            elif c["kind"] == "mul":
+                b.add_mul(c["inputs"][0], c["inputs"][1], c["output"])
+            elif c["kind"].startswith("cmp_"):
+                ops = ("cmp_eq", "cmp_ne", "cmp_ltu", "cmp_gtu", "cmp_leu", "cmp_geu", "cmp_lts", "cmp_gts", "cmp_les", "cmp_ges")
+                b.add_compare(ops.index(c["kind"]), c["inputs"][0], c["inputs"][1], c["output"])
+            elif c["kind"] in ("shl", "lshr", "ashr"):
+                b.add_shift(c["kind"], c["inputs"][0], c["inputs"][1], c["output"])
             elif c["kind"] in HKIND:
                 b.add_horizontal_gate(HKIND[c["kind"]], c["inputs"][0], c["output"])
             else:

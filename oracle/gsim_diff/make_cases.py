@@ -87,6 +87,19 @@ def cases():
                 "comps": [{"kind": "add", "inputs": [0, 1], "output": 2}, {"kind": "sub", "inputs": [0, 1], "output": 3}],
                 "runs": [{"drives": [[0, [x], [ma]], [1, [y], [mb]]], "max_steps": 10} for x, y, ma, mb in
                          ((200, 100, 255, 255), (3, 5, 255, 255), (255, 1, 255, 255), (5, 3, 254, 255), (5, 3, 255, 127), (0, 0, 0, 0))]})
+    # multiplier, comparators (unsigned and signed), shifters: wrap-around, sign handling, amounts past the width, one invalid bit
+    cmps = ("cmp_eq", "cmp_ne", "cmp_ltu", "cmp_gtu", "cmp_leu", "cmp_geu", "cmp_lts", "cmp_gts", "cmp_les", "cmp_ges")
+    out.append({"name": "mul_compare_8", "wires": [8, 8, 8] + [1] * 10,
+                "comps": [{"kind": "mul", "inputs": [0, 1], "output": 2}] + [{"kind": k, "inputs": [0, 1], "output": 3 + i} for i, k in enumerate(cmps)],
+                "runs": [{"drives": [[0, [x], [ma]], [1, [y], [mb]]], "max_steps": 10} for x, y, ma, mb in
+                         ((200, 100, 255, 255), (3, 5, 255, 255), (255, 255, 255, 255), (0x80, 0x7F, 255, 255), (5, 5, 255, 255),
+                          (5, 3, 254, 255), (5, 3, 255, 127), (0, 0, 0, 0))]})
+    out.append({"name": "shifts_8", "wires": [8, 4, 8, 8, 8],
+                "comps": [{"kind": "shl", "inputs": [0, 1], "output": 2}, {"kind": "lshr", "inputs": [0, 1], "output": 3},
+                          {"kind": "ashr", "inputs": [0, 1], "output": 4}],
+                "runs": [{"drives": [[0, [x], [ma]], [1, [n], [mn]]], "max_steps": 10} for x, n, ma, mn in
+                         ((0x96, 0, 255, 15), (0x96, 1, 255, 15), (0x96, 7, 255, 15), (0x96, 8, 255, 15), (0x96, 15, 255, 15),
+                          (0x16, 3, 255, 15), (0x96, 1, 254, 15), (0x96, 1, 255, 14))]})
     out.append({"name": "horizontal_gates_4", "wires": [4, 1, 1, 1, 1, 1, 1],
                 "comps": [{"kind": k, "inputs": [0], "output": i + 1} for i, k in enumerate(("hand", "hor", "hxor", "hnand", "hnor", "hxnor"))],
                 "runs": [{"drives": [[0, [v], [m]]], "max_steps": 10} for v, m in

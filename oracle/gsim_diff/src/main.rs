@@ -62,6 +62,20 @@ fn main() {
                 "register" => builder.add_register(ins[0], o, ins[1], ins[2]),
                 "add" => builder.add_add(ins[0], ins[1], o),
                 "sub" => builder.add_sub(ins[0], ins[1], o),
+                "mul" => builder.add_mul(ins[0], ins[1], o),
+                "cmp_eq" => builder.add_compare_equal(ins[0], ins[1], o),
+                "cmp_ne" => builder.add_compare_not_equal(ins[0], ins[1], o),
+                "cmp_ltu" => builder.add_compare_less_than(ins[0], ins[1], o),
+                "cmp_gtu" => builder.add_compare_greater_than(ins[0], ins[1], o),
+                "cmp_leu" => builder.add_compare_less_than_or_equal(ins[0], ins[1], o),
+                "cmp_geu" => builder.add_compare_greater_than_or_equal(ins[0], ins[1], o),
+                "cmp_lts" => builder.add_compare_less_than_signed(ins[0], ins[1], o),
+                "cmp_gts" => builder.add_compare_greater_than_signed(ins[0], ins[1], o),
+                "cmp_les" => builder.add_compare_less_than_or_equal_signed(ins[0], ins[1], o),
+                "cmp_ges" => builder.add_compare_greater_than_or_equal_signed(ins[0], ins[1], o),
+                "shl" => builder.add_left_shift(ins[0], ins[1], o),
+                "lshr" => builder.add_logical_right_shift(ins[0], ins[1], o),
+                "ashr" => builder.add_arithmetic_right_shift(ins[0], ins[1], o),
                 "hand" => builder.add_horizontal_and_gate(ins[0], o),
                 "hor" => builder.add_horizontal_or_gate(ins[0], o),
                 "hxor" => builder.add_horizontal_xor_gate(ins[0], o),
