@@ -15,6 +15,9 @@ import make_cases  # noqa: E402
 import oracle  # noqa: E402
 
 
+CMPS = ("cmp_eq", "cmp_ne", "cmp_ltu", "cmp_gtu", "cmp_leu", "cmp_geu", "cmp_lts", "cmp_gts", "cmp_les", "cmp_ges")
+
+
 def build(case, builder):
     for w in case["wires"]:
         builder.add_wire(w)
@@ -33,6 +36,12 @@ def build(case, builder):
             builder.add_register(c["inputs"][0], c["output"], c["inputs"][1], c["inputs"][2])
         elif c["kind"] in ("add", "sub"):
             (builder.add_add if c["kind"] == "add" else builder.add_sub)(c["inputs"][0], c["inputs"][1], c["output"])
+        elif c["kind"] == "mul":
+            builder.add_mul(c["inputs"][0], c["inputs"][1], c["output"])
+        elif c["kind"].startswith("cmp_"):
+            builder.add_compare(CMPS.index(c["kind"]), c["inputs"][0], c["inputs"][1], c["output"])
+        elif c["kind"] in ("shl", "lshr", "ashr"):
+            builder.add_shift(c["kind"], c["inputs"][0], c["inputs"][1], c["output"])
         elif c["kind"] in compare.HKIND:
             builder.add_horizontal_gate(compare.HKIND[c["kind"]], c["inputs"][0], c["output"])
         else:
