@@ -78,6 +78,7 @@ def parse_args():
     ap.add_argument("--e2e-ring-tiles", type=int, default=0, help="host stimulus ring size in tiles (0 = whole batch on 1 GPU, 2^20 lanes otherwise)")
     ap.add_argument("--cpu-lanes-per-core", type=int, default=24)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pair-fusion", action="store_true", help="B2_OPT_PAIR_FUSION = 0: one launch per level (round-1/2 kernels)")
     ap.add_argument("--no-elision-probe", action="store_true", help="skip the secondary run with B2_OPT_VALID_ELISION")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-unit-delay-probe", action="store_true", help="skip the secondary config-4 (feedback) run")
@@ -282,6 +283,7 @@ def run_b200(args):
     tile = min(args.tile_words, words_local) if args.tile_words else auto_tile
     slots = args.slots or auto_slots
     args.tile_words, args.slots = tile, slots
+    sim.set_option(sim.OPT_PAIR_FUSION, 0 if args.no_pair_fusion else 1)
     batch = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=local_rank, stream=stream.cuda_stream)
     batch.set_option(Batch.OPT_SWEEP, 1 if args.sweep else 0)
     batch.set_option(Batch.OPT_TASK_ITERS, args.task_iters)
@@ -320,6 +322,11 @@ def run_b200(args):
     assert worst == SimulationRunResult.Ok
     binfo = batch.info
     assert binfo.sweep == (1 if args.sweep else 0)
+
+    pair_plan = None
+    if binfo.pair_launches:
+        pair_plan = sim.plan_pairs(gen.outputs)   # host-side statistics of the plan the replicas run (same planner, same kept rows)
+        assert pair_plan["launches"] == binfo.pair_launches
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -379,6 +386,8 @@ def run_b200(args):
         per_level_ctas4 = -(-(args.gates // info.depth) // (max(256 // max(tile // 2, 1), 1) * 4)) * max((tile // 2 + 255) // 256, 1)
         kernel = "k_eval2<4,false,false>" if per_level_ctas4 >= 148 * 3 * 4 else "k_eval2<2,false,false>"   # Engine::run_levelised's rule
         launches_per_step = n_tiles * info.depth
+        if binfo.pair_launches:      # level-pair fusion (B2_OPT_PAIR_FUSION): items of two dependent gates, about depth / 2 launches per tile
+            kernel, launches_per_step = "k_eval_pair", n_tiles * binfo.pair_launches
     launch_s = step_s / launches_per_step
     algo_bytes = ALGO_BYTES_PER_GATE_WORD * gate_words / launches_per_step
     peak, peak_kind = load_peaks()
@@ -397,7 +406,8 @@ def run_b200(args):
             with open(traffic_path) as f:
                 tj = json.load(f)
             if (tj.get("engine") == ("sweep" if args.sweep else "replicas") and tj.get("tile_words") == tile
-                    and tj.get("slots") == slots and tj.get("gates") == args.gates):
+                    and tj.get("slots") == slots and tj.get("gates") == args.gates
+                    and bool(tj.get("pair_fusion")) == bool(binfo.pair_launches)):
                 roofline["traffic"] = tj["dram_bytes_per_gate_word"] * gate_words / launches_per_step
                 roofline["dram_frac"] = roofline["traffic"] / launch_s / 1e9 / peak
                 roofline["l2_hit_rate_pct"] = tj.get("l2_hit_rate_pct")
@@ -465,7 +475,8 @@ def run_b200(args):
                                                 "tasks_per_tile": binfo.tasks_per_pass,
                                                 "gather": None if world == 1 else ("ncclAllGather" if args.nccl_gather else
                                                                                    "fused: the kernel that reads a tile's output rows stores them into every rank's planes over NVLink (CUDA IPC)"),
-                                                "engine": "sweep" if args.sweep else "replicas"}),
+                                                "engine": "sweep" if args.sweep else "replicas",
+                                                "pair_fusion": pair_plan}),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "valid_elision": elision, "unit_delay": unit_delay,
             "gpu_launches": int(launches), "clocks": clocks, "output_checksum": f"{checksum:#018x}",
         }

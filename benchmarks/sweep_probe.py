@@ -50,6 +50,7 @@ def main():
         pdl = f[9] if len(f) > 9 else 0
         sim.set_option(sim.OPT_PDL, pdl)
         sim.set_option(sim.OPT_L2_HINTS, hints)
+        sim.set_option(sim.OPT_PAIR_FUSION, f[10] if len(f) > 10 else 1)
         b = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=0, stream=stream.cuda_stream)
         b.set_option(Batch.OPT_TASK_ITERS, iters)
         b.set_option(Batch.OPT_UNROLL, unroll)
@@ -69,7 +70,7 @@ def main():
         cs = int((ov.sum() ^ om.sum()).item()) & 0xFFFFFFFFFFFFFFFF
         first = cs if first is None else first
         info = b.info
-        print(json.dumps({"tile": tile, "slots": slots, "iters": iters, "unroll": unroll, "ctas_per_sm": ctas, "ld_mode": ld_mode, "sweep": sweep, "l2_hints": hints, "discard": discard, "pdl": pdl, "grid": info.grid_ctas,
+        print(json.dumps({"tile": tile, "slots": slots, "iters": iters, "unroll": unroll, "ctas_per_sm": ctas, "ld_mode": ld_mode, "sweep": sweep, "l2_hints": hints, "discard": discard, "pdl": pdl, "pair_launches": info.pair_launches,
                           "ms": round(ms, 2), "evals_per_s": args.gates * args.lanes / (ms * 1e-3),
                           "algo_frac": 48.0 * args.gates * words / (ms * 1e-3) / 1e9 / peak, "checksum_equal": cs == first,
                           "checksum": f"{cs:#018x}"}), flush=True)

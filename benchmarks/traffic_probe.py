@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--tile-words", type=int, default=256)
     ap.add_argument("--slots", type=int, default=3)
     ap.add_argument("--sweep", type=int, default=0)
+    ap.add_argument("--pair", type=int, default=1)
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0xD1610003)
     args = ap.parse_args()
     import torch
@@ -37,6 +38,7 @@ def main():
     torch.cuda.set_stream(stream)
     ov = torch.zeros((len(gen.outputs), words), dtype=torch.int64, device="cuda")
     om = torch.zeros_like(ov)
+    sim.set_option(sim.OPT_PAIR_FUSION, args.pair)
     b = Batch(sim, gen.inputs, gen.outputs, args.tile_words, args.slots, device=0, stream=stream.cuda_stream)
     b.set_option(Batch.OPT_SWEEP, args.sweep)
     for _ in range(2):                       # warm-up: graphs captured, stores allocated
@@ -53,7 +55,7 @@ def main():
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     gate_words = args.gates * words
-    print(json.dumps({"lanes": args.lanes, "tile_words": args.tile_words, "slots": args.slots, "sweep": args.sweep, "ms": ms,
+    print(json.dumps({"lanes": args.lanes, "tile_words": args.tile_words, "slots": args.slots, "sweep": args.sweep, "pair_launches": b.info.pair_launches, "ms": ms,
                       "gate_words": gate_words, "algorithmic_bytes": 48 * gate_words,
                       "checksum": f"{int((ov.sum() ^ om.sum()).item()) & 0xFFFFFFFFFFFFFFFF:#018x}"}))
 

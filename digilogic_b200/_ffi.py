@@ -24,7 +24,7 @@ class SimInfo(C.Structure):
 class BatchInfo(C.Structure):
     _fields_ = [
         ("tile_words", u32), ("n_slots", u32), ("sweep", u32), ("tasks_per_pass", u32), ("grid_ctas", u32),
-        ("gates_per_task", u32), ("n_ranks", u32), ("rank", u32), ("peers_mapped", u32), ("pad", u32),
+        ("gates_per_task", u32), ("n_ranks", u32), ("rank", u32), ("peers_mapped", u32), ("pair_launches", u32),
         ("store_bytes", u64), ("words_local", u64), ("last_tiles", u64), ("last_tickets", u64),
     ]
 
@@ -55,6 +55,8 @@ SIGNATURES = {
     "b2_build": (vp, [vp]),
     "b2_sim_free": (None, [vp]),
     "b2_sim_get_info": (i32, [vp, C.POINTER(SimInfo)]),
+    "b2_sim_get_pair_info": (i32, [vp, pu64, pu64, pu64]),
+    "b2_sim_plan_pairs": (i32, [vp, vp, u32, pu64]),
     "b2_wire_width": (i32, [vp, u32, pu8]),
     "b2_sim_set_device": (i32, [vp, i32]),
     "b2_sim_set_stream": (i32, [vp, vp]),

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdigilogic_b200.so")
 SOURCES = ["engine.cu", "batch.cu", "netlist.cpp", "capi.cpp"]
-HEADERS = ["engine.hpp", "netlist.hpp", "batch.hpp", "sweep.cuh", "device_ops.cuh", "capi_types.hpp", os.path.join("..", "..", "include", "digilogic_b200.h")]
+HEADERS = ["engine.hpp", "netlist.hpp", "batch.hpp", "sweep.cuh", "pair.cuh", "pair_plan.hpp", "device_ops.cuh", "capi_types.hpp", os.path.join("..", "..", "include", "digilogic_b200.h")]
 
 
 def _nvcc() -> str:

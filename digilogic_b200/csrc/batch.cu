@@ -382,6 +382,11 @@ int Batch::info(BatchInfo *out) {
     out->n_ranks = comm_ ? (uint32_t)comm_->n_ranks() : 1;
     out->rank = comm_ ? (uint32_t)comm_->rank() : 0;
     out->peers_mapped = peers_mapped_ ? 1 : 0;
+    if (!replicas_.empty()) {
+        uint64_t pl = 0;
+        replicas_[0]->pair_info(&pl, nullptr, nullptr);
+        out->pair_launches = (uint32_t)pl;
+    }
     out->store_bytes = store_bytes_;
     out->words_local = words_local_;
     out->last_tiles = last_tiles_;

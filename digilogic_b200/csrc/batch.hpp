@@ -42,7 +42,7 @@ struct BatchInfo {
     uint32_t tasks_per_pass;   // sweep: tasks of one tile
     uint32_t grid_ctas, gates_per_task;
     uint32_t n_ranks, rank, peers_mapped;
-    uint32_t pad;
+    uint32_t pair_launches;    // replicas: launches per tile of the level-pair plan (0 = one per level)
     uint64_t store_bytes;
     uint64_t words_local;      // lane-words per rank of the gathered planes (0 without a communicator)
     uint64_t last_tiles, last_tickets;

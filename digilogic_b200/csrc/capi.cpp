@@ -1,6 +1,7 @@
 // capi.cpp — the extern "C" boundary declared in include/digilogic_b200.h, and the
 // B200Server state machine that mirrors GsimServer (reference
 // crates/digilogic_gsim/src/lib.rs:5-52,101-239).
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -9,6 +10,7 @@
 #include "../../include/digilogic_b200.h"
 #include "engine.hpp"
 #include "netlist.hpp"
+#include "pair_plan.hpp"
 
 #include "capi_types.hpp"
 
@@ -242,6 +244,38 @@ int b2_sim_get_info(const b2_sim *s, b2_sim_info *out) {
     return B2_OK;
 }
 
+int b2_sim_get_pair_info(const b2_sim *s, uint64_t *launches, uint64_t *children, uint64_t *unstored) {
+    if (!s) return B2_ERR_NULL;
+    s->e->pair_info(launches, children, unstored);
+    return B2_OK;
+}
+
+int b2_sim_plan_pairs(const b2_sim *s, const uint32_t *keep_wires, uint32_t n_keep, uint64_t out[6]) {
+    if (!s || !out || (n_keep && !keep_wires)) return B2_ERR_NULL;
+    GUARD_BEGIN
+    const b2::Compiled &n = s->e->net();
+    std::vector<uint32_t> keep;
+    for (uint32_t i = 0; i < n_keep; i++) {
+        if (keep_wires[i] >= n.n_wires()) return B2_ERR_INVALID_WIRE_ID;
+        for (uint32_t j = 0; j < n.width[keep_wires[i]]; j++) keep.push_back(n.row_of_bit[n.bit_off[keep_wires[i]] + j]);
+    }
+    std::sort(keep.begin(), keep.end());
+    keep.erase(std::unique(keep.begin(), keep.end()), keep.end());
+    b2::PairPlanHost plan;
+    if (!b2::plan_pairs(n, keep, plan)) return B2_ERR_INVALID_ARG;
+    uint64_t now = 0;
+    for (const b2::PairItem &it : plan.items)
+        now += ((it.meta & b2::PM_NOW_P) != 0) + ((it.meta & b2::PM_NOW_C1) != 0) + ((it.meta & b2::PM_NOW_C2) != 0);
+    out[0] = plan.launches.size();
+    out[1] = plan.items.size();
+    out[2] = plan.n_children;
+    out[3] = plan.n_unstored;
+    out[4] = plan.disc_rows.size();
+    out[5] = now;
+    return B2_OK;
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
 int b2_wire_width(const b2_sim *s, uint32_t wire, uint8_t *out_width) {
     if (!s || !out_width) return B2_ERR_NULL;
     if (wire >= s->e->net().n_wires()) return B2_ERR_INVALID_WIRE_ID;
@@ -266,6 +300,7 @@ int b2_sim_set_option(b2_sim *s, int option, int64_t value) {
         case B2_OPT_L2_HINTS: s->e->set_l2_hints(value != 0); return B2_OK;
         case B2_OPT_PERIOD2_SKIP: s->e->set_period2_skip(value != 0); return B2_OK;
         case B2_OPT_PDL: s->e->set_pdl((uint32_t)value); return B2_OK;
+        case B2_OPT_PAIR_FUSION: s->e->set_pair_fusion(value != 0); return B2_OK;
         case B2_OPT_CONFLICT_NEEDS_DISAGREE: return s->e->set_lenient_conflicts(value != 0) ? B2_OK : B2_ERR_INVALID_ARG;
         default: return B2_ERR_INVALID_ARG;
     }

@@ -48,6 +48,12 @@ __device__ __forceinline__ void st_pair(uint64_t *p, ulonglong2 v) {
     asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }
 
+// the same store; with `first` the line gets L2 evict-first priority (a row nobody reads soon)
+__device__ __forceinline__ void st_pair_hint(uint64_t *p, ulonglong2 v, uint32_t first, uint64_t policy) {
+    if (first) asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1,%2}, %3;" ::"l"(p), "l"(v.x), "l"(v.y), "l"(policy) : "memory");
+    else asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+
 // 4-state gate on one 64-lane word: k1 = known one, k0 = known zero.
 typedef unsigned long long u64;  // the element type of ulonglong2
 // sem: SemFlags of the netlist — the reconstructed points A.6-6 / A.6-7 (does an enabled buffer / a slice or merge pass a

@@ -23,6 +23,7 @@
 #include "../../include/digilogic_b200.h"
 #include "engine.hpp"
 #include "device_ops.cuh"
+#include "pair.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -1414,9 +1415,17 @@ void Engine::copy_options_from(const Engine &o) {
     opt_l2_hints_ = o.opt_l2_hints_;
     opt_pdl_ = o.opt_pdl_;
     opt_discard_ = o.opt_discard_;
+    opt_pair_ = o.opt_pair_;
     disc_short_ = o.disc_short_;
     disc_never_ = o.disc_never_;
     opt_flags_ = o.opt_flags_;
+}
+
+PairPlanDev::~PairPlanDev() {
+    if (device < 0) return;
+    cudaSetDevice(device);
+    cudaFree(items);
+    cudaFree(disc_rows);
 }
 
 DeviceNet::~DeviceNet() {
@@ -2146,6 +2155,51 @@ int Engine::materialise_valid() {
 }
 
 #define EVAL2_U 4
+
+// The level-pair plan for this netlist, device and set of kept rows: taken from the netlist's cache when another replica
+// has built it, else planned on the host (plan_pairs) and uploaded.  pair_ stays null when the netlist is not eligible.
+int Engine::ensure_pair_plan() {
+    if (pair_ || pair_tried_) return B2_OK;
+    pair_tried_ = true;
+    std::lock_guard<std::mutex> lock(share_->m);
+    auto it = share_->pair_plans.find(device_);
+    if (it != share_->pair_plans.end()) {
+        std::shared_ptr<PairPlanDev> have = it->second.lock();
+        if (have && have->keep_rows == keep_rows_) {
+            pair_ = have;
+            return B2_OK;
+        }
+    }
+    PairPlanHost plan;
+    if (!plan_pairs(net_, keep_rows_, plan)) return B2_OK;
+    auto dev = std::make_shared<PairPlanDev>();
+    dev->device = device_;
+    dev->keep_rows = keep_rows_;
+    dev->n_items = plan.items.size();
+    dev->n_children = plan.n_children;
+    dev->n_unstored = plan.n_unstored;
+    for (const PairLaunch &l : plan.launches) {
+        dev->launch_tab.push_back(l.item_begin);
+        dev->launch_tab.push_back(l.item_end);
+        dev->launch_tab.push_back(l.disc_begin);
+        dev->launch_tab.push_back(l.disc_end);
+    }
+    CU_TRY(cudaMalloc(&dev->items, std::max<size_t>(plan.items.size(), 1) * sizeof(PairItem)));
+    CU_TRY(cudaMalloc((void **)&dev->disc_rows, std::max<size_t>(plan.disc_rows.size(), 1) * 4));
+    CU_TRY(cudaMemcpyAsync(dev->items, plan.items.data(), plan.items.size() * sizeof(PairItem), cudaMemcpyHostToDevice, ST));
+    CU_TRY(cudaMemcpyAsync(dev->disc_rows, plan.disc_rows.data(), plan.disc_rows.size() * 4, cudaMemcpyHostToDevice, ST));
+    CU_TRY(cudaStreamSynchronize(ST));  // the host vectors go away; other replicas' streams may use the plan next
+    share_->pair_plans[device_] = dev;
+    pair_ = dev;
+    return B2_OK;
+}
+
+void Engine::pair_info(uint64_t *launches, uint64_t *children, uint64_t *unstored) const {
+    const bool on = pair_ && last_mode_ == 1 && last_pair_;
+    if (launches) *launches = on ? pair_->launch_tab.size() / 4 : 0;
+    if (children) *children = on ? pair_->n_children : 0;
+    if (unstored) *unstored = on ? pair_->n_unstored : 0;
+}
 static const uint32_t kFlagSlots = 8, kFlagLag = 2;
 // device-side loop: entered when listed gates x row words of an application is at most this, left above four times this
 static const uint64_t kLoopEntryRowWords = 1ull << 20;
@@ -2175,7 +2229,12 @@ int Engine::run_levelised(bool async) {
     // CUDA graph and replayed per run, which takes the per-launch CPU cost and most of the
     // launch-to-launch gap out of small tiles (hundreds of levels of a few microseconds each).
     const bool want_graph = opt_graph_ && net_.levels.size() >= 8;
-    const uint64_t gkey = ((uint64_t)(uintptr_t)V) ^ ((uint64_t)stride_ << 2) ^ (kv ? 1u : 0u) ^ (opt_l2_hints_ ? 2u : 0u) ^ (opt_discard_ ? 8u : 0u) ^ ((uint64_t)opt_pdl_ << 4);
+    const uint64_t gkey = ((uint64_t)(uintptr_t)V) ^ ((uint64_t)stride_ << 2) ^ (kv ? 1u : 0u) ^ (opt_l2_hints_ ? 2u : 0u) ^ (opt_discard_ ? 8u : 0u) ^ ((uint64_t)opt_pdl_ << 4) ^ (opt_pair_ ? 64u : 0u);
+    // level-pair fusion: only where rows need not survive their last reader (set_discard), plain two-plane rows, whole-line rows
+    const bool pair_path = opt_pair_ && opt_discard_ && !kv && extra_rows_.empty() && stride_ % 16 == 0;
+    if (pair_path && (rc0 = ensure_pair_plan())) return rc0;
+    const bool use_pair = pair_path && pair_ != nullptr;
+    last_pair_ = use_pair;
     if (want_graph && level_graph_exec_ && level_graph_key_ == gkey) {
         CU_TRY(cudaGraphLaunch((cudaGraphExec_t)level_graph_exec_, ST));
         g_launches.fetch_add(level_graph_nodes_, std::memory_order_relaxed);
@@ -2190,7 +2249,39 @@ int Engine::run_levelised(bool async) {
             if (!capturing) cudaGetLastError();
         }
         uint32_t nodes = 0;
+        if (use_pair) {
+            const std::vector<uint32_t> &tab = pair_->launch_tab;
+            for (size_t l = 0; l + 3 < tab.size(); l += 4) {
+                PairArgs a;
+                a.items = (const uint4 *)pair_->items + 2 * (size_t)tab[l];
+                a.n_items = tab[l + 1] - tab[l];
+                a.disc_rows = pair_->disc_rows + tab[l + 2];
+                a.n_disc = tab[l + 3] - tab[l + 2];
+                a.val = V;
+                a.vld = M;
+                a.stride = stride_;
+                a.pairs = pairs;
+                a.pair_blocks = sh.pair_blocks;
+                a.sem = net_.sem_flags;
+                a.discard = 1;
+                a.hints = opt_l2_hints_ ? 1 : 0;
+                a.pdl = opt_pdl_;
+                if (a.n_items == 0) continue;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(sh.pair_blocks * ((a.n_items + sh.block.y - 1) / sh.block.y));
+                cfg.blockDim = sh.block;
+                cfg.stream = ST;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = a.pdl ? 1 : 0;
+                cudaLaunchKernelEx(&cfg, k_eval_pair, a);
+                nodes++;
+            }
+        }
         for (const Level &lv : net_.levels) {
+            if (use_pair) break;
             if (lv.g2_end > lv.g2_begin) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, V, M, V, M, nullptr, lv.g2_begin, lv.g2_end, net_.n_src, stride_, pairs,
                             sh.pair_blocks, d_kv_, nullptr, nullptr, d_all_valid_};
@@ -2824,12 +2915,17 @@ void Engine::set_discard(bool on, const uint32_t *keep_wires, uint32_t n) {
     level_graph_key_ = 0;
     disc_short_.clear();
     disc_never_.clear();
+    pair_.reset();
+    pair_tried_ = false;
+    keep_rows_.clear();
     if (!opt_discard_) return;
     std::vector<uint32_t> keep;
     for (uint32_t i = 0; i < n; i++)
         if (keep_wires[i] < net_.n_wires())
             for (uint32_t j = 0; j < net_.width[keep_wires[i]]; j++) keep.push_back(net_.row_of_bit[net_.bit_off[keep_wires[i]] + j]);
     std::sort(keep.begin(), keep.end());
+    keep.erase(std::unique(keep.begin(), keep.end()), keep.end());
+    keep_rows_ = keep;
     // the largest stretch of [b, e) without a kept row
     auto largest_gap = [&](uint32_t b, uint32_t e) -> RowRange {
         RowRange best{b, b};

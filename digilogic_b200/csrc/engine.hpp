@@ -37,6 +37,19 @@ struct DeviceNet {
     ~DeviceNet();
 };
 
+// Level-pair fusion plan of a netlist on one device (pair.cuh): items, discard lists, launch table.  Shared by the
+// replicas of a batch (same netlist, same kept rows).
+struct PairLaunch;
+struct PairPlanDev {
+    int device = -1;
+    std::vector<uint32_t> keep_rows;  // sorted: the rows the plan keeps (its key)
+    void *items = nullptr;            // PairItem[] on the device
+    uint32_t *disc_rows = nullptr;
+    std::vector<uint32_t> launch_tab;  // 4 per launch: item_begin, item_end, disc_begin, disc_end
+    uint64_t n_items = 0, n_children = 0, n_unstored = 0;
+    ~PairPlanDev();
+};
+
 // One compiled netlist (host arrays) and its per-device copies.
 struct NetShare {
     explicit NetShare(Compiled &&c) : net(std::move(c)) {}
@@ -45,6 +58,7 @@ struct NetShare {
     std::map<int, std::weak_ptr<DeviceNet>> on_device;
     // the device copy for `device` (current CUDA device must be `device`); uploaded on first use; rc = b2_status
     std::shared_ptr<DeviceNet> acquire(int device, int &rc);
+    std::map<int, std::weak_ptr<PairPlanDev>> pair_plans;  // per device: the last plan built (reused when the kept rows match)
 };
 
 class Engine {
@@ -112,6 +126,10 @@ class Engine {
     void set_device_loop(bool on) { opt_device_loop_ = on; }
     void set_period2_skip(bool on) { opt_period2_ = on; }
     void set_pdl(uint32_t mode) { opt_pdl_ = mode <= 2 ? mode : 0; level_graph_key_ = 0; }
+    // Level-pair fusion (pair.cuh): acts only on levelised runs with set_discard on, for netlists of one/two-input gates.
+    void set_pair_fusion(bool on) { opt_pair_ = on; level_graph_key_ = 0; }
+    // launches of the last levelised pass / gates evaluated as children / parent rows never stored (0 when the plan is off)
+    void pair_info(uint64_t *launches, uint64_t *children, uint64_t *unstored) const;
     // SURVEY.md A.6-2 alternative (agreeing valid drivers do not conflict); refused for netlists with two firm drivers on a net
     bool set_lenient_conflicts(bool on) {
         if (on && net_.multi_driver) return false;
@@ -239,6 +257,11 @@ class Engine {
     struct RowRange { uint32_t begin, end; };
     std::vector<RowRange> disc_short_, disc_never_;  // per level: rows of the one/two-input class that may be dropped
     bool opt_l2_hints_ = false;
+    bool opt_pair_ = true;
+    std::vector<uint32_t> keep_rows_;      // sorted rows kept by set_discard
+    std::shared_ptr<PairPlanDev> pair_;    // null: not built yet, or the netlist is not eligible (pair_tried_)
+    bool pair_tried_ = false, last_pair_ = false;
+    int ensure_pair_plan();
     uint32_t opt_pdl_ = 2;  // programmatic dependent launch between the level kernels: 0 off, 1 early release, 2 late release  // levelised pass: evict-first hint on fan-ins produced long ago (Compiled::far2)
     bool opt_period2_ = true;   // unit-delay loops fast-forward over an exact period-2 oscillation
     uint32_t opt_flags_ = 0;    // SemFlags: the reconstructed points of SURVEY.md A.6-4..7, one bit each

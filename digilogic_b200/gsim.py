@@ -330,6 +330,20 @@ class Simulator:
         _check(self._lib.b2_sim_get_info(self._h, C.byref(out)), "get_info")
         return out
 
+    @property
+    def pair_info(self) -> tuple:
+        """(launches, children, unstored rows) of the level-pair plan the last levelised run used; zeros = per-level kernels."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self._lib.b2_sim_get_pair_info(self._h, C.byref(a), C.byref(b), C.byref(c)), "get_pair_info")
+        return a.value, b.value, c.value
+
+    def plan_pairs(self, keep_wires) -> dict:
+        """The level-pair plan for `keep_wires` as designated outputs, computed on the host (b2_sim_plan_pairs)."""
+        keep = np.ascontiguousarray(keep_wires, np.uint32)
+        out = (C.c_uint64 * 6)()
+        _check(self._lib.b2_sim_plan_pairs(self._h, _p(keep), keep.size, out), "plan_pairs")
+        return dict(zip(("launches", "items", "children", "unstored", "dropped_later", "dropped_now"), (int(x) for x in out)))
+
     def set_device(self, device: int):
         _check(self._lib.b2_sim_set_device(self._h, device), "set_device")
 
@@ -347,6 +361,7 @@ class Simulator:
     OPT_L2_HINTS = 9
     OPT_PERIOD2_SKIP = 10
     OPT_PDL = 11
+    OPT_PAIR_FUSION = 12
 
     def set_option(self, option: int, value: int):
         _check(self._lib.b2_sim_set_option(self._h, option, value), "set_option")

@@ -198,6 +198,14 @@ typedef struct b2_sim_info {
 } b2_sim_info;
 
 int b2_sim_get_info(const b2_sim *s, b2_sim_info *out);
+/* Level-pair fusion of the last levelised run (B2_OPT_PAIR_FUSION): launches of one pass, gates evaluated as the second gate of an
+   item, rows never stored; all 0 when the last run used the per-level kernels.  Any pointer may be NULL. */
+int b2_sim_get_pair_info(const b2_sim *s, uint64_t *launches, uint64_t *children, uint64_t *unstored);
+/* The level-pair plan this netlist would get with `keep_wires` as the designated outputs, computed on the host (no device
+   needed): out[0] launches, out[1] items, out[2] gates evaluated as the second gate of an item, out[3] rows never stored,
+   out[4] rows dropped from L2 by a later launch, out[5] rows dropped right after their store.  B2_ERR_INVALID_ARG when the
+   netlist is not eligible (feedback, tri-state nets, registers, gates with three or more inputs). */
+int b2_sim_plan_pairs(const b2_sim *s, const uint32_t *keep_wires, uint32_t n_keep, uint64_t out[6]);
 
 /* Simulator::get_wire_width(wire)  (lib.rs:228) */
 int b2_wire_width(const b2_sim *s, uint32_t wire, uint8_t *out_width);
@@ -236,6 +244,11 @@ enum b2_option {
     B2_OPT_PDL = 11,           /* Levelised pass: consecutive level kernels of a simulator are launched with programmatic stream
                                   serialisation (griddepcontrol): the next level's launch and index loads overlap this level's tail.
                                   0 off, 1 dependents released when every CTA has started, 2 (default) when every CTA is about to finish. */
+    B2_OPT_PAIR_FUSION = 12,   /* default 1.  Levelised pass of a simulator that need not keep rows after their last reader (the replicas
+                                  of a batch, B2_BATCH_OPT_DISCARD) and whose netlist has only one/two-input gates: two dependent gates
+                                  are evaluated by one thread — a launch holds items of one gate whose fan-ins are older than the launch
+                                  plus up to two gates reading its output, which they get in registers; a row read only inside its item
+                                  is never stored.  Half the launches, a quarter less traffic through L2; kept rows are bit-identical. */
     B2_OPT_PERIOD2_SKIP = 10,  /* default 1.  Unit-delay loops (device-side loop, resident kernel) detect an exact period-2 oscillation
                                   — every row an application writes equals the row two applications earlier — and jump ahead by an
                                   even number of applications: the state, lane results and step accounting are those of walking
@@ -349,7 +362,7 @@ typedef struct b2_batch_info {
     uint32_t tasks_per_pass;   /* sweep: tasks of one tile (after the first run) */
     uint32_t grid_ctas, gates_per_task;
     uint32_t n_ranks, rank, peers_mapped;
-    uint32_t pad;
+    uint32_t pair_launches;    /* replicas: launches per tile of the level-pair plan (B2_OPT_PAIR_FUSION) after the first run; 0 = one per level */
     uint64_t store_bytes;
     uint64_t words_local;      /* lane-words per rank of the gathered planes (0 without a communicator) */
     uint64_t last_tiles, last_tickets;

@@ -33,7 +33,7 @@ pub struct B2BatchInfo {
     pub n_ranks: u32,
     pub rank: u32,
     pub peers_mapped: u32,
-    pub pad: u32,
+    pub pair_launches: u32,
     pub store_bytes: u64,
     pub words_local: u64,
     pub last_tiles: u64,

@@ -162,6 +162,19 @@ def test_netlist_compiler_fuzz_under_sanitizers(tmp_path):
     assert run.returncode == 0 and "netlist_fuzz ok" in run.stdout, run.stderr[-2000:]
 
 
+def test_level_pair_planner_executed_on_a_scalar_model(tmp_path):
+    """tests/pair_plan_check.cpp: the level-pair plan (B2_OPT_PAIR_FUSION, csrc/pair_plan.hpp) of random netlists, executed on
+    a 4-state scalar model that tracks which rows hold data — every gate once, no read of a dropped or unstored row, kept
+    rows equal to a plain evaluation; host-only, AddressSanitizer + UBSan."""
+    exe = str(tmp_path / "pair_plan_check")
+    res = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", exe,
+                          os.path.join(ROOT, "tests", "pair_plan_check.cpp"), os.path.join(ROOT, "digilogic_b200", "csrc", "netlist.cpp")],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe, "300"], capture_output=True, text=True)
+    assert run.returncode == 0 and "pair_plan_check ok" in run.stdout, run.stderr[-2000:]
+
+
 def test_build_takes_the_builder():
     b = d.SimulatorBuilder()
     a = b.add_wire()
