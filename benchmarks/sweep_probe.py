@@ -50,7 +50,7 @@ def main():
         pdl = f[9] if len(f) > 9 else 0
         sim.set_option(sim.OPT_PDL, pdl)
         sim.set_option(sim.OPT_L2_HINTS, hints)
-        sim.set_option(sim.OPT_PAIR_FUSION, f[10] if len(f) > 10 else 1)
+        sim.set_option(sim.OPT_PAIR_FUSION, f[10] if len(f) > 10 else 0)
         b = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=0, stream=stream.cuda_stream)
         b.set_option(Batch.OPT_TASK_ITERS, iters)
         b.set_option(Batch.OPT_UNROLL, unroll)

@@ -44,6 +44,33 @@ __device__ __forceinline__ ulonglong2 ld_stream_unless(const uint64_t *p, bool s
         : "l"(p), "r"((uint32_t)skip));
     return r;
 }
+// Row loads of a kernel launched with programmatic stream serialisation: the rows are written by the previous grid while this one
+// is already resident, so they are NOT read-only for this kernel's lifetime and must not be .nc loads — ptxas is free to hoist a
+// non-coherent load above griddepcontrol.wait (seen in SASS: LDG...CONSTANT before ACQBULK, and wrong results).  A plain weak
+// load with a memory clobber stays behind the wait.
+__device__ __forceinline__ ulonglong2 ld_dep(const uint64_t *p) {
+    ulonglong2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+    return r;
+}
+// with `first` the line is inserted into L2 with evict-first priority (see ld_stream_hint)
+__device__ __forceinline__ ulonglong2 ld_dep_hint(const uint64_t *p, uint32_t first, uint64_t policy) {
+    ulonglong2 r;
+    if (first)
+        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(r.x), "=l"(r.y) : "l"(p), "l"(policy) : "memory");
+    else
+        asm volatile("ld.global.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ ulonglong2 ld_dep_unless(const uint64_t *p, bool skip) {
+    ulonglong2 r = make_ulonglong2(~0ull, ~0ull);
+    asm volatile(
+        "{ .reg .pred q; setp.eq.u32 q, %3, 0; @q ld.global.L1::no_allocate.v2.u64 {%0,%1}, [%2]; }"
+        : "+l"(r.x), "+l"(r.y)
+        : "l"(p), "r"((uint32_t)skip)
+        : "memory");
+    return r;
+}
 __device__ __forceinline__ void st_pair(uint64_t *p, ulonglong2 v) {
     asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }

@@ -201,15 +201,16 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : ((U == 2 && NIN == 2 && !KV)
                 av[u] = ld_stream(a.in_val + r0);
                 bv[u] = ld_stream(a.in_val + r1);
             } else {
-                av[u] = ld_stream_hint(a.in_val + r0, far[u] & 1, pol_first);
-                bv[u] = ld_stream_hint(a.in_val + r1, far[u] & 2, pol_first);
+                // (ld_dep: with programmatic dependent launch the rows are written while this grid is resident — not .nc data)
+                av[u] = ld_dep_hint(a.in_val + r0, far[u] & 1, pol_first);
+                bv[u] = ld_dep_hint(a.in_val + r1, far[u] & 2, pol_first);
             }
             if (KV) {
                 am[u] = ld_stream_unless(a.in_vld + r0, k0[u]);
                 bm[u] = ld_stream_unless(a.in_vld + r1, k1[u]);
             } else {
-                am[u] = ld_stream_hint(a.in_vld + r0, far[u] & 1, pol_first);
-                bm[u] = ld_stream_hint(a.in_vld + r1, far[u] & 2, pol_first);
+                am[u] = ld_dep_hint(a.in_vld + r0, far[u] & 1, pol_first);
+                bm[u] = ld_dep_hint(a.in_vld + r1, far[u] & 2, pol_first);
             }
         }
     }

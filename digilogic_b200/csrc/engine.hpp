@@ -126,7 +126,7 @@ class Engine {
     void set_device_loop(bool on) { opt_device_loop_ = on; }
     void set_period2_skip(bool on) { opt_period2_ = on; }
     void set_pdl(uint32_t mode) { opt_pdl_ = mode <= 2 ? mode : 0; level_graph_key_ = 0; }
-    // Level-pair fusion (pair.cuh): acts only on levelised runs with set_discard on, for netlists of one/two-input gates.
+    // Level-pair fusion (pair.cuh; default off): acts only on levelised runs with set_discard on, for netlists of one/two-input gates.
     void set_pair_fusion(bool on) { opt_pair_ = on; level_graph_key_ = 0; }
     // launches of the last levelised pass / gates evaluated as children / parent rows never stored (0 when the plan is off)
     void pair_info(uint64_t *launches, uint64_t *children, uint64_t *unstored) const;
@@ -257,7 +257,7 @@ class Engine {
     struct RowRange { uint32_t begin, end; };
     std::vector<RowRange> disc_short_, disc_never_;  // per level: rows of the one/two-input class that may be dropped
     bool opt_l2_hints_ = false;
-    bool opt_pair_ = true;
+    bool opt_pair_ = false;
     std::vector<uint32_t> keep_rows_;      // sorted rows kept by set_discard
     std::shared_ptr<PairPlanDev> pair_;    // null: not built yet, or the netlist is not eligible (pair_tried_)
     bool pair_tried_ = false, last_pair_ = false;

@@ -61,10 +61,12 @@ __global__ void __launch_bounds__(256, 5) k_eval_pair(const PairArgs a) {
     const bool c1 = meta & PM_C1, c2 = meta & PM_C2;
     const bool skip1 = !c1 || (meta & PM_C1_SELF), skip2 = !c2 || (meta & PM_C2_SELF);
     const uint64_t *v = a.val + col, *m = a.vld + col;
-    const ulonglong2 av = ld_stream(v + (size_t)q0.x * a.stride), am = ld_stream(m + (size_t)q0.x * a.stride);
-    const ulonglong2 bv = ld_stream(v + (size_t)q0.y * a.stride), bm = ld_stream(m + (size_t)q0.y * a.stride);
-    const ulonglong2 xv = ld_stream_unless(v + (size_t)q1.x * a.stride, skip1), xm = ld_stream_unless(m + (size_t)q1.x * a.stride, skip1);
-    const ulonglong2 yv = ld_stream_unless(v + (size_t)q1.z * a.stride, skip2), ym = ld_stream_unless(m + (size_t)q1.z * a.stride, skip2);
+    // (ld_dep, not .nc loads: the rows were written by the previous grid while this one was already resident, and ptxas hoists
+    // non-coherent loads above griddepcontrol.wait)
+    const ulonglong2 av = ld_dep(v + (size_t)q0.x * a.stride), am = ld_dep(m + (size_t)q0.x * a.stride);
+    const ulonglong2 bv = ld_dep(v + (size_t)q0.y * a.stride), bm = ld_dep(m + (size_t)q0.y * a.stride);
+    const ulonglong2 xv = ld_dep_unless(v + (size_t)q1.x * a.stride, skip1), xm = ld_dep_unless(m + (size_t)q1.x * a.stride, skip1);
+    const ulonglong2 yv = ld_dep_unless(v + (size_t)q1.z * a.stride, skip2), ym = ld_dep_unless(m + (size_t)q1.z * a.stride, skip2);
     // a row whose last reader ran in the previous launch: dropped from L2 by the CTAs that start first, once this thread's
     // own loads are on their way
     if (drops) {

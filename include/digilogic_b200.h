@@ -244,11 +244,11 @@ enum b2_option {
     B2_OPT_PDL = 11,           /* Levelised pass: consecutive level kernels of a simulator are launched with programmatic stream
                                   serialisation (griddepcontrol): the next level's launch and index loads overlap this level's tail.
                                   0 off, 1 dependents released when every CTA has started, 2 (default) when every CTA is about to finish. */
-    B2_OPT_PAIR_FUSION = 12,   /* default 1.  Levelised pass of a simulator that need not keep rows after their last reader (the replicas
+    B2_OPT_PAIR_FUSION = 12,   /* default 0 (measured: as fast as the per-level kernels, not faster — DESIGN.md section 10).  Levelised pass of a simulator that need not keep rows after their last reader (the replicas
                                   of a batch, B2_BATCH_OPT_DISCARD) and whose netlist has only one/two-input gates: two dependent gates
                                   are evaluated by one thread — a launch holds items of one gate whose fan-ins are older than the launch
                                   plus up to two gates reading its output, which they get in registers; a row read only inside its item
-                                  is never stored.  Half the launches, a quarter less traffic through L2; kept rows are bit-identical. */
+                                  is never stored.  Half the launches, 17 % less traffic between the SMs and L2; kept rows are bit-identical. */
     B2_OPT_PERIOD2_SKIP = 10,  /* default 1.  Unit-delay loops (device-side loop, resident kernel) detect an exact period-2 oscillation
                                   — every row an application writes equals the row two applications earlier — and jump ahead by an
                                   even number of applications: the state, lane results and step accounting are those of walking

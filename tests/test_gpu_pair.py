@@ -118,3 +118,28 @@ def test_plain_simulator_runs_never_use_it():
     rv, rm = _oracle_rows(gen, gen.n_wires, gen.inputs, 32, 1, 0, 1)
     gv, gm = sim.gather_wires_host(np.arange(gen.n_wires, dtype=np.uint32))
     assert (gv == rv).all() and (gm == rm).all()
+
+
+@pytest.mark.parametrize("pair", [1, 0])
+@pytest.mark.parametrize("pdl", [1, 2])
+def test_programmatic_dependent_launch_keeps_the_row_loads_behind_the_wait(pdl, pair):
+    """Tiny tiles, tiny launches: the next launch is resident long before the previous one has written its rows.  A row load
+    hoisted above griddepcontrol.wait (ptxas does that to .nc loads) shows up here as wrong outputs; with early release
+    (B2_OPT_PDL = 1) on every run."""
+    rng = np.random.default_rng(16 * 7 + 300)
+    nl, first_in = random_netlist(rng, 20, 300, cyclic=False, wide=False, mux=False)
+    inputs = np.arange(first_in, first_in + 20, dtype=np.uint32)
+    outputs = np.arange(20, nl.n_wires, 3, dtype=np.uint32)
+    words = 16 * 5
+    rv, rm = _oracle_rows(nl, nl.n_wires, inputs, words, 0xFACE, 3, 1)
+    for rep in range(3):
+        sim = nl.replay(d.SimulatorBuilder()).build()
+        sim.set_option(sim.OPT_PDL, pdl)
+        sim.set_option(sim.OPT_PAIR_FUSION, pair)
+        b = Batch(sim, inputs, outputs, 16, 2)
+        ov = np.zeros((len(outputs), words), np.uint64)
+        om = np.zeros_like(ov)
+        for _ in range(3):
+            b.run_generated(0xFACE, 1, 3, words, 10_000, ov, om)
+            assert b.wait() == SimulationRunResult.Ok
+            assert (ov == rv[outputs]).all() and (om == rm[outputs]).all()
