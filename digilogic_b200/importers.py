@@ -12,7 +12,8 @@ and 2 — SURVEY.md §8 row f1.
   set: `$xnor`, `$mux`, `$pmux`, `$reduce_and/or/xor/xnor/bool`, `$logic_not/and/or`, `$tribuf`, `$dff`,
   `$dffe`, `$sdff`, `$sdffe`, `$sdffce`, `$dlatch`, and — through gsim's word-level components, on wide wires that `emit()`
   merges from and slices back into the 1-bit nets — `$add`, `$sub`, `$neg`, `$mul`, `$lt/$le/$eq/$ne/$ge/$gt`,
-  `$shl/$sshl/$shr/$sshr`; constant bits "0"/"1" become two extra input nets (`const_nets`) the caller drives.
+  `$shl/$sshl/$shr/$sshr`, `$pos`, `$eqx/$nex`; `$mem_v2` is lowered onto registers, address decoders and multiplexer trees
+  (`_lower_mem_v2`); constant bits "0"/"1" become two extra input nets (`const_nets`) the caller drives.
 
 Both produce an `ImportedCircuit`, whose `emit()` issues the same calls the GUI client sends
 (crates/digilogic_netcode/src/client.rs:288-427): one 1-bit net per net, then one gate per
@@ -37,7 +38,8 @@ DIG_SYMBOLS = {
 }
 YOSYS_CELLS = {"$and": AND, "$or": OR, "$xor": XOR, "$not": NOT, "$xnor": XNOR}
 # cell -> (unsigned, signed) comparator op of the engine (b2_compare_op)
-YOSYS_COMPARE = {"$eq": (0, 0), "$ne": (1, 1), "$lt": (2, 6), "$gt": (3, 7), "$le": (4, 8), "$ge": (5, 9)}
+YOSYS_COMPARE = {"$eq": (0, 0), "$ne": (1, 1), "$lt": (2, 6), "$gt": (3, 7), "$le": (4, 8), "$ge": (5, 9),
+                 "$eqx": (0, 0), "$nex": (1, 1)}     # case equality: the same comparator on defined inputs
 YOSYS_REDUCE = {"$reduce_and": AND, "$reduce_or": OR, "$reduce_bool": OR, "$reduce_xor": XOR, "$reduce_xnor": XNOR, "$logic_not": NOR}
 
 
@@ -239,6 +241,92 @@ def adder_dig(nbits: int = 4) -> str:
 
 # ------------------------------------------------------------------------------ Yosys JSON
 
+def _lower_mem_v2(circ, cname, conn, params, net, tmp, flag, param_bits):
+    """Yosys `$mem_v2` (crates/digilogic_serde/src/yosys.rs:207, `MemV2 => todo!()`) lowered onto registers, multiplexers and
+    gates: one register per stored bit (so a word is Undefined until it has been written, like gsim's register), per write port
+    an address decoder (n-ary AND over the address bits or their complements) whose hit, ANDed with the port's per-bit write
+    enable, is the register's enable; per read port a binary tree of 2:1 multiplexers over the words, selected by the address
+    bits (an address bit that is not a valid 0/1 reads Undefined).  Supported: any number of read ports, asynchronous or clocked
+    on a rising edge with an enable (read-before-write: both registers sample the state before the edge); ONE write port clocked
+    on a rising edge; SIZE <= 256 words; no reset values, no initial contents other than 'x'."""
+    size, abits, width, offset = flag("SIZE"), flag("ABITS"), flag("WIDTH"), flag("OFFSET")
+    n_rd, n_wr = flag("RD_PORTS"), flag("WR_PORTS")
+    if not (1 <= size <= 256 and 1 <= abits <= 16 and width >= 1):
+        raise ValueError(f"$mem_v2 {cname}: SIZE {size} / ABITS {abits} / WIDTH {width} outside the supported range")
+    if n_wr > 1:
+        raise ValueError(f"$mem_v2 {cname}: {n_wr} write ports (one is supported)")
+    init = params.get("INIT", "x")
+    if isinstance(init, str) and set(init) - set("xX"):
+        raise ValueError(f"$mem_v2 {cname}: initial contents are not supported (registers start Undefined)")
+    if n_wr and (flag("WR_CLK_ENABLE") & 1) != 1:
+        raise ValueError(f"$mem_v2 {cname}: asynchronous write ports are not supported")
+    if n_wr and (flag("WR_CLK_POLARITY") & 1) != 1:
+        raise ValueError(f"$mem_v2 {cname}: falling-edge write ports are not supported")
+    if flag("RD_TRANSPARENCY_MASK") or flag("RD_COLLISION_X_MASK"):
+        raise ValueError(f"$mem_v2 {cname}: transparent / collision-x read ports are not supported")
+
+    def complement(n):
+        inv = tmp()
+        circ.gates.append((NOT, [n], inv))
+        return inv
+
+    def gate(kind, ins):
+        out = tmp()
+        circ.gates.append((kind, ins if len(ins) > 1 else ins * 2, out))
+        return out
+
+    # the stored bits
+    q = [[tmp() for _ in range(width)] for _ in range(size)]
+    if n_wr:
+        wa = [net(b) for b in conn["WR_ADDR"][:abits]]
+        wa_n = [complement(a) for a in wa]
+        clk = net(conn["WR_CLK"][0])
+        wen = [net(b) for b in conn["WR_EN"][:width]]
+        wdat = [net(b) for b in conn["WR_DATA"][:width]]
+        for e in range(size):
+            addr = e + offset
+            if addr >> abits:
+                raise ValueError(f"$mem_v2 {cname}: word {addr} is not addressable with {abits} address bits")
+            hit = gate(AND, [wa[i] if (addr >> i) & 1 else wa_n[i] for i in range(abits)])
+            for j in range(width):
+                circ.gates.append((REG, [wdat[j], gate(AND, [hit, wen[j]]), clk], q[e][j]))
+    floating = None
+    for r in range(n_rd):
+        ra = [net(b) for b in conn["RD_ADDR"][r * abits:(r + 1) * abits]]
+        clocked = (flag("RD_CLK_ENABLE") >> r) & 1
+        if clocked and ((flag("RD_CLK_POLARITY") >> r) & 1) != 1:
+            raise ValueError(f"$mem_v2 {cname}: falling-edge read ports are not supported")
+        for j in range(width):
+            # words by address, padded to a power of two with a floating net (reads Undefined through the multiplexer)
+            level = []
+            for addr in range(1 << abits):
+                e = addr - offset
+                if 0 <= e < size:
+                    level.append(q[e][j])
+                else:
+                    if floating is None:
+                        floating = tmp()
+                    level.append(floating)
+            out = net(conn["RD_DATA"][r * width + j])
+            for i in range(abits):
+                last = i == abits - 1 and not clocked
+                nxt = []
+                for k in range(0, len(level), 2):
+                    if level[k] == level[k + 1] == floating and floating is not None:
+                        nxt.append(floating)
+                        continue
+                    y = out if (last and len(level) == 2) else tmp()
+                    circ.gates.append((MUX, [ra[i], level[k], level[k + 1]], y))
+                    nxt.append(y)
+                level = nxt
+            if clocked:
+                en = net(conn["RD_EN"][r]) if "RD_EN" in conn else net("1")
+                circ.gates.append((REG, [level[0], en, net(conn["RD_CLK"][r])], out))
+            elif level[0] != out:       # a one-word memory behind floating padding: copy
+                circ.gates.append((OR, [level[0], level[0]], out))
+
+
+
 def load_yosys(text: str, module: str | None = None) -> ImportedCircuit:
     doc = json.loads(text)
     mods = doc["modules"]
@@ -393,6 +481,11 @@ def load_yosys(text: str, module: str | None = None) -> ImportedCircuit:
                 raise ValueError(f"{ctype} with a shift amount wider than 8 bits ({cname})")
             op = "shl" if ctype in ("$shl", "$sshl") else ("ashr" if ctype == "$sshr" and flag("A_SIGNED") else "lshr")
             circ.wide.append((op, [extend(conn["A"], "A_SIGNED", width), [net(b) for b in conn["B"]]], [net(b) for b in conn["Y"]]))
+        elif ctype == "$pos":      # Y = A, extended to the width of Y
+            for j, src in enumerate(extend(conn["A"], "A_SIGNED", len(conn["Y"]))):
+                circ.gates.append((OR, [src, src], net(conn["Y"][j])))
+        elif ctype == "$mem_v2":
+            _lower_mem_v2(circ, cname, conn, params, net, tmp, flag, param_bits)
         else:
             raise ValueError(f"unsupported cell type {ctype!r} ({cname})")
     circ.n_nets = len(net_of)

@@ -270,3 +270,159 @@ def test_word_level_cells_on_gpu_against_oracle(resident):
         assert int(sim.run_sim(ms)) == ref.run_sim(ms), rnd
         for w in range(n_wires):
             assert sim.get_wire_state(w) == LogicState(*ref.get_wire_state(w)), (rnd, w)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# $mem_v2: lowered onto registers, address decoders and multiplexer trees
+
+MEM = dict(size=12, offset=2, abits=4, width=4)
+
+
+def mem_json():
+    """clk 2; write port: wa 10..13, wd 20..23, we 30..33 (per bit); read port 0 (asynchronous): ra 40..43 -> rd 50..53;
+    read port 1 (clocked on clk, enable 3): rb 60..63 -> rq 70..73."""
+    p = MEM
+    cells = {"mem": {"hide_name": 0, "type": "$mem_v2", "attributes": {}, "port_directions": {},
+                     "parameters": {"MEMID": "\\\\m", "SIZE": format(p["size"], "b"), "OFFSET": format(p["offset"], "b"), "ABITS": format(p["abits"], "b"),
+                                    "WIDTH": format(p["width"], "b"), "INIT": "x", "RD_PORTS": "10", "WR_PORTS": "1",
+                                    "RD_CLK_ENABLE": "10", "RD_CLK_POLARITY": "11", "RD_TRANSPARENCY_MASK": "00", "RD_COLLISION_X_MASK": "00",
+                                    "WR_CLK_ENABLE": "1", "WR_CLK_POLARITY": "1"},
+                     "connections": {"RD_CLK": ["x", 2], "RD_EN": ["1", 3], "RD_ADDR": [40, 41, 42, 43, 60, 61, 62, 63],
+                                     "RD_DATA": [50, 51, 52, 53, 70, 71, 72, 73], "RD_ARST": ["0", "0"], "RD_SRST": ["0", "0"],
+                                     "WR_CLK": [2], "WR_EN": [30, 31, 32, 33], "WR_ADDR": [10, 11, 12, 13], "WR_DATA": [20, 21, 22, 23]}}}
+    ports = {"clk": {"direction": "input", "bits": [2]}, "ren": {"direction": "input", "bits": [3]},
+             "wa": {"direction": "input", "bits": [10, 11, 12, 13]}, "wd": {"direction": "input", "bits": [20, 21, 22, 23]},
+             "we": {"direction": "input", "bits": [30, 31, 32, 33]}, "ra": {"direction": "input", "bits": [40, 41, 42, 43]},
+             "rb": {"direction": "input", "bits": [60, 61, 62, 63]},
+             "rd": {"direction": "output", "bits": [50, 51, 52, 53]}, "rq": {"direction": "output", "bits": [70, 71, 72, 73]}}
+    return json.dumps({"creator": "test", "modules": {"ram": {"attributes": {"top": "1".zfill(32)}, "ports": ports, "cells": cells, "netnames": {}}}})
+
+
+def mem_check(make, set_drive, run, get, clocks=120):
+    """Random writes with per-bit enables, reads through both ports, against a per-bit Python model (None = Undefined)."""
+    p = MEM
+    circ = importers.load_yosys(mem_json())
+    kinds = [g[0] for g in circ.gates]
+    assert kinds.count(importers.REG) == p["size"] * p["width"] + p["width"]       # stored bits + the clocked read port
+    sim = make(circ)
+    for n, v in circ.const_nets.items():
+        set_drive(sim, n, (v, 1))
+    rng = np.random.default_rng(21)
+    mem = {a: [None] * p["width"] for a in range(p["offset"], p["offset"] + p["size"])}
+    rq = [None] * p["width"]
+
+    def drive(name, value):
+        for j, n in enumerate(circ.inputs[name]):
+            set_drive(sim, n, ((value >> j) & 1, 1))
+
+    def word(name):
+        return [get(sim, n) for n in circ.outputs[name]]
+
+    def want(bits):
+        return [X if b is None else (b, 1) for b in bits]
+
+    drive("clk", 0); drive("ren", 0)
+    for t in range(clocks):
+        wa, wd, we, ra, rb, ren = (int(x) for x in (rng.integers(0, 16), rng.integers(0, 16), rng.integers(0, 16), rng.integers(0, 16),
+                                                        rng.integers(0, 16), rng.integers(0, 2)))
+        if t % 3 == 0:
+            ra = wa                                        # read what is being written: old value before the edge, new after
+        if t % 5 == 0:
+            rb = wa                                        # the clocked port reads the word before the write lands
+        drive("wa", wa); drive("wd", wd); drive("we", we); drive("ra", ra); drive("rb", rb); drive("ren", ren)
+        run(sim)
+        assert word("rd") == want(mem.get(ra, [None] * p["width"])), t
+        drive("clk", 1); run(sim)
+        if ren:
+            rq = list(mem.get(rb, [None] * p["width"]))    # sampled from the state before the edge
+        if wa in mem:
+            mem[wa] = [((wd >> j) & 1) if (we >> j) & 1 else mem[wa][j] for j in range(p["width"])]
+        assert word("rd") == want(mem.get(ra, [None] * p["width"])), t
+        assert word("rq") == want(rq), t
+        drive("clk", 0); run(sim)
+        assert word("rq") == want(rq), t
+    assert any(b is not None for w in mem.values() for b in w) and any(b is None for w in mem.values() for b in w)
+
+
+def test_mem_v2_on_the_oracle():
+    mem_check(lambda c: c.emit(oracle.Builder()).build(), lambda s, n, st: s.set_wire_drive(n, *st),
+              lambda s: s.run_sim(1000), lambda s, n: s.get_wire_state(n))
+
+
+def test_mem_v2_refuses_what_it_cannot_lower():
+    doc = json.loads(mem_json())
+    cell = doc["modules"]["ram"]["cells"]["mem"]
+    for key, value in (("WR_PORTS", "10"), ("INIT", "0101"), ("WR_CLK_ENABLE", "0"), ("RD_TRANSPARENCY_MASK", "01"), ("SIZE", format(300, "b"))):
+        bad = json.loads(json.dumps(doc))
+        bad["modules"]["ram"]["cells"]["mem"]["parameters"][key] = value
+        with pytest.raises(ValueError):
+            importers.load_yosys(json.dumps(bad))
+    assert cell["parameters"]["WR_PORTS"] == "1"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [1, 0])
+def test_mem_v2_on_gpu(resident):
+    from digilogic_b200 import LogicState, SimulatorBuilder
+
+    def make(c):
+        s = c.emit(SimulatorBuilder()).build()
+        s.set_option(s.OPT_RESIDENT_KERNEL, resident)
+        return s
+
+    def get(s, n):
+        st = s.get_wire_state(n)
+        return (st.plane0, st.plane1)
+
+    mem_check(make, lambda s, n, st: s.set_wire_drive(n, LogicState(*st)), lambda s: s.run_sim(1000), get, clocks=60)
+
+
+@pytest.mark.gpu
+def test_mem_v2_with_undefined_address_bits_gpu_equals_oracle():
+    """Every wire, including X / Z on address, enable and data bits, against the oracle."""
+    from digilogic_b200 import LogicState, SimulatorBuilder
+    circ = importers.load_yosys(mem_json())
+    ref = circ.emit(oracle.Builder()).build()
+    sim = circ.emit(SimulatorBuilder()).build()
+    n_wires = sim.info.n_wires
+
+    def drive(net, v, m=1):
+        ref.set_wire_drive(net, v, m)
+        sim.set_wire_drive(net, LogicState(v, m))
+
+    for n, v in circ.const_nets.items():
+        drive(n, v)
+    rng = np.random.default_rng(5)
+    clk = circ.inputs["clk"][0]
+    others = [n for k, nets in circ.inputs.items() if k != "clk" for n in nets]
+    for rnd in range(60):
+        for n in others:
+            drive(n, int(rng.integers(0, 2)), int(rng.random() > 0.05))
+        for level in (1, 0):
+            drive(clk, level)
+            assert int(sim.run_sim(1000)) == ref.run_sim(1000), rnd
+            for w in range(n_wires):
+                assert sim.get_wire_state(w) == LogicState(*ref.get_wire_state(w)), (rnd, level, w)
+
+
+def test_pos_and_case_equality_cells():
+    cells = {"p": {"type": "$pos", "parameters": {"A_SIGNED": "1"}, "connections": {"A": [10, 11, 12], "Y": [20, 21, 22, 23, 24]}},
+             "e": {"type": "$eqx", "parameters": {"A_SIGNED": "0", "B_SIGNED": "0"}, "connections": {"A": [10, 11, 12], "B": [13, 14, 15], "Y": [30]}},
+             "n": {"type": "$nex", "parameters": {"A_SIGNED": "0", "B_SIGNED": "0"}, "connections": {"A": [10, 11, 12], "B": [13, 14, 15], "Y": [31]}}}
+    ports = {"a": {"direction": "input", "bits": [10, 11, 12]}, "b": {"direction": "input", "bits": [13, 14, 15]},
+             "y": {"direction": "output", "bits": [20, 21, 22, 23, 24]}, "eq": {"direction": "output", "bits": [30]},
+             "ne": {"direction": "output", "bits": [31]}}
+    circ = importers.load_yosys(json.dumps({"modules": {"m": {"ports": ports, "cells": cells, "netnames": {}}}}))
+    sim = circ.emit(oracle.Builder()).build()
+    for n, v in circ.const_nets.items():
+        sim.set_wire_drive(n, v, 1)
+    for a in range(8):
+        for b in (a, (a + 3) % 8):
+            for j in range(3):
+                sim.set_wire_drive(circ.inputs["a"][j], (a >> j) & 1, 1)
+                sim.set_wire_drive(circ.inputs["b"][j], (b >> j) & 1, 1)
+            assert sim.run_sim(100) == oracle.RUN_OK
+            y = sum(sim.get_wire_state(n)[0] << j for j, n in enumerate(circ.outputs["y"]))
+            assert y == (a | (0b11000 if a & 4 else 0))                      # sign-extended
+            assert sim.get_wire_state(circ.outputs["eq"][0]) == (int(a == b), 1)
+            assert sim.get_wire_state(circ.outputs["ne"][0]) == (int(a != b), 1)
