@@ -128,6 +128,7 @@ def config4(args):
     sim = seq.emit(SimulatorBuilder()).build()
     sim.set_option(sim.OPT_RESIDENT_KERNEL, 0 if args.no_resident else 1)
     sim.set_option(sim.OPT_DEVICE_LOOP, 0 if args.host_loop else 1)
+    sim.set_option(sim.OPT_HOT_STAGING, 1 if args.hot else 0)
     sim.set_lanes(n_lanes)
     words = (n_lanes + 63) // 64
     ones, zeros = np.full(words, ALL1, np.uint64), np.zeros(words, np.uint64)
@@ -204,7 +205,7 @@ def config4(args):
                       "applications_total": apps, "seconds_in_run_sim": t_gpu, "ms_per_run_sim": 1e3 * t_gpu / runs,
                       "gate_lane_evals_per_s": seq.n_gates * n_lanes * runs / t_gpu,
                       "gate_lane_steps_per_s": seq.n_gates * n_lanes * apps / t_gpu, "mode": info.last_mode,
-                      "hazard_latches": args.hazard, "runs_ending_max_steps_reached": int(unsettled_runs),
+                      "hazard_latches": args.hazard, "hot_rows_staged": len(sim.hot_rows), "runs_ending_max_steps_reached": int(unsettled_runs),
                       "lfsr_mismatches": int(bad), "lanes_checked_vs_software_lfsr": int(len(sample_lanes)),
                       "oracle_lanes": 0 if lanes is None else n_oracle, "all_wires_equal_oracle": oracle_ok}))
     assert bad == 0 and oracle_ok in (None, True)
@@ -354,6 +355,7 @@ def main():
     ap.add_argument("--host-loop", action="store_true", help="config 4: B2_OPT_DEVICE_LOOP = 0")
     ap.add_argument("--registers", action="store_true", help="config 4 built from gsim registers instead of NAND flip-flops")
     ap.add_argument("--no-resident", action="store_true")
+    ap.add_argument("--hot", action="store_true", help="config 4: B2_OPT_HOT_STAGING = 1 (hot fan-in rows staged in shared memory instead of read from L2)")
     args = ap.parse_args()
     if args.lanes is None:
         args.lanes = {2: 1 << 20, 4: 65536, 5: 1 << 23}[args.config]

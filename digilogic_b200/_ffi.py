@@ -56,6 +56,7 @@ SIGNATURES = {
     "b2_sim_free": (None, [vp]),
     "b2_sim_get_info": (i32, [vp, C.POINTER(SimInfo)]),
     "b2_sim_get_pair_info": (i32, [vp, pu64, pu64, pu64]),
+    "b2_sim_get_hot_rows": (i32, [vp, pu32, pu32]),
     "b2_sim_plan_pairs": (i32, [vp, vp, u32, pu64]),
     "b2_wire_width": (i32, [vp, u32, pu8]),
     "b2_sim_set_device": (i32, [vp, i32]),

@@ -250,6 +250,14 @@ int b2_sim_get_pair_info(const b2_sim *s, uint64_t *launches, uint64_t *children
     return B2_OK;
 }
 
+int b2_sim_get_hot_rows(b2_sim *s, uint32_t out_rows[4], uint32_t *out_n) {
+    if (!s || !out_rows || !out_n) return B2_ERR_NULL;
+    GUARD_BEGIN
+    s->e->hot_rows(out_rows, out_n);
+    return B2_OK;
+    GUARD_END(B2_ERR_OUT_OF_MEMORY)
+}
+
 int b2_sim_plan_pairs(const b2_sim *s, const uint32_t *keep_wires, uint32_t n_keep, uint64_t out[6]) {
     if (!s || !out || (n_keep && !keep_wires)) return B2_ERR_NULL;
     GUARD_BEGIN
@@ -301,6 +309,7 @@ int b2_sim_set_option(b2_sim *s, int option, int64_t value) {
         case B2_OPT_PERIOD2_SKIP: s->e->set_period2_skip(value != 0); return B2_OK;
         case B2_OPT_PDL: s->e->set_pdl((uint32_t)value); return B2_OK;
         case B2_OPT_PAIR_FUSION: s->e->set_pair_fusion(value != 0); return B2_OK;
+        case B2_OPT_HOT_STAGING: s->e->set_hot_staging(value != 0); return B2_OK;
         case B2_OPT_CONFLICT_NEEDS_DISAGREE: return s->e->set_lenient_conflicts(value != 0) ? B2_OK : B2_ERR_INVALID_ARG;
         default: return B2_ERR_INVALID_ARG;
     }

@@ -91,7 +91,60 @@ struct Eval2Args {
     // device-side loop: set to 1 when a row written by this application differs from what the buffer held (the state two
     // applications ago) — the period-2 detector of k_unit_delay_loop; nullptr elsewhere
     uint32_t *p2diff = nullptr;
+    // k_eval_list: rows read by very many gates (a clock, a reset), staged once per CTA in shared memory (hot_n = 0: none)
+    uint32_t hot_n = 0, hot_row[4] = {0, 0, 0, 0};
 };
+
+// ---- hot fan-in staging (k_eval_list).  A row with a fan-out in the thousands is re-read from L2 by every listed gate that
+// has it as an operand.  The buffer an application reads is constant for the whole launch, so each CTA of the persistent grid
+// copies its column block of the (at most four) hottest rows into shared memory once — one bulk asynchronous copy
+// (cp.async.bulk, completion on an mbarrier) per row and plane, issued by one thread — and the gate loop takes those operands
+// from there.
+static constexpr uint32_t kHotRows = 4, kHotPairs = 256, kHotMinFanout = 100;
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stage_hot_rows(const Eval2Args &a, ulonglong2 *s_hot, uint64_t *s_bar, uint32_t pb) {
+    const uint32_t tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const uint32_t p0 = pb * blockDim.x, np = min(blockDim.x, a.pairs - p0), bytes = np * 16;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(s_bar)), "r"(bytes * 2 * a.hot_n) : "memory");
+        for (uint32_t h = 0; h < a.hot_n; h++)
+            for (uint32_t plane = 0; plane < 2; plane++) {
+                const uint64_t *src = (plane ? a.in_vld : a.in_val) + (size_t)a.hot_row[h] * a.stride + (size_t)p0 * 2;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(s_hot + (plane * kHotRows + h) * kHotPairs)),
+                             "l"(src), "r"(bytes), "r"(smem_u32(s_bar))
+                             : "memory");
+            }
+    }
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(s_bar)) : "memory");
+}
+// staged slot of operand `row` of a listed gate, or kHotRows if it is not one of the hot rows
+__device__ __forceinline__ uint32_t hot_slot(const Eval2Args &a, uint32_t row) {
+    uint32_t s = kHotRows;
+#pragma unroll
+    for (uint32_t h = 0; h < kHotRows; h++)
+        if (h < a.hot_n && row == a.hot_row[h]) s = h;
+    return s;
+}
+// both planes of an operand: a predicated-off global load (no branch, so the loads of all operands of an iteration are in flight
+// together) patched from the staged copy when the row is hot
+__device__ __forceinline__ void ld_operand(const Eval2Args &a, const ulonglong2 *s_hot, uint32_t row, size_t off, ulonglong2 &v, ulonglong2 &m) {
+    const uint32_t s = s_hot ? hot_slot(a, row) : kHotRows;
+    const bool staged = s < kHotRows;
+    asm volatile("{ .reg .pred q; setp.eq.u32 q, %3, 0; @q ld.volatile.global.v2.u64 {%0,%1}, [%2]; }" : "=l"(v.x), "=l"(v.y) : "l"(a.in_val + off), "r"((uint32_t)staged) : "memory");
+    asm volatile("{ .reg .pred q; setp.eq.u32 q, %3, 0; @q ld.volatile.global.v2.u64 {%0,%1}, [%2]; }" : "=l"(m.x), "=l"(m.y) : "l"(a.in_vld + off), "r"((uint32_t)staged) : "memory");
+    if (staged) {
+        v = s_hot[s * kHotPairs + threadIdx.x];
+        m = s_hot[(kHotRows + s) * kHotPairs + threadIdx.x];
+    }
+}
 
 // Changed-row frontier write: with a whole warp on one gate, one ballot and one byte store.
 __device__ __forceinline__ void mark_changed(uint8_t *chg, uint32_t row, bool changed) {
@@ -348,7 +401,8 @@ __global__ void __launch_bounds__(256) k_copy_list(const uint32_t *rows, const u
 // Gates of `list[0 .. *count)` (one/two-input, or three-input with NIN = 3): B[row] = F(A), change detection
 // against A[row], changed-row flag.  Persistent: the grid is sized for the machine, CTAs stride over the list.
 template <int NIN>
-__device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *list, const uint32_t *count, uint32_t bid, uint32_t nblk) {
+__device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *list, const uint32_t *count, uint32_t bid, uint32_t nblk,
+                                               const ulonglong2 *s_hot = nullptr) {
     constexpr int U = 2;
     const uint32_t n = *count;
     const uint32_t pb = bid % a.pair_blocks, gbi = bid / a.pair_blocks, gbs = nblk / a.pair_blocks;
@@ -382,15 +436,9 @@ __device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const size_t r0 = (size_t)f0[u] * a.stride + col, r1 = (size_t)f1[u] * a.stride + col, o = (size_t)orow[u] * a.stride + col;
-            av[u] = ld_row(a.in_val + r0);
-            bv[u] = ld_row(a.in_val + r1);
-            am[u] = ld_row(a.in_vld + r0);
-            bm[u] = ld_row(a.in_vld + r1);
-            if (NIN == 3) {
-                const size_t r2 = (size_t)f2[u] * a.stride + col;
-                cv[u] = ld_row(a.in_val + r2);
-                cm[u] = ld_row(a.in_vld + r2);
-            }
+            ld_operand(a, s_hot, f0[u], r0, av[u], am[u]);
+            ld_operand(a, s_hot, f1[u], r1, bv[u], bm[u]);
+            if (NIN == 3) ld_operand(a, s_hot, f2[u], (size_t)f2[u] * a.stride + col, cv[u], cm[u]);
             ov[u] = ld_row(a.in_val + o);
             om[u] = ld_row(a.in_vld + o);
         }
@@ -442,7 +490,11 @@ __device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *
 
 template <int NIN>
 __global__ void __launch_bounds__(256, NIN == 3 ? 2 : 3) k_eval_list(const Eval2Args a, const uint4 *list, const uint32_t *count) {
-    eval_list_body<NIN>(a, list, count, blockIdx.x, gridDim.x);
+    __shared__ __align__(128) ulonglong2 s_hot[2 * kHotRows * kHotPairs];  // [plane][hot row][pair of this CTA's column block]
+    __shared__ __align__(8) uint64_t s_bar;
+    const bool hot = a.hot_n != 0 && *count != 0;  // uniform over the grid; an idle launch stages nothing
+    if (hot) stage_hot_rows(a, s_hot, &s_bar, blockIdx.x % a.pair_blocks);
+    eval_list_body<NIN>(a, list, count, blockIdx.x, gridDim.x, hot ? s_hot : nullptr);
 }
 
 template <bool JACOBI>
@@ -1417,6 +1469,7 @@ void Engine::copy_options_from(const Engine &o) {
     opt_pdl_ = o.opt_pdl_;
     opt_discard_ = o.opt_discard_;
     opt_pair_ = o.opt_pair_;
+    opt_hot_ = o.opt_hot_;
     disc_short_ = o.disc_short_;
     disc_never_ = o.disc_never_;
     opt_flags_ = o.opt_flags_;
@@ -2195,6 +2248,38 @@ int Engine::ensure_pair_plan() {
     return B2_OK;
 }
 
+// The (at most four) rows with the largest fan-out among the fast gates, if a hundred gates or more read them: staged in
+// shared memory by k_eval_list.
+void Engine::find_hot_rows() {
+    if (hot_ready_) return;
+    hot_ready_ = true;
+    n_hot_ = 0;
+    std::vector<uint32_t> fanout(net_.n_rows, 0);
+    for (uint32_t g = 0; g < net_.n_fast(); g++) {
+        const uint32_t f[3] = {net_.fan0[g], net_.fan1[g], net_.fan2[g]};
+        fanout[f[0]]++;
+        if (f[1] != f[0]) fanout[f[1]]++;
+        if (f[2] != f[0] && f[2] != f[1]) fanout[f[2]]++;
+    }
+    for (uint32_t h = 0; h < kHotRows; h++) {
+        uint32_t best = 0, best_n = kHotMinFanout - 1;
+        for (uint32_t r = 0; r < net_.n_rows; r++)
+            if (fanout[r] > best_n) {
+                best = r;
+                best_n = fanout[r];
+            }
+        if (best_n < kHotMinFanout) break;
+        hot_rows_[n_hot_++] = best;
+        fanout[best] = 0;
+    }
+}
+
+void Engine::hot_rows(uint32_t *rows, uint32_t *n) {
+    find_hot_rows();
+    *n = opt_hot_ ? n_hot_ : 0;
+    for (uint32_t h = 0; h < *n; h++) rows[h] = hot_rows_[h];
+}
+
 void Engine::pair_info(uint64_t *launches, uint64_t *children, uint64_t *unstored) const {
     const bool on = pair_ && last_mode_ == 1 && last_pair_;
     if (launches) *launches = on ? pair_->launch_tab.size() / 4 : 0;
@@ -2585,10 +2670,16 @@ int Engine::run_jacobi(uint64_t max_steps) {
             // persistent grids: exactly as many CTAs as are resident at once (a partial second wave would double the time)
             auto slots = [&](int ctas_per_sm) { return std::max<uint32_t>(1, (uint32_t)(sm_count_ * ctas_per_sm) / sh.pair_blocks); };
             uint32_t gbs_max = slots(occ_list_[0]);
+            find_hot_rows();
+            auto set_hot = [&](Eval2Args &a) {
+                a.hot_n = opt_hot_ ? n_hot_ : 0;
+                for (uint32_t h = 0; h < a.hot_n; h++) a.hot_row[h] = hot_rows_[h];
+            };
             if (net_.n_g2()) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, 0, net_.n_g2(), net_.n_src, stride_, pairs,
                             sh.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
                 a.sem = net_.sem_flags;
+                set_hot(a);
                 const uint32_t gbs = std::min<uint32_t>((net_.n_g2() + per - 1) / per, gbs_max);
                 k_eval_list<2><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[0], act_counts);
                 LAUNCHED();
@@ -2598,6 +2689,7 @@ int Engine::run_jacobi(uint64_t max_steps) {
                 Eval2Args a{d_fan0_, d_fan1_, d_fan2_, d_kind2_, AV, AM, BV, BM, d_changed_, net_.n_g2(), net_.n_fast(), net_.n_src, stride_,
                             pairs, sh.pair_blocks, nullptr, nullptr, chg_cur, nullptr};
                 a.sem = net_.sem_flags;
+                set_hot(a);
                 const uint32_t gbs = std::min<uint32_t>((net_.n_g3() + per - 1) / per, gbs_max);
                 k_eval_list<3><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[1], act_counts + 1);
                 LAUNCHED();

@@ -128,6 +128,9 @@ class Engine {
     void set_pdl(uint32_t mode) { opt_pdl_ = mode <= 2 ? mode : 0; level_graph_key_ = 0; }
     // Level-pair fusion (pair.cuh; default off): acts only on levelised runs with set_discard on, for netlists of one/two-input gates.
     void set_pair_fusion(bool on) { opt_pair_ = on; level_graph_key_ = 0; }
+    // Unit-delay work-list kernels keep the (at most four) rows with the largest fan-out (>= 100 gates) in shared memory.
+    void set_hot_staging(bool on) { opt_hot_ = on; }
+    void hot_rows(uint32_t *rows, uint32_t *n);  // store rows staged (n = 0: none qualifies, or the option is off)
     // launches of the last levelised pass / gates evaluated as children / parent rows never stored (0 when the plan is off)
     void pair_info(uint64_t *launches, uint64_t *children, uint64_t *unstored) const;
     // SURVEY.md A.6-2 alternative (agreeing valid drivers do not conflict); refused for netlists with two firm drivers on a net
@@ -258,6 +261,10 @@ class Engine {
     std::vector<RowRange> disc_short_, disc_never_;  // per level: rows of the one/two-input class that may be dropped
     bool opt_l2_hints_ = false;
     bool opt_pair_ = false;
+    bool opt_hot_ = false;  // k_eval_list stages the hottest fan-in rows in shared memory (measured: L2 serves them as well)
+    bool hot_ready_ = false;
+    uint32_t n_hot_ = 0, hot_rows_[4] = {0, 0, 0, 0};
+    void find_hot_rows();
     std::vector<uint32_t> keep_rows_;      // sorted rows kept by set_discard
     std::shared_ptr<PairPlanDev> pair_;    // null: not built yet, or the netlist is not eligible (pair_tried_)
     bool pair_tried_ = false, last_pair_ = false;

@@ -337,6 +337,13 @@ class Simulator:
         _check(self._lib.b2_sim_get_pair_info(self._h, C.byref(a), C.byref(b), C.byref(c)), "get_pair_info")
         return a.value, b.value, c.value
 
+    @property
+    def hot_rows(self) -> list:
+        """Store rows the unit-delay work-list kernel stages in shared memory (b2_sim_get_hot_rows)."""
+        rows, n = (C.c_uint32 * 4)(), C.c_uint32()
+        _check(self._lib.b2_sim_get_hot_rows(self._h, rows, C.byref(n)), "get_hot_rows")
+        return [int(rows[i]) for i in range(n.value)]
+
     def plan_pairs(self, keep_wires) -> dict:
         """The level-pair plan for `keep_wires` as designated outputs, computed on the host (b2_sim_plan_pairs)."""
         keep = np.ascontiguousarray(keep_wires, np.uint32)
@@ -362,6 +369,7 @@ class Simulator:
     OPT_PERIOD2_SKIP = 10
     OPT_PDL = 11
     OPT_PAIR_FUSION = 12
+    OPT_HOT_STAGING = 13
 
     def set_option(self, option: int, value: int):
         _check(self._lib.b2_sim_set_option(self._h, option, value), "set_option")

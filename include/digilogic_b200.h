@@ -205,6 +205,8 @@ int b2_sim_get_pair_info(const b2_sim *s, uint64_t *launches, uint64_t *children
    needed): out[0] launches, out[1] items, out[2] gates evaluated as the second gate of an item, out[3] rows never stored,
    out[4] rows dropped from L2 by a later launch, out[5] rows dropped right after their store.  B2_ERR_INVALID_ARG when the
    netlist is not eligible (feedback, tri-state nets, registers, gates with three or more inputs). */
+/* Store rows the unit-delay work-list kernel stages in shared memory (B2_OPT_HOT_STAGING): out_rows[0 .. *out_n), at most 4. */
+int b2_sim_get_hot_rows(b2_sim *s, uint32_t out_rows[4], uint32_t *out_n);
 int b2_sim_plan_pairs(const b2_sim *s, const uint32_t *keep_wires, uint32_t n_keep, uint64_t out[6]);
 
 /* Simulator::get_wire_width(wire)  (lib.rs:228) */
@@ -249,6 +251,10 @@ enum b2_option {
                                   are evaluated by one thread — a launch holds items of one gate whose fan-ins are older than the launch
                                   plus up to two gates reading its output, which they get in registers; a row read only inside its item
                                   is never stored.  Half the launches, 17 % less traffic between the SMs and L2; kept rows are bit-identical. */
+    B2_OPT_HOT_STAGING = 13,   /* default 0 (measured on config 4: 7 % fewer L2 reads, 2-3 % slower — the 126 MB L2 serves such rows as
+                                  well).  Unit-delay work-list kernel (k_eval_list): the rows with the largest fan-out — at most four,
+                                  each read by a hundred gates or more: a clock, a reset — are copied once per CTA into shared memory
+                                  (cp.async.bulk + mbarrier) and the listed gates take those operands from there instead of from L2. */
     B2_OPT_PERIOD2_SKIP = 10,  /* default 1.  Unit-delay loops (device-side loop, resident kernel) detect an exact period-2 oscillation
                                   — every row an application writes equals the row two applications earlier — and jump ahead by an
                                   even number of applications: the state, lane results and step accounting are those of walking
