@@ -63,8 +63,13 @@ def auto_batch_shape(sim: Simulator, n_words: int) -> tuple[int, int]:
     of one tile's level sweep are filled by the others — and a tile small enough that TWO levels of all three slots
     (gates per level x 16 B x tile_words x 3 x 2) stay in L2: the next level reads the rows a level wrote from L2, and rows
     that are dead after that are dropped from L2 before they are written back (B2_BATCH_OPT_DISCARD).  Config 3 (5000 gates
-    per level) -> 128 x 3 (measured optimum, profiles/README.md), config 5 (50 000 per level) -> 32 x 3."""
-    return auto_tile_words(sim, n_words, l2_level_bytes=10 << 20), 3
+    per level) -> 128 x 3 (measured optimum, profiles/README.md).  Where the tile is already at its floor of 32 words and a level
+    still exceeds that budget (config 5: 50 000 gates per level = 25.6 MB), two slots do better than three (865 vs 892 ms per
+    2^20 lanes of config 5): -> 32 x 2."""
+    tile = auto_tile_words(sim, n_words, l2_level_bytes=10 << 20)
+    info = sim.info
+    per_level = (info.n_gates2 + info.n_gates_wide) / max(info.depth, 1)
+    return tile, (2 if per_level * 16 * tile > (16 << 20) else 3)
 
 
 class _DeviceArray:
