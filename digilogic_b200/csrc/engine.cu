@@ -164,7 +164,7 @@ __device__ __forceinline__ void mark_changed(uint8_t *chg, uint32_t row, bool ch
 // full two-plane path; the result is bit-identical either way.
 // NIN = 3: three-input gates, ((a op b) op c) with one inversion at the end for NAND/NOR/XNOR.
 template <int U, bool JACOBI, bool KV, int NIN = 2>
-__global__ void __launch_bounds__(256, JACOBI ? 2 : ((U == 2 && NIN == 2 && !KV) ? 5 : 3)) k_eval2(const Eval2Args a) {
+__global__ void __launch_bounds__(256, JACOBI ? 2 : ((U == 2 && NIN == 2) ? (KV ? 4 : 5) : 3)) k_eval2(const Eval2Args a) {
     const uint32_t pb = blockIdx.x % a.pair_blocks, gb = blockIdx.x / a.pair_blocks;
     const uint32_t pair = pb * blockDim.x + threadIdx.x;
     // Programmatic dependent launch (levelised pass, a.pdl): the next level's kernel of this stream may be launched while
@@ -251,16 +251,16 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : ((U == 2 && NIN == 2 && !KV)
             om[u] = ld_stream_unless(a.in_vld + o, skip);
         } else {
             if (KV) {
-                av[u] = ld_stream(a.in_val + r0);
-                bv[u] = ld_stream(a.in_val + r1);
+                av[u] = ld_dep(a.in_val + r0);
+                bv[u] = ld_dep(a.in_val + r1);
             } else {
                 // (ld_dep: with programmatic dependent launch the rows are written while this grid is resident — not .nc data)
                 av[u] = ld_dep_hint(a.in_val + r0, far[u] & 1, pol_first);
                 bv[u] = ld_dep_hint(a.in_val + r1, far[u] & 2, pol_first);
             }
             if (KV) {
-                am[u] = ld_stream_unless(a.in_vld + r0, k0[u]);
-                bm[u] = ld_stream_unless(a.in_vld + r1, k1[u]);
+                am[u] = ld_dep_unless(a.in_vld + r0, k0[u]);
+                bm[u] = ld_dep_unless(a.in_vld + r1, k1[u]);
             } else {
                 am[u] = ld_dep_hint(a.in_vld + r0, far[u] & 1, pol_first);
                 bm[u] = ld_dep_hint(a.in_vld + r1, far[u] & 2, pol_first);
@@ -291,9 +291,9 @@ __global__ void __launch_bounds__(256, JACOBI ? 2 : ((U == 2 && NIN == 2 && !KV)
             const bool okv = KV && k0[u] && k1[u] && k2[u];
             st_pair(a.out_val + o, rv);
             if (!okv) st_pair(a.out_vld + o, rm);
-            if (!JACOBI && !KV && (pair & 7) == 0 && orow[u] - a.row_base >= a.now_begin && orow[u] - a.row_base < a.now_end) {
+            if (!JACOBI && (pair & 7) == 0 && orow[u] - a.row_base >= a.now_begin && orow[u] - a.row_base < a.now_end) {
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_val + o) : "memory");
-                asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_vld + o) : "memory");
+                if (!okv) asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.out_vld + o) : "memory");
             }
             if (KV && !allv && pb == 0 && threadIdx.x == 0) a.kv[orow[u]] = okv ? 1 : 0;
             if (JACOBI) {
@@ -2373,7 +2373,7 @@ int Engine::run_levelised(bool async) {
                             sh.pair_blocks, d_kv_, nullptr, nullptr, d_all_valid_};
                 a.sem = net_.sem_flags;
                 a.far = opt_l2_hints_ ? d_far2_ : nullptr;
-                if (opt_discard_ && !kv && stride_ % 16 == 0) {
+                if (opt_discard_ && stride_ % 16 == 0) {
                     const size_t li = (size_t)(&lv - net_.levels.data());
                     if (li < disc_never_.size() && stride_ >= 16) {  // rows of this level that nobody reads (gate indices)
                         a.now_begin = disc_never_[li].begin - net_.n_src;
@@ -2391,7 +2391,7 @@ int Engine::run_levelised(bool async) {
                 const uint32_t U = (opt_u_ ? opt_u_ : (ctas4 >= 148 * 3 * 4 ? 4u : 2u));
                 const uint32_t per = sh.block.y * U;
                 const uint32_t gb = (n_g + per - 1) / per;
-                a.pdl = kv ? 0 : opt_pdl_;
+                a.pdl = opt_pdl_;
                 auto launch = [&](void (*kern)(const Eval2Args)) {
                     if (!a.pdl) {
                         kern<<<sh.pair_blocks * gb, sh.block, 0, ST>>>(a);
