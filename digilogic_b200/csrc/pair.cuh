@@ -6,15 +6,17 @@
 // plus up to two gates that read the parent's output and, apart from it, only rows of earlier launches (its children).
 // The parent's value reaches its children in registers — no load — and a parent row that nobody else reads and that is
 // not a designated output is not stored at all.  Everything else is as in k_eval2: one thread per 128-bit pair of
-// lane-words, all plane loads of an item issued before the first use, dead rows dropped from L2 (discard.global.L2)
-// once their last reader has run, consecutive launches chained by programmatic dependent launch.
+// lane-words, all plane loads of an item issued before the first use, rows that die within a launch of being written dropped
+// from L2 (discard.global.L2) once their last reader has run, consecutive launches chained by programmatic dependent launch
+// (row loads behind griddepcontrol.wait: plain loads, device_ops.cuh ld_dep).  Measured on config 3: half the launches, 17 % fewer
+// sectors between the SMs and L2, the same time as the per-level kernels — hence an option, default off.
 //
 // plan_pairs() is the host side: a greedy as-soon-as-possible assignment of every gate to (launch, parent | child) in
 // level order.  A gate that cannot be a child (two fan-ins written by the launch it would join, a parent that already has two
 // children, a parent that is itself a child) becomes a parent of the next launch, so the plan is valid for any acyclic
 // netlist of one/two-input gates; config 3 (depth 200) becomes 100 launches plus a few for the gates pushed back.
 //
-// The results are bit-identical to the per-level kernels on every row that is kept (tests/test_gpu_batch.py); rows that
+// The results are bit-identical to the per-level kernels on every row that is kept (tests/test_gpu_pair.py); rows that
 // are not kept are undefined after a run, as with B2_BATCH_OPT_DISCARD alone.
 #pragma once
 #include <algorithm>

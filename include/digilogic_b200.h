@@ -240,7 +240,7 @@ enum b2_option {
                                   High-Z" (SURVEY.md A.6-2); 1 selects the alternative reading in which two valid operands that
                                   agree do not conflict — the oracle's `conflict_needs_disagree` switch, for the day a run of real
                                   gsim decides.  Refused (InvalidArgument) for a netlist with two plain gates on one net. */
-    B2_OPT_L2_HINTS = 9,       /* default 1.  Levelised pass: fan-in rows produced more than one level below the reading gate are
+    B2_OPT_L2_HINTS = 9,       /* default 0 (measured: no gain).  Levelised pass: fan-in rows produced more than one level below the reading gate are
                                   loaded with an L2 evict-first hint (createpolicy + ld.L2::cache_hint), so that these one-off reads
                                   do not displace the rows the previous level has just written and the next kernel re-reads. */
     B2_OPT_PDL = 11,           /* Levelised pass: consecutive level kernels of a simulator are launched with programmatic stream
