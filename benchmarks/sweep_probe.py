@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=1 << 22)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0xD1610003)
+    ap.add_argument("--eval-unroll", type=int, default=0, help="B2_OPT_EVAL_UNROLL on the replicas (0 = automatic, 2, 4)")
     ap.add_argument("--elision", type=int, default=0, help="B2_OPT_VALID_ELISION on the replicas")
     ap.add_argument("--shapes", default="64x4x1x4x0,64x8x1x4x0,128x4x1x4x0,128x2x1x4x0,256x2x1x4x0,256x3x1x4x0,32x8x1x4x0")
     args = ap.parse_args()
@@ -52,6 +53,7 @@ def main():
         sim.set_option(sim.OPT_PDL, pdl)
         sim.set_option(sim.OPT_L2_HINTS, hints)
         sim.set_option(sim.OPT_VALID_ELISION, args.elision)
+        sim.set_option(sim.OPT_EVAL_UNROLL, args.eval_unroll)
         sim.set_option(sim.OPT_PAIR_FUSION, f[10] if len(f) > 10 else 0)
         b = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=0, stream=stream.cuda_stream)
         b.set_option(Batch.OPT_TASK_ITERS, iters)
