@@ -12,8 +12,8 @@ and 2 — SURVEY.md §8 row f1.
   set: `$xnor`, `$mux`, `$pmux`, `$reduce_and/or/xor/xnor/bool`, `$logic_not/and/or`, `$tribuf`, `$dff`,
   `$dffe`, `$sdff`, `$sdffe`, `$sdffce`, `$dlatch`, and — through gsim's word-level components, on wide wires that `emit()`
   merges from and slices back into the 1-bit nets — `$add`, `$sub`, `$neg`, `$mul`, `$lt/$le/$eq/$ne/$ge/$gt`,
-  `$shl/$sshl/$shr/$sshr`, `$pos`, `$eqx/$nex`; `$mem_v2` is lowered onto registers, address decoders and multiplexer trees
-  (`_lower_mem_v2`); constant bits "0"/"1" become two extra input nets (`const_nets`) the caller drives.
+  `$shl/$sshl/$shr/$sshr`, `$pos`, `$eqx/$nex`, `$sr`; `$mem_v2` — or the `$memrd_v2` / `$memwr_v2` port cells of a memory,
+  collected first — is lowered onto registers, address decoders and multiplexer trees (`_lower_mem_v2`); constant bits "0"/"1" become two extra input nets (`const_nets`) the caller drives.
 
 Both produce an `ImportedCircuit`, whose `emit()` issues the same calls the GUI client sends
 (crates/digilogic_netcode/src/client.rs:288-427): one 1-bit net per net, then one gate per
@@ -241,6 +241,56 @@ def adder_dig(nbits: int = 4) -> str:
 
 # ------------------------------------------------------------------------------ Yosys JSON
 
+def _collect_memory_ports(mod) -> dict:
+    """The cells of a module with every group of `$memrd_v2` / `$memwr_v2` port cells of one memory (what Yosys emits before its
+    memory_collect pass; crates/digilogic_serde/src/yosys.rs:204-206) replaced by the `$mem_v2` cell memory_collect would make
+    of them; size and offset come from the module's `memories` section.  `$meminit_v2` (initial contents) is refused like a
+    defined INIT of `$mem_v2`."""
+    cells = mod.get("cells", {})
+    if not any(c["type"] in ("$memrd_v2", "$memwr_v2", "$meminit_v2") for c in cells.values()):
+        return cells
+
+    def num(v):
+        return int(v, 2) if isinstance(v, str) else int(v)
+
+    out, groups = {}, {}
+    for name, c in cells.items():
+        if c["type"] == "$meminit_v2":
+            raise ValueError(f"$meminit_v2 {name}: initial contents are not supported (registers start Undefined)")
+        if c["type"] in ("$memrd_v2", "$memwr_v2"):
+            memid = c["parameters"]["MEMID"]
+            groups.setdefault(memid, {"rd": [], "wr": []})["rd" if c["type"] == "$memrd_v2" else "wr"].append((name, c))
+        else:
+            out[name] = c
+    for memid, g in groups.items():
+        info = mod.get("memories", {}).get(memid) or mod.get("memories", {}).get(memid.lstrip("\\"))
+        if info is None:
+            raise ValueError(f"memory {memid!r}: no entry in the module's `memories` section")
+        ports = g["rd"] + g["wr"]
+        abits, width = num(ports[0][1]["parameters"]["ABITS"]), int(info["width"])
+        if any(num(c["parameters"]["ABITS"]) != abits or num(c["parameters"]["WIDTH"]) != width for _, c in ports):
+            raise ValueError(f"memory {memid!r}: ports of differing address or data width (wide ports) are not supported")
+
+        def bits(key, which, default="0"):
+            return "".join(str(num(c["parameters"].get(key, default)) & 1) for _, c in reversed(g[which])) or "0"
+
+        params = {"MEMID": memid, "SIZE": format(int(info["size"]), "b"), "OFFSET": format(int(info.get("start_offset", 0)), "b"),
+                  "ABITS": format(abits, "b"), "WIDTH": format(width, "b"), "INIT": "x",
+                  "RD_PORTS": format(len(g["rd"]), "b"), "WR_PORTS": format(len(g["wr"]), "b"),
+                  "RD_CLK_ENABLE": bits("CLK_ENABLE", "rd"), "RD_CLK_POLARITY": bits("CLK_POLARITY", "rd", "1"),
+                  "WR_CLK_ENABLE": bits("CLK_ENABLE", "wr"), "WR_CLK_POLARITY": bits("CLK_POLARITY", "wr", "1"),
+                  "RD_TRANSPARENCY_MASK": "1" if any(num(c["parameters"].get("TRANSPARENCY_MASK", 0)) for _, c in g["rd"]) else "0",
+                  "RD_COLLISION_X_MASK": "1" if any(num(c["parameters"].get("COLLISION_X_MASK", 0)) for _, c in g["rd"]) else "0"}
+        conn = {"RD_CLK": [c["connections"]["CLK"][0] for _, c in g["rd"]], "RD_EN": [c["connections"]["EN"][0] for _, c in g["rd"]],
+                "RD_ADDR": [b for _, c in g["rd"] for b in c["connections"]["ADDR"]],
+                "RD_DATA": [b for _, c in g["rd"] for b in c["connections"]["DATA"]],
+                "WR_CLK": [c["connections"]["CLK"][0] for _, c in g["wr"]], "WR_EN": [b for _, c in g["wr"] for b in c["connections"]["EN"]],
+                "WR_ADDR": [b for _, c in g["wr"] for b in c["connections"]["ADDR"]],
+                "WR_DATA": [b for _, c in g["wr"] for b in c["connections"]["DATA"]]}
+        out[f"$mem_v2:{memid}"] = {"type": "$mem_v2", "parameters": params, "connections": conn}
+    return out
+
+
 def _lower_mem_v2(circ, cname, conn, params, net, tmp, flag, param_bits):
     """Yosys `$mem_v2` (crates/digilogic_serde/src/yosys.rs:207, `MemV2 => todo!()`) lowered onto registers, multiplexers and
     gates: one register per stored bit (so a word is Undefined until it has been written, like gsim's register), per write port
@@ -367,7 +417,8 @@ def load_yosys(text: str, module: str | None = None) -> ImportedCircuit:
     def tmp():
         return net(("tmp", len(net_of)))
 
-    for cname, cell in mod.get("cells", {}).items():
+    cells = _collect_memory_ports(mod)
+    for cname, cell in cells.items():
         ctype = cell["type"]
         conn = cell["connections"]
         params = cell.get("parameters", {})
@@ -481,6 +532,11 @@ def load_yosys(text: str, module: str | None = None) -> ImportedCircuit:
                 raise ValueError(f"{ctype} with a shift amount wider than 8 bits ({cname})")
             op = "shl" if ctype in ("$shl", "$sshl") else ("ashr" if ctype == "$sshr" and flag("A_SIGNED") else "lshr")
             circ.wide.append((op, [extend(conn["A"], "A_SIGNED", width), [net(b) for b in conn["B"]]], [net(b) for b in conn["Y"]]))
+        elif ctype == "$sr":       # set / reset latch, reset wins: Q = CLR ? 0 : (SET ? 1 : Q)
+            for j in range(len(conn["Q"])):
+                q, hold = net(conn["Q"][j]), tmp()
+                circ.gates.append((MUX, [positive(conn["SET"][j], "SET_POLARITY"), q, net("1")], hold))
+                circ.gates.append((MUX, [positive(conn["CLR"][j], "CLR_POLARITY"), hold, net("0")], q))
         elif ctype == "$pos":      # Y = A, extended to the width of Y
             for j, src in enumerate(extend(conn["A"], "A_SIGNED", len(conn["Y"]))):
                 circ.gates.append((OR, [src, src], net(conn["Y"][j])))

@@ -426,3 +426,50 @@ def test_pos_and_case_equality_cells():
             assert y == (a | (0b11000 if a & 4 else 0))                      # sign-extended
             assert sim.get_wire_state(circ.outputs["eq"][0]) == (int(a == b), 1)
             assert sim.get_wire_state(circ.outputs["ne"][0]) == (int(a != b), 1)
+
+
+def test_memory_port_cells_give_the_same_circuit_as_mem_v2():
+    """`$memrd_v2` / `$memwr_v2` (the form before Yosys' memory_collect) are collected into the `$mem_v2` they stand for."""
+    doc = json.loads(mem_json())
+    mod = doc["modules"]["ram"]
+    m = mod["cells"].pop("mem")
+    p, c = m["parameters"], m["connections"]
+    ab, w = MEM["abits"], MEM["width"]
+    mod["memories"] = {"\\m": {"width": w, "start_offset": MEM["offset"], "size": MEM["size"]}}
+    for r in range(2):
+        mod["cells"][f"rd{r}"] = {"type": "$memrd_v2", "parameters": {"MEMID": "\\m", "ABITS": p["ABITS"], "WIDTH": p["WIDTH"],
+                                  "CLK_ENABLE": str(r), "CLK_POLARITY": "1", "TRANSPARENCY_MASK": "0", "COLLISION_X_MASK": "0"},
+                                  "connections": {"CLK": [c["RD_CLK"][r]], "EN": [c["RD_EN"][r]], "ARST": ["0"], "SRST": ["0"],
+                                                  "ADDR": c["RD_ADDR"][r * ab:(r + 1) * ab], "DATA": c["RD_DATA"][r * w:(r + 1) * w]}}
+    mod["cells"]["wr0"] = {"type": "$memwr_v2", "parameters": {"MEMID": "\\m", "ABITS": p["ABITS"], "WIDTH": p["WIDTH"], "CLK_ENABLE": "1",
+                           "CLK_POLARITY": "1", "PORTID": "0", "PRIORITY_MASK": "0"},
+                           "connections": {"CLK": c["WR_CLK"], "EN": c["WR_EN"], "ADDR": c["WR_ADDR"], "DATA": c["WR_DATA"]}}
+    split = importers.load_yosys(json.dumps(doc))
+    whole = importers.load_yosys(mem_json())
+    assert split.gates == whole.gates and split.inputs == whole.inputs and split.outputs == whole.outputs
+    mod["cells"]["init"] = {"type": "$meminit_v2", "parameters": {"MEMID": "\\m"}, "connections": {}}
+    with pytest.raises(ValueError):
+        importers.load_yosys(json.dumps(doc))
+
+
+def test_sr_cell_on_the_oracle():
+    cells = {"l": {"type": "$sr", "parameters": {"SET_POLARITY": "1", "CLR_POLARITY": "0", "WIDTH": "10"},
+                   "connections": {"SET": [10, 11], "CLR": [12, 13], "Q": [20, 21]}}}
+    ports = {"s": {"direction": "input", "bits": [10, 11]}, "rn": {"direction": "input", "bits": [12, 13]}, "q": {"direction": "output", "bits": [20, 21]}}
+    circ = importers.load_yosys(json.dumps({"modules": {"m": {"ports": ports, "cells": cells, "netnames": {}}}}))
+    sim = circ.emit(oracle.Builder()).build()
+    for n, v in circ.const_nets.items():
+        sim.set_wire_drive(n, v, 1)
+
+    def step(s, rn):
+        for j in range(2):
+            sim.set_wire_drive(circ.inputs["s"][j], (s >> j) & 1, 1)
+            sim.set_wire_drive(circ.inputs["rn"][j], (rn >> j) & 1, 1)
+        assert sim.run_sim(100) == oracle.RUN_OK
+        return [sim.get_wire_state(n) for n in circ.outputs["q"]]
+
+    assert step(0b00, 0b00) == [L0, L0]            # CLR is active low: both cleared
+    assert step(0b01, 0b11) == [L1, L0]            # bit 0 set, bit 1 holds its 0
+    assert step(0b00, 0b11) == [L1, L0]            # hold
+    assert step(0b11, 0b10) == [L0, L1]            # bit 0: set and clear together -> clear wins; bit 1 set
+    assert step(0b00, 0b11) == [L0, L1]
