@@ -333,3 +333,24 @@ def test_builder_switches_survive_build():
     b.add_multiplexer([x, y], s, z)
     second = b.build()
     assert first.info.cyclic == 0 and second.info.cyclic == 1   # a multiplexer that can float makes its net a resolved net
+
+
+def test_pair_plan_statistics_need_no_device():
+    """b2_sim_plan_pairs: the level-pair plan of a netlist, computed on the host; refused for netlists it cannot serve."""
+    from digilogic_b200 import SimulatorBuilder, netgen
+    from digilogic_b200.gsim import B200Error
+    gen = netgen.random_dag(n_gates=20_000, depth=40, n_inputs=128, n_outputs=64, seed=7)
+    sim = gen.emit(SimulatorBuilder()).build()
+    plan = sim.plan_pairs(gen.outputs)
+    assert plan["items"] + plan["children"] == 20_000                       # every gate once, as a parent or as a child
+    assert 20 <= plan["launches"] <= 40 and plan["children"] > 6000 and plan["unstored"] > 1000
+    assert plan["dropped_now"] + plan["dropped_later"] + plan["unstored"] < 20_000
+    everything = sim.plan_pairs(np.arange(gen.n_wires, dtype=np.uint32))    # all wires kept: nothing may be dropped or skipped
+    assert everything["unstored"] == 0 and everything["dropped_now"] == 0 and everything["dropped_later"] == 0
+    assert everything["launches"] == plan["launches"] and everything["children"] == plan["children"]
+    b = SimulatorBuilder()
+    w = [b.add_wire() for _ in range(5)]
+    b.add_and_gate([w[0], w[1], w[2]], w[3])                                # a three-input gate: not eligible
+    b.add_not_gate(w[3], w[4])
+    with pytest.raises(B200Error):
+        b.build().plan_pairs([w[4]])
