@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256) k_copy_list(const uint32_t *rows, const u
 
 // Gates of `list[0 .. *count)` (one/two-input, or three-input with NIN = 3): B[row] = F(A), change detection
 // against A[row], changed-row flag.  Persistent: the grid is sized for the machine, CTAs stride over the list.
-template <int NIN>
+template <int NIN, bool HOT = false>
 __device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *list, const uint32_t *count, uint32_t bid, uint32_t nblk,
                                                const ulonglong2 *s_hot = nullptr) {
     constexpr int U = 2;
@@ -437,9 +437,21 @@ __device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const size_t r0 = (size_t)f0[u] * a.stride + col, r1 = (size_t)f1[u] * a.stride + col, o = (size_t)orow[u] * a.stride + col;
-            ld_operand(a, s_hot, f0[u], r0, av[u], am[u]);
-            ld_operand(a, s_hot, f1[u], r1, bv[u], bm[u]);
-            if (NIN == 3) ld_operand(a, s_hot, f2[u], (size_t)f2[u] * a.stride + col, cv[u], cm[u]);
+            if (HOT) {
+                ld_operand(a, s_hot, f0[u], r0, av[u], am[u]);
+                ld_operand(a, s_hot, f1[u], r1, bv[u], bm[u]);
+                if (NIN == 3) ld_operand(a, s_hot, f2[u], (size_t)f2[u] * a.stride + col, cv[u], cm[u]);
+            } else {
+                av[u] = ld_row(a.in_val + r0);
+                bv[u] = ld_row(a.in_val + r1);
+                am[u] = ld_row(a.in_vld + r0);
+                bm[u] = ld_row(a.in_vld + r1);
+                if (NIN == 3) {
+                    const size_t r2 = (size_t)f2[u] * a.stride + col;
+                    cv[u] = ld_row(a.in_val + r2);
+                    cm[u] = ld_row(a.in_vld + r2);
+                }
+            }
             ov[u] = ld_row(a.in_val + o);
             om[u] = ld_row(a.in_vld + o);
         }
@@ -491,11 +503,16 @@ __device__ __forceinline__ void eval_list_body(const Eval2Args &a, const uint4 *
 
 template <int NIN>
 __global__ void __launch_bounds__(256, NIN == 3 ? 2 : 3) k_eval_list(const Eval2Args a, const uint4 *list, const uint32_t *count) {
+    eval_list_body<NIN>(a, list, count, blockIdx.x, gridDim.x);
+}
+// the same with the hot rows of a.hot_row staged in shared memory (B2_OPT_HOT_STAGING)
+template <int NIN>
+__global__ void __launch_bounds__(256, NIN == 3 ? 2 : 3) k_eval_list_hot(const Eval2Args a, const uint4 *list, const uint32_t *count) {
     __shared__ __align__(128) ulonglong2 s_hot[2 * kHotRows * kHotPairs];  // [plane][hot row][pair of this CTA's column block]
     __shared__ __align__(8) uint64_t s_bar;
-    const bool hot = a.hot_n != 0 && *count != 0;  // uniform over the grid; an idle launch stages nothing
-    if (hot) stage_hot_rows(a, s_hot, &s_bar, blockIdx.x % a.pair_blocks);
-    eval_list_body<NIN>(a, list, count, blockIdx.x, gridDim.x, hot ? s_hot : nullptr);
+    if (*count == 0) return;  // uniform over the grid; an idle launch stages nothing
+    stage_hot_rows(a, s_hot, &s_bar, blockIdx.x % a.pair_blocks);
+    eval_list_body<NIN, true>(a, list, count, blockIdx.x, gridDim.x, s_hot);
 }
 
 template <bool JACOBI>
@@ -2686,7 +2703,8 @@ int Engine::run_jacobi(uint64_t max_steps) {
                 a.sem = net_.sem_flags;
                 set_hot(a);
                 const uint32_t gbs = std::min<uint32_t>((net_.n_g2() + per - 1) / per, gbs_max);
-                k_eval_list<2><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[0], act_counts);
+                if (a.hot_n) k_eval_list_hot<2><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[0], act_counts);
+                else k_eval_list<2><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[0], act_counts);
                 LAUNCHED();
             }
             gbs_max = slots(occ_list_[1]);
@@ -2696,7 +2714,8 @@ int Engine::run_jacobi(uint64_t max_steps) {
                 a.sem = net_.sem_flags;
                 set_hot(a);
                 const uint32_t gbs = std::min<uint32_t>((net_.n_g3() + per - 1) / per, gbs_max);
-                k_eval_list<3><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[1], act_counts + 1);
+                if (a.hot_n) k_eval_list_hot<3><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[1], act_counts + 1);
+                else k_eval_list<3><<<sh.pair_blocks * gbs, sh.block, 0, ST>>>(a, (const uint4 *)d_act_list_[1], act_counts + 1);
                 LAUNCHED();
             }
             gbs_max = slots(occ_list_[2]);
