@@ -143,3 +143,19 @@ def test_programmatic_dependent_launch_keeps_the_row_loads_behind_the_wait(pdl, 
             b.run_generated(0xFACE, 1, 3, words, 10_000, ov, om)
             assert b.wait() == SimulationRunResult.Ok
             assert (ov == rv[outputs]).all() and (om == rm[outputs]).all()
+
+
+def test_config3_shape_fused_equals_per_level_kernels():
+    """200 000 gates, depth 200 (the shape of BASELINE config 3 at a fifth of its width), the bench's batch shape: the fused
+    plan and the per-level kernels hand out the same output planes, and the plan is the one b2_sim_plan_pairs reports."""
+    gen = netgen.random_dag(n_gates=200_000, depth=200, n_inputs=4096, n_outputs=1024, seed=0xD1610003)
+    sim = gen.emit(d.SimulatorBuilder()).build()
+    words = 128 * 6
+    ov1, om1, launches = _run(sim, gen.inputs, gen.outputs, 128, 3, words, 0xD1610003, 0, pair=1)
+    plan = sim.plan_pairs(gen.outputs)
+    assert launches == plan["launches"] and 100 <= launches <= 125
+    assert plan["items"] + plan["children"] == 200_000 and plan["children"] > 80_000 and plan["unstored"] > 20_000
+    ov0, om0, launches0 = _run(sim, gen.inputs, gen.outputs, 128, 3, words, 0xD1610003, 0, pair=0)
+    assert launches0 == 0
+    assert (ov1 == ov0).all() and (om1 == om0).all()
+    assert (om1 == np.uint64(0xFFFFFFFFFFFFFFFF)).all()          # two-valued stimulus: every output lane is a valid 0 / 1
