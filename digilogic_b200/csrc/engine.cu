@@ -1108,6 +1108,7 @@ __global__ void __launch_bounds__(256, 2) k_unit_delay_loop(const LoopArgs a) {
 // drives (in) and the final state + lane status (out) touches HBM.  Lanes are independent, so
 // CTAs never talk to each other and each stops at its own fixed point.  This is the path of the
 // reference's real use (GUI: one lane, max_steps = 10 000, latches that may oscillate).
+static constexpr uint32_t kInlineBits = 96;
 struct ResidentArgs {
     const uint32_t *fan0, *fan1, *fan2;
     const uint8_t *kind2;
@@ -1140,6 +1141,13 @@ struct ResidentArgs {
     uint32_t snap_bytes;
     uint32_t sem;  // SemFlags of the netlist
     int period2;   // B2_OPT_PERIOD2_SKIP
+    // One-CTA runs (the reference server's one-lane cycle: set a few drives, eval, read every net): the drives queued by
+    // set_wire_drive travel in the kernel's arguments and are broadcast into their drive rows by the kernel itself, and the
+    // run's flags (like the snapshot above) are stored straight into page-locked host memory — one launch and one
+    // synchronisation per eval, no copy in either direction.
+    RunFlags *host_flags;  // [2] on the host, or nullptr: flags through `flags` / `max_apps` and a device-to-host copy
+    uint32_t n_inline;
+    PendingBit inl[kInlineBits];
 };
 
 __device__ __forceinline__ void wide_gate_word(const ResidentArgs &a, uint32_t g, const uint64_t *av, const uint64_t *am, uint32_t wpc,
@@ -1204,6 +1212,15 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
              *s_unsettled = s_conflict + wpc;
     __shared__ unsigned s_any, s_p2[2];
     if (threadIdx.x < 2) s_p2[threadIdx.x] = 0;
+    if (a.n_inline) {  // one CTA (the host sees to it): queued drives into their rows, like k_broadcast_bits
+        for (uint32_t i = tid; i < a.n_inline * a.stride; i += nt) {
+            const PendingBit &b = a.inl[i / a.stride];
+            b.val[i % a.stride] = (b.flags & 1) ? ~0ull : 0ull;
+            b.vld[i % a.stride] = (b.flags & 2) ? ~0ull : 0ull;
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
 
     // ---- load: the current state, or the cold start W_1 = resolve(D, all outputs High-Z) = D
     //      (a levelised pass recomputes every row: only the source rows are loaded, from their drives)
@@ -1444,7 +1461,21 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
             a.vld[(size_t)row * a.stride + w] = AM[i];
         }
     }
-    if (a.snap0 && blockIdx.x == 0) {  // lane 0 = bit 0 of the first lane-word, which CTA 0 holds
+    if (a.snap0 && a.host_flags) {
+        // straight into page-locked host memory: 64 rows per store (a byte store each would be a PCIe write each)
+        for (uint32_t q = tid; q < (a.snap_bytes + 7) / 8; q += nt) {
+            uint64_t b0 = 0, b1 = 0;
+            for (uint32_t j = 0; j < 64; j++) {
+                const uint32_t row = q * 64 + j;
+                if (row < a.n_rows) {
+                    b0 |= (AV[(size_t)row * wpc] & 1) << j;
+                    b1 |= (AM[(size_t)row * wpc] & 1) << j;
+                }
+            }
+            ((uint64_t *)a.snap0)[q] = b0;
+            ((uint64_t *)a.snap1)[q] = b1;
+        }
+    } else if (a.snap0 && blockIdx.x == 0) {  // lane 0 = bit 0 of the first lane-word, which CTA 0 holds
         for (uint32_t byte = tid; byte < a.snap_bytes; byte += nt) {
             uint32_t b0 = 0, b1 = 0;
             for (uint32_t j = 0; j < 8; j++) {
@@ -1461,10 +1492,30 @@ __global__ void __launch_bounds__(1024, 1) k_resident_run(const ResidentArgs a) 
     if (tid < wpc && w0 + tid < a.stride) {
         a.conflict[w0 + tid] = s_conflict[tid];
         a.unsettled[w0 + tid] = s_unsettled[tid];
-        if (s_conflict[tid]) atomicOr(&a.flags->any_conflict, 1u);
-        if (s_unsettled[tid]) atomicOr(&a.flags->any_unsettled, 1u);
+        if (!a.host_flags) {
+            if (s_conflict[tid]) atomicOr(&a.flags->any_conflict, 1u);
+            if (s_unsettled[tid]) atomicOr(&a.flags->any_unsettled, 1u);
+        }
     }
-    if (tid == 0) atomicMax(a.max_apps, apps);
+    if (a.host_flags) {  // one CTA: the flags of the run go straight to the host
+        if (tid == 0) {
+            uint64_t c = 0, u = 0;
+            for (uint32_t j = 0; j < wpc; j++)
+                if (w0 + j < a.stride) {
+                    c |= s_conflict[j];
+                    u |= s_unsettled[j];
+                }
+            RunFlags f;
+            f.any_live = 0;
+            f.any_conflict = c != 0;
+            f.any_unsettled = u != 0;
+            f.active = 0;
+            a.host_flags[0] = f;
+            *(unsigned long long *)(a.host_flags + 1) = apps;
+        }
+    } else if (tid == 0) {
+        atomicMax(a.max_apps, apps);
+    }
 }
 
 // ---------------------------------------------------------------------------- Engine: setup
@@ -1488,6 +1539,7 @@ void Engine::copy_options_from(const Engine &o) {
     opt_discard_ = o.opt_discard_;
     opt_pair_ = o.opt_pair_;
     opt_hot_ = o.opt_hot_;
+    opt_direct_ = o.opt_direct_;
     disc_short_ = o.disc_short_;
     disc_never_ = o.disc_never_;
     opt_flags_ = o.opt_flags_;
@@ -1562,6 +1614,7 @@ Engine::~Engine() {
     cudaFree(d_loop_result_);
     if (h_loop_result_) cudaFreeHost(h_loop_result_);
     if (h_flags_) cudaFreeHost(h_flags_);
+    if (h_snap_) cudaFreeHost(h_snap_);
     if (own_stream_ && stream_) cudaStreamDestroy(ST);
     if (cin_stream_) cudaStreamDestroy(CIN);
     if (cout_stream_) cudaStreamDestroy(COUT);
@@ -1723,7 +1776,13 @@ int Engine::ensure_device() {
     }
     if (!d_flags_) CU_TRY(cudaMalloc((void **)&d_flags_, 8 * sizeof(RunFlags)));
     CU_TRY(cudaMemset(d_flags_, 0, 8 * sizeof(RunFlags)));
-    if (!h_flags_) CU_TRY(cudaMallocHost((void **)&h_flags_, 8 * sizeof(RunFlags)));
+    if (!h_flags_) {
+        CU_TRY(cudaHostAlloc((void **)&h_flags_, 8 * sizeof(RunFlags), cudaHostAllocMapped));
+        if (cudaHostGetDevicePointer(&h_flags_dev_, h_flags_, 0) != cudaSuccess) {
+            cudaGetLastError();
+            h_flags_dev_ = nullptr;  // no direct stores into host memory: flags and snapshot are copied
+        }
+    }
     for (int i = 0; i < 8; i++) {
         if (ev_flags_[i]) continue;
         cudaEvent_t ev;
@@ -1995,6 +2054,37 @@ int Engine::set_wire_drive(uint32_t wire, const uint32_t *p0, const uint32_t *p1
     }
     pending_.push_back(d);
     if (pending_.size() >= (1u << 16)) return flush_pending_drives();
+    return B2_OK;
+}
+
+// The queued drives as at most `cap` (row pointers, planes) entries for the resident kernel's arguments; *n = 0 (and the queue
+// untouched) when they do not fit.
+int Engine::pending_to_bits(void *out, uint32_t cap, uint32_t *n) {
+    *n = 0;
+    size_t n_bits = 0;
+    for (const PendingDrive &d : pending_) n_bits += net_.width[d.wire];
+    if (n_bits == 0 || n_bits > cap) return B2_OK;
+    // a wire driven twice keeps only its last drive: later entries overwrite earlier ones in queue order (one thread block
+    // writes them, but in an unspecified order) — so drop the earlier ones here
+    std::unordered_map<uint32_t, size_t> last;
+    for (size_t i = 0; i < pending_.size(); i++) last[pending_[i].wire] = i;
+    PendingBit *bits = (PendingBit *)out;
+    int rc;
+    for (int pass = 0; pass < 2; pass++) {  // two passes: the first may grow the extra store and move earlier rows
+        size_t k = 0;
+        for (size_t i = 0; i < pending_.size(); i++) {
+            const PendingDrive &d = pending_[i];
+            if (last[d.wire] != i) continue;
+            for (uint32_t j = 0; j < net_.width[d.wire]; j++, k++) {
+                PendingBit &b = bits[k];
+                if ((rc = drive_target(net_.bit_off[d.wire] + j, &b.val, &b.vld))) return rc;
+                b.flags = ((d.p0[j >> 5] >> (j & 31)) & 1) | (((d.p1[j >> 5] >> (j & 31)) & 1) << 1);
+                b.pad = 0;
+            }
+        }
+        *n = (uint32_t)k;
+    }
+    pending_.clear();
     return B2_OK;
 }
 
@@ -2832,7 +2922,27 @@ uint32_t Engine::resident_wpc() const {
     return (uint32_t)(wpc ? wpc : 1);
 }
 
-int Engine::run_resident(uint64_t max_steps, bool levelised) {
+// Page-locked host memory the device can store the run flags and the lane-0 snapshot into (one-CTA resident runs).
+bool Engine::direct_ready() {
+    if (!opt_direct_ || !h_flags_dev_) return false;
+    const size_t need = 2 * (((size_t)net_.n_rows / 8 + 1 + 7) & ~(size_t)7) + 64;
+    if (h_snap_cap_ >= need) return true;
+    if (cudaStreamSynchronize(ST) != cudaSuccess) return false;
+    if (h_snap_) cudaFreeHost(h_snap_);
+    h_snap_ = h_snap_dev_ = nullptr;
+    h_snap_cap_ = 0;
+    if (cudaHostAlloc((void **)&h_snap_, need, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&h_snap_dev_, h_snap_, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (h_snap_) cudaFreeHost(h_snap_);
+        h_snap_ = h_snap_dev_ = nullptr;
+        return false;
+    }
+    h_snap_cap_ = need;
+    return true;
+}
+
+int Engine::run_resident(uint64_t max_steps, bool levelised, const void *inline_bits, uint32_t n_inline) {
     const uint32_t wpc = resident_wpc();
     // step_sim calls gsim allows after begin_sim: max_steps + 1 with its `steps > max_steps` check
     const uint64_t N = opt_budget_inclusive_ ? max_steps : (max_steps == UINT64_MAX ? UINT64_MAX : max_steps + 1);
@@ -2842,9 +2952,18 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
     if ((rc = materialise_valid())) return rc;
     if ((rc = drives_begin())) return rc;
     if ((rc = sync_extra_tables())) return rc;
+    const uint32_t ctas = (stride_ + wpc - 1) / wpc;
+    const bool with_snapshot = T_ <= 64;  // interactive-sized runs: get_wire_state will want lane 0 next
+    // one CTA and page-locked memory the device can store into: flags and snapshot go straight to the host
+    const size_t snap_bytes = (size_t)net_.n_rows / 8 + 1;
+    const bool direct = ctas == 1 && with_snapshot && direct_ready();
+    if (n_inline && !direct) return B2_ERR_INVALID_ARG;  // Engine::run checked the same conditions
     // flag slot 0 takes the run's flags, slot 1 the application count: one clear before, one copy after the kernel
-    CU_TRY(cudaMemsetAsync(d_flags_, 0, 2 * sizeof(RunFlags), ST));
+    if (!direct) CU_TRY(cudaMemsetAsync(d_flags_, 0, 2 * sizeof(RunFlags), ST));
     ResidentArgs a;
+    a.host_flags = direct ? (RunFlags *)h_flags_dev_ : nullptr;
+    a.n_inline = n_inline;
+    for (uint32_t i = 0; i < n_inline; i++) a.inl[i] = ((const PendingBit *)inline_bits)[i];
     a.fan0 = d_fan0_; a.fan1 = d_fan1_; a.fan2 = d_fan2_; a.kind2 = d_kind2_;
     a.woff = d_wide_off_; a.win = d_wide_in_; a.wkind = d_wide_kind_; a.wnsel = d_wide_nsel_; a.waux = d_wide_aux_;
     a.xrows = d_extra_rows_; a.xval = xdrv_val_; a.xvld = xdrv_vld_;
@@ -2872,12 +2991,15 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
     }
     const size_t items = (size_t)net_.n_rows * wpc;
     const uint32_t threads = items >= 1024 ? 1024 : (items >= 256 ? 512 : 128);
-    const uint32_t ctas = (stride_ + wpc - 1) / wpc;
-    const size_t snap_bytes = (size_t)net_.n_rows / 8 + 1;
-    const bool with_snapshot = T_ <= 64;  // interactive-sized runs: get_wire_state will want lane 0 next
     a.snap0 = a.snap1 = nullptr;
     a.snap_bytes = 0;
-    if (with_snapshot) {
+    const size_t snap_pitch = (snap_bytes + 7) & ~(size_t)7;  // the direct path stores 8 bytes at a time
+    if (direct) {
+        a.snap0 = h_snap_dev_;
+        a.snap1 = h_snap_dev_ + snap_pitch;
+        a.snap_bytes = (uint32_t)snap_bytes;
+        snap_.resize(2 * snap_bytes);
+    } else if (with_snapshot) {
         if (pack_cap_ < 2 * snap_bytes) {
             CU_TRY(cudaStreamSynchronize(ST));
             cudaFree(d_pack_);
@@ -2893,10 +3015,16 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
     }
     k_resident_run<<<ctas, threads, smem, ST>>>(a);
     LAUNCHED();
-    CU_TRY(cudaMemcpyAsync(h_flags_, d_flags_, 2 * sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
-    if (with_snapshot) CU_TRY(cudaMemcpyAsync(snap_.data(), d_pack_, 2 * snap_bytes, cudaMemcpyDeviceToHost, ST));
+    if (!direct) {
+        CU_TRY(cudaMemcpyAsync(h_flags_, d_flags_, 2 * sizeof(RunFlags), cudaMemcpyDeviceToHost, ST));
+        if (with_snapshot) CU_TRY(cudaMemcpyAsync(snap_.data(), d_pack_, 2 * snap_bytes, cudaMemcpyDeviceToHost, ST));
+    }
     if ((rc = drives_end())) return rc;
     CU_TRY(cudaStreamSynchronize(ST));
+    if (direct) {
+        std::memcpy(snap_.data(), h_snap_, snap_bytes);
+        std::memcpy(snap_.data() + snap_bytes, h_snap_ + snap_pitch, snap_bytes);
+    }
     snap_valid_ = with_snapshot;
     cold_ = false;
     frontier_valid_ = false;
@@ -2910,7 +3038,17 @@ int Engine::run_resident(uint64_t max_steps, bool levelised) {
 int Engine::run(uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled, bool async) {
     int rc = ensure_lanes();
     if (rc) return -rc;
-    if ((rc = flush_pending_drives())) return -rc;
+    // the one-lane server cycle: a few queued drives, a netlist that runs in one resident CTA — the drives ride in the kernel's
+    // arguments instead of an upload and a launch of their own
+    PendingBit inl[kInlineBits];
+    uint32_t n_inline = 0;
+    {
+        const bool dag = !net_.cyclic && max_steps >= (uint64_t)net_.depth + 1;
+        const bool resident = !net_.multi_driver && use_resident_ && resident_wpc() && !(dag && !(stride_ <= 4)) && T_ <= 64 &&
+                              (stride_ + resident_wpc() - 1) / resident_wpc() == 1 && direct_ready();
+        if (resident && !pending_.empty() && (rc = pending_to_bits(inl, kInlineBits, &n_inline))) return -rc;
+    }
+    if (n_inline == 0 && (rc = flush_pending_drives())) return -rc;
     if (side_pending_) {  // a gather of the previous run's rows may still be reading the store on the side stream
         if (cudaStreamWaitEvent(ST, EV(ev_side_done_), 0) != cudaSuccess) return -B2_ERR_CUDA;
         side_pending_ = false;
@@ -2932,7 +3070,7 @@ int Engine::run(uint64_t max_steps, uint64_t *conflict, uint64_t *unsettled, boo
     } else if (dag_ok && !(stride_ <= 4 && resident_wpc() && use_resident_)) {
         result = run_levelised(async && !conflict && !unsettled);
     } else if (use_resident_ && resident_wpc()) {
-        result = run_resident(max_steps, dag_ok);  // small netlist: the whole run_sim loop (or level sweep) on chip
+        result = run_resident(max_steps, dag_ok, inl, n_inline);  // small netlist: the whole run_sim loop (or level sweep) on chip
     } else {
         result = run_jacobi(max_steps);
     }

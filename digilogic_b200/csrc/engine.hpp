@@ -128,6 +128,7 @@ class Engine {
     void set_pdl(uint32_t mode) { opt_pdl_ = mode <= 2 ? mode : 0; level_graph_key_ = 0; }
     // Level-pair fusion (pair.cuh; default off): acts only on levelised runs with set_discard on, for netlists of one/two-input gates.
     void set_pair_fusion(bool on) { opt_pair_ = on; level_graph_key_ = 0; }
+    void set_direct_cycle(bool on) { opt_direct_ = on; }
     // Unit-delay work-list kernels keep the (at most four) rows with the largest fan-out (>= 100 gates) in shared memory.
     void set_hot_staging(bool on) { opt_hot_ = on; }
     void hot_rows(uint32_t *rows, uint32_t *n);  // store rows staged (n = 0: none qualifies, or the option is off)
@@ -155,7 +156,9 @@ class Engine {
     int run_levelised(bool async);
     int run_jacobi(uint64_t max_steps);
     int run_device_loop(uint64_t &k, uint64_t last, bool &finished, int &result);
-    int run_resident(uint64_t max_steps, bool levelised);
+    int run_resident(uint64_t max_steps, bool levelised, const void *inline_bits = nullptr, uint32_t n_inline = 0);
+    int pending_to_bits(void *out, uint32_t cap, uint32_t *n);
+    bool direct_ready();
     int materialise_valid();
     uint32_t resident_wpc() const;
 
@@ -200,6 +203,10 @@ class Engine {
     // per-lane status words [T]
     uint64_t *d_changed_ = nullptr, *d_conf_step_ = nullptr, *d_live_ = nullptr, *d_conflict_ = nullptr, *d_unsettled_ = nullptr;
     RunFlags *d_flags_ = nullptr, *h_flags_ = nullptr;
+    void *h_flags_dev_ = nullptr;     // h_flags_ as the device sees it (mapped page-locked memory), or nullptr
+    uint8_t *h_snap_ = nullptr, *h_snap_dev_ = nullptr;  // page-locked lane-0 snapshot the one-CTA resident run stores into
+    size_t h_snap_cap_ = 0;
+    bool opt_direct_ = true;          // one-CTA resident runs: drives in the kernel arguments, flags and snapshot stored to the host
 
     // staging for host <-> device plane transfers, on their own copy streams so that the H2D of
     // the next tile and the D2H of the previous one overlap the settle of the current tile
