@@ -78,7 +78,7 @@ def parse_args():
     ap.add_argument("--e2e-ring-tiles", type=int, default=0, help="host stimulus ring size in tiles (0 = whole batch on 1 GPU, 2^20 lanes otherwise)")
     ap.add_argument("--cpu-lanes-per-core", type=int, default=24)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--pair-fusion", action="store_true", help="B2_OPT_PAIR_FUSION = 1: items of two dependent gates per thread, about depth / 2 launches per tile (measured: no faster)")
+    ap.add_argument("--no-pair-fusion", action="store_true", help="B2_OPT_PAIR_FUSION = 0: one launch per level (the library default is automatic: fused for config 3, per level for config 5)")
     ap.add_argument("--no-elision-probe", action="store_true", help="skip the secondary run with B2_OPT_VALID_ELISION")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-unit-delay-probe", action="store_true", help="skip the secondary config-4 (feedback) run")
@@ -283,7 +283,8 @@ def run_b200(args):
     tile = min(args.tile_words, words_local) if args.tile_words else auto_tile
     slots = args.slots or auto_slots
     args.tile_words, args.slots = tile, slots
-    sim.set_option(sim.OPT_PAIR_FUSION, 1 if args.pair_fusion else 0)
+    if args.no_pair_fusion:
+        sim.set_option(sim.OPT_PAIR_FUSION, 0)
     batch = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=local_rank, stream=stream.cuda_stream)
     batch.set_option(Batch.OPT_SWEEP, 1 if args.sweep else 0)
     batch.set_option(Batch.OPT_TASK_ITERS, args.task_iters)

@@ -35,6 +35,10 @@ def unpack(words, n):
     return np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")[:n]
 
 
+def info_depth(sim):
+    return sim.info.depth
+
+
 def config2(args):
     import torch
     from digilogic_b200 import SimulationRunResult, SimulatorBuilder, importers
@@ -94,8 +98,33 @@ def config2(args):
         hi |= unpack(pv[32 + j], n_lanes).astype(np.uint64) << np.uint64(j)
     prod = a * b
     ok = bool((lo == (prod & np.uint64(0xFFFFFFFF))).all() and (hi == (prod >> np.uint64(32))).all())
+    # the batch runner on the same job (designated outputs only, so rows may be dropped and gates fused): shapes x level-pair fusion
+    from digilogic_b200.batch import Batch
+    batch_rows = []
+    dv, dm = torch.from_numpy(value.view(np.int64)).cuda(), torch.from_numpy(valid.view(np.int64)).cuda()
+    ov = torch.zeros((len(outs), words), dtype=torch.int64, device="cuda")
+    om = torch.zeros_like(ov)
+    for tile, slots in ((16384, 1), (8192, 2), (4096, 3), (2048, 3)):
+        for pair in (0, 1):
+            sim.set_option(sim.OPT_PAIR_FUSION, pair)
+            bt = Batch(sim, wires, outs, tile, slots, device=0, stream=st.cuda_stream)
+            for _ in range(2):
+                bt.run_planes(dv, dm, words, 10_000, ov, om)
+            assert bt.wait() == SimulationRunResult.Ok
+            e0.record(st)
+            for _ in range(reps):
+                bt.run_planes(dv, dm, words, 10_000, ov, om)
+            e1.record(st)
+            bt.wait()
+            ms = e0.elapsed_time(e1) / reps
+            same = bool((ov.cpu().numpy().view(np.uint64) == pv).all() and (om.cpu().numpy().view(np.uint64) == ALL1).all())
+            batch_rows.append({"tile_words": tile, "slots": slots, "pair_fusion": pair, "launches_per_tile": bt.info.pair_launches or info_depth(sim),
+                               "ms": round(ms, 4), "gate_lane_evals_per_s": len(circ.gates) * n_lanes / (ms * 1e-3), "outputs_equal": same})
+            del bt
+    sim.set_option(sim.OPT_PAIR_FUSION, 2)
     info = sim.info
     print(json.dumps({"config": 2, "workload": "32x32 array multiplier via Yosys JSON, 2^20 random vectors, host planes in and out",
+                      "batch_runner": batch_rows,
                       "gates": len(circ.gates), "depth": info.depth, "lanes": n_lanes, "seconds_e2e": dt,
                       "gate_lane_evals_per_s": len(circ.gates) * n_lanes / dt, "seconds_e2e_pinned_host_planes": dt_pinned,
                       "gate_lane_evals_per_s_pinned": len(circ.gates) * n_lanes / dt_pinned, "settle_ms_device": settle_ms,

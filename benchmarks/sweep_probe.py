@@ -54,7 +54,7 @@ def main():
         sim.set_option(sim.OPT_L2_HINTS, hints)
         sim.set_option(sim.OPT_VALID_ELISION, args.elision)
         sim.set_option(sim.OPT_EVAL_UNROLL, args.eval_unroll)
-        sim.set_option(sim.OPT_PAIR_FUSION, f[10] if len(f) > 10 else 0)
+        sim.set_option(sim.OPT_PAIR_FUSION, f[10] if len(f) > 10 else 2)
         b = Batch(sim, gen.inputs, gen.outputs, tile, slots, device=0, stream=stream.cuda_stream)
         b.set_option(Batch.OPT_TASK_ITERS, iters)
         b.set_option(Batch.OPT_UNROLL, unroll)

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--tile-words", type=int, default=256)
     ap.add_argument("--slots", type=int, default=3)
     ap.add_argument("--sweep", type=int, default=0)
-    ap.add_argument("--pair", type=int, default=0)
+    ap.add_argument("--pair", type=int, default=2)
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0xD1610003)
     args = ap.parse_args()
     import torch

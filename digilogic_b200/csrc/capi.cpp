@@ -308,7 +308,7 @@ int b2_sim_set_option(b2_sim *s, int option, int64_t value) {
         case B2_OPT_L2_HINTS: s->e->set_l2_hints(value != 0); return B2_OK;
         case B2_OPT_PERIOD2_SKIP: s->e->set_period2_skip(value != 0); return B2_OK;
         case B2_OPT_PDL: s->e->set_pdl((uint32_t)value); return B2_OK;
-        case B2_OPT_PAIR_FUSION: s->e->set_pair_fusion(value != 0); return B2_OK;
+        case B2_OPT_PAIR_FUSION: s->e->set_pair_fusion((uint32_t)value); return B2_OK;
         case B2_OPT_HOT_STAGING: s->e->set_hot_staging(value != 0); return B2_OK;
         case B2_OPT_CONFLICT_NEEDS_DISAGREE: return s->e->set_lenient_conflicts(value != 0) ? B2_OK : B2_ERR_INVALID_ARG;
         default: return B2_ERR_INVALID_ARG;

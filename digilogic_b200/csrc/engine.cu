@@ -2423,9 +2423,10 @@ int Engine::run_levelised(bool async) {
     // CUDA graph and replayed per run, which takes the per-launch CPU cost and most of the
     // launch-to-launch gap out of small tiles (hundreds of levels of a few microseconds each).
     const bool want_graph = opt_graph_ && net_.levels.size() >= 8;
-    const uint64_t gkey = ((uint64_t)(uintptr_t)V) ^ ((uint64_t)stride_ << 2) ^ (kv ? 1u : 0u) ^ (opt_l2_hints_ ? 2u : 0u) ^ (opt_discard_ ? 8u : 0u) ^ ((uint64_t)opt_pdl_ << 4) ^ (opt_pair_ ? 64u : 0u);
+    const uint64_t gkey = ((uint64_t)(uintptr_t)V) ^ ((uint64_t)stride_ << 2) ^ (kv ? 1u : 0u) ^ (opt_l2_hints_ ? 2u : 0u) ^ (opt_discard_ ? 8u : 0u) ^ ((uint64_t)opt_pdl_ << 4) ^ ((uint64_t)opt_pair_ << 6);
     // level-pair fusion: only where rows need not survive their last reader (set_discard), plain two-plane rows, whole-line rows
-    const bool pair_path = opt_pair_ && opt_discard_ && !kv && extra_rows_.empty() && stride_ % 16 == 0;
+    const bool pair_wanted = opt_pair_ == 1 || (opt_pair_ == 2 && net_.depth && net_.n_g2() / net_.depth <= kPairAutoWidth);
+    const bool pair_path = pair_wanted && opt_discard_ && !kv && extra_rows_.empty() && stride_ % 16 == 0;
     if (pair_path && (rc0 = ensure_pair_plan())) return rc0;
     const bool use_pair = pair_path && pair_ != nullptr;
     last_pair_ = use_pair;
@@ -2462,8 +2463,11 @@ int Engine::run_levelised(bool async) {
                 a.pdl = opt_pdl_;
                 if (a.n_items == 0) continue;
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(sh.pair_blocks * ((a.n_items + sh.block.y - 1) / sh.block.y));
-                cfg.blockDim = sh.block;
+                // CTAs of 128 threads, like k_eval2 with two gates per thread
+                dim3 blk = sh.block;
+                if (blk.x <= 128) blk.y = 128 / blk.x;
+                cfg.gridDim = dim3(sh.pair_blocks * ((a.n_items + blk.y - 1) / blk.y));
+                cfg.blockDim = blk;
                 cfg.stream = ST;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -9,7 +9,9 @@
 // lane-words, all plane loads of an item issued before the first use, rows that die within a launch of being written dropped
 // from L2 (discard.global.L2) once their last reader has run, consecutive launches chained by programmatic dependent launch
 // (row loads behind griddepcontrol.wait: plain loads, device_ops.cuh ld_dep).  Measured on config 3: half the launches, 17 % fewer
-// sectors between the SMs and L2, the same time as the per-level kernels — hence an option, default off.
+// sectors between the SMs and L2, the same time as the per-level kernels.  Where it pays is a netlist with NARROW levels, whose
+// per-level kernels are launch-bound: the 32x32 array multiplier of config 2 (32 gates per level on average, depth 184) settles
+// 2^20 vectors in 0.55 ms instead of 0.76 ms.  B2_OPT_PAIR_FUSION = 2 (default) turns it on for such netlists only.
 //
 // plan_pairs() is the host side: a greedy as-soon-as-possible assignment of every gate to (launch, parent | child) in
 // level order.  A gate that cannot be a child (two fan-ins written by the launch it would join, a parent that already has two
@@ -55,8 +57,10 @@ __global__ void __launch_bounds__(256, 5) k_eval_pair(const PairArgs a) {
     // loaded before the dependency wait
     const uint4 q0 = __ldg(a.items + 2 * (size_t)i), q1 = __ldg(a.items + 2 * (size_t)i + 1);
     const uint32_t lpr = a.stride >> 4;
-    const uint32_t j0 = blockIdx.x * 256 + threadIdx.y * blockDim.x + threadIdx.x;
-    const bool drops = a.discard && blockIdx.x < 296u && j0 < a.n_disc * lpr;  // launches drop far fewer than 296 x 256 lines
+    const uint32_t cta_threads = blockDim.x * blockDim.y;
+    const uint32_t j0 = blockIdx.x * cta_threads + threadIdx.y * blockDim.x + threadIdx.x;
+    // (by the CTAs that start first; launches drop far fewer than 296 x 256 lines)
+    const bool drops = a.discard && blockIdx.x < 296u * (256u / cta_threads) && j0 < a.n_disc * lpr;
     const uint32_t drow = drops ? __ldg(a.disc_rows + j0 / lpr) : 0;
     if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t meta = q0.w;

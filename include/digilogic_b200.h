@@ -246,7 +246,9 @@ enum b2_option {
     B2_OPT_PDL = 11,           /* Levelised pass: consecutive level kernels of a simulator are launched with programmatic stream
                                   serialisation (griddepcontrol): the next level's launch and index loads overlap this level's tail.
                                   0 off, 1 dependents released when every CTA has started, 2 (default) when every CTA is about to finish. */
-    B2_OPT_PAIR_FUSION = 12,   /* default 0 (measured: as fast as the per-level kernels, not faster — DESIGN.md section 10).  Levelised pass of a simulator that need not keep rows after their last reader (the replicas
+    B2_OPT_PAIR_FUSION = 12,   /* 0 off, 1 on, 2 (default) automatic: on up to 16 384 gates per level on average.  Measured: the 32x32
+                                  multiplier of config 2 (32 gates per level) settles 2^20 vectors in 0.54 ms instead of 0.77 ms, config 3
+                                  (5000 per level) gains 5 %, config 5 (50 000 per level) loses 2 % and keeps the per-level kernels.  Levelised pass of a simulator that need not keep rows after their last reader (the replicas
                                   of a batch, B2_BATCH_OPT_DISCARD) and whose netlist has only one/two-input gates: two dependent gates
                                   are evaluated by one thread — a launch holds items of one gate whose fan-ins are older than the launch
                                   plus up to two gates reading its output, which they get in registers; a row read only inside its item

@@ -159,3 +159,20 @@ def test_config3_shape_fused_equals_per_level_kernels():
     assert launches0 == 0
     assert (ov1 == ov0).all() and (om1 == om0).all()
     assert (om1 == np.uint64(0xFFFFFFFFFFFFFFFF)).all()          # two-valued stimulus: every output lane is a valid 0 / 1
+
+
+def test_automatic_choice_follows_the_level_width():
+    """B2_OPT_PAIR_FUSION = 2 (the default): narrow levels are fused, wide ones keep the per-level kernels."""
+    narrow = netgen.random_dag(n_gates=6000, depth=60, n_inputs=64, n_outputs=32, seed=2)        # 100 gates per level
+    wide = netgen.random_dag(n_gates=100_000, depth=5, n_inputs=64, n_outputs=32, seed=2)        # 20 000 gates per level
+    for gen, fused in ((narrow, True), (wide, False)):
+        sim = gen.emit(d.SimulatorBuilder()).build()
+        words = 64
+        b = Batch(sim, gen.inputs, gen.outputs, 32, 2)
+        ov = np.zeros((len(gen.outputs), words), np.uint64)
+        om = np.zeros_like(ov)
+        b.run_generated(11, 1, 0, words, 10_000, ov, om)
+        assert b.wait() == SimulationRunResult.Ok
+        assert (b.info.pair_launches > 0) == fused
+        rv, rm = _oracle_rows(gen, gen.n_wires, gen.inputs, words, 11, 0, 1)
+        assert (ov == rv[gen.outputs]).all() and (om == rm[gen.outputs]).all()
