@@ -45,6 +45,10 @@ pub const B2_BOPT_MUX_Z_PASSTHROUGH: c_int = 1;
 pub const B2_BOPT_INITIAL_UNDEFINED: c_int = 2;
 pub const B2_BOPT_BUFFER_Z_PASSTHROUGH: c_int = 3;
 pub const B2_BOPT_COPY_Z_PASSTHROUGH: c_int = 4;
+// b2_option (simulator): the switches a host is most likely to touch; the full list is in include/digilogic_b200.h
+pub const B2_OPT_STEP_BUDGET_INCLUSIVE: c_int = 6;
+pub const B2_OPT_CONFLICT_NEEDS_DISAGREE: c_int = 8;
+pub const B2_OPT_PAIR_FUSION: c_int = 12; // 0 off, 1 on, 2 automatic (default)
 // b2_batch_option
 pub const B2_BATCH_OPT_SWEEP: c_int = 1;
 pub const B2_BATCH_OPT_AUTO_GATHER: c_int = 5;
@@ -84,6 +88,9 @@ extern "C" {
     pub fn b2_pack_sim_state(s: *mut B2Sim, wires: *const u32, n: u32, p0: *mut u8, p1: *mut u8, cap: usize, bit_len: *mut u64) -> c_int;
     pub fn b2_builder_set_option(b: *mut B2Builder, option: c_int, value: i64) -> c_int; // SURVEY A.6-4..7 switches
     pub fn b2_sim_clone(s: *const B2Sim) -> *mut B2Sim; // a second simulator of the same compiled netlist (shared device copy)
+    pub fn b2_sim_set_option(s: *mut B2Sim, option: c_int, value: i64) -> c_int; // engine options (B2_OPT_*), copied into a batch's replicas
+    pub fn b2_sim_plan_pairs(s: *const B2Sim, keep_wires: *const u32, n_keep: u32, out: *mut u64) -> c_int; // [u64; 6]: the level-pair plan, host only
+    pub fn b2_sim_get_pair_info(s: *const B2Sim, launches: *mut u64, children: *mut u64, unstored: *mut u64) -> c_int;
 
     // ---- batch runner and multi-GPU gather (no gsim counterpart: L lanes = L Simulator::run_sim calls, lib.rs:216-219)
     pub fn b2_batch_new(sim: *const B2Sim, inputs: *const u32, n_inputs: u32, outputs: *const u32, n_outputs: u32, tile_words: u32, n_slots: u32, out: *mut *mut B2Batch) -> c_int;
