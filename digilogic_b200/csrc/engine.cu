@@ -2327,16 +2327,17 @@ int Engine::ensure_pair_plan() {
     auto it = share_->pair_plans.find(device_);
     if (it != share_->pair_plans.end()) {
         std::shared_ptr<PairPlanDev> have = it->second.lock();
-        if (have && have->keep_rows == keep_rows_) {
+        if (have && have->keep_all == !opt_discard_ && (have->keep_all || have->keep_rows == keep_rows_)) {
             pair_ = have;
             return B2_OK;
         }
     }
     PairPlanHost plan;
-    if (!plan_pairs(net_, keep_rows_, plan)) return B2_OK;
+    if (!plan_pairs(net_, keep_rows_, plan, !opt_discard_)) return B2_OK;
     auto dev = std::make_shared<PairPlanDev>();
     dev->device = device_;
     dev->keep_rows = keep_rows_;
+    dev->keep_all = !opt_discard_;
     dev->n_items = plan.items.size();
     dev->n_children = plan.n_children;
     dev->n_unstored = plan.n_unstored;
@@ -2426,7 +2427,8 @@ int Engine::run_levelised(bool async) {
     const uint64_t gkey = ((uint64_t)(uintptr_t)V) ^ ((uint64_t)stride_ << 2) ^ (kv ? 1u : 0u) ^ (opt_l2_hints_ ? 2u : 0u) ^ (opt_discard_ ? 8u : 0u) ^ ((uint64_t)opt_pdl_ << 4) ^ ((uint64_t)opt_pair_ << 6);
     // level-pair fusion: only where rows need not survive their last reader (set_discard), plain two-plane rows, whole-line rows
     const bool pair_wanted = opt_pair_ == 1 || (opt_pair_ == 2 && net_.depth && net_.n_g2() / net_.depth <= kPairAutoWidth);
-    const bool pair_path = pair_wanted && opt_discard_ && !kv && extra_rows_.empty() && stride_ % 16 == 0;
+    // (with set_discard: rows die and are dropped, which needs whole-line rows; without: every row is kept, only the launches are fused)
+    const bool pair_path = pair_wanted && !kv && extra_rows_.empty() && (!opt_discard_ || stride_ % 16 == 0);
     if (pair_path && (rc0 = ensure_pair_plan())) return rc0;
     const bool use_pair = pair_path && pair_ != nullptr;
     last_pair_ = use_pair;
@@ -2458,7 +2460,7 @@ int Engine::run_levelised(bool async) {
                 a.pairs = pairs;
                 a.pair_blocks = sh.pair_blocks;
                 a.sem = net_.sem_flags;
-                a.discard = 1;
+                a.discard = opt_discard_ ? 1 : 0;
                 a.hints = opt_l2_hints_ ? 1 : 0;
                 a.pdl = opt_pdl_;
                 if (a.n_items == 0) continue;

@@ -43,6 +43,7 @@ struct PairLaunch;
 struct PairPlanDev {
     int device = -1;
     std::vector<uint32_t> keep_rows;  // sorted: the rows the plan keeps (its key)
+    bool keep_all = false;            // ... or every row (plain simulator runs)
     void *items = nullptr;            // PairItem[] on the device
     uint32_t *disc_rows = nullptr;
     std::vector<uint32_t> launch_tab;  // 4 per launch: item_begin, item_end, disc_begin, disc_end

@@ -45,7 +45,9 @@ struct PairPlanHost {
 
 // keep_sorted: rows that must hold their value after the run (designated outputs).  Returns false if the netlist is not
 // eligible (anything but one/two-input gates of an acyclic single-driver netlist).
-inline bool plan_pairs(const Compiled &net, const std::vector<uint32_t> &keep_sorted, PairPlanHost &plan) {
+// keep_all: every row is kept (a plain simulator run, whose wires can all be read back): nothing is dropped, every parent is stored;
+// what remains is half the launches and the children's operand in registers.
+inline bool plan_pairs(const Compiled &net, const std::vector<uint32_t> &keep_sorted, PairPlanHost &plan, bool keep_all = false) {
     const uint32_t G = net.n_g2(), n_src = net.n_src;
     if (net.cyclic || net.multi_driver || net.has_tristate || net.has_state || net.n_g3() || net.n_wide() || net.n_res() || G == 0)
         return false;
@@ -89,7 +91,7 @@ inline bool plan_pairs(const Compiled &net, const std::vector<uint32_t> &keep_so
             }
         }
     }
-    auto kept = [&](uint32_t g) { return std::binary_search(keep_sorted.begin(), keep_sorted.end(), n_src + g); };
+    auto kept = [&](uint32_t g) { return keep_all || std::binary_search(keep_sorted.begin(), keep_sorted.end(), n_src + g); };
     // items in launch order (counting sort of the parents; gate order inside a launch)
     std::vector<uint32_t> count(n_launch + 1, 0), dcount(n_launch + 1, 0);
     for (uint32_t g = 0; g < G; g++)

@@ -72,8 +72,13 @@ int main(int argc, char **argv) {
         std::vector<uint32_t> keep;
         for (uint32_t r = n_src; r < c.n_rows; r++)
             if (rnd(10) == 0) keep.push_back(r);
+        for (int keep_all = 0; keep_all < 2; keep_all++) {
         PairPlanHost plan;
-        REQUIRE(plan_pairs(c, keep, plan));
+        REQUIRE(plan_pairs(c, keep, plan, keep_all != 0));
+        if (keep_all) {
+            REQUIRE(plan.n_unstored == 0 && plan.disc_rows.empty());
+            for (const PairItem &it : plan.items) REQUIRE((it.meta & PM_STORE_P) && !(it.meta & (PM_NOW_P | PM_NOW_C1 | PM_NOW_C2)));
+        }
         // plain evaluation
         std::vector<S4> ref(c.n_rows), st(c.n_rows, S4{0, 0});
         for (uint32_t r = 0; r < n_src; r++) ref[r] = st[r] = S4{rng(), rng() | rng()};
@@ -130,9 +135,14 @@ int main(int argc, char **argv) {
         for (uint32_t r = n_src; r < c.n_rows; r++)
             if (written[r] >= 0) REQUIRE(st[r].v == ref[r].v && st[r].m == ref[r].m);
         REQUIRE(plan.launches.size() <= c.depth);
-        total_children += plan.n_children;
-        total_unstored += plan.n_unstored;
-        total_gates += G;
+        if (keep_all)
+            for (uint32_t r = n_src; r < c.n_rows; r++) REQUIRE(written[r] >= 0);   // a plain run can read every wire back
+        if (!keep_all) {
+            total_children += plan.n_children;
+            total_unstored += plan.n_unstored;
+            total_gates += G;
+        }
+        }
     }
     REQUIRE(total_children > total_gates / 5);
     std::printf("pair_plan_check ok (%d rounds, %llu gates, %llu as children, %llu rows never stored)\n", rounds,

@@ -107,17 +107,22 @@ def test_netlists_with_other_gate_classes_keep_the_per_level_kernels():
     assert (ov == rv[outputs]).all() and (om == rm[outputs]).all()
 
 
-def test_plain_simulator_runs_never_use_it():
-    """b2_run_sim_lanes keeps every row: the fusion only acts where rows need not survive their last reader."""
+@pytest.mark.parametrize("pair", [2, 1, 0])
+def test_plain_simulator_runs_keep_every_row(pair):
+    """b2_run_sim_lanes must leave every wire readable: the launches are fused (half as many), but every parent row is stored
+    and nothing is dropped."""
     gen = netgen.random_dag(n_gates=4000, depth=10, n_inputs=32, n_outputs=16, seed=3)
     sim = gen.emit(d.SimulatorBuilder()).build()
+    sim.set_option(sim.OPT_PAIR_FUSION, pair)
     sim.set_lanes(64 * 32)
-    sim.fill_stimulus(gen.inputs, 1, 0, 1)
-    assert sim.run_sim_lanes(100)[0] == SimulationRunResult.Ok
-    assert sim.pair_info == (0, 0, 0)
     rv, rm = _oracle_rows(gen, gen.n_wires, gen.inputs, 32, 1, 0, 1)
-    gv, gm = sim.gather_wires_host(np.arange(gen.n_wires, dtype=np.uint32))
-    assert (gv == rv).all() and (gm == rm).all()
+    for _ in range(2):                                   # the second run replays the captured graph
+        sim.fill_stimulus(gen.inputs, 1, 0, 1)
+        assert sim.run_sim_lanes(100)[0] == SimulationRunResult.Ok and sim.info.last_mode == 1
+        launches, children, unstored = sim.pair_info
+        assert unstored == 0 and (launches > 0) == (pair != 0) and (children > 0) == (pair != 0)
+        gv, gm = sim.gather_wires_host(np.arange(gen.n_wires, dtype=np.uint32))
+        assert (gv == rv).all() and (gm == rm).all()
 
 
 @pytest.mark.parametrize("pair", [1, 0])
